@@ -1,0 +1,97 @@
+"""Import the reference's own parser, unmodified, for pinning the oracle.  TEST INFRASTRUCTURE.
+
+Works only where ``/root/reference`` exists (the build container — never the GPU box).  The
+reference's ``datatest.py`` imports plotting / augmentation packages at module level that
+this image does not have (datatest.py:11-14,24,37-38 and, through ``dataset.py``/``aug.py``/
+``eval_helpers.py``, skimage, imgaug, shapely); none of them is touched by the parser
+functions, so empty stand-in modules are registered for them before the import.  Nothing is
+copied: the functions executed are the reference's files where they lie.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.machinery
+import os
+import sys
+import types
+
+REFERENCE_DIR = os.environ.get("PPN_REFERENCE_DIR", "/root/reference")
+
+_MISSING = [
+    "skimage", "skimage.io", "skimage.transform", "skimage.color",
+    "matplotlib", "matplotlib.pyplot", "matplotlib.patches",
+    "imgaug", "imgaug.augmenters", "torchsummary", "shapely", "shapely.geometry",
+]
+
+
+class _Absent(types.ModuleType):
+    """A module whose every attribute is another such module and which can be called."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        child = _Absent(f"{self.__name__}.{name}")
+        setattr(self, name, child)
+        return child
+
+    def __call__(self, *args, **kwargs):
+        return None
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "datatest.py"))
+
+
+_datatest = None
+
+
+def load():
+    """Return the reference's ``datatest`` module (cached)."""
+    global _datatest
+    if _datatest is not None:
+        return _datatest
+    if not available():
+        raise RuntimeError(f"reference not present at {REFERENCE_DIR}")
+    for name in _MISSING:
+        try:
+            importlib.import_module(name)
+        except Exception:
+            mod = _Absent(name)
+            mod.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            mod.__path__ = []
+            sys.modules[name] = mod
+    if REFERENCE_DIR not in sys.path:
+        sys.path.insert(0, REFERENCE_DIR)
+    # the reference's flat module names ('config', 'utils', 'dataset', 'aug') must resolve
+    # to ITS files; drop same-named modules imported from elsewhere first
+    for flat in ("config", "utils", "dataset", "aug", "datatest", "eval_helpers", "evaluateAP"):
+        m = sys.modules.get(flat)
+        if m is not None and not str(getattr(m, "__file__", "")).startswith(REFERENCE_DIR):
+            del sys.modules[flat]
+    import logging
+    level = logging.getLogger().level
+    _datatest = importlib.import_module("datatest")
+    logging.getLogger().setLevel(max(level, logging.WARNING))
+    return _datatest
+
+
+def configure(g):
+    """Patch the module globals the reference's functions read (datatest.py:53-60) and its
+    star-imported DIRECTED_GRAPHS (config.py:75-80) to the geometry ``g`` (oracle Geometry)."""
+    dt = load()
+    dt.insize = (g.inW, g.inH)
+    dt.outsize = (g.W, g.H)
+    dt.local_grid_size = (g.sW, g.sH)
+    dt.gridsize = (int(g.inW / g.W), int(g.inH / g.H))
+    dt.DIRECTED_GRAPHS = [[list(eis), list(ts)] for eis, ts in g.graphs]
+    return dt
+
+
+def reference_parse(out, g):
+    """Run rt_test.py:109-133's host steps and the reference parser on one image [C,H,W]."""
+    dt = configure(g)
+    K = g.K
+    resp, conf, x, y, w, h = (out[i * K:(i + 1) * K] for i in range(6))
+    e = out[6 * K:].reshape(g.E, g.sH, g.sW, g.H, g.W)
+    return dt.get_humans_by_feature(resp * conf, x, y, w, h, e,
+                                    detection_thresh=g.det_thresh, min_num_keypoints=g.min_kp)
