@@ -1,0 +1,168 @@
+/*
+ * libppn_decode — C ABI of the B200 (sm_100a) Pose Proposal Network output parser.
+ *
+ * The reference (noirmist/Pytorch_Pose_Proposal_Network) has no FFI or plugin layer: its
+ * "operator API" for this path is four module-level Python functions plus the head-tensor
+ * layout.  Each entry point below names the reference interface it stands in for
+ * (paths under /root/reference):
+ *
+ *   ppn_limb_argmax ........ the np.argmax of every limb window, datatest.py:100,113
+ *   ppn_decode_candidates .. resp*conf, restore_xy/restore_size, box assembly and
+ *                            np.where(score > thresh): rt_test.py:130, datatest.py:63-71,80-92
+ *   ppn_restore_xy/_size ... restore_xy(x, y) / restore_size(w, h), datatest.py:63-71
+ *   ppn_nms ................ non_maximum_suppression(bbox, thresh, score, limit), datatest.py:134-160
+ *   ppn_tree_parse ......... the per-root walk of get_humans_by_feature, datatest.py:103-131
+ *   ppn_parse .............. get_humans_by_feature end to end on a device batch: what
+ *                            rt_test.py:109-133 / main.py:946-972 do per image after model(image)
+ *   ppn_parse_host ......... the same from host memory (the reference's numpy arrays), with the
+ *                            copies the reference's `.cpu()` calls stand for done here in reverse
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; no CUDA or torch types.  `stream` is a cudaStream_t
+ *     passed as void* (NULL = the legacy default stream).
+ *   - every function returns int: 0 = ok, > 0 = a cudaError_t value, < 0 = a PPN_E_* code;
+ *     ppn_strerror() turns either into text.  Nothing throws across the boundary.
+ *   - device entry points only ENQUEUE work on `stream`; they never synchronise and never
+ *     allocate.  The caller owns every buffer (torch tensors in the Python host layer) and
+ *     selects the device (cudaSetDevice / torch.cuda.set_device) before calling.
+ *   - thread-safe for distinct streams and buffers; no global mutable state except the
+ *     tuning table set by ppn_tune() (meant for benchmarking, set once before use).
+ *   - head tensor: fp32, NCHW contiguous [B, 6K + sH*sW*E, H, W]; channel groups resp, conf,
+ *     x, y, w, h (K each) then the limb block viewed as [E, sH, sW, H, W] (model.py:64,
+ *     rt_test.py:109-120).  16-byte aligned base.
+ *   - cells are flat indices h*W + w; boxes are (ymin, xmin, ymax, xmax) in pixels.
+ *   - all floating-point results are bit-identical to numpy's fp32 evaluation of the
+ *     reference's expressions (single rounding per operation, no FMA contraction).
+ */
+#ifndef PPN_DECODE_H_
+#define PPN_DECODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPN_ABI_VERSION 1
+
+/* library error codes (negative); positive return values are cudaError_t */
+#define PPN_OK               0
+#define PPN_E_BADARG        -1   /* NULL pointer, non-positive size, misaligned base            */
+#define PPN_E_UNSUPPORTED   -2   /* shape outside what the kernels handle (see ppn_limits)      */
+#define PPN_E_WORKSPACE     -3   /* workspace smaller than ppn_workspace_bytes()                */
+#define PPN_E_CHAINS        -4   /* track orders too long / indexes outside K or E              */
+#define PPN_E_NO_DEVICE     -5   /* no CUDA device, or not an sm_100 class device               */
+
+#define PPN_MAX_CHAINS       32  /* track orders (config.py:67-73 has 5)                        */
+#define PPN_MAX_CHAIN_STEPS 192  /* total limb steps over all track orders (reference: 25)      */
+#define PPN_MAX_CELLS      1024  /* H*W handled by the in-shared-memory NMS and parse kernels   */
+
+/* Geometry of one head tensor.  Mirrors the module globals of datatest.py:53-60 and the
+ * attributes of PoseProposalNet (model.py:54-64). */
+typedef struct PPNShape {
+    int32_t B;              /* images in the batch                                              */
+    int32_t K, E;           /* parts (incl. 'instance' = part 0), limbs                          */
+    int32_t H, W;           /* grid: outH, outW                                                  */
+    int32_t sH, sW;         /* limb displacement window                                          */
+    int32_t inW, inH;       /* network input size in pixels                                      */
+    int32_t gridW, gridH;   /* int(inW/outW), int(inH/outH)  (datatest.py:60)                    */
+    int32_t off_h, off_w;   /* half-windows subtracted from row / column (datatest.py:115-116)   */
+} PPNShape;
+
+/* Thresholds and the track orders (config.py:67-80 DIRECTED_GRAPHS, flattened).  The three
+ * chain arrays are HOST pointers; they are copied into kernel arguments at launch. */
+typedef struct PPNParams {
+    float   det_thresh;         /* 0.15 at rt_test.py:133; root: delta > thr, limb target: delta >= thr */
+    float   nms_thresh;         /* 0.3 at datatest.py:94; IoU >= thr suppresses                  */
+    int32_t min_num_keypoints;  /* datatest.py:74,129                                            */
+    int32_t n_nms_parts;        /* parts 0..n-1 get a compacted candidate list and NMS; the
+                                   reference uses only part 0 (datatest.py:86-94) => 1           */
+    int32_t n_chains;
+    const int32_t* chain_off;   /* [n_chains + 1]                                                */
+    const int32_t* chain_limb;  /* [chain_off[n_chains]] limb index of each step  ("eis")        */
+    const int32_t* chain_part;  /* [chain_off[n_chains]] target part of each step ("ts")         */
+} PPNParams;
+
+/* Packed result, device memory owned by the caller.  Humans of image b occupy slots
+ * [0, min(count[b], R)) in descending root-score (NMS) order, as the reference's list is. */
+typedef struct PPNHumans {
+    int32_t* count;        /* [B]        humans found (may exceed R: only the first R are stored) */
+    int32_t* root_cell;    /* [B, R]                                                             */
+    int32_t* part_cell;    /* [B, R, K]  cell of part k, -1 = absent; part 0 = root               */
+    float*   part_score;   /* [B, R, K]  delta at that cell (0 where absent)                      */
+    float*   part_box;     /* [B, R, K, 4] (ymin, xmin, ymax, xmax) (0 where absent)              */
+    int32_t  R;            /* slots per image; H*W can never overflow                             */
+} PPNHumans;
+
+int         ppn_abi_version(void);
+const char* ppn_strerror(int code);
+
+/* Bytes of scratch ppn_parse needs for this shape (arg-max map, candidate lists, NMS lists). */
+int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* bytes);
+
+/* Number of kernel launches one ppn_parse call enqueues for this shape. */
+int ppn_parse_launches(const PPNShape* shape, const PPNParams* params);
+
+/* amax[B, E, H*W] (uint16) = index in [0, sH*sW) of the FIRST maximum of each limb window;
+ * NaN counts as the maximum (numpy argmax).  Streams the limb block once. */
+int ppn_limb_argmax(const float* head, const PPNShape* shape, uint16_t* amax, void* stream);
+
+/* For parts 0..n_parts-1 of every image: cells with resp*conf > det_thresh in ascending cell
+ * order, with score and box.  Lists are [B, n_parts, H*W]; cand_count is [B, n_parts]. */
+int ppn_decode_candidates(const float* head, const PPNShape* shape, int32_t n_parts, float det_thresh,
+                          int32_t* cand_cell, float* cand_score, float* cand_box, int32_t* cand_count,
+                          void* stream);
+
+/* restore_xy(x, y) and restore_size(w, h) of datatest.py:63-71 as operators over n_planes
+ * contiguous [H, W] planes: rx = (x + col) * gridW, ry = (y + row) * gridH; rw = inW*w, rh = inH*h. */
+int ppn_restore_xy(const float* x, const float* y, float* rx, float* ry, int64_t n_planes,
+                   const PPNShape* shape, void* stream);
+int ppn_restore_size(const float* w, const float* h, float* rw, float* rh, int64_t n_planes,
+                     const PPNShape* shape, void* stream);
+
+/* Greedy IoU suppression of n_problems independent box lists laid out with `stride` slots
+ * each: box [n_problems, stride, 4], score [n_problems, stride] or NULL (keep input order),
+ * count [n_problems] (device).  keep_idx [n_problems, stride] receives indices into each list
+ * in visiting order (descending score; equal scores: larger index first), keep_count
+ * [n_problems] how many.  limit <= 0 means no limit.  stride <= PPN_MAX_CELLS uses the
+ * shared-memory kernel; larger lists take a slower global-memory kernel. */
+int ppn_nms(const float* box, const float* score, const int32_t* count, int32_t n_problems,
+            int32_t stride, float nms_thresh, int32_t limit,
+            int32_t* keep_idx, int32_t* keep_count, void* stream);
+
+/* Walk the track orders from every surviving root of part 0.  cand_cell/keep_idx/keep_count
+ * are the outputs of the two calls above with the given n_parts. */
+int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* params,
+                   const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
+                   const int32_t* keep_count, const PPNHumans* out, void* stream);
+
+/* The whole path on a device batch: limb arg-max, decode, NMS, tree parse. */
+int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
+              const PPNHumans* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The whole path from HOST memory (pinned for full speed): uploads `head` in chunks
+ * overlapped with the kernels, runs ppn_parse, downloads the packed result into the HOST
+ * arrays of `out_host`.  Synchronous.  dev_scratch/dev_scratch_bytes: device memory of at
+ * least ppn_parse_host_scratch_bytes(). */
+int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params, int32_t R, size_t* bytes);
+int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParams* params,
+                   const PPNHumans* out_host, void* dev_scratch, size_t dev_scratch_bytes);
+
+/* Per-stage timing of ppn_parse for benchmarks.  After ppn_profile_enable(1) every ppn_parse
+ * call (up to 4096) records CUDA events on its stream at the stage boundaries;
+ * ppn_profile_read() waits for them and returns the summed milliseconds of the four stages
+ * {limb arg-max, decode, NMS, tree parse} and the number of calls covered, then resets. */
+int ppn_profile_enable(int32_t on);
+int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
+
+/* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
+ * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
+ * "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
+int ppn_tune(const char* key, int32_t value);
+int ppn_tune_get(const char* key, int32_t* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPN_DECODE_H_ */

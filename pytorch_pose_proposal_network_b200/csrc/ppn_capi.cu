@@ -1,0 +1,413 @@
+// C ABI of libppn_decode (declared in include/ppn_decode.h): argument checking, workspace
+// carving, the 4-kernel pipeline, and the host-memory entry with overlapped copies.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "ppn_decode.h"
+#include "ppn_kernels.h"
+
+namespace {
+
+ppn::Tuning g_tuning;
+
+// ---- optional per-stage timing of ppn_parse (ppn_profile_*) --------------------------------
+// When enabled, ppn_parse records CUDA events at its five stage boundaries on the caller's
+// stream; ppn_profile_read() sums the elapsed times.  Used by bench.py to time the dominant
+// kernel inside the timed region.  Not thread-safe: enable it from one thread.
+constexpr int kStages = 4;
+constexpr int kMaxProfiled = 4096;
+struct Profile {
+    bool on = false;
+    int used = 0;
+    cudaEvent_t* ev = nullptr;          // [kMaxProfiled][kStages + 1]
+} g_prof;
+
+inline cudaEvent_t* profile_slot() {
+    if (!g_prof.on || g_prof.used >= kMaxProfiled) return nullptr;
+    return g_prof.ev + (size_t)(g_prof.used++) * (kStages + 1);
+}
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? PPN_OK : (int)e; }
+
+int check_shape(const PPNShape* s) {
+    if (!s) return PPN_E_BADARG;
+    if (s->B < 0 || s->K < 1 || s->E < 0 || s->H < 1 || s->W < 1 || s->sH < 1 || s->sW < 1) return PPN_E_BADARG;
+    if (s->inW < 1 || s->inH < 1 || s->gridW < 0 || s->gridH < 0) return PPN_E_BADARG;
+    if ((long long)s->sH * s->sW > 65535) return PPN_E_UNSUPPORTED;            // arg-max map is uint16
+    if (s->K > 255 || s->E > 255) return PPN_E_UNSUPPORTED;                    // chain tables are uint8
+    const long long per_img = ((long long)6 * s->K + (long long)s->sH * s->sW * s->E) * s->H * s->W;
+    if (per_img > 0x7fffffffLL) return PPN_E_UNSUPPORTED;
+    return PPN_OK;
+}
+
+ppn::Geom make_geom(const PPNShape* s) {
+    ppn::Geom g;
+    g.B = s->B; g.K = s->K; g.E = s->E; g.H = s->H; g.W = s->W; g.HW = s->H * s->W;
+    g.sH = s->sH; g.sW = s->sW; g.S = s->sH * s->sW; g.C = 6 * s->K + g.S * s->E;
+    g.off_h = s->off_h; g.off_w = s->off_w;
+    g.gridW = (float)s->gridW; g.gridH = (float)s->gridH; g.inW = (float)s->inW; g.inH = (float)s->inH;
+    g.img_stride = (size_t)g.C * g.HW;
+    g.limb_off = (size_t)6 * g.K * g.HW;
+    return g;
+}
+
+int make_chains(const PPNShape* s, const PPNParams* p, ppn::ChainTable* ch) {
+    if (!p) return PPN_E_BADARG;
+    if (p->n_chains < 0 || p->n_chains > PPN_MAX_CHAINS) return PPN_E_CHAINS;
+    if (p->n_chains > 0 && (!p->chain_off || !p->chain_limb || !p->chain_part)) return PPN_E_BADARG;
+    std::memset(ch, 0, sizeof(*ch));
+    ch->n_chains = p->n_chains;
+    if (p->n_chains == 0) return PPN_OK;
+    if (p->chain_off[0] != 0) return PPN_E_CHAINS;
+    for (int c = 0; c < p->n_chains; ++c)
+        if (p->chain_off[c + 1] < p->chain_off[c]) return PPN_E_CHAINS;
+    const int total = p->chain_off[p->n_chains];
+    if (total > PPN_MAX_CHAIN_STEPS) return PPN_E_CHAINS;
+    for (int c = 0; c <= p->n_chains; ++c) ch->off[c] = (uint8_t)p->chain_off[c];
+    for (int q = 0; q < total; ++q) {
+        if (p->chain_limb[q] < 0 || p->chain_limb[q] >= s->E || p->chain_part[q] < 0 || p->chain_part[q] >= s->K)
+            return PPN_E_CHAINS;
+        ch->limb[q] = (uint8_t)p->chain_limb[q];
+        ch->part[q] = (uint8_t)p->chain_part[q];
+    }
+    return PPN_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Workspace layout of ppn_parse, every block 256-byte aligned.
+struct Workspace {
+    size_t amax, cand_cell, cand_score, cand_box, cand_count, keep_idx, keep_count, total;
+};
+
+Workspace carve(const PPNShape* s, int n_parts) {
+    Workspace w;
+    const size_t B = (size_t)s->B, HW = (size_t)s->H * s->W, P = (size_t)n_parts;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t at = off; off = align_up(off + bytes, 256); return at; };
+    w.amax = take(B * s->E * HW * sizeof(uint16_t));
+    w.cand_cell = take(B * P * HW * sizeof(int32_t));
+    w.cand_score = take(B * P * HW * sizeof(float));
+    w.cand_box = take(B * P * HW * 4 * sizeof(float));
+    w.cand_count = take(B * P * sizeof(int32_t));
+    w.keep_idx = take(B * P * HW * sizeof(int32_t));
+    w.keep_count = take(B * P * sizeof(int32_t));
+    w.total = off;
+    return w;
+}
+
+int check_params(const PPNShape* s, const PPNParams* p) {
+    if (!p) return PPN_E_BADARG;
+    if (p->n_nms_parts < 1 || p->n_nms_parts > s->K) return PPN_E_BADARG;
+    return PPN_OK;
+}
+
+int check_humans(const PPNHumans* h) {
+    if (!h || !h->count || !h->root_cell || !h->part_cell || !h->part_score || !h->part_box || h->R < 1) return PPN_E_BADARG;
+    return PPN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ppn_abi_version(void) { return PPN_ABI_VERSION; }
+
+const char* ppn_strerror(int code) {
+    switch (code) {
+        case PPN_OK: return "ok";
+        case PPN_E_BADARG: return "ppn: bad argument (null pointer, non-positive size or misaligned base)";
+        case PPN_E_UNSUPPORTED: return "ppn: shape not supported by the kernels";
+        case PPN_E_WORKSPACE: return "ppn: workspace smaller than ppn_workspace_bytes()";
+        case PPN_E_CHAINS: return "ppn: track orders too long or indexing outside K/E";
+        case PPN_E_NO_DEVICE: return "ppn: no usable CUDA device";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "ppn: unknown error";
+}
+
+int ppn_tune(const char* key, int32_t value) {
+    if (!key) return PPN_E_BADARG;
+    ppn::Tuning& t = g_tuning;
+    if (!std::strcmp(key, "argmax.variant")) t.argmax_variant = value;
+    else if (!std::strcmp(key, "argmax.stage_bytes")) t.argmax_stage_bytes = value < 1024 ? 1024 : value;
+    else if (!std::strcmp(key, "argmax.stages")) t.argmax_stages = value < 2 ? 2 : (value > 32 ? 32 : value);
+    else if (!std::strcmp(key, "argmax.threads")) t.argmax_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
+    else if (!std::strcmp(key, "argmax.ctas_per_sm")) t.argmax_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
+    else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
+    else return PPN_E_BADARG;
+    return PPN_OK;
+}
+
+int ppn_tune_get(const char* key, int32_t* value) {
+    if (!key || !value) return PPN_E_BADARG;
+    const ppn::Tuning& t = g_tuning;
+    if (!std::strcmp(key, "argmax.variant")) *value = t.argmax_variant;
+    else if (!std::strcmp(key, "argmax.stage_bytes")) *value = t.argmax_stage_bytes;
+    else if (!std::strcmp(key, "argmax.stages")) *value = t.argmax_stages;
+    else if (!std::strcmp(key, "argmax.threads")) *value = t.argmax_threads;
+    else if (!std::strcmp(key, "argmax.ctas_per_sm")) *value = t.argmax_ctas_per_sm;
+    else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
+    else return PPN_E_BADARG;
+    return PPN_OK;
+}
+
+int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* bytes) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_params(shape, params))) return rc;
+    if (!bytes) return PPN_E_BADARG;
+    *bytes = carve(shape, params->n_nms_parts).total;
+    return PPN_OK;
+}
+
+int ppn_parse_launches(const PPNShape* shape, const PPNParams* params) {
+    if (check_shape(shape) || check_params(shape, params)) return 0;
+    return shape->B > 0 ? 4 : 0;
+}
+
+int ppn_limb_argmax(const float* head, const PPNShape* shape, uint16_t* amax, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (shape->B == 0 || shape->E == 0) return PPN_OK;
+    if (!head || !amax) return PPN_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(head) & 3) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_limb_argmax(head, amax, make_geom(shape), g_tuning, (cudaStream_t)stream));
+}
+
+int ppn_decode_candidates(const float* head, const PPNShape* shape, int32_t n_parts, float det_thresh,
+                          int32_t* cand_cell, float* cand_score, float* cand_box, int32_t* cand_count, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (n_parts < 1 || n_parts > shape->K) return PPN_E_BADARG;
+    if (shape->B == 0) return PPN_OK;
+    if (!head || !cand_cell || !cand_score || !cand_box || !cand_count) return PPN_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(cand_box) & 15) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_decode_candidates(head, make_geom(shape), n_parts, det_thresh, cand_cell, cand_score,
+                                                 cand_box, cand_count, (cudaStream_t)stream));
+}
+
+int ppn_restore_xy(const float* x, const float* y, float* rx, float* ry, int64_t n_planes, const PPNShape* shape, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (n_planes < 0) return PPN_E_BADARG;
+    if (n_planes == 0) return PPN_OK;
+    if (!x || !y || !rx || !ry) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_restore_xy(x, y, rx, ry, (size_t)n_planes * shape->H * shape->W, shape->H, shape->W,
+                                          (float)shape->gridW, (float)shape->gridH, (cudaStream_t)stream));
+}
+
+int ppn_restore_size(const float* w, const float* h, float* rw, float* rh, int64_t n_planes, const PPNShape* shape, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (n_planes < 0) return PPN_E_BADARG;
+    if (n_planes == 0) return PPN_OK;
+    if (!w || !h || !rw || !rh) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_restore_size(w, h, rw, rh, (size_t)n_planes * shape->H * shape->W, (float)shape->inW,
+                                            (float)shape->inH, (cudaStream_t)stream));
+}
+
+int ppn_nms(const float* box, const float* score, const int32_t* count, int32_t n_problems, int32_t stride,
+            float nms_thresh, int32_t limit, int32_t* keep_idx, int32_t* keep_count, void* stream) {
+    if (n_problems < 0 || stride < 1) return PPN_E_BADARG;
+    if (n_problems == 0) return PPN_OK;
+    if (!box || !count || !keep_idx || !keep_count) return PPN_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(box) & 15) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_nms(box, score, count, n_problems, stride, nms_thresh, limit, keep_idx, keep_count,
+                                   (cudaStream_t)stream));
+}
+
+int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* params, const uint16_t* amax,
+                   const int32_t* cand_cell, const int32_t* keep_idx, const int32_t* keep_count,
+                   const PPNHumans* out, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_params(shape, params))) return rc;
+    if ((rc = check_humans(out))) return rc;
+    ppn::ChainTable ch;
+    if ((rc = make_chains(shape, params, &ch))) return rc;
+    if (shape->B == 0) return PPN_OK;
+    if (!head || !cand_cell || !keep_idx || !keep_count || (!amax && shape->E > 0)) return PPN_E_BADARG;
+    if ((long long)shape->H * shape->W > PPN_MAX_CELLS) return PPN_E_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(out->part_box) & 15) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_tree_parse(head, make_geom(shape), ch, params->det_thresh, params->min_num_keypoints,
+                                          params->n_nms_parts, amax, cand_cell, keep_idx, keep_count, out->count,
+                                          out->root_cell, out->part_cell, out->part_score, out->part_box, out->R,
+                                          (cudaStream_t)stream));
+}
+
+int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+              void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_params(shape, params))) return rc;
+    if ((rc = check_humans(out))) return rc;
+    ppn::ChainTable ch;
+    if ((rc = make_chains(shape, params, &ch))) return rc;
+    if (shape->B == 0) return PPN_OK;
+    if (!head || !workspace) return PPN_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(head) & 3) || (reinterpret_cast<uintptr_t>(workspace) & 255)) return PPN_E_BADARG;
+    if ((long long)shape->H * shape->W > PPN_MAX_CELLS) return PPN_E_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(out->part_box) & 15) return PPN_E_BADARG;
+    const int P = params->n_nms_parts;
+    const Workspace w = carve(shape, P);
+    if (workspace_bytes < w.total) return PPN_E_WORKSPACE;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    uint16_t* amax = reinterpret_cast<uint16_t*>(ws + w.amax);
+    int32_t* cand_cell = reinterpret_cast<int32_t*>(ws + w.cand_cell);
+    float* cand_score = reinterpret_cast<float*>(ws + w.cand_score);
+    float* cand_box = reinterpret_cast<float*>(ws + w.cand_box);
+    int32_t* cand_count = reinterpret_cast<int32_t*>(ws + w.cand_count);
+    int32_t* keep_idx = reinterpret_cast<int32_t*>(ws + w.keep_idx);
+    int32_t* keep_count = reinterpret_cast<int32_t*>(ws + w.keep_count);
+    const ppn::Geom g = make_geom(shape);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    cudaEvent_t* ev = profile_slot();
+    if (ev) cudaEventRecord(ev[0], st);
+    if ((e = ppn::launch_limb_argmax(head, amax, g, g_tuning, st)) != cudaSuccess) return (int)e;
+    if (ev) cudaEventRecord(ev[1], st);
+    if ((e = ppn::launch_decode_candidates(head, g, P, params->det_thresh, cand_cell, cand_score, cand_box, cand_count, st)) != cudaSuccess) return (int)e;
+    if (ev) cudaEventRecord(ev[2], st);
+    if ((e = ppn::launch_nms(cand_box, cand_score, cand_count, g.B * P, g.HW, params->nms_thresh, 0, keep_idx, keep_count, st)) != cudaSuccess) return (int)e;
+    if (ev) cudaEventRecord(ev[3], st);
+    if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, cand_cell, keep_idx,
+                                    keep_count, out->count, out->root_cell, out->part_cell, out->part_score, out->part_box,
+                                    out->R, st)) != cudaSuccess) return (int)e;
+    if (ev) cudaEventRecord(ev[4], st);
+    return PPN_OK;
+}
+
+int ppn_profile_enable(int32_t on) {
+    if (on && !g_prof.ev) {
+        g_prof.ev = new cudaEvent_t[(size_t)kMaxProfiled * (kStages + 1)];
+        for (size_t i = 0; i < (size_t)kMaxProfiled * (kStages + 1); ++i) {
+            cudaError_t e = cudaEventCreate(&g_prof.ev[i]);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+    return PPN_OK;
+}
+
+int ppn_profile_read(float* stage_ms, int32_t* n_calls) {
+    if (!stage_ms || !n_calls) return PPN_E_BADARG;
+    for (int s = 0; s < kStages; ++s) stage_ms[s] = 0.0f;
+    *n_calls = g_prof.used;
+    for (int c = 0; c < g_prof.used; ++c) {
+        cudaEvent_t* ev = g_prof.ev + (size_t)c * (kStages + 1);
+        cudaError_t e = cudaEventSynchronize(ev[kStages]);
+        if (e != cudaSuccess) return (int)e;
+        for (int s = 0; s < kStages; ++s) {
+            float ms = 0.0f;
+            if ((e = cudaEventElapsedTime(&ms, ev[s], ev[s + 1])) != cudaSuccess) return (int)e;
+            stage_ms[s] += ms;
+        }
+    }
+    g_prof.used = 0;
+    return PPN_OK;
+}
+
+// ---- host-memory entry --------------------------------------------------------------------
+// Device scratch layout: [head chunk A][head chunk B][workspace A][workspace B][packed result B*R].
+namespace {
+struct HostPlan {
+    int chunk;                 // images per chunk
+    size_t head_bytes;         // per chunk buffer
+    size_t ws_bytes;           // per chunk workspace
+    size_t off_head[2], off_ws[2], off_count, off_root, off_cell, off_score, off_box, total;
+};
+HostPlan plan_host(const PPNShape* s, const PPNParams* p, int R) {
+    HostPlan h;
+    h.chunk = g_tuning.host_chunk_images;
+    if (h.chunk > s->B) h.chunk = s->B > 0 ? s->B : 1;
+    PPNShape cs = *s;
+    cs.B = h.chunk;
+    const size_t per_img = ((size_t)6 * s->K + (size_t)s->sH * s->sW * s->E) * s->H * s->W * sizeof(float);
+    h.head_bytes = align_up(per_img * h.chunk, 256);
+    h.ws_bytes = carve(&cs, p->n_nms_parts).total;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t at = off; off = align_up(off + bytes, 256); return at; };
+    h.off_head[0] = take(h.head_bytes); h.off_head[1] = take(h.head_bytes);
+    h.off_ws[0] = take(h.ws_bytes); h.off_ws[1] = take(h.ws_bytes);
+    const size_t B = (size_t)s->B, K = (size_t)s->K;
+    h.off_count = take(B * sizeof(int32_t));
+    h.off_root = take(B * R * sizeof(int32_t));
+    h.off_cell = take(B * R * K * sizeof(int32_t));
+    h.off_score = take(B * R * K * sizeof(float));
+    h.off_box = take(B * R * K * 4 * sizeof(float));
+    h.total = off;
+    return h;
+}
+}  // namespace
+
+int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params, int32_t R, size_t* bytes) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_params(shape, params))) return rc;
+    if (!bytes || R < 1) return PPN_E_BADARG;
+    *bytes = plan_host(shape, params, R).total;
+    return PPN_OK;
+}
+
+int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParams* params, const PPNHumans* out_host,
+                   void* dev_scratch, size_t dev_scratch_bytes) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_params(shape, params))) return rc;
+    if ((rc = check_humans(out_host))) return rc;
+    if (shape->B == 0) return PPN_OK;
+    if (!head_host || !dev_scratch || (reinterpret_cast<uintptr_t>(dev_scratch) & 255)) return PPN_E_BADARG;
+    const int R = out_host->R;
+    const HostPlan h = plan_host(shape, params, R);
+    if (dev_scratch_bytes < h.total) return PPN_E_WORKSPACE;
+    unsigned char* d = static_cast<unsigned char*>(dev_scratch);
+    const size_t K = (size_t)shape->K;
+    const size_t per_img_f = ((size_t)6 * shape->K + (size_t)shape->sH * shape->sW * shape->E) * shape->H * shape->W;
+
+    // two streams ping-pong over two (head, workspace) buffer pairs: the upload of chunk i+1
+    // overlaps the kernels of chunk i; created once per thread and kept.
+    static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaError_t e;
+    for (int i = 0; i < 2; ++i)
+        if (!streams[i] && (e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+
+    int32_t* d_count = reinterpret_cast<int32_t*>(d + h.off_count);
+    int32_t* d_root = reinterpret_cast<int32_t*>(d + h.off_root);
+    int32_t* d_cell = reinterpret_cast<int32_t*>(d + h.off_cell);
+    float* d_score = reinterpret_cast<float*>(d + h.off_score);
+    float* d_box = reinterpret_cast<float*>(d + h.off_box);
+
+    int slot = 0;
+    for (int b0 = 0; b0 < shape->B; b0 += h.chunk, slot ^= 1) {
+        const int nb = (shape->B - b0 < h.chunk) ? shape->B - b0 : h.chunk;
+        cudaStream_t st = streams[slot];
+        float* d_head = reinterpret_cast<float*>(d + h.off_head[slot]);
+        if ((e = cudaMemcpyAsync(d_head, head_host + (size_t)b0 * per_img_f, (size_t)nb * per_img_f * sizeof(float),
+                                 cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+        PPNShape cs = *shape;
+        cs.B = nb;
+        PPNHumans dev_out;
+        dev_out.count = d_count + b0;
+        dev_out.root_cell = d_root + (size_t)b0 * R;
+        dev_out.part_cell = d_cell + (size_t)b0 * R * K;
+        dev_out.part_score = d_score + (size_t)b0 * R * K;
+        dev_out.part_box = d_box + (size_t)b0 * R * K * 4;
+        dev_out.R = R;
+        if ((rc = ppn_parse(d_head, &cs, params, &dev_out, d + h.off_ws[slot], h.ws_bytes, st))) return rc;
+        // results of this chunk go home on the same stream, behind its kernels
+        if ((e = cudaMemcpyAsync(out_host->count + b0, dev_out.count, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(out_host->root_cell + (size_t)b0 * R, dev_out.root_cell, (size_t)nb * R * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(out_host->part_cell + (size_t)b0 * R * K, dev_out.part_cell, (size_t)nb * R * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(out_host->part_score + (size_t)b0 * R * K, dev_out.part_score, (size_t)nb * R * K * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemcpyAsync(out_host->part_box + (size_t)b0 * R * K * 4, dev_out.part_box, (size_t)nb * R * K * 4 * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+    }
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamSynchronize(streams[i])) != cudaSuccess) return (int)e;
+    return PPN_OK;
+}
+
+}  // extern "C"

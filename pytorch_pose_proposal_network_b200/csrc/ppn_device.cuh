@@ -1,0 +1,130 @@
+// Device-side helpers shared by the PPN parser kernels (sm_100a).
+//
+// Exact arithmetic: every fp32 operation that the reference evaluates in numpy is written
+// with the __f*_rn intrinsics, which round once and are never contracted into FMAs, so the
+// results are bit-identical to numpy's regardless of compiler flags.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ppn {
+
+// Track orders (config.py:67-80) carried by value in kernel arguments.
+struct ChainTable {
+    int32_t n_chains;
+    uint8_t off[33];        // PPN_MAX_CHAINS + 1
+    uint8_t limb[192];      // PPN_MAX_CHAIN_STEPS
+    uint8_t part[192];
+};
+
+struct Geom {               // per-launch constants derived from PPNShape
+    int32_t B, K, E, H, W, HW, sH, sW, S, C;
+    int32_t off_h, off_w;
+    float gridW, gridH, inW, inH;
+    size_t img_stride;      // C*HW floats
+    size_t limb_off;        // 6*K*HW floats
+};
+
+// ---- the reference's cell arithmetic --------------------------------------------------
+// delta = resp * conf  (rt_test.py:130)
+__device__ __forceinline__ float delta_at(const float* __restrict__ img, const Geom& g, int k, int c) {
+    return __fmul_rn(__ldg(img + (size_t)k * g.HW + c), __ldg(img + (size_t)(g.K + k) * g.HW + c));
+}
+
+// (ymin, xmin, ymax, xmax) of part k at cell c  (datatest.py:63-71, 80-85)
+__device__ __forceinline__ float4 box_at(const float* __restrict__ img, const Geom& g, int k, int c) {
+    const int h = c / g.W, w = c - h * g.W;
+    const size_t HW = g.HW;
+    const float x = __ldg(img + (size_t)(2 * g.K + k) * HW + c);
+    const float y = __ldg(img + (size_t)(3 * g.K + k) * HW + c);
+    const float bw = __ldg(img + (size_t)(4 * g.K + k) * HW + c);
+    const float bh = __ldg(img + (size_t)(5 * g.K + k) * HW + c);
+    const float rx = __fmul_rn(__fadd_rn(x, (float)w), g.gridW);
+    const float ry = __fmul_rn(__fadd_rn(y, (float)h), g.gridH);
+    const float hw = __fmul_rn(__fmul_rn(g.inW, bw), 0.5f);     // rw / 2 (exact halving)
+    const float hh = __fmul_rn(__fmul_rn(g.inH, bh), 0.5f);
+    return make_float4(__fsub_rn(ry, hh), __fsub_rn(rx, hw), __fadd_rn(ry, hh), __fadd_rn(rx, hw));
+}
+
+// numpy's maximum / minimum: propagate NaN (datatest.py:145-146)
+__device__ __forceinline__ float np_max(float a, float b) { return (a >= b || a != a) ? a : b; }
+__device__ __forceinline__ float np_min(float a, float b) { return (a <= b || a != a) ? a : b; }
+
+// IoU >= thr of a tested box against an already kept one  (datatest.py:145-150)
+__device__ __forceinline__ bool suppresses(const float4 tested, float area_tested,
+                                           const float4 kept, float area_kept, float thr) {
+    const float tly = np_max(tested.x, kept.x), tlx = np_max(tested.y, kept.y);
+    const float bry = np_min(tested.z, kept.z), brx = np_min(tested.w, kept.w);
+    const float prod = __fmul_rn(__fsub_rn(bry, tly), __fsub_rn(brx, tlx));
+    const float inter = __fmul_rn(prod, (tly < bry && tlx < brx) ? 1.0f : 0.0f);
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_tested, area_kept), inter));
+    return iou >= thr;      // NaN compares false: not suppressed
+}
+
+__device__ __forceinline__ float box_area(const float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));   // datatest.py:141
+}
+
+// ---- numpy argmax semantics -------------------------------------------------------------
+// Sequential rule: a later element replaces the running best iff !(v <= best) and best is not
+// NaN (first maximum wins; the first NaN wins and ends the scan).
+__device__ __forceinline__ void argmax_step(float& best, int& idx, float v, int a) {
+    const bool take = !(v <= best) && (best == best);
+    best = take ? v : best;
+    idx = take ? a : idx;
+}
+
+// Merge of two partial results over disjoint index sets: does (v2, i2) beat (v1, i1)?
+__device__ __forceinline__ bool argmax_beats(float v2, int i2, float v1, int i1) {
+    const bool n1 = v1 != v1, n2 = v2 != v2;
+    if (n1 || n2) return n2 && (!n1 || i2 < i1);
+    return v2 > v1 || (v2 == v1 && i2 < i1);
+}
+
+// ---- mbarrier / bulk-copy (TMA) PTX ----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PPN_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PPN_DONE;\n"
+        "bra PPN_WAIT;\n"
+        "PPN_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier; evict-first in
+// L2 because the limb block is read exactly once.  bytes % 16 == 0, both addresses 16 B aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    const uint64_t evict_first = 0x12F0000000000000ull;
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(evict_first) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+// streaming 128-bit load that does not allocate in L1
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+}  // namespace ppn

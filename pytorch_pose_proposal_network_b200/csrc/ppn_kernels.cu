@@ -1,0 +1,660 @@
+// The four kernels of the PPN output parser, hand-written for sm_100a (B200).
+//
+//   K3 limb_argmax_*      streams the limb block once and keeps the arg-max of every window
+//                         (>= 92 % of all bytes; HBM-bound)           datatest.py:100,113
+//   K1 decode_candidates  resp*conf, threshold, ordered compaction, box  datatest.py:63-92
+//   K2 nms_*              greedy IoU suppression per box list           datatest.py:134-160
+//   K4 tree_parse         walk the track orders from every kept root    datatest.py:103-131
+//
+// Launchers at the bottom are called by ppn_capi.cu.
+#include "ppn_kernels.h"
+
+namespace ppn {
+
+// =========================================================================================
+// K3 — limb window arg-max
+// =========================================================================================
+// One (image, limb) "matrix" is S rows (window positions) by HW columns (cells), contiguous in
+// the head tensor, and the answer is the column-wise arg-max.  Rows are contiguous, so any run
+// of rows is one contiguous byte range: the producer thread moves such runs into a
+// shared-memory ring with 1-D bulk copies (TMA engine, completion on an mbarrier), and the
+// consumer threads reduce them from shared memory.  Thread (g, cv) owns float4 column cv and
+// every G-th row of each chunk; the G partial results per column are merged once per matrix.
+// Persistent: grid = SM count x ctas_per_sm, matrices are dealt round-robin.
+
+struct Partial { float v; int32_t i; };
+
+__global__ void __launch_bounds__(1024, 1)
+limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* ring = smem;
+    Partial* part = reinterpret_cast<Partial*>(smem + (size_t)p.stages * p.stage_bytes);   // [2][G][HW]
+    uint64_t* full = reinterpret_cast<uint64_t*>(part + (size_t)2 * p.G * g.HW);
+    uint64_t* empty = full + p.stages;
+
+    const int tid = threadIdx.x;
+    const int n_cons = p.threads_padded;                 // consumer threads incl. idle lanes of the last warp
+    const int n_mats = g.B * g.E;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], n_cons / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= n_cons) {
+        // ---------------- producer: one thread feeds the ring ----------------
+        if (tid == n_cons) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int m = blockIdx.x; m < n_mats; m += gridDim.x) {
+                const int b = m / g.E, ei = m - b * g.E;
+                const float* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
+                for (int c = 0; c < p.chunks; ++c) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    const int rows = min(p.rows, g.S - c * p.rows);
+                    const uint32_t bytes = (uint32_t)rows * g.HW * 4u;
+                    mbar_arrive_expect_tx(&full[stage], bytes);
+                    bulk_g2s(ring + (size_t)stage * p.stage_bytes, src + (size_t)c * p.rows * g.HW, bytes, &full[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const bool active = tid < p.threads;
+    const int grp = tid / p.CV, cv = tid - grp * p.CV;
+    const int lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int m = blockIdx.x; m < n_mats; m += gridDim.x, ++it) {
+        float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+        int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+        for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait(&full[stage], phase);
+            if (active) {
+                const int rows = min(p.rows, g.S - c * p.rows);
+                const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes) + cv;
+                int a = c * p.rows + grp;
+                int r = grp;
+#pragma unroll 1
+                for (; r + 3 * p.G < rows; r += 4 * p.G, a += 4 * p.G) {
+                    const float4 v0 = col[(size_t)r * p.CV];
+                    const float4 v1 = col[(size_t)(r + p.G) * p.CV];
+                    const float4 v2 = col[(size_t)(r + 2 * p.G) * p.CV];
+                    const float4 v3 = col[(size_t)(r + 3 * p.G) * p.CV];
+                    argmax_step(b0, i0, v0.x, a); argmax_step(b1, i1, v0.y, a);
+                    argmax_step(b2, i2, v0.z, a); argmax_step(b3, i3, v0.w, a);
+                    argmax_step(b0, i0, v1.x, a + p.G); argmax_step(b1, i1, v1.y, a + p.G);
+                    argmax_step(b2, i2, v1.z, a + p.G); argmax_step(b3, i3, v1.w, a + p.G);
+                    argmax_step(b0, i0, v2.x, a + 2 * p.G); argmax_step(b1, i1, v2.y, a + 2 * p.G);
+                    argmax_step(b2, i2, v2.z, a + 2 * p.G); argmax_step(b3, i3, v2.w, a + 2 * p.G);
+                    argmax_step(b0, i0, v3.x, a + 3 * p.G); argmax_step(b1, i1, v3.y, a + 3 * p.G);
+                    argmax_step(b2, i2, v3.z, a + 3 * p.G); argmax_step(b3, i3, v3.w, a + 3 * p.G);
+                }
+                for (; r < rows; r += p.G, a += p.G) {
+                    const float4 v = col[(size_t)r * p.CV];
+                    argmax_step(b0, i0, v.x, a); argmax_step(b1, i1, v.y, a);
+                    argmax_step(b2, i2, v.z, a); argmax_step(b3, i3, v.w, a);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        uint16_t* dst = amax + (size_t)m * g.HW;
+        if (p.G == 1) {
+            if (active) {
+                const uint32_t lo = (uint32_t)i0 | ((uint32_t)i1 << 16), hi = (uint32_t)i2 | ((uint32_t)i3 << 16);
+                *reinterpret_cast<uint2*>(dst + 4 * cv) = make_uint2(lo, hi);
+            }
+        } else {
+            Partial* mine = part + (size_t)(it & 1) * p.G * g.HW;
+            if (active) {
+                Partial* row = mine + (size_t)grp * g.HW + 4 * cv;
+                row[0] = Partial{b0, i0}; row[1] = Partial{b1, i1};
+                row[2] = Partial{b2, i2}; row[3] = Partial{b3, i3};
+            }
+            named_bar_sync(1, n_cons);
+            for (int c = tid; c < g.HW; c += n_cons) {
+                Partial best = mine[c];
+                for (int q = 1; q < p.G; ++q) {
+                    const Partial o = mine[(size_t)q * g.HW + c];
+                    if (argmax_beats(o.v, o.i, best.v, best.i)) best = o;
+                }
+                dst[c] = (uint16_t)best.i;
+            }
+            // `part` is double-buffered on the matrix parity, so one barrier per matrix is enough:
+            // a thread can only overwrite buffer (it & 1) two matrices later, after the barrier of
+            // matrix it+1, which every thread reaches only after finishing this merge.
+        }
+    }
+}
+
+// Variant without the ring: one CTA per matrix, 128-bit streaming loads straight to registers.
+// Kept as the measured alternative (ppn_tune "argmax.variant" = 1).
+__global__ void __launch_bounds__(1024, 1)
+limb_argmax_ldg_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Partial* part = reinterpret_cast<Partial*>(smem);                  // [G][HW]
+    const int tid = threadIdx.x;
+    const int m = blockIdx.x;
+    const int b = m / g.E, ei = m - b * g.E;
+    const float4* src = reinterpret_cast<const float4*>(head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW);
+    const bool active = tid < p.threads;
+    const int grp = tid / p.CV, cv = tid - grp * p.CV;
+    float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    if (active) {
+        const float4* col = src + cv;
+        int r = grp;
+        constexpr int U = 8;
+#pragma unroll 1
+        for (; r + (U - 1) * p.G < g.S; r += U * p.G) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ldg_stream(col + (size_t)(r + u * p.G) * p.CV);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int a = r + u * p.G;
+                argmax_step(b0, i0, v[u].x, a); argmax_step(b1, i1, v[u].y, a);
+                argmax_step(b2, i2, v[u].z, a); argmax_step(b3, i3, v[u].w, a);
+            }
+        }
+        for (; r < g.S; r += p.G) {
+            const float4 v = ldg_stream(col + (size_t)r * p.CV);
+            argmax_step(b0, i0, v.x, r); argmax_step(b1, i1, v.y, r);
+            argmax_step(b2, i2, v.z, r); argmax_step(b3, i3, v.w, r);
+        }
+        Partial* row = part + (size_t)grp * g.HW + 4 * cv;
+        row[0] = Partial{b0, i0}; row[1] = Partial{b1, i1};
+        row[2] = Partial{b2, i2}; row[3] = Partial{b3, i3};
+    }
+    __syncthreads();
+    uint16_t* dst = amax + (size_t)m * g.HW;
+    for (int c = tid; c < g.HW; c += blockDim.x) {
+        Partial best = part[c];
+        for (int q = 1; q < p.G; ++q) {
+            const Partial o = part[(size_t)q * g.HW + c];
+            if (argmax_beats(o.v, o.i, best.v, best.i)) best = o;
+        }
+        dst[c] = (uint16_t)best.i;
+    }
+}
+
+// Any shape (H*W not a multiple of 4, huge grids): one thread per column, scalar loads.
+__global__ void __launch_bounds__(256)
+limb_argmax_generic_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g) {
+    const int m = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.HW) return;
+    const int b = m / g.E, ei = m - b * g.E;
+    const float* col = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW + c;
+    float best = -INFINITY;
+    int idx = 0;
+    for (int a = 0; a < g.S; ++a) argmax_step(best, idx, __ldg(col + (size_t)a * g.HW), a);
+    amax[(size_t)m * g.HW + c] = (uint16_t)idx;
+}
+
+// =========================================================================================
+// K1 — decode + ordered compaction of candidates, one CTA per (image, part)
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+decode_candidates_kernel(const float* __restrict__ head, Geom g, int n_parts, float thr,
+                         int32_t* __restrict__ cand_cell, float* __restrict__ cand_score,
+                         float4* __restrict__ cand_box, int32_t* __restrict__ cand_count) {
+    __shared__ int warp_tot[8];
+    __shared__ int base_s;
+    const int b = blockIdx.x, k = blockIdx.y;
+    const float* img = head + (size_t)b * g.img_stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t list = ((size_t)b * n_parts + k) * g.HW;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < g.HW; c0 += blockDim.x) {
+        const int c = c0 + tid;
+        float d = 0.0f;
+        bool hit = false;
+        if (c < g.HW) {
+            d = delta_at(img, g, k, c);
+            hit = d > thr;                                   // strict, datatest.py:89
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s, total = 0;
+        for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) {
+            const int t = warp_tot[wi];
+            if (wi < warp) off += t;
+            total += t;
+        }
+        if (hit) {
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            cand_cell[list + slot] = c;
+            cand_score[list + slot] = d;
+            cand_box[list + slot] = box_at(img, g, k, c);
+        }
+        __syncthreads();
+        if (tid == 0) base_s += total;
+        __syncthreads();
+    }
+    if (tid == 0) cand_count[(size_t)b * n_parts + k] = base_s;
+}
+
+// restore_xy / restore_size as stand-alone operators (datatest.py:63-71) over n_planes [H,W] planes
+__global__ void __launch_bounds__(256)
+restore_xy_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ rx,
+                  float* __restrict__ ry, size_t n, int HW, int W, float gridW, float gridH) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % HW);
+    const int h = c / W, w = c - h * W;
+    rx[i] = __fmul_rn(__fadd_rn(x[i], (float)w), gridW);
+    ry[i] = __fmul_rn(__fadd_rn(y[i], (float)h), gridH);
+}
+
+__global__ void __launch_bounds__(256)
+restore_size_kernel(const float* __restrict__ w, const float* __restrict__ h, float* __restrict__ rw,
+                    float* __restrict__ rh, size_t n, float inW, float inH) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rw[i] = __fmul_rn(inW, w[i]);
+    rh[i] = __fmul_rn(inH, h[i]);
+}
+
+// =========================================================================================
+// K2 — greedy IoU NMS, one CTA per box list, everything in shared memory
+// =========================================================================================
+// 1. rank sort by (score desc, index desc) — keys are unique, so the rank is a permutation;
+// 2. upper-triangle suppression bitmask: bit j of row i says "kept box i suppresses later box j";
+// 3. one warp scans in order, 32 candidates at a time: the serial dependency lives in the 32x32
+//    diagonal block (kept in registers), the rows of the boxes kept in that block are then OR-ed
+//    into the per-lane `removed` words.
+__device__ __forceinline__ unsigned long long score_key(float s, int idx) {
+    unsigned u = __float_as_uint(s);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // monotone map of fp32 order
+    return ((unsigned long long)u << 32) | (unsigned)idx;
+}
+
+__global__ void __launch_bounds__(256)
+nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score, const int32_t* __restrict__ count,
+                int stride, float thr, int limit, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int prob = blockIdx.x;
+    const int n = min(count[prob], stride);
+    const int tid = threadIdx.x, T = blockDim.x;
+    int32_t* out = keep_idx + (size_t)prob * stride;
+    if (n <= 0) { if (tid == 0) keep_count[prob] = 0; return; }
+    const int Wd = (n + 31) >> 5;
+
+    float4* sbox = reinterpret_cast<float4*>(smem);                              // [stride] sorted boxes
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(sbox + stride);  // [stride]
+    float* sarea = reinterpret_cast<float*>(key + stride);                       // [stride]
+    int32_t* sidx = reinterpret_cast<int32_t*>(sarea + stride);                  // [stride] original index
+    unsigned* mask = reinterpret_cast<unsigned*>(sidx + stride);                 // [n * Wd]
+
+    const float4* pbox = box + (size_t)prob * stride;
+    for (int i = tid; i < n; i += T)
+        key[i] = score ? score_key(score[(size_t)prob * stride + i], i) : (unsigned long long)(unsigned)(n - 1 - i);
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+        const unsigned long long mine = key[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (key[j] > mine);
+        const float4 bx = pbox[i];
+        sbox[rank] = bx;
+        sarea[rank] = box_area(bx);
+        sidx[rank] = i;
+    }
+    __syncthreads();
+    for (int item = tid; item < n * Wd; item += T) {
+        const int wj = item / n, i = item - wj * n;
+        unsigned bitsw = 0;
+        if (wj >= (i >> 5)) {
+            const float4 bi = sbox[i];
+            const float ai = sarea[i];
+            const int j0 = wj << 5;
+            const int jend = min(32, n - j0);
+            for (int t = 0; t < jend; ++t) {
+                const int j = j0 + t;
+                if (j > i && suppresses(sbox[j], sarea[j], bi, ai, thr)) bitsw |= 1u << t;
+            }
+        }
+        mask[(size_t)i * Wd + wj] = bitsw;
+    }
+    __syncthreads();
+    if (tid >= 32) return;
+    const int lane = tid;
+    unsigned removed = 0;            // lane l holds word l of the removed set (n <= 1024)
+    int m = 0;
+    bool done = false;
+    for (int w = 0; w < Wd && !done; ++w) {
+        unsigned cur = __shfl_sync(0xffffffffu, removed, w);
+        const int i0 = w << 5;
+        const int nb = min(32, n - i0);
+        const unsigned diag = (lane < nb) ? mask[(size_t)(i0 + lane) * Wd + w] : 0u;
+        unsigned kept = 0;
+        for (int t = 0; t < nb; ++t) {
+            const unsigned d = __shfl_sync(0xffffffffu, diag, t);
+            if (!((cur >> t) & 1u)) { kept |= 1u << t; cur |= d; }
+        }
+        if (limit > 0 && m + __popc(kept) >= limit) {      // datatest.py:154-155
+            int need = limit - m;
+            unsigned trimmed = 0;
+            for (unsigned rest = kept; need > 0 && rest; --need) { const unsigned low = rest & (0u - rest); trimmed |= low; rest ^= low; }
+            kept = trimmed;
+            done = true;
+        }
+        if ((kept >> lane) & 1u) out[m + __popc(kept & ((1u << lane) - 1u))] = sidx[i0 + lane];
+        m += __popc(kept);
+        if (lane > w && lane < Wd) {
+            for (unsigned rest = kept; rest;) {
+                const int t = __ffs(rest) - 1;
+                rest &= rest - 1;
+                removed |= mask[(size_t)(i0 + t) * Wd + lane];
+            }
+        }
+    }
+    if (lane == 0) keep_count[prob] = m;
+}
+
+// Lists longer than PPN_MAX_CELLS: no bitmask; the CTA visits boxes in order and, for every box
+// still alive, marks the later boxes it suppresses.  The visiting order lives in keep_idx itself
+// (slot m <= i is only overwritten after order[i] has been consumed) with the sign bit as the
+// "suppressed" flag, so no extra workspace is needed.
+__global__ void __launch_bounds__(1024)
+nms_global_kernel(const float4* __restrict__ box, const float* __restrict__ score, const int32_t* __restrict__ count,
+                  int stride, float thr, int limit, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count) {
+    const int prob = blockIdx.x;
+    const int n = min(count[prob], stride);
+    const int tid = threadIdx.x, T = blockDim.x;
+    int32_t* out = keep_idx + (size_t)prob * stride;     // doubles as order[] | dead bit
+    const float4* pbox = box + (size_t)prob * stride;
+    const float* psc = score ? score + (size_t)prob * stride : nullptr;
+    __shared__ int m_s;
+    if (n <= 0) { if (tid == 0) keep_count[prob] = 0; return; }
+    for (int i = tid; i < n; i += T) {
+        int rank = i;
+        if (psc) {
+            const unsigned long long mine = score_key(psc[i], i);
+            rank = 0;
+            for (int j = 0; j < n; ++j) rank += (score_key(psc[j], j) > mine);
+        }
+        out[rank] = i;
+    }
+    if (tid == 0) m_s = 0;
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {
+        const int oi = out[i];
+        if (oi < 0) continue;                        // uniform: flags are written before a barrier
+        const float4 bi = pbox[oi];
+        const float ai = box_area(bi);
+        __syncthreads();                             // everyone has read out[i] before slot m_s <= i is reused
+        if (tid == 0) out[m_s] = oi;
+        for (int j = i + 1 + tid; j < n; j += T) {
+            const int oj = out[j];
+            if (oj >= 0) {
+                const float4 bj = pbox[oj];
+                if (suppresses(bj, box_area(bj), bi, ai, thr)) out[j] = oj | (int)0x80000000;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) m_s += 1;
+        __syncthreads();
+        if (limit > 0 && m_s >= limit) break;
+    }
+    if (tid == 0) keep_count[prob] = m_s;
+}
+
+// =========================================================================================
+// K4 — tree parse, one CTA per image, one thread per surviving root
+// =========================================================================================
+// The arg-max map and delta = resp*conf of every part are staged in shared memory, so each of
+// the <= 25 dependent limb steps costs a shared-memory read instead of an HBM round trip.
+__global__ void __launch_bounds__(128)
+tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
+                  const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
+                  const int32_t* __restrict__ keep_idx, const int32_t* __restrict__ keep_count,
+                  int32_t* __restrict__ h_count, int32_t* __restrict__ h_root, int32_t* __restrict__ h_cell,
+                  float* __restrict__ h_score, float4* __restrict__ h_box, int R) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* s_delta = reinterpret_cast<float*>(smem);                                  // [K*HW]
+    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_delta + (size_t)g.K * g.HW);     // [E*HW] (+pad)
+    int16_t* s_pos = reinterpret_cast<int16_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [K][T]
+    __shared__ int warp_tot[4];
+    __shared__ int base_s;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const float* img = head + (size_t)b * g.img_stride;
+    const int n_keep = keep_count[(size_t)b * n_parts];
+    if (n_keep == 0) { if (tid == 0) h_count[b] = 0; return; }
+
+    for (int i = tid; i < g.K * g.HW; i += T) s_delta[i] = __fmul_rn(__ldg(img + i), __ldg(img + (size_t)g.K * g.HW + i));
+    const uint16_t* am = amax + (size_t)b * g.E * g.HW;
+    for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+
+    const int32_t* cells = cand_cell + (size_t)b * n_parts * g.HW;
+    const int32_t* keep = keep_idx + (size_t)b * n_parts * g.HW;
+    for (int r0 = 0; r0 < n_keep; r0 += T) {
+        const int r = r0 + tid;
+        bool valid = false;
+        int root = -1;
+        if (r < n_keep) {
+            root = cells[keep[r]];
+            for (int t = 0; t < g.K; ++t) s_pos[t * T + tid] = -1;
+            s_pos[tid] = (int16_t)root;
+            for (int cidx = 0; cidx < ch.n_chains; ++cidx) {
+                int cur = root;
+                for (int q = ch.off[cidx]; q < ch.off[cidx + 1]; ++q) {
+                    const int ei = ch.limb[q], t = ch.part[q];
+                    const int a = s_amax[ei * g.HW + cur];
+                    const int dy = a / g.sW, dx = a - dy * g.sW;
+                    const int ih = cur / g.W, iw = cur - ih * g.W;
+                    const int jh = ih + dy - g.off_h, jw = iw + dx - g.off_w;
+                    if (jh < 0 || jw < 0 || jh >= g.H || jw >= g.W) break;      // datatest.py:118
+                    const int j = jh * g.W + jw;
+                    if (s_delta[t * g.HW + j] < thr) break;                    // datatest.py:121
+                    s_pos[t * T + tid] = (int16_t)j;
+                    cur = j;
+                }
+            }
+            int present = 0;
+            for (int t = 1; t < g.K; ++t) present += (s_pos[t * T + tid] >= 0);
+            valid = min_kp <= present;                                          // datatest.py:129
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s, total = 0;
+        for (int wi = 0; wi < (T >> 5); ++wi) {
+            const int t = warp_tot[wi];
+            if (wi < warp) off += t;
+            total += t;
+        }
+        const int slot = off + __popc(bal & ((1u << lane) - 1u));
+        if (valid && slot < R) {
+            const size_t hbase = (size_t)b * R + slot;
+            h_root[hbase] = root;
+            for (int t = 0; t < g.K; ++t) {
+                const int c = s_pos[t * T + tid];
+                h_cell[hbase * g.K + t] = c;
+                h_score[hbase * g.K + t] = c >= 0 ? s_delta[t * g.HW + c] : 0.0f;
+                h_box[hbase * g.K + t] = c >= 0 ? box_at(img, g, t, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) base_s += total;
+        __syncthreads();
+    }
+    if (tid == 0) h_count[b] = base_s;
+}
+
+// =========================================================================================
+// launchers
+// =========================================================================================
+struct DeviceInfo { int sms = 0; int smem_optin = 0; size_t tma = 0, ldg = 48 * 1024, nms = 48 * 1024, tree = 48 * 1024; };
+static DeviceInfo g_dev[64];
+
+// Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
+// drives one GPU, but nothing here assumes it.
+static cudaError_t device_info(DeviceInfo** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    DeviceInfo& d = g_dev[dev];
+    if (!d.sms) {
+        int sms = 0, optin = 0;
+        if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        d.smem_optin = optin;
+        d.sms = sms;
+    }
+    *out = &d;
+    return cudaSuccess;
+}
+
+template <typename F>
+static cudaError_t ensure_smem(F kernel, size_t want, size_t* have) {
+    if (want <= *have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e == cudaSuccess) *have = want;
+    return e;
+}
+
+bool plan_argmax(const Geom& g, const Tuning& t, ArgmaxPlan* p) {
+    if (g.HW % 4 != 0 || g.HW / 4 > 992) return false;
+    p->CV = g.HW / 4;
+    int G = t.argmax_threads / p->CV;
+    if (G < 1) G = 1;
+    if (G > g.S) G = g.S;
+    while (G > 1 && p->CV * G > 992) --G;
+    p->G = G;
+    p->threads = p->CV * G;
+    p->threads_padded = (p->threads + 31) & ~31;
+    const int row_bytes = g.HW * 4;
+    int max_rows = t.argmax_stage_bytes / row_bytes;
+    if (max_rows < 1) max_rows = 1;
+    if (max_rows > g.S) max_rows = g.S;
+    p->chunks = (g.S + max_rows - 1) / max_rows;
+    p->rows = (g.S + p->chunks - 1) / p->chunks;
+    p->chunks = (g.S + p->rows - 1) / p->rows;
+    p->stage_bytes = (uint32_t)((p->rows * row_bytes + 127) & ~127);
+    p->stages = t.argmax_stages;
+    p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
+    p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * G * g.HW * sizeof(Partial) + (size_t)2 * p->stages * sizeof(uint64_t);
+    return true;
+}
+
+cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st) {
+    DeviceInfo* d = nullptr;
+    cudaError_t e = device_info(&d);
+    if (e != cudaSuccess) return e;
+    const int n_mats = g.B * g.E;
+    if (n_mats == 0) return cudaSuccess;
+    ArgmaxPlan p;
+    const bool vec_ok = plan_argmax(g, t, &p) && ((reinterpret_cast<uintptr_t>(head) & 15) == 0);
+    if (vec_ok && t.argmax_variant == 0) {
+        // shrink the ring until it fits the opt-in shared memory (split between resident CTAs)
+        const size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
+        while (p.smem_bytes > budget && p.stages > 2) {
+            --p.stages;
+            p.smem_bytes -= p.stage_bytes + 2 * sizeof(uint64_t);
+        }
+        if (p.smem_bytes <= budget) {
+            if ((e = ensure_smem(limb_argmax_tma_kernel, p.smem_bytes, &d->tma)) != cudaSuccess) return e;
+            int grid = d->sms * p.ctas_per_sm;
+            if (grid > n_mats) grid = n_mats;
+            limb_argmax_tma_kernel<<<grid, p.threads_padded + 32, p.smem_bytes, st>>>(head, amax, g, p);
+            return cudaGetLastError();
+        }
+    }
+    if (vec_ok) {
+        const size_t smem = (size_t)p.G * g.HW * sizeof(Partial);
+        if ((e = ensure_smem(limb_argmax_ldg_kernel, smem, &d->ldg)) != cudaSuccess) return e;
+        limb_argmax_ldg_kernel<<<n_mats, p.threads_padded, smem, st>>>(head, amax, g, p);
+        return cudaGetLastError();
+    }
+    dim3 grid((g.HW + 255) / 256, n_mats);
+    limb_argmax_generic_kernel<<<grid, 256, 0, st>>>(head, amax, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_candidates(const float* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
+                                     float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st) {
+    if (g.B == 0 || n_parts == 0) return cudaSuccess;
+    dim3 grid(g.B, n_parts);
+    decode_candidates_kernel<<<grid, 256, 0, st>>>(head, g, n_parts, thr, cand_cell, cand_score,
+                                                   reinterpret_cast<float4*>(cand_box), cand_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* ry, size_t n, int H, int W,
+                              float gridW, float gridH, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    restore_xy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, rx, ry, n, H * W, W, gridW, gridH);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float* rh, size_t n, float inW, float inH,
+                                cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    restore_size_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, h, rw, rh, n, inW, inH);
+    return cudaGetLastError();
+}
+
+size_t nms_smem_bytes(int stride) {
+    const size_t words = (size_t)stride * ((stride + 31) / 32);
+    return (size_t)stride * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float) + sizeof(int32_t)) + words * sizeof(unsigned);
+}
+
+cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
+                       float thr, int limit, int32_t* keep_idx, int32_t* keep_count, cudaStream_t st) {
+    if (n_problems == 0) return cudaSuccess;
+    DeviceInfo* d = nullptr;
+    cudaError_t e = device_info(&d);
+    if (e != cudaSuccess) return e;
+    const size_t smem = nms_smem_bytes(stride);
+    if (stride <= 1024 && smem <= (size_t)d->smem_optin) {
+        if ((e = ensure_smem(nms_smem_kernel, smem, &d->nms)) != cudaSuccess) return e;
+        nms_smem_kernel<<<n_problems, 256, smem, st>>>(reinterpret_cast<const float4*>(box), score, count, stride, thr,
+                                                       limit, keep_idx, keep_count);
+        return cudaGetLastError();
+    }
+    nms_global_kernel<<<n_problems, 1024, 0, st>>>(reinterpret_cast<const float4*>(box), score, count, stride, thr,
+                                                   limit, keep_idx, keep_count);
+    return cudaGetLastError();
+}
+
+size_t tree_parse_smem_bytes(const Geom& g, int threads) {
+    return (size_t)g.K * g.HW * sizeof(float) + ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
+           (size_t)g.K * threads * sizeof(int16_t);
+}
+
+cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
+                              const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
+                              const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
+                              float* h_score, float* h_box, int R, cudaStream_t st) {
+    if (g.B == 0) return cudaSuccess;
+    DeviceInfo* d = nullptr;
+    cudaError_t e = device_info(&d);
+    if (e != cudaSuccess) return e;
+    const int threads = 128;
+    const size_t smem = tree_parse_smem_bytes(g, threads);
+    if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
+    if ((e = ensure_smem(tree_parse_kernel, smem, &d->tree)) != cudaSuccess) return e;
+    tree_parse_kernel<<<g.B, threads, smem, st>>>(head, g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count,
+                                                  h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R);
+    return cudaGetLastError();
+}
+
+}  // namespace ppn

@@ -1,0 +1,51 @@
+// Internal interface between the kernels (ppn_kernels.cu) and the C ABI (ppn_capi.cu).
+#pragma once
+#include "ppn_device.cuh"
+
+namespace ppn {
+
+struct Tuning {
+    int argmax_variant = 0;            // 0 = TMA bulk-copy ring (persistent), 1 = direct 128-bit loads
+    int argmax_stage_bytes = 32 * 1024;
+    int argmax_stages = 5;
+    int argmax_threads = 320;          // target consumer threads per CTA
+    int argmax_ctas_per_sm = 1;
+    int host_chunk_images = 64;
+};
+
+struct ArgmaxPlan {
+    int CV;               // float4 columns per row = HW / 4
+    int G;                // row groups: thread (g, cv) takes rows g, g+G, ... of every chunk
+    int threads;          // CV * G working consumer threads
+    int threads_padded;   // rounded up to whole warps
+    int rows;             // rows per ring stage
+    int chunks;           // stages per matrix = ceil(S / rows)
+    int stages;           // ring depth
+    int ctas_per_sm;
+    uint32_t stage_bytes;
+    size_t smem_bytes;
+};
+
+bool plan_argmax(const Geom& g, const Tuning& t, ArgmaxPlan* p);
+
+cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st);
+
+cudaError_t launch_decode_candidates(const float* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
+                                     float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st);
+
+cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
+                       float thr, int limit, int32_t* keep_idx, int32_t* keep_count, cudaStream_t st);
+
+cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* ry, size_t n, int H, int W,
+                              float gridW, float gridH, cudaStream_t st);
+cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float* rh, size_t n, float inW, float inH,
+                                cudaStream_t st);
+
+size_t tree_parse_smem_bytes(const Geom& g, int threads);
+
+cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
+                              const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
+                              const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
+                              float* h_score, float* h_box, int R, cudaStream_t st);
+
+}  // namespace ppn

@@ -1,0 +1,139 @@
+"""Drop-in for the parser functions of the reference's ``datatest.py``, computed on the B200.
+
+Same names, arguments, return types and module globals as /root/reference/datatest.py:53-160:
+
+    from pytorch_pose_proposal_network_b200.datatest import get_humans_by_feature, \
+        non_maximum_suppression, restore_xy, restore_size
+
+so ``rt_test.inference`` (rt_test.py:133), ``main.test_output`` (main.py:972) and
+``main.validate`` (main.py:1141) keep calling ``get_humans_by_feature(resp, x, y, w, h, e,
+detection_thresh=0.15)`` unchanged.  Inputs may be numpy arrays (as the reference passes them)
+or torch tensors on any device; every function uploads, runs the CUDA kernels through the C
+ABI, and returns numpy values of the reference's dtypes.  There is no CPU implementation
+behind these functions: without a CUDA device or without ``libppn_decode.so`` they raise.
+
+For throughput use :class:`..parser.PoseParser` on the un-sliced device tensor instead — this
+module pays one upload and one download per call because the reference's signature does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import DIRECTED_GRAPHS, PPNConfig  # noqa: F401  (re-exported like the reference's star import)
+from .parser import PoseParser, _ptr, _stream_ptr
+
+# module globals with the reference's names and defaults (datatest.py:53-60); patch them the
+# same way the reference would be patched for another resolution
+insize = (384, 384)
+outsize = (24, 24)
+local_grid_size = (21, 21)
+inW, inH = insize
+outW, outH = outsize
+sW, sH = local_grid_size
+gridsize = (int(inW / outW), int(inH / outH))
+
+NMS_THRESH = 0.3                       # literal at datatest.py:94
+
+_parsers = {}
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("pytorch_pose_proposal_network_b200 needs a CUDA device; there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _dev32(a) -> torch.Tensor:
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return t.to(device=_device(), dtype=torch.float32).contiguous()
+
+
+def _parser_for(cfg: PPNConfig) -> PoseParser:
+    key = (cfg, torch.cuda.current_device())
+    if key not in _parsers:
+        _parsers[key] = PoseParser(cfg)
+    return _parsers[key]
+
+
+def _shape_struct(H, W):
+    gW, gH = gridsize
+    return _lib.PPNShape(B=1, K=1, E=0, H=H, W=W, sH=1, sW=1, inW=insize[0], inH=insize[1],
+                         gridW=gW, gridH=gH, off_h=0, off_w=0)
+
+
+def restore_xy(x, y):
+    """(x + col) * gridW, (y + row) * gridH for [..., outH, outW] arrays  (datatest.py:63-67)."""
+    xd, yd = _dev32(x), _dev32(y)
+    H, W = xd.shape[-2], xd.shape[-1]
+    if (W, H) != tuple(outsize):
+        raise ValueError(f"arrays are {W}x{H} cells but datatest.outsize is {outsize}")
+    rx, ry = torch.empty_like(xd), torch.empty_like(yd)
+    shape = _shape_struct(H, W)
+    _lib.check(_lib.lib().ppn_restore_xy(_ptr(xd), _ptr(yd), _ptr(rx), _ptr(ry), xd.numel() // (H * W),
+                                         C.byref(shape), _stream_ptr(xd.device)), "ppn_restore_xy")
+    return rx.cpu().numpy(), ry.cpu().numpy()
+
+
+def restore_size(w, h):
+    """inW * w, inH * h  (datatest.py:69-71)."""
+    wd, hd = _dev32(w), _dev32(h)
+    H, W = wd.shape[-2], wd.shape[-1]
+    rw, rh = torch.empty_like(wd), torch.empty_like(hd)
+    shape = _shape_struct(H, W)
+    _lib.check(_lib.lib().ppn_restore_size(_ptr(wd), _ptr(hd), _ptr(rw), _ptr(rh), wd.numel() // (H * W),
+                                           C.byref(shape), _stream_ptr(wd.device)), "ppn_restore_size")
+    return rw.cpu().numpy(), rh.cpu().numpy()
+
+
+def _config_from_arrays(delta, e, detection_thresh, min_num_keypoints, nms_thresh, graphs, swap=False) -> PPNConfig:
+    K, H, W = delta.shape
+    E, eH, eW = e.shape[0], e.shape[1], e.shape[2]
+    if tuple(e.shape[3:]) != (H, W):
+        raise ValueError(f"e has grid {tuple(e.shape[3:])}, delta has {(H, W)}")
+    if (W, H) != tuple(outsize):
+        raise ValueError(f"arrays are {W}x{H} cells but datatest.outsize is {outsize}")
+    return PPNConfig(K=K, E=E, insize=tuple(insize), outsize=(W, H), local_grid_size=(eW, eH),
+                     directed_graphs=graphs, detection_thresh=detection_thresh, nms_thresh=nms_thresh,
+                     min_num_keypoints=min_num_keypoints, swap_window_offsets=swap)
+
+
+def get_humans_by_feature(delta, x, y, w, h, e, detection_thresh=0.15, min_num_keypoints=1):
+    """Parse one image's feature maps into humans  (datatest.py:74-132).
+
+    delta, x, y, w, h: [K, outH, outW]; e: [E, sH, sW, outH, outW]; ``delta`` is already
+    ``resp * conf`` (rt_test.py:130).  Returns ``(humans, scores)``: lists, in descending
+    root-score order, of dicts ``part id -> float32[4] (ymin, xmin, ymax, xmax)`` and
+    ``part id -> float32`` with the reference's key insertion order.
+    """
+    delta_d, e_d = _dev32(delta), _dev32(e)
+    cfg = _config_from_arrays(delta_d, e_d, detection_thresh, min_num_keypoints, NMS_THRESH, DIRECTED_GRAPHS)
+    K, H, W = delta_d.shape
+    # the kernels take the head-tensor layout [resp, conf, x, y, w, h, limbs]; delta * 1 == delta exactly
+    head = torch.cat([delta_d, torch.ones_like(delta_d), _dev32(x), _dev32(y), _dev32(w), _dev32(h),
+                      e_d.reshape(-1, H, W)], dim=0).unsqueeze(0)
+    packed = _parser_for(cfg).parse(head)
+    return packed.humans(0)
+
+
+def non_maximum_suppression(bbox, thresh, score=None, limit=None):
+    """Greedy IoU NMS  (datatest.py:134-160): int32 indices into ``bbox`` in descending-score
+    order (input order when ``score`` is None), at most ``limit`` of them."""
+    box = _dev32(bbox).reshape(-1, 4)
+    n = box.shape[0]
+    if n == 0:
+        return np.zeros((0,), dtype=np.int32)
+    dev = box.device
+    sc = None if score is None else _dev32(score).reshape(-1)
+    count = torch.tensor([n], dtype=torch.int32, device=dev)
+    keep = torch.empty(1, n, dtype=torch.int32, device=dev)
+    kcount = torch.empty(1, dtype=torch.int32, device=dev)
+    # the reference stops once `count >= limit` AFTER keeping a box, so any limit <= 1 keeps one
+    lim = 0 if limit is None else max(int(limit), 1)
+    _lib.check(_lib.lib().ppn_nms(_ptr(box), _ptr(sc), _ptr(count), 1, n, float(np.float32(thresh)), lim,
+                                  _ptr(keep), _ptr(kcount), _stream_ptr(dev)), "ppn_nms")
+    m = int(kcount.item())
+    return keep[0, :m].cpu().numpy().astype(np.int32)

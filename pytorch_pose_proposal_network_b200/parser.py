@@ -1,0 +1,255 @@
+"""Host side of the B200 pose parser: torch tensors in, packed humans out.
+
+:class:`PoseParser` owns the device buffers (torch is used for memory and streams only) and
+calls the C ABI in ``libppn_decode.so`` through ctypes.  The batched entry
+:meth:`PoseParser.parse` takes the un-sliced head tensor ``out[B, C, H, W]`` straight from
+``PoseProposalNet.forward`` (model.py:104-136) so the seven ``.cpu().numpy()`` copies of
+rt_test.py:109-120 disappear; :class:`PackedHumans` converts the packed result back into the
+reference's ``(humans, scores)`` lists of dicts (datatest.py:98-132) on request.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import PPNConfig
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _CConfig:
+    """ctypes views of a PPNConfig; keeps the chain arrays alive."""
+
+    def __init__(self, cfg: PPNConfig, n_nms_parts: int = 1):
+        self.cfg = cfg
+        self.off, self.limb, self.part = cfg.chains()
+        if len(self.off) - 1 > _lib.MAX_CHAINS or len(self.limb) > _lib.MAX_CHAIN_STEPS:
+            raise ValueError("too many / too long track orders for the kernel argument table")
+        gW, gH = cfg.gridsize
+        self._shape_fields = dict(K=cfg.K, E=cfg.E, H=cfg.H, W=cfg.W, sH=cfg.sH, sW=cfg.sW, inW=cfg.inW, inH=cfg.inH,
+                                  gridW=gW, gridH=gH, off_h=cfg.off_h, off_w=cfg.off_w)
+        # numpy demotes the Python-float thresholds to fp32 when comparing with fp32 arrays
+        self.params = _lib.PPNParams(
+            float(np.float32(cfg.detection_thresh)), float(np.float32(cfg.nms_thresh)), int(cfg.min_num_keypoints),
+            int(n_nms_parts), len(self.off) - 1,
+            self.off.ctypes.data_as(_lib.i32p), self.limb.ctypes.data_as(_lib.i32p), self.part.ctypes.data_as(_lib.i32p))
+
+    def shape(self, B: int) -> _lib.PPNShape:
+        return _lib.PPNShape(B=B, **self._shape_fields)
+
+
+class PackedHumans:
+    """Fixed-stride packed result (layout of ``PPNHumans`` in include/ppn_decode.h).
+
+    ``count[b]`` humans of image ``b`` sit in slots ``[0, count[b])`` in the reference's list
+    order (descending root score).  Tensors stay where the parser wrote them (device for
+    :meth:`PoseParser.parse`, host for :meth:`PoseParser.parse_host`) until asked.
+    """
+
+    def __init__(self, cfg: PPNConfig, count, root_cell, part_cell, part_score, part_box):
+        self.cfg = cfg
+        self.count, self.root_cell, self.part_cell = count, root_cell, part_cell
+        self.part_score, self.part_box = part_score, part_box
+
+    @property
+    def R(self) -> int:
+        return self.root_cell.shape[1]
+
+    def cpu(self) -> "PackedHumans":
+        if self.count.device.type == "cpu":
+            return self
+        return PackedHumans(self.cfg, *(t.cpu() for t in (self.count, self.root_cell, self.part_cell,
+                                                           self.part_score, self.part_box)))
+
+    def numpy(self):
+        h = self.cpu()
+        return {k: getattr(h, k).numpy() for k in ("count", "root_cell", "part_cell", "part_score", "part_box")}
+
+    def humans(self, b: int = 0):
+        """(humans, scores) of image ``b`` exactly as ``get_humans_by_feature`` returns them:
+        dicts keyed by part id in first-insertion order, fp32 ``(ymin,xmin,ymax,xmax)`` boxes."""
+        return self.to_lists()[b]
+
+    def to_lists(self) -> List[Tuple[list, list]]:
+        a = self.numpy()
+        graphs = self.cfg.directed_graphs
+        K = self.cfg.K
+        result = []
+        for b in range(a["count"].shape[0]):
+            n = int(a["count"][b])
+            if n > self.R:
+                raise RuntimeError(f"image {b}: {n} humans but only {self.R} slots were provided")
+            humans, scores = [], []
+            for i in range(n):
+                cell = a["part_cell"][b, i]
+                keys = [0]
+                for _, ts in graphs:                       # insertion order of datatest.py:104-125
+                    for t in ts:
+                        if cell[t] < 0:
+                            break
+                        if t not in keys:
+                            keys.append(t)
+                assert len(keys) == int((cell[:K] >= 0).sum()), "track orders do not form a tree"
+                humans.append({t: a["part_box"][b, i, t].copy() for t in keys})
+                scores.append({t: np.float32(a["part_score"][b, i, t]) for t in keys})
+            result.append((humans, scores))
+        return result
+
+
+class PoseParser:
+    """Decode + NMS + limb arg-max + tree parse of PPN head tensors on one B200.
+
+    Not thread-safe per instance (buffers are reused); make one per stream/thread.
+    """
+
+    def __init__(self, cfg: PPNConfig, device=None, max_humans: Optional[int] = None, n_nms_parts: int = 1):
+        if cfg.HW > _lib.MAX_CELLS:
+            raise ValueError(f"grid of {cfg.HW} cells exceeds the kernels' limit of {_lib.MAX_CELLS}")
+        self.cfg = cfg
+        self.lib = _lib.lib()                      # raises if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("PoseParser needs a CUDA device; there is no CPU path")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.R = int(max_humans) if max_humans else cfg.HW
+        self.n_nms_parts = int(n_nms_parts)
+        self.c = _CConfig(cfg, self.n_nms_parts)
+        self._ws = None
+        self._out = None
+        self._out_B = 0
+        self._host_scratch = None
+
+    # ---- buffers --------------------------------------------------------------------- #
+    def _check_head(self, head: torch.Tensor) -> int:
+        cfg = self.cfg
+        if head.dtype != torch.float32 or head.dim() != 4 or tuple(head.shape[1:]) != (cfg.C, cfg.H, cfg.W):
+            raise ValueError(f"head must be fp32 [B,{cfg.C},{cfg.H},{cfg.W}], got {head.dtype} {tuple(head.shape)}")
+        if not head.is_contiguous():
+            raise ValueError("head must be contiguous NCHW")
+        return head.shape[0]
+
+    def _workspace(self, B: int) -> torch.Tensor:
+        need = C.c_size_t()
+        shape = self.c.shape(B)
+        _lib.check(self.lib.ppn_workspace_bytes(C.byref(shape), C.byref(self.c.params), C.byref(need)), "ppn_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def alloc_output(self, B: int, device=None, pin: bool = False) -> PackedHumans:
+        dev = self.device if device is None else torch.device(device)
+        kw = dict(device=dev, pin_memory=pin) if dev.type == "cpu" else dict(device=dev)
+        K, R = self.cfg.K, self.R
+        return PackedHumans(self.cfg,
+                            torch.zeros(B, dtype=torch.int32, **kw),
+                            torch.empty(B, R, dtype=torch.int32, **kw),
+                            torch.empty(B, R, K, dtype=torch.int32, **kw),
+                            torch.empty(B, R, K, dtype=torch.float32, **kw),
+                            torch.empty(B, R, K, 4, dtype=torch.float32, **kw))
+
+    def _humans_struct(self, out: PackedHumans) -> _lib.PPNHumans:
+        return _lib.PPNHumans(out.count.data_ptr(), out.root_cell.data_ptr(), out.part_cell.data_ptr(),
+                              out.part_score.data_ptr(), out.part_box.data_ptr(), out.R)
+
+    # ---- the whole path ---------------------------------------------------------------- #
+    def parse(self, head: torch.Tensor, out: Optional[PackedHumans] = None) -> PackedHumans:
+        """Enqueue the whole path for a device batch on torch's current stream (asynchronous).
+
+        ``out`` may be a preallocated :meth:`alloc_output` to reuse; otherwise the parser's own
+        buffer is returned and overwritten by the next call.
+        """
+        B = self._check_head(head)
+        if head.device != self.device:
+            raise ValueError(f"head is on {head.device}, parser on {self.device}")
+        if out is None:
+            if self._out is None or self._out_B < B:
+                self._out, self._out_B = self.alloc_output(B), B
+            o = self._out
+            out = o if self._out_B == B else PackedHumans(self.cfg, o.count[:B], o.root_cell[:B], o.part_cell[:B],
+                                                          o.part_score[:B], o.part_box[:B])
+        ws = self._workspace(B)
+        shape, hs = self.c.shape(B), self._humans_struct(out)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ppn_parse(_ptr(head), C.byref(shape), C.byref(self.c.params), C.byref(hs),
+                                          _ptr(ws), ws.numel(), _stream_ptr(self.device)), "ppn_parse")
+        return out
+
+    def launches_per_parse(self, B: int) -> int:
+        shape = self.c.shape(B)
+        return int(self.lib.ppn_parse_launches(C.byref(shape), C.byref(self.c.params)))
+
+    def parse_host(self, head: torch.Tensor, out: Optional[PackedHumans] = None) -> PackedHumans:
+        """The whole path from HOST memory (pinned for full copy speed) to host results;
+        synchronous.  This is the end-to-end call with the host<->device copies inside."""
+        B = self._check_head(head)
+        if head.device.type != "cpu":
+            raise ValueError("parse_host takes a CPU tensor")
+        if out is None:
+            out = self.alloc_output(B, device="cpu", pin=True)
+        need = C.c_size_t()
+        shape = self.c.shape(B)
+        _lib.check(self.lib.ppn_parse_host_scratch_bytes(C.byref(shape), C.byref(self.c.params), self.R, C.byref(need)),
+                   "ppn_parse_host_scratch_bytes")
+        if self._host_scratch is None or self._host_scratch.numel() < need.value:
+            self._host_scratch = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        hs = self._humans_struct(out)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ppn_parse_host(_ptr(head), C.byref(shape), C.byref(self.c.params), C.byref(hs),
+                                               _ptr(self._host_scratch), self._host_scratch.numel()), "ppn_parse_host")
+        return out
+
+    # ---- single stages (what the stage-level parity tests call) ------------------------- #
+    def limb_argmax(self, head: torch.Tensor) -> torch.Tensor:
+        """uint16 [B, E, H, W]: first arg-max of every limb window (datatest.py:100,113)."""
+        B = self._check_head(head)
+        cfg = self.cfg
+        amax = torch.empty(B, cfg.E, cfg.H, cfg.W, dtype=torch.uint16, device=self.device)
+        shape = self.c.shape(B)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ppn_limb_argmax(_ptr(head), C.byref(shape), _ptr(amax), _stream_ptr(self.device)), "ppn_limb_argmax")
+        return amax
+
+    def decode_candidates(self, head: torch.Tensor, n_parts: int = 1, detection_thresh: Optional[float] = None):
+        """-> (cell [B,P,HW] i32, score [B,P,HW] f32, box [B,P,HW,4] f32, count [B,P] i32)."""
+        B = self._check_head(head)
+        HW = self.cfg.HW
+        thr = float(np.float32(self.cfg.detection_thresh if detection_thresh is None else detection_thresh))
+        cell = torch.empty(B, n_parts, HW, dtype=torch.int32, device=self.device)
+        score = torch.empty(B, n_parts, HW, dtype=torch.float32, device=self.device)
+        box = torch.empty(B, n_parts, HW, 4, dtype=torch.float32, device=self.device)
+        count = torch.empty(B, n_parts, dtype=torch.int32, device=self.device)
+        shape = self.c.shape(B)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ppn_decode_candidates(_ptr(head), C.byref(shape), n_parts, thr, _ptr(cell), _ptr(score),
+                                                      _ptr(box), _ptr(count), _stream_ptr(self.device)), "ppn_decode_candidates")
+        return cell, score, box, count
+
+    def nms(self, box: torch.Tensor, score: Optional[torch.Tensor], count: torch.Tensor, thresh: float,
+            limit: Optional[int] = None):
+        """box [P, stride, 4], score [P, stride] or None, count [P] -> (keep_idx [P, stride], keep_count [P])."""
+        n_prob, stride = box.shape[0], box.shape[1]
+        keep = torch.empty(n_prob, stride, dtype=torch.int32, device=self.device)
+        kcount = torch.empty(n_prob, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ppn_nms(_ptr(box), _ptr(score), _ptr(count), n_prob, stride, float(np.float32(thresh)),
+                                        int(limit or 0), _ptr(keep), _ptr(kcount), _stream_ptr(self.device)), "ppn_nms")
+        return keep, kcount
+
+    def tree_parse(self, head, amax, cand_cell, keep_idx, keep_count, out: Optional[PackedHumans] = None) -> PackedHumans:
+        B = self._check_head(head)
+        if out is None:
+            out = self.alloc_output(B)
+        shape, hs = self.c.shape(B), self._humans_struct(out)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ppn_tree_parse(_ptr(head), C.byref(shape), C.byref(self.c.params), _ptr(amax), _ptr(cand_cell),
+                                               _ptr(keep_idx), _ptr(keep_count), C.byref(hs), _stream_ptr(self.device)), "ppn_tree_parse")
+        return out

@@ -1,0 +1,95 @@
+"""Image-sharded multi-GPU parsing: one process per GPU, no data-path collective.
+
+Images are independent (the reference parses them one at a time, rt_test.py:133), so a job of
+N images is cut into contiguous blocks, rank r owning images ``[r*n, (r+1)*n)`` with
+``n = ceil(N / world)``; every rank runs the single-GPU pipeline on its block.  The only
+communication is the gather of the per-rank pose lists (and of timings in bench.py): an
+``all_gather`` of the per-image counts and of the fixed-stride packed records, over NCCL on
+NVLink/NVSwitch on a GPU box and over gloo in the CPU tests.
+
+The reference's own use of torch.distributed (main.py:240-245, 1233-1238) is data-parallel
+training; nothing of it is on this path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .config import PPNConfig
+
+
+def shard_range(n_images: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block of images owned by ``rank``: [lo, hi)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world/rank")
+    per = -(-n_images // world)
+    lo = min(rank * per, n_images)
+    return lo, min(lo + per, n_images)
+
+
+def shard_sizes(n_images: int, world: int):
+    return [hi - lo for lo, hi in (shard_range(n_images, world, r) for r in range(world))]
+
+
+_FIELDS = ("count", "root_cell", "part_cell", "part_score", "part_box")
+
+
+def gather_packed(local, n_images: int, group=None, trim_humans: Optional[int] = None):
+    """All-gather the packed humans of every rank's shard into the full job's result.
+
+    ``local`` is a :class:`..parser.PackedHumans` for this rank's block (device tensors with
+    NCCL, CPU tensors with gloo).  Every rank returns the same full-size ``PackedHumans``; images
+    keep their global order because blocks are contiguous.  ``trim_humans`` gathers only the
+    first that many slots per image (callers that know an upper bound on humans per image cut
+    the payload with it; ``count`` still reports the true number).
+    """
+    from .parser import PackedHumans
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = shard_sizes(n_images, world)
+    per = max(sizes) if sizes else 0
+    lo, hi = shard_range(n_images, world, rank)
+    if local.count.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} holds {local.count.shape[0]} images, its shard is {hi - lo}")
+    R = local.R if trim_humans is None else min(local.R, int(trim_humans))
+    gathered = {}
+    for name in _FIELDS:
+        t = getattr(local, name)
+        if name != "count":
+            t = t[:, :R]
+        if t.shape[0] < per:                                   # last rank(s): pad to the common block size
+            pad = torch.zeros((per - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            t = torch.cat([t, pad], dim=0)
+        t = t.contiguous()
+        full = torch.empty((world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, t, group=group)
+        if world * per != n_images:
+            full = torch.cat([full[r * per: r * per + sizes[r]] for r in range(world)], dim=0)
+        gathered[name] = full
+    return PackedHumans(local.cfg, *(gathered[n] for n in _FIELDS))
+
+
+class ShardedPoseParser:
+    """Streams this rank's block of a job through a :class:`PoseParser` in chunks."""
+
+    def __init__(self, cfg: PPNConfig, device=None, chunk_images: int = 512, max_humans: Optional[int] = None):
+        from .parser import PoseParser
+        self.cfg = cfg
+        self.chunk = int(chunk_images)
+        self.parser = PoseParser(cfg, device=device, max_humans=max_humans)
+
+    def parse_block(self, head: torch.Tensor, out=None):
+        """head: this rank's images [n, C, H, W] on the device.  Chunks run back to back on the
+        current stream, each writing its slice of one output block (no host sync in between)."""
+        from .parser import PackedHumans
+        n = head.shape[0]
+        if out is None:
+            out = self.parser.alloc_output(n)
+        for b0 in range(0, n, self.chunk):
+            b1 = min(n, b0 + self.chunk)
+            view = PackedHumans(self.cfg, out.count[b0:b1], out.root_cell[b0:b1], out.part_cell[b0:b1],
+                                out.part_score[b0:b1], out.part_box[b0:b1])
+            self.parser.parse(head[b0:b1], out=view)
+        return out

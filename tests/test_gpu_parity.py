@@ -1,0 +1,374 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden vectors.
+
+Bar: bit-exact on candidate cells, NMS survivors, arg-max indices, human assignment AND on the
+fp32 boxes / scores (the spec allows 1e-5 relative; the kernels reproduce numpy's roundings, so
+the tests demand 0 ulp).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle, ppn_oracle as O, synth
+from tests.golden_util import case_names, load_case, load_nms_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def cfg_of(g: O.Geometry):
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    return PPNConfig(K=g.K, E=g.E, insize=(g.inW, g.inH), outsize=(g.W, g.H), local_grid_size=(g.sW, g.sH),
+                     directed_graphs=g.graphs, detection_thresh=g.det_thresh, nms_thresh=g.nms_thresh,
+                     min_num_keypoints=g.min_kp)
+
+
+def parser_for(g):
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    return PoseParser(cfg_of(g))
+
+
+def assert_packed_equals_oracle(packed, ref, B):
+    """packed: PackedHumans.numpy(); ref: c_oracle.parse_batch dict."""
+    assert np.array_equal(packed["count"], ref["counts"][:, 2])
+    for b in range(B):
+        n = int(ref["counts"][b, 2])
+        assert np.array_equal(packed["root_cell"][b, :n], ref["root_cell"][b, :n]), b
+        assert np.array_equal(packed["part_cell"][b, :n], ref["part_cell"][b, :n]), b
+        assert np.array_equal(bits(packed["part_score"][b, :n]), bits(ref["part_score"][b, :n])), b
+        assert np.array_equal(bits(packed["part_box"][b, :n]), bits(ref["part_box"][b, :n])), b
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors: outputs of the reference's own functions
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", case_names())
+def test_golden_stages_and_humans(name):
+    g, out, fx = load_case(name)
+    parser = parser_for(g)
+    head = torch.from_numpy(out[None]).cuda()
+
+    amax = parser.limb_argmax(head)
+    assert synth.digest(amax[0].cpu().numpy()) == str(fx["amax_sha256"])
+
+    cell, score, box, count = parser.decode_candidates(head)
+    n = int(count[0, 0])
+    assert np.array_equal(cell[0, 0, :n].cpu().numpy(), fx["cand_cell"])
+
+    keep, kcount = parser.nms(box[:, 0], score[:, 0], count[:, 0].contiguous(), g.nms_thresh)
+    m = int(kcount[0])
+    assert np.array_equal(keep[0, :m].cpu().numpy(), fx["ref_keep_idx"])
+
+    staged = parser.tree_parse(head, amax, cell, keep.reshape(1, 1, -1), kcount.reshape(1, 1))
+    fused = parser.parse(head)
+    torch.cuda.synchronize()
+    order = fx["ref_key_order"]
+    for packed in (staged, fused):
+        a = packed.numpy()
+        nh = int(a["count"][0])
+        assert nh == order.shape[0]
+        assert np.array_equal(a["part_cell"][0, :nh], fx["part_cell"])
+        assert np.array_equal(a["root_cell"][0, :nh], fx["root_cell"])
+        assert np.array_equal(bits(a["part_box"][0, :nh]), bits(fx["ref_box"]))
+        assert np.array_equal(bits(a["part_score"][0, :nh]), bits(fx["ref_score"]))
+        humans, scores = packed.humans(0)
+        for i, (hm, sc) in enumerate(zip(humans, scores)):
+            want = [int(t) for t in order[i] if t >= 0]
+            assert list(hm.keys()) == want and list(sc.keys()) == want
+            for t in want:
+                assert hm[t].dtype == np.float32 and hm[t].shape == (4,)
+                assert isinstance(sc[t], np.float32)
+
+
+def test_golden_dropin_signature_native():
+    """datatest.get_humans_by_feature with the reference's own argument convention (numpy, squeezed)."""
+    from pytorch_pose_proposal_network_b200 import datatest as dt
+    g, out, fx = load_case("native_U_s0")
+    resp, conf, x, y, w, h, e = O.split_head(out, g)
+    humans, scores = dt.get_humans_by_feature(resp * conf, x, y, w, h, e, detection_thresh=0.15)
+    order = fx["ref_key_order"]
+    assert len(humans) == order.shape[0]
+    for i, (hm, sc) in enumerate(zip(humans, scores)):
+        want = [int(t) for t in order[i] if t >= 0]
+        assert list(hm.keys()) == want
+        for t in want:
+            assert np.array_equal(bits(hm[t]), bits(fx["ref_box"][i, t]))
+            assert bits(sc[t]) == bits(fx["ref_score"][i, t])
+
+
+def test_dropin_restore_functions():
+    from pytorch_pose_proposal_network_b200 import datatest as dt
+    g, out, _ = load_case("native_U_s0")
+    _, _, x, y, w, h, _ = O.split_head(out, g)
+    rx, ry = dt.restore_xy(x, y)
+    rw, rh = dt.restore_size(w, h)
+    ex, ey = O.restore_xy(x, y, g)
+    ew, eh = O.restore_size(w, h, g)
+    for got, want in ((rx, ex), (ry, ey), (rw, ew), (rh, eh)):
+        assert got.dtype == np.float32 and np.array_equal(bits(got), bits(want))
+
+
+def test_dropin_nms_hand_cases():
+    from pytorch_pose_proposal_network_b200 import datatest as dt
+    for name, c in load_nms_cases().items():
+        score = c["score"] if bool(c["has_score"]) else None
+        limit = None if int(c["limit"]) < 0 else int(c["limit"])
+        got = dt.non_maximum_suppression(c["box"], float(c["thresh"]), score=score, limit=limit)
+        assert got.dtype == np.int32
+        assert np.array_equal(got, c["keep"]), name
+
+
+def test_nms_long_list_uses_global_kernel():
+    """> 1024 boxes: the no-bitmask kernel; checked against the C restatement."""
+    from pytorch_pose_proposal_network_b200 import datatest as dt
+    rng = np.random.default_rng(5)
+    n = 3000
+    c = rng.random((n, 2), dtype=np.float32) * 600
+    s = rng.random((n, 2), dtype=np.float32) * 60 + 4
+    box = np.concatenate([c - s / 2, c + s / 2], axis=1)
+    score = rng.permutation(n).astype(np.float32)
+    for sc, lim in ((score, None), (None, None), (score, 40)):
+        got = dt.non_maximum_suppression(box, 0.3, score=sc, limit=lim)
+        assert np.array_equal(got, c_oracle.nms(box, 0.3, score=sc, limit=lim))
+
+
+# ------------------------------------------------------------------------------------------
+# batches against the C restatement, every distribution and preset
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("preset,dist,B", [("cfg2", "U", 48), ("cfg2", "R", 16), ("cfg2", "D", 16), ("cfg2", "S", 16),
+                                           ("cfg3", "D", 12), ("cfg3", "U", 12), ("cfg4", "U", 6), ("cfg4", "D", 4),
+                                           ("native", "U", 3)])
+def test_batch_matches_c_oracle(preset, dist, B):
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    head = synth.make_head(g, dist, seed=100 + B, B=B)
+    assert synth.root_scores_distinct(head, g)
+    ref = c_oracle.parse_batch(head, g, n_threads=8)
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    parser = PoseParser(cfg)
+    packed = parser.parse(torch.from_numpy(head).cuda())
+    assert_packed_equals_oracle(packed.numpy(), ref, B)
+    # the host-memory entry (chunked, overlapped copies) must give the same bytes
+    host = parser.parse_host(torch.from_numpy(head).pin_memory())
+    assert_packed_equals_oracle(host.numpy(), ref, B)
+
+
+@pytest.mark.parametrize("variant,stage_bytes,stages,threads,ctas", [
+    (0, 32768, 5, 320, 1), (0, 4096, 3, 96, 2), (0, 65536, 2, 640, 1), (0, 16384, 8, 256, 2), (1, 32768, 5, 320, 1),
+    (1, 32768, 5, 64, 1)])
+@pytest.mark.parametrize("preset", ["cfg2", "cfg4", "native"])
+def test_limb_argmax_every_tuning(preset, variant, stage_bytes, stages, threads, ctas):
+    """The arg-max kernel under every ring shape / thread split, against the C restatement."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    B = 3 if preset == "native" else 7
+    head = synth.make_head(g, "U", seed=7, B=B)
+    want = np.stack([c_oracle.limb_argmax(img, g) for img in head]).astype(np.uint16)
+    _lib.tune(argmax_variant=variant, argmax_stage_bytes=stage_bytes, argmax_stages=stages, argmax_threads=threads,
+              argmax_ctas_per_sm=ctas)
+    try:
+        got = PoseParser(cfg).limb_argmax(torch.from_numpy(head).cuda()).cpu().numpy()
+    finally:
+        _lib.tune(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=5, argmax_threads=320, argmax_ctas_per_sm=1)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("W,H,sW,sH", [(13, 13, 9, 9), (5, 7, 3, 5), (10, 6, 7, 7), (31, 33, 3, 3)])
+def test_odd_shapes_generic_paths(W, H, sW, sH):
+    """Grids whose cell count is not a multiple of 4 (scalar arg-max kernel), non-square grids and
+    windows (row/column half-window convention of datatest.py:115-116)."""
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PPNConfig.mpii16(insize=(W * 16, H * 16), outsize=(W, H), local_grid_size=(sW, sH))
+    g = O.Geometry.of(cfg)
+    head = synth.make_head(g, "U", seed=W * 100 + H, B=5)
+    ref = c_oracle.parse_batch(head, g)
+    parser = PoseParser(cfg)
+    dev = torch.from_numpy(head).cuda()
+    want = np.stack([c_oracle.limb_argmax(img, g) for img in head]).astype(np.uint16)
+    assert np.array_equal(parser.limb_argmax(dev).cpu().numpy(), want)
+    assert_packed_equals_oracle(parser.parse(dev).numpy(), ref, 5)
+
+
+def test_argmax_nan_tie_signed_zero():
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PPNConfig.mpii16(outsize=(4, 4), local_grid_size=(3, 3), insize=(128, 128))
+    g = O.Geometry.of(cfg)
+    out = np.zeros((1, g.C, g.H, g.W), np.float32)
+    e = out[0, 6 * g.K:].reshape(g.E, g.S, g.H * g.W)
+    rng = np.random.default_rng(0)
+    e[:] = rng.integers(0, 3, e.shape).astype(np.float32)            # plenty of exact ties
+    e[0, :, 0] = [1, 5, 5, 2, 5, 0, 0, 0, 0]
+    e[0, :, 1] = [1, np.nan, 7, np.nan, 9, 0, 0, 0, 0]
+    e[0, :, 2] = [-np.inf] * 9
+    e[0, :, 3] = [-0.0, 0.0, -0.0, 0, 0, 0, 0, 0, 0]
+    e[0, :, 4] = [np.inf, np.nan, np.inf, 0, 0, 0, 0, 0, 0]
+    e[1, :, 5] = [np.nan] * 9
+    want = e.reshape(g.E, g.S, g.H, g.W).argmax(1).astype(np.uint16)
+    for threads in (320, 8):              # several row groups (merge path) and one
+        from pytorch_pose_proposal_network_b200 import _lib
+        _lib.tune(argmax_threads=max(threads, 32))
+        try:
+            got = PoseParser(cfg).limb_argmax(torch.from_numpy(out).cuda()).cpu().numpy()[0]
+        finally:
+            _lib.tune(argmax_threads=320)
+        assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases of the parse (KAT-3)
+# ------------------------------------------------------------------------------------------
+def _tiny():
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    graphs = (((0, 1), (1, 2)), ((0, 2), (1, 3)), ((3,), (4,)))
+    return PPNConfig(K=5, E=4, insize=(128, 128), outsize=(8, 8), local_grid_size=(5, 5), directed_graphs=graphs)
+
+
+def test_edge_cases_match_oracle():
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = _tiny()
+    g = O.Geometry.of(cfg)
+    thr = np.float32(0.15)
+    imgs = []
+    base = synth.make_head(g, "U", seed=1, B=1)[0]
+    # 0: nothing above threshold
+    a = base.copy(); a[0:g.K] = 0.1; a[g.K:2 * g.K] = 1.0; imgs.append(a)
+    # 1: every delta exactly == thr: no roots (strict >)
+    a = base.copy(); a[0:g.K] = thr; a[g.K:2 * g.K] = 1.0; imgs.append(a)
+    # 2: one root; limb targets exactly at threshold are ACCEPTED (delta < thr breaks)
+    a = base.copy(); a[0:g.K] = thr; a[g.K:2 * g.K] = 1.0; a[0, 3, 3] = 0.9; imgs.append(a)
+    # 3: every limb points to the top-left window corner -> walks leave the grid near the border
+    a = base.copy(); a[6 * g.K:] = 0.0; a[6 * g.K:].reshape(g.E, g.S, g.H, g.W)[:, 0] = 1.0; imgs.append(a)
+    # 4: all window entries equal -> arg-max 0 everywhere
+    a = base.copy(); a[6 * g.K:] = 0.5; imgs.append(a)
+    # 5: identical root boxes everywhere (IoU = 1), distinct scores
+    a = base.copy(); a[2 * g.K] = 0.0; a[3 * g.K] = 0.0
+    a[4 * g.K] = 0.5; a[5 * g.K] = 0.5
+    X, Y = np.meshgrid(np.arange(g.W, dtype=np.float32), np.arange(g.H, dtype=np.float32))
+    a[2 * g.K] = (4 - X) ; a[3 * g.K] = (4 - Y)          # (x + X) constant -> same centre for every cell
+    imgs.append(a)
+    # 6: zero-area root boxes (w = h = 0): IoU is 0/0 = NaN -> nothing suppressed
+    a = base.copy(); a[4 * g.K] = 0.0; a[5 * g.K] = 0.0; a[2 * g.K] = 0.0; a[3 * g.K] = 0.0; imgs.append(a)
+    head = np.stack(imgs).astype(np.float32)
+    for min_kp in (1, -1, 3):
+        c2 = cfg.with_(min_num_keypoints=min_kp)
+        g2 = O.Geometry.of(c2)
+        ref = c_oracle.parse_batch(head, g2)
+        with np.errstate(all="ignore"):
+            for b in range(head.shape[0]):     # numpy twin agrees with the C twin on these too
+                p = O.parse_image(head[b], g2)
+                assert np.array_equal(p.part_cell, ref["part_cell"][b, :len(p.root_cell)])
+        packed = PoseParser(c2).parse(torch.from_numpy(head).cuda()).numpy()
+        assert_packed_equals_oracle(packed, ref, head.shape[0])
+    assert ref["counts"][0, 0] == 0 and ref["counts"][1, 0] == 0 and ref["counts"][2, 0] == 1
+
+
+def test_tie_rule_is_larger_cell_first():
+    """Equal root scores: the reference's order is undefined (unstable argsort); ours is pinned."""
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = _tiny().with_(min_num_keypoints=-1)
+    g = O.Geometry.of(cfg)
+    a = synth.make_head(g, "U", seed=2, B=1)
+    a[0, 0] = 0.0; a[0, g.K] = 1.0
+    a[0, 4 * g.K] = 0.01; a[0, 5 * g.K] = 0.01                  # tiny boxes: nothing suppressed
+    for c in (5, 17, 40, 41):
+        a[0, 0].reshape(-1)[c] = 0.5
+    packed = PoseParser(cfg).parse(torch.from_numpy(a).cuda()).numpy()
+    assert list(packed["root_cell"][0, :4]) == [41, 40, 17, 5]
+    ref = c_oracle.parse_batch(a, g)
+    assert list(ref["root_cell"][0, :4]) == [41, 40, 17, 5]
+
+
+def test_capacity_limit_keeps_top_scores():
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    cfg = PPNConfig.mpii16()
+    g = O.Geometry.of(cfg)
+    head = synth.make_head(g, "D", seed=3, B=2)
+    ref = c_oracle.parse_batch(head, g)
+    packed = PoseParser(cfg, max_humans=10).parse(torch.from_numpy(head).cuda())
+    a = packed.numpy()
+    assert np.array_equal(a["count"], ref["counts"][:, 2]) and a["count"].min() > 10
+    assert np.array_equal(a["part_cell"][:, :10], ref["part_cell"][:, :10])
+    with pytest.raises(RuntimeError):
+        packed.to_lists()
+
+
+def test_bad_arguments_raise():
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PPNConfig.mpii16()
+    p = PoseParser(cfg)
+    with pytest.raises(ValueError):
+        p.parse(torch.zeros(1, cfg.C + 1, cfg.H, cfg.W, device="cuda"))
+    with pytest.raises(ValueError):
+        p.parse(torch.zeros(1, cfg.C, cfg.H, cfg.W, device="cuda", dtype=torch.float16))
+    shape = p.c.shape(1)
+    hs = _lib.PPNHumans(0, 0, 0, 0, 0, 4)
+    rc = _lib.lib().ppn_parse(None, C.byref(shape), C.byref(p.c.params), C.byref(hs), None, 0, None)
+    assert rc == -1 and b"bad argument" in _lib.lib().ppn_strerror(rc)
+    out = p.alloc_output(1)
+    hs = p._humans_struct(out)
+    ws = torch.empty(256, dtype=torch.uint8, device="cuda")
+    head = torch.zeros(1, cfg.C, cfg.H, cfg.W, device="cuda")
+    rc = _lib.lib().ppn_parse(head.data_ptr(), C.byref(shape), C.byref(p.c.params), C.byref(hs), ws.data_ptr(), 256, None)
+    assert rc == -3
+    with pytest.raises(ValueError):
+        PoseParser(PPNConfig.mpii16(outsize=(40, 40), insize=(640, 640)))
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties + sampled oracle check
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("preset,B,dist", [("cfg2", 512, "U"), ("cfg3", 1024, "D"), ("cfg4", 256, "U")])
+def test_full_size_properties(preset, B, dist):
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    head = torch.rand(B, cfg.C, cfg.H, cfg.W, device="cuda", generator=gen)
+    if dist == "D":
+        head[:, :2 * cfg.K] = 0.4 + 0.6 * head[:, :2 * cfg.K]
+        head[:, 4 * cfg.K:6 * cfg.K] *= 0.08
+    parser = PoseParser(cfg)
+    first = {k: v.copy() for k, v in parser.parse(head).numpy().items()}
+    # determinism / idempotence: same input, same bytes (compare only the valid slots)
+    second = parser.parse(head).numpy()
+    assert np.array_equal(first["count"], second["count"])
+    # permutation equivariance: images are independent, so parse(head[perm]) == parse(head)[perm]
+    perm = torch.randperm(B, device="cuda", generator=gen)
+    shuffled = parser.parse(head[perm].contiguous()).numpy()
+    pc = perm.cpu().numpy()
+    assert np.array_equal(shuffled["count"], first["count"][pc])
+    for i in range(0, B, max(1, B // 64)):
+        n = int(shuffled["count"][i])
+        assert np.array_equal(shuffled["part_cell"][i, :n], first["part_cell"][pc[i], :n])
+        assert np.array_equal(bits(shuffled["part_box"][i, :n]), bits(first["part_box"][pc[i], :n]))
+    # structural invariants of every human
+    for b in range(0, B, max(1, B // 32)):
+        n = int(first["count"][b])
+        cells = first["part_cell"][b, :n]
+        assert (cells[:, 0] == first["root_cell"][b, :n]).all()
+        assert ((cells >= -1) & (cells < cfg.HW)).all()
+        assert ((cells[:, 1:] >= 0).sum(1) >= cfg.min_num_keypoints).all()
+        sc = first["part_score"][b, :n]
+        assert (sc[cells >= 0] >= np.float32(cfg.detection_thresh)).all()
+        assert (np.diff(sc[:, 0]) <= 0).all()                 # descending root score
+    # a sample of images against the C restatement, bit for bit
+    pick = np.linspace(0, B - 1, 12).astype(int)
+    sub = head[torch.from_numpy(pick).cuda()].cpu().numpy()
+    if synth.root_scores_distinct(sub, g):
+        ref = c_oracle.parse_batch(sub, g, n_threads=8)
+        sample = {k: v[pick] for k, v in first.items()}
+        assert_packed_equals_oracle(sample, ref, len(pick))
