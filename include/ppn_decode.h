@@ -98,7 +98,7 @@ typedef struct PPNHumans {
 int         ppn_abi_version(void);
 const char* ppn_strerror(int code);
 
-/* Bytes of scratch ppn_parse needs for this shape (arg-max map, candidate lists, NMS lists). */
+/* Bytes of scratch ppn_parse needs for this shape (arg-max map, surviving root cells, counts). */
 int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* bytes);
 
 /* Number of kernel launches one ppn_parse call enqueues for this shape. */
@@ -132,12 +132,15 @@ int ppn_nms(const float* box, const float* score, const int32_t* count, int32_t 
             int32_t* keep_idx, int32_t* keep_count, void* stream);
 
 /* Walk the track orders from every surviving root of part 0.  cand_cell/keep_idx/keep_count
- * are the outputs of the two calls above with the given n_parts. */
+ * are the outputs of the two calls above with params->n_nms_parts lists per image; with
+ * cand_cell == NULL, keep_idx holds root CELLS directly instead of indices into cand_cell. */
 int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* params,
                    const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                    const int32_t* keep_count, const PPNHumans* out, void* stream);
 
-/* The whole path on a device batch: limb arg-max, decode, NMS, tree parse. */
+/* The whole path on a device batch: limb arg-max on `stream`; decode+NMS fused in one kernel
+ * (candidates stay in shared memory) on an internal side stream beside it; then the tree parse.
+ * Results are identical to calling the four stage functions above in sequence. */
 int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
               const PPNHumans* out, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -158,7 +161,8 @@ int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
 
 /* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
  * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
- * "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
+ * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
+ * "parse.overlap" (1 = decode+NMS on a side stream beside the arg-max), "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);
 int ppn_tune_get(const char* key, int32_t* value);
 

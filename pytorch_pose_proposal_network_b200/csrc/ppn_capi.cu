@@ -20,12 +20,38 @@ constexpr int kMaxProfiled = 4096;
 struct Profile {
     bool on = false;
     int used = 0;
-    cudaEvent_t* ev = nullptr;          // [kMaxProfiled][kStages + 1]
+    cudaEvent_t* ev = nullptr;          // [kMaxProfiled][2 * kStages]: (start, stop) per stage
 } g_prof;
 
 inline cudaEvent_t* profile_slot() {
     if (!g_prof.on || g_prof.used >= kMaxProfiled) return nullptr;
-    return g_prof.ev + (size_t)(g_prof.used++) * (kStages + 1);
+    return g_prof.ev + (size_t)(g_prof.used++) * (2 * kStages);
+}
+
+// ---- side lane: decode + NMS run beside the limb arg-max ---------------------------------
+// The arg-max stream (K3) and decode+NMS (K1, K2) are independent; only the tree parse (K4)
+// needs both.  ppn_parse forks K1/K2 onto a private non-blocking stream and joins before K4,
+// so the latency-bound small kernels hide behind the HBM-bound one.  One lane per host thread
+// and device; event record/wait pairs are also legal under stream capture (CUDA graphs).
+struct SideLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+thread_local SideLane t_side[64];
+
+cudaError_t side_lane(SideLane** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    SideLane& l = t_side[dev];
+    if (!l.stream) {
+        if ((e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    *out = &l;
+    return cudaSuccess;
 }
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? PPN_OK : (int)e; }
@@ -76,9 +102,10 @@ int make_chains(const PPNShape* s, const PPNParams* p, ppn::ChainTable* ch) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Workspace layout of ppn_parse, every block 256-byte aligned.
+// Workspace layout of ppn_parse (arg-max map, surviving root cells per (image, part), their
+// counts), every block 256-byte aligned.
 struct Workspace {
-    size_t amax, cand_cell, cand_score, cand_box, cand_count, keep_idx, keep_count, total;
+    size_t amax, keep_idx, keep_count, total;
 };
 
 Workspace carve(const PPNShape* s, int n_parts) {
@@ -87,10 +114,6 @@ Workspace carve(const PPNShape* s, int n_parts) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t at = off; off = align_up(off + bytes, 256); return at; };
     w.amax = take(B * s->E * HW * sizeof(uint16_t));
-    w.cand_cell = take(B * P * HW * sizeof(int32_t));
-    w.cand_score = take(B * P * HW * sizeof(float));
-    w.cand_box = take(B * P * HW * 4 * sizeof(float));
-    w.cand_count = take(B * P * sizeof(int32_t));
     w.keep_idx = take(B * P * HW * sizeof(int32_t));
     w.keep_count = take(B * P * sizeof(int32_t));
     w.total = off;
@@ -136,6 +159,8 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.stages")) t.argmax_stages = value < 2 ? 2 : (value > 32 ? 32 : value);
     else if (!std::strcmp(key, "argmax.threads")) t.argmax_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) t.argmax_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
+    else if (!std::strcmp(key, "argmax.split")) t.argmax_split = value;
+    else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value != 0;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -149,6 +174,8 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.stages")) *value = t.argmax_stages;
     else if (!std::strcmp(key, "argmax.threads")) *value = t.argmax_threads;
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) *value = t.argmax_ctas_per_sm;
+    else if (!std::strcmp(key, "argmax.split")) *value = t.argmax_split;
+    else if (!std::strcmp(key, "parse.overlap")) *value = t.parse_overlap;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -165,7 +192,7 @@ int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* 
 
 int ppn_parse_launches(const PPNShape* shape, const PPNParams* params) {
     if (check_shape(shape) || check_params(shape, params)) return 0;
-    return shape->B > 0 ? 4 : 0;
+    return shape->B > 0 ? 3 : 0;
 }
 
 int ppn_limb_argmax(const float* head, const PPNShape* shape, uint16_t* amax, void* stream) {
@@ -229,7 +256,7 @@ int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* pa
     ppn::ChainTable ch;
     if ((rc = make_chains(shape, params, &ch))) return rc;
     if (shape->B == 0) return PPN_OK;
-    if (!head || !cand_cell || !keep_idx || !keep_count || (!amax && shape->E > 0)) return PPN_E_BADARG;
+    if (!head || !keep_idx || !keep_count || (!amax && shape->E > 0)) return PPN_E_BADARG;   // cand_cell may be NULL
     if ((long long)shape->H * shape->W > PPN_MAX_CELLS) return PPN_E_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out->part_box) & 15) return PPN_E_BADARG;
     return cuda_rc(ppn::launch_tree_parse(head, make_geom(shape), ch, params->det_thresh, params->min_num_keypoints,
@@ -256,34 +283,45 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     if (workspace_bytes < w.total) return PPN_E_WORKSPACE;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     uint16_t* amax = reinterpret_cast<uint16_t*>(ws + w.amax);
-    int32_t* cand_cell = reinterpret_cast<int32_t*>(ws + w.cand_cell);
-    float* cand_score = reinterpret_cast<float*>(ws + w.cand_score);
-    float* cand_box = reinterpret_cast<float*>(ws + w.cand_box);
-    int32_t* cand_count = reinterpret_cast<int32_t*>(ws + w.cand_count);
     int32_t* keep_idx = reinterpret_cast<int32_t*>(ws + w.keep_idx);
     int32_t* keep_count = reinterpret_cast<int32_t*>(ws + w.keep_count);
     const ppn::Geom g = make_geom(shape);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     cudaEvent_t* ev = profile_slot();
+    cudaStream_t side = st;
+    SideLane* lane = nullptr;
+    if (g_tuning.parse_overlap) {
+        if ((e = side_lane(&lane)) != cudaSuccess) return (int)e;
+        side = lane->stream;
+        if ((e = cudaEventRecord(lane->fork, st)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(side, lane->fork, 0)) != cudaSuccess) return (int)e;
+    }
+    // K3 on the caller's stream
     if (ev) cudaEventRecord(ev[0], st);
     if ((e = ppn::launch_limb_argmax(head, amax, g, g_tuning, st)) != cudaSuccess) return (int)e;
     if (ev) cudaEventRecord(ev[1], st);
-    if ((e = ppn::launch_decode_candidates(head, g, P, params->det_thresh, cand_cell, cand_score, cand_box, cand_count, st)) != cudaSuccess) return (int)e;
-    if (ev) cudaEventRecord(ev[2], st);
-    if ((e = ppn::launch_nms(cand_box, cand_score, cand_count, g.B * P, g.HW, params->nms_thresh, 0, keep_idx, keep_count, st)) != cudaSuccess) return (int)e;
-    if (ev) cudaEventRecord(ev[3], st);
-    if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, cand_cell, keep_idx,
-                                    keep_count, out->count, out->root_cell, out->part_cell, out->part_score, out->part_box,
-                                    out->R, st)) != cudaSuccess) return (int)e;
-    if (ev) cudaEventRecord(ev[4], st);
+    // K1+K2 (fused: candidates never leave shared memory) beside it
+    if (ev) { cudaEventRecord(ev[2], side); cudaEventRecord(ev[3], side); cudaEventRecord(ev[4], side); }
+    if ((e = ppn::launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, side)) != cudaSuccess) return (int)e;
+    if (ev) cudaEventRecord(ev[5], side);
+    if (lane) {
+        if ((e = cudaEventRecord(lane->join, side)) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(st, lane->join, 0)) != cudaSuccess) return (int)e;
+    }
+    // K4 needs both
+    if (ev) cudaEventRecord(ev[6], st);
+    if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr /*keep_idx holds cells*/,
+                                    keep_idx, keep_count, out->count, out->root_cell, out->part_cell, out->part_score,
+                                    out->part_box, out->R, st)) != cudaSuccess) return (int)e;
+    if (ev) cudaEventRecord(ev[7], st);
     return PPN_OK;
 }
 
 int ppn_profile_enable(int32_t on) {
     if (on && !g_prof.ev) {
-        g_prof.ev = new cudaEvent_t[(size_t)kMaxProfiled * (kStages + 1)];
-        for (size_t i = 0; i < (size_t)kMaxProfiled * (kStages + 1); ++i) {
+        g_prof.ev = new cudaEvent_t[(size_t)kMaxProfiled * (2 * kStages)];
+        for (size_t i = 0; i < (size_t)kMaxProfiled * (2 * kStages); ++i) {
             cudaError_t e = cudaEventCreate(&g_prof.ev[i]);
             if (e != cudaSuccess) return (int)e;
         }
@@ -298,12 +336,12 @@ int ppn_profile_read(float* stage_ms, int32_t* n_calls) {
     for (int s = 0; s < kStages; ++s) stage_ms[s] = 0.0f;
     *n_calls = g_prof.used;
     for (int c = 0; c < g_prof.used; ++c) {
-        cudaEvent_t* ev = g_prof.ev + (size_t)c * (kStages + 1);
-        cudaError_t e = cudaEventSynchronize(ev[kStages]);
+        cudaEvent_t* ev = g_prof.ev + (size_t)c * (2 * kStages);
+        cudaError_t e = cudaEventSynchronize(ev[2 * kStages - 1]);
         if (e != cudaSuccess) return (int)e;
         for (int s = 0; s < kStages; ++s) {
             float ms = 0.0f;
-            if ((e = cudaEventElapsedTime(&ms, ev[s], ev[s + 1])) != cudaSuccess) return (int)e;
+            if ((e = cudaEventElapsedTime(&ms, ev[2 * s], ev[2 * s + 1])) != cudaSuccess) return (int)e;
             stage_ms[s] += ms;
         }
     }

@@ -50,13 +50,18 @@ __device__ __forceinline__ float4 box_at(const float* __restrict__ img, const Ge
 __device__ __forceinline__ float np_max(float a, float b) { return (a >= b || a != a) ? a : b; }
 __device__ __forceinline__ float np_min(float a, float b) { return (a <= b || a != a) ? a : b; }
 
-// IoU >= thr of a tested box against an already kept one  (datatest.py:145-150)
+// IoU >= thr of a tested box against an already kept one  (datatest.py:145-150).
+// `thr_positive` (thr > 0, uniform) allows an exact shortcut: without overlap the reference's
+// intersection is prod * 0, so its IoU is +-0 or NaN, and neither is >= a positive threshold —
+// the division can be skipped without changing the answer.
 __device__ __forceinline__ bool suppresses(const float4 tested, float area_tested,
-                                           const float4 kept, float area_kept, float thr) {
+                                           const float4 kept, float area_kept, float thr, bool thr_positive) {
     const float tly = np_max(tested.x, kept.x), tlx = np_max(tested.y, kept.y);
     const float bry = np_min(tested.z, kept.z), brx = np_min(tested.w, kept.w);
+    const bool overlap = tly < bry && tlx < brx;
+    if (thr_positive && !overlap) return false;
     const float prod = __fmul_rn(__fsub_rn(bry, tly), __fsub_rn(brx, tlx));
-    const float inter = __fmul_rn(prod, (tly < bry && tlx < brx) ? 1.0f : 0.0f);
+    const float inter = __fmul_rn(prod, overlap ? 1.0f : 0.0f);
     const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_tested, area_kept), inter));
     return iou >= thr;      // NaN compares false: not suppressed
 }

@@ -137,6 +137,109 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
     }
 }
 
+// Ring, second thread mapping, for SMALL matrices (S*HW*4 below ~64 KB): instead of splitting the
+// rows of one matrix over G thread groups (which costs a merge and a barrier per matrix), the G
+// groups take G different matrices.  Thread (j, cv) owns float4 column cv of matrix j of the
+// current item for ALL rows, so there is nothing to merge and no barrier at all; each ring stage
+// holds `rows` rows of each of the M = G matrices, brought in by M bulk copies issued by the
+// lanes of the producer warp.
+__global__ void __launch_bounds__(1024, 1)
+limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* ring = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t* empty = full + p.stages;
+
+    const int tid = threadIdx.x;
+    const int n_cons = p.threads_padded;
+    const int n_mats = g.B * g.E;
+    const int M = p.G;
+    const int n_items = (n_mats + M - 1) / M;
+    const uint32_t slot_bytes = (uint32_t)p.rows * g.HW * 4u;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], n_cons / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (tid >= n_cons) {
+        // ---------------- producer warp: lane j fetches the rows of matrix j ----------------
+        const int lane = tid - n_cons;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int m = item * M + lane;
+            const int nm = min(M, n_mats - item * M);
+            const int b = m / g.E, ei = m - b * g.E;
+            const float* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                const int rows = min(p.rows, g.S - c * p.rows);
+                const uint32_t bytes = (uint32_t)rows * g.HW * 4u;
+                if (lane == 0) mbar_arrive_expect_tx(&full[stage], bytes * nm);
+                __syncwarp();
+                if (lane < nm)
+                    bulk_g2s(ring + (size_t)stage * p.stage_bytes + (size_t)lane * slot_bytes,
+                             src + (size_t)c * p.rows * g.HW, bytes, &full[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int j = tid / p.CV, cv = tid - j * p.CV;
+    const int lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int m = item * M + j;
+        const bool active = tid < p.threads && m < n_mats;
+        float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+        int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+        for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait(&full[stage], phase);
+            if (active) {
+                const int rows = min(p.rows, g.S - c * p.rows);
+                const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
+                int a = c * p.rows;
+                int r = 0;
+#pragma unroll 1
+                for (; r + 3 < rows; r += 4, a += 4) {
+                    const float4 v0 = col[(size_t)r * p.CV];
+                    const float4 v1 = col[(size_t)(r + 1) * p.CV];
+                    const float4 v2 = col[(size_t)(r + 2) * p.CV];
+                    const float4 v3 = col[(size_t)(r + 3) * p.CV];
+                    argmax_step(b0, i0, v0.x, a); argmax_step(b1, i1, v0.y, a);
+                    argmax_step(b2, i2, v0.z, a); argmax_step(b3, i3, v0.w, a);
+                    argmax_step(b0, i0, v1.x, a + 1); argmax_step(b1, i1, v1.y, a + 1);
+                    argmax_step(b2, i2, v1.z, a + 1); argmax_step(b3, i3, v1.w, a + 1);
+                    argmax_step(b0, i0, v2.x, a + 2); argmax_step(b1, i1, v2.y, a + 2);
+                    argmax_step(b2, i2, v2.z, a + 2); argmax_step(b3, i3, v2.w, a + 2);
+                    argmax_step(b0, i0, v3.x, a + 3); argmax_step(b1, i1, v3.y, a + 3);
+                    argmax_step(b2, i2, v3.z, a + 3); argmax_step(b3, i3, v3.w, a + 3);
+                }
+                for (; r < rows; ++r, ++a) {
+                    const float4 v = col[(size_t)r * p.CV];
+                    argmax_step(b0, i0, v.x, a); argmax_step(b1, i1, v.y, a);
+                    argmax_step(b2, i2, v.z, a); argmax_step(b3, i3, v.w, a);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (active) {
+            const uint32_t lo = (uint32_t)i0 | ((uint32_t)i1 << 16), hi = (uint32_t)i2 | ((uint32_t)i3 << 16);
+            *reinterpret_cast<uint2*>(amax + (size_t)m * g.HW + 4 * cv) = make_uint2(lo, hi);
+        }
+    }
+}
+
 // Variant without the ring: one CTA per matrix, 128-bit streaming loads straight to registers.
 // Kept as the measured alternative (ppn_tune "argmax.variant" = 1).
 __global__ void __launch_bounds__(1024, 1)
@@ -282,54 +385,59 @@ __device__ __forceinline__ unsigned long long score_key(float s, int idx) {
     return ((unsigned long long)u << 32) | (unsigned)idx;
 }
 
-__global__ void __launch_bounds__(256)
-nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score, const int32_t* __restrict__ count,
-                int stride, float thr, int limit, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int prob = blockIdx.x;
-    const int n = min(count[prob], stride);
+struct NmsSmem {
+    float4* sbox;                 // [stride] boxes in visiting order
+    unsigned long long* key;      // [stride] sort keys of the unsorted list
+    float* sarea;                 // [stride]
+    int32_t* sidx;                // [stride] index into the unsorted list
+    unsigned* mask;               // [n * ceil(n/32)]
+};
+
+__device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int stride) {
+    NmsSmem s;
+    s.sbox = reinterpret_cast<float4*>(base);
+    s.key = reinterpret_cast<unsigned long long*>(s.sbox + stride);
+    s.sarea = reinterpret_cast<float*>(s.key + stride);
+    s.sidx = reinterpret_cast<int32_t*>(s.sarea + stride);
+    s.mask = reinterpret_cast<unsigned*>(s.sidx + stride);
+    return s;
+}
+
+// Whole CTA.  Precondition: s.key[0..n) holds the keys of the n unsorted boxes `ubox` (global or
+// shared) and a __syncthreads() has made them visible.  Writes out[pos] = map ? map[idx] : idx for
+// the kept boxes in visiting order and returns their number (valid in warp 0 only).
+__device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, int n, float thr, int limit,
+                                        int32_t* __restrict__ out, const int32_t* map) {
     const int tid = threadIdx.x, T = blockDim.x;
-    int32_t* out = keep_idx + (size_t)prob * stride;
-    if (n <= 0) { if (tid == 0) keep_count[prob] = 0; return; }
     const int Wd = (n + 31) >> 5;
-
-    float4* sbox = reinterpret_cast<float4*>(smem);                              // [stride] sorted boxes
-    unsigned long long* key = reinterpret_cast<unsigned long long*>(sbox + stride);  // [stride]
-    float* sarea = reinterpret_cast<float*>(key + stride);                       // [stride]
-    int32_t* sidx = reinterpret_cast<int32_t*>(sarea + stride);                  // [stride] original index
-    unsigned* mask = reinterpret_cast<unsigned*>(sidx + stride);                 // [n * Wd]
-
-    const float4* pbox = box + (size_t)prob * stride;
-    for (int i = tid; i < n; i += T)
-        key[i] = score ? score_key(score[(size_t)prob * stride + i], i) : (unsigned long long)(unsigned)(n - 1 - i);
-    __syncthreads();
     for (int i = tid; i < n; i += T) {
-        const unsigned long long mine = key[i];
+        const unsigned long long mine = s.key[i];
+        const float4 bx = ubox[i];
         int rank = 0;
-        for (int j = 0; j < n; ++j) rank += (key[j] > mine);
-        const float4 bx = pbox[i];
-        sbox[rank] = bx;
-        sarea[rank] = box_area(bx);
-        sidx[rank] = i;
+        for (int j = 0; j < n; ++j) rank += (s.key[j] > mine);
+        s.sbox[rank] = bx;
+        s.sarea[rank] = box_area(bx);
+        s.sidx[rank] = i;
     }
     __syncthreads();
+    const bool thr_pos = thr > 0.0f;
     for (int item = tid; item < n * Wd; item += T) {
         const int wj = item / n, i = item - wj * n;
         unsigned bitsw = 0;
         if (wj >= (i >> 5)) {
-            const float4 bi = sbox[i];
-            const float ai = sarea[i];
+            const float4 bi = s.sbox[i];
+            const float ai = s.sarea[i];
             const int j0 = wj << 5;
             const int jend = min(32, n - j0);
             for (int t = 0; t < jend; ++t) {
                 const int j = j0 + t;
-                if (j > i && suppresses(sbox[j], sarea[j], bi, ai, thr)) bitsw |= 1u << t;
+                if (j > i && suppresses(s.sbox[j], s.sarea[j], bi, ai, thr, thr_pos)) bitsw |= 1u << t;
             }
         }
-        mask[(size_t)i * Wd + wj] = bitsw;
+        s.mask[(size_t)i * Wd + wj] = bitsw;
     }
     __syncthreads();
-    if (tid >= 32) return;
+    if (tid >= 32) return 0;
     const int lane = tid;
     unsigned removed = 0;            // lane l holds word l of the removed set (n <= 1024)
     int m = 0;
@@ -338,7 +446,7 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
         unsigned cur = __shfl_sync(0xffffffffu, removed, w);
         const int i0 = w << 5;
         const int nb = min(32, n - i0);
-        const unsigned diag = (lane < nb) ? mask[(size_t)(i0 + lane) * Wd + w] : 0u;
+        const unsigned diag = (lane < nb) ? s.mask[(size_t)(i0 + lane) * Wd + w] : 0u;
         unsigned kept = 0;
         for (int t = 0; t < nb; ++t) {
             const unsigned d = __shfl_sync(0xffffffffu, diag, t);
@@ -351,17 +459,90 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
             kept = trimmed;
             done = true;
         }
-        if ((kept >> lane) & 1u) out[m + __popc(kept & ((1u << lane) - 1u))] = sidx[i0 + lane];
+        if ((kept >> lane) & 1u) {
+            const int idx = s.sidx[i0 + lane];
+            out[m + __popc(kept & ((1u << lane) - 1u))] = map ? map[idx] : idx;
+        }
         m += __popc(kept);
         if (lane > w && lane < Wd) {
             for (unsigned rest = kept; rest;) {
                 const int t = __ffs(rest) - 1;
                 rest &= rest - 1;
-                removed |= mask[(size_t)(i0 + t) * Wd + lane];
+                removed |= s.mask[(size_t)(i0 + t) * Wd + lane];
             }
         }
     }
-    if (lane == 0) keep_count[prob] = m;
+    return m;
+}
+
+__global__ void __launch_bounds__(256)
+nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score, const int32_t* __restrict__ count,
+                int stride, float thr, int limit, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int prob = blockIdx.x;
+    const int n = min(count[prob], stride);
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (n <= 0) { if (tid == 0) keep_count[prob] = 0; return; }
+    const NmsSmem s = nms_carve(smem, stride);
+    for (int i = tid; i < n; i += T)
+        s.key[i] = score ? score_key(score[(size_t)prob * stride + i], i) : (unsigned long long)(unsigned)(n - 1 - i);
+    __syncthreads();
+    const int m = nms_core(s, box + (size_t)prob * stride, n, thr, limit, keep_idx + (size_t)prob * stride, nullptr);
+    if (tid == 0) keep_count[prob] = m;
+}
+
+// K1 + K2 fused for the whole-path call: one CTA per (image, part) decodes the part's cells,
+// compacts the candidates into SHARED memory (never to HBM) and suppresses them right there; what
+// leaves the kernel is the list of surviving root CELLS in visiting order.  All six values of a
+// cell are loaded up front so the CTA pays one HBM round trip.
+__global__ void __launch_bounds__(256)
+decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
+                  int32_t* __restrict__ keep_cell, int32_t* __restrict__ keep_count) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int warp_tot[8];
+    __shared__ int base_s;
+    float4* ubox = reinterpret_cast<float4*>(smem);                         // [HW] candidate boxes, cell order
+    int32_t* ucell = reinterpret_cast<int32_t*>(ubox + g.HW);               // [HW]
+    const NmsSmem s = nms_carve(reinterpret_cast<unsigned char*>(ucell + ((g.HW + 3) & ~3)), g.HW);
+    const int b = blockIdx.x, k = blockIdx.y;
+    const float* img = head + (size_t)b * g.img_stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < g.HW; c0 += blockDim.x) {
+        const int c = c0 + tid;
+        float d = 0.0f;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool hit = false;
+        if (c < g.HW) {
+            d = delta_at(img, g, k, c);
+            bx = box_at(img, g, k, c);                       // loads issued before d is tested
+            hit = d > det_thr;                               // strict, datatest.py:89
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s, total = 0;
+        for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) {
+            const int t = warp_tot[wi];
+            if (wi < warp) off += t;
+            total += t;
+        }
+        if (hit) {
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            ucell[slot] = c;
+            ubox[slot] = bx;
+            s.key[slot] = score_key(d, slot);                // ties: larger candidate index (= larger cell) first
+        }
+        __syncthreads();
+        if (tid == 0) base_s += total;
+        __syncthreads();
+    }
+    const int n = base_s;
+    const size_t list = ((size_t)b * n_parts + k) * g.HW;
+    if (n == 0) { if (tid == 0) keep_count[(size_t)b * n_parts + k] = 0; return; }
+    const int m = nms_core(s, ubox, n, nms_thr, 0, keep_cell + list, ucell);
+    if (tid == 0) keep_count[(size_t)b * n_parts + k] = m;
 }
 
 // Lists longer than PPN_MAX_CELLS: no bitmask; the CTA visits boxes in order and, for every box
@@ -401,7 +582,7 @@ nms_global_kernel(const float4* __restrict__ box, const float* __restrict__ scor
             const int oj = out[j];
             if (oj >= 0) {
                 const float4 bj = pbox[oj];
-                if (suppresses(bj, box_area(bj), bi, ai, thr)) out[j] = oj | (int)0x80000000;
+                if (suppresses(bj, box_area(bj), bi, ai, thr, thr > 0.0f)) out[j] = oj | (int)0x80000000;
             }
         }
         __syncthreads();
@@ -413,45 +594,71 @@ nms_global_kernel(const float4* __restrict__ box, const float* __restrict__ scor
 }
 
 // =========================================================================================
-// K4 — tree parse, one CTA per image, one thread per surviving root
+// K4 — tree parse, one CTA per image
 // =========================================================================================
-// The arg-max map and delta = resp*conf of every part are staged in shared memory, so each of
-// the <= 25 dependent limb steps costs a shared-memory read instead of an HBM round trip.
+// resp, conf (adjacent channel groups: ONE contiguous range) and the image's arg-max map are
+// staged in shared memory by two bulk copies (TMA) on one mbarrier — a single HBM round trip —
+// so each of the <= 25 dependent limb steps costs shared-memory reads instead of HBM ones.
+// Phase A: one thread per surviving root walks the track orders and takes its output slot
+// (ordered compaction of the humans that pass min_num_keypoints).  Phase B: ALL threads write
+// the humans out, one (human, part) pair each, so the scattered x/y/w/h reads of the boxes are
+// in flight together and the stores are contiguous.
+// `use_tma` = 0 (shapes whose byte ranges are not 16-byte multiples): cooperative loads instead.
 __global__ void __launch_bounds__(128)
 tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
                   const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
                   const int32_t* __restrict__ keep_idx, const int32_t* __restrict__ keep_count,
                   int32_t* __restrict__ h_count, int32_t* __restrict__ h_root, int32_t* __restrict__ h_cell,
-                  float* __restrict__ h_score, float4* __restrict__ h_box, int R) {
+                  float* __restrict__ h_score, float4* __restrict__ h_box, int R, int use_tma) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float* s_delta = reinterpret_cast<float*>(smem);                                  // [K*HW]
-    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_delta + (size_t)g.K * g.HW);     // [E*HW] (+pad)
-    int16_t* s_pos = reinterpret_cast<int16_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [K][T]
+    const int KHW = g.K * g.HW;
+    float* s_resp = reinterpret_cast<float*>(smem);                                    // [K*HW]
+    float* s_conf = s_resp + KHW;                                                      // [K*HW]
+    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_conf + KHW);                      // [E*HW] (+pad)
+    int16_t* s_pos = reinterpret_cast<int16_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [T][K]
+    __shared__ __align__(8) uint64_t bar;
     __shared__ int warp_tot[4];
     __shared__ int base_s;
+    __shared__ int s_slot[128];
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const float* img = head + (size_t)b * g.img_stride;
     const int n_keep = keep_count[(size_t)b * n_parts];
     if (n_keep == 0) { if (tid == 0) h_count[b] = 0; return; }
-
-    for (int i = tid; i < g.K * g.HW; i += T) s_delta[i] = __fmul_rn(__ldg(img + i), __ldg(img + (size_t)g.K * g.HW + i));
     const uint16_t* am = amax + (size_t)b * g.E * g.HW;
-    for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
-    if (tid == 0) base_s = 0;
-    __syncthreads();
 
-    const int32_t* cells = cand_cell + (size_t)b * n_parts * g.HW;
+    if (use_tma) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+            const uint32_t bytes_rc = (uint32_t)KHW * 8u, bytes_am = (uint32_t)g.E * g.HW * 2u;
+            mbar_arrive_expect_tx(&bar, bytes_rc + bytes_am);
+            bulk_g2s(s_resp, img, bytes_rc, &bar);
+            if (bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
+            base_s = 0;
+        }
+    } else {
+        for (int i = tid; i < 2 * KHW; i += T) s_resp[i] = __ldg(img + i);
+        for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
+        if (tid == 0) base_s = 0;
+    }
+    // the root cells do not depend on the staged data: fetch them while the copies fly
     const int32_t* keep = keep_idx + (size_t)b * n_parts * g.HW;
+    const int32_t* cells = cand_cell ? cand_cell + (size_t)b * n_parts * g.HW : nullptr;
+    int first_root = -1;
+    if (tid < n_keep) first_root = cells ? cells[keep[tid]] : keep[tid];
+    __syncthreads();                                   // barrier init / cooperative loads visible
+    if (use_tma) mbar_wait(&bar, 0);
+
+    int16_t* my_pos = s_pos + tid * g.K;
     for (int r0 = 0; r0 < n_keep; r0 += T) {
         const int r = r0 + tid;
         bool valid = false;
-        int root = -1;
         if (r < n_keep) {
-            root = cells[keep[r]];
-            for (int t = 0; t < g.K; ++t) s_pos[t * T + tid] = -1;
-            s_pos[tid] = (int16_t)root;
+            const int root = r0 == 0 ? first_root : (cells ? cells[keep[r]] : keep[r]);
+            for (int t = 0; t < g.K; ++t) my_pos[t] = -1;
+            my_pos[0] = (int16_t)root;
             for (int cidx = 0; cidx < ch.n_chains; ++cidx) {
                 int cur = root;
                 for (int q = ch.off[cidx]; q < ch.off[cidx + 1]; ++q) {
@@ -462,13 +669,13 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
                     const int jh = ih + dy - g.off_h, jw = iw + dx - g.off_w;
                     if (jh < 0 || jw < 0 || jh >= g.H || jw >= g.W) break;      // datatest.py:118
                     const int j = jh * g.W + jw;
-                    if (s_delta[t * g.HW + j] < thr) break;                    // datatest.py:121
-                    s_pos[t * T + tid] = (int16_t)j;
+                    if (__fmul_rn(s_resp[t * g.HW + j], s_conf[t * g.HW + j]) < thr) break;   // datatest.py:121
+                    my_pos[t] = (int16_t)j;
                     cur = j;
                 }
             }
             int present = 0;
-            for (int t = 1; t < g.K; ++t) present += (s_pos[t * T + tid] >= 0);
+            for (int t = 1; t < g.K; ++t) present += (my_pos[t] >= 0);
             valid = min_kp <= present;                                          // datatest.py:129
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -481,15 +688,19 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             total += t;
         }
         const int slot = off + __popc(bal & ((1u << lane) - 1u));
-        if (valid && slot < R) {
-            const size_t hbase = (size_t)b * R + slot;
-            h_root[hbase] = root;
-            for (int t = 0; t < g.K; ++t) {
-                const int c = s_pos[t * T + tid];
-                h_cell[hbase * g.K + t] = c;
-                h_score[hbase * g.K + t] = c >= 0 ? s_delta[t * g.HW + c] : 0.0f;
-                h_box[hbase * g.K + t] = c >= 0 ? box_at(img, g, t, c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        s_slot[tid] = (valid && slot < R) ? slot : -1;
+        __syncthreads();
+        const int n_round = min(T, n_keep - r0);
+        for (int pair = tid; pair < n_round * g.K; pair += T) {
+            const int lr = pair / g.K, t = pair - lr * g.K;
+            const int sl = s_slot[lr];
+            if (sl < 0) continue;
+            const int c = s_pos[lr * g.K + t];
+            const size_t o = ((size_t)b * R + sl) * g.K + t;
+            if (t == 0) h_root[(size_t)b * R + sl] = c;
+            h_cell[o] = c;
+            h_score[o] = c >= 0 ? __fmul_rn(s_resp[t * g.HW + c], s_conf[t * g.HW + c]) : 0.0f;
+            h_box[o] = c >= 0 ? box_at(img, g, t, c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
         if (tid == 0) base_s += total;
@@ -501,7 +712,7 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
 // =========================================================================================
 // launchers
 // =========================================================================================
-struct DeviceInfo { int sms = 0; int smem_optin = 0; size_t tma = 0, ldg = 48 * 1024, nms = 48 * 1024, tree = 48 * 1024; };
+struct DeviceInfo { int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 48 * 1024, ldg = 48 * 1024, nms = 48 * 1024, tree = 48 * 1024; };
 static DeviceInfo g_dev[64];
 
 // Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
@@ -531,27 +742,50 @@ static cudaError_t ensure_smem(F kernel, size_t want, size_t* have) {
     return e;
 }
 
-bool plan_argmax(const Geom& g, const Tuning& t, ArgmaxPlan* p) {
+bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     if (g.HW % 4 != 0 || g.HW / 4 > 992) return false;
     p->CV = g.HW / 4;
+    const int row_bytes = g.HW * 4;
     int G = t.argmax_threads / p->CV;
     if (G < 1) G = 1;
-    if (G > g.S) G = g.S;
     while (G > 1 && p->CV * G > 992) --G;
+    // thread groups split the rows of one matrix (mode 0) or take one small matrix each (mode 1)
+    const bool small = (size_t)g.S * row_bytes <= 64 * 1024;
+    p->split_mats = (t.argmax_split < 0 ? (small && G > 1) : (t.argmax_split != 0)) ? 1 : 0;
+    if (p->split_mats) {
+        if (G > 32) G = 32;                               // one producer lane per matrix
+        if (G > g.B * g.E) G = g.B * g.E;
+        // items are dealt round-robin to `grid` persistent CTAs: among G/2..G matrices per item take
+        // the count whose last wave is fullest (cfg2: 8 -> 960 items, 6.5 waves, 7 % idle; 4 -> 12.97)
+        const long long n_mats = (long long)g.B * g.E;
+        const long long grid = (long long)sms * (t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm);
+        int bestM = G;
+        double best_eff = 0.0;
+        for (int M = G; M >= (G + 1) / 2 && M >= 1; --M) {
+            const long long items = (n_mats + M - 1) / M;
+            const long long waves = (items + grid - 1) / grid;
+            const double eff = (double)n_mats / (double)(waves * grid * M);
+            if (eff > best_eff + 0.02) { best_eff = eff; bestM = M; }
+        }
+        G = bestM;
+    } else if (G > g.S) {
+        G = g.S;
+    }
     p->G = G;
     p->threads = p->CV * G;
     p->threads_padded = (p->threads + 31) & ~31;
-    const int row_bytes = g.HW * 4;
-    int max_rows = t.argmax_stage_bytes / row_bytes;
+    const int per_row = p->split_mats ? row_bytes * G : row_bytes;     // ring bytes per row index
+    int max_rows = t.argmax_stage_bytes / per_row;
     if (max_rows < 1) max_rows = 1;
     if (max_rows > g.S) max_rows = g.S;
     p->chunks = (g.S + max_rows - 1) / max_rows;
     p->rows = (g.S + p->chunks - 1) / p->chunks;
     p->chunks = (g.S + p->rows - 1) / p->rows;
-    p->stage_bytes = (uint32_t)((p->rows * row_bytes + 127) & ~127);
+    p->stage_bytes = (uint32_t)(((size_t)p->rows * per_row + 127) & ~(size_t)127);
     p->stages = t.argmax_stages;
     p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
-    p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * G * g.HW * sizeof(Partial) + (size_t)2 * p->stages * sizeof(uint64_t);
+    p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * p->stages * sizeof(uint64_t) +
+                    (p->split_mats ? 0 : (size_t)2 * G * g.HW * sizeof(Partial));
     return true;
 }
 
@@ -562,7 +796,7 @@ cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g,
     const int n_mats = g.B * g.E;
     if (n_mats == 0) return cudaSuccess;
     ArgmaxPlan p;
-    const bool vec_ok = plan_argmax(g, t, &p) && ((reinterpret_cast<uintptr_t>(head) & 15) == 0);
+    const bool vec_ok = plan_argmax(g, t, d->sms, &p) && ((reinterpret_cast<uintptr_t>(head) & 15) == 0);
     if (vec_ok && t.argmax_variant == 0) {
         // shrink the ring until it fits the opt-in shared memory (split between resident CTAs)
         const size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
@@ -571,14 +805,26 @@ cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g,
             p.smem_bytes -= p.stage_bytes + 2 * sizeof(uint64_t);
         }
         if (p.smem_bytes <= budget) {
-            if ((e = ensure_smem(limb_argmax_tma_kernel, p.smem_bytes, &d->tma)) != cudaSuccess) return e;
             int grid = d->sms * p.ctas_per_sm;
-            if (grid > n_mats) grid = n_mats;
-            limb_argmax_tma_kernel<<<grid, p.threads_padded + 32, p.smem_bytes, st>>>(head, amax, g, p);
+            if (p.split_mats) {
+                const int n_items = (n_mats + p.G - 1) / p.G;
+                if (grid > n_items) grid = n_items;
+                if ((e = ensure_smem(limb_argmax_tma_multi_kernel, p.smem_bytes, &d->tma_multi)) != cudaSuccess) return e;
+                limb_argmax_tma_multi_kernel<<<grid, p.threads_padded + 32, p.smem_bytes, st>>>(head, amax, g, p);
+            } else {
+                if (grid > n_mats) grid = n_mats;
+                if ((e = ensure_smem(limb_argmax_tma_kernel, p.smem_bytes, &d->tma)) != cudaSuccess) return e;
+                limb_argmax_tma_kernel<<<grid, p.threads_padded + 32, p.smem_bytes, st>>>(head, amax, g, p);
+            }
             return cudaGetLastError();
         }
     }
     if (vec_ok) {
+        if (p.split_mats) {                     // the direct-load kernel always splits rows
+            Tuning rows_mode = t;
+            rows_mode.argmax_split = 0;
+            plan_argmax(g, rows_mode, d->sms, &p);
+        }
         const size_t smem = (size_t)p.G * g.HW * sizeof(Partial);
         if ((e = ensure_smem(limb_argmax_ldg_kernel, smem, &d->ldg)) != cudaSuccess) return e;
         limb_argmax_ldg_kernel<<<n_mats, p.threads_padded, smem, st>>>(head, amax, g, p);
@@ -635,8 +881,26 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
     return cudaGetLastError();
 }
 
+size_t decode_nms_smem_bytes(const Geom& g) {
+    return (size_t)g.HW * sizeof(float4) + (size_t)((g.HW + 3) & ~3) * sizeof(int32_t) + nms_smem_bytes(g.HW);
+}
+
+cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st) {
+    if (g.B == 0 || n_parts == 0) return cudaSuccess;
+    DeviceInfo* d = nullptr;
+    cudaError_t e = device_info(&d);
+    if (e != cudaSuccess) return e;
+    const size_t smem = decode_nms_smem_bytes(g);
+    if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
+    if ((e = ensure_smem(decode_nms_kernel, smem, &d->decode_nms)) != cudaSuccess) return e;
+    dim3 grid(g.B, n_parts);
+    decode_nms_kernel<<<grid, 256, smem, st>>>(head, g, n_parts, det_thr, nms_thr, keep_cell, keep_count);
+    return cudaGetLastError();
+}
+
 size_t tree_parse_smem_bytes(const Geom& g, int threads) {
-    return (size_t)g.K * g.HW * sizeof(float) + ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
+    return (size_t)2 * g.K * g.HW * sizeof(float) + ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
            (size_t)g.K * threads * sizeof(int16_t);
 }
 
@@ -652,8 +916,14 @@ cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable
     const size_t smem = tree_parse_smem_bytes(g, threads);
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(tree_parse_kernel, smem, &d->tree)) != cudaSuccess) return e;
+    // bulk copies need 16-byte sizes and sources: resp+conf is 8*K*HW bytes at image offset
+    // 4*C*HW*b, the arg-max map 2*E*HW bytes at offset 2*E*HW*b
+    const bool tma_ok = ((size_t)g.K * g.HW * 8) % 16 == 0 && (g.img_stride * 4) % 16 == 0 &&
+                        ((size_t)g.E * g.HW * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(head) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(amax) & 15) == 0;
     tree_parse_kernel<<<g.B, threads, smem, st>>>(head, g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count,
-                                                  h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R);
+                                                  h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R,
+                                                  tma_ok ? 1 : 0);
     return cudaGetLastError();
 }
 

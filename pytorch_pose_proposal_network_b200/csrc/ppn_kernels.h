@@ -10,7 +10,9 @@ struct Tuning {
     int argmax_stages = 5;
     int argmax_threads = 320;          // target consumer threads per CTA
     int argmax_ctas_per_sm = 1;
+    int argmax_split = -1;             // -1 auto, 0 = groups split rows, 1 = groups take one matrix each
     int host_chunk_images = 64;
+    int parse_overlap = 1;             // run decode + NMS on a side stream beside the arg-max
 };
 
 struct ArgmaxPlan {
@@ -20,13 +22,14 @@ struct ArgmaxPlan {
     int threads_padded;   // rounded up to whole warps
     int rows;             // rows per ring stage
     int chunks;           // stages per matrix = ceil(S / rows)
+    int split_mats;       // 1: the G groups take G different matrices (no merge), 0: they split rows
     int stages;           // ring depth
     int ctas_per_sm;
     uint32_t stage_bytes;
     size_t smem_bytes;
 };
 
-bool plan_argmax(const Geom& g, const Tuning& t, ArgmaxPlan* p);
+bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p);
 
 cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st);
 
@@ -35,6 +38,10 @@ cudaError_t launch_decode_candidates(const float* head, const Geom& g, int n_par
 
 cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
                        float thr, int limit, int32_t* keep_idx, int32_t* keep_count, cudaStream_t st);
+
+// fused K1+K2 of the whole-path call: surviving root cells per (image, part), nothing else
+cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st);
 
 cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* ry, size_t n, int H, int W,
                               float gridW, float gridH, cudaStream_t st);

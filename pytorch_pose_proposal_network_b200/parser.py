@@ -9,6 +9,7 @@ reference's ``(humans, scores)`` lists of dicts (datatest.py:98-132) on request.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import List, Optional, Tuple
 
@@ -124,9 +125,23 @@ class PoseParser:
         self.n_nms_parts = int(n_nms_parts)
         self.c = _CConfig(cfg, self.n_nms_parts)
         self._ws = None
+        self._ws_need = {}            # B -> workspace bytes (ppn_workspace_bytes is pure arithmetic)
+        self._shapes = {}             # B -> PPNShape
         self._out = None
         self._out_B = 0
         self._host_scratch = None
+
+    def _guard(self):
+        """Make the parser's device current for the C call (no-op when it already is)."""
+        if torch.cuda.current_device() == self.device.index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
+
+    def _shape(self, B: int) -> _lib.PPNShape:
+        s = self._shapes.get(B)
+        if s is None:
+            s = self._shapes[B] = self.c.shape(B)
+        return s
 
     # ---- buffers --------------------------------------------------------------------- #
     def _check_head(self, head: torch.Tensor) -> int:
@@ -138,11 +153,14 @@ class PoseParser:
         return head.shape[0]
 
     def _workspace(self, B: int) -> torch.Tensor:
-        need = C.c_size_t()
-        shape = self.c.shape(B)
-        _lib.check(self.lib.ppn_workspace_bytes(C.byref(shape), C.byref(self.c.params), C.byref(need)), "ppn_workspace_bytes")
-        if self._ws is None or self._ws.numel() < need.value:
-            self._ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+        need = self._ws_need.get(B)
+        if need is None:
+            n = C.c_size_t()
+            _lib.check(self.lib.ppn_workspace_bytes(C.byref(self._shape(B)), C.byref(self.c.params), C.byref(n)),
+                       "ppn_workspace_bytes")
+            need = self._ws_need[B] = n.value
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
         return self._ws
 
     def alloc_output(self, B: int, device=None, pin: bool = False) -> PackedHumans:
@@ -177,10 +195,12 @@ class PoseParser:
             out = o if self._out_B == B else PackedHumans(self.cfg, o.count[:B], o.root_cell[:B], o.part_cell[:B],
                                                           o.part_score[:B], o.part_box[:B])
         ws = self._workspace(B)
-        shape, hs = self.c.shape(B), self._humans_struct(out)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.ppn_parse(_ptr(head), C.byref(shape), C.byref(self.c.params), C.byref(hs),
-                                          _ptr(ws), ws.numel(), _stream_ptr(self.device)), "ppn_parse")
+        hs = self._humans_struct(out)
+        with self._guard():
+            rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B)), C.byref(self.c.params), C.byref(hs),
+                                    ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            raise _lib.PPNError(rc, "ppn_parse")
         return out
 
     def launches_per_parse(self, B: int) -> int:

@@ -158,27 +158,52 @@ def test_batch_matches_c_oracle(preset, dist, B):
     assert_packed_equals_oracle(host.numpy(), ref, B)
 
 
-@pytest.mark.parametrize("variant,stage_bytes,stages,threads,ctas", [
-    (0, 32768, 5, 320, 1), (0, 4096, 3, 96, 2), (0, 65536, 2, 640, 1), (0, 16384, 8, 256, 2), (1, 32768, 5, 320, 1),
-    (1, 32768, 5, 64, 1)])
+TUNE_DEFAULTS = dict(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=5, argmax_threads=320,
+                     argmax_ctas_per_sm=1, argmax_split=-1)
+
+
+@pytest.mark.parametrize("variant,stage_bytes,stages,threads,ctas,split", [
+    (0, 32768, 5, 320, 1, -1), (0, 4096, 3, 96, 2, 0), (0, 65536, 2, 640, 1, 0), (0, 16384, 8, 256, 2, 0),
+    (0, 32768, 4, 320, 1, 1), (0, 8192, 3, 160, 2, 1), (0, 65536, 3, 992, 1, 1), (0, 2048, 6, 64, 1, 1),
+    (1, 32768, 5, 320, 1, -1), (1, 32768, 5, 64, 1, 1)])
 @pytest.mark.parametrize("preset", ["cfg2", "cfg4", "native"])
-def test_limb_argmax_every_tuning(preset, variant, stage_bytes, stages, threads, ctas):
-    """The arg-max kernel under every ring shape / thread split, against the C restatement."""
+def test_limb_argmax_every_tuning(preset, variant, stage_bytes, stages, threads, ctas, split):
+    """The arg-max kernel under every ring shape / thread mapping, against the C restatement."""
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PRESETS
     from pytorch_pose_proposal_network_b200.parser import PoseParser
     cfg = PRESETS[preset]()
     g = O.Geometry.of(cfg)
-    B = 3 if preset == "native" else 7
+    B = 3 if preset == "native" else 7          # 7 x 15 = 105 matrices: a ragged last item in split-matrix mode
     head = synth.make_head(g, "U", seed=7, B=B)
     want = np.stack([c_oracle.limb_argmax(img, g) for img in head]).astype(np.uint16)
     _lib.tune(argmax_variant=variant, argmax_stage_bytes=stage_bytes, argmax_stages=stages, argmax_threads=threads,
-              argmax_ctas_per_sm=ctas)
+              argmax_ctas_per_sm=ctas, argmax_split=split)
     try:
         got = PoseParser(cfg).limb_argmax(torch.from_numpy(head).cuda()).cpu().numpy()
     finally:
-        _lib.tune(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=5, argmax_threads=320, argmax_ctas_per_sm=1)
+        _lib.tune(**TUNE_DEFAULTS)
     assert np.array_equal(got, want)
+
+
+def test_overlap_off_gives_same_result():
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PPNConfig.mpii16()
+    g = O.Geometry.of(cfg)
+    head = synth.make_head(g, "U", seed=9, B=20)
+    ref = c_oracle.parse_batch(head, g, n_threads=8)
+    dev = torch.from_numpy(head).cuda()
+    for overlap in (0, 1):
+        _lib.tune(parse_overlap=overlap)
+        try:
+            parser = PoseParser(cfg)
+            for _ in range(3):                     # back-to-back calls reuse the workspace
+                packed = parser.parse(dev)
+            assert_packed_equals_oracle(packed.numpy(), ref, 20)
+        finally:
+            _lib.tune(parse_overlap=1)
 
 
 @pytest.mark.parametrize("W,H,sW,sH", [(13, 13, 9, 9), (5, 7, 3, 5), (10, 6, 7, 7), (31, 33, 3, 3)])
@@ -214,13 +239,13 @@ def test_argmax_nan_tie_signed_zero():
     e[0, :, 4] = [np.inf, np.nan, np.inf, 0, 0, 0, 0, 0, 0]
     e[1, :, 5] = [np.nan] * 9
     want = e.reshape(g.E, g.S, g.H, g.W).argmax(1).astype(np.uint16)
-    for threads in (320, 8):              # several row groups (merge path) and one
-        from pytorch_pose_proposal_network_b200 import _lib
-        _lib.tune(argmax_threads=max(threads, 32))
+    from pytorch_pose_proposal_network_b200 import _lib
+    for split in (0, 1):                  # row-split (merge path) and matrix-split mappings
+        _lib.tune(argmax_split=split)
         try:
             got = PoseParser(cfg).limb_argmax(torch.from_numpy(out).cuda()).cpu().numpy()[0]
         finally:
-            _lib.tune(argmax_threads=320)
+            _lib.tune(argmax_split=-1)
         assert np.array_equal(got, want)
 
 
