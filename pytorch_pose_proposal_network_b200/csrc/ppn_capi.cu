@@ -75,6 +75,9 @@ ppn::Geom make_geom(const PPNShape* s) {
     g.gridW = (float)s->gridW; g.gridH = (float)s->gridH; g.inW = (float)s->inW; g.inH = (float)s->inH;
     g.img_stride = (size_t)g.C * g.HW;
     g.limb_off = (size_t)6 * g.K * g.HW;
+    auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
+    g.magic_W = magic(g.W);
+    g.magic_K = magic(g.K);
     return g;
 }
 
@@ -97,6 +100,19 @@ int make_chains(const PPNShape* s, const PPNParams* p, ppn::ChainTable* ch) {
         ch->limb[q] = (uint8_t)p->chain_limb[q];
         ch->part[q] = (uint8_t)p->chain_part[q];
     }
+    // Do the track orders form a tree?  Then a part's cell does not depend on which chain reaches
+    // it, and the kernel may walk the chains of one root concurrently (config.py:67-80 does).
+    int limb_of[256], pred_of[256];
+    for (int t = 0; t < 256; ++t) limb_of[t] = pred_of[t] = -1;
+    ch->parallel_ok = 1;
+    for (int c = 0; c < p->n_chains && ch->parallel_ok; ++c)
+        for (int q = p->chain_off[c]; q < p->chain_off[c + 1]; ++q) {
+            const int t = p->chain_part[q], e = p->chain_limb[q];
+            const int pred = q == p->chain_off[c] ? 0 : p->chain_part[q - 1];
+            if (t == 0) { ch->parallel_ok = 0; break; }
+            if (limb_of[t] < 0) { limb_of[t] = e; pred_of[t] = pred; }
+            else if (limb_of[t] != e || pred_of[t] != pred) { ch->parallel_ok = 0; break; }
+        }
     return PPN_OK;
 }
 

@@ -12,6 +12,7 @@ namespace ppn {
 // Track orders (config.py:67-80) carried by value in kernel arguments.
 struct ChainTable {
     int32_t n_chains;
+    int32_t parallel_ok;    // 1: every part has one limb and one predecessor, chains may be walked concurrently
     uint8_t off[33];        // PPN_MAX_CHAINS + 1
     uint8_t limb[192];      // PPN_MAX_CHAIN_STEPS
     uint8_t part[192];
@@ -23,6 +24,7 @@ struct Geom {               // per-launch constants derived from PPNShape
     float gridW, gridH, inW, inH;
     size_t img_stride;      // C*HW floats
     size_t limb_off;        // 6*K*HW floats
+    uint32_t magic_W, magic_K;   // ceil(2^32 / d) for exact x / d, 0 <= x < 65536 (0 when d == 1)
 };
 
 // ---- the reference's cell arithmetic --------------------------------------------------

@@ -390,6 +390,7 @@ struct NmsSmem {
     unsigned long long* key;      // [stride] sort keys of the unsorted list
     float* sarea;                 // [stride]
     int32_t* sidx;                // [stride] index into the unsorted list
+    int32_t* rank;                // [stride] rank accumulators of the split counting sort
     unsigned* mask;               // [n * ceil(n/32)]
 };
 
@@ -399,46 +400,83 @@ __device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int stride) {
     s.key = reinterpret_cast<unsigned long long*>(s.sbox + stride);
     s.sarea = reinterpret_cast<float*>(s.key + stride);
     s.sidx = reinterpret_cast<int32_t*>(s.sarea + stride);
-    s.mask = reinterpret_cast<unsigned*>(s.sidx + stride);
+    s.rank = s.sidx + stride;
+    s.mask = reinterpret_cast<unsigned*>(s.rank + stride);
     return s;
 }
 
+// Same answer as suppresses() when no coordinate is NaN: fmaxf/fminf differ from numpy's
+// maximum/minimum only in NaN propagation and in the sign of a zero result, and a zero's sign
+// cannot change `tl < br` nor the final `iou >= thr` ("NMS exactness").
+__device__ __forceinline__ bool suppresses_finite(const float4 tested, float area_tested,
+                                                  const float4 kept, float area_kept, float thr, bool thr_positive) {
+    const float tly = fmaxf(tested.x, kept.x), tlx = fmaxf(tested.y, kept.y);
+    const float bry = fminf(tested.z, kept.z), brx = fminf(tested.w, kept.w);
+    const bool overlap = tly < bry && tlx < brx;
+    if (thr_positive && !overlap) return false;
+    const float prod = __fmul_rn(__fsub_rn(bry, tly), __fsub_rn(brx, tlx));
+    const float inter = __fmul_rn(prod, overlap ? 1.0f : 0.0f);
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_tested, area_kept), inter));
+    return iou >= thr;
+}
+
 // Whole CTA.  Precondition: s.key[0..n) holds the keys of the n unsorted boxes `ubox` (global or
-// shared) and a __syncthreads() has made them visible.  Writes out[pos] = map ? map[idx] : idx for
-// the kept boxes in visiting order and returns their number (valid in warp 0 only).
+// shared), s.rank[0..n) is zero, and a __syncthreads() has made both visible.  Writes
+// out[pos] = map ? map[idx] : idx for the kept boxes in visiting order and returns their number
+// (valid in warp 0 only).
+//   1. counting sort by key: every box's rank = number of larger keys, the key range split over
+//      T/n threads per box;  2. suppression bitmask, one WARP per (row i, 32-column word): lane t
+//      tests pair (i, 32*wj + t) and the word is the ballot;  3. one warp scans in visiting order,
+//      32 boxes at a time: the serial dependency lives in the 32x32 diagonal block (registers,
+//      fully unrolled), then the rows of the boxes kept in that block are OR-ed into the per-lane
+//      `removed` words with independent shared-memory loads.
 __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, int n, float thr, int limit,
                                         int32_t* __restrict__ out, const int32_t* map) {
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = T >> 5;
     const int Wd = (n + 31) >> 5;
-    for (int i = tid; i < n; i += T) {
+    // ---- 1. rank -------------------------------------------------------------------------
+    int split = T / n;
+    split = split < 1 ? 1 : (split > 8 ? 8 : split);
+    const int chunk = (n + split - 1) / split;
+    for (int item = tid; item < n * split; item += T) {
+        const int part = item / n, i = item - part * n;
         const unsigned long long mine = s.key[i];
-        const float4 bx = ubox[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) rank += (s.key[j] > mine);
-        s.sbox[rank] = bx;
-        s.sarea[rank] = box_area(bx);
-        s.sidx[rank] = i;
+        const int j1 = min(n, (part + 1) * chunk);
+        int r = 0;
+        for (int j = part * chunk; j < j1; ++j) r += (s.key[j] > mine);
+        if (split == 1) s.rank[i] = r; else atomicAdd(&s.rank[i], r);
     }
     __syncthreads();
+    bool has_nan = false;
+    for (int i = tid; i < n; i += T) {
+        const float4 bx = ubox[i];
+        const int r = s.rank[i];
+        has_nan |= (bx.x != bx.x) | (bx.y != bx.y) | (bx.z != bx.z) | (bx.w != bx.w);
+        s.sbox[r] = bx;
+        s.sarea[r] = box_area(bx);
+        s.sidx[r] = i;
+    }
+    const bool any_nan = __syncthreads_or(has_nan);
+    // ---- 2. mask -------------------------------------------------------------------------
     const bool thr_pos = thr > 0.0f;
-    for (int item = tid; item < n * Wd; item += T) {
-        const int wj = item / n, i = item - wj * n;
-        unsigned bitsw = 0;
-        if (wj >= (i >> 5)) {
-            const float4 bi = s.sbox[i];
-            const float ai = s.sarea[i];
-            const int j0 = wj << 5;
-            const int jend = min(32, n - j0);
-            for (int t = 0; t < jend; ++t) {
-                const int j = j0 + t;
-                if (j > i && suppresses(s.sbox[j], s.sarea[j], bi, ai, thr, thr_pos)) bitsw |= 1u << t;
+    for (int i = warp; i < n; i += n_warps) {
+        const float4 bi = s.sbox[i];
+        const float ai = s.sarea[i];
+        for (int wj = i >> 5; wj < Wd; ++wj) {
+            const int j = (wj << 5) + lane;
+            bool bit = false;
+            if (j > i && j < n) {
+                const float4 bj = s.sbox[j];
+                bit = any_nan ? suppresses(bj, s.sarea[j], bi, ai, thr, thr_pos)
+                              : suppresses_finite(bj, s.sarea[j], bi, ai, thr, thr_pos);
             }
+            const unsigned word = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) s.mask[(size_t)i * Wd + wj] = word;
         }
-        s.mask[(size_t)i * Wd + wj] = bitsw;
     }
     __syncthreads();
     if (tid >= 32) return 0;
-    const int lane = tid;
+    // ---- 3. scan -------------------------------------------------------------------------
     unsigned removed = 0;            // lane l holds word l of the removed set (n <= 1024)
     int m = 0;
     bool done = false;
@@ -446,12 +484,17 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         unsigned cur = __shfl_sync(0xffffffffu, removed, w);
         const int i0 = w << 5;
         const int nb = min(32, n - i0);
+        const unsigned valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
         const unsigned diag = (lane < nb) ? s.mask[(size_t)(i0 + lane) * Wd + w] : 0u;
         unsigned kept = 0;
-        for (int t = 0; t < nb; ++t) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
             const unsigned d = __shfl_sync(0xffffffffu, diag, t);
-            if (!((cur >> t) & 1u)) { kept |= 1u << t; cur |= d; }
+            const unsigned take = (~cur >> t) & 1u;
+            kept |= take << t;
+            cur |= d & (0u - take);
         }
+        kept &= valid;
         if (limit > 0 && m + __popc(kept) >= limit) {      // datatest.py:154-155
             int need = limit - m;
             unsigned trimmed = 0;
@@ -465,17 +508,22 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         }
         m += __popc(kept);
         if (lane > w && lane < Wd) {
-            for (unsigned rest = kept; rest;) {
-                const int t = __ffs(rest) - 1;
-                rest &= rest - 1;
-                removed |= s.mask[(size_t)(i0 + t) * Wd + lane];
+            const unsigned* row = s.mask + (size_t)i0 * Wd + lane;
+            unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+            for (int t = 0; t < 32; t += 4) {
+                if ((kept >> t) & 1u) a0 |= row[(size_t)t * Wd];
+                if ((kept >> (t + 1)) & 1u) a1 |= row[(size_t)(t + 1) * Wd];
+                if ((kept >> (t + 2)) & 1u) a2 |= row[(size_t)(t + 2) * Wd];
+                if ((kept >> (t + 3)) & 1u) a3 |= row[(size_t)(t + 3) * Wd];
             }
+            removed |= (a0 | a1) | (a2 | a3);
         }
     }
     return m;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score, const int32_t* __restrict__ count,
                 int stride, float thr, int limit, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -484,8 +532,10 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
     const int tid = threadIdx.x, T = blockDim.x;
     if (n <= 0) { if (tid == 0) keep_count[prob] = 0; return; }
     const NmsSmem s = nms_carve(smem, stride);
-    for (int i = tid; i < n; i += T)
+    for (int i = tid; i < n; i += T) {
         s.key[i] = score ? score_key(score[(size_t)prob * stride + i], i) : (unsigned long long)(unsigned)(n - 1 - i);
+        s.rank[i] = 0;
+    }
     __syncthreads();
     const int m = nms_core(s, box + (size_t)prob * stride, n, thr, limit, keep_idx + (size_t)prob * stride, nullptr);
     if (tid == 0) keep_count[prob] = m;
@@ -495,11 +545,11 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
 // compacts the candidates into SHARED memory (never to HBM) and suppresses them right there; what
 // leaves the kernel is the list of surviving root CELLS in visiting order.  All six values of a
 // cell are loaded up front so the CTA pays one HBM round trip.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
                   int32_t* __restrict__ keep_cell, int32_t* __restrict__ keep_count) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ int warp_tot[8];
+    __shared__ int warp_tot[16];
     __shared__ int base_s;
     float4* ubox = reinterpret_cast<float4*>(smem);                         // [HW] candidate boxes, cell order
     int32_t* ucell = reinterpret_cast<int32_t*>(ubox + g.HW);               // [HW]
@@ -508,6 +558,7 @@ decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det
     const float* img = head + (size_t)b * g.img_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) base_s = 0;
+    for (int i = tid; i < g.HW; i += blockDim.x) s.rank[i] = 0;
     __syncthreads();
     for (int c0 = 0; c0 < g.HW; c0 += blockDim.x) {
         const int c = c0 + tid;
@@ -598,28 +649,69 @@ nms_global_kernel(const float4* __restrict__ box, const float* __restrict__ scor
 // =========================================================================================
 // resp, conf (adjacent channel groups: ONE contiguous range) and the image's arg-max map are
 // staged in shared memory by two bulk copies (TMA) on one mbarrier — a single HBM round trip —
-// so each of the <= 25 dependent limb steps costs shared-memory reads instead of HBM ones.
-// Phase A: one thread per surviving root walks the track orders and takes its output slot
-// (ordered compaction of the humans that pass min_num_keypoints).  Phase B: ALL threads write
-// the humans out, one (human, part) pair each, so the scattered x/y/w/h reads of the boxes are
-// in flight together and the stores are contiguous.
-// `use_tma` = 0 (shapes whose byte ranges are not 16-byte multiples): cooperative loads instead.
-__global__ void __launch_bounds__(128)
+// so each dependent limb step costs shared-memory reads instead of HBM ones.  The kernel is a
+// latency chain, so the chain is kept short:
+//   * window index -> (dy - off_h, dx - off_w) comes from a shared-memory table, the walk keeps
+//     (row, col) as state: no integer division on the dependent path;
+//   * when the track orders form a tree (every part has one limb and one predecessor — checked on
+//     the host), the chains of a root are walked by DIFFERENT threads: they write identical
+//     values where they share a prefix, and the critical path is the longest chain (7 steps for
+//     the reference skeleton) instead of the sum (25);
+//   * the write-out is one (human, part) pair per thread, so the scattered x/y/w/h reads of the
+//     boxes are in flight together and the stores are contiguous.
+// Roots are handled 64 per round.  `use_tma` = 0 (byte ranges not 16-byte multiples): cooperative loads.
+constexpr int kRootsPerRound = 64;
+constexpr int kMaxDyxTable = 2048;
+
+__device__ __forceinline__ int fast_div(int x, uint32_t magic) {      // exact for 0 <= x < 65536
+    return magic ? (int)__umulhi((unsigned)x, magic) : x;
+}
+
+__device__ __forceinline__ void walk_chain(const ChainTable& ch, int cidx, int root, const Geom& g, float thr,
+                                           const float* s_resp, const float* s_conf, const uint16_t* s_amax,
+                                           const int32_t* s_dyx, bool use_tab, int16_t* my_pos) {
+    int ih = fast_div(root, g.magic_W), iw = root - ih * g.W;
+    for (int q = ch.off[cidx]; q < ch.off[cidx + 1]; ++q) {
+        const int ei = ch.limb[q], t = ch.part[q];
+        const int a = s_amax[ei * g.HW + ih * g.W + iw];
+        int jh, jw;
+        if (use_tab) {
+            const int d = s_dyx[a];
+            jh = ih + (d >> 16);
+            jw = iw + (int)(int16_t)(d & 0xffff);
+        } else {
+            const int dy = a / g.sW, dx = a - dy * g.sW;
+            jh = ih + dy - g.off_h;
+            jw = iw + dx - g.off_w;
+        }
+        if (jh < 0 || jw < 0 || jh >= g.H || jw >= g.W) break;                         // datatest.py:118
+        const int j = jh * g.W + jw;
+        if (__fmul_rn(s_resp[t * g.HW + j], s_conf[t * g.HW + j]) < thr) break;        // datatest.py:121
+        my_pos[t] = (int16_t)j;
+        ih = jh;
+        iw = jw;
+    }
+}
+
+__global__ void __launch_bounds__(256)
 tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
                   const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
                   const int32_t* __restrict__ keep_idx, const int32_t* __restrict__ keep_count,
                   int32_t* __restrict__ h_count, int32_t* __restrict__ h_root, int32_t* __restrict__ h_cell,
                   float* __restrict__ h_score, float4* __restrict__ h_box, int R, int use_tma) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int RR = kRootsPerRound;
     const int KHW = g.K * g.HW;
     float* s_resp = reinterpret_cast<float*>(smem);                                    // [K*HW]
     float* s_conf = s_resp + KHW;                                                      // [K*HW]
     uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_conf + KHW);                      // [E*HW] (+pad)
-    int16_t* s_pos = reinterpret_cast<int16_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [T][K]
+    int16_t* s_pos = reinterpret_cast<int16_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [RR][K]
+    int32_t* s_dyx = reinterpret_cast<int32_t*>(s_pos + (((size_t)RR * g.K + 1) & ~(size_t)1));     // [S] if small
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int warp_tot[4];
+    __shared__ int warp_tot[2];
     __shared__ int base_s;
-    __shared__ int s_slot[128];
+    __shared__ int s_slot[RR];
+    __shared__ int s_root[RR];
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -627,6 +719,7 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
     const int n_keep = keep_count[(size_t)b * n_parts];
     if (n_keep == 0) { if (tid == 0) h_count[b] = 0; return; }
     const uint16_t* am = amax + (size_t)b * g.E * g.HW;
+    const bool use_tab = g.S <= kMaxDyxTable;
 
     if (use_tma) {
         if (tid == 0) {
@@ -636,66 +729,67 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             mbar_arrive_expect_tx(&bar, bytes_rc + bytes_am);
             bulk_g2s(s_resp, img, bytes_rc, &bar);
             if (bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
-            base_s = 0;
         }
     } else {
         for (int i = tid; i < 2 * KHW; i += T) s_resp[i] = __ldg(img + i);
         for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
-        if (tid == 0) base_s = 0;
     }
-    // the root cells do not depend on the staged data: fetch them while the copies fly
+    if (tid == 0) base_s = 0;
+    if (use_tab)
+        for (int a = tid; a < g.S; a += T) {
+            const int dy = a / g.sW, dx = a - dy * g.sW;
+            s_dyx[a] = ((dy - g.off_h) << 16) | ((dx - g.off_w) & 0xffff);
+        }
     const int32_t* keep = keep_idx + (size_t)b * n_parts * g.HW;
     const int32_t* cells = cand_cell ? cand_cell + (size_t)b * n_parts * g.HW : nullptr;
-    int first_root = -1;
-    if (tid < n_keep) first_root = cells ? cells[keep[tid]] : keep[tid];
-    __syncthreads();                                   // barrier init / cooperative loads visible
-    if (use_tma) mbar_wait(&bar, 0);
+    const int n_par = ch.parallel_ok ? ch.n_chains : 1;
+    unsigned bal = 0;
+    bool valid = false;
 
-    int16_t* my_pos = s_pos + tid * g.K;
-    for (int r0 = 0; r0 < n_keep; r0 += T) {
-        const int r = r0 + tid;
-        bool valid = false;
-        if (r < n_keep) {
-            const int root = r0 == 0 ? first_root : (cells ? cells[keep[r]] : keep[r]);
-            for (int t = 0; t < g.K; ++t) my_pos[t] = -1;
-            my_pos[0] = (int16_t)root;
-            for (int cidx = 0; cidx < ch.n_chains; ++cidx) {
-                int cur = root;
-                for (int q = ch.off[cidx]; q < ch.off[cidx + 1]; ++q) {
-                    const int ei = ch.limb[q], t = ch.part[q];
-                    const int a = s_amax[ei * g.HW + cur];
-                    const int dy = a / g.sW, dx = a - dy * g.sW;
-                    const int ih = cur / g.W, iw = cur - ih * g.W;
-                    const int jh = ih + dy - g.off_h, jw = iw + dx - g.off_w;
-                    if (jh < 0 || jw < 0 || jh >= g.H || jw >= g.W) break;      // datatest.py:118
-                    const int j = jh * g.W + jw;
-                    if (__fmul_rn(s_resp[t * g.HW + j], s_conf[t * g.HW + j]) < thr) break;   // datatest.py:121
-                    my_pos[t] = (int16_t)j;
-                    cur = j;
+    for (int r0 = 0; r0 < n_keep; r0 += RR) {
+        const int n_round = min(RR, n_keep - r0);
+        for (int i = tid; i < n_round * g.K; i += T) s_pos[i] = -1;
+        int root = -1;
+        if (tid < n_round) root = cells ? cells[keep[r0 + tid]] : keep[r0 + tid];   // flies with the bulk copies
+        __syncthreads();                     // s_pos cleared; barrier init / cooperative loads visible
+        if (tid < n_round) { s_root[tid] = root; s_pos[tid * g.K] = (int16_t)root; }
+        if (r0 == 0 && use_tma) mbar_wait(&bar, 0);
+        __syncthreads();
+        for (int item = tid; item < n_par * RR; item += T) {
+            const int cidx = item / RR, lr = item - cidx * RR;
+            if (lr < n_round) {
+                int16_t* my_pos = s_pos + lr * g.K;
+                if (ch.parallel_ok) {
+                    walk_chain(ch, cidx, s_root[lr], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+                } else {
+                    for (int c = 0; c < ch.n_chains; ++c)
+                        walk_chain(ch, c, s_root[lr], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
                 }
             }
-            int present = 0;
-            for (int t = 1; t < g.K; ++t) present += (my_pos[t] >= 0);
-            valid = min_kp <= present;                                          // datatest.py:129
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, valid);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
         __syncthreads();
-        int off = base_s, total = 0;
-        for (int wi = 0; wi < (T >> 5); ++wi) {
-            const int t = warp_tot[wi];
-            if (wi < warp) off += t;
-            total += t;
+        if (tid < RR) {
+            valid = false;
+            if (tid < n_round) {
+                int present = 0;
+                for (int t = 1; t < g.K; ++t) present += (s_pos[tid * g.K + t] >= 0);
+                valid = min_kp <= present;                                          // datatest.py:129
+            }
+            bal = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) warp_tot[warp] = __popc(bal);
         }
-        const int slot = off + __popc(bal & ((1u << lane) - 1u));
-        s_slot[tid] = (valid && slot < R) ? slot : -1;
         __syncthreads();
-        const int n_round = min(T, n_keep - r0);
+        const int total = warp_tot[0] + warp_tot[1];
+        if (tid < RR) {
+            const int slot = base_s + (warp == 1 ? warp_tot[0] : 0) + __popc(bal & ((1u << lane) - 1u));
+            s_slot[tid] = (valid && slot < R) ? slot : -1;
+        }
+        __syncthreads();
         for (int pair = tid; pair < n_round * g.K; pair += T) {
-            const int lr = pair / g.K, t = pair - lr * g.K;
+            const int lr = fast_div(pair, g.magic_K), t = pair - lr * g.K;
             const int sl = s_slot[lr];
             if (sl < 0) continue;
-            const int c = s_pos[lr * g.K + t];
+            const int c = s_pos[pair];
             const size_t o = ((size_t)b * R + sl) * g.K + t;
             if (t == 0) h_root[(size_t)b * R + sl] = c;
             h_cell[o] = c;
@@ -704,15 +798,15 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
         }
         __syncthreads();
         if (tid == 0) base_s += total;
-        __syncthreads();
     }
+    __syncthreads();
     if (tid == 0) h_count[b] = base_s;
 }
 
 // =========================================================================================
 // launchers
 // =========================================================================================
-struct DeviceInfo { int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 48 * 1024, ldg = 48 * 1024, nms = 48 * 1024, tree = 48 * 1024; };
+struct DeviceInfo { int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 0, ldg = 0, nms = 0, tree = 0; };
 static DeviceInfo g_dev[64];
 
 // Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
@@ -734,11 +828,19 @@ static cudaError_t device_info(DeviceInfo** out) {
     return cudaSuccess;
 }
 
+// First use of a kernel on a device (and whenever it needs more dynamic shared memory than it was
+// last granted): raise its limit and ask for the largest shared-memory carveout.  The carveout is
+// an SM-wide setting; if the ring kernel were given just enough for itself, no CTA of another
+// kernel could become resident beside it and the side-stream overlap in ppn_parse would silently
+// serialise (measured: it did).
 template <typename F>
 static cudaError_t ensure_smem(F kernel, size_t want, size_t* have) {
-    if (want <= *have) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
-    if (e == cudaSuccess) *have = want;
+    if (*have != 0 && want <= *have) return cudaSuccess;
+    const size_t grant = want > 48 * 1024 ? want : 48 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grant);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) *have = grant;
     return e;
 }
 
@@ -860,7 +962,7 @@ cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float
 
 size_t nms_smem_bytes(int stride) {
     const size_t words = (size_t)stride * ((stride + 31) / 32);
-    return (size_t)stride * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float) + sizeof(int32_t)) + words * sizeof(unsigned);
+    return (size_t)stride * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float) + 2 * sizeof(int32_t)) + words * sizeof(unsigned);
 }
 
 cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
@@ -872,8 +974,8 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
     const size_t smem = nms_smem_bytes(stride);
     if (stride <= 1024 && smem <= (size_t)d->smem_optin) {
         if ((e = ensure_smem(nms_smem_kernel, smem, &d->nms)) != cudaSuccess) return e;
-        nms_smem_kernel<<<n_problems, 256, smem, st>>>(reinterpret_cast<const float4*>(box), score, count, stride, thr,
-                                                       limit, keep_idx, keep_count);
+        nms_smem_kernel<<<n_problems, stride <= 256 ? 256 : 512, smem, st>>>(reinterpret_cast<const float4*>(box), score, count,
+                                                                             stride, thr, limit, keep_idx, keep_count);
         return cudaGetLastError();
     }
     nms_global_kernel<<<n_problems, 1024, 0, st>>>(reinterpret_cast<const float4*>(box), score, count, stride, thr,
@@ -895,13 +997,14 @@ cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, flo
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(decode_nms_kernel, smem, &d->decode_nms)) != cudaSuccess) return e;
     dim3 grid(g.B, n_parts);
-    decode_nms_kernel<<<grid, 256, smem, st>>>(head, g, n_parts, det_thr, nms_thr, keep_cell, keep_count);
+    decode_nms_kernel<<<grid, g.HW <= 256 ? 256 : 512, smem, st>>>(head, g, n_parts, det_thr, nms_thr, keep_cell, keep_count);
     return cudaGetLastError();
 }
 
-size_t tree_parse_smem_bytes(const Geom& g, int threads) {
+size_t tree_parse_smem_bytes(const Geom& g) {
     return (size_t)2 * g.K * g.HW * sizeof(float) + ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
-           (size_t)g.K * threads * sizeof(int16_t);
+           (((size_t)kRootsPerRound * g.K + 1) & ~(size_t)1) * sizeof(int16_t) +
+           (g.S <= kMaxDyxTable ? (size_t)g.S * sizeof(int32_t) : 0);
 }
 
 cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
@@ -912,8 +1015,8 @@ cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
     if (e != cudaSuccess) return e;
-    const int threads = 128;
-    const size_t smem = tree_parse_smem_bytes(g, threads);
+    const int threads = 256;
+    const size_t smem = tree_parse_smem_bytes(g);
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(tree_parse_kernel, smem, &d->tree)) != cudaSuccess) return e;
     // bulk copies need 16-byte sizes and sources: resp+conf is 8*K*HW bytes at image offset

@@ -48,7 +48,7 @@ cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* 
 cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float* rh, size_t n, float inW, float inH,
                                 cudaStream_t st);
 
-size_t tree_parse_smem_bytes(const Geom& g, int threads);
+size_t tree_parse_smem_bytes(const Geom& g);
 
 cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,

@@ -297,6 +297,22 @@ def test_edge_cases_match_oracle():
     assert ref["counts"][0, 0] == 0 and ref["counts"][1, 0] == 0 and ref["counts"][2, 0] == 1
 
 
+def test_track_orders_that_are_not_a_tree():
+    """A part reached through different limbs in different track orders: the reference's rule is
+    'the later chain overwrites' (datatest.py:124); the kernel must then walk chains in order."""
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    graphs = (((0, 1), (1, 2)), ((2, 3), (3, 2)), ((0,), (4,)))      # part 2 via limb 1 and via limb 3; part 4 via limb 0 (!= part 1's)
+    cfg = PPNConfig(K=5, E=4, insize=(128, 128), outsize=(8, 8), local_grid_size=(5, 5), directed_graphs=graphs,
+                    detection_thresh=0.05)
+    g = O.Geometry.of(cfg)
+    head = synth.make_head(g, "U", seed=11, B=9)
+    ref = c_oracle.parse_batch(head, g)
+    assert ref["counts"][:, 2].sum() > 20
+    packed = PoseParser(cfg).parse(torch.from_numpy(head).cuda()).numpy()
+    assert_packed_equals_oracle(packed, ref, 9)
+
+
 def test_tie_rule_is_larger_cell_first():
     """Equal root scores: the reference's order is undefined (unstable argsort); ours is pinned."""
     from pytorch_pose_proposal_network_b200.parser import PoseParser
