@@ -171,7 +171,7 @@ def run_ours(args, rank, world, local_rank):
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PRESETS
     from pytorch_pose_proposal_network_b200.parser import PackedHumans, PoseParser
-    from pytorch_pose_proposal_network_b200.sharded import gather_packed
+    from pytorch_pose_proposal_network_b200.sharded import PoseGatherer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
@@ -190,7 +190,8 @@ def run_ours(args, rank, world, local_rank):
     # humans per image kept in the packed output; H*W can never overflow.  For N > 1 the gather
     # ships a trimmed stride (checked against the true counts after the run).
     parser = PoseParser(cfg, device=dev, max_humans=args.max_humans or None)
-    gather_R = min(parser.R, args.gather_humans)
+    cap_records = B * args.gather_humans            # dense records shipped per rank and step (overflow is checked)
+    gatherer = PoseGatherer(parser, B, cap_records, group_steps=args.gather_every) if world > 1 else None
 
     # distinct input batches, rotated so that no step finds its input in the 126 MB L2
     batch_bytes = B * cfg.bytes_per_image
@@ -205,11 +206,19 @@ def run_ours(args, rank, world, local_rank):
         bufs.append(t)
     outs = [parser.alloc_output(B) for _ in range(2)]
 
+    released = [None, None]
+
     def step(i):
+        if released[i % 2] is not None:             # the gather's pack kernel has read this output buffer
+            torch.cuda.current_stream(dev).wait_event(released[i % 2])
         out = parser.parse(bufs[i % n_buf], out=outs[i % 2])
-        if world > 1:
-            return gather_packed(out, B * world, trim_humans=gather_R)
+        if gatherer is not None:
+            released[i % 2] = gatherer.submit(out)  # side stream: pack + (every few steps) one async all_gather
         return out
+
+    def drain():
+        if gatherer is not None:
+            gatherer.finish()
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -220,18 +229,23 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank).start()
     # warm-up: W steps, then keep the GPU under the same load for ~0.4 s so that the clock
     # sampler sees loaded clocks even when the timed region is only milliseconds long
+    t_w = time.perf_counter()
     for i in range(W):
         step(i)
+    drain()
     torch.cuda.synchronize(dev)
-    t_settle = time.perf_counter()
-    extra = 0
-    while time.perf_counter() - t_settle < args.settle_s:
-        for i in range(8):
-            step(extra + i)
-        extra += 8
-        torch.cuda.synchronize(dev)
+    # the number of extra steps must be the SAME on every rank (each submits collectives): rank 0
+    # sizes it from its own warm-up time and broadcasts it
+    per_step = max((time.perf_counter() - t_w) / W, 1e-5)
+    n_extra = torch.tensor([min(20000, int(args.settle_s / per_step) + 1)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.broadcast(n_extra, src=0)
+    extra = int(n_extra.item())
+    for i in range(extra):
+        step(i)
+    drain()
+    torch.cuda.synchronize(dev)
 
-    _lib.profile_enable(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     t0 = time.perf_counter()
@@ -239,10 +253,29 @@ def run_ours(args, rank, world, local_rank):
     last = None
     for i in range(K):
         last = step(i)
+    drain()                                         # the timed region ends when every gather has landed
     ev1.record()
+    host_issue_ms = (time.perf_counter() - t0) * 1e3 / K     # host time to ENQUEUE a step (GPU runs behind)
     sync_all()
     t1 = time.perf_counter()
     elapsed_ms = ev0.elapsed_time(ev1)
+
+    # Per-kernel durations: the same K steps again, same inputs, with the library recording CUDA
+    # events around every kernel on its stream (ppn_profile_*).  Bracketing a kernel with events
+    # forbids the overlapped launch chain the timed region above uses, so this pass runs the three
+    # kernels back to back; its step time is reported too and is NOT the headline value.
+    _lib.profile_enable(True)
+    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Kp = min(K, 4096)
+    sync_all()
+    evp0.record()
+    for i in range(Kp):
+        last = step(i)
+    drain()
+    evp1.record()
+    sync_all()
+    t1 = time.perf_counter()
+    profiled_ms_per_step = evp0.elapsed_time(evp1) / Kp
     stage_ms, n_prof = _lib.profile_read()
     _lib.profile_enable(False)
     clocks = sampler.summary(t0, t1)
@@ -256,8 +289,14 @@ def run_ours(args, rank, world, local_rank):
     # sanity on what was produced (outside the timed region): counts must fit the gathered stride
     counts = last.count.cpu()
     humans_per_image = float(counts.float().mean())
-    if world > 1 and int(counts.max()) > gather_R:
-        raise SystemExit(f"bench.py: an image has {int(counts.max())} humans, more than --gather-humans {gather_R}")
+    if gatherer is not None:
+        for r in range(world):
+            rec = gatherer.records_of(r)
+            if rec["overflow"]:
+                raise SystemExit(f"bench.py: rank {r} produced {rec['total']} pose records, more than the {cap_records} "
+                                 f"shipped per step; raise --gather-humans")
+        mine = gatherer.records_of(rank)            # what every rank received from this rank == what it produced
+        assert int(mine["total"]) == int(counts.clamp(max=parser.R).sum()), "gathered records differ from local result"
 
     # ---- end to end through the public host-buffer call: H2D + kernels + D2H every step ----
     host_in = torch.empty(B, cfg.C, cfg.H, cfg.W, dtype=torch.float32, pin_memory=True)
@@ -294,7 +333,12 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "limb_argmax", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": limb_bytes, "avg_launch_ms": k3_ms,
-                "stage_ms_per_step": {k: v / max(n_prof, 1) for k, v in stage_ms.items()},
+                "timing": f"CUDA events around each kernel on its stream, {n_prof} steps run right after the timed region "
+                          "(events forbid the overlapped launch chain, so kernels run back to back in this pass)",
+                "stage_ms_per_step": {"limb_argmax": stage_ms["limb_argmax"] / max(n_prof, 1),
+                                      "decode_nms": stage_ms["nms"] / max(n_prof, 1),
+                                      "tree_parse": stage_ms["tree_parse"] / max(n_prof, 1)},
+                "serial_ms_per_step": profiled_ms_per_step,
                 "pipeline_gbs": B * cfg.bytes_per_image / (elapsed_ms / K * 1e-3) / 1e9,
                 "pipeline_frac": B * cfg.bytes_per_image / (elapsed_ms / K * 1e-3) / 1e9 / peak}
 
@@ -307,7 +351,11 @@ def run_ours(args, rank, world, local_rank):
                    "bytes_per_image": cfg.bytes_per_image, "input_distribution": DIST[args.config],
                    "l2": f"{n_buf} distinct input batches of {batch_bytes / 1e6:.0f} MB rotated (each larger than L2)",
                    "humans_per_image": humans_per_image, "extra_warmup_steps": extra,
-                   "pose_gather": "none (1 GPU)" if world == 1 else f"all_gather of packed poses, {gather_R} slots/image, every step"},
+                   "host_issue_ms_per_step": host_issue_ms,
+                   "pose_gather": "none (1 GPU)" if world == 1 else
+                   f"every step: device-side pack to dense records (cap {args.gather_humans}/image avg); every "
+                   f"{args.gather_every} steps one async NCCL all_gather of {args.gather_every * gatherer.nbytes / 1e6:.2f} MB "
+                   f"per rank, overlapped with the following steps; all gathers complete inside the timed region"},
         "roofline": roofline, "e2e": e2e, "clocks": clocks,
         "gpu_launches": parser.launches_per_parse(B) * K,
     }
@@ -356,7 +404,9 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(BATCH))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
     ap.add_argument("--max-humans", type=int, default=0, help="slots per image in the packed output (default H*W)")
-    ap.add_argument("--gather-humans", type=int, default=64, help="slots per image shipped by the N>1 pose gather")
+    ap.add_argument("--gather-humans", type=int, default=32,
+                    help="average pose records per image shipped by the N>1 gather (dense; overflow is detected)")
+    ap.add_argument("--gather-every", type=int, default=4, help="steps per pose all_gather (N > 1)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--settle-s", type=float, default=0.4)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)

@@ -23,7 +23,7 @@
  *   - every function returns int: 0 = ok, > 0 = a cudaError_t value, < 0 = a PPN_E_* code;
  *     ppn_strerror() turns either into text.  Nothing throws across the boundary.
  *   - device entry points only ENQUEUE work on `stream`; they never synchronise and never
- *     allocate.  The caller owns every buffer (torch tensors in the Python host layer) and
+ *     allocate (one exception: 512 bytes of work counters per device on the very first launch).  The caller owns every buffer (torch tensors in the Python host layer) and
  *     selects the device (cudaSetDevice / torch.cuda.set_device) before calling.
  *   - thread-safe for distinct streams and buffers; no global mutable state except the
  *     tuning table set by ppn_tune() (meant for benchmarking, set once before use).
@@ -138,9 +138,10 @@ int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* pa
                    const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                    const int32_t* keep_count, const PPNHumans* out, void* stream);
 
-/* The whole path on a device batch: limb arg-max on `stream`; decode+NMS fused in one kernel
- * (candidates stay in shared memory) on an internal side stream beside it; then the tree parse.
- * Results are identical to calling the four stage functions above in sequence. */
+/* The whole path on a device batch in three launches on `stream`: decode+NMS fused in one kernel
+ * (candidates stay in shared memory), the limb arg-max started beside it, and the tree parse,
+ * chained by programmatic dependent launch so that each kernel's start-up hides under its
+ * predecessor.  Results are identical to calling the four stage functions above in sequence. */
 int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
               const PPNHumans* out, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -152,6 +153,16 @@ int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params,
 int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParams* params,
                    const PPNHumans* out_host, void* dev_scratch, size_t dev_scratch_bytes);
 
+/* Dense pose records for shipping results (the multi-GPU gather): one contiguous device buffer
+ *   int32 header[2 + B] = {total records, overflow flag, count[B]}
+ *   int32 cell [cap][K], float score[cap][K], float box[cap][K][4]     (256-byte aligned blocks)
+ * image b's min(count[b], R) humans start at record sum_{i<b} min(count[i], R); records beyond
+ * `cap_records` are dropped and the overflow flag is set.  ppn_packed_bytes gives the buffer size
+ * and, if `offsets` != NULL, the byte offsets of {header, cell, score, box}. */
+int ppn_packed_bytes(int32_t B, int32_t K, int32_t cap_records, size_t* bytes, size_t* offsets /*[4] or NULL*/);
+int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_records,
+                    void* packed, size_t packed_bytes, void* stream);
+
 /* Per-stage timing of ppn_parse for benchmarks.  After ppn_profile_enable(1) every ppn_parse
  * call (up to 4096) records CUDA events on its stream at the stage boundaries;
  * ppn_profile_read() waits for them and returns the summed milliseconds of the four stages
@@ -162,7 +173,8 @@ int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
 /* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
  * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
  * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
- * "parse.overlap" (1 = decode+NMS on a side stream beside the arg-max), "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
+ * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "parse.stage_all" (-1 auto, 0, 1),
+ * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);
 int ppn_tune_get(const char* key, int32_t* value);
 

@@ -176,7 +176,10 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.threads")) t.argmax_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) t.argmax_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
     else if (!std::strcmp(key, "argmax.split")) t.argmax_split = value;
-    else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value != 0;
+    else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
+    else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value != 0;
+    else if (!std::strcmp(key, "argmax.dynamic")) t.argmax_dynamic = value != 0;
+    else if (!std::strcmp(key, "parse.stage_all")) t.parse_stage_all = value;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -192,6 +195,9 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) *value = t.argmax_ctas_per_sm;
     else if (!std::strcmp(key, "argmax.split")) *value = t.argmax_split;
     else if (!std::strcmp(key, "parse.overlap")) *value = t.parse_overlap;
+    else if (!std::strcmp(key, "argmax.tail_opt")) *value = t.argmax_tail_opt;
+    else if (!std::strcmp(key, "argmax.dynamic")) *value = t.argmax_dynamic;
+    else if (!std::strcmp(key, "parse.stage_all")) *value = t.parse_stage_all;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -304,20 +310,38 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     const ppn::Geom g = make_geom(shape);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    // Three kernels.  The limb arg-max (K3) and decode+NMS (K12) are independent; the tree parse
+    // (K4) needs both.  parse.overlap selects how they are ordered:
+    //   2  one stream, programmatic dependent launches: K12 starts, K3 starts beside it at once
+    //      (it reads nothing of K12's) and only waits for K12 before it completes; K4 starts its
+    //      prologue (staging the decode planes) under K3's tail and waits for K3 before reading the
+    //      arg-max map and the root lists.  No events, no second stream.
+    //   1  K12 on a private side stream, joined before K4.
+    //   0  serial: K3, K12, K4 (also used while ppn_profile_* brackets the stages with events,
+    //      so that the stage times are clean).
     cudaEvent_t* ev = profile_slot();
+    const int mode = ev ? 0 : g_tuning.parse_overlap;
+    if (mode == 2) {
+        bool chained = false;
+        if ((e = ppn::launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, true)) != cudaSuccess) return (int)e;
+        if ((e = ppn::launch_limb_argmax(head, amax, g, g_tuning, st, true, &chained)) != cudaSuccess) return (int)e;
+        if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr, keep_idx,
+                                        keep_count, out->count, out->root_cell, out->part_cell, out->part_score,
+                                        out->part_box, out->R, st, chained, g_tuning.parse_stage_all)) != cudaSuccess) return (int)e;
+        return PPN_OK;
+    }
     cudaStream_t side = st;
     SideLane* lane = nullptr;
-    if (g_tuning.parse_overlap) {
+    if (mode == 1) {
         if ((e = side_lane(&lane)) != cudaSuccess) return (int)e;
         side = lane->stream;
         if ((e = cudaEventRecord(lane->fork, st)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamWaitEvent(side, lane->fork, 0)) != cudaSuccess) return (int)e;
     }
-    // K3 on the caller's stream
     if (ev) cudaEventRecord(ev[0], st);
     if ((e = ppn::launch_limb_argmax(head, amax, g, g_tuning, st)) != cudaSuccess) return (int)e;
     if (ev) cudaEventRecord(ev[1], st);
-    // K1+K2 (fused: candidates never leave shared memory) beside it
+    // K1+K2 fused: candidates never leave shared memory (stage slot 1 = decode is inside slot 2)
     if (ev) { cudaEventRecord(ev[2], side); cudaEventRecord(ev[3], side); cudaEventRecord(ev[4], side); }
     if ((e = ppn::launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, side)) != cudaSuccess) return (int)e;
     if (ev) cudaEventRecord(ev[5], side);
@@ -325,13 +349,50 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
         if ((e = cudaEventRecord(lane->join, side)) != cudaSuccess) return (int)e;
         if ((e = cudaStreamWaitEvent(st, lane->join, 0)) != cudaSuccess) return (int)e;
     }
-    // K4 needs both
     if (ev) cudaEventRecord(ev[6], st);
     if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr /*keep_idx holds cells*/,
                                     keep_idx, keep_count, out->count, out->root_cell, out->part_cell, out->part_score,
-                                    out->part_box, out->R, st)) != cudaSuccess) return (int)e;
+                                    out->part_box, out->R, st, false, g_tuning.parse_stage_all)) != cudaSuccess) return (int)e;
     if (ev) cudaEventRecord(ev[7], st);
     return PPN_OK;
+}
+
+// ---- dense pose records ----------------------------------------------------------------------
+namespace {
+struct PackedLayout { size_t header, cell, score, box, total; };
+PackedLayout packed_layout(int B, int K, int cap) {
+    PackedLayout l;
+    l.header = 0;
+    l.cell = align_up((size_t)(2 + B) * sizeof(int32_t), 256);
+    l.score = l.cell + align_up((size_t)cap * K * sizeof(int32_t), 256);
+    l.box = l.score + align_up((size_t)cap * K * sizeof(float), 256);
+    l.total = l.box + align_up((size_t)cap * K * 4 * sizeof(float), 256);
+    return l;
+}
+}  // namespace
+
+int ppn_packed_bytes(int32_t B, int32_t K, int32_t cap_records, size_t* bytes, size_t* offsets) {
+    if (B < 0 || K < 1 || cap_records < 0 || !bytes) return PPN_E_BADARG;
+    const PackedLayout l = packed_layout(B, K, cap_records);
+    *bytes = l.total;
+    if (offsets) { offsets[0] = l.header; offsets[1] = l.cell; offsets[2] = l.score; offsets[3] = l.box; }
+    return PPN_OK;
+}
+
+int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_records, void* packed, size_t packed_bytes,
+                    void* stream) {
+    int rc = check_humans(humans);
+    if (rc) return rc;
+    if (B < 0 || K < 1 || cap_records < 0) return PPN_E_BADARG;
+    if (B == 0) return PPN_OK;
+    if (!packed || (reinterpret_cast<uintptr_t>(packed) & 255)) return PPN_E_BADARG;
+    const PackedLayout l = packed_layout(B, K, cap_records);
+    if (packed_bytes < l.total) return PPN_E_WORKSPACE;
+    unsigned char* p = static_cast<unsigned char*>(packed);
+    return cuda_rc(ppn::launch_pack_humans(humans->count, humans->part_cell, humans->part_score, humans->part_box, B,
+                                           humans->R, K, cap_records, reinterpret_cast<int32_t*>(p + l.header),
+                                           reinterpret_cast<int32_t*>(p + l.cell), reinterpret_cast<float*>(p + l.score),
+                                           reinterpret_cast<float*>(p + l.box), (cudaStream_t)stream));
 }
 
 int ppn_profile_enable(int32_t on) {

@@ -33,19 +33,23 @@ __device__ __forceinline__ float delta_at(const float* __restrict__ img, const G
     return __fmul_rn(__ldg(img + (size_t)k * g.HW + c), __ldg(img + (size_t)(g.K + k) * g.HW + c));
 }
 
-// (ymin, xmin, ymax, xmax) of part k at cell c  (datatest.py:63-71, 80-85)
-__device__ __forceinline__ float4 box_at(const float* __restrict__ img, const Geom& g, int k, int c) {
-    const int h = c / g.W, w = c - h * g.W;
-    const size_t HW = g.HW;
-    const float x = __ldg(img + (size_t)(2 * g.K + k) * HW + c);
-    const float y = __ldg(img + (size_t)(3 * g.K + k) * HW + c);
-    const float bw = __ldg(img + (size_t)(4 * g.K + k) * HW + c);
-    const float bh = __ldg(img + (size_t)(5 * g.K + k) * HW + c);
+// (ymin, xmin, ymax, xmax) from the four raw head values of a cell at (row h, col w)
+// (datatest.py:63-71, 80-85): two roundings for the centre (add, then multiply), one for the size,
+// an exact halving, one for each corner.
+__device__ __forceinline__ float4 box_from(float x, float y, float bw, float bh, int h, int w, const Geom& g) {
     const float rx = __fmul_rn(__fadd_rn(x, (float)w), g.gridW);
     const float ry = __fmul_rn(__fadd_rn(y, (float)h), g.gridH);
     const float hw = __fmul_rn(__fmul_rn(g.inW, bw), 0.5f);     // rw / 2 (exact halving)
     const float hh = __fmul_rn(__fmul_rn(g.inH, bh), 0.5f);
     return make_float4(__fsub_rn(ry, hh), __fsub_rn(rx, hw), __fadd_rn(ry, hh), __fadd_rn(rx, hw));
+}
+
+// the same for part k at cell c, reading the head tensor of one image
+__device__ __forceinline__ float4 box_at(const float* __restrict__ img, const Geom& g, int k, int c) {
+    const int h = c / g.W, w = c - h * g.W;
+    const size_t HW = g.HW;
+    return box_from(__ldg(img + (size_t)(2 * g.K + k) * HW + c), __ldg(img + (size_t)(3 * g.K + k) * HW + c),
+                    __ldg(img + (size_t)(4 * g.K + k) * HW + c), __ldg(img + (size_t)(5 * g.K + k) * HW + c), h, w, g);
 }
 
 // numpy's maximum / minimum: propagate NaN (datatest.py:145-146)
@@ -123,6 +127,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(evict_first) : "memory");
 }
+// Programmatic dependent launch (PDL): let the next kernel in the stream start its prologue /
+// wait until every kernel this one depends on has completed and flushed.  Both are no-ops when
+// the kernel was launched without a programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }

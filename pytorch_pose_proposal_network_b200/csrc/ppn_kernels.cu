@@ -7,6 +7,8 @@
 //   K4 tree_parse         walk the track orders from every kept root    datatest.py:103-131
 //
 // Launchers at the bottom are called by ppn_capi.cu.
+#include <mutex>
+
 #include "ppn_kernels.h"
 
 namespace ppn {
@@ -20,17 +22,24 @@ namespace ppn {
 // shared-memory ring with 1-D bulk copies (TMA engine, completion on an mbarrier), and the
 // consumer threads reduce them from shared memory.  Thread (g, cv) owns float4 column cv and
 // every G-th row of each chunk; the G partial results per column are merged once per matrix.
-// Persistent: grid = SM count x ctas_per_sm, matrices are dealt round-robin.
+// Persistent: grid = SM count x ctas_per_sm.  Work is handed out DYNAMICALLY: the producer draws the
+// next matrix from a global ticket counter and passes its index to the consumers through the ring
+// (s_item[stage], published by the mbarrier's release/acquire).  A CTA that becomes resident late —
+// e.g. because an NCCL kernel holds its SM — then simply takes fewer matrices instead of delaying its
+// fixed share (measured: static dealing lost 35 % with a concurrent all_gather), and the last wave
+// has no tail.  The last CTA to finish resets the counter for the next launch.
 
 struct Partial { float v; int32_t i; };
 
 __global__ void __launch_bounds__(1024, 1)
-limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p) {
+limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p, int pdl,
+                       int* __restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
     Partial* part = reinterpret_cast<Partial*>(smem + (size_t)p.stages * p.stage_bytes);   // [2][G][HW]
     uint64_t* full = reinterpret_cast<uint64_t*>(part + (size_t)2 * p.G * g.HW);
     uint64_t* empty = full + p.stages;
+    int* s_item = reinterpret_cast<int*>(empty + p.stages);                                // [stages]
 
     const int tid = threadIdx.x;
     const int n_cons = p.threads_padded;                 // consumer threads incl. idle lanes of the last warp
@@ -43,6 +52,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
         }
         fence_mbar_init();
     }
+    if (pdl) pdl_launch_dependents();        // the tree-parse kernel may start its prologue now
     __syncthreads();
 
     if (tid >= n_cons) {
@@ -50,11 +60,18 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
         if (tid == n_cons) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int m = blockIdx.x; m < n_mats; m += gridDim.x) {
+            for (int m = ticket ? atomicAdd(ticket, 1) : (int)blockIdx.x;; m = ticket ? atomicAdd(ticket, 1) : m + (int)gridDim.x) {
+                if (m >= n_mats) {                                   // no work left: tell the consumers
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    s_item[stage] = -1;
+                    mbar_arrive(&full[stage]);
+                    break;
+                }
                 const int b = m / g.E, ei = m - b * g.E;
                 const float* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
                 for (int c = 0; c < p.chunks; ++c) {
                     mbar_wait(&empty[stage], phase ^ 1u);
+                    if (c == 0) s_item[stage] = m;
                     const int rows = min(p.rows, g.S - c * p.rows);
                     const uint32_t bytes = (uint32_t)rows * g.HW * 4u;
                     mbar_arrive_expect_tx(&full[stage], bytes);
@@ -62,6 +79,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (ticket && atomicAdd(ticket + 1, 1) == (int)gridDim.x - 1) { ticket[0] = 0; ticket[1] = 0; }
         }
         return;
     }
@@ -72,12 +90,14 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
     const int lane = tid & 31;
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int m = blockIdx.x; m < n_mats; m += gridDim.x, ++it) {
+    for (int it = 0;; ++it) {
+        mbar_wait(&full[stage], phase);
+        const int m = s_item[stage];
+        if (m < 0) break;
         float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
         int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
         for (int c = 0; c < p.chunks; ++c) {
-            mbar_wait(&full[stage], phase);
+            if (c > 0) mbar_wait(&full[stage], phase);
             if (active) {
                 const int rows = min(p.rows, g.S - c * p.rows);
                 const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes) + cv;
@@ -135,6 +155,9 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
             // matrix it+1, which every thread reaches only after finishing this merge.
         }
     }
+    // In the PDL chain this kernel started without waiting for decode+NMS (it does not read their
+    // output); it must not COMPLETE before they do, because the tree parse waits only for us.
+    if (pdl && tid == 0) pdl_wait();
 }
 
 // Ring, second thread mapping, for SMALL matrices (S*HW*4 below ~64 KB): instead of splitting the
@@ -144,11 +167,13 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
 // holds `rows` rows of each of the M = G matrices, brought in by M bulk copies issued by the
 // lanes of the producer warp.
 __global__ void __launch_bounds__(1024, 1)
-limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p) {
+limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p, int pdl,
+                             int* __restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
     uint64_t* empty = full + p.stages;
+    int* s_item = reinterpret_cast<int*>(empty + p.stages);                 // [stages] item index, -1 = no more work
 
     const int tid = threadIdx.x;
     const int n_cons = p.threads_padded;
@@ -164,6 +189,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         }
         fence_mbar_init();
     }
+    if (pdl) pdl_launch_dependents();        // the tree-parse kernel may start its prologue now
     __syncthreads();
 
     if (tid >= n_cons) {
@@ -171,7 +197,17 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         const int lane = tid - n_cons;
         int stage = 0;
         uint32_t phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int item = blockIdx.x;
+        for (;;) {
+            if (ticket) {                                            // lane 0 draws, the warp shares
+                if (lane == 0) item = atomicAdd(ticket, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+            }
+            if (item >= n_items) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                if (lane == 0) { s_item[stage] = -1; mbar_arrive(&full[stage]); }
+                break;
+            }
             const int m = item * M + lane;
             const int nm = min(M, n_mats - item * M);
             const int b = m / g.E, ei = m - b * g.E;
@@ -180,14 +216,19 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
                 mbar_wait(&empty[stage], phase ^ 1u);
                 const int rows = min(p.rows, g.S - c * p.rows);
                 const uint32_t bytes = (uint32_t)rows * g.HW * 4u;
-                if (lane == 0) mbar_arrive_expect_tx(&full[stage], bytes * nm);
+                if (lane == 0) {
+                    if (c == 0) s_item[stage] = item;
+                    mbar_arrive_expect_tx(&full[stage], bytes * nm);
+                }
                 __syncwarp();
                 if (lane < nm)
                     bulk_g2s(ring + (size_t)stage * p.stage_bytes + (size_t)lane * slot_bytes,
                              src + (size_t)c * p.rows * g.HW, bytes, &full[stage]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
+            if (!ticket) item += gridDim.x;
         }
+        if (ticket && lane == 0 && atomicAdd(ticket + 1, 1) == (int)gridDim.x - 1) { ticket[0] = 0; ticket[1] = 0; }
         return;
     }
 
@@ -196,13 +237,16 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
     const int lane = tid & 31;
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        mbar_wait(&full[stage], phase);
+        const int item = s_item[stage];
+        if (item < 0) break;
         const int m = item * M + j;
         const bool active = tid < p.threads && m < n_mats;
         float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
         int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
         for (int c = 0; c < p.chunks; ++c) {
-            mbar_wait(&full[stage], phase);
+            if (c > 0) mbar_wait(&full[stage], phase);
             if (active) {
                 const int rows = min(p.rows, g.S - c * p.rows);
                 const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
@@ -238,6 +282,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
             *reinterpret_cast<uint2*>(amax + (size_t)m * g.HW + 4 * cv) = make_uint2(lo, hi);
         }
     }
+    if (pdl && tid == 0) pdl_wait();         // see limb_argmax_tma_kernel
 }
 
 // Variant without the ring: one CTA per matrix, 128-bit streaming loads straight to registers.
@@ -547,8 +592,9 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
 // cell are loaded up front so the CTA pays one HBM round trip.
 __global__ void __launch_bounds__(512)
 decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
-                  int32_t* __restrict__ keep_cell, int32_t* __restrict__ keep_count) {
+                  int32_t* __restrict__ keep_cell, int32_t* __restrict__ keep_count, int pdl) {
     extern __shared__ __align__(128) unsigned char smem[];
+    if (pdl) pdl_launch_dependents();        // the arg-max kernel does not need anything from this one
     __shared__ int warp_tot[16];
     __shared__ int base_s;
     float4* ubox = reinterpret_cast<float4*>(smem);                         // [HW] candidate boxes, cell order
@@ -659,8 +705,8 @@ nms_global_kernel(const float4* __restrict__ box, const float* __restrict__ scor
 //     the reference skeleton) instead of the sum (25);
 //   * the write-out is one (human, part) pair per thread, so the scattered x/y/w/h reads of the
 //     boxes are in flight together and the stores are contiguous.
-// Roots are handled 64 per round.  `use_tma` = 0 (byte ranges not 16-byte multiples): cooperative loads.
-constexpr int kRootsPerRound = 64;
+// All surviving roots of the image are handled in one pass (positions for up to H*W roots fit in
+// shared memory).  `use_tma` = 0 (byte ranges not 16-byte multiples): cooperative loads.
 constexpr int kMaxDyxTable = 2048;
 
 __device__ __forceinline__ int fast_div(int x, uint32_t magic) {      // exact for 0 <= x < 65536
@@ -693,46 +739,43 @@ __device__ __forceinline__ void walk_chain(const ChainTable& ch, int cidx, int r
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
                   const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
                   const int32_t* __restrict__ keep_idx, const int32_t* __restrict__ keep_count,
                   int32_t* __restrict__ h_count, int32_t* __restrict__ h_root, int32_t* __restrict__ h_cell,
-                  float* __restrict__ h_score, float4* __restrict__ h_box, int R, int use_tma) {
+                  float* __restrict__ h_score, float4* __restrict__ h_box, int R, int use_tma, int stage_all, int pdl) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int RR = kRootsPerRound;
     const int KHW = g.K * g.HW;
-    float* s_resp = reinterpret_cast<float*>(smem);                                    // [K*HW]
-    float* s_conf = s_resp + KHW;                                                      // [K*HW]
-    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_conf + KHW);                      // [E*HW] (+pad)
-    int16_t* s_pos = reinterpret_cast<int16_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [RR][K]
-    int32_t* s_dyx = reinterpret_cast<int32_t*>(s_pos + (((size_t)RR * g.K + 1) & ~(size_t)1));     // [S] if small
+    const int n_groups = stage_all ? 6 : 2;            // resp, conf [, x, y, w, h]: adjacent channel groups
+    float* s_resp = reinterpret_cast<float*>(smem);                                    // [n_groups][K*HW]
+    float* s_conf = s_resp + KHW;
+    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_resp + (size_t)n_groups * KHW);   // [E*HW] (+pad)
+    int32_t* s_root = reinterpret_cast<int32_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [HW]
+    int32_t* s_slot = s_root + g.HW;                                                   // [HW]
+    int32_t* s_dyx = s_slot + g.HW;                                                    // [S] if small
+    int16_t* s_pos = reinterpret_cast<int16_t*>(s_dyx + (g.S <= kMaxDyxTable ? g.S : 0));   // [HW][K]
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int warp_tot[2];
+    __shared__ int warp_tot[8];
     __shared__ int base_s;
-    __shared__ int s_slot[RR];
-    __shared__ int s_root[RR];
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const float* img = head + (size_t)b * g.img_stride;
-    const int n_keep = keep_count[(size_t)b * n_parts];
-    if (n_keep == 0) { if (tid == 0) h_count[b] = 0; return; }
     const uint16_t* am = amax + (size_t)b * g.E * g.HW;
     const bool use_tab = g.S <= kMaxDyxTable;
+    const uint32_t bytes_planes = (uint32_t)n_groups * KHW * 4u, bytes_am = (uint32_t)g.E * g.HW * 2u;
 
+    // ---- prologue: nothing here depends on the kernels before this one -----------------------
     if (use_tma) {
         if (tid == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
-            const uint32_t bytes_rc = (uint32_t)KHW * 8u, bytes_am = (uint32_t)g.E * g.HW * 2u;
-            mbar_arrive_expect_tx(&bar, bytes_rc + bytes_am);
-            bulk_g2s(s_resp, img, bytes_rc, &bar);
-            if (bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
+            mbar_arrive_expect_tx(&bar, bytes_planes + bytes_am);
+            bulk_g2s(s_resp, img, bytes_planes, &bar);
         }
     } else {
-        for (int i = tid; i < 2 * KHW; i += T) s_resp[i] = __ldg(img + i);
-        for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
+        for (int i = tid; i < n_groups * KHW; i += T) s_resp[i] = __ldg(img + i);
     }
     if (tid == 0) base_s = 0;
     if (use_tab)
@@ -740,73 +783,164 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             const int dy = a / g.sW, dx = a - dy * g.sW;
             s_dyx[a] = ((dy - g.off_h) << 16) | ((dx - g.off_w) & 0xffff);
         }
+    // ---- from here on we read what the arg-max and decode+NMS kernels wrote ---------------------
+    if (pdl) pdl_wait();
+    if (use_tma) {
+        if (tid == 0 && bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
+    } else {
+        for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
+    }
+    const int n_keep = min(keep_count[(size_t)b * n_parts], g.HW);
     const int32_t* keep = keep_idx + (size_t)b * n_parts * g.HW;
     const int32_t* cells = cand_cell ? cand_cell + (size_t)b * n_parts * g.HW : nullptr;
-    const int n_par = ch.parallel_ok ? ch.n_chains : 1;
-    unsigned bal = 0;
-    bool valid = false;
 
-    for (int r0 = 0; r0 < n_keep; r0 += RR) {
-        const int n_round = min(RR, n_keep - r0);
-        for (int i = tid; i < n_round * g.K; i += T) s_pos[i] = -1;
-        int root = -1;
-        if (tid < n_round) root = cells ? cells[keep[r0 + tid]] : keep[r0 + tid];   // flies with the bulk copies
-        __syncthreads();                     // s_pos cleared; barrier init / cooperative loads visible
-        if (tid < n_round) { s_root[tid] = root; s_pos[tid * g.K] = (int16_t)root; }
-        if (r0 == 0 && use_tma) mbar_wait(&bar, 0);
-        __syncthreads();
-        for (int item = tid; item < n_par * RR; item += T) {
-            const int cidx = item / RR, lr = item - cidx * RR;
-            if (lr < n_round) {
-                int16_t* my_pos = s_pos + lr * g.K;
-                if (ch.parallel_ok) {
-                    walk_chain(ch, cidx, s_root[lr], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
-                } else {
-                    for (int c = 0; c < ch.n_chains; ++c)
-                        walk_chain(ch, c, s_root[lr], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
-                }
+    // ---- 1. roots and cleared positions (the loads fly with the bulk copies) --------------------
+    for (int i = tid; i < n_keep * g.K; i += T) s_pos[i] = -1;
+    for (int r = tid; r < n_keep; r += T) s_root[r] = cells ? cells[keep[r]] : keep[r];
+    __syncthreads();                          // also: barrier init / cooperative loads visible
+    for (int r = tid; r < n_keep; r += T) s_pos[r * g.K] = (int16_t)s_root[r];
+    if (use_tma) mbar_wait(&bar, 0);          // on every path: never exit under an in-flight copy
+    if (n_keep == 0) { if (tid == 0) h_count[b] = 0; return; }
+    __syncthreads();
+
+    // ---- 2. walk: one thread per (chain, root) when the track orders are a tree -----------------
+    const int n_pad = (n_keep + 31) & ~31;    // whole warps share a chain: uniform chain-table reads
+    const int n_par = ch.parallel_ok ? ch.n_chains : 1;
+    for (int item = tid; item < n_par * n_pad; item += T) {
+        const int cidx = item / n_pad, r = item - cidx * n_pad;
+        if (r < n_keep) {
+            int16_t* my_pos = s_pos + r * g.K;
+            if (ch.parallel_ok) {
+                walk_chain(ch, cidx, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+            } else {
+                for (int c = 0; c < ch.n_chains; ++c)
+                    walk_chain(ch, c, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
             }
         }
-        __syncthreads();
-        if (tid < RR) {
-            valid = false;
-            if (tid < n_round) {
-                int present = 0;
-                for (int t = 1; t < g.K; ++t) present += (s_pos[tid * g.K + t] >= 0);
-                valid = min_kp <= present;                                          // datatest.py:129
-            }
-            bal = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) warp_tot[warp] = __popc(bal);
+    }
+    __syncthreads();
+
+    // ---- 3. humans with enough parts take consecutive output slots, in root order ---------------
+    for (int r0 = 0; r0 < n_keep; r0 += T) {
+        const int r = r0 + tid;
+        bool valid = false;
+        if (r < n_keep) {
+            int present = 0;
+            for (int t = 1; t < g.K; ++t) present += (s_pos[r * g.K + t] >= 0);
+            valid = min_kp <= present;                                          // datatest.py:129
         }
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
         __syncthreads();
-        const int total = warp_tot[0] + warp_tot[1];
-        if (tid < RR) {
-            const int slot = base_s + (warp == 1 ? warp_tot[0] : 0) + __popc(bal & ((1u << lane) - 1u));
-            s_slot[tid] = (valid && slot < R) ? slot : -1;
+        int off = base_s, total = 0;
+        for (int wi = 0; wi < (T >> 5); ++wi) {
+            const int v = warp_tot[wi];
+            if (wi < warp) off += v;
+            total += v;
         }
-        __syncthreads();
-        for (int pair = tid; pair < n_round * g.K; pair += T) {
-            const int lr = fast_div(pair, g.magic_K), t = pair - lr * g.K;
-            const int sl = s_slot[lr];
-            if (sl < 0) continue;
-            const int c = s_pos[pair];
-            const size_t o = ((size_t)b * R + sl) * g.K + t;
-            if (t == 0) h_root[(size_t)b * R + sl] = c;
-            h_cell[o] = c;
-            h_score[o] = c >= 0 ? __fmul_rn(s_resp[t * g.HW + c], s_conf[t * g.HW + c]) : 0.0f;
-            h_box[o] = c >= 0 ? box_at(img, g, t, c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const int slot = off + __popc(bal & ((1u << lane) - 1u));
+        if (r < n_keep) s_slot[r] = (valid && slot < R) ? slot : -1;
         __syncthreads();
         if (tid == 0) base_s += total;
     }
     __syncthreads();
+
+    // ---- 4. write-out: one (human, part) pair per thread and step, four steps in flight ----------
+    const int n_pairs = n_keep * g.K;
+    for (int p0 = tid; p0 < n_pairs; p0 += 4 * T) {
+        int cc[4], tt[4], ss[4];
+        float xs[4], ys[4], ws[4], hs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pair = p0 + u * T;
+            cc[u] = -2;                                       // -2: nothing to write
+            if (pair < n_pairs) {
+                const int r = fast_div(pair, g.magic_K), t = pair - r * g.K;
+                const int sl = s_slot[r];
+                if (sl >= 0) {
+                    cc[u] = s_pos[pair];
+                    tt[u] = t;
+                    ss[u] = sl;
+                    if (cc[u] >= 0) {
+                        const int at = t * g.HW + cc[u];
+                        if (stage_all) {
+                            xs[u] = s_resp[2 * KHW + at]; ys[u] = s_resp[3 * KHW + at];
+                            ws[u] = s_resp[4 * KHW + at]; hs[u] = s_resp[5 * KHW + at];
+                        } else {
+                            xs[u] = __ldg(img + (size_t)2 * KHW + at); ys[u] = __ldg(img + (size_t)3 * KHW + at);
+                            ws[u] = __ldg(img + (size_t)4 * KHW + at); hs[u] = __ldg(img + (size_t)5 * KHW + at);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (cc[u] == -2) continue;
+            const int c = cc[u];
+            float score = 0.0f;
+            float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c >= 0) {
+                const int at = tt[u] * g.HW + c;
+                const int h = fast_div(c, g.magic_W), w = c - h * g.W;
+                score = __fmul_rn(s_resp[at], s_conf[at]);
+                box = box_from(xs[u], ys[u], ws[u], hs[u], h, w, g);
+            }
+            const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
+            if (tt[u] == 0) h_root[human] = c;
+            h_cell[o] = c;
+            h_score[o] = score;
+            h_box[o] = box;
+        }
+    }
     if (tid == 0) h_count[b] = base_s;
+}
+
+// =========================================================================================
+// pack — dense pose records for the multi-GPU gather
+// =========================================================================================
+// Fixed-stride PPNHumans -> one contiguous buffer: header {total, overflow, count[B]} followed by
+// record arrays cell[cap][K], score[cap][K], box[cap][K][4]; image b's humans start at record
+// sum(count[0..b)).  One CTA per image; every CTA sums the counts before it (B loads, coalesced).
+__global__ void __launch_bounds__(256)
+pack_humans_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ cell, const float* __restrict__ score,
+                   const float4* __restrict__ box, int B, int R, int K, int cap,
+                   int32_t* __restrict__ header, int32_t* __restrict__ rec_cell, float* __restrict__ rec_score,
+                   float4* __restrict__ rec_box) {
+    __shared__ int red[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int before = 0;
+    for (int i = tid; i < b; i += blockDim.x) before += min(count[i], R);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) red[warp] = before;
+    __syncthreads();
+    int off = 0;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) off += red[wi];
+    const int n = min(count[b], R);
+    if (tid == 0) {
+        header[2 + b] = count[b];
+        if (b == B - 1) { header[0] = off + n; header[1] = (off + n > cap) ? 1 : 0; }
+    }
+    const int room = max(0, min(n, cap - off));          // records of this image that still fit
+    const size_t src = (size_t)b * R * K, dst = (size_t)off * K;
+    for (int i = tid; i < room * K; i += blockDim.x) {
+        rec_cell[dst + i] = cell[src + i];
+        rec_score[dst + i] = score[src + i];
+        rec_box[dst + i] = box[src + i];
+    }
 }
 
 // =========================================================================================
 // launchers
 // =========================================================================================
-struct DeviceInfo { int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 0, ldg = 0, nms = 0, tree = 0; };
+// Work counters of the ring kernels: {next ticket, finished CTAs} per stream, zero between launches
+// (the last CTA of a launch resets its pair).  Kernels on one stream never overlap, kernels on
+// different streams get different pairs.  The only memory the library ever allocates: 512 bytes
+// per device, on the first launch (so make the first call outside stream capture).
+constexpr int kTicketSlots = 64;
+struct DeviceInfo { int* tickets = nullptr; cudaStream_t slot_stream[kTicketSlots] = {}; int slots_used = 0;
+                    int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 0, ldg = 0, nms = 0, tree = 0; };
 static DeviceInfo g_dev[64];
 
 // Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
@@ -833,6 +967,23 @@ static cudaError_t device_info(DeviceInfo** out) {
 // an SM-wide setting; if the ring kernel were given just enough for itself, no CTA of another
 // kernel could become resident beside it and the side-stream overlap in ppn_parse would silently
 // serialise (measured: it did).
+static std::mutex g_ticket_mu;
+
+static cudaError_t ticket_for(DeviceInfo* d, cudaStream_t st, int** out) {
+    std::lock_guard<std::mutex> lock(g_ticket_mu);
+    if (!d->tickets) {
+        cudaError_t e = cudaMalloc(&d->tickets, kTicketSlots * 2 * sizeof(int));
+        if (e != cudaSuccess) return e;
+        if ((e = cudaMemset(d->tickets, 0, kTicketSlots * 2 * sizeof(int))) != cudaSuccess) return e;
+    }
+    for (int i = 0; i < d->slots_used; ++i)
+        if (d->slot_stream[i] == st) { *out = d->tickets + 2 * i; return cudaSuccess; }
+    if (d->slots_used == kTicketSlots) { *out = nullptr; return cudaSuccess; }    // static dealing for further streams
+    d->slot_stream[d->slots_used] = st;
+    *out = d->tickets + 2 * d->slots_used++;
+    return cudaSuccess;
+}
+
 template <typename F>
 static cudaError_t ensure_smem(F kernel, size_t want, size_t* have) {
     if (*have != 0 && want <= *have) return cudaSuccess;
@@ -842,6 +993,25 @@ static cudaError_t ensure_smem(F kernel, size_t want, size_t* have) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) *have = grant;
     return e;
+}
+
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute: with it the
+// kernel may begin while the previous kernel in the stream is still running, once every CTA of that
+// kernel has executed griddepcontrol.launch_dependents (or exited).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
@@ -863,7 +1033,7 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
         const long long grid = (long long)sms * (t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm);
         int bestM = G;
         double best_eff = 0.0;
-        for (int M = G; M >= (G + 1) / 2 && M >= 1; --M) {
+        for (int M = G; t.argmax_tail_opt && M >= (G + 1) / 2 && M >= 1; --M) {
             const long long items = (n_mats + M - 1) / M;
             const long long waves = (items + grid - 1) / grid;
             const double eff = (double)n_mats / (double)(waves * grid * M);
@@ -887,11 +1057,13 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     p->stages = t.argmax_stages;
     p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
     p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * p->stages * sizeof(uint64_t) +
-                    (p->split_mats ? 0 : (size_t)2 * G * g.HW * sizeof(Partial));
+                    (size_t)p->stages * sizeof(int) + (p->split_mats ? 0 : (size_t)2 * G * g.HW * sizeof(Partial));
     return true;
 }
 
-cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st) {
+cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
+                               bool pdl, bool* pdl_used) {
+    if (pdl_used) *pdl_used = false;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
     if (e != cudaSuccess) return e;
@@ -904,21 +1076,26 @@ cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g,
         const size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
         while (p.smem_bytes > budget && p.stages > 2) {
             --p.stages;
-            p.smem_bytes -= p.stage_bytes + 2 * sizeof(uint64_t);
+            p.smem_bytes -= p.stage_bytes + 2 * sizeof(uint64_t) + sizeof(int);
         }
         if (p.smem_bytes <= budget) {
+            int* ticket = nullptr;
+            if (t.argmax_dynamic && (e = ticket_for(d, st, &ticket)) != cudaSuccess) return e;
             int grid = d->sms * p.ctas_per_sm;
             if (p.split_mats) {
                 const int n_items = (n_mats + p.G - 1) / p.G;
                 if (grid > n_items) grid = n_items;
                 if ((e = ensure_smem(limb_argmax_tma_multi_kernel, p.smem_bytes, &d->tma_multi)) != cudaSuccess) return e;
-                limb_argmax_tma_multi_kernel<<<grid, p.threads_padded + 32, p.smem_bytes, st>>>(head, amax, g, p);
+                e = launch_kernel(limb_argmax_tma_multi_kernel, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
+                                  head, amax, g, p, pdl ? 1 : 0, ticket);
             } else {
                 if (grid > n_mats) grid = n_mats;
                 if ((e = ensure_smem(limb_argmax_tma_kernel, p.smem_bytes, &d->tma)) != cudaSuccess) return e;
-                limb_argmax_tma_kernel<<<grid, p.threads_padded + 32, p.smem_bytes, st>>>(head, amax, g, p);
+                e = launch_kernel(limb_argmax_tma_kernel, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
+                                  head, amax, g, p, pdl ? 1 : 0, ticket);
             }
-            return cudaGetLastError();
+            if (pdl_used) *pdl_used = pdl;
+            return e;
         }
     }
     if (vec_ok) {
@@ -983,12 +1160,21 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
     return cudaGetLastError();
 }
 
+cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const float* score, const float* box, int B, int R,
+                               int K, int cap, int32_t* header, int32_t* rec_cell, float* rec_score, float* rec_box,
+                               cudaStream_t st) {
+    if (B == 0) return cudaSuccess;
+    pack_humans_kernel<<<B, 256, 0, st>>>(count, cell, score, reinterpret_cast<const float4*>(box), B, R, K, cap, header,
+                                          rec_cell, rec_score, reinterpret_cast<float4*>(rec_box));
+    return cudaGetLastError();
+}
+
 size_t decode_nms_smem_bytes(const Geom& g) {
     return (size_t)g.HW * sizeof(float4) + (size_t)((g.HW + 3) & ~3) * sizeof(int32_t) + nms_smem_bytes(g.HW);
 }
 
 cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
-                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st) {
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_trigger) {
     if (g.B == 0 || n_parts == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -997,37 +1183,45 @@ cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, flo
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(decode_nms_kernel, smem, &d->decode_nms)) != cudaSuccess) return e;
     dim3 grid(g.B, n_parts);
-    decode_nms_kernel<<<grid, g.HW <= 256 ? 256 : 512, smem, st>>>(head, g, n_parts, det_thr, nms_thr, keep_cell, keep_count);
+    decode_nms_kernel<<<grid, g.HW <= 256 ? 256 : 512, smem, st>>>(head, g, n_parts, det_thr, nms_thr, keep_cell, keep_count,
+                                                                   pdl_trigger ? 1 : 0);
     return cudaGetLastError();
 }
 
-size_t tree_parse_smem_bytes(const Geom& g) {
-    return (size_t)2 * g.K * g.HW * sizeof(float) + ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
-           (((size_t)kRootsPerRound * g.K + 1) & ~(size_t)1) * sizeof(int16_t) +
-           (g.S <= kMaxDyxTable ? (size_t)g.S * sizeof(int32_t) : 0);
+size_t tree_parse_smem_bytes(const Geom& g, bool stage_all) {
+    return (size_t)(stage_all ? 6 : 2) * g.K * g.HW * sizeof(float) +
+           ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
+           (size_t)2 * g.HW * sizeof(int32_t) + (g.S <= kMaxDyxTable ? (size_t)g.S * sizeof(int32_t) : 0) +
+           (((size_t)g.HW * g.K + 7) & ~(size_t)7) * sizeof(int16_t);
 }
 
 cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
-                              float* h_score, float* h_box, int R, cudaStream_t st) {
+                              float* h_score, float* h_box, int R, cudaStream_t st, bool pdl, int stage_all_pref) {
     if (g.B == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
     if (e != cudaSuccess) return e;
     const int threads = 256;
-    const size_t smem = tree_parse_smem_bytes(g);
+    // x, y, w, h can be staged beside resp, conf so that the write-out needs no global gathers; by
+    // default only when that keeps the CTA small (<= 32 KB): a light CTA lets every image of the
+    // batch be resident at once and lets several start their prologue under the arg-max kernel's
+    // tail (PDL), which measured faster than saving the gathers at 62 KB per CTA
+    const size_t all_bytes = tree_parse_smem_bytes(g, true);
+    const bool stage_all = stage_all_pref < 0 ? all_bytes <= 32 * 1024
+                                              : (stage_all_pref > 0 && all_bytes <= (size_t)d->smem_optin);
+    const size_t smem = tree_parse_smem_bytes(g, stage_all);
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(tree_parse_kernel, smem, &d->tree)) != cudaSuccess) return e;
-    // bulk copies need 16-byte sizes and sources: resp+conf is 8*K*HW bytes at image offset
-    // 4*C*HW*b, the arg-max map 2*E*HW bytes at offset 2*E*HW*b
+    // bulk copies need 16-byte sizes and sources: the staged planes are 4*n*K*HW bytes at image
+    // offset 4*C*HW*b, the arg-max map 2*E*HW bytes at offset 2*E*HW*b
     const bool tma_ok = ((size_t)g.K * g.HW * 8) % 16 == 0 && (g.img_stride * 4) % 16 == 0 &&
                         ((size_t)g.E * g.HW * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(head) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(amax) & 15) == 0;
-    tree_parse_kernel<<<g.B, threads, smem, st>>>(head, g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count,
-                                                  h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R,
-                                                  tma_ok ? 1 : 0);
-    return cudaGetLastError();
+    return launch_kernel(tree_parse_kernel, dim3(g.B), dim3(threads), smem, st, pdl, head, g, ch, thr, min_kp, n_parts, amax,
+                         cand_cell, keep_idx, keep_count, h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box),
+                         R, tma_ok ? 1 : 0, stage_all ? 1 : 0, pdl ? 1 : 0);
 }
 
 }  // namespace ppn

@@ -107,6 +107,22 @@ class PackedHumans:
         return result
 
 
+def unpack_records(buf, B: int, K: int, cap_records: int, offsets):
+    """Host view of one dense record buffer (see include/ppn_decode.h, ppn_pack_humans).
+
+    buf: uint8 numpy array or CPU tensor.  Returns dict(total, overflow, count[B], start[B],
+    cell[cap,K], score[cap,K], box[cap,K,4]); image b's humans are records start[b] : start[b]+n."""
+    a = buf.numpy() if isinstance(buf, torch.Tensor) else np.asarray(buf)
+    o_h, o_c, o_s, o_b = offsets
+    header = a[o_h:o_h + 4 * (2 + B)].view(np.int32)
+    count = header[2:2 + B]
+    cell = a[o_c:o_c + 4 * cap_records * K].view(np.int32).reshape(cap_records, K)
+    score = a[o_s:o_s + 4 * cap_records * K].view(np.float32).reshape(cap_records, K)
+    box = a[o_b:o_b + 16 * cap_records * K].view(np.float32).reshape(cap_records, K, 4)
+    start = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64) if B else np.zeros(0, np.int64)
+    return dict(total=int(header[0]), overflow=bool(header[1]), count=count, start=start, cell=cell, score=score, box=box)
+
+
 class PoseParser:
     """Decode + NMS + limb arg-max + tree parse of PPN head tensors on one B200.
 
@@ -127,6 +143,7 @@ class PoseParser:
         self._ws = None
         self._ws_need = {}            # B -> workspace bytes (ppn_workspace_bytes is pure arithmetic)
         self._shapes = {}             # B -> PPNShape
+        self._layouts = {}            # (B, cap) -> dense record layout
         self._out = None
         self._out_B = 0
         self._host_scratch = None
@@ -226,6 +243,35 @@ class PoseParser:
             _lib.check(self.lib.ppn_parse_host(_ptr(head), C.byref(shape), C.byref(self.c.params), C.byref(hs),
                                                _ptr(self._host_scratch), self._host_scratch.numel()), "ppn_parse_host")
         return out
+
+    # ---- dense records (what the multi-GPU gather ships) -------------------------------- #
+    def packed_layout(self, B: int, cap_records: int):
+        """-> (bytes, (header, cell, score, box) byte offsets) of the dense record buffer."""
+        key = (B, cap_records)
+        hit = self._layouts.get(key)
+        if hit is not None:
+            return hit
+        self._layouts[key] = self._packed_layout(B, cap_records)
+        return self._layouts[key]
+
+    def _packed_layout(self, B: int, cap_records: int):
+        nbytes = C.c_size_t()
+        offs = (C.c_size_t * 4)()
+        _lib.check(self.lib.ppn_packed_bytes(B, self.cfg.K, cap_records, C.byref(nbytes), offs), "ppn_packed_bytes")
+        return nbytes.value, tuple(int(o) for o in offs)
+
+    def pack(self, humans: PackedHumans, cap_records: int, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Compact the fixed-stride result into one contiguous uint8 buffer (asynchronous): counts
+        plus dense (cell, score, box) records, `cap_records` records at most (ppn_pack_humans)."""
+        B = humans.count.shape[0]
+        nbytes, _ = self.packed_layout(B, cap_records)
+        if buf is None:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        hs = self._humans_struct(humans)
+        with self._guard():
+            _lib.check(self.lib.ppn_pack_humans(C.byref(hs), B, self.cfg.K, cap_records, buf.data_ptr(), buf.numel(),
+                                                torch.cuda.current_stream(self.device).cuda_stream), "ppn_pack_humans")
+        return buf
 
     # ---- single stages (what the stage-level parity tests call) ------------------------- #
     def limb_argmax(self, head: torch.Tensor) -> torch.Tensor:

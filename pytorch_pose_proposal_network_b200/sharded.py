@@ -93,3 +93,82 @@ class ShardedPoseParser:
                                 out.part_score[b0:b1], out.part_box[b0:b1])
             self.parser.parse(head[b0:b1], out=view)
         return out
+
+
+class PoseGatherer:
+    """Gather of every rank's poses as ONE small asynchronous collective per group of steps.
+
+    Each step the local result is compacted on the device into a dense record buffer
+    (``PoseParser.pack`` -> ``ppn_pack_humans``: counts + up to ``cap_records`` (cell, score, box)
+    records).  Every ``group_steps`` steps the group's buffers are all-gathered with a single
+    ``all_gather_into_tensor`` issued with ``async_op``: the collective runs on NCCL's own stream
+    while the next steps' kernels run on the compute stream (one NCCL call costs tens of µs of host
+    time, comparable to a whole step, hence the grouping).  Two buffer sets alternate; before a set is
+    reused the compute stream waits for the collective that last read it.  Every rank ends up with
+    every rank's records of every step.
+    """
+
+    def __init__(self, parser, images_per_rank: int, cap_records: int, group=None, group_steps: int = 1):
+        self.parser = parser
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.B = int(images_per_rank)
+        self.cap = int(cap_records)
+        self.gs = max(1, int(group_steps))
+        self.nbytes, self.offsets = parser.packed_layout(self.B, self.cap)
+        dev = parser.device
+        self.local = [torch.zeros(self.gs * self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.full = [torch.zeros(self.world * self.gs * self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.work = [None, None]
+        self.step = 0
+        # packing and the collective live on a side stream: the compute stream goes straight on to
+        # the next step's kernels
+        self.side = torch.cuda.Stream(device=dev)
+
+    def submit(self, humans) -> torch.cuda.Event:
+        """Pack `humans` (this rank's PackedHumans of the step) on the side stream and, when a group
+        is full, start its gather.  Returns an event that fires once `humans` has been read: wait
+        for it (``stream.wait_event``) before the parser overwrites that output buffer."""
+        grp, k = divmod(self.step, self.gs)
+        i = grp & 1
+        parsed = torch.cuda.Event()
+        parsed.record(torch.cuda.current_stream(self.parser.device))
+        released = torch.cuda.Event()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(parsed)
+            if k == 0 and self.work[i] is not None:
+                self.work[i].wait()               # side stream waits for the gather that last read this set
+                self.work[i] = None
+            self.parser.pack(humans, self.cap, buf=self.local[i][k * self.nbytes:(k + 1) * self.nbytes])
+            released.record(self.side)
+            if k == self.gs - 1:
+                self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
+        self.step += 1
+        return released
+
+    def finish(self):
+        """Gather a partly filled last group, then make the CURRENT stream wait for every gather.
+        Every rank must have submitted the same number of steps."""
+        grp, k = divmod(self.step, self.gs)
+        with torch.cuda.stream(self.side):
+            if k != 0:                            # flush: ship the partial group as it is
+                i = grp & 1
+                self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
+                self.step = (grp + 1) * self.gs
+            for j in range(2):
+                if self.work[j] is not None:
+                    self.work[j].wait()
+                    self.work[j] = None
+            landed = torch.cuda.Event()
+            landed.record(self.side)
+        torch.cuda.current_stream(self.parser.device).wait_event(landed)
+
+    def records_of(self, rank: int, step_back: int = 0):
+        """Host view of `rank`'s records for the last submitted step minus `step_back`
+        (within the two most recent groups; call after finish(); synchronises)."""
+        from .parser import unpack_records
+        grp, k = divmod(self.step - 1 - step_back, self.gs)
+        buf = self.full[grp & 1]
+        lo = (rank * self.gs + k) * self.nbytes
+        part = buf[lo:lo + self.nbytes].cpu()
+        return unpack_records(part, self.B, self.parser.cfg.K, self.cap, self.offsets)

@@ -37,8 +37,10 @@ def main():
     ap.add_argument("--presets", default="cfg2,cfg3,cfg4,native")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--tail-opt", type=int, default=1)
     args = ap.parse_args()
     peak = 6553.0
+    _lib.tune(argmax_tail_opt=args.tail_opt)
     for name in args.presets.split(","):
         cfg = PRESETS[name]()
         B = BATCH[name]
@@ -47,8 +49,8 @@ def main():
         parser = PoseParser(cfg)
         limb_bytes = B * cfg.E * cfg.S * cfg.HW * 4
         rows = []
-        grid = list(itertools.product([0], [16384, 32768, 49152, 65536], [3, 4, 6, 8], [192, 320, 512], [1, 2], [0, 1]))
-        grid += list(itertools.product([1], [32768], [5], [128, 192, 320, 512], [1], [0]))
+        grid = list(itertools.product([0], [16384, 32768, 49152, 65536], [3, 4, 5, 6], [144, 192, 256, 320, 512], [1, 2], [-1]))
+        grid += list(itertools.product([1], [32768], [5], [128, 192], [1], [0]))
         if args.quick:
             grid = grid[::7]
         for variant, sb, st, th, ctas, split in grid:

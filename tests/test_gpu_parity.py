@@ -159,7 +159,7 @@ def test_batch_matches_c_oracle(preset, dist, B):
 
 
 TUNE_DEFAULTS = dict(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=5, argmax_threads=320,
-                     argmax_ctas_per_sm=1, argmax_split=-1)
+                     argmax_ctas_per_sm=1, argmax_split=-1, argmax_dynamic=1, argmax_tail_opt=0)
 
 
 @pytest.mark.parametrize("variant,stage_bytes,stages,threads,ctas,split", [
@@ -186,7 +186,34 @@ def test_limb_argmax_every_tuning(preset, variant, stage_bytes, stages, threads,
     assert np.array_equal(got, want)
 
 
-def test_overlap_off_gives_same_result():
+@pytest.mark.parametrize("preset", ["cfg2", "cfg4"])
+@pytest.mark.parametrize("dynamic,tail_opt,ctas", [(0, 0, 1), (0, 1, 2), (1, 0, 1), (1, 1, 2)])
+def test_limb_argmax_work_distribution(preset, dynamic, tail_opt, ctas):
+    """Static round-robin vs ticket scheduling, repeated launches (the counter must reset itself)."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    head = synth.make_head(g, "U", seed=21, B=40 if preset == "cfg2" else 12)
+    want = np.stack([c_oracle.limb_argmax(img, g) for img in head]).astype(np.uint16)
+    dev = torch.from_numpy(head).cuda()
+    _lib.tune(argmax_dynamic=dynamic, argmax_tail_opt=tail_opt, argmax_ctas_per_sm=ctas)
+    try:
+        parser = PoseParser(cfg)
+        side = torch.cuda.Stream()
+        for rep in range(4):
+            got = parser.limb_argmax(dev)
+            with torch.cuda.stream(side):                  # a second stream gets its own counter pair
+                got2 = parser.limb_argmax(dev)
+            torch.cuda.synchronize()
+            assert np.array_equal(got.cpu().numpy(), want), rep
+            assert np.array_equal(got2.cpu().numpy(), want), rep
+    finally:
+        _lib.tune(**TUNE_DEFAULTS)
+
+
+def test_every_launch_ordering_gives_same_result():
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PPNConfig
     from pytorch_pose_proposal_network_b200.parser import PoseParser
@@ -195,7 +222,7 @@ def test_overlap_off_gives_same_result():
     head = synth.make_head(g, "U", seed=9, B=20)
     ref = c_oracle.parse_batch(head, g, n_threads=8)
     dev = torch.from_numpy(head).cuda()
-    for overlap in (0, 1):
+    for overlap in (0, 1, 2):
         _lib.tune(parse_overlap=overlap)
         try:
             parser = PoseParser(cfg)
@@ -203,7 +230,7 @@ def test_overlap_off_gives_same_result():
                 packed = parser.parse(dev)
             assert_packed_equals_oracle(packed.numpy(), ref, 20)
         finally:
-            _lib.tune(parse_overlap=1)
+            _lib.tune(parse_overlap=2)
 
 
 @pytest.mark.parametrize("W,H,sW,sH", [(13, 13, 9, 9), (5, 7, 3, 5), (10, 6, 7, 7), (31, 33, 3, 3)])
@@ -342,6 +369,32 @@ def test_capacity_limit_keeps_top_scores():
     assert np.array_equal(a["part_cell"][:, :10], ref["part_cell"][:, :10])
     with pytest.raises(RuntimeError):
         packed.to_lists()
+
+
+def test_pack_dense_records_roundtrip():
+    """ppn_pack_humans: fixed-stride result -> dense records (what the multi-GPU gather ships)."""
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser, unpack_records
+    cfg = PPNConfig.mpii16()
+    g = O.Geometry.of(cfg)
+    B = 37
+    head = synth.make_head(g, "U", seed=5, B=B)
+    ref = c_oracle.parse_batch(head, g, n_threads=8)
+    parser = PoseParser(cfg)
+    out = parser.parse(torch.from_numpy(head).cuda())
+    total = int(ref["counts"][:, 2].sum())
+    for cap in (total + 10, total, total // 2):
+        buf = parser.pack(out, cap)
+        _, offs = parser.packed_layout(B, cap)
+        rec = unpack_records(buf.cpu(), B, cfg.K, cap, offs)
+        assert rec["total"] == total and rec["overflow"] == (total > cap)
+        assert np.array_equal(rec["count"], ref["counts"][:, 2])
+        for b in range(B):
+            n, s0 = int(rec["count"][b]), int(rec["start"][b])
+            n = max(0, min(n, cap - s0))                       # records that fit
+            assert np.array_equal(rec["cell"][s0:s0 + n], ref["part_cell"][b, :n])
+            assert np.array_equal(bits(rec["score"][s0:s0 + n]), bits(ref["part_score"][b, :n]))
+            assert np.array_equal(bits(rec["box"][s0:s0 + n]), bits(ref["part_box"][b, :n]))
 
 
 def test_bad_arguments_raise():

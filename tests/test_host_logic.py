@@ -125,6 +125,28 @@ def test_shard_ranges_cover_job():
             assert max(shard_sizes(n, world)) == -(-n // world)
 
 
+def test_dense_record_layout_host_side():
+    """unpack_records against a buffer laid out by hand from ppn_packed_bytes' offsets (no GPU)."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.parser import unpack_records
+    B, K, cap = 5, 16, 11
+    nbytes, offs = C.c_size_t(), (C.c_size_t * 4)()
+    assert _lib.lib().ppn_packed_bytes(B, K, cap, C.byref(nbytes), offs) == 0
+    offs = tuple(int(o) for o in offs)
+    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and offs[1] >= 4 * (2 + B)
+    assert nbytes.value >= offs[3] + cap * K * 16
+    buf = np.zeros(nbytes.value, np.uint8)
+    count = np.array([2, 0, 3, 1, 4], np.int32)
+    buf[0:4 * (2 + B)].view(np.int32)[:] = np.concatenate([[count.sum(), 0], count])
+    cell = np.arange(cap * K, dtype=np.int32).reshape(cap, K)
+    buf[offs[1]:offs[1] + cell.nbytes].view(np.int32)[:] = cell.reshape(-1)
+    rec = unpack_records(buf, B, K, cap, offs)
+    assert rec["total"] == 10 and not rec["overflow"]
+    assert list(rec["start"]) == [0, 2, 2, 5, 6]
+    assert np.array_equal(rec["cell"], cell)
+    assert _lib.lib().ppn_packed_bytes(-1, K, cap, C.byref(nbytes), None) == -1
+
+
 def _gloo_worker(rank, world, port, n_images, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
