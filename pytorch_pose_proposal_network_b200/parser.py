@@ -260,17 +260,20 @@ class PoseParser:
         _lib.check(self.lib.ppn_packed_bytes(B, self.cfg.K, cap_records, C.byref(nbytes), offs), "ppn_packed_bytes")
         return nbytes.value, tuple(int(o) for o in offs)
 
-    def pack(self, humans: PackedHumans, cap_records: int, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def pack(self, humans: PackedHumans, cap_records: int, buf: Optional[torch.Tensor] = None,
+             stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """Compact the fixed-stride result into one contiguous uint8 buffer (asynchronous): counts
-        plus dense (cell, score, box) records, `cap_records` records at most (ppn_pack_humans)."""
+        plus dense (cell, score, box) records, `cap_records` records at most (ppn_pack_humans).
+        Runs on `stream` (default: torch's current stream)."""
         B = humans.count.shape[0]
         nbytes, _ = self.packed_layout(B, cap_records)
         if buf is None:
             buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         hs = self._humans_struct(humans)
         with self._guard():
-            _lib.check(self.lib.ppn_pack_humans(C.byref(hs), B, self.cfg.K, cap_records, buf.data_ptr(), buf.numel(),
-                                                torch.cuda.current_stream(self.device).cuda_stream), "ppn_pack_humans")
+            st = (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream
+            _lib.check(self.lib.ppn_pack_humans(C.byref(hs), B, self.cfg.K, cap_records, buf.data_ptr(), buf.numel(), st),
+                       "ppn_pack_humans")
         return buf
 
     # ---- single stages (what the stage-level parity tests call) ------------------------- #

@@ -122,26 +122,32 @@ class PoseGatherer:
         self.work = [None, None]
         self.step = 0
         # packing and the collective live on a side stream: the compute stream goes straight on to
-        # the next step's kernels
+        # the next step's kernels.  Events are preallocated and reused (a handful of cheap calls per
+        # step; the stream context manager is entered only when a collective is issued).
         self.side = torch.cuda.Stream(device=dev)
+        self._parsed = [torch.cuda.Event() for _ in range(4)]
+        self._released = [torch.cuda.Event() for _ in range(4)]
+        self._slices = [[self.local[i][k * self.nbytes:(k + 1) * self.nbytes] for k in range(self.gs)] for i in range(2)]
 
     def submit(self, humans) -> torch.cuda.Event:
         """Pack `humans` (this rank's PackedHumans of the step) on the side stream and, when a group
         is full, start its gather.  Returns an event that fires once `humans` has been read: wait
-        for it (``stream.wait_event``) before the parser overwrites that output buffer."""
+        for it (``stream.wait_event``) before the parser overwrites that output buffer (callers
+        alternating fewer than four output buffers are covered by the event ring)."""
         grp, k = divmod(self.step, self.gs)
         i = grp & 1
-        parsed = torch.cuda.Event()
+        e = self.step & 3
+        parsed, released = self._parsed[e], self._released[e]
         parsed.record(torch.cuda.current_stream(self.parser.device))
-        released = torch.cuda.Event()
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(parsed)
-            if k == 0 and self.work[i] is not None:
+        self.side.wait_event(parsed)
+        if k == 0 and self.work[i] is not None:
+            with torch.cuda.stream(self.side):
                 self.work[i].wait()               # side stream waits for the gather that last read this set
-                self.work[i] = None
-            self.parser.pack(humans, self.cap, buf=self.local[i][k * self.nbytes:(k + 1) * self.nbytes])
-            released.record(self.side)
-            if k == self.gs - 1:
+            self.work[i] = None
+        self.parser.pack(humans, self.cap, buf=self._slices[i][k], stream=self.side)
+        released.record(self.side)
+        if k == self.gs - 1:
+            with torch.cuda.stream(self.side):
                 self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
         self.step += 1
         return released
