@@ -173,7 +173,7 @@ int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
 /* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
  * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
  * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
- * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "parse.stage_all" (-1 auto, 0, 1),
+ * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "parse.chain_calls", "parse.stage_all" (-1 auto, 0, 1),
  * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);
 int ppn_tune_get(const char* key, int32_t* value);

@@ -180,6 +180,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value != 0;
     else if (!std::strcmp(key, "argmax.dynamic")) t.argmax_dynamic = value != 0;
     else if (!std::strcmp(key, "parse.stage_all")) t.parse_stage_all = value;
+    else if (!std::strcmp(key, "parse.chain_calls")) t.parse_chain_calls = value != 0;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -198,6 +199,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.tail_opt")) *value = t.argmax_tail_opt;
     else if (!std::strcmp(key, "argmax.dynamic")) *value = t.argmax_dynamic;
     else if (!std::strcmp(key, "parse.stage_all")) *value = t.parse_stage_all;
+    else if (!std::strcmp(key, "parse.chain_calls")) *value = t.parse_chain_calls;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -323,7 +325,11 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     const int mode = ev ? 0 : g_tuning.parse_overlap;
     if (mode == 2) {
         bool chained = false;
-        if ((e = ppn::launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, true)) != cudaSuccess) return (int)e;
+        // K12 is itself a programmatic dependent of whatever precedes it in the stream (normally the
+        // previous call's K4, which triggers early): it becomes resident under that kernel, WAITS for
+        // it to complete, then releases K3 — only the launch latency between calls is hidden.
+        if ((e = ppn::launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, true,
+                                        g_tuning.parse_chain_calls != 0)) != cudaSuccess) return (int)e;
         if ((e = ppn::launch_limb_argmax(head, amax, g, g_tuning, st, true, &chained)) != cudaSuccess) return (int)e;
         if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr, keep_idx,
                                         keep_count, out->count, out->root_cell, out->part_cell, out->part_score,

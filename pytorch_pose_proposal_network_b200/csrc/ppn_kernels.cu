@@ -594,7 +594,11 @@ __global__ void __launch_bounds__(512)
 decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
                   int32_t* __restrict__ keep_cell, int32_t* __restrict__ keep_count, int pdl) {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (pdl) pdl_launch_dependents();        // the arg-max kernel does not need anything from this one
+    // pdl & 2: launched as a programmatic dependent itself (of the previous call's tree parse, or of
+    // whatever kernel produced `head`): it may have become resident early, so it must wait before it
+    // reads anything.  pdl & 1: then release the arg-max kernel, which needs nothing from this one.
+    if (pdl & 2) pdl_wait();
+    if (pdl & 1) pdl_launch_dependents();
     __shared__ int warp_tot[16];
     __shared__ int base_s;
     float4* ubox = reinterpret_cast<float4*>(smem);                         // [HW] candidate boxes, cell order
@@ -784,7 +788,10 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             s_dyx[a] = ((dy - g.off_h) << 16) | ((dx - g.off_w) & 0xffff);
         }
     // ---- from here on we read what the arg-max and decode+NMS kernels wrote ---------------------
-    if (pdl) pdl_wait();
+    if (pdl) {
+        pdl_wait();
+        pdl_launch_dependents();             // the NEXT call's decode+NMS may become resident (it waits for us)
+    }
     if (use_tma) {
         if (tid == 0 && bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
     } else {
@@ -1174,7 +1181,7 @@ size_t decode_nms_smem_bytes(const Geom& g) {
 }
 
 cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
-                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_trigger) {
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_trigger, bool pdl_self) {
     if (g.B == 0 || n_parts == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -1183,9 +1190,8 @@ cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, flo
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(decode_nms_kernel, smem, &d->decode_nms)) != cudaSuccess) return e;
     dim3 grid(g.B, n_parts);
-    decode_nms_kernel<<<grid, g.HW <= 256 ? 256 : 512, smem, st>>>(head, g, n_parts, det_thr, nms_thr, keep_cell, keep_count,
-                                                                   pdl_trigger ? 1 : 0);
-    return cudaGetLastError();
+    return launch_kernel(decode_nms_kernel, grid, dim3(g.HW <= 256 ? 256 : 512), smem, st, pdl_self, head, g, n_parts, det_thr,
+                         nms_thr, keep_cell, keep_count, (pdl_trigger ? 1 : 0) | (pdl_self ? 2 : 0));
 }
 
 size_t tree_parse_smem_bytes(const Geom& g, bool stage_all) {

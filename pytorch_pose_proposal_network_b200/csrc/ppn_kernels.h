@@ -14,6 +14,7 @@ struct Tuning {
     int argmax_dynamic = 1;            // ring kernels draw work from a global ticket counter (0: static round-robin)
     int argmax_tail_opt = 0;           // split-matrix mode: pick matrices/item that fills the last wave best
     int parse_stage_all = -1;          // tree parse stages x,y,w,h too: -1 auto (when small), 0 never, 1 if it fits
+    int parse_chain_calls = 1;         // PDL chain: the first kernel of a call is a programmatic dependent too
     int host_chunk_images = 64;
     int parse_overlap = 2;             // 0 serial; 1 decode+NMS on a side stream beside the arg-max;
                                        // 2 one stream, programmatic dependent launches (PDL chain)
@@ -48,7 +49,8 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
 
 // fused K1+K2 of the whole-path call: surviving root cells per (image, part), nothing else
 cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
-                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_trigger = false);
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_trigger = false,
+                              bool pdl_self = false);
 
 cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* ry, size_t n, int H, int W,
                               float gridW, float gridH, cudaStream_t st);
