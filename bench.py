@@ -211,7 +211,9 @@ def run_ours(args, rank, world, local_rank):
     def step(i):
         if released[i % 2] is not None:             # the gather's pack kernel has read this output buffer
             torch.cuda.current_stream(dev).wait_event(released[i % 2])
-        out = parser.parse(bufs[i % n_buf], out=outs[i % 2])
+        # the inputs have been resident in HBM since before the timed region: the parser may overlap
+        # consecutive steps (PPN_FLAG_INPUT_COMPLETE); results still complete in step order
+        out = parser.parse(bufs[i % n_buf], out=outs[i % 2], input_complete=not args.no_step_overlap)
         if gatherer is not None:
             released[i % 2] = gatherer.submit(out)  # side stream: pack + (every few steps) one async all_gather
         return out
@@ -358,6 +360,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2": f"{n_buf} distinct input batches of {batch_bytes / 1e6:.0f} MB rotated (each larger than L2)",
                    "humans_per_image": humans_per_image, "extra_warmup_steps": extra,
                    "host_issue_ms_per_step": host_issue_ms,
+                   "step_overlap": "off" if args.no_step_overlap else
+                   "PPN_FLAG_INPUT_COMPLETE: inputs resident before the timed region, so step i+1's arg-max may start while "
+                   "step i's tree parse finishes; steps complete in order",
                    "pose_gather": "none (1 GPU)" if world == 1 else
                    f"every step: device-side pack to dense records (cap {args.gather_humans}/image avg); every "
                    f"{args.gather_every} steps one async NCCL all_gather of {args.gather_every * gatherer.nbytes / 1e6:.2f} MB "
@@ -417,6 +422,8 @@ def main():
     ap.add_argument("--settle-s", type=float, default=0.4)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-step-overlap", action="store_true",
+                    help="do not pass PPN_FLAG_INPUT_COMPLETE (each step's kernels wait for the previous step's)")
     ap.add_argument("--tune", action="append", default=[], help="library knob, e.g. argmax.stages=6")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define PPN_ABI_VERSION 1
+#define PPN_ABI_VERSION 2
 
 /* library error codes (negative); positive return values are cudaError_t */
 #define PPN_OK               0
@@ -79,10 +79,18 @@ typedef struct PPNParams {
     int32_t n_nms_parts;        /* parts 0..n-1 get a compacted candidate list and NMS; the
                                    reference uses only part 0 (datatest.py:86-94) => 1           */
     int32_t n_chains;
+    int32_t flags;              /* PPN_FLAG_* , 0 = none                                         */
     const int32_t* chain_off;   /* [n_chains + 1]                                                */
     const int32_t* chain_limb;  /* [chain_off[n_chains]] limb index of each step  ("eis")        */
     const int32_t* chain_part;  /* [chain_off[n_chains]] target part of each step ("ts")         */
 } PPNParams;
+
+/* ppn_parse only.  The caller vouches that the head tensor was completely written before the call
+ * was enqueued (it is resident from an earlier, already completed step, or was followed by a
+ * synchronisation) — NOT merely ordered before it on the stream by a still-running producer kernel.
+ * Then the call's arg-max and decode kernels may start while the previous ppn_parse on the same
+ * stream is still in its tree parse; results still complete in call order. */
+#define PPN_FLAG_INPUT_COMPLETE 1
 
 /* Packed result, device memory owned by the caller.  Humans of image b occupy slots
  * [0, min(count[b], R)) in descending root-score (NMS) order, as the reference's list is. */
@@ -98,7 +106,8 @@ typedef struct PPNHumans {
 int         ppn_abi_version(void);
 const char* ppn_strerror(int code);
 
-/* Bytes of scratch ppn_parse needs for this shape (arg-max map, surviving root cells, counts). */
+/* Bytes of scratch ppn_parse needs for this shape: two sets of (arg-max map, surviving root cells,
+ * counts), used alternately by successive calls on the same workspace. */
 int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* bytes);
 
 /* Number of kernel launches one ppn_parse call enqueues for this shape. */
@@ -173,7 +182,7 @@ int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
 /* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
  * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
  * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
- * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "parse.chain_calls", "parse.stage_all" (-1 auto, 0, 1),
+ * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "parse.chain_calls", "parse.threads", "parse.stage_all" (-1 auto, 0 none, 1 resp+conf, 2 all six groups),
  * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);
 int ppn_tune_get(const char* key, int32_t* value);

@@ -10,7 +10,8 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_INPUT_COMPLETE = 1
 MAX_CELLS = 1024
 MAX_CHAINS = 32
 MAX_CHAIN_STEPS = 192
@@ -27,7 +28,7 @@ class PPNShape(C.Structure):
 
 class PPNParams(C.Structure):
     _fields_ = [("det_thresh", C.c_float), ("nms_thresh", C.c_float), ("min_num_keypoints", C.c_int32),
-                ("n_nms_parts", C.c_int32), ("n_chains", C.c_int32),
+                ("n_nms_parts", C.c_int32), ("n_chains", C.c_int32), ("flags", C.c_int32),
                 ("chain_off", i32p), ("chain_limb", i32p), ("chain_part", i32p)]
 
 

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "ppn_decode.h"
 #include "ppn_kernels.h"
@@ -136,6 +137,16 @@ Workspace carve(const PPNShape* s, int n_parts) {
     return w;
 }
 
+// ppn_parse alternates between the two halves of the caller's workspace from call to call, so that
+// a call may overlap the previous one (PPN_FLAG_INPUT_COMPLETE) without sharing scratch with it.
+std::mutex g_parity_mu;
+std::unordered_map<void*, unsigned> g_parity;
+
+unsigned next_parity(void* workspace) {
+    std::lock_guard<std::mutex> lock(g_parity_mu);
+    return g_parity[workspace]++ & 1u;
+}
+
 int check_params(const PPNShape* s, const PPNParams* p) {
     if (!p) return PPN_E_BADARG;
     if (p->n_nms_parts < 1 || p->n_nms_parts > s->K) return PPN_E_BADARG;
@@ -181,6 +192,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.dynamic")) t.argmax_dynamic = value != 0;
     else if (!std::strcmp(key, "parse.stage_all")) t.parse_stage_all = value;
     else if (!std::strcmp(key, "parse.chain_calls")) t.parse_chain_calls = value != 0;
+    else if (!std::strcmp(key, "parse.threads")) t.parse_threads = value;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -200,6 +212,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.dynamic")) *value = t.argmax_dynamic;
     else if (!std::strcmp(key, "parse.stage_all")) *value = t.parse_stage_all;
     else if (!std::strcmp(key, "parse.chain_calls")) *value = t.parse_chain_calls;
+    else if (!std::strcmp(key, "parse.threads")) *value = t.parse_threads;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -210,7 +223,7 @@ int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* 
     if (rc) return rc;
     if ((rc = check_params(shape, params))) return rc;
     if (!bytes) return PPN_E_BADARG;
-    *bytes = carve(shape, params->n_nms_parts).total;
+    *bytes = 2 * carve(shape, params->n_nms_parts).total;         // two sets, used alternately
     return PPN_OK;
 }
 
@@ -304,8 +317,8 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     if (reinterpret_cast<uintptr_t>(out->part_box) & 15) return PPN_E_BADARG;
     const int P = params->n_nms_parts;
     const Workspace w = carve(shape, P);
-    if (workspace_bytes < w.total) return PPN_E_WORKSPACE;
-    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    if (workspace_bytes < 2 * w.total) return PPN_E_WORKSPACE;
+    unsigned char* ws = static_cast<unsigned char*>(workspace) + (next_parity(workspace) ? w.total : 0);
     uint16_t* amax = reinterpret_cast<uint16_t*>(ws + w.amax);
     int32_t* keep_idx = reinterpret_cast<int32_t*>(ws + w.keep_idx);
     int32_t* keep_count = reinterpret_cast<int32_t*>(ws + w.keep_count);
@@ -324,16 +337,29 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     cudaEvent_t* ev = profile_slot();
     const int mode = ev ? 0 : g_tuning.parse_overlap;
     if (mode == 2) {
+        using namespace ppn;
         bool chained = false;
         // K12 is itself a programmatic dependent of whatever precedes it in the stream (normally the
-        // previous call's K4, which triggers early): it becomes resident under that kernel, WAITS for
-        // it to complete, then releases K3 — only the launch latency between calls is hidden.
-        if ((e = ppn::launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, true,
-                                        g_tuning.parse_chain_calls != 0)) != cudaSuccess) return (int)e;
-        if ((e = ppn::launch_limb_argmax(head, amax, g, g_tuning, st, true, &chained)) != cudaSuccess) return (int)e;
-        if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr, keep_idx,
-                                        keep_count, out->count, out->root_cell, out->part_cell, out->part_score,
-                                        out->part_box, out->R, st, chained, g_tuning.parse_stage_all)) != cudaSuccess) return (int)e;
+        // previous call's K4, which triggers once it is past its own wait): it becomes resident under
+        // that kernel.
+        //  * default: it WAITS for that kernel to complete before reading anything (the producer of
+        //    `head` may be that kernel), then releases K3 — only launch latency is hidden;
+        //  * PPN_FLAG_INPUT_COMPLETE: the caller vouches that `head` was completely written before the
+        //    call was enqueued, so K12 and K3 start at once, beside the previous call's tree parse
+        //    (which reads the OTHER workspace set), and K12 only waits for that kernel before it
+        //    COMPLETES.  Completion stays transitive: K4(i+1) waits for K3(i+1), which waits at its end
+        //    for K12(i+1), which waits at its end for K4(i) — so calls complete in order, the two
+        //    workspace sets are never shared, and no waiting kernel can starve the one it waits for
+        //    (K12(i+1) is only launched once every CTA of K4(i) is resident and running).
+        const bool overlap_calls = (params->flags & PPN_FLAG_INPUT_COMPLETE) != 0;
+        const bool chain_calls = g_tuning.parse_chain_calls != 0;
+        if ((e = launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, chain_calls,
+                                   PDL_TRIGGER | (!chain_calls ? 0 : (overlap_calls ? PDL_WAIT_END : PDL_WAIT_START)))) != cudaSuccess) return (int)e;
+        if ((e = launch_limb_argmax(head, amax, g, g_tuning, st, true, &chained)) != cudaSuccess) return (int)e;
+        if ((e = launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr, keep_idx,
+                                   keep_count, out->count, out->root_cell, out->part_cell, out->part_score, out->part_box,
+                                   out->R, st, chained, chained ? (PDL_WAIT_START | PDL_TRIGGER) : 0, g_tuning.parse_stage_all,
+                                   g_tuning.parse_threads)) != cudaSuccess) return (int)e;
         return PPN_OK;
     }
     cudaStream_t side = st;
@@ -358,7 +384,7 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     if (ev) cudaEventRecord(ev[6], st);
     if ((e = ppn::launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr /*keep_idx holds cells*/,
                                     keep_idx, keep_count, out->count, out->root_cell, out->part_cell, out->part_score,
-                                    out->part_box, out->R, st, false, g_tuning.parse_stage_all)) != cudaSuccess) return (int)e;
+                                    out->part_box, out->R, st, false, 0, g_tuning.parse_stage_all, g_tuning.parse_threads)) != cudaSuccess) return (int)e;
     if (ev) cudaEventRecord(ev[7], st);
     return PPN_OK;
 }
@@ -449,7 +475,7 @@ HostPlan plan_host(const PPNShape* s, const PPNParams* p, int R) {
     cs.B = h.chunk;
     const size_t per_img = ((size_t)6 * s->K + (size_t)s->sH * s->sW * s->E) * s->H * s->W * sizeof(float);
     h.head_bytes = align_up(per_img * h.chunk, 256);
-    h.ws_bytes = carve(&cs, p->n_nms_parts).total;
+    h.ws_bytes = 2 * carve(&cs, p->n_nms_parts).total;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t at = off; off = align_up(off + bytes, 256); return at; };
     h.off_head[0] = take(h.head_bytes); h.off_head[1] = take(h.head_bytes);

@@ -130,6 +130,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // Programmatic dependent launch (PDL): let the next kernel in the stream start its prologue /
 // wait until every kernel this one depends on has completed and flushed.  Both are no-ops when
 // the kernel was launched without a programmatic dependency.
+enum : int {
+    PDL_TRIGGER = 1,       // let the next kernel in the stream become resident now
+    PDL_WAIT_START = 2,    // wait for the previous kernel before reading anything it (or a producer) wrote
+    PDL_WAIT_END = 4,      // wait for the previous kernel before completing (keeps completion transitive)
+};
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -52,7 +52,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
         }
         fence_mbar_init();
     }
-    if (pdl) pdl_launch_dependents();        // the tree-parse kernel may start its prologue now
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the tree-parse kernel may start its prologue now
     __syncthreads();
 
     if (tid >= n_cons) {
@@ -157,7 +157,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
     }
     // In the PDL chain this kernel started without waiting for decode+NMS (it does not read their
     // output); it must not COMPLETE before they do, because the tree parse waits only for us.
-    if (pdl && tid == 0) pdl_wait();
+    if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
 }
 
 // Ring, second thread mapping, for SMALL matrices (S*HW*4 below ~64 KB): instead of splitting the
@@ -189,7 +189,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         }
         fence_mbar_init();
     }
-    if (pdl) pdl_launch_dependents();        // the tree-parse kernel may start its prologue now
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the tree-parse kernel may start its prologue now
     __syncthreads();
 
     if (tid >= n_cons) {
@@ -282,7 +282,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
             *reinterpret_cast<uint2*>(amax + (size_t)m * g.HW + 4 * cv) = make_uint2(lo, hi);
         }
     }
-    if (pdl && tid == 0) pdl_wait();         // see limb_argmax_tma_kernel
+    if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();    // see limb_argmax_tma_kernel
 }
 
 // Variant without the ring: one CTA per matrix, 128-bit streaming loads straight to registers.
@@ -436,8 +436,18 @@ struct NmsSmem {
     float* sarea;                 // [stride]
     int32_t* sidx;                // [stride] index into the unsorted list
     int32_t* rank;                // [stride] rank accumulators of the split counting sort
-    unsigned* mask;               // [n * ceil(n/32)]
+    unsigned* mask;               // upper triangle of the n x n bit matrix, see tri_row()
 };
+
+// The suppression matrix only has bits j > i.  Row i of 32-row block k = i / 32 stores the words
+// wj = k .. Wd-1 (Wd - k of them), rows packed block after block: half the shared memory of the
+// square layout (21.9 KB instead of 41.5 KB at 576 boxes), which is what lets this kernel sit
+// beside the arg-max ring on the same SM.
+__device__ __forceinline__ int tri_block_base(int k, int Wd) { return 32 * (k * Wd - ((k * (k - 1)) >> 1)); }
+__device__ __forceinline__ int tri_row(int i, int Wd) {          // offset of word (i, wj = i / 32)
+    const int k = i >> 5;
+    return tri_block_base(k, Wd) + (i - (k << 5)) * (Wd - k);
+}
 
 __device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int stride) {
     NmsSmem s;
@@ -507,6 +517,7 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
     for (int i = warp; i < n; i += n_warps) {
         const float4 bi = s.sbox[i];
         const float ai = s.sarea[i];
+        unsigned* mrow = s.mask + tri_row(i, Wd) - (i >> 5);     // mrow[wj] = word (i, wj), wj >= i / 32
         for (int wj = i >> 5; wj < Wd; ++wj) {
             const int j = (wj << 5) + lane;
             bool bit = false;
@@ -516,7 +527,7 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
                               : suppresses_finite(bj, s.sarea[j], bi, ai, thr, thr_pos);
             }
             const unsigned word = __ballot_sync(0xffffffffu, bit);
-            if (lane == 0) s.mask[(size_t)i * Wd + wj] = word;
+            if (lane == 0) mrow[wj] = word;
         }
     }
     __syncthreads();
@@ -530,7 +541,9 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         const int i0 = w << 5;
         const int nb = min(32, n - i0);
         const unsigned valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        const unsigned diag = (lane < nb) ? s.mask[(size_t)(i0 + lane) * Wd + w] : 0u;
+        const int row_len = Wd - w;                               // words per row in this block
+        const unsigned* blk = s.mask + tri_block_base(w, Wd);     // blk[t * row_len + (l - w)] = word (i0 + t, l)
+        const unsigned diag = (lane < nb) ? blk[lane * row_len] : 0u;
         unsigned kept = 0;
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
@@ -553,14 +566,14 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         }
         m += __popc(kept);
         if (lane > w && lane < Wd) {
-            const unsigned* row = s.mask + (size_t)i0 * Wd + lane;
+            const unsigned* row = blk + (lane - w);
             unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
             for (int t = 0; t < 32; t += 4) {
-                if ((kept >> t) & 1u) a0 |= row[(size_t)t * Wd];
-                if ((kept >> (t + 1)) & 1u) a1 |= row[(size_t)(t + 1) * Wd];
-                if ((kept >> (t + 2)) & 1u) a2 |= row[(size_t)(t + 2) * Wd];
-                if ((kept >> (t + 3)) & 1u) a3 |= row[(size_t)(t + 3) * Wd];
+                if ((kept >> t) & 1u) a0 |= row[t * row_len];
+                if ((kept >> (t + 1)) & 1u) a1 |= row[(t + 1) * row_len];
+                if ((kept >> (t + 2)) & 1u) a2 |= row[(t + 2) * row_len];
+                if ((kept >> (t + 3)) & 1u) a3 |= row[(t + 3) * row_len];
             }
             removed |= (a0 | a1) | (a2 | a3);
         }
@@ -597,8 +610,8 @@ decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det
     // pdl & 2: launched as a programmatic dependent itself (of the previous call's tree parse, or of
     // whatever kernel produced `head`): it may have become resident early, so it must wait before it
     // reads anything.  pdl & 1: then release the arg-max kernel, which needs nothing from this one.
-    if (pdl & 2) pdl_wait();
-    if (pdl & 1) pdl_launch_dependents();
+    if (pdl & PDL_WAIT_START) pdl_wait();
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();
     __shared__ int warp_tot[16];
     __shared__ int base_s;
     float4* ubox = reinterpret_cast<float4*>(smem);                         // [HW] candidate boxes, cell order
@@ -641,9 +654,15 @@ decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det
     }
     const int n = base_s;
     const size_t list = ((size_t)b * n_parts + k) * g.HW;
-    if (n == 0) { if (tid == 0) keep_count[(size_t)b * n_parts + k] = 0; return; }
-    const int m = nms_core(s, ubox, n, nms_thr, 0, keep_cell + list, ucell);
-    if (tid == 0) keep_count[(size_t)b * n_parts + k] = m;
+    int m = 0;
+    if (n > 0) m = nms_core(s, ubox, n, nms_thr, 0, keep_cell + list, ucell);
+    if (tid == 0) {
+        keep_count[(size_t)b * n_parts + k] = m;
+        // overlapped calls (PPN_FLAG_INPUT_COMPLETE): this kernel started without waiting for the
+        // previous call's tree parse; it must not COMPLETE before it, so that "the arg-max kernel
+        // completed" (which waits for us) still implies "everything of the previous call completed"
+        if (pdl & PDL_WAIT_END) pdl_wait();
+    }
 }
 
 // Lists longer than PPN_MAX_CELLS: no bitmask; the CTA visits boxes in order and, for every box
@@ -743,7 +762,7 @@ __device__ __forceinline__ void walk_chain(const ChainTable& ch, int cidx, int r
     }
 }
 
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(1024)
 tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
                   const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
                   const int32_t* __restrict__ keep_idx, const int32_t* __restrict__ keep_count,
@@ -751,21 +770,24 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
                   float* __restrict__ h_score, float4* __restrict__ h_box, int R, int use_tma, int stage_all, int pdl) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int KHW = g.K * g.HW;
-    const int n_groups = stage_all ? 6 : 2;            // resp, conf [, x, y, w, h]: adjacent channel groups
-    float* s_resp = reinterpret_cast<float*>(smem);                                    // [n_groups][K*HW]
-    float* s_conf = s_resp + KHW;
-    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_resp + (size_t)n_groups * KHW);   // [E*HW] (+pad)
+    // staged channel groups: 0 = none (big grids: the walk reads resp/conf through L2 and the CTA
+    // stays light enough to sit beside the arg-max ring), 2 = resp, conf, 6 = also x, y, w, h
+    const int n_groups = stage_all;
+    float* s_planes = reinterpret_cast<float*>(smem);                                  // [n_groups][K*HW]
+    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_planes + (size_t)n_groups * KHW); // [E*HW] (+pad)
     int32_t* s_root = reinterpret_cast<int32_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [HW]
     int32_t* s_slot = s_root + g.HW;                                                   // [HW]
     int32_t* s_dyx = s_slot + g.HW;                                                    // [S] if small
     int16_t* s_pos = reinterpret_cast<int16_t*>(s_dyx + (g.S <= kMaxDyxTable ? g.S : 0));   // [HW][K]
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int warp_tot[8];
+    __shared__ int warp_tot[32];
     __shared__ int base_s;
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const float* img = head + (size_t)b * g.img_stride;
+    const float* s_resp = n_groups ? s_planes : img;              // generic pointers: shared or global
+    const float* s_conf = s_resp + KHW;
     const uint16_t* am = amax + (size_t)b * g.E * g.HW;
     const bool use_tab = g.S <= kMaxDyxTable;
     const uint32_t bytes_planes = (uint32_t)n_groups * KHW * 4u, bytes_am = (uint32_t)g.E * g.HW * 2u;
@@ -776,10 +798,10 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             mbar_init(&bar, 1);
             fence_mbar_init();
             mbar_arrive_expect_tx(&bar, bytes_planes + bytes_am);
-            bulk_g2s(s_resp, img, bytes_planes, &bar);
+            if (bytes_planes) bulk_g2s(s_planes, img, bytes_planes, &bar);
         }
     } else {
-        for (int i = tid; i < n_groups * KHW; i += T) s_resp[i] = __ldg(img + i);
+        for (int i = tid; i < n_groups * KHW; i += T) s_planes[i] = __ldg(img + i);
     }
     if (tid == 0) base_s = 0;
     if (use_tab)
@@ -788,10 +810,8 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             s_dyx[a] = ((dy - g.off_h) << 16) | ((dx - g.off_w) & 0xffff);
         }
     // ---- from here on we read what the arg-max and decode+NMS kernels wrote ---------------------
-    if (pdl) {
-        pdl_wait();
-        pdl_launch_dependents();             // the NEXT call's decode+NMS may become resident (it waits for us)
-    }
+    if (pdl & PDL_WAIT_START) pdl_wait();
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the NEXT call's decode+NMS may become resident
     if (use_tma) {
         if (tid == 0 && bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
     } else {
@@ -870,9 +890,9 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
                     ss[u] = sl;
                     if (cc[u] >= 0) {
                         const int at = t * g.HW + cc[u];
-                        if (stage_all) {
-                            xs[u] = s_resp[2 * KHW + at]; ys[u] = s_resp[3 * KHW + at];
-                            ws[u] = s_resp[4 * KHW + at]; hs[u] = s_resp[5 * KHW + at];
+                        if (n_groups == 6) {
+                            xs[u] = s_planes[2 * KHW + at]; ys[u] = s_planes[3 * KHW + at];
+                            ws[u] = s_planes[4 * KHW + at]; hs[u] = s_planes[5 * KHW + at];
                         } else {
                             xs[u] = __ldg(img + (size_t)2 * KHW + at); ys[u] = __ldg(img + (size_t)3 * KHW + at);
                             ws[u] = __ldg(img + (size_t)4 * KHW + at); hs[u] = __ldg(img + (size_t)5 * KHW + at);
@@ -1069,8 +1089,9 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
 }
 
 cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
-                               bool pdl, bool* pdl_used) {
+                               bool pdl, bool* pdl_used, int pdl_bits) {
     if (pdl_used) *pdl_used = false;
+    if (pdl_bits < 0) pdl_bits = pdl ? (PDL_TRIGGER | PDL_WAIT_END) : 0;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
     if (e != cudaSuccess) return e;
@@ -1094,12 +1115,12 @@ cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g,
                 if (grid > n_items) grid = n_items;
                 if ((e = ensure_smem(limb_argmax_tma_multi_kernel, p.smem_bytes, &d->tma_multi)) != cudaSuccess) return e;
                 e = launch_kernel(limb_argmax_tma_multi_kernel, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
-                                  head, amax, g, p, pdl ? 1 : 0, ticket);
+                                  head, amax, g, p, pdl_bits, ticket);
             } else {
                 if (grid > n_mats) grid = n_mats;
                 if ((e = ensure_smem(limb_argmax_tma_kernel, p.smem_bytes, &d->tma)) != cudaSuccess) return e;
                 e = launch_kernel(limb_argmax_tma_kernel, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
-                                  head, amax, g, p, pdl ? 1 : 0, ticket);
+                                  head, amax, g, p, pdl_bits, ticket);
             }
             if (pdl_used) *pdl_used = pdl;
             return e;
@@ -1145,7 +1166,8 @@ cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float
 }
 
 size_t nms_smem_bytes(int stride) {
-    const size_t words = (size_t)stride * ((stride + 31) / 32);
+    const size_t Wd = (stride + 31) / 32;
+    const size_t words = 32 * Wd * (Wd + 1) / 2;                  // upper triangle, whole 32-row blocks
     return (size_t)stride * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float) + 2 * sizeof(int32_t)) + words * sizeof(unsigned);
 }
 
@@ -1181,7 +1203,7 @@ size_t decode_nms_smem_bytes(const Geom& g) {
 }
 
 cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
-                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_trigger, bool pdl_self) {
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr, int pdl_bits) {
     if (g.B == 0 || n_parts == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -1190,12 +1212,12 @@ cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, flo
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(decode_nms_kernel, smem, &d->decode_nms)) != cudaSuccess) return e;
     dim3 grid(g.B, n_parts);
-    return launch_kernel(decode_nms_kernel, grid, dim3(g.HW <= 256 ? 256 : 512), smem, st, pdl_self, head, g, n_parts, det_thr,
-                         nms_thr, keep_cell, keep_count, (pdl_trigger ? 1 : 0) | (pdl_self ? 2 : 0));
+    return launch_kernel(decode_nms_kernel, grid, dim3(g.HW <= 256 ? 256 : 512), smem, st, pdl_attr, head, g, n_parts, det_thr,
+                         nms_thr, keep_cell, keep_count, pdl_bits);
 }
 
-size_t tree_parse_smem_bytes(const Geom& g, bool stage_all) {
-    return (size_t)(stage_all ? 6 : 2) * g.K * g.HW * sizeof(float) +
+size_t tree_parse_smem_bytes(const Geom& g, int n_groups) {
+    return (size_t)n_groups * g.K * g.HW * sizeof(float) +
            ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
            (size_t)2 * g.HW * sizeof(int32_t) + (g.S <= kMaxDyxTable ? (size_t)g.S * sizeof(int32_t) : 0) +
            (((size_t)g.HW * g.K + 7) & ~(size_t)7) * sizeof(int16_t);
@@ -1204,20 +1226,27 @@ size_t tree_parse_smem_bytes(const Geom& g, bool stage_all) {
 cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
-                              float* h_score, float* h_box, int R, cudaStream_t st, bool pdl, int stage_all_pref) {
+                              float* h_score, float* h_box, int R, cudaStream_t st, bool pdl_attr, int pdl_bits,
+                              int stage_all_pref, int threads_pref) {
     if (g.B == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
     if (e != cudaSuccess) return e;
-    const int threads = 256;
-    // x, y, w, h can be staged beside resp, conf so that the write-out needs no global gathers; by
-    // default only when that keeps the CTA small (<= 32 KB): a light CTA lets every image of the
-    // batch be resident at once and lets several start their prologue under the arg-max kernel's
-    // tail (PDL), which measured faster than saving the gathers at 62 KB per CTA
-    const size_t all_bytes = tree_parse_smem_bytes(g, true);
-    const bool stage_all = stage_all_pref < 0 ? all_bytes <= 32 * 1024
-                                              : (stage_all_pref > 0 && all_bytes <= (size_t)d->smem_optin);
-    const size_t smem = tree_parse_smem_bytes(g, stage_all);
+    // How much of the decode block is staged in shared memory (stage_all_pref: -1 auto, 0 none,
+    // 1 resp+conf, 2 all six groups).  Auto: all six when that keeps the CTA under 32 KB (tiny
+    // grids), resp+conf when under 64 KB (cfg2: 25 KB, cfg3: 57 KB), nothing otherwise — a light CTA lets every
+    // image be resident at once, several of them UNDER the arg-max ring, and under the next call's
+    // kernels (measured: at 24x24 the 107 KB staged CTA shut both overlaps out).
+    int n_groups;
+    if (stage_all_pref < 0)
+        n_groups = tree_parse_smem_bytes(g, 6) <= 32 * 1024 ? 6 : (tree_parse_smem_bytes(g, 2) <= 64 * 1024 ? 2 : 0);
+    else
+        n_groups = stage_all_pref >= 2 ? 6 : (stage_all_pref == 1 ? 2 : 0);
+    while (n_groups > 0 && tree_parse_smem_bytes(g, n_groups) > (size_t)d->smem_optin) n_groups = n_groups == 6 ? 2 : 0;
+    const size_t smem = tree_parse_smem_bytes(g, n_groups);
+    // one thread per (chain, root) in the walk and per (human, part) pair in the write-out
+    int threads = threads_pref > 0 ? threads_pref : ((g.HW <= 144 || n_groups == 0) ? 256 : 512);
+    threads = ((threads < 64 ? 64 : (threads > 1024 ? 1024 : threads)) + 31) & ~31;
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     if ((e = ensure_smem(tree_parse_kernel, smem, &d->tree)) != cudaSuccess) return e;
     // bulk copies need 16-byte sizes and sources: the staged planes are 4*n*K*HW bytes at image
@@ -1225,9 +1254,9 @@ cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable
     const bool tma_ok = ((size_t)g.K * g.HW * 8) % 16 == 0 && (g.img_stride * 4) % 16 == 0 &&
                         ((size_t)g.E * g.HW * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(head) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(amax) & 15) == 0;
-    return launch_kernel(tree_parse_kernel, dim3(g.B), dim3(threads), smem, st, pdl, head, g, ch, thr, min_kp, n_parts, amax,
+    return launch_kernel(tree_parse_kernel, dim3(g.B), dim3(threads), smem, st, pdl_attr, head, g, ch, thr, min_kp, n_parts, amax,
                          cand_cell, keep_idx, keep_count, h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box),
-                         R, tma_ok ? 1 : 0, stage_all ? 1 : 0, pdl ? 1 : 0);
+                         R, tma_ok ? 1 : 0, n_groups, pdl_bits);
 }
 
 }  // namespace ppn

@@ -7,13 +7,14 @@ namespace ppn {
 struct Tuning {
     int argmax_variant = 0;            // 0 = TMA bulk-copy ring (persistent), 1 = direct 128-bit loads
     int argmax_stage_bytes = 32 * 1024;
-    int argmax_stages = 5;
+    int argmax_stages = 4;
     int argmax_threads = 320;          // target consumer threads per CTA
     int argmax_ctas_per_sm = 1;
     int argmax_split = -1;             // -1 auto, 0 = groups split rows, 1 = groups take one matrix each
     int argmax_dynamic = 1;            // ring kernels draw work from a global ticket counter (0: static round-robin)
     int argmax_tail_opt = 0;           // split-matrix mode: pick matrices/item that fills the last wave best
-    int parse_stage_all = -1;          // tree parse stages x,y,w,h too: -1 auto (when small), 0 never, 1 if it fits
+    int parse_stage_all = -1;          // tree parse stages: -1 auto, 0 nothing, 1 resp+conf, 2 all six groups
+    int parse_threads = 0;             // tree-parse CTA size, 0 = by grid size
     int parse_chain_calls = 1;         // PDL chain: the first kernel of a call is a programmatic dependent too
     int host_chunk_images = 64;
     int parse_overlap = 2;             // 0 serial; 1 decode+NMS on a side stream beside the arg-max;
@@ -39,7 +40,7 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p);
 // pdl: launch as a programmatic dependent of the previous kernel in `st` (starts beside it, waits
 // for it only before completing); *pdl_used tells whether the chosen kernel variant honoured it.
 cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
-                               bool pdl = false, bool* pdl_used = nullptr);
+                               bool pdl = false, bool* pdl_used = nullptr, int pdl_bits = -1 /* default: trigger + end wait */);
 
 cudaError_t launch_decode_candidates(const float* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
                                      float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st);
@@ -49,8 +50,8 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
 
 // fused K1+K2 of the whole-path call: surviving root cells per (image, part), nothing else
 cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
-                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_trigger = false,
-                              bool pdl_self = false);
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr = false,
+                              int pdl_bits = 0);
 
 cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* ry, size_t n, int H, int W,
                               float gridW, float gridH, cudaStream_t st);
@@ -61,11 +62,12 @@ cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const 
                                int K, int cap, int32_t* header, int32_t* rec_cell, float* rec_score, float* rec_box,
                                cudaStream_t st);
 
-size_t tree_parse_smem_bytes(const Geom& g, bool stage_all);
+size_t tree_parse_smem_bytes(const Geom& g, int n_groups);
 
 cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
-                              float* h_score, float* h_box, int R, cudaStream_t st, bool pdl = false, int stage_all_pref = -1);
+                              float* h_score, float* h_box, int R, cudaStream_t st, bool pdl_attr = false, int pdl_bits = 0,
+                              int stage_all_pref = -1, int threads_pref = 0);
 
 }  // namespace ppn

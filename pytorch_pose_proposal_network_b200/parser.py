@@ -40,9 +40,13 @@ class _CConfig:
         self._shape_fields = dict(K=cfg.K, E=cfg.E, H=cfg.H, W=cfg.W, sH=cfg.sH, sW=cfg.sW, inW=cfg.inW, inH=cfg.inH,
                                   gridW=gW, gridH=gH, off_h=cfg.off_h, off_w=cfg.off_w)
         # numpy demotes the Python-float thresholds to fp32 when comparing with fp32 arrays
-        self.params = _lib.PPNParams(
+        self.params = self._make_params(cfg, n_nms_parts, 0)
+        self.params_input_complete = self._make_params(cfg, n_nms_parts, _lib.FLAG_INPUT_COMPLETE)
+
+    def _make_params(self, cfg, n_nms_parts, flags):
+        return _lib.PPNParams(
             float(np.float32(cfg.detection_thresh)), float(np.float32(cfg.nms_thresh)), int(cfg.min_num_keypoints),
-            int(n_nms_parts), len(self.off) - 1,
+            int(n_nms_parts), len(self.off) - 1, int(flags),
             self.off.ctypes.data_as(_lib.i32p), self.limb.ctypes.data_as(_lib.i32p), self.part.ctypes.data_as(_lib.i32p))
 
     def shape(self, B: int) -> _lib.PPNShape:
@@ -196,11 +200,17 @@ class PoseParser:
                               out.part_score.data_ptr(), out.part_box.data_ptr(), out.R)
 
     # ---- the whole path ---------------------------------------------------------------- #
-    def parse(self, head: torch.Tensor, out: Optional[PackedHumans] = None) -> PackedHumans:
+    def parse(self, head: torch.Tensor, out: Optional[PackedHumans] = None, input_complete: bool = False) -> PackedHumans:
         """Enqueue the whole path for a device batch on torch's current stream (asynchronous).
 
         ``out`` may be a preallocated :meth:`alloc_output` to reuse; otherwise the parser's own
         buffer is returned and overwritten by the next call.
+
+        ``input_complete=True`` (``PPN_FLAG_INPUT_COMPLETE``) is a promise that ``head`` was fully
+        written before this call — e.g. it has been resident since an earlier, finished step — not
+        just ordered before it on the stream by a producer kernel that may still be running.  The
+        call may then overlap the previous ``parse`` on this stream (its arg-max streams while the
+        previous call's tree parse finishes); give consecutive overlapping calls different ``out``.
         """
         B = self._check_head(head)
         if head.device != self.device:
@@ -214,7 +224,8 @@ class PoseParser:
         ws = self._workspace(B)
         hs = self._humans_struct(out)
         with self._guard():
-            rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B)), C.byref(self.c.params), C.byref(hs),
+            params = self.c.params_input_complete if input_complete else self.c.params
+            rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B)), C.byref(params), C.byref(hs),
                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             raise _lib.PPNError(rc, "ppn_parse")

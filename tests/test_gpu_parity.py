@@ -158,7 +158,7 @@ def test_batch_matches_c_oracle(preset, dist, B):
     assert_packed_equals_oracle(host.numpy(), ref, B)
 
 
-TUNE_DEFAULTS = dict(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=5, argmax_threads=320,
+TUNE_DEFAULTS = dict(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=4, argmax_threads=320,
                      argmax_ctas_per_sm=1, argmax_split=-1, argmax_dynamic=1, argmax_tail_opt=0)
 
 
@@ -211,6 +211,35 @@ def test_limb_argmax_work_distribution(preset, dynamic, tail_opt, ctas):
             assert np.array_equal(got2.cpu().numpy(), want), rep
     finally:
         _lib.tune(**TUNE_DEFAULTS)
+
+
+@pytest.mark.parametrize("preset,dist,B", [("cfg2", "U", 40), ("cfg3", "D", 24), ("cfg4", "U", 10)])
+def test_overlapped_consecutive_calls(preset, dist, B):
+    """PPN_FLAG_INPUT_COMPLETE: back-to-back calls overlap (call i's tree parse under call i+1's
+    arg-max, alternating workspace sets).  Every call's result must still be exact, with inputs and
+    outputs changing from call to call and the modes interleaved."""
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    n_in = 5
+    heads = [synth.make_head(g, dist, seed=500 + i, B=B) for i in range(n_in)]
+    refs = [c_oracle.parse_batch(h, g, n_threads=8) for h in heads]
+    devs = [torch.from_numpy(h).cuda() for h in heads]
+    parser = PoseParser(cfg)
+    n_calls = 23
+    outs = [parser.alloc_output(B) for _ in range(n_calls)]
+    torch.cuda.synchronize()
+    for i in range(n_calls):
+        parser.parse(devs[i % n_in], out=outs[i], input_complete=(i % 7 != 3))     # mostly overlapped, some not
+    torch.cuda.synchronize()
+    for i in range(n_calls):
+        assert_packed_equals_oracle(outs[i].numpy(), refs[i % n_in], B)
+    # same output buffer reused by overlapping calls: the last writer must win cleanly
+    for i in range(6):
+        last = parser.parse(devs[i % n_in], out=outs[0], input_complete=True)
+    torch.cuda.synchronize()
+    assert_packed_equals_oracle(last.numpy(), refs[5 % n_in], B)
 
 
 def test_every_launch_ordering_gives_same_result():
@@ -322,6 +351,25 @@ def test_edge_cases_match_oracle():
         packed = PoseParser(c2).parse(torch.from_numpy(head).cuda()).numpy()
         assert_packed_equals_oracle(packed, ref, head.shape[0])
     assert ref["counts"][0, 0] == 0 and ref["counts"][1, 0] == 0 and ref["counts"][2, 0] == 1
+
+
+@pytest.mark.parametrize("threads,stage", [(64, 0), (160, 1), (512, 2), (1024, 0), (256, 1), (256, 2)])
+@pytest.mark.parametrize("preset,dist", [("cfg2", "D"), ("cfg4", "U")])
+def test_tree_parse_cta_sizes_and_staging(preset, dist, threads, stage):
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    B = 6
+    head = synth.make_head(g, dist, seed=31, B=B)
+    ref = c_oracle.parse_batch(head, g, n_threads=8)
+    _lib.tune(parse_threads=threads, parse_stage_all=stage)
+    try:
+        packed = PoseParser(cfg).parse(torch.from_numpy(head).cuda()).numpy()
+    finally:
+        _lib.tune(parse_threads=0, parse_stage_all=-1)
+    assert_packed_equals_oracle(packed, ref, B)
 
 
 def test_track_orders_that_are_not_a_tree():
