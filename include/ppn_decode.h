@@ -162,14 +162,16 @@ int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params,
 int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParams* params,
                    const PPNHumans* out_host, void* dev_scratch, size_t dev_scratch_bytes);
 
-/* Dense pose records for shipping results (the multi-GPU gather): one contiguous device buffer
- *   int32 header[2 + B] = {total records, overflow flag, count[B]}
- *   int32 cell [cap][K], float score[cap][K], float box[cap][K][4]     (256-byte aligned blocks)
- * image b's min(count[b], R) humans start at record sum_{i<b} min(count[i], R); records beyond
- * `cap_records` are dropped and the overflow flag is set.  ppn_packed_bytes gives the buffer size
- * and, if `offsets` != NULL, the byte offsets of {header, cell, score, box}. */
-int ppn_packed_bytes(int32_t B, int32_t K, int32_t cap_records, size_t* bytes, size_t* offsets /*[4] or NULL*/);
-int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_records,
+/* Dense pose ENTRIES for shipping results (the multi-GPU gather): one contiguous device buffer
+ *   int32  header[2 + 2B] = {total entries, overflow flag, count[B] humans, entries[B] per image}
+ *   uint32 idcell[cap]    = part id << 16 | cell      float score[cap]      float box[cap][4]
+ * (256-byte aligned blocks).  One entry per PRESENT part; a human's root (part 0) is its first
+ * entry, so an entry with part id 0 starts a new human and the list needs no per-human table.
+ * Image b's entries start at sum_{i<b} entries[i]; entries beyond `cap_entries` are dropped and
+ * the overflow flag is set.  ppn_packed_bytes gives the buffer size and, if `offsets` != NULL,
+ * the byte offsets of {header, idcell, score, box}. */
+int ppn_packed_bytes(int32_t B, int32_t cap_entries, size_t* bytes, size_t* offsets /*[4] or NULL*/);
+int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_entries,
                     void* packed, size_t packed_bytes, void* stream);
 
 /* Per-stage timing of ppn_parse for benchmarks.  After ppn_profile_enable(1) every ppn_parse

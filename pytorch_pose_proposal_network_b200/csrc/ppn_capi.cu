@@ -389,41 +389,42 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     return PPN_OK;
 }
 
-// ---- dense pose records ----------------------------------------------------------------------
+// ---- dense pose entries ----------------------------------------------------------------------
 namespace {
-struct PackedLayout { size_t header, cell, score, box, total; };
-PackedLayout packed_layout(int B, int K, int cap) {
+struct PackedLayout { size_t header, idcell, score, box, total; };
+PackedLayout packed_layout(int B, int cap) {
     PackedLayout l;
     l.header = 0;
-    l.cell = align_up((size_t)(2 + B) * sizeof(int32_t), 256);
-    l.score = l.cell + align_up((size_t)cap * K * sizeof(int32_t), 256);
-    l.box = l.score + align_up((size_t)cap * K * sizeof(float), 256);
-    l.total = l.box + align_up((size_t)cap * K * 4 * sizeof(float), 256);
+    l.idcell = align_up((size_t)(2 + 2 * (size_t)B) * sizeof(int32_t), 256);
+    l.score = l.idcell + align_up((size_t)cap * sizeof(uint32_t), 256);
+    l.box = l.score + align_up((size_t)cap * sizeof(float), 256);
+    l.total = l.box + align_up((size_t)cap * 4 * sizeof(float), 256);
     return l;
 }
 }  // namespace
 
-int ppn_packed_bytes(int32_t B, int32_t K, int32_t cap_records, size_t* bytes, size_t* offsets) {
-    if (B < 0 || K < 1 || cap_records < 0 || !bytes) return PPN_E_BADARG;
-    const PackedLayout l = packed_layout(B, K, cap_records);
+int ppn_packed_bytes(int32_t B, int32_t cap_entries, size_t* bytes, size_t* offsets) {
+    if (B < 0 || cap_entries < 0 || !bytes) return PPN_E_BADARG;
+    const PackedLayout l = packed_layout(B, cap_entries);
     *bytes = l.total;
-    if (offsets) { offsets[0] = l.header; offsets[1] = l.cell; offsets[2] = l.score; offsets[3] = l.box; }
+    if (offsets) { offsets[0] = l.header; offsets[1] = l.idcell; offsets[2] = l.score; offsets[3] = l.box; }
     return PPN_OK;
 }
 
-int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_records, void* packed, size_t packed_bytes,
+int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_entries, void* packed, size_t packed_bytes,
                     void* stream) {
     int rc = check_humans(humans);
     if (rc) return rc;
-    if (B < 0 || K < 1 || cap_records < 0) return PPN_E_BADARG;
+    if (B < 0 || K < 1 || cap_entries < 0) return PPN_E_BADARG;
+    if (K > 65535 || humans->R > 65536) return PPN_E_UNSUPPORTED;          // part id and cell share 32 bits
     if (B == 0) return PPN_OK;
     if (!packed || (reinterpret_cast<uintptr_t>(packed) & 255)) return PPN_E_BADARG;
-    const PackedLayout l = packed_layout(B, K, cap_records);
+    const PackedLayout l = packed_layout(B, cap_entries);
     if (packed_bytes < l.total) return PPN_E_WORKSPACE;
     unsigned char* p = static_cast<unsigned char*>(packed);
     return cuda_rc(ppn::launch_pack_humans(humans->count, humans->part_cell, humans->part_score, humans->part_box, B,
-                                           humans->R, K, cap_records, reinterpret_cast<int32_t*>(p + l.header),
-                                           reinterpret_cast<int32_t*>(p + l.cell), reinterpret_cast<float*>(p + l.score),
+                                           humans->R, K, cap_entries, reinterpret_cast<int32_t*>(p + l.header),
+                                           reinterpret_cast<uint32_t*>(p + l.idcell), reinterpret_cast<float*>(p + l.score),
                                            reinterpret_cast<float*>(p + l.box), (cudaStream_t)stream));
 }
 

@@ -924,37 +924,101 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
 }
 
 // =========================================================================================
-// pack — dense pose records for the multi-GPU gather
+// pack — dense pose entries for the multi-GPU gather
 // =========================================================================================
-// Fixed-stride PPNHumans -> one contiguous buffer: header {total, overflow, count[B]} followed by
-// record arrays cell[cap][K], score[cap][K], box[cap][K][4]; image b's humans start at record
-// sum(count[0..b)).  One CTA per image; every CTA sums the counts before it (B loads, coalesced).
+// Fixed-stride PPNHumans -> one contiguous buffer of (human, part) ENTRIES, present parts only:
+//   header   int32 {total entries, overflow, count[B], entries[B]}
+//   idcell   uint32[cap]  = part id << 16 | cell        (the root, part 0, is always a human's first
+//   score    float [cap]                                  entry, so the list delimits itself)
+//   box      float4[cap]
+// Most humans have a few of K parts, so this is several times smaller than K slots per human.
+// Two launches: per-image entry counts, then one CTA per image places its entries behind the
+// entries of the images before it (B coalesced loads) and its humans behind one another (scan).
 __global__ void __launch_bounds__(256)
-pack_humans_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ cell, const float* __restrict__ score,
-                   const float4* __restrict__ box, int B, int R, int K, int cap,
-                   int32_t* __restrict__ header, int32_t* __restrict__ rec_cell, float* __restrict__ rec_score,
-                   float4* __restrict__ rec_box) {
+pack_count_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ cell, int R, int K,
+                  int32_t* __restrict__ header, int B) {
     __shared__ int red[8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(count[b], R);
+    const int32_t* c = cell + (size_t)b * R * K;
+    int present = 0;
+    for (int i = tid; i < n * K; i += blockDim.x) present += (c[i] >= 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) present += __shfl_xor_sync(0xffffffffu, present, o);
+    if (lane == 0) red[warp] = present;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) tot += red[wi];
+        header[2 + b] = count[b];
+        header[2 + B + b] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pack_entries_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ cell, const float* __restrict__ score,
+                    const float4* __restrict__ box, int B, int R, int K, int cap, int32_t* __restrict__ header,
+                    uint32_t* __restrict__ e_idcell, float* __restrict__ e_score, float4* __restrict__ e_box) {
+    extern __shared__ __align__(16) int s_start[];          // [n + 1] entry offset of every human of the image
+    __shared__ int red[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    const int32_t* per_image = header + 2 + B;
     int before = 0;
-    for (int i = tid; i < b; i += blockDim.x) before += min(count[i], R);
+    for (int i = tid; i < b; i += blockDim.x) before += per_image[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
     if (lane == 0) red[warp] = before;
     __syncthreads();
     int off = 0;
-    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) off += red[wi];
-    const int n = min(count[b], R);
-    if (tid == 0) {
-        header[2 + b] = count[b];
-        if (b == B - 1) { header[0] = off + n; header[1] = (off + n > cap) ? 1 : 0; }
+    for (int wi = 0; wi < n_warps; ++wi) off += red[wi];
+    if (tid == 0 && b == B - 1) {
+        const int total = off + per_image[b];
+        header[0] = total;
+        header[1] = total > cap ? 1 : 0;
     }
-    const int room = max(0, min(n, cap - off));          // records of this image that still fit
-    const size_t src = (size_t)b * R * K, dst = (size_t)off * K;
-    for (int i = tid; i < room * K; i += blockDim.x) {
-        rec_cell[dst + i] = cell[src + i];
-        rec_score[dst + i] = score[src + i];
-        rec_box[dst + i] = box[src + i];
+    const int n = min(count[b], R);
+    const int32_t* c = cell + (size_t)b * R * K;
+    // parts per human, one warp per human (lanes = parts, 32 at a time), then an exclusive scan
+    for (int h = warp; h < n; h += n_warps) {
+        int cnt = 0;
+        for (int t0 = 0; t0 < K; t0 += 32) {
+            const int t = t0 + lane;
+            cnt += __popc(__ballot_sync(0xffffffffu, t < K && c[h * K + t] >= 0));
+        }
+        if (lane == 0) s_start[h + 1] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {                                        // n <= 1024: 32 humans per step
+        int carry = 0;
+        for (int h0 = 0; h0 < n; h0 += 32) {
+            const int h = h0 + lane;
+            int v = h < n ? s_start[h + 1] : 0, incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (h < n) s_start[h + 1] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_start[0] = 0;
+    }
+    __syncthreads();
+    for (int h = warp; h < n; h += n_warps) {
+        int base = off + s_start[h];
+        for (int t0 = 0; t0 < K; t0 += 32) {
+            const int t = t0 + lane;
+            const int cc = t < K ? c[h * K + t] : -1;
+            const unsigned bal = __ballot_sync(0xffffffffu, cc >= 0);
+            const int pos = base + __popc(bal & ((1u << lane) - 1u));
+            if (cc >= 0 && pos < cap) {
+                const size_t src = ((size_t)b * R + h) * K + t;
+                e_idcell[pos] = ((uint32_t)t << 16) | (uint32_t)cc;
+                e_score[pos] = score[src];
+                e_box[pos] = box[src];
+            }
+            base += __popc(bal);
+        }
     }
 }
 
@@ -1190,11 +1254,15 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
 }
 
 cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const float* score, const float* box, int B, int R,
-                               int K, int cap, int32_t* header, int32_t* rec_cell, float* rec_score, float* rec_box,
+                               int K, int cap, int32_t* header, uint32_t* e_idcell, float* e_score, float* e_box,
                                cudaStream_t st) {
     if (B == 0) return cudaSuccess;
-    pack_humans_kernel<<<B, 256, 0, st>>>(count, cell, score, reinterpret_cast<const float4*>(box), B, R, K, cap, header,
-                                          rec_cell, rec_score, reinterpret_cast<float4*>(rec_box));
+    pack_count_kernel<<<B, 256, 0, st>>>(count, cell, R, K, header, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    pack_entries_kernel<<<B, 256, (size_t)(R + 1) * sizeof(int), st>>>(count, cell, score, reinterpret_cast<const float4*>(box),
+                                                                        B, R, K, cap, header, e_idcell, e_score,
+                                                                        reinterpret_cast<float4*>(e_box));
     return cudaGetLastError();
 }
 

@@ -59,7 +59,7 @@ cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float
                                 cudaStream_t st);
 
 cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const float* score, const float* box, int B, int R,
-                               int K, int cap, int32_t* header, int32_t* rec_cell, float* rec_score, float* rec_box,
+                               int K, int cap, int32_t* header, uint32_t* e_idcell, float* e_score, float* e_box,
                                cudaStream_t st);
 
 size_t tree_parse_smem_bytes(const Geom& g, int n_groups);

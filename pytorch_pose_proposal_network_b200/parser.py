@@ -111,20 +111,38 @@ class PackedHumans:
         return result
 
 
-def unpack_records(buf, B: int, K: int, cap_records: int, offsets):
-    """Host view of one dense record buffer (see include/ppn_decode.h, ppn_pack_humans).
+def unpack_entries(buf, B: int, cap_entries: int, offsets):
+    """Host view of one dense entry buffer (see include/ppn_decode.h, ppn_pack_humans).
 
-    buf: uint8 numpy array or CPU tensor.  Returns dict(total, overflow, count[B], start[B],
-    cell[cap,K], score[cap,K], box[cap,K,4]); image b's humans are records start[b] : start[b]+n."""
+    buf: uint8 numpy array or CPU tensor.  Returns dict(total, overflow, count[B] humans per image,
+    entries[B] per image, start[B] first entry of each image, part[cap], cell[cap], score[cap],
+    box[cap,4]).  Within an image an entry with part 0 starts a new human."""
     a = buf.numpy() if isinstance(buf, torch.Tensor) else np.asarray(buf)
-    o_h, o_c, o_s, o_b = offsets
-    header = a[o_h:o_h + 4 * (2 + B)].view(np.int32)
-    count = header[2:2 + B]
-    cell = a[o_c:o_c + 4 * cap_records * K].view(np.int32).reshape(cap_records, K)
-    score = a[o_s:o_s + 4 * cap_records * K].view(np.float32).reshape(cap_records, K)
-    box = a[o_b:o_b + 16 * cap_records * K].view(np.float32).reshape(cap_records, K, 4)
-    start = np.concatenate([[0], np.cumsum(count)[:-1]]).astype(np.int64) if B else np.zeros(0, np.int64)
-    return dict(total=int(header[0]), overflow=bool(header[1]), count=count, start=start, cell=cell, score=score, box=box)
+    o_h, o_i, o_s, o_b = offsets
+    header = a[o_h:o_h + 4 * (2 + 2 * B)].view(np.int32)
+    count, entries = header[2:2 + B], header[2 + B:2 + 2 * B]
+    idcell = a[o_i:o_i + 4 * cap_entries].view(np.uint32)
+    score = a[o_s:o_s + 4 * cap_entries].view(np.float32)
+    box = a[o_b:o_b + 16 * cap_entries].view(np.float32).reshape(cap_entries, 4)
+    start = np.concatenate([[0], np.cumsum(entries)[:-1]]).astype(np.int64) if B else np.zeros(0, np.int64)
+    return dict(total=int(header[0]), overflow=bool(header[1]), count=count, entries=entries, start=start,
+                part=(idcell >> 16).astype(np.int32), cell=(idcell & 0xffff).astype(np.int32), score=score, box=box)
+
+
+def entries_to_packed(rec, b: int, K: int):
+    """Rebuild image b's fixed-K arrays (part_cell [n,K], part_score [n,K], part_box [n,K,4]) from
+    unpack_entries() output — the inverse of the packing, for consumers and tests."""
+    s0, n_e = int(rec["start"][b]), int(rec["entries"][b])
+    part, cell = rec["part"][s0:s0 + n_e], rec["cell"][s0:s0 + n_e]
+    human = np.cumsum(part == 0) - 1                       # entry -> human index within the image
+    n = int(human[-1]) + 1 if n_e else 0
+    pc = np.full((n, K), -1, np.int32)
+    ps = np.zeros((n, K), np.float32)
+    pb = np.zeros((n, K, 4), np.float32)
+    pc[human, part] = cell
+    ps[human, part] = rec["score"][s0:s0 + n_e]
+    pb[human, part] = rec["box"][s0:s0 + n_e]
+    return pc, ps, pb
 
 
 class PoseParser:
@@ -255,35 +273,32 @@ class PoseParser:
                                                _ptr(self._host_scratch), self._host_scratch.numel()), "ppn_parse_host")
         return out
 
-    # ---- dense records (what the multi-GPU gather ships) -------------------------------- #
-    def packed_layout(self, B: int, cap_records: int):
-        """-> (bytes, (header, cell, score, box) byte offsets) of the dense record buffer."""
-        key = (B, cap_records)
+    # ---- dense entries (what the multi-GPU gather ships) -------------------------------- #
+    def packed_layout(self, B: int, cap_entries: int):
+        """-> (bytes, (header, idcell, score, box) byte offsets) of the dense entry buffer."""
+        key = (B, cap_entries)
         hit = self._layouts.get(key)
         if hit is not None:
             return hit
-        self._layouts[key] = self._packed_layout(B, cap_records)
-        return self._layouts[key]
-
-    def _packed_layout(self, B: int, cap_records: int):
         nbytes = C.c_size_t()
         offs = (C.c_size_t * 4)()
-        _lib.check(self.lib.ppn_packed_bytes(B, self.cfg.K, cap_records, C.byref(nbytes), offs), "ppn_packed_bytes")
-        return nbytes.value, tuple(int(o) for o in offs)
+        _lib.check(self.lib.ppn_packed_bytes(B, cap_entries, C.byref(nbytes), offs), "ppn_packed_bytes")
+        self._layouts[key] = (nbytes.value, tuple(int(o) for o in offs))
+        return self._layouts[key]
 
-    def pack(self, humans: PackedHumans, cap_records: int, buf: Optional[torch.Tensor] = None,
+    def pack(self, humans: PackedHumans, cap_entries: int, buf: Optional[torch.Tensor] = None,
              stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """Compact the fixed-stride result into one contiguous uint8 buffer (asynchronous): counts
-        plus dense (cell, score, box) records, `cap_records` records at most (ppn_pack_humans).
-        Runs on `stream` (default: torch's current stream)."""
+        plus one dense (part, cell, score, box) entry per PRESENT part, `cap_entries` at most
+        (ppn_pack_humans).  Runs on `stream` (default: torch's current stream)."""
         B = humans.count.shape[0]
-        nbytes, _ = self.packed_layout(B, cap_records)
+        nbytes, _ = self.packed_layout(B, cap_entries)
         if buf is None:
             buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         hs = self._humans_struct(humans)
         with self._guard():
             st = (stream if stream is not None else torch.cuda.current_stream(self.device)).cuda_stream
-            _lib.check(self.lib.ppn_pack_humans(C.byref(hs), B, self.cfg.K, cap_records, buf.data_ptr(), buf.numel(), st),
+            _lib.check(self.lib.ppn_pack_humans(C.byref(hs), B, self.cfg.K, cap_entries, buf.data_ptr(), buf.numel(), st),
                        "ppn_pack_humans")
         return buf
 

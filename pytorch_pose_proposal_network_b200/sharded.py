@@ -99,8 +99,8 @@ class PoseGatherer:
     """Gather of every rank's poses as ONE small asynchronous collective per group of steps.
 
     Each step the local result is compacted on the device into a dense record buffer
-    (``PoseParser.pack`` -> ``ppn_pack_humans``: counts + up to ``cap_records`` (cell, score, box)
-    records).  Every ``group_steps`` steps the group's buffers are all-gathered with a single
+    (``PoseParser.pack`` -> ``ppn_pack_humans``: counts + one (part, cell, score, box) entry per
+    present part, up to ``cap_entries``).  Every ``group_steps`` steps the group's buffers are all-gathered with a single
     ``all_gather_into_tensor`` issued with ``async_op``: the collective runs on NCCL's own stream
     while the next steps' kernels run on the compute stream (one NCCL call costs tens of µs of host
     time, comparable to a whole step, hence the grouping).  Two buffer sets alternate; before a set is
@@ -108,12 +108,12 @@ class PoseGatherer:
     every rank's records of every step.
     """
 
-    def __init__(self, parser, images_per_rank: int, cap_records: int, group=None, group_steps: int = 1):
+    def __init__(self, parser, images_per_rank: int, cap_entries: int, group=None, group_steps: int = 1):
         self.parser = parser
         self.group = group
         self.world = dist.get_world_size(group)
         self.B = int(images_per_rank)
-        self.cap = int(cap_records)
+        self.cap = int(cap_entries)
         self.gs = max(1, int(group_steps))
         self.nbytes, self.offsets = parser.packed_layout(self.B, self.cap)
         dev = parser.device
@@ -172,9 +172,9 @@ class PoseGatherer:
     def records_of(self, rank: int, step_back: int = 0):
         """Host view of `rank`'s records for the last submitted step minus `step_back`
         (within the two most recent groups; call after finish(); synchronises)."""
-        from .parser import unpack_records
+        from .parser import unpack_entries
         grp, k = divmod(self.step - 1 - step_back, self.gs)
         buf = self.full[grp & 1]
         lo = (rank * self.gs + k) * self.nbytes
         part = buf[lo:lo + self.nbytes].cpu()
-        return unpack_records(part, self.B, self.parser.cfg.K, self.cap, self.offsets)
+        return unpack_entries(part, self.B, self.cap, self.offsets)

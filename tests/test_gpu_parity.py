@@ -419,30 +419,34 @@ def test_capacity_limit_keeps_top_scores():
         packed.to_lists()
 
 
-def test_pack_dense_records_roundtrip():
-    """ppn_pack_humans: fixed-stride result -> dense records (what the multi-GPU gather ships)."""
+def test_pack_dense_entries_roundtrip():
+    """ppn_pack_humans: fixed-stride result -> dense (human, part) entries (what the multi-GPU gather ships)."""
     from pytorch_pose_proposal_network_b200.config import PPNConfig
-    from pytorch_pose_proposal_network_b200.parser import PoseParser, unpack_records
-    cfg = PPNConfig.mpii16()
-    g = O.Geometry.of(cfg)
-    B = 37
-    head = synth.make_head(g, "U", seed=5, B=B)
-    ref = c_oracle.parse_batch(head, g, n_threads=8)
-    parser = PoseParser(cfg)
-    out = parser.parse(torch.from_numpy(head).cuda())
-    total = int(ref["counts"][:, 2].sum())
-    for cap in (total + 10, total, total // 2):
-        buf = parser.pack(out, cap)
-        _, offs = parser.packed_layout(B, cap)
-        rec = unpack_records(buf.cpu(), B, cfg.K, cap, offs)
-        assert rec["total"] == total and rec["overflow"] == (total > cap)
-        assert np.array_equal(rec["count"], ref["counts"][:, 2])
-        for b in range(B):
-            n, s0 = int(rec["count"][b]), int(rec["start"][b])
-            n = max(0, min(n, cap - s0))                       # records that fit
-            assert np.array_equal(rec["cell"][s0:s0 + n], ref["part_cell"][b, :n])
-            assert np.array_equal(bits(rec["score"][s0:s0 + n]), bits(ref["part_score"][b, :n]))
-            assert np.array_equal(bits(rec["box"][s0:s0 + n]), bits(ref["part_box"][b, :n]))
+    from pytorch_pose_proposal_network_b200.parser import PoseParser, entries_to_packed, unpack_entries
+    for cfg, dist in ((PPNConfig.mpii16(), "U"), (PPNConfig.coco18(), "D")):
+        g = O.Geometry.of(cfg)
+        B = 21
+        head = synth.make_head(g, dist, seed=5, B=B)
+        ref = c_oracle.parse_batch(head, g, n_threads=8)
+        parser = PoseParser(cfg)
+        out = parser.parse(torch.from_numpy(head).cuda())
+        want_entries = np.array([(ref["part_cell"][b, :ref["counts"][b, 2]] >= 0).sum() for b in range(B)])
+        total = int(want_entries.sum())
+        for cap in (total + 10, total, total // 2):
+            buf = parser.pack(out, cap)
+            _, offs = parser.packed_layout(B, cap)
+            rec = unpack_entries(buf.cpu(), B, cap, offs)
+            assert rec["total"] == total and rec["overflow"] == (total > cap)
+            assert np.array_equal(rec["count"], ref["counts"][:, 2])
+            assert np.array_equal(rec["entries"], want_entries)
+            for b in range(B):
+                if rec["start"][b] + rec["entries"][b] > cap:
+                    continue                                       # (partly) dropped: overflow was flagged
+                n = int(ref["counts"][b, 2])
+                pc, ps, pb = entries_to_packed(rec, b, cfg.K)
+                assert np.array_equal(pc, ref["part_cell"][b, :n])
+                assert np.array_equal(bits(ps), bits(ref["part_score"][b, :n]))
+                assert np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
 
 
 def test_bad_arguments_raise():

@@ -126,26 +126,31 @@ def test_shard_ranges_cover_job():
             assert max(shard_sizes(n, world)) == -(-n // world)
 
 
-def test_dense_record_layout_host_side():
-    """unpack_records against a buffer laid out by hand from ppn_packed_bytes' offsets (no GPU)."""
+def test_dense_entry_layout_host_side():
+    """unpack_entries / entries_to_packed against a buffer laid out by hand from ppn_packed_bytes' offsets (no GPU)."""
     from pytorch_pose_proposal_network_b200 import _lib
-    from pytorch_pose_proposal_network_b200.parser import unpack_records
-    B, K, cap = 5, 16, 11
+    from pytorch_pose_proposal_network_b200.parser import entries_to_packed, unpack_entries
+    B, K, cap = 3, 4, 16
     nbytes, offs = C.c_size_t(), (C.c_size_t * 4)()
-    assert _lib.lib().ppn_packed_bytes(B, K, cap, C.byref(nbytes), offs) == 0
+    assert _lib.lib().ppn_packed_bytes(B, cap, C.byref(nbytes), offs) == 0
     offs = tuple(int(o) for o in offs)
-    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and offs[1] >= 4 * (2 + B)
-    assert nbytes.value >= offs[3] + cap * K * 16
+    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and offs[1] >= 4 * (2 + 2 * B)
+    assert nbytes.value >= offs[3] + cap * 16
     buf = np.zeros(nbytes.value, np.uint8)
-    count = np.array([2, 0, 3, 1, 4], np.int32)
-    buf[0:4 * (2 + B)].view(np.int32)[:] = np.concatenate([[count.sum(), 0], count])
-    cell = np.arange(cap * K, dtype=np.int32).reshape(cap, K)
-    buf[offs[1]:offs[1] + cell.nbytes].view(np.int32)[:] = cell.reshape(-1)
-    rec = unpack_records(buf, B, K, cap, offs)
-    assert rec["total"] == 10 and not rec["overflow"]
-    assert list(rec["start"]) == [0, 2, 2, 5, 6]
-    assert np.array_equal(rec["cell"], cell)
-    assert _lib.lib().ppn_packed_bytes(-1, K, cap, C.byref(nbytes), None) == -1
+    # image 0: humans {0,2} and {0}; image 1: none; image 2: human {0,1,3}
+    parts = [0, 2, 0, 0, 1, 3]
+    cells = [5, 6, 9, 1, 2, 3]
+    count, entries = np.array([2, 0, 1], np.int32), np.array([3, 0, 3], np.int32)
+    buf[0:4 * (2 + 2 * B)].view(np.int32)[:] = np.concatenate([[6, 0], count, entries])
+    buf[offs[1]:offs[1] + 4 * 6].view(np.uint32)[:] = [(p << 16) | c for p, c in zip(parts, cells)]
+    buf[offs[2]:offs[2] + 4 * 6].view(np.float32)[:] = np.arange(6, dtype=np.float32) / 8
+    rec = unpack_entries(buf, B, cap, offs)
+    assert rec["total"] == 6 and not rec["overflow"] and list(rec["start"]) == [0, 3, 3]
+    pc, ps, pb = entries_to_packed(rec, 0, K)
+    assert pc.tolist() == [[5, -1, 6, -1], [9, -1, -1, -1]] and ps[0, 2] == np.float32(1 / 8)
+    assert entries_to_packed(rec, 1, K)[0].shape == (0, K)
+    assert entries_to_packed(rec, 2, K)[0].tolist() == [[1, 2, -1, 3]]
+    assert _lib.lib().ppn_packed_bytes(-1, cap, C.byref(nbytes), None) == -1
 
 
 def _gloo_worker(rank, world, port, n_images, tmp):
