@@ -518,3 +518,57 @@ def test_full_size_properties(preset, B, dist):
         ref = c_oracle.parse_batch(sub, g, n_threads=8)
         sample = {k: v[pick] for k, v in first.items()}
         assert_packed_equals_oracle(sample, ref, len(pick))
+
+
+# ------------------------------------------------------------------------------------------
+# fuzz: random geometries, skeletons and thresholds against the C restatement
+# ------------------------------------------------------------------------------------------
+def _random_tree(rng, K):
+    """Random rooted tree over parts 0..K-1 as track orders (root-to-leaf chains) + limb list."""
+    parent = [-1] + [int(rng.integers(0, k)) for k in range(1, K)]
+    limb_of = {k: k - 1 for k in range(1, K)}                 # limb k-1 joins parent[k] -> k
+    children = {k: [] for k in range(K)}
+    for k in range(1, K):
+        children[parent[k]].append(k)
+    leaves = [k for k in range(K) if not children[k]]
+    graphs = []
+    for leaf in leaves:
+        path = []
+        k = leaf
+        while k != 0:
+            path.append(k)
+            k = parent[k]
+        path.reverse()
+        if path:
+            graphs.append((tuple(limb_of[t] for t in path), tuple(path)))
+    return tuple(graphs), K - 1
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_geometry(seed):
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    rng = np.random.default_rng(1000 + seed)
+    K = int(rng.integers(2, 20))
+    graphs, E = _random_tree(rng, K)
+    W, H = int(rng.integers(2, 27)), int(rng.integers(2, 27))
+    while W * H > 1024:
+        W, H = int(rng.integers(2, 27)), int(rng.integers(2, 27))
+    s = int(rng.choice([1, 3, 5, 7, 9, 13]))
+    cell = int(rng.choice([8, 16, 32]))
+    cfg = PPNConfig(K=K, E=E, insize=(W * cell, H * cell), outsize=(W, H), local_grid_size=(s, s),
+                    directed_graphs=graphs, detection_thresh=float(rng.choice([0.05, 0.15, 0.3, 0.6])),
+                    nms_thresh=float(rng.choice([0.1, 0.3, 0.5, 0.9])), min_num_keypoints=int(rng.choice([-1, 1, 2])))
+    g = O.Geometry.of(cfg)
+    B = int(rng.integers(1, 9))
+    head = synth.make_head(g, str(rng.choice(["U", "R", "D", "S"])), seed=seed, B=B)
+    if not synth.root_scores_distinct(head, g, cfg.detection_thresh):
+        pytest.skip("duplicate root scores in this draw")
+    ref = c_oracle.parse_batch(head, g, n_threads=4)
+    parser = PoseParser(cfg)
+    dev = torch.from_numpy(head).cuda()
+    assert_packed_equals_oracle(parser.parse(dev).numpy(), ref, B)
+    assert_packed_equals_oracle(parser.parse(dev, input_complete=True).numpy(), ref, B)
+    want = np.stack([c_oracle.limb_argmax(img, g) for img in head]).astype(np.uint16) if E else None
+    if E:
+        assert np.array_equal(parser.limb_argmax(dev).cpu().numpy(), want)

@@ -1,0 +1,61 @@
+"""Property tests (hypothesis) of the two CPU restatements against each other and against
+simple invariants — no GPU, no reference needed."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import c_oracle, ppn_oracle as O
+
+boxes = st.lists(st.tuples(st.floats(0, 300, width=32), st.floats(0, 300, width=32),
+                           st.floats(0, 120, width=32), st.floats(0, 120, width=32)), min_size=0, max_size=60)
+
+
+@settings(max_examples=150, deadline=None)
+@given(boxes, st.sampled_from([0.1, 0.3, 0.5, 0.75]), st.integers(0, 2 ** 31 - 1), st.sampled_from([None, 1, 3, 10]))
+def test_nms_numpy_equals_c_and_is_a_valid_greedy_selection(bx, thr, seed, limit):
+    b = np.array([[y, x, y + h, x + w] for y, x, h, w in bx], np.float32).reshape(-1, 4)
+    n = len(b)
+    rng = np.random.default_rng(seed)
+    score = rng.permutation(n).astype(np.float32)                       # distinct
+    with np.errstate(all="ignore"):
+        keep = O.nms(b, thr, score=score, limit=limit)
+        assert np.array_equal(keep, c_oracle.nms(b, thr, score=score, limit=limit))
+        assert len(set(keep.tolist())) == len(keep)
+        assert (np.diff(score[keep]) < 0).all()                          # visiting order = descending score
+        if limit is not None:
+            assert len(keep) <= limit
+        # no kept box suppresses a later kept box; every dropped box (before the limit hit) is suppressed by a kept one
+        area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+        for pos, i in enumerate(keep):
+            if pos:
+                iou = O.iou_one_to_many(b[i], area[i], b[keep[:pos]], area[keep[:pos]])
+                assert not (iou >= np.float32(thr)).any()
+        if limit is None:
+            kept = set(keep.tolist())
+            for i in range(n):
+                if i not in kept:
+                    better = [j for j in keep if score[j] > score[i]]
+                    iou = O.iou_one_to_many(b[i], area[i], b[better], area[better])
+                    assert (iou >= np.float32(thr)).any()
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 10 ** 6), st.sampled_from(["U", "R", "D", "S"]), st.integers(2, 7), st.integers(2, 7),
+       st.sampled_from([1, 3, 5]))
+def test_parse_numpy_equals_c(seed, dist, W, H, s):
+    from oracle import synth
+    graphs = (((0, 1), (1, 2)), ((0, 2), (1, 3)), ((3,), (4,)))
+    g = O.Geometry(K=5, E=4, inW=16 * W, inH=16 * H, W=W, H=H, sW=s, sH=s, graphs=graphs)
+    head = synth.make_head(g, dist, seed, B=2)
+    if not synth.root_scores_distinct(head, g):
+        return
+    c = c_oracle.parse_batch(head, g)
+    for b in range(2):
+        p = O.parse_image(head[b], g)
+        n = len(p.root_cell)
+        assert int(c["counts"][b, 2]) == n
+        assert np.array_equal(c["part_cell"][b, :n], p.part_cell)
+        assert np.array_equal(c["part_box"][b, :n].view(np.uint32), p.part_box.view(np.uint32))
+        # invariants: root is part 0; every present part is above the threshold; root scores descend
+        assert (p.part_cell[:, 0] == p.root_cell).all()
+        assert (p.part_score[p.part_cell >= 0] >= np.float32(g.det_thresh)).all()
+        assert (np.diff(p.part_score[:, 0]) <= 0).all()
