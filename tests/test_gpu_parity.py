@@ -100,6 +100,51 @@ def test_golden_dropin_signature_native():
             assert bits(sc[t]) == bits(fx["ref_score"][i, t])
 
 
+def test_dropin_test_py_variant():
+    """test.py's stale copy: thresholds 0.09 / NMS 0.5 / min_num_keypoints=-1, resp*conf inside,
+    geometry from `model`, humans only (test.py:159-221) — same kernels, other parameters."""
+    from types import SimpleNamespace
+    from pytorch_pose_proposal_network_b200 import variant_test_py as tv
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    cfg = PPNConfig.reference_native(detection_thresh=0.09, nms_thresh=0.5, min_num_keypoints=-1, swap_window_offsets=True)
+    g = O.Geometry.of(cfg)
+    out = synth.make_head(g, "U", seed=8, B=1)[0]
+    want_h, want_s = O.humans_as_dicts(O.parse_image(out, g))
+    resp, conf, x, y, w, h, e = O.split_head(out, g)
+    model = SimpleNamespace(insize=(384, 384), outsize=(24, 24), local_grid_size=(21, 21))
+    humans = tv.get_humans_by_feature(model, resp, conf, x, y, w, h, e)
+    assert len(humans) == len(want_h) and any(len(hm) == 1 for hm in humans)      # root-only humans are kept
+    for hm, wh in zip(humans, want_h):
+        assert list(hm.keys()) == list(wh.keys())
+        for t in hm:
+            assert np.array_equal(bits(hm[t]), bits(wh[t]))
+
+
+def test_dropin_rt_test_inference():
+    """rt_test.inference with a stand-in model: same preprocessing, GPU parse instead of 7 copies + numpy."""
+    from pytorch_pose_proposal_network_b200 import rt_test
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    cfg = PPNConfig.reference_native()
+    g = O.Geometry.of(cfg)
+    fixed = torch.from_numpy(synth.make_head(g, "U", seed=9, B=1)).cuda()
+
+    class Head(torch.nn.Module):
+        insize, outsize, local_grid_size = (384, 384), (24, 24), (21, 21)
+        def forward(self, x):
+            assert x.shape == (1, 3, 384, 384) and x.dtype == torch.float32
+            return fixed
+    image = (np.random.default_rng(0).random((384, 384, 3)) * 255).astype(np.uint8)
+    humans, scores = rt_test.inference(image, Head(), (24, 24), (21, 21))
+    want_h, want_s = O.humans_as_dicts(O.parse_image(fixed[0].cpu().numpy(), g))
+    assert len(humans) == len(want_h) > 0
+    for hm, wh, sc, ws in zip(humans, want_h, scores, want_s):
+        assert list(hm.keys()) == list(wh.keys())
+        for t in hm:
+            assert np.array_equal(bits(hm[t]), bits(wh[t])) and bits(sc[t]) == bits(ws[t])
+    drawn = rt_test.inference(image, Head(), (24, 24), (21, 21), draw=lambda **kw: (kw["pil_image"].size, len(kw["humans"])))
+    assert drawn == ((384, 384), len(want_h))
+
+
 def test_dropin_restore_functions():
     from pytorch_pose_proposal_network_b200 import datatest as dt
     g, out, _ = load_case("native_U_s0")
