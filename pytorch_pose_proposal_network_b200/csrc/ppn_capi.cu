@@ -1,5 +1,6 @@
 // C ABI of libppn_decode (declared in include/ppn_decode.h): argument checking, workspace
-// carving, the 4-kernel pipeline, and the host-memory entry with overlapped copies.
+// carving, the launch chain of ppn_parse (decode+NMS | limb arg-max -> tree parse), the dense
+// entry packing, and the host-memory entry with overlapped copies.
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -13,9 +14,9 @@ namespace {
 ppn::Tuning g_tuning;
 
 // ---- optional per-stage timing of ppn_parse (ppn_profile_*) --------------------------------
-// When enabled, ppn_parse records CUDA events at its five stage boundaries on the caller's
-// stream; ppn_profile_read() sums the elapsed times.  Used by bench.py to time the dominant
-// kernel inside the timed region.  Not thread-safe: enable it from one thread.
+// When enabled, ppn_parse runs its kernels back to back and brackets each with a (start, stop)
+// pair of CUDA events on the caller's stream; ppn_profile_read() sums the elapsed times.  Used by
+// bench.py for the per-kernel durations behind `roofline`.  Not thread-safe: one thread only.
 constexpr int kStages = 4;
 constexpr int kMaxProfiled = 4096;
 struct Profile {
@@ -30,10 +31,9 @@ inline cudaEvent_t* profile_slot() {
 }
 
 // ---- side lane: decode + NMS run beside the limb arg-max ---------------------------------
-// The arg-max stream (K3) and decode+NMS (K1, K2) are independent; only the tree parse (K4)
-// needs both.  ppn_parse forks K1/K2 onto a private non-blocking stream and joins before K4,
-// so the latency-bound small kernels hide behind the HBM-bound one.  One lane per host thread
-// and device; event record/wait pairs are also legal under stream capture (CUDA graphs).
+// parse.overlap = 1 (the alternative to the default PDL chain): decode+NMS is forked onto a private
+// non-blocking stream and joined before the tree parse.  One lane per host thread and device;
+// event record/wait pairs are also legal under stream capture (CUDA graphs).
 struct SideLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -139,6 +139,7 @@ Workspace carve(const PPNShape* s, int n_parts) {
 
 // ppn_parse alternates between the two halves of the caller's workspace from call to call, so that
 // a call may overlap the previous one (PPN_FLAG_INPUT_COMPLETE) without sharing scratch with it.
+// Host state: one counter per distinct workspace address ever passed (never erased: a few bytes).
 std::mutex g_parity_mu;
 std::unordered_map<void*, unsigned> g_parity;
 
@@ -529,6 +530,8 @@ int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParam
     float* d_score = reinterpret_cast<float*>(d + h.off_score);
     float* d_box = reinterpret_cast<float*>(d + h.off_box);
 
+    PPNParams chunk_params = *params;
+    chunk_params.flags &= ~PPN_FLAG_INPUT_COMPLETE;      // the chunk's head arrives by the copy just ahead of it
     int slot = 0;
     for (int b0 = 0; b0 < shape->B; b0 += h.chunk, slot ^= 1) {
         const int nb = (shape->B - b0 < h.chunk) ? shape->B - b0 : h.chunk;
@@ -545,7 +548,7 @@ int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParam
         dev_out.part_score = d_score + (size_t)b0 * R * K;
         dev_out.part_box = d_box + (size_t)b0 * R * K * 4;
         dev_out.R = R;
-        if ((rc = ppn_parse(d_head, &cs, params, &dev_out, d + h.off_ws[slot], h.ws_bytes, st))) return rc;
+        if ((rc = ppn_parse(d_head, &cs, &chunk_params, &dev_out, d + h.off_ws[slot], h.ws_bytes, st))) return rc;
         // results of this chunk go home on the same stream, behind its kernels
         if ((e = cudaMemcpyAsync(out_host->count + b0, dev_out.count, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
         if ((e = cudaMemcpyAsync(out_host->root_cell + (size_t)b0 * R, dev_out.root_cell, (size_t)nb * R * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;

@@ -736,6 +736,15 @@ __device__ __forceinline__ int fast_div(int x, uint32_t magic) {      // exact f
     return magic ? (int)__umulhi((unsigned)x, magic) : x;
 }
 
+// kStaged: resp/conf live in shared memory (plain LDS) — otherwise they are read from the head tensor
+// through the read-only path.  A compile-time switch, so neither case pays for generic addressing.
+template <bool kStaged>
+__device__ __forceinline__ float delta_lookup(const float* resp, const float* conf, int at) {
+    if (kStaged) return __fmul_rn(resp[at], conf[at]);
+    return __fmul_rn(__ldg(resp + at), __ldg(conf + at));
+}
+
+template <bool kStaged>
 __device__ __forceinline__ void walk_chain(const ChainTable& ch, int cidx, int root, const Geom& g, float thr,
                                            const float* s_resp, const float* s_conf, const uint16_t* s_amax,
                                            const int32_t* s_dyx, bool use_tab, int16_t* my_pos) {
@@ -755,13 +764,14 @@ __device__ __forceinline__ void walk_chain(const ChainTable& ch, int cidx, int r
         }
         if (jh < 0 || jw < 0 || jh >= g.H || jw >= g.W) break;                         // datatest.py:118
         const int j = jh * g.W + jw;
-        if (__fmul_rn(s_resp[t * g.HW + j], s_conf[t * g.HW + j]) < thr) break;        // datatest.py:121
+        if (delta_lookup<kStaged>(s_resp, s_conf, t * g.HW + j) < thr) break;          // datatest.py:121
         my_pos[t] = (int16_t)j;
         ih = jh;
         iw = jw;
     }
 }
 
+template <bool kStaged>
 __global__ void __launch_bounds__(1024)
 tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
                   const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
@@ -786,7 +796,7 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
     const int b = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const float* img = head + (size_t)b * g.img_stride;
-    const float* s_resp = n_groups ? s_planes : img;              // generic pointers: shared or global
+    const float* s_resp = kStaged ? s_planes : img;               // shared when kStaged, else the head tensor
     const float* s_conf = s_resp + KHW;
     const uint16_t* am = amax + (size_t)b * g.E * g.HW;
     const bool use_tab = g.S <= kMaxDyxTable;
@@ -838,10 +848,10 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
         if (r < n_keep) {
             int16_t* my_pos = s_pos + r * g.K;
             if (ch.parallel_ok) {
-                walk_chain(ch, cidx, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+                walk_chain<kStaged>(ch, cidx, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
             } else {
                 for (int c = 0; c < ch.n_chains; ++c)
-                    walk_chain(ch, c, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+                    walk_chain<kStaged>(ch, c, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
             }
         }
     }
@@ -910,7 +920,7 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             if (c >= 0) {
                 const int at = tt[u] * g.HW + c;
                 const int h = fast_div(c, g.magic_W), w = c - h * g.W;
-                score = __fmul_rn(s_resp[at], s_conf[at]);
+                score = delta_lookup<kStaged>(s_resp, s_conf, at);
                 box = box_from(xs[u], ys[u], ws[u], hs[u], h, w, g);
             }
             const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
@@ -1031,7 +1041,7 @@ pack_entries_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
 // per device, on the first launch (so make the first call outside stream capture).
 constexpr int kTicketSlots = 64;
 struct DeviceInfo { int* tickets = nullptr; cudaStream_t slot_stream[kTicketSlots] = {}; int slots_used = 0;
-                    int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 0, ldg = 0, nms = 0, tree = 0; };
+                    int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 0, ldg = 0, nms = 0, tree = 0, tree_light = 0; };
 static DeviceInfo g_dev[64];
 
 // Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
@@ -1316,15 +1326,16 @@ cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable
     int threads = threads_pref > 0 ? threads_pref : ((g.HW <= 144 || n_groups == 0) ? 256 : 512);
     threads = ((threads < 64 ? 64 : (threads > 1024 ? 1024 : threads)) + 31) & ~31;
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
-    if ((e = ensure_smem(tree_parse_kernel, smem, &d->tree)) != cudaSuccess) return e;
+    if ((e = n_groups ? ensure_smem(tree_parse_kernel<true>, smem, &d->tree)
+                      : ensure_smem(tree_parse_kernel<false>, smem, &d->tree_light)) != cudaSuccess) return e;
     // bulk copies need 16-byte sizes and sources: the staged planes are 4*n*K*HW bytes at image
     // offset 4*C*HW*b, the arg-max map 2*E*HW bytes at offset 2*E*HW*b
     const bool tma_ok = ((size_t)g.K * g.HW * 8) % 16 == 0 && (g.img_stride * 4) % 16 == 0 &&
                         ((size_t)g.E * g.HW * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(head) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(amax) & 15) == 0;
-    return launch_kernel(tree_parse_kernel, dim3(g.B), dim3(threads), smem, st, pdl_attr, head, g, ch, thr, min_kp, n_parts, amax,
-                         cand_cell, keep_idx, keep_count, h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box),
-                         R, tma_ok ? 1 : 0, n_groups, pdl_bits);
+    return launch_kernel(n_groups ? tree_parse_kernel<true> : tree_parse_kernel<false>, dim3(g.B), dim3(threads), smem, st,
+                         pdl_attr, head, g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root,
+                         h_cell, h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, pdl_bits);
 }
 
 }  // namespace ppn
