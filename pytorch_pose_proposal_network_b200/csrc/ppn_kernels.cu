@@ -1122,9 +1122,10 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     int G = t.argmax_threads / p->CV;
     if (G < 1) G = 1;
     while (G > 1 && p->CV * G > 992) --G;
-    // thread groups split the rows of one matrix (mode 0) or take one small matrix each (mode 1)
-    const bool small = (size_t)g.S * row_bytes <= 64 * 1024;
-    p->split_mats = (t.argmax_split < 0 ? (small && G > 1) : (t.argmax_split != 0)) ? 1 : 0;
+    // thread groups take one matrix each (mode 1: no merge, no barrier) whenever there are several
+    // groups; splitting the rows of one matrix over the groups (mode 0) is kept as the alternative —
+    // measured equal or slower at every BASELINE shape (profiles/sweep_argmax_*_r1.txt)
+    p->split_mats = (t.argmax_split < 0 ? (G > 1) : (t.argmax_split != 0)) ? 1 : 0;
     if (p->split_mats) {
         if (G > 32) G = 32;                               // one producer lane per matrix
         if (G > g.B * g.E) G = g.B * g.E;

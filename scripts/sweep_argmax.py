@@ -49,7 +49,7 @@ def main():
         parser = PoseParser(cfg)
         limb_bytes = B * cfg.E * cfg.S * cfg.HW * 4
         rows = []
-        grid = list(itertools.product([0], [16384, 32768, 49152, 65536], [3, 4, 5, 6], [144, 192, 256, 320, 512], [1, 2], [-1]))
+        grid = list(itertools.product([0], [16384, 32768, 49152, 65536], [3, 4, 5, 6], [192, 320, 512], [1, 2], [0, 1]))
         grid += list(itertools.product([1], [32768], [5], [128, 192], [1], [0]))
         if args.quick:
             grid = grid[::7]
