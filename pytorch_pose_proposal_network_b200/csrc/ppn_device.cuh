@@ -138,6 +138,11 @@ enum : int {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Ask the L2 to fetch a contiguous range (bytes % 16 == 0, 16 B aligned): later scattered reads of
+// it then cost an L2 hit instead of a DRAM sector each.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
