@@ -12,6 +12,7 @@
  *   ppn_restore_xy/_size ... restore_xy(x, y) / restore_size(w, h), datatest.py:63-71
  *   ppn_nms ................ non_maximum_suppression(bbox, thresh, score, limit), datatest.py:134-160
  *   ppn_tree_parse ......... the per-root walk of get_humans_by_feature, datatest.py:103-131
+ *   ppn_part_centres ....... box -> keypoint of draw_humans / evaluation, datatest.py:200-211, 314-317
  *   ppn_parse .............. get_humans_by_feature end to end on a device batch: what
  *                            rt_test.py:109-133 / main.py:946-972 do per image after model(image)
  *   ppn_parse_host ......... the same from host memory (the reference's numpy arrays), with the
@@ -161,6 +162,12 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
 int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params, int32_t R, size_t* bytes);
 int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParams* params,
                    const PPNHumans* out_host, void* dev_scratch, size_t dev_scratch_bytes);
+
+/* Centre of every part's box, centre_yx[B, R, K, 2] = ((ymin + ymax) / 2, (xmin + xmax) / 2), (0, 0)
+ * for absent parts and unused slots: what the code right after the path reads off the boxes — the
+ * keypoints drawn by draw_humans (datatest.py:200-211) and the x / y of the AP-evaluation records
+ * (datatest.py:314-317).  Same fp32 arithmetic as numpy's. */
+int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centre_yx, void* stream);
 
 /* Dense pose ENTRIES for shipping results (the multi-GPU gather): one contiguous device buffer
  *   int32  header[2 + 2B] = {total entries, overflow flag, count[B] humans, entries[B] per image}

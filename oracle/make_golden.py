@@ -197,6 +197,35 @@ def roundtrip_case(name, cfg, seed, n_people):
     return out
 
 
+def pred_frame_cases(presets):
+    """datatest.evaluation's prediction records (datatest.py:298-328) for two of the cases above."""
+    cases = {}
+    for name, g, dist, seed in (("tiny_U_s11", tiny_geometry(), "U", 11),
+                                ("cfg2_U_s1", O.Geometry.of(presets["cfg2"]), "U", 1)):
+        out = synth.make_head(g, dist, seed)[0]
+        ref_live.configure(g)
+        humans, scores = ref_live.reference_parse(out, g)
+        if g.K != 18:
+            # evaluation() loops over len(KEYPOINT_NAMES) of the reference's config (18): give it K names
+            dt = ref_live.load()
+            saved = dt.KEYPOINT_NAMES
+            dt.KEYPOINT_NAMES = list(range(g.K))
+        try:
+            frames = ref_live.reference_pred_frames([name + ".jpg"], [humans], [scores])
+        finally:
+            if g.K != 18:
+                dt.KEYPOINT_NAMES = saved
+        want = O.canonical(frames[0])
+        assert O.canonical(O.pred_frame(name + ".jpg", humans, scores, g.K)) == want, name
+        p = O.parse_image(out, g)
+        ho, so = O.humans_as_dicts(p)
+        assert O.canonical(O.pred_frame(name + ".jpg", ho, so, g.K)) == want, name
+        cases[name] = want
+        print(f"pred_frame {name}: {len(frames[0]['annorect'])} persons")
+    with open(os.path.join(GOLDEN, "pred_frames.json"), "w") as f:
+        json.dump(cases, f)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     assert ref_live.available(), "run this where /root/reference exists"
@@ -225,6 +254,7 @@ def main():
     one_case("cfg2_U_s5_minkp-1_thr0.09", g, synth.make_head(g, "U", 5)[0],
              dict(preset="cfg2", dist="U", seed=5, min_num_keypoints=-1, detection_thresh=0.09))
 
+    pred_frame_cases(presets)
     roundtrip_case("roundtrip_cfg2_s21", presets["cfg2"], 21, 3)
     roundtrip_case("roundtrip_native_s22", presets["native"], 22, 5)
     nms_cases(dt)

@@ -24,6 +24,7 @@ What is restated, with the reference lines each function follows:
 ``walk``                datatest.py:103-131
 ``parse_image``         rt_test.py:130-133 + datatest.py:74-132, packed output
 ``humans_as_dicts``     datatest.py:98-99,129-132 (return types, key order)
+``pred_frame``          datatest.py:298-328 (prediction record for the AP evaluation)
 =====================  =====================================================
 
 All arithmetic is IEEE fp32 with one rounding per written operation (numpy never fuses),
@@ -289,3 +290,42 @@ def parse_head_like_reference(out: np.ndarray, g: Geometry):
     """rt_test.py:109-133 on one host image: slice, multiply, parse."""
     resp, conf, x, y, w, h, e = split_head(out, g)
     return get_humans_by_feature(resp * conf, x, y, w, h, e, g, g.det_thresh, g.min_kp)
+
+
+# --------------------------------------------------------------------------- #
+# the consumer right after the path: AP-evaluation prediction records
+# --------------------------------------------------------------------------- #
+def pred_frame(fname, humans, scores, K: int):
+    """One image's prediction frame exactly as datatest.evaluation builds it (datatest.py:298-328):
+    per person the root box and score, then for joints 1..K-1 the box centre ((a + b) / 2 in fp32)
+    and score, or integer zeros when the part is absent."""
+    rects = []
+    for person, score in zip(humans, scores):
+        y1, x1, y2, x2 = person[0]
+        pp = {"x1": [x1], "y1": [y1], "x2": [x2], "y2": [y2], "score": [score[0]], "annopoints": [{"point": []}]}
+        for num in range(1, K):
+            if num in person:
+                y = (person[num][0] + person[num][2]) / 2
+                x = (person[num][1] + person[num][3]) / 2
+                s = score[num]
+            else:
+                y, x, s = 0, 0, 0
+            pp["annopoints"][0]["point"].append({"id": [num - 1], "x": [x], "y": [y], "score": [s]})
+        rects.append(pp)
+    return {"image": [fname], "annorect": rects}
+
+
+def canonical(obj):
+    """JSON-able form that keeps the value TYPES (numpy fp32 vs Python int), for comparing frames."""
+    if isinstance(obj, dict):
+        return {k: canonical(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [canonical(v) for v in obj]
+    if isinstance(obj, np.floating):
+        assert obj.dtype == np.float32, obj.dtype
+        return ["f32", int(np.float32(obj).view(np.uint32))]
+    if isinstance(obj, (int, np.integer)):
+        return ["int", int(obj)]
+    if isinstance(obj, str):
+        return ["str", obj]
+    raise TypeError(type(obj))

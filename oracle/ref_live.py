@@ -95,3 +95,29 @@ def reference_parse(out, g):
     e = out[6 * K:].reshape(g.E, g.sH, g.sW, g.H, g.W)
     return dt.get_humans_by_feature(resp * conf, x, y, w, h, e,
                                     detection_thresh=g.det_thresh, min_num_keypoints=g.min_kp)
+
+
+class _Captured(Exception):
+    def __init__(self, gt, pr):
+        self.gt, self.pr = gt, pr
+
+
+def reference_pred_frames(fnames, humans_list, scores_list):
+    """The prediction frames the reference's own ``evaluation`` builds (datatest.py:298-348), captured
+    at the point where it hands them to the poseval code (``eval_helpers.load_data``, :350)."""
+    dt = load()
+
+    def grab(gt, pr):
+        raise _Captured(gt, pr)
+
+    saved = dt.eval_helpers.load_data
+    dt.eval_helpers.load_data = grab
+    try:
+        n = len(fnames)
+        dt.evaluation([list(fnames), [[] for _ in range(n)], list(humans_list), list(scores_list),
+                       [[] for _ in range(n)], [[] for _ in range(n)], [[] for _ in range(n)]])
+    except _Captured as c:
+        return c.pr
+    finally:
+        dt.eval_helpers.load_data = saved
+    raise RuntimeError("the reference did not reach eval_helpers.load_data")

@@ -58,6 +58,7 @@ EXPORTS = {
                                                C.POINTER(C.c_size_t)]),
     "ppn_parse_host": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.POINTER(PPNParams), C.POINTER(PPNHumans),
                                  C.c_void_p, C.c_size_t]),
+    "ppn_part_centres": (C.c_int, [C.POINTER(PPNHumans), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ppn_packed_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "ppn_pack_humans": (C.c_int, [C.POINTER(PPNHumans), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ppn_profile_enable": (C.c_int, [C.c_int32]),

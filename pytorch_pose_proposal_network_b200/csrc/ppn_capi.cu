@@ -390,6 +390,16 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     return PPN_OK;
 }
 
+int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centre_yx, void* stream) {
+    int rc = check_humans(humans);
+    if (rc) return rc;
+    if (B < 0 || K < 1) return PPN_E_BADARG;
+    if (B == 0) return PPN_OK;
+    if (!centre_yx || (reinterpret_cast<uintptr_t>(centre_yx) & 7) || (reinterpret_cast<uintptr_t>(humans->part_box) & 15)) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_part_centres(humans->count, humans->part_cell, humans->part_box, B, humans->R, K, centre_yx,
+                                            (cudaStream_t)stream));
+}
+
 // ---- dense pose entries ----------------------------------------------------------------------
 namespace {
 struct PackedLayout { size_t header, idcell, score, box, total; };

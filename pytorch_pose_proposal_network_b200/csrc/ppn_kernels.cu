@@ -940,6 +940,27 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
 }
 
 // =========================================================================================
+// part centres — what the consumers right after the path read off each box
+// =========================================================================================
+// datatest.py:200-211 (drawing) and :316-317 (AP-evaluation records) both reduce a part's box to
+// its centre, y = (ymin + ymax) / 2, x = (xmin + xmax) / 2 in fp32 (an add and an exact halving).
+// One thread per (image, slot, part); slots beyond count[b] and absent parts give (0, 0).
+__global__ void __launch_bounds__(256)
+part_centres_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ cell, const float4* __restrict__ box,
+                    size_t n, int R, int K, float2* __restrict__ centre) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t human = i / K;
+    const int b = (int)(human / R), slot = (int)(human - (size_t)b * R);
+    float2 c = make_float2(0.0f, 0.0f);
+    if (slot < count[b] && cell[i] >= 0) {
+        const float4 bx = box[i];
+        c = make_float2(__fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f), __fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f));
+    }
+    centre[i] = c;
+}
+
+// =========================================================================================
 // pack — dense pose entries for the multi-GPU gather
 // =========================================================================================
 // Fixed-stride PPNHumans -> one contiguous buffer of (human, part) ENTRIES, present parts only:
@@ -1267,6 +1288,15 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
     }
     nms_global_kernel<<<n_problems, 1024, 0, st>>>(reinterpret_cast<const float4*>(box), score, count, stride, thr,
                                                    limit, keep_idx, keep_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_part_centres(const int32_t* count, const int32_t* cell, const float* box, int B, int R, int K,
+                                float* centre, cudaStream_t st) {
+    const size_t n = (size_t)B * R * K;
+    if (n == 0) return cudaSuccess;
+    part_centres_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(count, cell, reinterpret_cast<const float4*>(box), n, R, K,
+                                                                     reinterpret_cast<float2*>(centre));
     return cudaGetLastError();
 }
 

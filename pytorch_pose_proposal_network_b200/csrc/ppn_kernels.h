@@ -58,6 +58,9 @@ cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* 
 cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float* rh, size_t n, float inW, float inH,
                                 cudaStream_t st);
 
+cudaError_t launch_part_centres(const int32_t* count, const int32_t* cell, const float* box, int B, int R, int K,
+                                float* centre, cudaStream_t st);
+
 cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const float* score, const float* box, int B, int R,
                                int K, int cap, int32_t* header, uint32_t* e_idcell, float* e_score, float* e_box,
                                cudaStream_t st);

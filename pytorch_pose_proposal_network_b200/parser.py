@@ -273,6 +273,18 @@ class PoseParser:
                                                _ptr(self._host_scratch), self._host_scratch.numel()), "ppn_parse_host")
         return out
 
+    # ---- keypoints (what drawing and AP evaluation read off the boxes) ------------------- #
+    def part_centres(self, humans: PackedHumans) -> torch.Tensor:
+        """fp32 [B, R, K, 2] = (y, x) centre of every part's box, (0, 0) where absent
+        (datatest.py:200-211, 314-317); asynchronous, on torch's current stream."""
+        B = humans.count.shape[0]
+        out = torch.empty(B, humans.R, self.cfg.K, 2, dtype=torch.float32, device=self.device)
+        hs = self._humans_struct(humans)
+        with self._guard():
+            _lib.check(self.lib.ppn_part_centres(C.byref(hs), B, self.cfg.K, out.data_ptr(),
+                                                 torch.cuda.current_stream(self.device).cuda_stream), "ppn_part_centres")
+        return out
+
     # ---- dense entries (what the multi-GPU gather ships) -------------------------------- #
     def packed_layout(self, B: int, cap_entries: int):
         """-> (bytes, (header, idcell, score, box) byte offsets) of the dense entry buffer."""

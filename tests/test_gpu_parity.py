@@ -145,6 +145,27 @@ def test_dropin_rt_test_inference():
     assert drawn == ((384, 384), len(want_h))
 
 
+def test_part_centres_and_evaluation_frames():
+    """ppn_part_centres + evaluation.pred_frame against the frames the reference's evaluation() builds."""
+    import json
+    import os
+    from tests.golden_util import GOLDEN
+    from pytorch_pose_proposal_network_b200 import evaluation
+    want = json.load(open(os.path.join(GOLDEN, "pred_frames.json")))
+    for name, frame in want.items():
+        g, out, _ = load_case(name)
+        parser = parser_for(g)
+        packed = parser.parse(torch.from_numpy(out[None]).cuda())
+        centres = parser.part_centres(packed)
+        got = evaluation.pred_frames([name + ".jpg"], packed, centres)[0]
+        assert O.canonical(got) == frame, name
+        # unused slots and absent parts are zero
+        c = centres.cpu().numpy()[0]
+        a = packed.numpy()
+        n = int(a["count"][0])
+        assert not c[n:].any() and not c[:n][a["part_cell"][0, :n] < 0].any()
+
+
 def test_dropin_restore_functions():
     from pytorch_pose_proposal_network_b200 import datatest as dt
     g, out, _ = load_case("native_U_s0")

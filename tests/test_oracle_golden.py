@@ -103,3 +103,15 @@ def test_argmax_nan_and_tie_semantics():
     assert list(want[0].reshape(-1)[:5]) == [1, 1, 0, 0, 1]
     assert np.array_equal(c_oracle.limb_argmax(out, g), want)
     assert np.array_equal(O.limb_argmax(out[6 * g.K:].reshape(g.E, g.sH, g.sW, g.H, g.W)), want)
+
+
+def test_pred_frames_match_reference():
+    """datatest.evaluation's prediction records (datatest.py:298-328), captured from the reference."""
+    import json
+    import os
+    from tests.golden_util import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, "pred_frames.json")))
+    for name, frame in want.items():
+        g, out, _ = load_case(name)
+        humans, scores = O.humans_as_dicts(O.parse_image(out, g))
+        assert O.canonical(O.pred_frame(name + ".jpg", humans, scores, g.K)) == frame, name
