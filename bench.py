@@ -249,13 +249,37 @@ def run_ours(args, rank, world, local_rank):
     drain()
     torch.cuda.synchronize(dev)
 
+    # optional: replay the steps from a CUDA graph (one graph = `group` consecutive steps, so that the
+    # rotation of input and output buffers is part of it); the remainder of K runs eagerly
+    graph, group = None, 0
+    if args.cuda_graph and world == 1:
+        group = 2 * n_buf                           # a multiple of both rotations
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(group):
+                    step(i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize(dev)
+
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     t0 = time.perf_counter()
     ev0.record()
     last = None
-    for i in range(K):
-        last = step(i)
+    if graph is not None:
+        for _ in range(K // group):
+            graph.replay()
+        for i in range(K - K % group, K):
+            last = step(i)
+        last = outs[(K - 1) % 2] if last is None else last
+    else:
+        for i in range(K):
+            last = step(i)
     drain()                                         # the timed region ends when every gather has landed
     ev1.record()
     host_issue_ms = (time.perf_counter() - t0) * 1e3 / K     # host time to ENQUEUE a step (GPU runs behind)
@@ -360,7 +384,7 @@ def run_ours(args, rank, world, local_rank):
                    "bytes_per_image": cfg.bytes_per_image, "input_distribution": DIST[args.config],
                    "l2": f"{n_buf} distinct input batches of {batch_bytes / 1e6:.0f} MB rotated (each larger than L2)",
                    "humans_per_image": humans_per_image, "extra_warmup_steps": extra,
-                   "host_issue_ms_per_step": host_issue_ms,
+                   "host_issue_ms_per_step": host_issue_ms, "cuda_graph": bool(graph is not None),
                    "step_overlap": "off" if args.no_step_overlap else
                    "PPN_FLAG_INPUT_COMPLETE: inputs resident before the timed region, so step i+1's arg-max may start while "
                    "step i's tree parse finishes; steps complete in order",
@@ -423,6 +447,7 @@ def main():
     ap.add_argument("--settle-s", type=float, default=0.4)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the timed steps from a CUDA graph (1 GPU)")
     ap.add_argument("--no-step-overlap", action="store_true",
                     help="do not pass PPN_FLAG_INPUT_COMPLETE (each step's kernels wait for the previous step's)")
     ap.add_argument("--tune", action="append", default=[], help="library knob, e.g. argmax.stages=6")

@@ -308,6 +308,39 @@ def test_overlapped_consecutive_calls(preset, dist, B):
     assert_packed_equals_oracle(last.numpy(), refs[5 % n_in], B)
 
 
+@pytest.mark.parametrize("overlap", [1, 2])
+def test_cuda_graph_capture(overlap):
+    """The whole path is capturable: three parses (PDL chain or side-stream fork/join) recorded into
+    one CUDA graph and replayed on new data."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PPNConfig.mpii16()
+    g = O.Geometry.of(cfg)
+    B = 12
+    heads = [synth.make_head(g, "U", seed=700 + i, B=B) for i in range(2)]
+    refs = [c_oracle.parse_batch(h, g, n_threads=8) for h in heads]
+    static_in = torch.from_numpy(heads[0]).cuda()
+    _lib.tune(parse_overlap=overlap)
+    try:
+        parser = PoseParser(cfg)
+        outs = [parser.alloc_output(B) for _ in range(3)]
+        parser.parse(static_in, out=outs[0])                 # first call outside capture (one-time set-up)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for o in outs:
+                parser.parse(static_in, out=o, input_complete=True)
+        for which in (1, 0, 1):
+            static_in.copy_(torch.from_numpy(heads[which]).cuda())
+            graph.replay()
+            torch.cuda.synchronize()
+            for o in outs:
+                assert_packed_equals_oracle(o.numpy(), refs[which], B)
+    finally:
+        _lib.tune(parse_overlap=2)
+
+
 def test_every_launch_ordering_gives_same_result():
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PPNConfig
