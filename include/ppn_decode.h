@@ -28,7 +28,7 @@
  *     selects the device (cudaSetDevice / torch.cuda.set_device) before calling.
  *   - thread-safe for distinct streams and buffers; no global mutable state except the
  *     tuning table set by ppn_tune() (meant for benchmarking, set once before use).
- *   - head tensor: fp32, NCHW contiguous [B, 6K + sH*sW*E, H, W]; channel groups resp, conf,
+ *   - head tensor: fp32 (or fp16 / bf16, PPNShape.head_dtype), NCHW contiguous [B, 6K + sH*sW*E, H, W]; channel groups resp, conf,
  *     x, y, w, h (K each) then the limb block viewed as [E, sH, sW, H, W] (model.py:64,
  *     rt_test.py:109-120).  16-byte aligned base.
  *   - cells are flat indices h*W + w; boxes are (ymin, xmin, ymax, xmax) in pixels.
@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define PPN_ABI_VERSION 2
+#define PPN_ABI_VERSION 3
 
 /* library error codes (negative); positive return values are cudaError_t */
 #define PPN_OK               0
@@ -69,7 +69,15 @@ typedef struct PPNShape {
     int32_t inW, inH;       /* network input size in pixels                                      */
     int32_t gridW, gridH;   /* int(inW/outW), int(inH/outH)  (datatest.py:60)                    */
     int32_t off_h, off_w;   /* half-windows subtracted from row / column (datatest.py:115-116)   */
+    int32_t head_dtype;     /* PPN_HEAD_F32 (the reference's), PPN_HEAD_F16 or PPN_HEAD_BF16          */
 } PPNShape;
+
+/* Element type of the head tensor.  A 16-bit head halves the HBM traffic of the path; every
+ * element is widened to fp32 exactly when loaded and all arithmetic stays the reference's fp32,
+ * so the result is the reference's on head.float(). */
+#define PPN_HEAD_F32  0
+#define PPN_HEAD_F16  1
+#define PPN_HEAD_BF16 2
 
 /* Thresholds and the track orders (config.py:67-80 DIRECTED_GRAPHS, flattened).  The three
  * chain arrays are HOST pointers; they are copied into kernel arguments at launch. */
@@ -116,11 +124,11 @@ int ppn_parse_launches(const PPNShape* shape, const PPNParams* params);
 
 /* amax[B, E, H*W] (uint16) = index in [0, sH*sW) of the FIRST maximum of each limb window;
  * NaN counts as the maximum (numpy argmax).  Streams the limb block once. */
-int ppn_limb_argmax(const float* head, const PPNShape* shape, uint16_t* amax, void* stream);
+int ppn_limb_argmax(const void* head, const PPNShape* shape, uint16_t* amax, void* stream);
 
 /* For parts 0..n_parts-1 of every image: cells with resp*conf > det_thresh in ascending cell
  * order, with score and box.  Lists are [B, n_parts, H*W]; cand_count is [B, n_parts]. */
-int ppn_decode_candidates(const float* head, const PPNShape* shape, int32_t n_parts, float det_thresh,
+int ppn_decode_candidates(const void* head, const PPNShape* shape, int32_t n_parts, float det_thresh,
                           int32_t* cand_cell, float* cand_score, float* cand_box, int32_t* cand_count,
                           void* stream);
 
@@ -144,7 +152,7 @@ int ppn_nms(const float* box, const float* score, const int32_t* count, int32_t 
 /* Walk the track orders from every surviving root of part 0.  cand_cell/keep_idx/keep_count
  * are the outputs of the two calls above with params->n_nms_parts lists per image; with
  * cand_cell == NULL, keep_idx holds root CELLS directly instead of indices into cand_cell. */
-int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* params,
+int ppn_tree_parse(const void* head, const PPNShape* shape, const PPNParams* params,
                    const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                    const int32_t* keep_count, const PPNHumans* out, void* stream);
 
@@ -152,7 +160,7 @@ int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* pa
  * (candidates stay in shared memory), the limb arg-max started beside it, and the tree parse,
  * chained by programmatic dependent launch so that each kernel's start-up hides under its
  * predecessor.  Results are identical to calling the four stage functions above in sequence. */
-int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
+int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params,
               const PPNHumans* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The whole path from HOST memory (pinned for full speed): uploads `head` in chunks
@@ -160,7 +168,7 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
  * arrays of `out_host`.  Synchronous.  dev_scratch/dev_scratch_bytes: device memory of at
  * least ppn_parse_host_scratch_bytes(). */
 int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params, int32_t R, size_t* bytes);
-int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParams* params,
+int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams* params,
                    const PPNHumans* out_host, void* dev_scratch, size_t dev_scratch_bytes);
 
 /* Centre of every part's box, centre_yx[B, R, K, 2] = ((ymin + ymax) / 2, (xmin + xmax) / 2), (0, 0)

@@ -10,7 +10,8 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+HEAD_F32, HEAD_F16, HEAD_BF16 = 0, 1, 2
 FLAG_INPUT_COMPLETE = 1
 MAX_CELLS = 1024
 MAX_CHAINS = 32
@@ -23,7 +24,7 @@ u16p = C.POINTER(C.c_uint16)
 
 class PPNShape(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("B", "K", "E", "H", "W", "sH", "sW", "inW", "inH", "gridW", "gridH", "off_h", "off_w")]
+                ("B", "K", "E", "H", "W", "sH", "sW", "inW", "inH", "gridW", "gridH", "off_h", "off_w", "head_dtype")]
 
 
 class PPNParams(C.Structure):

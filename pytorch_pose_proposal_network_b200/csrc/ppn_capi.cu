@@ -65,6 +65,7 @@ int check_shape(const PPNShape* s) {
     if (s->K > 255 || s->E > 255) return PPN_E_UNSUPPORTED;                    // chain tables are uint8
     const long long per_img = ((long long)6 * s->K + (long long)s->sH * s->sW * s->E) * s->H * s->W;
     if (per_img > 0x7fffffffLL) return PPN_E_UNSUPPORTED;
+    if (s->head_dtype < PPN_HEAD_F32 || s->head_dtype > PPN_HEAD_BF16) return PPN_E_BADARG;
     return PPN_OK;
 }
 
@@ -79,6 +80,7 @@ ppn::Geom make_geom(const PPNShape* s) {
     auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
     g.magic_W = magic(g.W);
     g.magic_K = magic(g.K);
+    g.dtype = s->head_dtype;
     return g;
 }
 
@@ -116,6 +118,9 @@ int make_chains(const PPNShape* s, const PPNParams* p, ppn::ChainTable* ch) {
         }
     return PPN_OK;
 }
+
+inline size_t elem_bytes(const PPNShape* s) { return s->head_dtype == PPN_HEAD_F32 ? 4 : 2; }
+inline bool misaligned(const void* p, const PPNShape* s) { return (reinterpret_cast<uintptr_t>(p) & (elem_bytes(s) - 1)) != 0; }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -233,16 +238,16 @@ int ppn_parse_launches(const PPNShape* shape, const PPNParams* params) {
     return shape->B > 0 ? 3 : 0;
 }
 
-int ppn_limb_argmax(const float* head, const PPNShape* shape, uint16_t* amax, void* stream) {
+int ppn_limb_argmax(const void* head, const PPNShape* shape, uint16_t* amax, void* stream) {
     int rc = check_shape(shape);
     if (rc) return rc;
     if (shape->B == 0 || shape->E == 0) return PPN_OK;
     if (!head || !amax) return PPN_E_BADARG;
-    if (reinterpret_cast<uintptr_t>(head) & 3) return PPN_E_BADARG;
+    if (misaligned(head, shape)) return PPN_E_BADARG;
     return cuda_rc(ppn::launch_limb_argmax(head, amax, make_geom(shape), g_tuning, (cudaStream_t)stream));
 }
 
-int ppn_decode_candidates(const float* head, const PPNShape* shape, int32_t n_parts, float det_thresh,
+int ppn_decode_candidates(const void* head, const PPNShape* shape, int32_t n_parts, float det_thresh,
                           int32_t* cand_cell, float* cand_score, float* cand_box, int32_t* cand_count, void* stream) {
     int rc = check_shape(shape);
     if (rc) return rc;
@@ -284,7 +289,7 @@ int ppn_nms(const float* box, const float* score, const int32_t* count, int32_t 
                                    (cudaStream_t)stream));
 }
 
-int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* params, const uint16_t* amax,
+int ppn_tree_parse(const void* head, const PPNShape* shape, const PPNParams* params, const uint16_t* amax,
                    const int32_t* cand_cell, const int32_t* keep_idx, const int32_t* keep_count,
                    const PPNHumans* out, void* stream) {
     int rc = check_shape(shape);
@@ -303,7 +308,7 @@ int ppn_tree_parse(const float* head, const PPNShape* shape, const PPNParams* pa
                                           (cudaStream_t)stream));
 }
 
-int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
               void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_shape(shape);
     if (rc) return rc;
@@ -313,7 +318,7 @@ int ppn_parse(const float* head, const PPNShape* shape, const PPNParams* params,
     if ((rc = make_chains(shape, params, &ch))) return rc;
     if (shape->B == 0) return PPN_OK;
     if (!head || !workspace) return PPN_E_BADARG;
-    if ((reinterpret_cast<uintptr_t>(head) & 3) || (reinterpret_cast<uintptr_t>(workspace) & 255)) return PPN_E_BADARG;
+    if (misaligned(head, shape) || (reinterpret_cast<uintptr_t>(workspace) & 255)) return PPN_E_BADARG;
     if ((long long)shape->H * shape->W > PPN_MAX_CELLS) return PPN_E_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out->part_box) & 15) return PPN_E_BADARG;
     const int P = params->n_nms_parts;
@@ -485,7 +490,7 @@ HostPlan plan_host(const PPNShape* s, const PPNParams* p, int R) {
     if (h.chunk > s->B) h.chunk = s->B > 0 ? s->B : 1;
     PPNShape cs = *s;
     cs.B = h.chunk;
-    const size_t per_img = ((size_t)6 * s->K + (size_t)s->sH * s->sW * s->E) * s->H * s->W * sizeof(float);
+    const size_t per_img = ((size_t)6 * s->K + (size_t)s->sH * s->sW * s->E) * s->H * s->W * elem_bytes(s);
     h.head_bytes = align_up(per_img * h.chunk, 256);
     h.ws_bytes = 2 * carve(&cs, p->n_nms_parts).total;
     size_t off = 0;
@@ -512,7 +517,7 @@ int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params,
     return PPN_OK;
 }
 
-int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParams* params, const PPNHumans* out_host,
+int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams* params, const PPNHumans* out_host,
                    void* dev_scratch, size_t dev_scratch_bytes) {
     int rc = check_shape(shape);
     if (rc) return rc;
@@ -525,7 +530,7 @@ int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParam
     if (dev_scratch_bytes < h.total) return PPN_E_WORKSPACE;
     unsigned char* d = static_cast<unsigned char*>(dev_scratch);
     const size_t K = (size_t)shape->K;
-    const size_t per_img_f = ((size_t)6 * shape->K + (size_t)shape->sH * shape->sW * shape->E) * shape->H * shape->W;
+    const size_t per_img_b = ((size_t)6 * shape->K + (size_t)shape->sH * shape->sW * shape->E) * shape->H * shape->W * elem_bytes(shape);
 
     // two streams ping-pong over two (head, workspace) buffer pairs: the upload of chunk i+1
     // overlaps the kernels of chunk i; created once per thread and kept.
@@ -546,9 +551,9 @@ int ppn_parse_host(const float* head_host, const PPNShape* shape, const PPNParam
     for (int b0 = 0; b0 < shape->B; b0 += h.chunk, slot ^= 1) {
         const int nb = (shape->B - b0 < h.chunk) ? shape->B - b0 : h.chunk;
         cudaStream_t st = streams[slot];
-        float* d_head = reinterpret_cast<float*>(d + h.off_head[slot]);
-        if ((e = cudaMemcpyAsync(d_head, head_host + (size_t)b0 * per_img_f, (size_t)nb * per_img_f * sizeof(float),
-                                 cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+        void* d_head = d + h.off_head[slot];
+        if ((e = cudaMemcpyAsync(d_head, static_cast<const unsigned char*>(head_host) + (size_t)b0 * per_img_b,
+                                 (size_t)nb * per_img_b, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
         PPNShape cs = *shape;
         cs.B = nb;
         PPNHumans dev_out;

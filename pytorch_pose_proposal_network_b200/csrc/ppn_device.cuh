@@ -4,6 +4,8 @@
 // with the __f*_rn intrinsics, which round once and are never contracted into FMAs, so the
 // results are bit-identical to numpy's regardless of compiler flags.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,12 +27,28 @@ struct Geom {               // per-launch constants derived from PPNShape
     size_t img_stride;      // C*HW floats
     size_t limb_off;        // 6*K*HW floats
     uint32_t magic_W, magic_K;   // ceil(2^32 / d) for exact x / d, 0 <= x < 65536 (0 when d == 1)
+    int32_t dtype;               // HeadDtype of the head tensor (host side: picks the kernel instantiation)
 };
+
+// ---- head element types ------------------------------------------------------------------
+// The head tensor may be fp32 (the reference's), fp16 or bf16 (a head emitted in 16 bits halves the
+// HBM traffic of this path).  Every element is widened to fp32 — exactly — the
+// moment it is loaded; all arithmetic after that is the fp32 arithmetic of the reference, so the
+// result equals the reference run on `head.float()`.
+enum HeadDtype : int { HEAD_F32 = 0, HEAD_F16 = 1, HEAD_BF16 = 2 };
+
+__device__ __forceinline__ float widen(float v) { return v; }
+__device__ __forceinline__ float widen(__half v) { return __half2float(v); }
+__device__ __forceinline__ float widen(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p) { return widen(__ldg(p)); }      // read-only path + widen
 
 // ---- the reference's cell arithmetic --------------------------------------------------
 // delta = resp * conf  (rt_test.py:130)
-__device__ __forceinline__ float delta_at(const float* __restrict__ img, const Geom& g, int k, int c) {
-    return __fmul_rn(__ldg(img + (size_t)k * g.HW + c), __ldg(img + (size_t)(g.K + k) * g.HW + c));
+template <typename T>
+__device__ __forceinline__ float delta_at(const T* __restrict__ img, const Geom& g, int k, int c) {
+    return __fmul_rn(ldf(img + (size_t)k * g.HW + c), ldf(img + (size_t)(g.K + k) * g.HW + c));
 }
 
 // (ymin, xmin, ymax, xmax) from the four raw head values of a cell at (row h, col w)
@@ -45,11 +63,12 @@ __device__ __forceinline__ float4 box_from(float x, float y, float bw, float bh,
 }
 
 // the same for part k at cell c, reading the head tensor of one image
-__device__ __forceinline__ float4 box_at(const float* __restrict__ img, const Geom& g, int k, int c) {
+template <typename T>
+__device__ __forceinline__ float4 box_at(const T* __restrict__ img, const Geom& g, int k, int c) {
     const int h = c / g.W, w = c - h * g.W;
     const size_t HW = g.HW;
-    return box_from(__ldg(img + (size_t)(2 * g.K + k) * HW + c), __ldg(img + (size_t)(3 * g.K + k) * HW + c),
-                    __ldg(img + (size_t)(4 * g.K + k) * HW + c), __ldg(img + (size_t)(5 * g.K + k) * HW + c), h, w, g);
+    return box_from(ldf(img + (size_t)(2 * g.K + k) * HW + c), ldf(img + (size_t)(3 * g.K + k) * HW + c),
+                    ldf(img + (size_t)(4 * g.K + k) * HW + c), ldf(img + (size_t)(5 * g.K + k) * HW + c), h, w, g);
 }
 
 // numpy's maximum / minimum: propagate NaN (datatest.py:145-146)

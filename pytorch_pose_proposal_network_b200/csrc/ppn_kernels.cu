@@ -285,6 +285,147 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();    // see limb_argmax_tma_kernel
 }
 
+// The same ring and thread mapping for a 16-bit head (fp16 / bf16): rows are HW * 2 bytes, a thread
+// owns EIGHT columns (one 16-byte vector) and widens each value to fp32 before the comparison, so
+// the answer is the fp32 kernel's on `head.float()`.  p.CV counts 16-byte vectors per row (HW / 8).
+template <typename T16>
+__device__ __forceinline__ void widen8(const uint4 raw, float* v);
+template <>
+__device__ __forceinline__ void widen8<__half>(const uint4 raw, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void widen8<__nv_bfloat16>(const uint4 raw, float* v) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                     // bf16 -> fp32 is a 16-bit shift
+        v[2 * q] = __uint_as_float(w[q] << 16);
+        v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+    }
+}
+
+template <typename T16>
+__global__ void __launch_bounds__(1024, 1)
+limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p, int pdl,
+                               int* __restrict__ ticket) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* ring = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t* empty = full + p.stages;
+    int* s_item = reinterpret_cast<int*>(empty + p.stages);
+
+    const int tid = threadIdx.x;
+    const int n_cons = p.threads_padded;
+    const int n_mats = g.B * g.E;
+    const int M = p.G;
+    const int n_items = (n_mats + M - 1) / M;
+    const uint32_t slot_bytes = (uint32_t)p.rows * g.HW * 2u;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], n_cons / 32);
+        }
+        fence_mbar_init();
+    }
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();
+    __syncthreads();
+
+    if (tid >= n_cons) {
+        const int lane = tid - n_cons;
+        int stage = 0;
+        uint32_t phase = 0;
+        int item = blockIdx.x;
+        for (;;) {
+            if (ticket) {
+                if (lane == 0) item = atomicAdd(ticket, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+            }
+            if (item >= n_items) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                if (lane == 0) { s_item[stage] = -1; mbar_arrive(&full[stage]); }
+                break;
+            }
+            const int m = item * M + lane;
+            const int nm = min(M, n_mats - item * M);
+            const int b = m / g.E, ei = m - b * g.E;
+            const T16* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
+            for (int c = 0; c < p.chunks; ++c) {
+                mbar_wait(&empty[stage], phase ^ 1u);
+                const int rows = min(p.rows, g.S - c * p.rows);
+                const uint32_t bytes = (uint32_t)rows * g.HW * 2u;
+                if (lane == 0) {
+                    if (c == 0) s_item[stage] = item;
+                    mbar_arrive_expect_tx(&full[stage], bytes * nm);
+                }
+                __syncwarp();
+                if (lane < nm)
+                    bulk_g2s(ring + (size_t)stage * p.stage_bytes + (size_t)lane * slot_bytes,
+                             src + (size_t)c * p.rows * g.HW, bytes, &full[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            if (!ticket) item += gridDim.x;
+        }
+        if (ticket && lane == 0 && atomicAdd(ticket + 1, 1) == (int)gridDim.x - 1) { ticket[0] = 0; ticket[1] = 0; }
+        return;
+    }
+
+    const int j = tid / p.CV, cv = tid - j * p.CV;
+    const int lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        mbar_wait(&full[stage], phase);
+        const int item = s_item[stage];
+        if (item < 0) break;
+        const int m = item * M + j;
+        const bool active = tid < p.threads && m < n_mats;
+        float best[8];
+        int idx[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; idx[q] = 0; }
+        for (int c = 0; c < p.chunks; ++c) {
+            if (c > 0) mbar_wait(&full[stage], phase);
+            if (active) {
+                const int rows = min(p.rows, g.S - c * p.rows);
+                const uint4* col = reinterpret_cast<const uint4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
+                int a = c * p.rows;
+                int r = 0;
+#pragma unroll 1
+                for (; r + 1 < rows; r += 2, a += 2) {
+                    const uint4 r0 = col[(size_t)r * p.CV];
+                    const uint4 r1 = col[(size_t)(r + 1) * p.CV];
+                    float v0[8], v1[8];
+                    widen8<T16>(r0, v0);
+                    widen8<T16>(r1, v1);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) argmax_step(best[q], idx[q], v0[q], a);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) argmax_step(best[q], idx[q], v1[q], a + 1);
+                }
+                for (; r < rows; ++r, ++a) {
+                    float v[8];
+                    widen8<T16>(col[(size_t)r * p.CV], v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) argmax_step(best[q], idx[q], v[q], a);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (active) {
+            uint4 o;
+            o.x = (uint32_t)idx[0] | ((uint32_t)idx[1] << 16); o.y = (uint32_t)idx[2] | ((uint32_t)idx[3] << 16);
+            o.z = (uint32_t)idx[4] | ((uint32_t)idx[5] << 16); o.w = (uint32_t)idx[6] | ((uint32_t)idx[7] << 16);
+            *reinterpret_cast<uint4*>(amax + (size_t)m * g.HW + 8 * cv) = o;
+        }
+    }
+    if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
+}
+
 // Variant without the ring: one CTA per matrix, 128-bit streaming loads straight to registers.
 // Kept as the measured alternative (ppn_tune "argmax.variant" = 1).
 __global__ void __launch_bounds__(1024, 1)
@@ -337,30 +478,32 @@ limb_argmax_ldg_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
 }
 
 // Any shape (H*W not a multiple of 4, huge grids): one thread per column, scalar loads.
+template <typename T>
 __global__ void __launch_bounds__(256)
-limb_argmax_generic_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g) {
+limb_argmax_generic_kernel(const T* __restrict__ head, uint16_t* __restrict__ amax, Geom g) {
     const int m = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.HW) return;
     const int b = m / g.E, ei = m - b * g.E;
-    const float* col = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW + c;
+    const T* col = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW + c;
     float best = -INFINITY;
     int idx = 0;
-    for (int a = 0; a < g.S; ++a) argmax_step(best, idx, __ldg(col + (size_t)a * g.HW), a);
+    for (int a = 0; a < g.S; ++a) argmax_step(best, idx, ldf(col + (size_t)a * g.HW), a);
     amax[(size_t)m * g.HW + c] = (uint16_t)idx;
 }
 
 // =========================================================================================
 // K1 — decode + ordered compaction of candidates, one CTA per (image, part)
 // =========================================================================================
+template <typename T>
 __global__ void __launch_bounds__(256)
-decode_candidates_kernel(const float* __restrict__ head, Geom g, int n_parts, float thr,
+decode_candidates_kernel(const T* __restrict__ head, Geom g, int n_parts, float thr,
                          int32_t* __restrict__ cand_cell, float* __restrict__ cand_score,
                          float4* __restrict__ cand_box, int32_t* __restrict__ cand_count) {
     __shared__ int warp_tot[8];
     __shared__ int base_s;
     const int b = blockIdx.x, k = blockIdx.y;
-    const float* img = head + (size_t)b * g.img_stride;
+    const T* img = head + (size_t)b * g.img_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t list = ((size_t)b * n_parts + k) * g.HW;
     if (tid == 0) base_s = 0;
@@ -603,8 +746,9 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
 // compacts the candidates into SHARED memory (never to HBM) and suppresses them right there; what
 // leaves the kernel is the list of surviving root CELLS in visiting order.  All six values of a
 // cell are loaded up front so the CTA pays one HBM round trip.
+template <typename T>
 __global__ void __launch_bounds__(512)
-decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
+decode_nms_kernel(const T* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
                   int32_t* __restrict__ keep_cell, int32_t* __restrict__ keep_count, int pdl) {
     extern __shared__ __align__(128) unsigned char smem[];
     // pdl & 2: launched as a programmatic dependent itself (of the previous call's tree parse, or of
@@ -618,7 +762,7 @@ decode_nms_kernel(const float* __restrict__ head, Geom g, int n_parts, float det
     int32_t* ucell = reinterpret_cast<int32_t*>(ubox + g.HW);               // [HW]
     const NmsSmem s = nms_carve(reinterpret_cast<unsigned char*>(ucell + ((g.HW + 3) & ~3)), g.HW);
     const int b = blockIdx.x, k = blockIdx.y;
-    const float* img = head + (size_t)b * g.img_stride;
+    const T* img = head + (size_t)b * g.img_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) base_s = 0;
     for (int i = tid; i < g.HW; i += blockDim.x) s.rank[i] = 0;
@@ -738,15 +882,15 @@ __device__ __forceinline__ int fast_div(int x, uint32_t magic) {      // exact f
 
 // kStaged: resp/conf live in shared memory (plain LDS) — otherwise they are read from the head tensor
 // through the read-only path.  A compile-time switch, so neither case pays for generic addressing.
-template <bool kStaged>
-__device__ __forceinline__ float delta_lookup(const float* resp, const float* conf, int at) {
-    if (kStaged) return __fmul_rn(resp[at], conf[at]);
-    return __fmul_rn(__ldg(resp + at), __ldg(conf + at));
+template <bool kStaged, typename HT>
+__device__ __forceinline__ float delta_lookup(const HT* resp, const HT* conf, int at) {
+    if (kStaged) return __fmul_rn(widen(resp[at]), widen(conf[at]));
+    return __fmul_rn(ldf(resp + at), ldf(conf + at));
 }
 
-template <bool kStaged>
+template <bool kStaged, typename HT>
 __device__ __forceinline__ void walk_chain(const ChainTable& ch, int cidx, int root, const Geom& g, float thr,
-                                           const float* s_resp, const float* s_conf, const uint16_t* s_amax,
+                                           const HT* s_resp, const HT* s_conf, const uint16_t* s_amax,
                                            const int32_t* s_dyx, bool use_tab, int16_t* my_pos) {
     int ih = fast_div(root, g.magic_W), iw = root - ih * g.W;
     for (int q = ch.off[cidx]; q < ch.off[cidx + 1]; ++q) {
@@ -764,16 +908,16 @@ __device__ __forceinline__ void walk_chain(const ChainTable& ch, int cidx, int r
         }
         if (jh < 0 || jw < 0 || jh >= g.H || jw >= g.W) break;                         // datatest.py:118
         const int j = jh * g.W + jw;
-        if (delta_lookup<kStaged>(s_resp, s_conf, t * g.HW + j) < thr) break;          // datatest.py:121
+        if (delta_lookup<kStaged, HT>(s_resp, s_conf, t * g.HW + j) < thr) break;          // datatest.py:121
         my_pos[t] = (int16_t)j;
         ih = jh;
         iw = jw;
     }
 }
 
-template <bool kStaged>
+template <bool kStaged, typename HT>
 __global__ void __launch_bounds__(1024)
-tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
+tree_parse_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float thr, int min_kp, int n_parts,
                   const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
                   const int32_t* __restrict__ keep_idx, const int32_t* __restrict__ keep_count,
                   int32_t* __restrict__ h_count, int32_t* __restrict__ h_root, int32_t* __restrict__ h_cell,
@@ -783,8 +927,8 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
     // staged channel groups: 0 = none (big grids: the walk reads resp/conf through L2 and the CTA
     // stays light enough to sit beside the arg-max ring), 2 = resp, conf, 6 = also x, y, w, h
     const int n_groups = stage_all;
-    float* s_planes = reinterpret_cast<float*>(smem);                                  // [n_groups][K*HW]
-    uint16_t* s_amax = reinterpret_cast<uint16_t*>(s_planes + (size_t)n_groups * KHW); // [E*HW] (+pad)
+    HT* s_planes = reinterpret_cast<HT*>(smem);                                          // [n_groups][K*HW]
+    uint16_t* s_amax = reinterpret_cast<uint16_t*>(smem + ((((size_t)n_groups * KHW * sizeof(HT)) + 15) & ~(size_t)15));  // [E*HW] (+pad)
     int32_t* s_root = reinterpret_cast<int32_t*>(s_amax + (((size_t)g.E * g.HW + 7) & ~(size_t)7));  // [HW]
     int32_t* s_slot = s_root + g.HW;                                                   // [HW]
     int32_t* s_dyx = s_slot + g.HW;                                                    // [S] if small
@@ -795,12 +939,12 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
 
     const int b = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const float* img = head + (size_t)b * g.img_stride;
-    const float* s_resp = kStaged ? s_planes : img;               // shared when kStaged, else the head tensor
-    const float* s_conf = s_resp + KHW;
+    const HT* img = head + (size_t)b * g.img_stride;
+    const HT* s_resp = kStaged ? s_planes : img;                   // shared when kStaged, else the head tensor
+    const HT* s_conf = s_resp + KHW;
     const uint16_t* am = amax + (size_t)b * g.E * g.HW;
     const bool use_tab = g.S <= kMaxDyxTable;
-    const uint32_t bytes_planes = (uint32_t)n_groups * KHW * 4u, bytes_am = (uint32_t)g.E * g.HW * 2u;
+    const uint32_t bytes_planes = (uint32_t)n_groups * KHW * (uint32_t)sizeof(HT), bytes_am = (uint32_t)g.E * g.HW * 2u;
 
     // ---- prologue: nothing here depends on the kernels before this one -----------------------
     if (use_tma) {
@@ -833,7 +977,7 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
     // as one contiguous read, so that those gathers are L2 hits instead of scattered DRAM sectors
     // (dense-crowd config: tree parse 111 -> 96 us); for sparse images it would only add traffic.
     if (use_tma && tid == 0 && n_groups < 6 && n_keep * 8 >= g.HW * 3)
-        bulk_prefetch_l2(img + (size_t)n_groups * KHW, (uint32_t)(6 - n_groups) * KHW * 4u);
+        bulk_prefetch_l2(img + (size_t)n_groups * KHW, (uint32_t)(6 - n_groups) * KHW * (uint32_t)sizeof(HT));
     const int32_t* keep = keep_idx + (size_t)b * n_parts * g.HW;
     const int32_t* cells = cand_cell ? cand_cell + (size_t)b * n_parts * g.HW : nullptr;
 
@@ -854,10 +998,10 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
         if (r < n_keep) {
             int16_t* my_pos = s_pos + r * g.K;
             if (ch.parallel_ok) {
-                walk_chain<kStaged>(ch, cidx, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+                walk_chain<kStaged, HT>(ch, cidx, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
             } else {
                 for (int c = 0; c < ch.n_chains; ++c)
-                    walk_chain<kStaged>(ch, c, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+                    walk_chain<kStaged, HT>(ch, c, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
             }
         }
     }
@@ -907,11 +1051,11 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
                     if (cc[u] >= 0) {
                         const int at = t * g.HW + cc[u];
                         if (n_groups == 6) {
-                            xs[u] = s_planes[2 * KHW + at]; ys[u] = s_planes[3 * KHW + at];
-                            ws[u] = s_planes[4 * KHW + at]; hs[u] = s_planes[5 * KHW + at];
+                            xs[u] = widen(s_planes[2 * KHW + at]); ys[u] = widen(s_planes[3 * KHW + at]);
+                            ws[u] = widen(s_planes[4 * KHW + at]); hs[u] = widen(s_planes[5 * KHW + at]);
                         } else {
-                            xs[u] = __ldg(img + (size_t)2 * KHW + at); ys[u] = __ldg(img + (size_t)3 * KHW + at);
-                            ws[u] = __ldg(img + (size_t)4 * KHW + at); hs[u] = __ldg(img + (size_t)5 * KHW + at);
+                            xs[u] = ldf(img + (size_t)2 * KHW + at); ys[u] = ldf(img + (size_t)3 * KHW + at);
+                            ws[u] = ldf(img + (size_t)4 * KHW + at); hs[u] = ldf(img + (size_t)5 * KHW + at);
                         }
                     }
                 }
@@ -926,7 +1070,7 @@ tree_parse_kernel(const float* __restrict__ head, Geom g, ChainTable ch, float t
             if (c >= 0) {
                 const int at = tt[u] * g.HW + c;
                 const int h = fast_div(c, g.magic_W), w = c - h * g.W;
-                score = delta_lookup<kStaged>(s_resp, s_conf, at);
+                score = delta_lookup<kStaged, HT>(s_resp, s_conf, at);
                 box = box_from(xs[u], ys[u], ws[u], hs[u], h, w, g);
             }
             const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
@@ -1068,7 +1212,8 @@ pack_entries_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
 // per device, on the first launch (so make the first call outside stream capture).
 constexpr int kTicketSlots = 64;
 struct DeviceInfo { int* tickets = nullptr; cudaStream_t slot_stream[kTicketSlots] = {}; int slots_used = 0;
-                    int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, decode_nms = 0, ldg = 0, nms = 0, tree = 0, tree_light = 0; };
+                    int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, tma16[2] = {0, 0}, decode_nms[3] = {0, 0, 0}, ldg = 0, nms = 0,
+                           tree[3] = {0, 0, 0}, tree_light[3] = {0, 0, 0}; };
 static DeviceInfo g_dev[64];
 
 // Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
@@ -1190,7 +1335,66 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     return true;
 }
 
-cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
+// Ring plan for a 16-bit head: always the split-matrix mapping, 16-byte vectors of 8 columns.
+static bool plan_argmax16(const Geom& g, const Tuning& t, ArgmaxPlan* p) {
+    if (g.HW % 8 != 0 || g.HW / 8 > 992) return false;
+    p->CV = g.HW / 8;
+    const int row_bytes = g.HW * 2;
+    int G = t.argmax_threads / p->CV;
+    if (G < 1) G = 1;
+    while (G > 1 && p->CV * G > 992) --G;
+    if (G > 32) G = 32;
+    if (G > g.B * g.E) G = g.B * g.E;
+    p->split_mats = 1;
+    p->G = G;
+    p->threads = p->CV * G;
+    p->threads_padded = (p->threads + 31) & ~31;
+    const int per_row = row_bytes * G;
+    int max_rows = t.argmax_stage_bytes / per_row;
+    if (max_rows < 1) max_rows = 1;
+    if (max_rows > g.S) max_rows = g.S;
+    p->chunks = (g.S + max_rows - 1) / max_rows;
+    p->rows = (g.S + p->chunks - 1) / p->chunks;
+    p->chunks = (g.S + p->rows - 1) / p->rows;
+    p->stage_bytes = (uint32_t)(((size_t)p->rows * per_row + 127) & ~(size_t)127);
+    p->stages = t.argmax_stages;
+    p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
+    p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * p->stages * sizeof(uint64_t) + (size_t)p->stages * sizeof(int);
+    return true;
+}
+
+template <typename T16>
+static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
+                                        bool pdl, bool* pdl_used, int pdl_bits, DeviceInfo* d, size_t* have) {
+    const int n_mats = g.B * g.E;
+    ArgmaxPlan p;
+    cudaError_t e;
+    if (plan_argmax16(g, t, &p) && (reinterpret_cast<uintptr_t>(head) & 15) == 0 && (g.img_stride * 2) % 16 == 0 &&
+        (g.limb_off * 2) % 16 == 0) {
+        const size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
+        while (p.smem_bytes > budget && p.stages > 2) {
+            --p.stages;
+            p.smem_bytes -= p.stage_bytes + 2 * sizeof(uint64_t) + sizeof(int);
+        }
+        if (p.smem_bytes <= budget) {
+            int* ticket = nullptr;
+            if (t.argmax_dynamic && (e = ticket_for(d, st, &ticket)) != cudaSuccess) return e;
+            int grid = d->sms * p.ctas_per_sm;
+            const int n_items = (n_mats + p.G - 1) / p.G;
+            if (grid > n_items) grid = n_items;
+            if ((e = ensure_smem(limb_argmax_tma_multi16_kernel<T16>, p.smem_bytes, have)) != cudaSuccess) return e;
+            e = launch_kernel(limb_argmax_tma_multi16_kernel<T16>, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
+                              head, amax, g, p, pdl_bits, ticket);
+            if (pdl_used) *pdl_used = pdl;
+            return e;
+        }
+    }
+    dim3 grid((g.HW + 255) / 256, n_mats);
+    limb_argmax_generic_kernel<T16><<<grid, 256, 0, st>>>(head, amax, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
                                bool pdl, bool* pdl_used, int pdl_bits) {
     if (pdl_used) *pdl_used = false;
     if (pdl_bits < 0) pdl_bits = pdl ? (PDL_TRIGGER | PDL_WAIT_END) : 0;
@@ -1199,6 +1403,12 @@ cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g,
     if (e != cudaSuccess) return e;
     const int n_mats = g.B * g.E;
     if (n_mats == 0) return cudaSuccess;
+    if (g.dtype == HEAD_F16)
+        return launch_limb_argmax16(static_cast<const __half*>(head_v), amax, g, t, st, pdl, pdl_used, pdl_bits, d, &d->tma16[0]);
+    if (g.dtype == HEAD_BF16)
+        return launch_limb_argmax16(static_cast<const __nv_bfloat16*>(head_v), amax, g, t, st, pdl, pdl_used, pdl_bits, d, &d->tma16[1]);
+    if (g.dtype != HEAD_F32) return cudaErrorInvalidValue;
+    const float* head = static_cast<const float*>(head_v);
     ArgmaxPlan p;
     const bool vec_ok = plan_argmax(g, t, d->sms, &p) && ((reinterpret_cast<uintptr_t>(head) & 15) == 0);
     if (vec_ok && t.argmax_variant == 0) {
@@ -1240,16 +1450,25 @@ cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g,
         return cudaGetLastError();
     }
     dim3 grid((g.HW + 255) / 256, n_mats);
-    limb_argmax_generic_kernel<<<grid, 256, 0, st>>>(head, amax, g);
+    limb_argmax_generic_kernel<float><<<grid, 256, 0, st>>>(head, amax, g);
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode_candidates(const float* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
+// run `...` with T bound to the head tensor's element type
+#define PPN_DISPATCH_HEAD(dtype, ...)                                                        \
+    switch (dtype) {                                                                         \
+        case HEAD_F32: { using T = float; __VA_ARGS__; } break;                              \
+        case HEAD_F16: { using T = __half; __VA_ARGS__; } break;                             \
+        case HEAD_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break;                     \
+        default: return cudaErrorInvalidValue;                                               \
+    }
+
+cudaError_t launch_decode_candidates(const void* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
                                      float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st) {
     if (g.B == 0 || n_parts == 0) return cudaSuccess;
     dim3 grid(g.B, n_parts);
-    decode_candidates_kernel<<<grid, 256, 0, st>>>(head, g, n_parts, thr, cand_cell, cand_score,
-                                                   reinterpret_cast<float4*>(cand_box), cand_count);
+    PPN_DISPATCH_HEAD(g.dtype, decode_candidates_kernel<T><<<grid, 256, 0, st>>>(
+        static_cast<const T*>(head), g, n_parts, thr, cand_cell, cand_score, reinterpret_cast<float4*>(cand_box), cand_count));
     return cudaGetLastError();
 }
 
@@ -1317,7 +1536,7 @@ size_t decode_nms_smem_bytes(const Geom& g) {
     return (size_t)g.HW * sizeof(float4) + (size_t)((g.HW + 3) & ~3) * sizeof(int32_t) + nms_smem_bytes(g.HW);
 }
 
-cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
+cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
                               int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr, int pdl_bits) {
     if (g.B == 0 || n_parts == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
@@ -1325,20 +1544,25 @@ cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, flo
     if (e != cudaSuccess) return e;
     const size_t smem = decode_nms_smem_bytes(g);
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
-    if ((e = ensure_smem(decode_nms_kernel, smem, &d->decode_nms)) != cudaSuccess) return e;
     dim3 grid(g.B, n_parts);
-    return launch_kernel(decode_nms_kernel, grid, dim3(g.HW <= 256 ? 256 : 512), smem, st, pdl_attr, head, g, n_parts, det_thr,
-                         nms_thr, keep_cell, keep_count, pdl_bits);
+    PPN_DISPATCH_HEAD(g.dtype, {
+        if ((e = ensure_smem(decode_nms_kernel<T>, smem, &d->decode_nms[g.dtype])) != cudaSuccess) return e;
+        return launch_kernel(decode_nms_kernel<T>, grid, dim3(g.HW <= 256 ? 256 : 512), smem, st, pdl_attr,
+                             static_cast<const T*>(head), g, n_parts, det_thr, nms_thr, keep_cell, keep_count, pdl_bits);
+    });
+    return cudaErrorInvalidValue;
 }
 
+static size_t head_elem_bytes(int dtype) { return dtype == HEAD_F32 ? 4 : 2; }
+
 size_t tree_parse_smem_bytes(const Geom& g, int n_groups) {
-    return (size_t)n_groups * g.K * g.HW * sizeof(float) +
+    return ((((size_t)n_groups * g.K * g.HW * head_elem_bytes(g.dtype)) + 15) & ~(size_t)15) +
            ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
            (size_t)2 * g.HW * sizeof(int32_t) + (g.S <= kMaxDyxTable ? (size_t)g.S * sizeof(int32_t) : 0) +
            (((size_t)g.HW * g.K + 7) & ~(size_t)7) * sizeof(int16_t);
 }
 
-cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
+cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
                               float* h_score, float* h_box, int R, cudaStream_t st, bool pdl_attr, int pdl_bits,
@@ -1363,16 +1587,25 @@ cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable
     int threads = threads_pref > 0 ? threads_pref : ((g.HW <= 144 || n_groups == 0) ? 256 : 512);
     threads = ((threads < 64 ? 64 : (threads > 1024 ? 1024 : threads)) + 31) & ~31;
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
-    if ((e = n_groups ? ensure_smem(tree_parse_kernel<true>, smem, &d->tree)
-                      : ensure_smem(tree_parse_kernel<false>, smem, &d->tree_light)) != cudaSuccess) return e;
-    // bulk copies need 16-byte sizes and sources: the staged planes are 4*n*K*HW bytes at image
-    // offset 4*C*HW*b, the arg-max map 2*E*HW bytes at offset 2*E*HW*b
-    const bool tma_ok = ((size_t)g.K * g.HW * 8) % 16 == 0 && (g.img_stride * 4) % 16 == 0 &&
+    // bulk copies need 16-byte sizes and sources: the staged planes are es*n*K*HW bytes at image
+    // offset es*C*HW*b (es = element size), the arg-max map 2*E*HW bytes at offset 2*E*HW*b
+    const size_t es = head_elem_bytes(g.dtype);
+    const bool tma_ok = ((size_t)g.K * g.HW * 2 * es) % 16 == 0 && (g.img_stride * es) % 16 == 0 &&
                         ((size_t)g.E * g.HW * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(head) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(amax) & 15) == 0;
-    return launch_kernel(n_groups ? tree_parse_kernel<true> : tree_parse_kernel<false>, dim3(g.B), dim3(threads), smem, st,
-                         pdl_attr, head, g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root,
-                         h_cell, h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, pdl_bits);
+    PPN_DISPATCH_HEAD(g.dtype, {
+        if (n_groups) {
+            if ((e = ensure_smem(tree_parse_kernel<true, T>, smem, &d->tree[g.dtype])) != cudaSuccess) return e;
+            return launch_kernel(tree_parse_kernel<true, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head),
+                                 g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root, h_cell,
+                                 h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, pdl_bits);
+        }
+        if ((e = ensure_smem(tree_parse_kernel<false, T>, smem, &d->tree_light[g.dtype])) != cudaSuccess) return e;
+        return launch_kernel(tree_parse_kernel<false, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head),
+                             g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root, h_cell,
+                             h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, pdl_bits);
+    });
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace ppn

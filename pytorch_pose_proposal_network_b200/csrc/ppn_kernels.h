@@ -39,17 +39,17 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p);
 
 // pdl: launch as a programmatic dependent of the previous kernel in `st` (starts beside it, waits
 // for it only before completing); *pdl_used tells whether the chosen kernel variant honoured it.
-cudaError_t launch_limb_argmax(const float* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
+cudaError_t launch_limb_argmax(const void* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
                                bool pdl = false, bool* pdl_used = nullptr, int pdl_bits = -1 /* default: trigger + end wait */);
 
-cudaError_t launch_decode_candidates(const float* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
+cudaError_t launch_decode_candidates(const void* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
                                      float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st);
 
 cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
                        float thr, int limit, int32_t* keep_idx, int32_t* keep_count, cudaStream_t st);
 
 // fused K1+K2 of the whole-path call: surviving root cells per (image, part), nothing else
-cudaError_t launch_decode_nms(const float* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
+cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
                               int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr = false,
                               int pdl_bits = 0);
 
@@ -67,7 +67,7 @@ cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const 
 
 size_t tree_parse_smem_bytes(const Geom& g, int n_groups);
 
-cudaError_t launch_tree_parse(const float* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
+cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
                               float* h_score, float* h_box, int R, cudaStream_t st, bool pdl_attr = false, int pdl_bits = 0,

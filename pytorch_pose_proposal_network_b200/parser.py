@@ -49,8 +49,8 @@ class _CConfig:
             int(n_nms_parts), len(self.off) - 1, int(flags),
             self.off.ctypes.data_as(_lib.i32p), self.limb.ctypes.data_as(_lib.i32p), self.part.ctypes.data_as(_lib.i32p))
 
-    def shape(self, B: int) -> _lib.PPNShape:
-        return _lib.PPNShape(B=B, **self._shape_fields)
+    def shape(self, B: int, head_dtype: int = 0) -> _lib.PPNShape:
+        return _lib.PPNShape(B=B, head_dtype=head_dtype, **self._shape_fields)
 
 
 class PackedHumans:
@@ -176,17 +176,19 @@ class PoseParser:
             return contextlib.nullcontext()
         return torch.cuda.device(self.device)
 
-    def _shape(self, B: int) -> _lib.PPNShape:
-        s = self._shapes.get(B)
+    def _shape(self, B: int, dtype: int = 0) -> _lib.PPNShape:
+        s = self._shapes.get((B, dtype))
         if s is None:
-            s = self._shapes[B] = self.c.shape(B)
+            s = self._shapes[(B, dtype)] = self.c.shape(B, dtype)
         return s
 
     # ---- buffers --------------------------------------------------------------------- #
+    _DTYPES = {torch.float32: _lib.HEAD_F32, torch.float16: _lib.HEAD_F16, torch.bfloat16: _lib.HEAD_BF16}
+
     def _check_head(self, head: torch.Tensor) -> int:
         cfg = self.cfg
-        if head.dtype != torch.float32 or head.dim() != 4 or tuple(head.shape[1:]) != (cfg.C, cfg.H, cfg.W):
-            raise ValueError(f"head must be fp32 [B,{cfg.C},{cfg.H},{cfg.W}], got {head.dtype} {tuple(head.shape)}")
+        if head.dtype not in self._DTYPES or head.dim() != 4 or tuple(head.shape[1:]) != (cfg.C, cfg.H, cfg.W):
+            raise ValueError(f"head must be fp32/fp16/bf16 [B,{cfg.C},{cfg.H},{cfg.W}], got {head.dtype} {tuple(head.shape)}")
         if not head.is_contiguous():
             raise ValueError("head must be contiguous NCHW")
         return head.shape[0]
@@ -243,7 +245,7 @@ class PoseParser:
         hs = self._humans_struct(out)
         with self._guard():
             params = self.c.params_input_complete if input_complete else self.c.params
-            rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B)), C.byref(params), C.byref(hs),
+            rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), C.byref(params), C.byref(hs),
                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             raise _lib.PPNError(rc, "ppn_parse")
@@ -262,7 +264,7 @@ class PoseParser:
         if out is None:
             out = self.alloc_output(B, device="cpu", pin=True)
         need = C.c_size_t()
-        shape = self.c.shape(B)
+        shape = self.c.shape(B, self._DTYPES[head.dtype])
         _lib.check(self.lib.ppn_parse_host_scratch_bytes(C.byref(shape), C.byref(self.c.params), self.R, C.byref(need)),
                    "ppn_parse_host_scratch_bytes")
         if self._host_scratch is None or self._host_scratch.numel() < need.value:
@@ -320,7 +322,7 @@ class PoseParser:
         B = self._check_head(head)
         cfg = self.cfg
         amax = torch.empty(B, cfg.E, cfg.H, cfg.W, dtype=torch.uint16, device=self.device)
-        shape = self.c.shape(B)
+        shape = self.c.shape(B, self._DTYPES[head.dtype])
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ppn_limb_argmax(_ptr(head), C.byref(shape), _ptr(amax), _stream_ptr(self.device)), "ppn_limb_argmax")
         return amax
@@ -334,7 +336,7 @@ class PoseParser:
         score = torch.empty(B, n_parts, HW, dtype=torch.float32, device=self.device)
         box = torch.empty(B, n_parts, HW, 4, dtype=torch.float32, device=self.device)
         count = torch.empty(B, n_parts, dtype=torch.int32, device=self.device)
-        shape = self.c.shape(B)
+        shape = self.c.shape(B, self._DTYPES[head.dtype])
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ppn_decode_candidates(_ptr(head), C.byref(shape), n_parts, thr, _ptr(cell), _ptr(score),
                                                       _ptr(box), _ptr(count), _stream_ptr(self.device)), "ppn_decode_candidates")
@@ -355,7 +357,7 @@ class PoseParser:
         B = self._check_head(head)
         if out is None:
             out = self.alloc_output(B)
-        shape, hs = self.c.shape(B), self._humans_struct(out)
+        shape, hs = self.c.shape(B, self._DTYPES[head.dtype]), self._humans_struct(out)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ppn_tree_parse(_ptr(head), C.byref(shape), C.byref(self.c.params), _ptr(amax), _ptr(cand_cell),
                                                _ptr(keep_idx), _ptr(keep_count), C.byref(hs), _stream_ptr(self.device)), "ppn_tree_parse")

@@ -224,6 +224,36 @@ def test_batch_matches_c_oracle(preset, dist, B):
     assert_packed_equals_oracle(host.numpy(), ref, B)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("preset,dist,B,grid", [("cfg2", "U", 24, None), ("cfg2", "D", 8, None), ("cfg3", "D", 6, None),
+                                               ("cfg4", "U", 4, None), ("cfg2", "U", 5, (13, 13)), ("cfg2", "R", 5, (10, 6))])
+def test_sixteen_bit_head(preset, dist, B, grid, dtype):
+    """fp16 / bf16 head tensors: every element is widened exactly, so the result must equal the fp32
+    restatement run on head.float() — including ties, which 16-bit values produce in abundance
+    (first arg-max wins; equal root scores: larger cell first, in oracle and kernel alike)."""
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    if grid:
+        cfg = cfg.with_(outsize=grid, insize=(grid[0] * 16, grid[1] * 16))
+    g = O.Geometry.of(cfg)
+    head16 = torch.from_numpy(synth.make_head(g, dist, seed=77, B=B)).to(dtype)
+    up = head16.float().numpy()
+    ref = c_oracle.parse_batch(up, g, n_threads=8)
+    parser = PoseParser(cfg)
+    dev = head16.cuda()
+    want_amax = np.stack([c_oracle.limb_argmax(img, g) for img in up]).astype(np.uint16)
+    assert np.array_equal(parser.limb_argmax(dev).cpu().numpy(), want_amax)
+    assert_packed_equals_oracle(parser.parse(dev).numpy(), ref, B)
+    assert_packed_equals_oracle(parser.parse(dev, input_complete=True).numpy(), ref, B)
+    cell, score, box, count = parser.decode_candidates(dev)
+    for b in range(B):
+        n = int(count[b, 0])
+        assert n == ref["counts"][b, 0] and np.array_equal(cell[b, 0, :n].cpu().numpy(), ref["cand_cell"][b, :n])
+    host = parser.parse_host(head16.pin_memory())
+    assert_packed_equals_oracle(host.numpy(), ref, B)
+
+
 TUNE_DEFAULTS = dict(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=4, argmax_threads=320,
                      argmax_ctas_per_sm=1, argmax_split=-1, argmax_dynamic=1, argmax_tail_opt=0)
 
@@ -557,7 +587,7 @@ def test_bad_arguments_raise():
     with pytest.raises(ValueError):
         p.parse(torch.zeros(1, cfg.C + 1, cfg.H, cfg.W, device="cuda"))
     with pytest.raises(ValueError):
-        p.parse(torch.zeros(1, cfg.C, cfg.H, cfg.W, device="cuda", dtype=torch.float16))
+        p.parse(torch.zeros(1, cfg.C, cfg.H, cfg.W, device="cuda", dtype=torch.float64))
     shape = p.c.shape(1)
     hs = _lib.PPNHumans(0, 0, 0, 0, 0, 4)
     rc = _lib.lib().ppn_parse(None, C.byref(shape), C.byref(p.c.params), C.byref(hs), None, 0, None)
