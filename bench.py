@@ -195,7 +195,9 @@ def run_ours(args, rank, world, local_rank):
     gatherer = PoseGatherer(parser, B, cap_entries, group_steps=args.gather_every) if world > 1 else None
 
     # distinct input batches, rotated so that no step finds its input in the 126 MB L2
-    batch_bytes = B * cfg.bytes_per_image
+    head_dtype = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[args.head_dtype]
+    elem = 4 if args.head_dtype == "f32" else 2
+    batch_bytes = B * cfg.C * cfg.HW * elem
     n_buf = max(2, min(6, -(-(1 << 30) // batch_bytes)))
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     bufs = []
@@ -204,7 +206,8 @@ def run_ours(args, rank, world, local_rank):
         if DIST[args.config] == "D":
             t[:, :2 * cfg.K] = 0.4 + 0.6 * t[:, :2 * cfg.K]
             t[:, 4 * cfg.K:6 * cfg.K] *= 0.08
-        bufs.append(t)
+        bufs.append(t.to(head_dtype))               # a 16-bit head: same values rounded once, widened exactly by the kernels
+        del t
     outs = [parser.alloc_output(B) for _ in range(2)]
 
     released = [None, None]
@@ -326,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
         assert int(mine["count"].sum()) == int(counts.sum()), "gathered humans differ from the local result"
 
     # ---- end to end through the public host-buffer call: H2D + kernels + D2H every step ----
-    host_in = torch.empty(B, cfg.C, cfg.H, cfg.W, dtype=torch.float32, pin_memory=True)
+    host_in = torch.empty(B, cfg.C, cfg.H, cfg.W, dtype=head_dtype, pin_memory=True)
     host_in.copy_(bufs[0])
     host_out = parser.alloc_output(B, device="cpu", pin=True)
     Ke = max(1, min(K, args.e2e_steps))
@@ -354,12 +357,12 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    limb_bytes = B * cfg.E * cfg.S * cfg.HW * 4 + B * cfg.E * cfg.HW * 2       # read once + uint16 map written
+    limb_bytes = B * cfg.E * cfg.S * cfg.HW * elem + B * cfg.E * cfg.HW * 2    # read once + uint16 map written
     traffic = None                                   # DRAM bytes per launch from the committed ncu capture
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         rec = json.load(open(tpath)).get(args.config)
-        if rec and rec.get("images") == B:
+        if rec and rec.get("images") == B and args.head_dtype == "f32":
             traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
     k3_ms = stage_ms["limb_argmax"] / max(n_prof, 1)
     achieved = limb_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
@@ -372,8 +375,8 @@ def run_ours(args, rank, world, local_rank):
                                       "decode_nms": stage_ms["nms"] / max(n_prof, 1),
                                       "tree_parse": stage_ms["tree_parse"] / max(n_prof, 1)},
                 "serial_ms_per_step": profiled_ms_per_step,
-                "pipeline_gbs": B * cfg.bytes_per_image / (elapsed_ms / K * 1e-3) / 1e9,
-                "pipeline_frac": B * cfg.bytes_per_image / (elapsed_ms / K * 1e-3) / 1e9 / peak}
+                "pipeline_gbs": batch_bytes / (elapsed_ms / K * 1e-3) / 1e9,
+                "pipeline_frac": batch_bytes / (elapsed_ms / K * 1e-3) / 1e9 / peak}
 
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -381,7 +384,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD[args.config], "preset": args.config, "images_per_gpu_per_step": B,
                    "K": cfg.K, "E": cfg.E, "grid": [cfg.H, cfg.W], "window": [cfg.sH, cfg.sW],
-                   "bytes_per_image": cfg.bytes_per_image, "input_distribution": DIST[args.config],
+                   "bytes_per_image": cfg.C * cfg.HW * elem, "head_dtype": args.head_dtype,
+                   "input_distribution": DIST[args.config],
                    "l2": f"{n_buf} distinct input batches of {batch_bytes / 1e6:.0f} MB rotated (each larger than L2)",
                    "humans_per_image": humans_per_image, "extra_warmup_steps": extra,
                    "host_issue_ms_per_step": host_issue_ms, "cuda_graph": bool(graph is not None),
@@ -447,6 +451,8 @@ def main():
     ap.add_argument("--settle-s", type=float, default=0.4)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16", "bf16"],
+                    help="element type of the head tensor (the reference's is f32; the arithmetic is fp32 either way)")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the timed steps from a CUDA graph (1 GPU)")
     ap.add_argument("--no-step-overlap", action="store_true",
                     help="do not pass PPN_FLAG_INPUT_COMPLETE (each step's kernels wait for the previous step's)")
