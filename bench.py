@@ -371,9 +371,12 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_bytes_per_launch": limb_bytes, "avg_launch_ms": k3_ms,
                 "timing": f"CUDA events around each kernel on its stream, {n_prof} steps run right after the timed region "
                           "(events forbid the overlapped launch chain, so kernels run back to back in this pass)",
-                "stage_ms_per_step": {"limb_argmax": stage_ms["limb_argmax"] / max(n_prof, 1),
-                                      "decode_nms": stage_ms["nms"] / max(n_prof, 1),
-                                      "tree_parse": stage_ms["tree_parse"] / max(n_prof, 1)},
+                "stage_ms_per_step": ({"limb_argmax": stage_ms["limb_argmax"] / max(n_prof, 1),
+                                       "parse_fused": stage_ms["tree_parse"] / max(n_prof, 1)}
+                                      if parser.launches_per_parse(B) == 2 else
+                                      {"limb_argmax": stage_ms["limb_argmax"] / max(n_prof, 1),
+                                       "decode_nms": stage_ms["nms"] / max(n_prof, 1),
+                                       "tree_parse": stage_ms["tree_parse"] / max(n_prof, 1)}),
                 "serial_ms_per_step": profiled_ms_per_step,
                 "pipeline_gbs": batch_bytes / (elapsed_ms / K * 1e-3) / 1e9,
                 "pipeline_frac": batch_bytes / (elapsed_ms / K * 1e-3) / 1e9 / peak}

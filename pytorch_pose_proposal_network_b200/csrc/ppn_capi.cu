@@ -195,9 +195,12 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.split")) t.argmax_split = value;
     else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value != 0;
+    else if (!std::strcmp(key, "argmax16.threads")) t.argmax16_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
+    else if (!std::strcmp(key, "argmax16.stage_bytes")) t.argmax16_stage_bytes = value < 1024 ? 1024 : value;
     else if (!std::strcmp(key, "argmax.dynamic")) t.argmax_dynamic = value != 0;
     else if (!std::strcmp(key, "parse.stage_all")) t.parse_stage_all = value;
     else if (!std::strcmp(key, "parse.chain_calls")) t.parse_chain_calls = value != 0;
+    else if (!std::strcmp(key, "parse.fused")) t.parse_fused = value < 0 ? -1 : (value != 0);
     else if (!std::strcmp(key, "parse.threads")) t.parse_threads = value;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else return PPN_E_BADARG;
@@ -215,9 +218,12 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.split")) *value = t.argmax_split;
     else if (!std::strcmp(key, "parse.overlap")) *value = t.parse_overlap;
     else if (!std::strcmp(key, "argmax.tail_opt")) *value = t.argmax_tail_opt;
+    else if (!std::strcmp(key, "argmax16.threads")) *value = t.argmax16_threads;
+    else if (!std::strcmp(key, "argmax16.stage_bytes")) *value = t.argmax16_stage_bytes;
     else if (!std::strcmp(key, "argmax.dynamic")) *value = t.argmax_dynamic;
     else if (!std::strcmp(key, "parse.stage_all")) *value = t.parse_stage_all;
     else if (!std::strcmp(key, "parse.chain_calls")) *value = t.parse_chain_calls;
+    else if (!std::strcmp(key, "parse.fused")) *value = t.parse_fused;
     else if (!std::strcmp(key, "parse.threads")) *value = t.parse_threads;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
     else return PPN_E_BADARG;
@@ -235,7 +241,13 @@ int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* 
 
 int ppn_parse_launches(const PPNShape* shape, const PPNParams* params) {
     if (check_shape(shape) || check_params(shape, params)) return 0;
-    return shape->B > 0 ? 3 : 0;
+    if (shape->B <= 0) return 0;
+    const ppn::Geom g = make_geom(shape);
+    size_t ring_cap = 0;
+    const bool P1 = params->n_nms_parts == 1 && g_tuning.parse_overlap != 1;
+    const bool fused = P1 && (g_tuning.parse_fused < 0 ? ppn::parse_fused_coresident(g, g_tuning.parse_stage_all, g_tuning, &ring_cap)
+                                                       : (g_tuning.parse_fused != 0 && ppn::parse_fused_supported(g, g_tuning.parse_stage_all)));
+    return fused ? 2 : 3;
 }
 
 int ppn_limb_argmax(const void* head, const PPNShape* shape, uint16_t* amax, void* stream) {
@@ -342,6 +354,47 @@ int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params, 
     //      so that the stage times are clean).
     cudaEvent_t* ev = profile_slot();
     const int mode = ev ? 0 : g_tuning.parse_overlap;
+    // Default: TWO kernels.  The limb arg-max (K3) and the fused decode + NMS + tree parse (K124), which
+    // is a programmatic dependent of K3: it becomes resident beside it, does everything that does not
+    // need the arg-max map (candidates, NMS, delta) while K3 streams, then waits for K3 and walks.
+    //  * default flags: K3 waits for whatever precedes it in the stream (it may be producing `head`),
+    //    K124 triggers after its wait — the next call's K3 only hides its launch latency;
+    //  * PPN_FLAG_INPUT_COMPLETE: K3 starts at once; K124 triggers EARLY (after seeing the previous
+    //    call's K124 complete), so the next call's K3 is launched while this call's K3 still runs and
+    //    takes over its SMs as they free up — the limb stream never pauses between calls.  K3 waits at
+    //    its end for the previous K124, K124 waits for its K3: calls complete in order.
+    // Needs n_nms_parts == 1 (the reference's case) and a grid of at most 1024 cells; otherwise, or with
+    // ppn_tune("parse.fused", 0), the three-kernel chain below runs.
+    size_t ring_cap = 0;
+    const bool fits_beside = P == 1 && ppn::parse_fused_coresident(g, g_tuning.parse_stage_all, g_tuning, &ring_cap);
+    const bool fused = P == 1 && mode != 1 && (g_tuning.parse_fused < 0 ? fits_beside : (g_tuning.parse_fused != 0 &&
+                       ppn::parse_fused_supported(g, g_tuning.parse_stage_all)));
+    if (fused) {
+        using namespace ppn;
+        Tuning tuning = g_tuning;
+        if (fits_beside) tuning.argmax_smem_cap = (int)ring_cap;      // leave room for every parse CTA on the SM
+        const bool overlap_calls = (params->flags & PPN_FLAG_INPUT_COMPLETE) != 0;
+        const bool chain = mode == 2 && g_tuning.parse_chain_calls != 0;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if ((e = cudaStreamIsCapturing(st, &cap)) != cudaSuccess) return (int)e;
+        const bool capturing = cap != cudaStreamCaptureStatusNone;
+        // an overlapped K3 may only start beside a fused parse that publishes; after anything else of
+        // ours it starts fully ordered (no launch attribute), which also restarts the chain cleanly
+        const bool k3_attr = chain && (!overlap_calls || capturing || chain_clean(st));
+        bool chained = false;
+        if (ev) cudaEventRecord(ev[0], st);
+        if ((e = launch_limb_argmax(head, amax, g, tuning, st, k3_attr, &chained,
+                                    mode != 2 ? 0 : (overlap_calls ? (PDL_TRIGGER | PDL_WAIT_END) : (PDL_WAIT_START | PDL_TRIGGER)))) != cudaSuccess) return (int)e;
+        if (ev) { cudaEventRecord(ev[1], st); for (int q = 2; q < 7; ++q) cudaEventRecord(ev[q], st); }
+        (void)chained;
+        const bool k124_attr = mode == 2;      // a programmatic dependent of K3 (implicit trigger if K3 is a fallback kernel)
+        if ((e = launch_parse_fused(head, g, ch, params->det_thresh, params->nms_thresh, params->min_num_keypoints, amax,
+                                    out->count, out->root_cell, out->part_cell, out->part_score, out->part_box, out->R, st,
+                                    k124_attr, (overlap_calls && chain && !capturing) ? 2 : 1, g_tuning.parse_stage_all)) != cudaSuccess) return (int)e;
+        if (ev) cudaEventRecord(ev[7], st);
+        return PPN_OK;
+    }
+    ppn::chain_break(st);
     if (mode == 2) {
         using namespace ppn;
         bool chained = false;

@@ -52,7 +52,8 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
         }
         fence_mbar_init();
     }
-    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the tree-parse kernel may start its prologue now
+    if (pdl & PDL_WAIT_START) pdl_wait();                // default chain: `head` may come from the kernel before us
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the parse kernel may start its prologue now
     __syncthreads();
 
     if (tid >= n_cons) {
@@ -189,7 +190,8 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         }
         fence_mbar_init();
     }
-    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the tree-parse kernel may start its prologue now
+    if (pdl & PDL_WAIT_START) pdl_wait();                // default chain: `head` may come from the kernel before us
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the parse kernel may start its prologue now
     __syncthreads();
 
     if (tid >= n_cons) {
@@ -285,25 +287,45 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();    // see limb_argmax_tma_kernel
 }
 
-// The same ring and thread mapping for a 16-bit head (fp16 / bf16): rows are HW * 2 bytes, a thread
-// owns EIGHT columns (one 16-byte vector) and widens each value to fp32 before the comparison, so
-// the answer is the fp32 kernel's on `head.float()`.  p.CV counts 16-byte vectors per row (HW / 8).
+// The same ring and thread mapping for a 16-bit head (fp16 / bf16): rows are HW * 2 bytes and a
+// thread owns EIGHT columns (one 16-byte vector).  Widening to fp32 is exact and monotone, so the
+// values are compared in their packed 16-bit form, two columns per instruction: `v > best` as a
+// per-half mask (HSET2), the running index (16 bits per column, S < 65536) updated through the mask
+// (one LOP3), the running maximum by a NaN-propagating packed max (HMNMX2) — three instructions
+// per two elements where the widened scalar form needed ten.  Signed zeros compare equal in both
+// forms (first one wins).  NaN: numpy's arg-max returns the FIRST NaN of a column; here a NaN makes
+// the running maximum NaN for good (and freezes the index), which is detected once per matrix and
+// repaired by `first_nan16` — a plain scan of that column for its first NaN.  p.CV counts 16-byte
+// vectors per row (HW / 8).
+template <typename T16> struct Packed16;
+template <> struct Packed16<__half> {
+    using V2 = __half2;
+    static constexpr uint32_t kNegInf2 = 0xFC00FC00u;
+    static __device__ __forceinline__ bool is_nan(uint32_t h) { return (h & 0x7FFFu) > 0x7C00u; }
+};
+template <> struct Packed16<__nv_bfloat16> {
+    using V2 = __nv_bfloat162;
+    static constexpr uint32_t kNegInf2 = 0xFF80FF80u;
+    static __device__ __forceinline__ bool is_nan(uint32_t h) { return (h & 0x7FFFu) > 0x7F80u; }
+};
+
 template <typename T16>
-__device__ __forceinline__ void widen8(const uint4 raw, float* v);
-template <>
-__device__ __forceinline__ void widen8<__half>(const uint4 raw, float* v) {
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+__device__ __forceinline__ void argmax_step2(uint32_t& best, uint32_t& idx, uint32_t v, uint32_t a2) {
+    using V2 = typename Packed16<T16>::V2;
+    const V2 bv = *reinterpret_cast<const V2*>(&best), vv = *reinterpret_cast<const V2*>(&v);
+    const uint32_t m = __hgt2_mask(vv, bv);                 // 0xFFFF per half where v > best (false on NaN)
+    idx = (idx & ~m) | (a2 & m);
+    const V2 nb = __hmax2_nan(bv, vv);
+    best = *reinterpret_cast<const uint32_t*>(&nb);
 }
-template <>
-__device__ __forceinline__ void widen8<__nv_bfloat16>(const uint4 raw, float* v) {
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {                     // bf16 -> fp32 is a 16-bit shift
-        v[2 * q] = __uint_as_float(w[q] << 16);
-        v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-    }
+
+// index of the first NaN in column `col` of one S x HW matrix (the column is known to hold one)
+template <typename T16>
+__device__ __noinline__ int first_nan16(const T16* __restrict__ mat, int S, int HW, int col) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(mat) + col;
+    for (int a = 0; a < S; ++a)
+        if (Packed16<T16>::is_nan(__ldg(p + (size_t)a * HW))) return a;
+    return 0;
 }
 
 template <typename T16>
@@ -330,6 +352,7 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
         }
         fence_mbar_init();
     }
+    if (pdl & PDL_WAIT_START) pdl_wait();
     if (pdl & PDL_TRIGGER) pdl_launch_dependents();
     __syncthreads();
 
@@ -382,34 +405,35 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
         if (item < 0) break;
         const int m = item * M + j;
         const bool active = tid < p.threads && m < n_mats;
-        float best[8];
-        int idx[8];
+        uint32_t best[4], idx[4];                                   // two columns per register
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; idx[q] = 0; }
+        for (int q = 0; q < 4; ++q) { best[q] = Packed16<T16>::kNegInf2; idx[q] = 0u; }
         for (int c = 0; c < p.chunks; ++c) {
             if (c > 0) mbar_wait(&full[stage], phase);
             if (active) {
                 const int rows = min(p.rows, g.S - c * p.rows);
                 const uint4* col = reinterpret_cast<const uint4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
-                int a = c * p.rows;
+                uint32_t a2 = (uint32_t)(c * p.rows) * 0x00010001u;       // the row index in both halves
                 int r = 0;
 #pragma unroll 1
-                for (; r + 1 < rows; r += 2, a += 2) {
+                for (; r + 3 < rows; r += 4, a2 += 0x00040004u) {
                     const uint4 r0 = col[(size_t)r * p.CV];
                     const uint4 r1 = col[(size_t)(r + 1) * p.CV];
-                    float v0[8], v1[8];
-                    widen8<T16>(r0, v0);
-                    widen8<T16>(r1, v1);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) argmax_step(best[q], idx[q], v0[q], a);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) argmax_step(best[q], idx[q], v1[q], a + 1);
+                    const uint4 r2 = col[(size_t)(r + 2) * p.CV];
+                    const uint4 r3 = col[(size_t)(r + 3) * p.CV];
+                    argmax_step2<T16>(best[0], idx[0], r0.x, a2); argmax_step2<T16>(best[1], idx[1], r0.y, a2);
+                    argmax_step2<T16>(best[2], idx[2], r0.z, a2); argmax_step2<T16>(best[3], idx[3], r0.w, a2);
+                    argmax_step2<T16>(best[0], idx[0], r1.x, a2 + 0x00010001u); argmax_step2<T16>(best[1], idx[1], r1.y, a2 + 0x00010001u);
+                    argmax_step2<T16>(best[2], idx[2], r1.z, a2 + 0x00010001u); argmax_step2<T16>(best[3], idx[3], r1.w, a2 + 0x00010001u);
+                    argmax_step2<T16>(best[0], idx[0], r2.x, a2 + 0x00020002u); argmax_step2<T16>(best[1], idx[1], r2.y, a2 + 0x00020002u);
+                    argmax_step2<T16>(best[2], idx[2], r2.z, a2 + 0x00020002u); argmax_step2<T16>(best[3], idx[3], r2.w, a2 + 0x00020002u);
+                    argmax_step2<T16>(best[0], idx[0], r3.x, a2 + 0x00030003u); argmax_step2<T16>(best[1], idx[1], r3.y, a2 + 0x00030003u);
+                    argmax_step2<T16>(best[2], idx[2], r3.z, a2 + 0x00030003u); argmax_step2<T16>(best[3], idx[3], r3.w, a2 + 0x00030003u);
                 }
-                for (; r < rows; ++r, ++a) {
-                    float v[8];
-                    widen8<T16>(col[(size_t)r * p.CV], v);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) argmax_step(best[q], idx[q], v[q], a);
+                for (; r < rows; ++r, a2 += 0x00010001u) {
+                    const uint4 v = col[(size_t)r * p.CV];
+                    argmax_step2<T16>(best[0], idx[0], v.x, a2); argmax_step2<T16>(best[1], idx[1], v.y, a2);
+                    argmax_step2<T16>(best[2], idx[2], v.z, a2); argmax_step2<T16>(best[3], idx[3], v.w, a2);
                 }
             }
             __syncwarp();
@@ -417,10 +441,22 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         if (active) {
-            uint4 o;
-            o.x = (uint32_t)idx[0] | ((uint32_t)idx[1] << 16); o.y = (uint32_t)idx[2] | ((uint32_t)idx[3] << 16);
-            o.z = (uint32_t)idx[4] | ((uint32_t)idx[5] << 16); o.w = (uint32_t)idx[6] | ((uint32_t)idx[7] << 16);
-            *reinterpret_cast<uint4*>(amax + (size_t)m * g.HW + 8 * cv) = o;
+            bool any_nan = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                any_nan |= Packed16<T16>::is_nan(best[q] & 0xFFFFu) || Packed16<T16>::is_nan(best[q] >> 16);
+            if (any_nan) {                                               // rare: repair the columns that hold a NaN
+                const int b = m / g.E, ei = m - b * g.E;
+                const T16* mat = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (Packed16<T16>::is_nan(best[q] & 0xFFFFu))
+                        idx[q] = (idx[q] & 0xFFFF0000u) | (uint32_t)first_nan16<T16>(mat, g.S, g.HW, 8 * cv + 2 * q);
+                    if (Packed16<T16>::is_nan(best[q] >> 16))
+                        idx[q] = (idx[q] & 0x0000FFFFu) | ((uint32_t)first_nan16<T16>(mat, g.S, g.HW, 8 * cv + 2 * q + 1) << 16);
+                }
+            }
+            *reinterpret_cast<uint4*>(amax + (size_t)m * g.HW + 8 * cv) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
         }
     }
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
@@ -1084,6 +1120,298 @@ tree_parse_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float thr,
 }
 
 // =========================================================================================
+// K124 — decode + NMS + tree parse in ONE kernel, one CTA per image (the whole-path call's default)
+// =========================================================================================
+// Everything the parse needs besides the arg-max map — the root candidates, their NMS, delta of
+// every (part, cell) — does not depend on the limb arg-max, so it is this kernel's PROLOGUE: the
+// kernel is launched as a programmatic dependent of the arg-max kernel, becomes resident beside it
+// at once, decodes and suppresses in shared memory while the arg-max streams the limb block, and
+// only then executes griddepcontrol.wait.  What is left after the wait is the walk and the
+// write-out.  Per call that is two launches (K3, K124) and no root lists in HBM.
+//
+// Consecutive overlapped calls (PPN_FLAG_INPUT_COMPLETE): K124(i) lets the NEXT call's arg-max
+// K3(i+1) be launched as soon as K124(i) is resident — long before K3(i) ends — so K3(i+1)'s CTAs
+// take over the SMs one by one as K3(i)'s CTAs exit and the limb stream never pauses between calls.
+// Two things make that safe:
+//  * K3(i+1) writes the arg-max buffer and draws from the ticket counters that call i-1 used.
+//    K124(i) therefore triggers only after it has SEEN K124(i-1) complete: the last CTA of every
+//    K124 publishes its sequence number (`sync[0]`, monotonic), and K124(i) polls it before
+//    griddepcontrol.launch_dependents.  K124(i-1) complete implies K3(i-1) complete (it waited for it).
+//    The poll cannot deadlock: K124(i) is only launched once every CTA of K3(i) has started, K3(i)
+//    only once every CTA of K124(i-1) was resident, and K124(i-1) waits only for K3(i-1), all of
+//    whose CTAs had started before K124(i-1) was launched.
+//  * completion stays transitive: K3(i+1) waits at its END for K124(i) (its programmatic primary),
+//    K124(i+1) waits for K3(i+1) — calls complete in order.
+// Sequence numbers are host state and would be frozen by stream capture; under capture (and without
+// the flag) the kernel triggers only AFTER its wait, which bounds the overlap to two calls without
+// any flag (K3(i+1) launched => K3(i) complete => K124(i-1) complete).
+enum : int {
+    FUSED_GUARD = 8,           // poll sync[0] >= seq before the early trigger
+    FUSED_TRIGGER_EARLY = 16,  // launch_dependents before the wait (after the guard)
+    FUSED_PUBLISH = 32,        // last CTA publishes seq + 1
+};
+
+struct FusedSmem { uint32_t delta, root, dyx, uni, amax, slot, pos, total; };
+
+__host__ __device__ inline FusedSmem fused_layout(const Geom& g, bool staged) {
+    FusedSmem l;
+    uint32_t off = 0;
+    l.delta = off; off += staged ? (uint32_t)g.K * g.HW * 4u : 0u;
+    l.root = off;  off += (uint32_t)g.HW * 4u;
+    l.dyx = off;   off += g.S <= 2048 ? (uint32_t)g.S * 4u : 0u;
+    off = (off + 15u) & ~15u;
+    l.uni = off;                                               // NMS scratch, later reused by the walk
+    const uint32_t Wd = ((uint32_t)g.HW + 31u) / 32u;
+    const uint32_t nms = (uint32_t)g.HW * 16u + (((uint32_t)g.HW + 3u) & ~3u) * 4u +
+                         (uint32_t)g.HW * (16u + 8u + 4u + 4u + 4u) + (32u * Wd * (Wd + 1u) / 2u) * 4u;
+    l.amax = l.uni;
+    l.slot = l.amax + ((((uint32_t)g.E * g.HW * 2u) + 15u) & ~15u);
+    l.pos = l.slot + (uint32_t)g.HW * 4u;
+    const uint32_t walk = (l.pos - l.uni) + ((((uint32_t)g.HW * g.K * 2u) + 15u) & ~15u);
+    l.total = l.uni + (nms > walk ? nms : walk);
+    return l;
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool kStaged, typename HT>
+__global__ void __launch_bounds__(512, 3)
+parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det_thr, float nms_thr, int min_kp,
+                   const uint16_t* __restrict__ amax, int32_t* __restrict__ h_count, int32_t* __restrict__ h_root,
+                   int32_t* __restrict__ h_cell, float* __restrict__ h_score, float4* __restrict__ h_box, int R,
+                   int pdl, int* __restrict__ sync, int seq) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const FusedSmem L = fused_layout(g, kStaged);
+    float* s_delta = reinterpret_cast<float*>(smem + L.delta);                  // [K*HW] resp*conf (kStaged)
+    int32_t* s_root = reinterpret_cast<int32_t*>(smem + L.root);                // [HW] surviving root cells
+    int32_t* s_dyx = reinterpret_cast<int32_t*>(smem + L.dyx);                  // [S]
+    float4* ubox = reinterpret_cast<float4*>(smem + L.uni);                     // NMS phase: candidate boxes,
+    int32_t* ucell = reinterpret_cast<int32_t*>(ubox + g.HW);                   //   their cells,
+    const NmsSmem s = nms_carve(reinterpret_cast<unsigned char*>(ucell + ((g.HW + 3) & ~3)), g.HW);   // sort + mask
+    uint16_t* s_amax = reinterpret_cast<uint16_t*>(smem + L.amax);              // walk phase (same bytes): [E*HW]
+    int32_t* s_slot = reinterpret_cast<int32_t*>(smem + L.slot);                // [HW]
+    int16_t* s_pos = reinterpret_cast<int16_t*>(smem + L.pos);                  // [HW][K]
+    __shared__ int warp_tot[16];
+    __shared__ int base_s;
+    __shared__ int n_keep_s;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int KHW = g.K * g.HW;
+    const HT* img = head + (size_t)b * g.img_stride;
+    const bool use_tab = g.S <= kMaxDyxTable;
+
+    // ---- let the next call's arg-max be launched (see the header comment): it only queues behind
+    //      this call's arg-max, so the earlier the better ---------------------------------------------
+    if (pdl & FUSED_GUARD) {
+        if (tid == 0) while (ld_acquire(sync) < seq) __nanosleep(200);
+        __syncthreads();
+    }
+    if (pdl & FUSED_TRIGGER_EARLY) pdl_launch_dependents();
+
+    // ---- prologue 1: root candidates of part 0, compacted into shared memory (datatest.py:80-92) ----
+    if (tid == 0) { base_s = 0; n_keep_s = 0; }
+    for (int i = tid; i < g.HW; i += T) s.rank[i] = 0;
+    if (use_tab)
+        for (int a = tid; a < g.S; a += T) {
+            const int dy = a / g.sW, dx = a - dy * g.sW;
+            s_dyx[a] = ((dy - g.off_h) << 16) | ((dx - g.off_w) & 0xffff);
+        }
+    __syncthreads();
+    for (int c0 = 0; c0 < g.HW; c0 += T) {
+        const int c = c0 + tid;
+        float d = 0.0f;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool hit = false;
+        if (c < g.HW) {
+            d = delta_at(img, g, 0, c);
+            bx = box_at(img, g, 0, c);
+            hit = d > det_thr;                               // strict, datatest.py:89
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s, total = 0;
+        for (int wi = 0; wi < (T >> 5); ++wi) {
+            const int t = warp_tot[wi];
+            if (wi < warp) off += t;
+            total += t;
+        }
+        if (hit) {
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            ucell[slot] = c;
+            ubox[slot] = bx;
+            s.key[slot] = score_key(d, slot);                // ties: larger candidate index (= larger cell) first
+        }
+        __syncthreads();
+        if (tid == 0) base_s += total;
+        __syncthreads();
+    }
+    // ---- prologue 2: delta of every (part, cell), one coalesced pass (rt_test.py:130) -----------------
+    if (kStaged)
+        for (int i = tid; i < KHW; i += T) s_delta[i] = __fmul_rn(ldf(img + i), ldf(img + KHW + i));
+    // ---- prologue 3: NMS of the candidates, survivors' cells in visiting order (datatest.py:93-95) ----
+    const int n_cand = base_s;
+    if (n_cand > 0) {
+        const int m = nms_core(s, ubox, n_cand, nms_thr, 0, s_root, ucell);
+        if (tid == 0) n_keep_s = m;
+    }
+    __syncthreads();                                          // NMS scratch is dead from here; n_keep_s, s_root visible
+    const int n_keep = n_keep_s;
+    // for a crowded image have the L2 stream the x/y/w/h planes in now (one contiguous read): the
+    // write-out's scattered gathers are then L2 hits
+    if (tid == 0 && n_keep * 8 >= g.HW * 3 && ((size_t)KHW * sizeof(HT)) % 16 == 0 && (g.img_stride * sizeof(HT)) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(head) & 15) == 0)
+        bulk_prefetch_l2(img + (size_t)2 * KHW, (uint32_t)4 * KHW * (uint32_t)sizeof(HT));
+    for (int i = tid; i < n_keep * g.K; i += T) s_pos[i] = -1;
+    __syncthreads();
+    for (int r = tid; r < n_keep; r += T) s_pos[r * g.K] = (int16_t)s_root[r];
+
+    // ---- from here on we read what the arg-max kernel wrote -------------------------------------------
+    if (pdl & PDL_WAIT_START) pdl_wait();
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();
+    if (n_keep > 0) {
+        const uint16_t* am = amax + (size_t)b * g.E * g.HW;    // L2 loads: the map was written while we were resident
+        const int n16 = (g.E * g.HW) >> 3;
+        if ((reinterpret_cast<uintptr_t>(am) & 15) == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(am);
+            uint4* dst = reinterpret_cast<uint4*>(s_amax);
+            for (int i = tid; i < n16; i += T) dst[i] = __ldcg(src + i);
+            for (int i = (n16 << 3) + tid; i < g.E * g.HW; i += T) s_amax[i] = __ldcg(am + i);
+        } else {
+            for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = __ldcg(am + i);
+        }
+    }
+    __syncthreads();
+
+    if (n_keep > 0) {
+        const HT* resp = img;
+        const HT* conf = img + KHW;
+        // ---- walk: one thread per (chain, root) when the track orders are a tree (datatest.py:103-127) ----
+        const int n_pad = (n_keep + 31) & ~31;
+        const int n_par = ch.parallel_ok ? ch.n_chains : 1;
+        for (int item = tid; item < n_par * n_pad; item += T) {
+            const int cidx = item / n_pad, r = item - cidx * n_pad;
+            if (r >= n_keep) continue;
+            int16_t* my_pos = s_pos + r * g.K;
+            const int c_lo = ch.parallel_ok ? cidx : 0, c_hi = ch.parallel_ok ? cidx + 1 : ch.n_chains;
+            for (int cc = c_lo; cc < c_hi; ++cc) {
+                const int root = s_root[r];
+                int ih = fast_div(root, g.magic_W), iw = root - ih * g.W;
+                for (int q = ch.off[cc]; q < ch.off[cc + 1]; ++q) {
+                    const int ei = ch.limb[q], t = ch.part[q];
+                    const int a = s_amax[ei * g.HW + ih * g.W + iw];
+                    int jh, jw;
+                    if (use_tab) {
+                        const int d = s_dyx[a];
+                        jh = ih + (d >> 16);
+                        jw = iw + (int)(int16_t)(d & 0xffff);
+                    } else {
+                        const int dy = a / g.sW, dx = a - dy * g.sW;
+                        jh = ih + dy - g.off_h;
+                        jw = iw + dx - g.off_w;
+                    }
+                    if (jh < 0 || jw < 0 || jh >= g.H || jw >= g.W) break;                     // datatest.py:118
+                    const int j = jh * g.W + jw, at = t * g.HW + j;
+                    const float dl = kStaged ? s_delta[at] : __fmul_rn(ldf(resp + at), ldf(conf + at));
+                    if (dl < det_thr) break;                                                   // datatest.py:121
+                    my_pos[t] = (int16_t)j;
+                    ih = jh;
+                    iw = jw;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) base_s = 0;
+        __syncthreads();
+        // ---- humans with enough parts take consecutive output slots, in root order (datatest.py:129) ----
+        for (int r0 = 0; r0 < n_keep; r0 += T) {
+            const int r = r0 + tid;
+            bool valid = false;
+            if (r < n_keep) {
+                int present = 0;
+                for (int t = 1; t < g.K; ++t) present += (s_pos[r * g.K + t] >= 0);
+                valid = min_kp <= present;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) warp_tot[warp] = __popc(bal);
+            __syncthreads();
+            int off = base_s, total = 0;
+            for (int wi = 0; wi < (T >> 5); ++wi) {
+                const int v = warp_tot[wi];
+                if (wi < warp) off += v;
+                total += v;
+            }
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            if (r < n_keep) s_slot[r] = (valid && slot < R) ? slot : -1;
+            __syncthreads();
+            if (tid == 0) base_s += total;
+        }
+        __syncthreads();
+        // ---- write-out: one (human, part) pair per thread and step, two steps in flight --------------
+        const int n_pairs = n_keep * g.K;
+        for (int p0 = tid; p0 < n_pairs; p0 += 2 * T) {
+            int cc[2], tt[2], ss[2];
+            float xs[2], ys[2], ws[2], hs[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int pair = p0 + u * T;
+                cc[u] = -2;                                       // -2: nothing to write
+                if (pair < n_pairs) {
+                    const int r = fast_div(pair, g.magic_K), t = pair - r * g.K;
+                    const int sl = s_slot[r];
+                    if (sl >= 0) {
+                        cc[u] = s_pos[pair];
+                        tt[u] = t;
+                        ss[u] = sl;
+                        if (cc[u] >= 0) {
+                            const int at = t * g.HW + cc[u];
+                            xs[u] = ldf(img + (size_t)2 * KHW + at); ys[u] = ldf(img + (size_t)3 * KHW + at);
+                            ws[u] = ldf(img + (size_t)4 * KHW + at); hs[u] = ldf(img + (size_t)5 * KHW + at);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (cc[u] == -2) continue;
+                const int c = cc[u];
+                float score = 0.0f;
+                float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c >= 0) {
+                    const int at = tt[u] * g.HW + c;
+                    const int h = fast_div(c, g.magic_W), w = c - h * g.W;
+                    score = kStaged ? s_delta[at] : __fmul_rn(ldf(resp + at), ldf(conf + at));
+                    box = box_from(xs[u], ys[u], ws[u], hs[u], h, w, g);
+                }
+                const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
+                if (tt[u] == 0) h_root[human] = c;
+                h_cell[o] = c;
+                h_score[o] = score;
+                h_box[o] = box;
+            }
+        }
+    }
+    if (tid == 0) h_count[b] = n_keep > 0 ? base_s : 0;
+    // ---- the last CTA publishes this call's sequence number ------------------------------------------
+    if (pdl & FUSED_PUBLISH) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(sync + 1, 1) == (int)gridDim.x - 1) {
+                sync[1] = 0;
+                __threadfence();
+                atomicMax(sync, seq + 1);
+            }
+        }
+    }
+}
+
+// =========================================================================================
 // part centres — what the consumers right after the path read off each box
 // =========================================================================================
 // datatest.py:200-211 (drawing) and :316-317 (AP-evaluation records) both reduce a part's box to
@@ -1206,14 +1534,19 @@ pack_entries_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
 // =========================================================================================
 // launchers
 // =========================================================================================
-// Work counters of the ring kernels: {next ticket, finished CTAs} per stream, zero between launches
-// (the last CTA of a launch resets its pair).  Kernels on one stream never overlap, kernels on
-// different streams get different pairs.  The only memory the library ever allocates: 512 bytes
-// per device, on the first launch (so make the first call outside stream capture).
+// Per-stream device words (the only memory the library ever allocates: 2 KB per device, on the
+// first launch — so make the first call outside stream capture):
+//   [0..3] two {next ticket, finished CTAs} pairs of the ring kernels, used ALTERNATELY by successive
+//          launches on the stream (consecutive arg-max launches may overlap, see K124), zero between
+//          uses: the last CTA of a launch resets its pair;
+//   [4..5] {published sequence number, finished CTAs} of the fused parse kernel.
+// Kernels on different streams get different slots.
 constexpr int kTicketSlots = 64;
-struct DeviceInfo { int* tickets = nullptr; cudaStream_t slot_stream[kTicketSlots] = {}; int slots_used = 0;
+constexpr int kSlotWords = 8;
+struct StreamSlot { cudaStream_t stream = nullptr; unsigned launches = 0; int published = 0; bool fast_open = false; };
+struct DeviceInfo { int* tickets = nullptr; StreamSlot slot[kTicketSlots]; int slots_used = 0;
                     int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, tma16[2] = {0, 0}, decode_nms[3] = {0, 0, 0}, ldg = 0, nms = 0,
-                           tree[3] = {0, 0, 0}, tree_light[3] = {0, 0, 0}; };
+                           tree[3] = {0, 0, 0}, tree_light[3] = {0, 0, 0}, fused[2][3] = {{0, 0, 0}, {0, 0, 0}}; };
 static DeviceInfo g_dev[64];
 
 // Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
@@ -1242,18 +1575,33 @@ static cudaError_t device_info(DeviceInfo** out) {
 // serialise (measured: it did).
 static std::mutex g_ticket_mu;
 
-static cudaError_t ticket_for(DeviceInfo* d, cudaStream_t st, int** out) {
+// The stream's slot (nullptr when all slots are taken: callers then deal work statically and do
+// not overlap calls).  Caller holds no lock.
+static cudaError_t slot_for(DeviceInfo* d, cudaStream_t st, StreamSlot** slot, int** words) {
     std::lock_guard<std::mutex> lock(g_ticket_mu);
     if (!d->tickets) {
-        cudaError_t e = cudaMalloc(&d->tickets, kTicketSlots * 2 * sizeof(int));
+        cudaError_t e = cudaMalloc(&d->tickets, kTicketSlots * kSlotWords * sizeof(int));
         if (e != cudaSuccess) return e;
-        if ((e = cudaMemset(d->tickets, 0, kTicketSlots * 2 * sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMemset(d->tickets, 0, kTicketSlots * kSlotWords * sizeof(int))) != cudaSuccess) return e;
     }
+    *slot = nullptr;
+    *words = nullptr;
     for (int i = 0; i < d->slots_used; ++i)
-        if (d->slot_stream[i] == st) { *out = d->tickets + 2 * i; return cudaSuccess; }
-    if (d->slots_used == kTicketSlots) { *out = nullptr; return cudaSuccess; }    // static dealing for further streams
-    d->slot_stream[d->slots_used] = st;
-    *out = d->tickets + 2 * d->slots_used++;
+        if (d->slot[i].stream == st) { *slot = &d->slot[i]; *words = d->tickets + kSlotWords * i; return cudaSuccess; }
+    if (d->slots_used == kTicketSlots) return cudaSuccess;
+    d->slot[d->slots_used].stream = st;
+    *slot = &d->slot[d->slots_used];
+    *words = d->tickets + kSlotWords * d->slots_used++;
+    return cudaSuccess;
+}
+
+// ticket pair for the next ring-kernel launch on `st`
+static cudaError_t ticket_for(DeviceInfo* d, cudaStream_t st, int** out) {
+    StreamSlot* slot = nullptr;
+    int* words = nullptr;
+    cudaError_t e = slot_for(d, st, &slot, &words);
+    if (e != cudaSuccess) return e;
+    *out = slot ? words + 2 * (slot->launches++ & 1u) : nullptr;
     return cudaSuccess;
 }
 
@@ -1336,21 +1684,38 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
 }
 
 // Ring plan for a 16-bit head: always the split-matrix mapping, 16-byte vectors of 8 columns.
-static bool plan_argmax16(const Geom& g, const Tuning& t, ArgmaxPlan* p) {
+// Items of G matrices are dealt to `grid` persistent CTAs; with few items per CTA (cfg2: 7680
+// matrices, 2-3 items each) the fill of the last wave decides, so among G/2..G matrices per item
+// the count whose last wave is fullest is taken (cfg2: 26 -> 296 items = 2.0 waves).
+static bool plan_argmax16(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     if (g.HW % 8 != 0 || g.HW / 8 > 992) return false;
     p->CV = g.HW / 8;
     const int row_bytes = g.HW * 2;
-    int G = t.argmax_threads / p->CV;
+    int G = t.argmax16_threads / p->CV;
     if (G < 1) G = 1;
     while (G > 1 && p->CV * G > 992) --G;
     if (G > 32) G = 32;
     if (G > g.B * g.E) G = g.B * g.E;
+    p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
+    {
+        const long long n_mats = (long long)g.B * g.E;
+        const long long grid = (long long)sms * p->ctas_per_sm;
+        int bestM = G;
+        double best_eff = 0.0;
+        for (int M = G; M >= (G + 1) / 2 && M >= 1; --M) {
+            const long long items = (n_mats + M - 1) / M;
+            const long long waves = (items + grid - 1) / grid;
+            const double eff = (double)n_mats / (double)(waves * grid * M);
+            if (eff > best_eff + 0.02) { best_eff = eff; bestM = M; }
+        }
+        G = bestM;
+    }
     p->split_mats = 1;
     p->G = G;
     p->threads = p->CV * G;
     p->threads_padded = (p->threads + 31) & ~31;
     const int per_row = row_bytes * G;
-    int max_rows = t.argmax_stage_bytes / per_row;
+    int max_rows = t.argmax16_stage_bytes / per_row;
     if (max_rows < 1) max_rows = 1;
     if (max_rows > g.S) max_rows = g.S;
     p->chunks = (g.S + max_rows - 1) / max_rows;
@@ -1358,7 +1723,6 @@ static bool plan_argmax16(const Geom& g, const Tuning& t, ArgmaxPlan* p) {
     p->chunks = (g.S + p->rows - 1) / p->rows;
     p->stage_bytes = (uint32_t)(((size_t)p->rows * per_row + 127) & ~(size_t)127);
     p->stages = t.argmax_stages;
-    p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
     p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * p->stages * sizeof(uint64_t) + (size_t)p->stages * sizeof(int);
     return true;
 }
@@ -1369,9 +1733,14 @@ static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const G
     const int n_mats = g.B * g.E;
     ArgmaxPlan p;
     cudaError_t e;
-    if (plan_argmax16(g, t, &p) && (reinterpret_cast<uintptr_t>(head) & 15) == 0 && (g.img_stride * 2) % 16 == 0 &&
+    if (plan_argmax16(g, t, d->sms, &p) && (reinterpret_cast<uintptr_t>(head) & 15) == 0 && (g.img_stride * 2) % 16 == 0 &&
         (g.limb_off * 2) % 16 == 0) {
-        const size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
+        size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
+        {   // honour the per-call cap if a ring of at least two stages fits under it
+            const size_t two = p.smem_bytes - (size_t)(p.stages - 2) * (p.stage_bytes + 2 * sizeof(uint64_t) + sizeof(int));
+            if (t.argmax_smem_cap > 0 && (size_t)t.argmax_smem_cap < budget && (p.stages < 2 || two <= (size_t)t.argmax_smem_cap))
+                budget = (size_t)t.argmax_smem_cap;
+        }
         while (p.smem_bytes > budget && p.stages > 2) {
             --p.stages;
             p.smem_bytes -= p.stage_bytes + 2 * sizeof(uint64_t) + sizeof(int);
@@ -1413,7 +1782,12 @@ cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g
     const bool vec_ok = plan_argmax(g, t, d->sms, &p) && ((reinterpret_cast<uintptr_t>(head) & 15) == 0);
     if (vec_ok && t.argmax_variant == 0) {
         // shrink the ring until it fits the opt-in shared memory (split between resident CTAs)
-        const size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
+        size_t budget = (size_t)d->smem_optin / p.ctas_per_sm - (p.ctas_per_sm > 1 ? 1024 : 0);
+        {   // honour the per-call cap if a ring of at least two stages fits under it
+            const size_t two = p.smem_bytes - (size_t)(p.stages - 2) * (p.stage_bytes + 2 * sizeof(uint64_t) + sizeof(int));
+            if (t.argmax_smem_cap > 0 && (size_t)t.argmax_smem_cap < budget && (p.stages < 2 || two <= (size_t)t.argmax_smem_cap))
+                budget = (size_t)t.argmax_smem_cap;
+        }
         while (p.smem_bytes > budget && p.stages > 2) {
             --p.stages;
             p.smem_bytes -= p.stage_bytes + 2 * sizeof(uint64_t) + sizeof(int);
@@ -1606,6 +1980,120 @@ cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable&
                              h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, pdl_bits);
     });
     return cudaErrorInvalidValue;
+}
+
+// ---- fused decode + NMS + tree parse --------------------------------------------------------------
+// Staging delta (K*HW floats) makes every walk step and score a shared-memory read; it is dropped
+// when the CTA would grow beyond 48 KB (big grids walk through L2 instead and stay light enough to
+// sit beside the arg-max ring).  stage_pref: -1 auto, 0 never, >= 1 whenever it fits at all.
+static bool fused_plan(const Geom& g, int smem_optin, int stage_pref, bool* staged, size_t* smem) {
+    if (g.HW > 1024) return false;                                 // the NMS bit matrix is built for <= 1024 boxes
+    const size_t with = fused_layout(g, true).total, without = fused_layout(g, false).total;
+    bool st = stage_pref < 0 ? with <= 48 * 1024 : (stage_pref > 0 && with <= (size_t)smem_optin);
+    if (!st && without > (size_t)smem_optin) return false;
+    *staged = st;
+    *smem = st ? with : without;
+    return true;
+}
+
+bool parse_fused_supported(const Geom& g, int stage_pref) {
+    DeviceInfo* d = nullptr;
+    if (device_info(&d) != cudaSuccess) return false;
+    bool staged;
+    size_t smem;
+    return fused_plan(g, d->smem_optin, stage_pref, &staged, &smem);
+}
+
+bool parse_fused_coresident(const Geom& g, int stage_pref, const Tuning& t, size_t* ring_cap) {
+    DeviceInfo* d = nullptr;
+    bool staged;
+    size_t smem = 0;
+    if (device_info(&d) != cudaSuccess || !fused_plan(g, d->smem_optin, stage_pref, &staged, &smem)) return false;
+    const int per_sm = (g.B + d->sms - 1) / d->sms;                        // parse CTAs an SM must hold at once
+    const int t124 = g.HW <= 256 ? 256 : 512;
+    // the arg-max CTA beside them: consumer threads + producer warp, 56 registers per thread (ptxas)
+    const int t3 = ((g.dtype == HEAD_F32 ? t.argmax_threads : t.argmax16_threads) + 31) / 32 * 32 + 32;
+    if (t3 + per_sm * t124 > 2048) return false;
+    if ((size_t)t3 * 56 + (size_t)per_sm * t124 * 40 > 65536) return false;
+    const size_t sm_bytes = (size_t)d->smem_optin + 1024;                  // per SM: the opt-in maximum + one CTA's reserve
+    const size_t taken = (size_t)per_sm * (smem + 1024) + 1024;
+    const size_t min_ring = 2 * 16 * 1024;
+    if (taken + min_ring > sm_bytes) return false;
+    *ring_cap = sm_bytes - taken;
+    return true;
+}
+
+size_t parse_fused_smem_bytes(const Geom& g, int stage_pref) {
+    DeviceInfo* d = nullptr;
+    bool staged;
+    size_t smem = 0;
+    if (device_info(&d) != cudaSuccess || !fused_plan(g, d->smem_optin, stage_pref, &staged, &smem)) return 0;
+    return smem;
+}
+
+cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
+                               const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
+                               float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref) {
+    if (g.B == 0) return cudaSuccess;
+    DeviceInfo* d = nullptr;
+    cudaError_t e = device_info(&d);
+    if (e != cudaSuccess) return e;
+    bool staged;
+    size_t smem;
+    if (!fused_plan(g, d->smem_optin, stage_pref, &staged, &smem)) return cudaErrorInvalidConfiguration;
+    // chain_mode 0: plain launch; 1: programmatic dependent that triggers after its wait;
+    //            2: overlapped calls — guard, early trigger (see the kernel's header comment)
+    StreamSlot* slot = nullptr;
+    int* words = nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if ((e = cudaStreamIsCapturing(st, &cap)) != cudaSuccess) return e;
+    if (cap == cudaStreamCaptureStatusNone && (e = slot_for(d, st, &slot, &words)) != cudaSuccess) return e;
+    int bits = 0;
+    if (pdl_attr) bits |= PDL_WAIT_START;
+    int seq = 0;
+    if (slot) { bits |= FUSED_PUBLISH; seq = slot->published; }
+    if (pdl_attr && chain_mode == 2 && slot) bits |= FUSED_GUARD | FUSED_TRIGGER_EARLY;
+    else if (pdl_attr) bits |= PDL_TRIGGER;
+    const int threads = g.HW <= 256 ? 256 : 512;
+    int* sync = words ? words + 4 : nullptr;
+    PPN_DISPATCH_HEAD(g.dtype, {
+        if (staged) {
+            if ((e = ensure_smem(parse_fused_kernel<true, T>, smem, &d->fused[1][g.dtype])) != cudaSuccess) return e;
+            e = launch_kernel(parse_fused_kernel<true, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head), g, ch,
+                              det_thr, nms_thr, min_kp, amax, h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R,
+                              bits, sync, seq);
+        } else {
+            if ((e = ensure_smem(parse_fused_kernel<false, T>, smem, &d->fused[0][g.dtype])) != cudaSuccess) return e;
+            e = launch_kernel(parse_fused_kernel<false, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head), g, ch,
+                              det_thr, nms_thr, min_kp, amax, h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R,
+                              bits, sync, seq);
+        }
+    });
+    if (e == cudaSuccess && slot) {
+        std::lock_guard<std::mutex> lock(g_ticket_mu);
+        slot->published = seq + 1;
+        slot->fast_open = true;
+    }
+    return e;
+}
+
+// May the next arg-max launch on `st` start beside the stream's previous parse?  Only when that was a
+// publishing fused parse (or nothing of ours): any other whole-path launch calls chain_break().
+bool chain_clean(cudaStream_t st) {
+    DeviceInfo* d = nullptr;
+    if (device_info(&d) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lock(g_ticket_mu);
+    for (int i = 0; i < d->slots_used; ++i)
+        if (d->slot[i].stream == st) return d->slot[i].fast_open;
+    return false;
+}
+
+void chain_break(cudaStream_t st) {
+    DeviceInfo* d = nullptr;
+    if (device_info(&d) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lock(g_ticket_mu);
+    for (int i = 0; i < d->slots_used; ++i)
+        if (d->slot[i].stream == st) d->slot[i].fast_open = false;
 }
 
 }  // namespace ppn

@@ -13,8 +13,14 @@ struct Tuning {
     int argmax_split = -1;             // -1 auto, 0 = groups split rows, 1 = groups take one matrix each
     int argmax_dynamic = 1;            // ring kernels draw work from a global ticket counter (0: static round-robin)
     int argmax_tail_opt = 0;           // split-matrix mode: pick matrices/item that fills the last wave best
+    int argmax_smem_cap = 0;           // > 0: the ring may use at most this much shared memory (set per call by ppn_parse
+                                       // so that the fused parse kernel's CTAs fit beside it on every SM)
+    int argmax16_threads = 320;        // 16-bit heads: their own ring shape (rows are half as long, so an item
+    int argmax16_stage_bytes = 32 * 1024;   // of G matrices is half the bytes; measured, profiles/sweep_argmax16_*)
     int parse_stage_all = -1;          // tree parse stages: -1 auto, 0 nothing, 1 resp+conf, 2 all six groups
     int parse_threads = 0;             // tree-parse CTA size, 0 = by grid size
+    int parse_fused = -1;              // whole-path call: decode+NMS+tree parse in one kernel.  -1 auto (when all of its
+                                       // CTAs fit on the SMs beside the arg-max ring), 0 never (three kernels), 1 whenever supported
     int parse_chain_calls = 1;         // PDL chain: the first kernel of a call is a programmatic dependent too
     int host_chunk_images = 64;
     int parse_overlap = 2;             // 0 serial; 1 decode+NMS on a side stream beside the arg-max;
@@ -72,5 +78,17 @@ cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable&
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
                               float* h_score, float* h_box, int R, cudaStream_t st, bool pdl_attr = false, int pdl_bits = 0,
                               int stage_all_pref = -1, int threads_pref = 0);
+
+// fused decode + NMS + tree parse (n_nms_parts == 1, H*W <= 1024): the whole-path call's second kernel
+bool parse_fused_supported(const Geom& g, int stage_pref);
+// Can every CTA of the fused parse kernel be resident beside one arg-max CTA per SM?  If so, *ring_cap is
+// the shared memory left for the ring on an SM.
+bool parse_fused_coresident(const Geom& g, int stage_pref, const Tuning& t, size_t* ring_cap);
+size_t parse_fused_smem_bytes(const Geom& g, int stage_pref);
+cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
+                               const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
+                               float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref);
+bool chain_clean(cudaStream_t st);      // the stream's last whole-path launch was a (publishing) fused parse
+void chain_break(cudaStream_t st);      // ... was something else: the next overlapped call starts fully ordered
 
 }  // namespace ppn

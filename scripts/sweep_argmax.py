@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--tail-opt", type=int, default=1)
+    ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16", "bf16"])
     args = ap.parse_args()
     peak = 6553.0
     _lib.tune(argmax_tail_opt=args.tail_opt)
@@ -45,18 +46,24 @@ def main():
         cfg = PRESETS[name]()
         B = BATCH[name]
         nbuf = 3 if B * cfg.bytes_per_image < (1 << 30) else 2
-        bufs = [torch.rand(B, cfg.C, cfg.H, cfg.W, device="cuda") for _ in range(nbuf)]
+        dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[args.head_dtype]
+        if dt != torch.float32:
+            nbuf = 4                                      # half the bytes per batch: keep the rotation larger than L2
+        bufs = [torch.rand(B, cfg.C, cfg.H, cfg.W, device="cuda").to(dt) for _ in range(nbuf)]
         parser = PoseParser(cfg)
-        limb_bytes = B * cfg.E * cfg.S * cfg.HW * 4
+        limb_bytes = B * cfg.E * cfg.S * cfg.HW * bufs[0].element_size()
         rows = []
         grid = list(itertools.product([0], [16384, 32768, 49152, 65536], [3, 4, 5, 6], [192, 320, 512], [1, 2], [0, 1]))
         grid += list(itertools.product([1], [32768], [5], [128, 192], [1], [0]))
+        if dt != torch.float32:                           # the 16-bit ring always splits matrices; more thread counts instead
+            grid = list(itertools.product([0], [16384, 32768, 49152], [3, 4, 5, 6], [160, 320, 480, 576, 768], [1, 2], [1]))
         if args.quick:
             grid = grid[::7]
         for variant, sb, st, th, ctas, split in grid:
             if variant == 0 and sb * st * ctas > 215 * 1024:
                 continue
-            _lib.tune(argmax_variant=variant, argmax_stage_bytes=sb, argmax_stages=st, argmax_threads=th, argmax_ctas_per_sm=ctas, argmax_split=split)
+            _lib.tune(argmax_variant=variant, argmax_stage_bytes=sb, argmax_stages=st, argmax_threads=th, argmax_ctas_per_sm=ctas, argmax_split=split,
+                      argmax16_stage_bytes=sb, argmax16_threads=th)
             try:
                 med, best = time_setting(parser, bufs, args.iters)
             except Exception as e:

@@ -309,8 +309,18 @@ def test_limb_argmax_work_distribution(preset, dynamic, tail_opt, ctas):
         _lib.tune(**TUNE_DEFAULTS)
 
 
+@pytest.fixture(params=[1, 0], ids=["fused", "three_kernels"])
+def fused(request):
+    """Run a whole-path test with the default two-kernel call (arg-max + fused parse) and with the
+    three-kernel chain (ppn_tune parse.fused = 0)."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    _lib.tune(parse_fused=request.param)
+    yield request.param
+    _lib.tune(parse_fused=-1)
+
+
 @pytest.mark.parametrize("preset,dist,B", [("cfg2", "U", 40), ("cfg3", "D", 24), ("cfg4", "U", 10)])
-def test_overlapped_consecutive_calls(preset, dist, B):
+def test_overlapped_consecutive_calls(preset, dist, B, fused):
     """PPN_FLAG_INPUT_COMPLETE: back-to-back calls overlap (call i's tree parse under call i+1's
     arg-max, alternating workspace sets).  Every call's result must still be exact, with inputs and
     outputs changing from call to call and the modes interleaved."""
@@ -338,8 +348,64 @@ def test_overlapped_consecutive_calls(preset, dist, B):
     assert_packed_equals_oracle(last.numpy(), refs[5 % n_in], B)
 
 
+def test_overlapped_chain_stress():
+    """The overlapped chain under everything that can interleave with it on one stream: full-size
+    batches (so that several calls' kernels really are in flight), changing batch sizes, calls
+    without the flag, the three-kernel path (two NMS parts -> not fusable), stand-alone arg-max
+    launches, a second parser with its own workspace, and foreign kernels in between.  Every one of
+    result must be exact."""
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS["cfg2"]()
+    g = O.Geometry.of(cfg)
+    sizes = [512, 64, 512, 7, 300]
+    heads = [synth.make_head(g, "U", seed=900 + i, B=n) for i, n in enumerate(sizes)]
+    refs = [c_oracle.parse_batch(h, g, n_threads=8) for h in heads]
+    devs = [torch.from_numpy(h).cuda() for h in heads]
+    pa, pb, p2 = PoseParser(cfg), PoseParser(cfg), PoseParser(cfg, n_nms_parts=2)
+    n_calls = 150
+    outs, which = [], []
+    scratch = torch.zeros(1 << 20, device="cuda")
+    torch.cuda.synchronize()
+    for i in range(n_calls):
+        k = (i * 7 + i // 11) % len(sizes)
+        parser = pb if i % 13 == 5 else pa
+        outs.append(parser.parse(devs[k], out=parser.alloc_output(sizes[k]), input_complete=(i % 17 != 9)))
+        which.append(k)
+        if i % 29 == 3:
+            pa.limb_argmax(devs[k])                           # stand-alone launch on the same stream
+        if i % 31 == 4:
+            scratch.add_(1.0)                                 # a foreign kernel between two calls
+        if i % 37 == 6:
+            outs.append(p2.parse(devs[k], out=p2.alloc_output(sizes[k]), input_complete=True))   # three-kernel path
+            which.append(k)
+    torch.cuda.synchronize()
+    for o, k in zip(outs, which):
+        assert_packed_equals_oracle(o.numpy(), refs[k], sizes[k])
+
+
+def test_overlapped_chain_every_result():
+    """120 overlapped full-size calls into 120 distinct outputs, all verified."""
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS["cfg2"]()
+    g = O.Geometry.of(cfg)
+    B = 256
+    heads = [synth.make_head(g, "U", seed=950 + i, B=B) for i in range(3)]
+    refs = [c_oracle.parse_batch(h, g, n_threads=8) for h in heads]
+    devs = [torch.from_numpy(h).cuda() for h in heads]
+    parser = PoseParser(cfg)
+    outs = [parser.alloc_output(B) for _ in range(120)]
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        parser.parse(devs[i % 3], out=o, input_complete=True)
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert_packed_equals_oracle(o.numpy(), refs[i % 3], B)
+
+
 @pytest.mark.parametrize("overlap", [1, 2])
-def test_cuda_graph_capture(overlap):
+def test_cuda_graph_capture(overlap, fused):
     """The whole path is capturable: three parses (PDL chain or side-stream fork/join) recorded into
     one CUDA graph and replayed on new data."""
     from pytorch_pose_proposal_network_b200 import _lib
@@ -371,7 +437,7 @@ def test_cuda_graph_capture(overlap):
         _lib.tune(parse_overlap=2)
 
 
-def test_every_launch_ordering_gives_same_result():
+def test_every_launch_ordering_gives_same_result(fused):
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PPNConfig
     from pytorch_pose_proposal_network_b200.parser import PoseParser
@@ -432,6 +498,43 @@ def test_argmax_nan_tie_signed_zero():
         finally:
             _lib.tune(argmax_split=-1)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("grid,window", [((4, 4), (3, 3)), ((8, 8), (5, 5)), ((12, 12), (9, 9))])
+def test_argmax_sixteen_bit_special_values(dtype, grid, window):
+    """The packed 16-bit comparison (HSET2 / HMNMX2 on raw halves) against numpy's arg-max of the
+    up-cast tensor: NaNs (first one wins, either sign, any payload), infinities, signed zeros,
+    denormals and long runs of ties, in the ring kernel (H*W % 8 == 0) over several ring shapes."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PPNConfig.mpii16(outsize=grid, local_grid_size=window, insize=(grid[0] * 32, grid[1] * 32))
+    g = O.Geometry.of(cfg)
+    B = 3
+    rng = np.random.default_rng(5)
+    # raw 16-bit patterns: every class of value appears, denormals and NaN payloads included
+    bits = rng.integers(0, 1 << 16, (B, g.C, g.H, g.W), dtype=np.uint16)
+    head16 = torch.from_numpy(bits.view(np.int16)).view(dtype).clone()
+    e = head16[:, 6 * g.K:].view(B, g.E, g.S, g.H * g.W)          # a view: the writes below land in head16
+    small = torch.from_numpy(rng.integers(0, 3, tuple(e.shape[1:])).astype(np.float32)).to(dtype)
+    e[1] = small                                                          # image 1: exact ties everywhere
+    tiny = torch.tensor([0.0, -0.0, 6e-8, -6e-8, 1e-40, -1e-40], dtype=torch.float32).to(dtype)
+    e[2] = tiny[torch.from_numpy(rng.integers(0, len(tiny), tuple(e.shape[1:])))]   # zeros and denormals only
+    e[2, 0, :, 0] = float("-inf")
+    e[2, 0, :, 1] = float("nan")
+    e[2, 0, 2:, 2] = float("inf")
+    e[2, 1, g.S - 1, 3] = float("nan")                                   # NaN in the very last row
+    up = head16.float().numpy()
+    want = up[:, 6 * g.K:].reshape(B, g.E, g.S, g.H, g.W).argmax(2).astype(np.uint16)
+    dev = head16.cuda()
+    for stage_bytes, stages, threads in [(49152, 4, 480), (2048, 3, 64), (8192, 5, 992)]:
+        _lib.tune(argmax16_stage_bytes=stage_bytes, argmax_stages=stages, argmax16_threads=threads)
+        try:
+            got = PoseParser(cfg).limb_argmax(dev).cpu().numpy()
+        finally:
+            _lib.tune(argmax16_stage_bytes=32768, argmax_stages=4, argmax16_threads=320)
+        assert np.array_equal(got, want), (stage_bytes, stages, threads)
 
 
 # ------------------------------------------------------------------------------------------
