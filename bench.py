@@ -213,14 +213,11 @@ def run_ours(args, rank, world, local_rank):
     released = [None, None]
 
     def step(i):
-        if released[i % 2] is not None:             # the gather's pack kernel has read this output buffer
-            torch.cuda.current_stream(dev).wait_event(released[i % 2])
         # the inputs have been resident in HBM since before the timed region: the parser may overlap
         # consecutive steps (PPN_FLAG_INPUT_COMPLETE); results still complete in step order
-        out = parser.parse(bufs[i % n_buf], out=outs[i % 2], input_complete=not args.no_step_overlap)
-        if gatherer is not None:
-            released[i % 2] = gatherer.submit(out)  # side stream: pack + (every few steps) one async all_gather
-        return out
+        if gatherer is not None:                    # poses go straight into the gather's group buffer (dense records);
+            return gatherer.parse(bufs[i % n_buf], out=outs[i % 2], input_complete=not args.no_step_overlap)
+        return parser.parse(bufs[i % n_buf], out=outs[i % 2], input_complete=not args.no_step_overlap)
 
     def drain():
         if gatherer is not None:
@@ -396,7 +393,7 @@ def run_ours(args, rank, world, local_rank):
                    "PPN_FLAG_INPUT_COMPLETE: inputs resident before the timed region, so step i+1's arg-max may start while "
                    "step i's tree parse finishes; steps complete in order",
                    "pose_gather": "none (1 GPU)" if world == 1 else
-                   f"every step: device-side pack to dense (human, part) entries (cap {per_image}/image avg); every "
+                   f"every step: the parse kernel writes dense (human, part) entries itself (cap {per_image}/image avg); every "
                    f"{args.gather_every} steps one async NCCL all_gather of {args.gather_every * gatherer.nbytes / 1e6:.2f} MB "
                    f"per rank, overlapped with the following steps; all gathers complete inside the timed region"},
         "roofline": roofline, "e2e": e2e, "clocks": clocks,

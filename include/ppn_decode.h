@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define PPN_ABI_VERSION 3
+#define PPN_ABI_VERSION 4
 
 /* library error codes (negative); positive return values are cudaError_t */
 #define PPN_OK               0
@@ -178,16 +178,30 @@ int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams
 int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centre_yx, void* stream);
 
 /* Dense pose ENTRIES for shipping results (the multi-GPU gather): one contiguous device buffer
- *   int32  header[2 + 2B] = {total entries, overflow flag, count[B] humans, entries[B] per image}
+ *   int32  header[2 + 3B] = {total entries, overflow flag, count[B] humans, entries[B] per image,
+ *                            start[B] first entry of each image}
  *   uint32 idcell[cap]    = part id << 16 | cell      float score[cap]      float box[cap][4]
  * (256-byte aligned blocks).  One entry per PRESENT part; a human's root (part 0) is its first
  * entry, so an entry with part id 0 starts a new human and the list needs no per-human table.
- * Image b's entries start at sum_{i<b} entries[i]; entries beyond `cap_entries` are dropped and
- * the overflow flag is set.  ppn_packed_bytes gives the buffer size and, if `offsets` != NULL,
- * the byte offsets of {header, idcell, score, box}. */
+ * An image's entries are contiguous, humans in result order; ppn_pack_humans lays the images out
+ * in order (start[b] = sum_{i<b} entries[i]), ppn_parse_dense in any order.  An image whose block
+ * would end beyond `cap_entries` is not written and the overflow flag is set.  ppn_packed_bytes
+ * gives the buffer size and, if `offsets` != NULL, the byte offsets of {header, idcell, score, box}. */
 int ppn_packed_bytes(int32_t B, int32_t cap_entries, size_t* bytes, size_t* offsets /*[4] or NULL*/);
 int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_entries,
                     void* packed, size_t packed_bytes, void* stream);
+
+/* ppn_parse that also produces the dense entry buffer `packed` (ppn_packed_bytes(B, cap_entries)).
+ * On the default two-kernel path the parse kernel writes the entries itself, straight from shared
+ * memory — no pack kernel, no second pass over the fixed-stride arrays, and nothing but kernels on
+ * the stream, so consecutive PPN_FLAG_INPUT_COMPLETE calls stay overlapped; otherwise (several NMS
+ * parts, more than 32 parts, grids the fused kernel does not take) it is ppn_parse followed by
+ * ppn_pack_humans.  `out` is always required (count[] is always written); skip_slots != 0 says the
+ * caller does not need root_cell / part_cell / part_score / part_box, which the two-kernel path
+ * then leaves untouched.  Consecutive overlapping calls need different `packed` buffers, like `out`. */
+int ppn_parse_dense(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+                    void* packed, size_t packed_bytes, int32_t cap_entries, int32_t skip_slots,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-stage timing of ppn_parse for benchmarks.  After ppn_profile_enable(1) every ppn_parse
  * call (up to 4096) records CUDA events on its stream at the stage boundaries;

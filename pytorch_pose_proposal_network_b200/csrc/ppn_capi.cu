@@ -166,6 +166,29 @@ int check_humans(const PPNHumans* h) {
 
 }  // namespace
 
+// ---- dense pose entries ----------------------------------------------------------------------
+namespace {
+struct PackedLayout { size_t header, idcell, score, box, total; };
+PackedLayout packed_layout(int B, int cap) {
+    PackedLayout l;
+    l.header = 0;
+    l.idcell = align_up((size_t)(2 + 3 * (size_t)B) * sizeof(int32_t), 256);
+    l.score = l.idcell + align_up((size_t)cap * sizeof(uint32_t), 256);
+    l.box = l.score + align_up((size_t)cap * sizeof(float), 256);
+    l.total = l.box + align_up((size_t)cap * 4 * sizeof(float), 256);
+    return l;
+}
+}  // namespace
+
+namespace {
+// dense entries from the fixed-stride result (paths on which the fused kernel did not write them)
+int pack_after(const PPNHumans* out, const PPNShape* shape, const ppn::DenseTarget* d, cudaStream_t st) {
+    if (out->R > 65536) return PPN_E_UNSUPPORTED;
+    return cuda_rc(ppn::launch_pack_humans(out->count, out->part_cell, out->part_score, out->part_box, shape->B, out->R,
+                                           shape->K, d->cap, d->header, d->idcell, d->score, d->box, st));
+}
+}  // namespace
+
 extern "C" {
 
 int ppn_abi_version(void) { return PPN_ABI_VERSION; }
@@ -320,8 +343,38 @@ int ppn_tree_parse(const void* head, const PPNShape* shape, const PPNParams* par
                                           (cudaStream_t)stream));
 }
 
+static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+                      void* workspace, size_t workspace_bytes, void* stream, const ppn::DenseTarget* dense);
+
 int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
               void* workspace, size_t workspace_bytes, void* stream) {
+    return parse_impl(head, shape, params, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+int ppn_parse_dense(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+                    void* packed, size_t packed_bytes, int32_t cap_entries, int32_t skip_slots,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (cap_entries < 0) return PPN_E_BADARG;
+    if (shape->K > 65535 || (long long)shape->H * shape->W > 65536) return PPN_E_UNSUPPORTED;   // part id and cell share 32 bits
+    if (shape->B == 0) return PPN_OK;
+    if (!packed || (reinterpret_cast<uintptr_t>(packed) & 255)) return PPN_E_BADARG;
+    const PackedLayout l = packed_layout(shape->B, cap_entries);
+    if (packed_bytes < l.total) return PPN_E_WORKSPACE;
+    unsigned char* p = static_cast<unsigned char*>(packed);
+    ppn::DenseTarget d;
+    d.header = reinterpret_cast<int32_t*>(p + l.header);
+    d.idcell = reinterpret_cast<uint32_t*>(p + l.idcell);
+    d.score = reinterpret_cast<float*>(p + l.score);
+    d.box = reinterpret_cast<float*>(p + l.box);
+    d.cap = cap_entries;
+    d.skip_slots = skip_slots != 0;
+    return parse_impl(head, shape, params, out, workspace, workspace_bytes, stream, &d);
+}
+
+static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+                      void* workspace, size_t workspace_bytes, void* stream, const ppn::DenseTarget* dense) {
     int rc = check_shape(shape);
     if (rc) return rc;
     if ((rc = check_params(shape, params))) return rc;
@@ -369,6 +422,11 @@ int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params, 
     const bool fits_beside = P == 1 && ppn::parse_fused_coresident(g, g_tuning.parse_stage_all, g_tuning, &ring_cap);
     const bool fused = P == 1 && mode != 1 && (g_tuning.parse_fused < 0 ? fits_beside : (g_tuning.parse_fused != 0 &&
                        ppn::parse_fused_supported(g, g_tuning.parse_stage_all)));
+    // the dense entry buffer: written by the fused kernel itself (its cursor, header[0..1], is cleared by
+    // the arg-max kernel of the same call — nothing but kernels goes on the stream, so the overlapped
+    // chain stays intact) or, on the other paths and for K > 32, by the pack kernels after the
+    // fixed-stride result
+    const bool dense_fused = dense && fused && shape->K <= 32;
     if (fused) {
         using namespace ppn;
         Tuning tuning = g_tuning;
@@ -383,15 +441,20 @@ int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params, 
         const bool k3_attr = chain && (!overlap_calls || capturing || chain_clean(st));
         bool chained = false;
         if (ev) cudaEventRecord(ev[0], st);
+        bool zeroed = false;
         if ((e = launch_limb_argmax(head, amax, g, tuning, st, k3_attr, &chained,
-                                    mode != 2 ? 0 : (overlap_calls ? (PDL_TRIGGER | PDL_WAIT_END) : (PDL_WAIT_START | PDL_TRIGGER)))) != cudaSuccess) return (int)e;
+                                    mode != 2 ? 0 : (overlap_calls ? (PDL_TRIGGER | PDL_WAIT_END) : (PDL_WAIT_START | PDL_TRIGGER)),
+                                    dense_fused ? dense->header : nullptr, &zeroed)) != cudaSuccess) return (int)e;
+        if (dense_fused && !zeroed && (e = cudaMemsetAsync(dense->header, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) return (int)e;
         if (ev) { cudaEventRecord(ev[1], st); for (int q = 2; q < 7; ++q) cudaEventRecord(ev[q], st); }
         (void)chained;
         const bool k124_attr = mode == 2;      // a programmatic dependent of K3 (implicit trigger if K3 is a fallback kernel)
         if ((e = launch_parse_fused(head, g, ch, params->det_thresh, params->nms_thresh, params->min_num_keypoints, amax,
                                     out->count, out->root_cell, out->part_cell, out->part_score, out->part_box, out->R, st,
-                                    k124_attr, (overlap_calls && chain && !capturing) ? 2 : 1, g_tuning.parse_stage_all)) != cudaSuccess) return (int)e;
+                                    k124_attr, (overlap_calls && chain && !capturing) ? 2 : 1, g_tuning.parse_stage_all,
+                                    dense_fused ? dense : nullptr)) != cudaSuccess) return (int)e;
         if (ev) cudaEventRecord(ev[7], st);
+        if (dense && !dense_fused) return pack_after(out, shape, dense, st);
         return PPN_OK;
     }
     ppn::chain_break(st);
@@ -419,7 +482,7 @@ int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params, 
                                    keep_count, out->count, out->root_cell, out->part_cell, out->part_score, out->part_box,
                                    out->R, st, chained, chained ? (PDL_WAIT_START | PDL_TRIGGER) : 0, g_tuning.parse_stage_all,
                                    g_tuning.parse_threads)) != cudaSuccess) return (int)e;
-        return PPN_OK;
+        return dense ? pack_after(out, shape, dense, st) : PPN_OK;
     }
     cudaStream_t side = st;
     SideLane* lane = nullptr;
@@ -445,7 +508,7 @@ int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params, 
                                     keep_idx, keep_count, out->count, out->root_cell, out->part_cell, out->part_score,
                                     out->part_box, out->R, st, false, 0, g_tuning.parse_stage_all, g_tuning.parse_threads)) != cudaSuccess) return (int)e;
     if (ev) cudaEventRecord(ev[7], st);
-    return PPN_OK;
+    return dense ? pack_after(out, shape, dense, st) : PPN_OK;
 }
 
 int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centre_yx, void* stream) {
@@ -458,19 +521,6 @@ int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centr
                                             (cudaStream_t)stream));
 }
 
-// ---- dense pose entries ----------------------------------------------------------------------
-namespace {
-struct PackedLayout { size_t header, idcell, score, box, total; };
-PackedLayout packed_layout(int B, int cap) {
-    PackedLayout l;
-    l.header = 0;
-    l.idcell = align_up((size_t)(2 + 2 * (size_t)B) * sizeof(int32_t), 256);
-    l.score = l.idcell + align_up((size_t)cap * sizeof(uint32_t), 256);
-    l.box = l.score + align_up((size_t)cap * sizeof(float), 256);
-    l.total = l.box + align_up((size_t)cap * 4 * sizeof(float), 256);
-    return l;
-}
-}  // namespace
 
 int ppn_packed_bytes(int32_t B, int32_t cap_entries, size_t* bytes, size_t* offsets) {
     if (B < 0 || cap_entries < 0 || !bytes) return PPN_E_BADARG;

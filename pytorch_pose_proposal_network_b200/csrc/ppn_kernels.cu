@@ -33,7 +33,7 @@ struct Partial { float v; int32_t i; };
 
 __global__ void __launch_bounds__(1024, 1)
 limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p, int pdl,
-                       int* __restrict__ ticket) {
+                       int* __restrict__ ticket, int32_t* __restrict__ zero2) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
     Partial* part = reinterpret_cast<Partial*>(smem + (size_t)p.stages * p.stage_bytes);   // [2][G][HW]
@@ -53,6 +53,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
         fence_mbar_init();
     }
     if (pdl & PDL_WAIT_START) pdl_wait();                // default chain: `head` may come from the kernel before us
+    if (zero2 && blockIdx.x == 0 && tid == 0) { zero2[0] = 0; zero2[1] = 0; }   // the parse kernel's dense-entry cursor
     if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the parse kernel may start its prologue now
     __syncthreads();
 
@@ -169,7 +170,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
 // lanes of the producer warp.
 __global__ void __launch_bounds__(1024, 1)
 limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p, int pdl,
-                             int* __restrict__ ticket) {
+                             int* __restrict__ ticket, int32_t* __restrict__ zero2) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -191,6 +192,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         fence_mbar_init();
     }
     if (pdl & PDL_WAIT_START) pdl_wait();                // default chain: `head` may come from the kernel before us
+    if (zero2 && blockIdx.x == 0 && tid == 0) { zero2[0] = 0; zero2[1] = 0; }   // the parse kernel's dense-entry cursor
     if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the parse kernel may start its prologue now
     __syncthreads();
 
@@ -331,7 +333,7 @@ __device__ __noinline__ int first_nan16(const T16* __restrict__ mat, int S, int 
 template <typename T16>
 __global__ void __launch_bounds__(1024, 1)
 limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p, int pdl,
-                               int* __restrict__ ticket) {
+                               int* __restrict__ ticket, int32_t* __restrict__ zero2) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* ring = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -353,6 +355,7 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
         fence_mbar_init();
     }
     if (pdl & PDL_WAIT_START) pdl_wait();
+    if (zero2 && blockIdx.x == 0 && tid == 0) { zero2[0] = 0; zero2[1] = 0; }
     if (pdl & PDL_TRIGGER) pdl_launch_dependents();
     __syncthreads();
 
@@ -1151,7 +1154,7 @@ enum : int {
     FUSED_PUBLISH = 32,        // last CTA publishes seq + 1
 };
 
-struct FusedSmem { uint32_t delta, root, dyx, uni, amax, slot, pos, total; };
+struct FusedSmem { uint32_t delta, root, dyx, uni, amax, slot, estart, pmask, pos, total; };
 
 __host__ __device__ inline FusedSmem fused_layout(const Geom& g, bool staged) {
     FusedSmem l;
@@ -1166,7 +1169,9 @@ __host__ __device__ inline FusedSmem fused_layout(const Geom& g, bool staged) {
                          (uint32_t)g.HW * (16u + 8u + 4u + 4u + 4u) + (32u * Wd * (Wd + 1u) / 2u) * 4u;
     l.amax = l.uni;
     l.slot = l.amax + ((((uint32_t)g.E * g.HW * 2u) + 15u) & ~15u);
-    l.pos = l.slot + (uint32_t)g.HW * 4u;
+    l.estart = l.slot + (uint32_t)g.HW * 4u;
+    l.pmask = l.estart + (uint32_t)g.HW * 4u;
+    l.pos = l.pmask + (uint32_t)g.HW * 4u;
     const uint32_t walk = (l.pos - l.uni) + ((((uint32_t)g.HW * g.K * 2u) + 15u) & ~15u);
     l.total = l.uni + (nms > walk ? nms : walk);
     return l;
@@ -1178,12 +1183,26 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
+// Optional second output of the fused kernel: the dense (human, part) entry buffer of the multi-GPU
+// gather (layout: see "pack" below), written straight from shared memory — no pack kernel, no pass
+// over the fixed-stride arrays.  An image's entries are contiguous and ordered (human, part); images
+// take their place with one atomicAdd on header[0] (which the caller zeroes before the launch), so
+// the ORDER of the images' blocks is arbitrary and header.start[b] says where image b begins.
+struct DenseOut {
+    int32_t* header;       // nullptr: no dense output
+    uint32_t* idcell;
+    float* score;
+    float4* box;
+    int32_t cap;
+    int32_t skip_slots;    // 1: the fixed-stride arrays (root_cell, part_*) need not be written; count[] still is
+};
+
 template <bool kStaged, typename HT>
 __global__ void __launch_bounds__(512, 3)
 parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det_thr, float nms_thr, int min_kp,
                    const uint16_t* __restrict__ amax, int32_t* __restrict__ h_count, int32_t* __restrict__ h_root,
                    int32_t* __restrict__ h_cell, float* __restrict__ h_score, float4* __restrict__ h_box, int R,
-                   int pdl, int* __restrict__ sync, int seq) {
+                   int pdl, int* __restrict__ sync, int seq, DenseOut dense) {
     extern __shared__ __align__(128) unsigned char smem[];
     const FusedSmem L = fused_layout(g, kStaged);
     float* s_delta = reinterpret_cast<float*>(smem + L.delta);                  // [K*HW] resp*conf (kStaged)
@@ -1194,9 +1213,13 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
     const NmsSmem s = nms_carve(reinterpret_cast<unsigned char*>(ucell + ((g.HW + 3) & ~3)), g.HW);   // sort + mask
     uint16_t* s_amax = reinterpret_cast<uint16_t*>(smem + L.amax);              // walk phase (same bytes): [E*HW]
     int32_t* s_slot = reinterpret_cast<int32_t*>(smem + L.slot);                // [HW]
+    int32_t* s_estart = reinterpret_cast<int32_t*>(smem + L.estart);            // [HW] first dense entry of a human
+    uint32_t* s_pmask = reinterpret_cast<uint32_t*>(smem + L.pmask);            // [HW] present parts of a human (K <= 32)
     int16_t* s_pos = reinterpret_cast<int16_t*>(smem + L.pos);                  // [HW][K]
     __shared__ int warp_tot[16];
+    __shared__ int warp_ent[16];
     __shared__ int base_s;
+    __shared__ int ebase_s;
     __shared__ int n_keep_s;
 
     const int b = blockIdx.x;
@@ -1326,15 +1349,21 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
             }
         }
         __syncthreads();
-        if (tid == 0) base_s = 0;
+        if (tid == 0) { base_s = 0; ebase_s = 0; }
         __syncthreads();
-        // ---- humans with enough parts take consecutive output slots, in root order (datatest.py:129) ----
+        // ---- humans with enough parts take consecutive output slots, in root order (datatest.py:129);
+        //      their dense entries (one per present part) follow one another in the same order ----------
         for (int r0 = 0; r0 < n_keep; r0 += T) {
             const int r = r0 + tid;
             bool valid = false;
+            int present = 0;
+            unsigned pm = 1u;                                         // the root is always present
             if (r < n_keep) {
-                int present = 0;
-                for (int t = 1; t < g.K; ++t) present += (s_pos[r * g.K + t] >= 0);
+                for (int t = 1; t < g.K; ++t) {
+                    const bool here = s_pos[r * g.K + t] >= 0;
+                    present += here;
+                    pm |= (here && t < 32) ? (1u << t) : 0u;
+                }
                 valid = min_kp <= present;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -1347,15 +1376,49 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
                 total += v;
             }
             const int slot = off + __popc(bal & ((1u << lane) - 1u));
-            if (r < n_keep) s_slot[r] = (valid && slot < R) ? slot : -1;
+            const bool placed = valid && slot < R;
+            const int n_ent = placed ? present + 1 : 0;               // dense entries of this human
+            int incl = n_ent;                                         // warp-inclusive scan
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            if (lane == 31) warp_ent[warp] = incl;
             __syncthreads();
-            if (tid == 0) base_s += total;
+            int eoff = ebase_s, etotal = 0;
+            for (int wi = 0; wi < (T >> 5); ++wi) {
+                const int ev = warp_ent[wi];
+                if (wi < warp) eoff += ev;
+                etotal += ev;
+            }
+            if (r < n_keep) {
+                s_slot[r] = placed ? slot : -1;
+                s_estart[r] = eoff + incl - n_ent;
+                s_pmask[r] = pm;
+            }
+            __syncthreads();
+            if (tid == 0) { base_s += total; ebase_s += etotal; }
         }
         __syncthreads();
+        // ---- the image's place in the dense buffer ---------------------------------------------------
+        const bool want_dense = dense.header != nullptr;
+        if (want_dense && tid == 0) {
+            const int n_ent = ebase_s, B = (int)gridDim.x;
+            const int start = atomicAdd(dense.header, n_ent);
+            dense.header[2 + b] = base_s;
+            dense.header[2 + B + b] = n_ent;
+            dense.header[2 + 2 * B + b] = start;
+            if (start + n_ent > dense.cap) dense.header[1] = 1;
+            ebase_s = start + n_ent > dense.cap ? -1 : start;           // -1: the image's entries do not fit
+        }
+        __syncthreads();
+        const int e_base = want_dense ? ebase_s : -1;
+        const bool slots_out = !(want_dense && dense.skip_slots);
         // ---- write-out: one (human, part) pair per thread and step, two steps in flight --------------
         const int n_pairs = n_keep * g.K;
         for (int p0 = tid; p0 < n_pairs; p0 += 2 * T) {
-            int cc[2], tt[2], ss[2];
+            int cc[2], tt[2], ss[2], rr[2];
             float xs[2], ys[2], ws[2], hs[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -1368,6 +1431,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
                         cc[u] = s_pos[pair];
                         tt[u] = t;
                         ss[u] = sl;
+                        rr[u] = r;
                         if (cc[u] >= 0) {
                             const int at = t * g.HW + cc[u];
                             xs[u] = ldf(img + (size_t)2 * KHW + at); ys[u] = ldf(img + (size_t)3 * KHW + at);
@@ -1388,13 +1452,27 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
                     score = kStaged ? s_delta[at] : __fmul_rn(ldf(resp + at), ldf(conf + at));
                     box = box_from(xs[u], ys[u], ws[u], hs[u], h, w, g);
                 }
-                const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
-                if (tt[u] == 0) h_root[human] = c;
-                h_cell[o] = c;
-                h_score[o] = score;
-                h_box[o] = box;
+                if (slots_out) {
+                    const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
+                    if (tt[u] == 0) h_root[human] = c;
+                    h_cell[o] = c;
+                    h_score[o] = score;
+                    h_box[o] = box;
+                }
+                if (e_base >= 0 && c >= 0) {
+                    const int r = rr[u];
+                    const int e = e_base + s_estart[r] + __popc(s_pmask[r] & ((1u << tt[u]) - 1u));
+                    dense.idcell[e] = ((uint32_t)tt[u] << 16) | (uint32_t)c;
+                    dense.score[e] = score;
+                    dense.box[e] = box;
+                }
             }
         }
+    } else if (dense.header != nullptr && tid == 0) {                     // no humans: an empty block
+        const int B = (int)gridDim.x;
+        dense.header[2 + b] = 0;
+        dense.header[2 + B + b] = 0;
+        dense.header[2 + 2 * B + b] = 0;
     }
     if (tid == 0) h_count[b] = n_keep > 0 ? base_s : 0;
     // ---- the last CTA publishes this call's sequence number ------------------------------------------
@@ -1436,7 +1514,7 @@ part_centres_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
 // pack — dense pose entries for the multi-GPU gather
 // =========================================================================================
 // Fixed-stride PPNHumans -> one contiguous buffer of (human, part) ENTRIES, present parts only:
-//   header   int32 {total entries, overflow, count[B], entries[B]}
+//   header   int32 {total entries, overflow, count[B], entries[B], start[B]}
 //   idcell   uint32[cap]  = part id << 16 | cell        (the root, part 0, is always a human's first
 //   score    float [cap]                                  entry, so the list delimits itself)
 //   box      float4[cap]
@@ -1480,10 +1558,13 @@ pack_entries_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
     __syncthreads();
     int off = 0;
     for (int wi = 0; wi < n_warps; ++wi) off += red[wi];
-    if (tid == 0 && b == B - 1) {
-        const int total = off + per_image[b];
-        header[0] = total;
-        header[1] = total > cap ? 1 : 0;
+    if (tid == 0) {
+        header[2 + 2 * B + b] = off;                        // start[b]: images in order here (the fused kernel: any order)
+        if (b == B - 1) {
+            const int total = off + per_image[b];
+            header[0] = total;
+            header[1] = total > cap ? 1 : 0;
+        }
     }
     const int n = min(count[b], R);
     const int32_t* c = cell + (size_t)b * R * K;
@@ -1729,7 +1810,7 @@ static bool plan_argmax16(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p
 
 template <typename T16>
 static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
-                                        bool pdl, bool* pdl_used, int pdl_bits, DeviceInfo* d, size_t* have) {
+                                        bool pdl, bool* pdl_used, int pdl_bits, DeviceInfo* d, size_t* have, int32_t* zero2, bool* zeroed) {
     const int n_mats = g.B * g.E;
     ArgmaxPlan p;
     cudaError_t e;
@@ -1753,8 +1834,9 @@ static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const G
             if (grid > n_items) grid = n_items;
             if ((e = ensure_smem(limb_argmax_tma_multi16_kernel<T16>, p.smem_bytes, have)) != cudaSuccess) return e;
             e = launch_kernel(limb_argmax_tma_multi16_kernel<T16>, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
-                              head, amax, g, p, pdl_bits, ticket);
+                              head, amax, g, p, pdl_bits, ticket, zero2);
             if (pdl_used) *pdl_used = pdl;
+            if (zeroed) *zeroed = zero2 != nullptr;
             return e;
         }
     }
@@ -1764,8 +1846,9 @@ static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const G
 }
 
 cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
-                               bool pdl, bool* pdl_used, int pdl_bits) {
+                               bool pdl, bool* pdl_used, int pdl_bits, int32_t* zero2, bool* zeroed) {
     if (pdl_used) *pdl_used = false;
+    if (zeroed) *zeroed = false;
     if (pdl_bits < 0) pdl_bits = pdl ? (PDL_TRIGGER | PDL_WAIT_END) : 0;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -1773,9 +1856,9 @@ cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g
     const int n_mats = g.B * g.E;
     if (n_mats == 0) return cudaSuccess;
     if (g.dtype == HEAD_F16)
-        return launch_limb_argmax16(static_cast<const __half*>(head_v), amax, g, t, st, pdl, pdl_used, pdl_bits, d, &d->tma16[0]);
+        return launch_limb_argmax16(static_cast<const __half*>(head_v), amax, g, t, st, pdl, pdl_used, pdl_bits, d, &d->tma16[0], zero2, zeroed);
     if (g.dtype == HEAD_BF16)
-        return launch_limb_argmax16(static_cast<const __nv_bfloat16*>(head_v), amax, g, t, st, pdl, pdl_used, pdl_bits, d, &d->tma16[1]);
+        return launch_limb_argmax16(static_cast<const __nv_bfloat16*>(head_v), amax, g, t, st, pdl, pdl_used, pdl_bits, d, &d->tma16[1], zero2, zeroed);
     if (g.dtype != HEAD_F32) return cudaErrorInvalidValue;
     const float* head = static_cast<const float*>(head_v);
     ArgmaxPlan p;
@@ -1801,14 +1884,15 @@ cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g
                 if (grid > n_items) grid = n_items;
                 if ((e = ensure_smem(limb_argmax_tma_multi_kernel, p.smem_bytes, &d->tma_multi)) != cudaSuccess) return e;
                 e = launch_kernel(limb_argmax_tma_multi_kernel, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
-                                  head, amax, g, p, pdl_bits, ticket);
+                                  head, amax, g, p, pdl_bits, ticket, zero2);
             } else {
                 if (grid > n_mats) grid = n_mats;
                 if ((e = ensure_smem(limb_argmax_tma_kernel, p.smem_bytes, &d->tma)) != cudaSuccess) return e;
                 e = launch_kernel(limb_argmax_tma_kernel, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
-                                  head, amax, g, p, pdl_bits, ticket);
+                                  head, amax, g, p, pdl_bits, ticket, zero2);
             }
             if (pdl_used) *pdl_used = pdl;
+            if (zeroed) *zeroed = zero2 != nullptr;
             return e;
         }
     }
@@ -2033,7 +2117,8 @@ size_t parse_fused_smem_bytes(const Geom& g, int stage_pref) {
 
 cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
-                               float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref) {
+                               float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
+                               const DenseTarget* dense_to) {
     if (g.B == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -2041,6 +2126,12 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
     bool staged;
     size_t smem;
     if (!fused_plan(g, d->smem_optin, stage_pref, &staged, &smem)) return cudaErrorInvalidConfiguration;
+    DenseOut dense = {nullptr, nullptr, nullptr, nullptr, 0, 0};
+    if (dense_to) {
+        if (g.K > 32) return cudaErrorInvalidConfiguration;          // present-part masks are 32 bits
+        dense = DenseOut{dense_to->header, dense_to->idcell, dense_to->score, reinterpret_cast<float4*>(dense_to->box),
+                         dense_to->cap, dense_to->skip_slots};
+    }
     // chain_mode 0: plain launch; 1: programmatic dependent that triggers after its wait;
     //            2: overlapped calls — guard, early trigger (see the kernel's header comment)
     StreamSlot* slot = nullptr;
@@ -2061,12 +2152,12 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
             if ((e = ensure_smem(parse_fused_kernel<true, T>, smem, &d->fused[1][g.dtype])) != cudaSuccess) return e;
             e = launch_kernel(parse_fused_kernel<true, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head), g, ch,
                               det_thr, nms_thr, min_kp, amax, h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R,
-                              bits, sync, seq);
+                              bits, sync, seq, dense);
         } else {
             if ((e = ensure_smem(parse_fused_kernel<false, T>, smem, &d->fused[0][g.dtype])) != cudaSuccess) return e;
             e = launch_kernel(parse_fused_kernel<false, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head), g, ch,
                               det_thr, nms_thr, min_kp, amax, h_count, h_root, h_cell, h_score, reinterpret_cast<float4*>(h_box), R,
-                              bits, sync, seq);
+                              bits, sync, seq, dense);
         }
     });
     if (e == cudaSuccess && slot) {

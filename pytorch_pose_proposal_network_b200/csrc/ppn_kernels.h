@@ -46,7 +46,9 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p);
 // pdl: launch as a programmatic dependent of the previous kernel in `st` (starts beside it, waits
 // for it only before completing); *pdl_used tells whether the chosen kernel variant honoured it.
 cudaError_t launch_limb_argmax(const void* head, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
-                               bool pdl = false, bool* pdl_used = nullptr, int pdl_bits = -1 /* default: trigger + end wait */);
+                               bool pdl = false, bool* pdl_used = nullptr, int pdl_bits = -1 /* default: trigger + end wait */,
+                               int32_t* zero2 = nullptr /* two ints the ring kernel clears before anything else runs */,
+                               bool* zeroed = nullptr);
 
 cudaError_t launch_decode_candidates(const void* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
                                      float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st);
@@ -85,9 +87,12 @@ bool parse_fused_supported(const Geom& g, int stage_pref);
 // the shared memory left for the ring on an SM.
 bool parse_fused_coresident(const Geom& g, int stage_pref, const Tuning& t, size_t* ring_cap);
 size_t parse_fused_smem_bytes(const Geom& g, int stage_pref);
+// dense (human, part) entry buffer written by the fused kernel itself (header[0..1] zeroed by the caller)
+struct DenseTarget { int32_t* header; uint32_t* idcell; float* score; float* box; int32_t cap; int32_t skip_slots; };
 cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
-                               float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref);
+                               float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
+                               const DenseTarget* dense_to = nullptr);
 bool chain_clean(cudaStream_t st);      // the stream's last whole-path launch was a (publishing) fused parse
 void chain_break(cudaStream_t st);      // ... was something else: the next overlapped call starts fully ordered
 

@@ -119,12 +119,11 @@ def unpack_entries(buf, B: int, cap_entries: int, offsets):
     box[cap,4]).  Within an image an entry with part 0 starts a new human."""
     a = buf.numpy() if isinstance(buf, torch.Tensor) else np.asarray(buf)
     o_h, o_i, o_s, o_b = offsets
-    header = a[o_h:o_h + 4 * (2 + 2 * B)].view(np.int32)
-    count, entries = header[2:2 + B], header[2 + B:2 + 2 * B]
+    header = a[o_h:o_h + 4 * (2 + 3 * B)].view(np.int32)
+    count, entries, start = header[2:2 + B], header[2 + B:2 + 2 * B], header[2 + 2 * B:2 + 3 * B].astype(np.int64)
     idcell = a[o_i:o_i + 4 * cap_entries].view(np.uint32)
     score = a[o_s:o_s + 4 * cap_entries].view(np.float32)
     box = a[o_b:o_b + 16 * cap_entries].view(np.float32).reshape(cap_entries, 4)
-    start = np.concatenate([[0], np.cumsum(entries)[:-1]]).astype(np.int64) if B else np.zeros(0, np.int64)
     return dict(total=int(header[0]), overflow=bool(header[1]), count=count, entries=entries, start=start,
                 part=(idcell >> 16).astype(np.int32), cell=(idcell & 0xffff).astype(np.int32), score=score, box=box)
 
@@ -220,7 +219,8 @@ class PoseParser:
                               out.part_score.data_ptr(), out.part_box.data_ptr(), out.R)
 
     # ---- the whole path ---------------------------------------------------------------- #
-    def parse(self, head: torch.Tensor, out: Optional[PackedHumans] = None, input_complete: bool = False) -> PackedHumans:
+    def parse(self, head: torch.Tensor, out: Optional[PackedHumans] = None, input_complete: bool = False,
+              dense: Optional[torch.Tensor] = None, cap_entries: int = 0, skip_slots: bool = False) -> PackedHumans:
         """Enqueue the whole path for a device batch on torch's current stream (asynchronous).
 
         ``out`` may be a preallocated :meth:`alloc_output` to reuse; otherwise the parser's own
@@ -231,6 +231,10 @@ class PoseParser:
         just ordered before it on the stream by a producer kernel that may still be running.  The
         call may then overlap the previous ``parse`` on this stream (its arg-max streams while the
         previous call's tree parse finishes); give consecutive overlapping calls different ``out``.
+
+        ``dense`` (a uint8 device buffer of ``packed_layout(B, cap_entries)`` bytes): also produce the
+        dense (human, part) entry buffer of the multi-GPU gather (``ppn_parse_dense``); with
+        ``skip_slots`` the fixed-stride arrays of ``out`` other than ``count`` may be left unwritten.
         """
         B = self._check_head(head)
         if head.device != self.device:
@@ -245,10 +249,16 @@ class PoseParser:
         hs = self._humans_struct(out)
         with self._guard():
             params = self.c.params_input_complete if input_complete else self.c.params
-            rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), C.byref(params), C.byref(hs),
-                                    ws.data_ptr(), ws.numel(), torch.cuda.current_stream(self.device).cuda_stream)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            if dense is None:
+                rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), C.byref(params), C.byref(hs),
+                                        ws.data_ptr(), ws.numel(), st)
+            else:
+                rc = self.lib.ppn_parse_dense(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), C.byref(params),
+                                              C.byref(hs), dense.data_ptr(), dense.numel(), int(cap_entries), int(bool(skip_slots)),
+                                              ws.data_ptr(), ws.numel(), st)
         if rc:
-            raise _lib.PPNError(rc, "ppn_parse")
+            raise _lib.PPNError(rc, "ppn_parse" if dense is None else "ppn_parse_dense")
         return out
 
     def launches_per_parse(self, B: int) -> int:

@@ -98,14 +98,16 @@ class ShardedPoseParser:
 class PoseGatherer:
     """Gather of every rank's poses as ONE small asynchronous collective per group of steps.
 
-    Each step the local result is compacted on the device into a dense record buffer
-    (``PoseParser.pack`` -> ``ppn_pack_humans``: counts + one (part, cell, score, box) entry per
-    present part, up to ``cap_entries``).  Every ``group_steps`` steps the group's buffers are all-gathered with a single
-    ``all_gather_into_tensor`` issued with ``async_op``: the collective runs on NCCL's own stream
-    while the next steps' kernels run on the compute stream (one NCCL call costs tens of µs of host
-    time, comparable to a whole step, hence the grouping).  Two buffer sets alternate; before a set is
-    reused the compute stream waits for the collective that last read it.  Every rank ends up with
-    every rank's records of every step.
+    Each step's parse writes its poses directly as dense records into a slice of a group buffer
+    (``PoseParser.parse(dense=...)`` -> ``ppn_parse_dense``: counts + one (part, cell, score, box) entry per
+    present part, up to ``cap_entries``) — by the parse kernel itself, so a step puts nothing but its
+    two kernels on the compute stream and consecutive steps stay overlapped.  Every ``group_steps``
+    steps the group's buffer is all-gathered with a single ``all_gather_into_tensor`` issued with
+    ``async_op`` on a side stream (one event per GROUP, not per step): the collective runs while the next
+    steps' kernels run on the compute stream (one NCCL call costs tens of µs of host time, comparable to
+    a whole step, hence the grouping).  Two buffer sets alternate; before a set is reused the compute
+    stream waits for the collective that last read it.  Every rank ends up with every rank's records of
+    every step.
     """
 
     def __init__(self, parser, images_per_rank: int, cap_entries: int, group=None, group_steps: int = 1):
@@ -121,19 +123,43 @@ class PoseGatherer:
         self.full = [torch.zeros(self.world * self.gs * self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.work = [None, None]
         self.step = 0
-        # packing and the collective live on a side stream: the compute stream goes straight on to
-        # the next step's kernels.  Events are preallocated and reused (a handful of cheap calls per
-        # step; the stream context manager is entered only when a collective is issued).
         self.side = torch.cuda.Stream(device=dev)
+        self._filled = [torch.cuda.Event() for _ in range(2)]
         self._parsed = [torch.cuda.Event() for _ in range(4)]
         self._released = [torch.cuda.Event() for _ in range(4)]
         self._slices = [[self.local[i][k * self.nbytes:(k + 1) * self.nbytes] for k in range(self.gs)] for i in range(2)]
 
+    def _ship(self, i: int):
+        """All-gather buffer set i on the side stream once the compute stream has filled it."""
+        main = torch.cuda.current_stream(self.parser.device)
+        self._filled[i].record(main)
+        self.side.wait_event(self._filled[i])
+        with torch.cuda.stream(self.side):
+            self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
+
+    def parse(self, head, out=None, input_complete: bool = False):
+        """The step: parse `head` on the current stream with the poses written straight into this step's
+        slice of the group buffer; when a group is full, start its gather.  Returns the PackedHumans whose
+        ``count`` is valid (the fixed-stride arrays are skipped where the kernel can write the dense
+        records itself)."""
+        grp, k = divmod(self.step, self.gs)
+        i = grp & 1
+        if k == 0 and self.work[i] is not None:
+            self.work[i].wait()                   # compute stream waits for the gather that last read this set
+            self.work[i] = None
+        res = self.parser.parse(head, out=out, input_complete=input_complete, dense=self._slices[i][k],
+                                cap_entries=self.cap, skip_slots=True)
+        if k == self.gs - 1:
+            self._ship(i)
+        self.step += 1
+        return res
+
     def submit(self, humans) -> torch.cuda.Event:
-        """Pack `humans` (this rank's PackedHumans of the step) on the side stream and, when a group
-        is full, start its gather.  Returns an event that fires once `humans` has been read: wait
-        for it (``stream.wait_event``) before the parser overwrites that output buffer (callers
-        alternating fewer than four output buffers are covered by the event ring)."""
+        """Alternative to :meth:`parse` for a result that already exists: pack `humans` (this rank's
+        PackedHumans of the step) on the side stream and, when a group is full, start its gather.
+        Returns an event that fires once `humans` has been read: wait for it (``stream.wait_event``)
+        before the parser overwrites that output buffer.  (Per-step events on the compute stream: steps
+        no longer overlap one another.)"""
         grp, k = divmod(self.step, self.gs)
         i = grp & 1
         e = self.step & 3
@@ -156,11 +182,10 @@ class PoseGatherer:
         """Gather a partly filled last group, then make the CURRENT stream wait for every gather.
         Every rank must have submitted the same number of steps."""
         grp, k = divmod(self.step, self.gs)
+        if k != 0:                                # flush: ship the partial group as it is
+            self._ship(grp & 1)
+            self.step = (grp + 1) * self.gs
         with torch.cuda.stream(self.side):
-            if k != 0:                            # flush: ship the partial group as it is
-                i = grp & 1
-                self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
-                self.step = (grp + 1) * self.gs
             for j in range(2):
                 if self.work[j] is not None:
                     self.work[j].wait()

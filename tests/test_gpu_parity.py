@@ -681,6 +681,57 @@ def test_pack_dense_entries_roundtrip():
                 assert np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
 
 
+@pytest.mark.parametrize("skip_slots", [False, True])
+def test_parse_dense_written_by_the_parse_kernel(fused, skip_slots):
+    """ppn_parse_dense: the dense (human, part) entries straight from the parse kernel (two-kernel path;
+    image blocks in any order, header.start says where) or via the pack kernels (three-kernel path) —
+    the same records either way, overlapped calls into rotating buffers included."""
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser, entries_to_packed, unpack_entries
+    for cfg, dist, B in ((PPNConfig.mpii16(), "U", 37), (PPNConfig.coco18(), "D", 9), (PPNConfig.mpii16(), "S", 300)):
+        g = O.Geometry.of(cfg)
+        heads = [synth.make_head(g, dist, seed=60 + i, B=B) for i in range(2)]
+        refs = [c_oracle.parse_batch(h, g, n_threads=8) for h in heads]
+        devs = [torch.from_numpy(h).cuda() for h in heads]
+        parser = PoseParser(cfg)
+        totals = [int(sum((r["part_cell"][b, :r["counts"][b, 2]] >= 0).sum() for b in range(B))) for r in refs]
+        for cap in (max(totals) + 7, max(totals) // 2):
+            nbytes, offs = parser.packed_layout(B, cap)
+            n_calls = 9
+            bufs = [torch.full((nbytes,), 0xAB, dtype=torch.uint8, device="cuda") for _ in range(n_calls)]
+            outs = [parser.alloc_output(B) for _ in range(n_calls)]
+            for o in outs:
+                o.part_cell.fill_(-7)
+            torch.cuda.synchronize()
+            for i in range(n_calls):
+                parser.parse(devs[i % 2], out=outs[i], input_complete=(i != 4), dense=bufs[i], cap_entries=cap, skip_slots=skip_slots)
+            torch.cuda.synchronize()
+            for i in range(n_calls):
+                ref, total = refs[i % 2], totals[i % 2]
+                rec = unpack_entries(bufs[i].cpu(), B, cap, offs)
+                want_entries = np.array([(ref["part_cell"][b, :ref["counts"][b, 2]] >= 0).sum() for b in range(B)])
+                assert rec["total"] == total and rec["overflow"] == (total > cap)
+                assert np.array_equal(rec["count"], ref["counts"][:, 2])
+                assert np.array_equal(rec["entries"], want_entries)
+                assert np.array_equal(outs[i].count.cpu().numpy(), ref["counts"][:, 2])
+                spans = []
+                for b in range(B):
+                    if rec["start"][b] + rec["entries"][b] > cap:
+                        continue                                   # dropped: overflow was flagged
+                    spans.append((int(rec["start"][b]), int(rec["start"][b] + rec["entries"][b])))
+                    n = int(ref["counts"][b, 2])
+                    pc, ps, pb = entries_to_packed(rec, b, cfg.K)
+                    assert np.array_equal(pc, ref["part_cell"][b, :n])
+                    assert np.array_equal(bits(ps), bits(ref["part_score"][b, :n]))
+                    assert np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
+                spans.sort()
+                assert all(a[1] <= b2[0] for a, b2 in zip(spans, spans[1:])), "image blocks overlap"
+                if total <= cap:
+                    assert sum(e - s0 for s0, e in spans) == total
+                if not skip_slots:
+                    assert_packed_equals_oracle(outs[i].numpy(), ref, B)
+
+
 def test_bad_arguments_raise():
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PPNConfig

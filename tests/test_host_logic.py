@@ -64,7 +64,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.ppn_abi_version() == 3
+    assert lib.ppn_abi_version() == _lib.ABI_VERSION == 4
     assert b"workspace" in lib.ppn_strerror(-3)
 
 
@@ -134,14 +134,14 @@ def test_dense_entry_layout_host_side():
     nbytes, offs = C.c_size_t(), (C.c_size_t * 4)()
     assert _lib.lib().ppn_packed_bytes(B, cap, C.byref(nbytes), offs) == 0
     offs = tuple(int(o) for o in offs)
-    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and offs[1] >= 4 * (2 + 2 * B)
+    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and offs[1] >= 4 * (2 + 3 * B)
     assert nbytes.value >= offs[3] + cap * 16
     buf = np.zeros(nbytes.value, np.uint8)
     # image 0: humans {0,2} and {0}; image 1: none; image 2: human {0,1,3}
     parts = [0, 2, 0, 0, 1, 3]
     cells = [5, 6, 9, 1, 2, 3]
     count, entries = np.array([2, 0, 1], np.int32), np.array([3, 0, 3], np.int32)
-    buf[0:4 * (2 + 2 * B)].view(np.int32)[:] = np.concatenate([[6, 0], count, entries])
+    buf[0:4 * (2 + 3 * B)].view(np.int32)[:] = np.concatenate([[6, 0], count, entries, [0, 3, 3]])
     buf[offs[1]:offs[1] + 4 * 6].view(np.uint32)[:] = [(p << 16) | c for p, c in zip(parts, cells)]
     buf[offs[2]:offs[2] + 4 * 6].view(np.float32)[:] = np.arange(6, dtype=np.float32) / 8
     rec = unpack_entries(buf, B, cap, offs)
