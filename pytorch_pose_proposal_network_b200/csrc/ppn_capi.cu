@@ -1,6 +1,7 @@
 // C ABI of libppn_decode (declared in include/ppn_decode.h): argument checking, workspace
 // carving, the launch chain of ppn_parse (decode+NMS | limb arg-max -> tree parse), the dense
 // entry packing, and the host-memory entry with overlapped copies.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -266,11 +267,12 @@ int ppn_parse_launches(const PPNShape* shape, const PPNParams* params) {
     if (check_shape(shape) || check_params(shape, params)) return 0;
     if (shape->B <= 0) return 0;
     const ppn::Geom g = make_geom(shape);
-    size_t ring_cap = 0;
+    ppn::FusedSplit split;
     const bool P1 = params->n_nms_parts == 1 && g_tuning.parse_overlap != 1;
-    const bool fused = P1 && (g_tuning.parse_fused < 0 ? ppn::parse_fused_coresident(g, g_tuning.parse_stage_all, g_tuning, &ring_cap)
-                                                       : (g_tuning.parse_fused != 0 && ppn::parse_fused_supported(g, g_tuning.parse_stage_all)));
-    return fused ? 2 : 3;
+    const bool fits = P1 && ppn::parse_fused_split(g, g_tuning.parse_stage_all, g_tuning, &split);
+    const bool fused = P1 && (g_tuning.parse_fused < 0 ? (fits && split.n_sub == 1) : (g_tuning.parse_fused != 0 && ppn::parse_fused_supported(g, g_tuning.parse_stage_all)));
+    if (fused) return 2 * (fits ? split.n_sub : 1);
+    return 3;
 }
 
 int ppn_limb_argmax(const void* head, const PPNShape* shape, uint16_t* amax, void* stream) {
@@ -418,9 +420,12 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
     //    its end for the previous K124, K124 waits for its K3: calls complete in order.
     // Needs n_nms_parts == 1 (the reference's case) and a grid of at most 1024 cells; otherwise, or with
     // ppn_tune("parse.fused", 0), the three-kernel chain below runs.
-    size_t ring_cap = 0;
-    const bool fits_beside = P == 1 && ppn::parse_fused_coresident(g, g_tuning.parse_stage_all, g_tuning, &ring_cap);
-    const bool fused = P == 1 && mode != 1 && (g_tuning.parse_fused < 0 ? fits_beside : (g_tuning.parse_fused != 0 &&
+    ppn::FusedSplit split;
+    const bool fits_beside = P == 1 && ppn::parse_fused_split(g, g_tuning.parse_stage_all, g_tuning, &split);
+    // auto: the two-kernel chain when the whole batch's parse CTAs fit beside the arg-max ring.  A batch that
+    // would have to be cut (dense 16x16 crowds at B = 1024: two sub-batches) measured no better than the
+    // three-kernel chain — there the parse work itself is as long as the arg-max — so it keeps that one.
+    const bool fused = P == 1 && mode != 1 && (g_tuning.parse_fused < 0 ? (fits_beside && split.n_sub == 1) : (g_tuning.parse_fused != 0 &&
                        ppn::parse_fused_supported(g, g_tuning.parse_stage_all)));
     // the dense entry buffer: written by the fused kernel itself (its cursor, header[0..1], is cleared by
     // the arg-max kernel of the same call — nothing but kernels goes on the stream, so the overlapped
@@ -430,30 +435,63 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
     if (fused) {
         using namespace ppn;
         Tuning tuning = g_tuning;
-        if (fits_beside) tuning.argmax_smem_cap = (int)ring_cap;      // leave room for every parse CTA on the SM
+        // A batch whose parse CTAs do not all fit on the SMs beside the arg-max ring is cut into equal
+        // sub-batches that do: K3(0) K124(0) K3(1) K124(1) ... — K3(j+1) streams while sub-batch j is parsed.
+        const int n_sub = fits_beside ? split.n_sub : 1;
+        const int sub_B = fits_beside ? split.sub_B : g.B;
+        const int staged_forced = fits_beside ? (split.staged ? 1 : 0) : -1;
+        if (fits_beside) tuning.argmax_smem_cap = (int)split.ring_cap;      // leave room for every parse CTA on the SM
         const bool overlap_calls = (params->flags & PPN_FLAG_INPUT_COMPLETE) != 0;
         const bool chain = mode == 2 && g_tuning.parse_chain_calls != 0;
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if ((e = cudaStreamIsCapturing(st, &cap)) != cudaSuccess) return (int)e;
         const bool capturing = cap != cudaStreamCaptureStatusNone;
-        // an overlapped K3 may only start beside a fused parse that publishes; after anything else of
-        // ours it starts fully ordered (no launch attribute), which also restarts the chain cleanly
-        const bool k3_attr = chain && (!overlap_calls || capturing || chain_clean(st));
-        bool chained = false;
-        if (ev) cudaEventRecord(ev[0], st);
-        bool zeroed = false;
-        if ((e = launch_limb_argmax(head, amax, g, tuning, st, k3_attr, &chained,
-                                    mode != 2 ? 0 : (overlap_calls ? (PDL_TRIGGER | PDL_WAIT_END) : (PDL_WAIT_START | PDL_TRIGGER)),
-                                    dense_fused ? dense->header : nullptr, &zeroed)) != cudaSuccess) return (int)e;
-        if (dense_fused && !zeroed && (e = cudaMemsetAsync(dense->header, 0, 2 * sizeof(int32_t), st)) != cudaSuccess) return (int)e;
-        if (ev) { cudaEventRecord(ev[1], st); for (int q = 2; q < 7; ++q) cudaEventRecord(ev[q], st); }
-        (void)chained;
-        const bool k124_attr = mode == 2;      // a programmatic dependent of K3 (implicit trigger if K3 is a fallback kernel)
-        if ((e = launch_parse_fused(head, g, ch, params->det_thresh, params->nms_thresh, params->min_num_keypoints, amax,
-                                    out->count, out->root_cell, out->part_cell, out->part_score, out->part_box, out->R, st,
-                                    k124_attr, (overlap_calls && chain && !capturing) ? 2 : 1, g_tuning.parse_stage_all,
-                                    dense_fused ? dense : nullptr)) != cudaSuccess) return (int)e;
-        if (ev) cudaEventRecord(ev[7], st);
+        const size_t es = elem_bytes(shape);
+        const size_t K = (size_t)shape->K, R = (size_t)out->R;
+        auto launch_k3 = [&](int j) -> cudaError_t {
+            Geom gj = g;
+            const int b0 = j * sub_B;
+            gj.B = std::min(sub_B, g.B - b0);
+            // an overlapped K3 may only start beside a fused parse that publishes; after anything else of
+            // ours it starts fully ordered (no launch attribute), which also restarts the chain cleanly.
+            // Inside a call the kernel before K3(j > 0) is this call's own K124(j - 1).
+            const bool attr = chain && (j > 0 || !overlap_calls || capturing || chain_clean(st));
+            const int bits = mode != 2 ? 0 : ((overlap_calls || j > 0) ? (PDL_TRIGGER | PDL_WAIT_END) : (PDL_WAIT_START | PDL_TRIGGER));
+            bool chained = false, zeroed = false;
+            int32_t* zero2 = (dense_fused && j == 0) ? dense->header : nullptr;
+            cudaError_t err = launch_limb_argmax(static_cast<const unsigned char*>(head) + (size_t)b0 * g.img_stride * es,
+                                                 amax + (size_t)b0 * g.E * g.HW, gj, tuning, st, attr, &chained, bits, zero2, &zeroed);
+            if (err == cudaSuccess && zero2 && !zeroed) err = cudaMemsetAsync(dense->header, 0, 2 * sizeof(int32_t), st);
+            return err;
+        };
+        auto launch_k124 = [&](int j) -> cudaError_t {
+            Geom gj = g;
+            const int b0 = j * sub_B;
+            gj.B = std::min(sub_B, g.B - b0);
+            DenseTarget dj;
+            if (dense_fused) { dj = *dense; dj.B_total = g.B; dj.b0 = b0; }
+            return launch_parse_fused(static_cast<const unsigned char*>(head) + (size_t)b0 * g.img_stride * es, gj, ch,
+                                      params->det_thresh, params->nms_thresh, params->min_num_keypoints,
+                                      amax + (size_t)b0 * g.E * g.HW, out->count + b0, out->root_cell + (size_t)b0 * R,
+                                      out->part_cell + (size_t)b0 * R * K, out->part_score + (size_t)b0 * R * K,
+                                      out->part_box + (size_t)b0 * R * K * 4, out->R, st,
+                                      mode == 2 /* a programmatic dependent of K3 (implicit trigger if K3 is a fallback kernel) */,
+                                      (overlap_calls && chain && !capturing) ? 2 : 1, g_tuning.parse_stage_all, staged_forced,
+                                      dense_fused ? &dj : nullptr);
+        };
+        if (ev) {                                      // per-stage events: serial, all arg-max launches, then all parse launches
+            cudaEventRecord(ev[0], st);
+            for (int j = 0; j < n_sub; ++j) if ((e = launch_k3(j)) != cudaSuccess) return (int)e;
+            cudaEventRecord(ev[1], st);
+            for (int q = 2; q < 7; ++q) cudaEventRecord(ev[q], st);
+            for (int j = 0; j < n_sub; ++j) if ((e = launch_k124(j)) != cudaSuccess) return (int)e;
+            cudaEventRecord(ev[7], st);
+        } else {
+            for (int j = 0; j < n_sub; ++j) {
+                if ((e = launch_k3(j)) != cudaSuccess) return (int)e;
+                if ((e = launch_k124(j)) != cudaSuccess) return (int)e;
+            }
+        }
         if (dense && !dense_fused) return pack_after(out, shape, dense, st);
         return PPN_OK;
     }

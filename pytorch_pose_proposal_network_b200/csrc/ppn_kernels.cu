@@ -7,6 +7,7 @@
 //   K4 tree_parse         walk the track orders from every kept root    datatest.py:103-131
 //
 // Launchers at the bottom are called by ppn_capi.cu.
+#include <algorithm>
 #include <mutex>
 
 #include "ppn_kernels.h"
@@ -1195,6 +1196,7 @@ struct DenseOut {
     float4* box;
     int32_t cap;
     int32_t skip_slots;    // 1: the fixed-stride arrays (root_cell, part_*) need not be written; count[] still is
+    int32_t B_total, b0;   // the launch covers images [b0, b0 + gridDim.x) of a batch of B_total (header indexing)
 };
 
 template <bool kStaged, typename HT>
@@ -1404,11 +1406,11 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
         // ---- the image's place in the dense buffer ---------------------------------------------------
         const bool want_dense = dense.header != nullptr;
         if (want_dense && tid == 0) {
-            const int n_ent = ebase_s, B = (int)gridDim.x;
+            const int n_ent = ebase_s, B = dense.B_total, gb = dense.b0 + b;
             const int start = atomicAdd(dense.header, n_ent);
-            dense.header[2 + b] = base_s;
-            dense.header[2 + B + b] = n_ent;
-            dense.header[2 + 2 * B + b] = start;
+            dense.header[2 + gb] = base_s;
+            dense.header[2 + B + gb] = n_ent;
+            dense.header[2 + 2 * B + gb] = start;
             if (start + n_ent > dense.cap) dense.header[1] = 1;
             ebase_s = start + n_ent > dense.cap ? -1 : start;           // -1: the image's entries do not fit
         }
@@ -1469,10 +1471,10 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
             }
         }
     } else if (dense.header != nullptr && tid == 0) {                     // no humans: an empty block
-        const int B = (int)gridDim.x;
-        dense.header[2 + b] = 0;
-        dense.header[2 + B + b] = 0;
-        dense.header[2 + 2 * B + b] = 0;
+        const int B = dense.B_total, gb = dense.b0 + b;
+        dense.header[2 + gb] = 0;
+        dense.header[2 + B + gb] = 0;
+        dense.header[2 + 2 * B + gb] = 0;
     }
     if (tid == 0) h_count[b] = n_keep > 0 ? base_s : 0;
     // ---- the last CTA publishes this call's sequence number ------------------------------------------
@@ -2067,11 +2069,49 @@ cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable&
 }
 
 // ---- fused decode + NMS + tree parse --------------------------------------------------------------
-// Staging delta (K*HW floats) makes every walk step and score a shared-memory read; it is dropped
-// when the CTA would grow beyond 48 KB (big grids walk through L2 instead and stay light enough to
-// sit beside the arg-max ring).  stage_pref: -1 auto, 0 never, >= 1 whenever it fits at all.
+// Staging delta (K*HW floats) makes every walk step and score a shared-memory read; it costs shared
+// memory, i.e. parse CTAs per SM beside the arg-max ring.  stage_pref: -1 auto, 0 never, >= 1 whenever
+// it fits at all.
+//
+// The overlapped chain needs EVERY parse CTA of a launch resident beside one arg-max CTA per SM
+// (threads, registers, shared memory with a ring of at least three 32 KB stages).  A batch too large
+// for that is cut into equal sub-batches that do fit, each with its own arg-max + parse launch pair:
+// sub-batch j+1's arg-max then streams while sub-batch j is parsed, exactly like consecutive calls.
+static int fused_ctas_per_sm(const Geom& g, const Tuning& t, int smem_optin, size_t smem) {
+    const int t124 = g.HW <= 256 ? 256 : 512;
+    // the arg-max CTA: consumer threads + producer warp, 56 registers per thread (ptxas)
+    const int t3 = ((g.dtype == HEAD_F32 ? t.argmax_threads : t.argmax16_threads) + 31) / 32 * 32 + 32;
+    const size_t sm_bytes = (size_t)smem_optin + 1024;             // per SM: the opt-in maximum + one CTA's reserve
+    const size_t min_ring = 3 * 32 * 1024 + 1024;
+    if (smem > (size_t)smem_optin || sm_bytes < min_ring + 1024) return 0;
+    long long n = (2048 - t3) / t124;
+    n = std::min<long long>(n, (65536 - (long long)t3 * 56) / ((long long)t124 * 40));
+    n = std::min<long long>(n, (long long)((sm_bytes - min_ring - 1024) / (smem + 1024)));
+    return n < 0 ? 0 : (int)n;
+}
+
+static bool fused_split_plan(const Geom& g, const Tuning& t, DeviceInfo* d, int stage_pref, FusedSplit* out) {
+    if (g.HW > 1024 || g.B < 1) return false;                      // the NMS bit matrix is built for <= 1024 boxes
+    const size_t with = fused_layout(g, true).total, without = fused_layout(g, false).total;
+    const int cap_with = stage_pref == 0 ? 0 : fused_ctas_per_sm(g, t, d->smem_optin, with) * d->sms;
+    const int cap_without = stage_pref > 0 ? 0 : fused_ctas_per_sm(g, t, d->smem_optin, without) * d->sms;
+    const int n_with = cap_with > 0 ? (g.B + cap_with - 1) / cap_with : 0;
+    const int n_without = cap_without > 0 ? (g.B + cap_without - 1) / cap_without : 0;
+    if (!n_with && !n_without) return false;
+    // fewer launch pairs win; at equal count staged delta (shorter walk chain) if the CTA stays under 48 KB
+    bool staged = n_with && (!n_without || n_with < n_without || (n_with == n_without && (stage_pref > 0 || with <= 48 * 1024)));
+    out->staged = staged;
+    out->smem = staged ? with : without;
+    out->n_sub = staged ? n_with : n_without;
+    out->sub_B = (g.B + out->n_sub - 1) / out->n_sub;
+    const int per_sm = (out->sub_B + d->sms - 1) / d->sms;
+    out->ring_cap = (size_t)d->smem_optin + 1024 - (size_t)per_sm * (out->smem + 1024) - 1024;
+    return true;
+}
+
+// Fallback shape when nothing fits beside a ring: one CTA per image, whatever staging fits at all.
 static bool fused_plan(const Geom& g, int smem_optin, int stage_pref, bool* staged, size_t* smem) {
-    if (g.HW > 1024) return false;                                 // the NMS bit matrix is built for <= 1024 boxes
+    if (g.HW > 1024) return false;
     const size_t with = fused_layout(g, true).total, without = fused_layout(g, false).total;
     bool st = stage_pref < 0 ? with <= 48 * 1024 : (stage_pref > 0 && with <= (size_t)smem_optin);
     if (!st && without > (size_t)smem_optin) return false;
@@ -2088,23 +2128,10 @@ bool parse_fused_supported(const Geom& g, int stage_pref) {
     return fused_plan(g, d->smem_optin, stage_pref, &staged, &smem);
 }
 
-bool parse_fused_coresident(const Geom& g, int stage_pref, const Tuning& t, size_t* ring_cap) {
+bool parse_fused_split(const Geom& g, int stage_pref, const Tuning& t, FusedSplit* out) {
     DeviceInfo* d = nullptr;
-    bool staged;
-    size_t smem = 0;
-    if (device_info(&d) != cudaSuccess || !fused_plan(g, d->smem_optin, stage_pref, &staged, &smem)) return false;
-    const int per_sm = (g.B + d->sms - 1) / d->sms;                        // parse CTAs an SM must hold at once
-    const int t124 = g.HW <= 256 ? 256 : 512;
-    // the arg-max CTA beside them: consumer threads + producer warp, 56 registers per thread (ptxas)
-    const int t3 = ((g.dtype == HEAD_F32 ? t.argmax_threads : t.argmax16_threads) + 31) / 32 * 32 + 32;
-    if (t3 + per_sm * t124 > 2048) return false;
-    if ((size_t)t3 * 56 + (size_t)per_sm * t124 * 40 > 65536) return false;
-    const size_t sm_bytes = (size_t)d->smem_optin + 1024;                  // per SM: the opt-in maximum + one CTA's reserve
-    const size_t taken = (size_t)per_sm * (smem + 1024) + 1024;
-    const size_t min_ring = 2 * 16 * 1024;
-    if (taken + min_ring > sm_bytes) return false;
-    *ring_cap = sm_bytes - taken;
-    return true;
+    if (device_info(&d) != cudaSuccess) return false;
+    return fused_split_plan(g, t, d, stage_pref, out);
 }
 
 size_t parse_fused_smem_bytes(const Geom& g, int stage_pref) {
@@ -2118,7 +2145,7 @@ size_t parse_fused_smem_bytes(const Geom& g, int stage_pref) {
 cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
                                float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
-                               const DenseTarget* dense_to) {
+                               int staged_forced, const DenseTarget* dense_to) {
     if (g.B == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -2126,11 +2153,16 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
     bool staged;
     size_t smem;
     if (!fused_plan(g, d->smem_optin, stage_pref, &staged, &smem)) return cudaErrorInvalidConfiguration;
-    DenseOut dense = {nullptr, nullptr, nullptr, nullptr, 0, 0};
+    if (staged_forced >= 0) {                                      // the caller planned the staging (sub-batches)
+        staged = staged_forced != 0;
+        smem = fused_layout(g, staged).total;
+        if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
+    }
+    DenseOut dense = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
     if (dense_to) {
         if (g.K > 32) return cudaErrorInvalidConfiguration;          // present-part masks are 32 bits
         dense = DenseOut{dense_to->header, dense_to->idcell, dense_to->score, reinterpret_cast<float4*>(dense_to->box),
-                         dense_to->cap, dense_to->skip_slots};
+                         dense_to->cap, dense_to->skip_slots, dense_to->B_total, dense_to->b0};
     }
     // chain_mode 0: plain launch; 1: programmatic dependent that triggers after its wait;
     //            2: overlapped calls — guard, early trigger (see the kernel's header comment)

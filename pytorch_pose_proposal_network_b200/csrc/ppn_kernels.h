@@ -83,16 +83,19 @@ cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable&
 
 // fused decode + NMS + tree parse (n_nms_parts == 1, H*W <= 1024): the whole-path call's second kernel
 bool parse_fused_supported(const Geom& g, int stage_pref);
-// Can every CTA of the fused parse kernel be resident beside one arg-max CTA per SM?  If so, *ring_cap is
-// the shared memory left for the ring on an SM.
-bool parse_fused_coresident(const Geom& g, int stage_pref, const Tuning& t, size_t* ring_cap);
+// How the overlapped two-kernel chain runs a batch: n_sub equal sub-batches of sub_B images, each small enough
+// that all of its parse CTAs are resident beside one arg-max CTA per SM; ring_cap = shared memory left for the
+// arg-max ring on an SM.  false: the fused kernel cannot sit beside a ring at all for this shape.
+struct FusedSplit { int n_sub, sub_B; bool staged; size_t smem, ring_cap; };
+bool parse_fused_split(const Geom& g, int stage_pref, const Tuning& t, FusedSplit* out);
 size_t parse_fused_smem_bytes(const Geom& g, int stage_pref);
-// dense (human, part) entry buffer written by the fused kernel itself (header[0..1] zeroed by the caller)
-struct DenseTarget { int32_t* header; uint32_t* idcell; float* score; float* box; int32_t cap; int32_t skip_slots; };
+// dense (human, part) entry buffer written by the fused kernel itself (header[0..1] cleared by the arg-max kernel)
+struct DenseTarget { int32_t* header; uint32_t* idcell; float* score; float* box; int32_t cap; int32_t skip_slots;
+                     int32_t B_total; int32_t b0; };
 cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
                                float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
-                               const DenseTarget* dense_to = nullptr);
+                               int staged_forced = -1, const DenseTarget* dense_to = nullptr);
 bool chain_clean(cudaStream_t st);      // the stream's last whole-path launch was a (publishing) fused parse
 void chain_break(cudaStream_t st);      // ... was something else: the next overlapped call starts fully ordered
 

@@ -16,9 +16,10 @@ ROUND = "r1"
 rows = [r for r in csv.reader(open(os.path.join(G, f"launches_{ROUND}.csv"))) if len(r) > 5]
 hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-seq = [(r[ki].split("(")[0], float(r[vi])) for r in rows[1:]]
+seq = [(r[ki].split("(")[0].replace("void ", "").split("<")[0], float(r[vi])) for r in rows[1:]]
 ppn = [(n, v) for n, v in seq if n.startswith("ppn::")]
-steps, chunks = ppn[:36], ppn[36:]          # 12 device steps x 3 kernels, then the host-buffer arm's chunks
+per_step = 2 if any("parse_fused" in n for n, _ in ppn) else 3
+steps, chunks = ppn[:12 * per_step], ppn[12 * per_step:]    # 12 device steps, then the host-buffer arm's chunks
 
 
 def table(lst, title):
@@ -35,9 +36,10 @@ def table(lst, title):
 
 out = ["# ncu launch list of `python bench.py --steps 4 --warmup 3 --settle-s 0 --no-cpu-baseline --e2e-steps 1`  (B200, round 1)",
        "# metric gpu__time_duration.sum, --clock-control none.  Under ncu every launch is serialised and cold-cache:",
-       "# compare the SHARES with bench.py's roofline.stage_ms_per_step (K3 60.1 / K12 19.8 / K4 12.7 us -> 65 / 21 / 14 %),",
-       "# not the absolutes.  Raw list: profiles/launches_r1.csv", ""]
-out += table(steps, "## device steps: 12 x ppn_parse on 512 images (warm-up 3+1, timed 4, per-kernel event pass 4)")
+       "# compare the SHARES with bench.py's roofline.stage_ms_per_step (event-bracketed serial pass: K3 62.8 / K124 38.7 us -> 62 / 38 %),",
+       "# not the absolutes.  In the timed region itself the two kernels of consecutive steps overlap (step = 57.7 us).",
+       "# Raw list: profiles/launches_r1.csv", ""]
+out += table(steps, "## device steps: 12 x ppn_parse on 512 images (warm-up 3+1, timed 4, per-kernel event pass 4): arg-max + fused parse")
 out += [""] + table(chunks, "## end-to-end arm: 3 x ppn_parse_host = 24 chunks of 64 images (host buffers, copies overlapped)")
 open(os.path.join(P, f"launches_{ROUND}_summary.txt"), "w").write("\n".join(out) + "\n")
 shutil.copy(os.path.join(G, f"launches_{ROUND}.csv"), os.path.join(P, f"launches_{ROUND}.csv"))
@@ -72,3 +74,25 @@ hot = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_hot.py"
 open(os.path.join(P, f"k3_ncu_stalls_{ROUND}.txt"), "w").write(
     "# limb arg-max kernel (cfg2, 512 images): warp-stall samples per SASS instruction, from `ncu --set full --import-source on`\n" + hot)
 print(hot[:600])
+
+rep2 = os.path.join(G, f"prof_k124_{ROUND}.ncu-rep")
+if os.path.exists(rep2):
+    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    keep = [h for h in hdr if any(s in h for s in want)]
+    idx = [hdr.index(k) for k in keep]
+    with open(os.path.join(P, f"k124_ncu_full_{ROUND}.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(keep)
+        w.writerow([units[i] for i in idx])
+        for r in rows[2:]:
+            w.writerow([r[i] for i in idx])
+    src = subprocess.run(["ncu", "-i", rep2, "--page", "source", "--csv", "--kernel-name", "regex:parse_fused"],
+                         capture_output=True, text=True).stdout
+    open("/tmp/src_k124.csv", "w").write(src)
+    hot = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_hot.py"), "/tmp/src_k124.csv", "20"],
+                         capture_output=True, text=True).stdout
+    open(os.path.join(P, f"k124_ncu_stalls_{ROUND}.txt"), "w").write(
+        "# fused parse kernel (cfg2, 512 images): warp-stall samples per SASS instruction, from `ncu --set full --import-source on`\n" + hot)
+    print(hot[:1500])
