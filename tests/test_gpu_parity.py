@@ -732,6 +732,46 @@ def test_parse_dense_written_by_the_parse_kernel(fused, skip_slots):
                     assert_packed_equals_oracle(outs[i].numpy(), ref, B)
 
 
+def test_two_kernel_chain_cut_into_sub_batches():
+    """A batch whose parse CTAs do not all fit beside the arg-max ring (16x16 grid, 700 images) forced onto
+    the two-kernel chain: it is cut into two sub-batches (4 launches), with and without the dense entry
+    buffer, overlapped and not — results as the oracle's."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser, entries_to_packed, unpack_entries
+    cfg = PRESETS["cfg3"]()
+    g = O.Geometry.of(cfg)
+    B = 700
+    head = synth.make_head(g, "D", seed=321, B=B)
+    ref = c_oracle.parse_batch(head, g, n_threads=8)
+    dev = torch.from_numpy(head).cuda()
+    _lib.tune(parse_fused=1)
+    try:
+        parser = PoseParser(cfg)
+        assert parser.launches_per_parse(B) == 4 and parser.launches_per_parse(500) == 2
+        total = int(sum((ref["part_cell"][b, :ref["counts"][b, 2]] >= 0).sum() for b in range(B)))
+        nbytes, offs = parser.packed_layout(B, total + 5)
+        outs = [parser.alloc_output(B) for _ in range(4)]
+        bufs = [torch.zeros(nbytes, dtype=torch.uint8, device="cuda") for _ in range(4)]
+        torch.cuda.synchronize()
+        for i in range(4):
+            parser.parse(dev, out=outs[i], input_complete=(i != 2), dense=bufs[i] if i % 2 else None, cap_entries=total + 5)
+        torch.cuda.synchronize()
+        for i in range(4):
+            assert_packed_equals_oracle(outs[i].numpy(), ref, B)
+        for i in (1, 3):
+            rec = unpack_entries(bufs[i].cpu(), B, total + 5, offs)
+            assert rec["total"] == total and not rec["overflow"]
+            assert np.array_equal(rec["count"], ref["counts"][:, 2])
+            for b in range(0, B, 7):
+                n = int(ref["counts"][b, 2])
+                pc, ps, pb = entries_to_packed(rec, b, cfg.K)
+                assert np.array_equal(pc, ref["part_cell"][b, :n])
+                assert np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
+    finally:
+        _lib.tune(parse_fused=-1)
+
+
 def test_bad_arguments_raise():
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PPNConfig
