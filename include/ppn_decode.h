@@ -203,6 +203,33 @@ int ppn_parse_dense(const void* head, const PPNShape* shape, const PPNParams* pa
                     void* packed, size_t packed_bytes, int32_t cap_entries, int32_t skip_slots,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the inverse of the parser: training targets from annotations ------------------------------
+ * Replaces the "# Encode samples" half of KeypointsDataset.__getitem__ (dataset.py:89-198) for a whole
+ * batch.  People of image b are rows [person_off[b], person_off[b+1]) of the four arrays, in the
+ * reference's post-transform types (aug.py:138-160): bbox float64 (cx, cy, w, h), keypoints fp32
+ * (x, y) of parts 1..K-1, visible 0/1 bytes, size float64 (side of a part's box).  All DEVICE pointers. */
+typedef struct PPNPeople {
+    const int32_t* person_off;  /* [B + 1]                                                          */
+    const double*  bbox;        /* [n, 4]                                                           */
+    const float*   keypoints;   /* [n, K - 1, 2]                                                    */
+    const uint8_t* visible;     /* [n, K - 1]                                                       */
+    const double*  size;        /* [n]                                                              */
+} PPNPeople;
+
+/* The ten grids __getitem__ returns after the image (dataset.py:198), batched, fp32, caller-owned
+ * device memory: [B, K, H, W] each, except weight_ij and te: [B, E, sH, sW, H, W]. */
+typedef struct PPNTargets {
+    float *delta, *weight, *weight_ij, *tx, *ty, *tx_half, *ty_half, *tw, *th, *te;
+} PPNTargets;
+
+/* edges: HOST array [E][2] of (source part, target part) (config.py:65 EDGES).  Every output element is
+ * written (no pre-zeroing needed).  Same arithmetic as the reference (fp32 cell division and offsets,
+ * float64 size division rounded once), people applied in order (later ones overwrite).  Like the
+ * reference's window slicing (dataset.py:163-167) it needs an odd square limb window:
+ * PPN_E_UNSUPPORTED otherwise. */
+int ppn_encode_targets(const PPNPeople* people, const PPNShape* shape, const int32_t* edges,
+                       const PPNTargets* out, void* stream);
+
 /* Per-stage timing of ppn_parse for benchmarks.  After ppn_profile_enable(1) every ppn_parse
  * call (up to 4096) records CUDA events on its stream at the stage boundaries;
  * ppn_profile_read() waits for them and returns the summed milliseconds of the four stages

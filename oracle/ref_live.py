@@ -121,3 +121,44 @@ def reference_pred_frames(fnames, humans_list, scores_list):
     finally:
         dt.eval_helpers.load_data = saved
     raise RuntimeError("the reference did not reach eval_helpers.load_data")
+
+
+def reference_encode_targets(samples, insize, outsize, local_grid_size, keypoint_names, edges):
+    """Run the reference's own ``KeypointsDataset.__getitem__`` (dataset.py:70-198), unmodified, on
+    prepared samples and return its target lists.
+
+    ``samples``: list of dicts as the reference's transform pipeline hands them to the encoder
+    (aug.py:138-160): 'keypoints' torch fp32 [n, K-1, 2], 'bbox' torch float64 [n, 4] (cx, cy, w, h),
+    'is_visible' list of bool arrays [K-1], 'size' list of floats, 'image' anything.  The dataset object
+    is created without its __init__ (which only reads the annotation JSON and uses the removed
+    ``np.bool``, dataset.py:53); image reading is stubbed; the ``transform`` hook returns the prepared
+    sample.  Everything after "# Encode samples" (dataset.py:89) is the reference's code as it lies.
+    """
+    load()
+    import numpy as np
+    ds_mod = importlib.import_module("dataset")
+    ds = object.__new__(ds_mod.KeypointsDataset)
+    names = [f"{i:04d}.jpg" for i in range(len(samples))]
+    ds.filename_list = names
+    ds.root_dir = ""
+    ds.draw = False
+    ds.data = {n: ([np.zeros((len(keypoint_names) - 1, 2), np.float32)], [], [], []) for n in names}
+    ds.insize, ds.outsize = tuple(insize), tuple(outsize)
+    ds.keypoint_names, ds.local_grid_size, ds.edges = list(keypoint_names), tuple(local_grid_size), [list(e) for e in edges]
+    ds.inW, ds.inH = insize
+    ds.outW, ds.outH = outsize
+    ds.gridW, ds.gridH = int(ds.inW / ds.outW), int(ds.inH / ds.outH)
+    by_name = dict(zip(names, samples))
+    current = {}
+    ds.transform = lambda sample: by_name[current["name"]]
+    saved = ds_mod.io.imread
+    ds_mod.io.imread = lambda path: np.zeros((2, 2, 3), np.uint8)
+    out = []
+    try:
+        for i, n in enumerate(names):
+            current["name"] = n
+            item = ds[i]
+            out.append([t.numpy().copy() for t in item[1:]])      # drop the image
+    finally:
+        ds_mod.io.imread = saved
+    return out          # per sample: [delta, weight, weight_ij, tx, ty, tx_half, ty_half, tw, th, te]

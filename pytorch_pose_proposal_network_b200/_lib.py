@@ -38,6 +38,18 @@ class PPNHumans(C.Structure):
                 ("part_score", C.c_void_p), ("part_box", C.c_void_p), ("R", C.c_int32)]
 
 
+class PPNPeople(C.Structure):
+    _fields_ = [("person_off", C.c_void_p), ("bbox", C.c_void_p), ("keypoints", C.c_void_p),
+                ("visible", C.c_void_p), ("size", C.c_void_p)]
+
+
+TARGET_NAMES = ("delta", "weight", "weight_ij", "tx", "ty", "tx_half", "ty_half", "tw", "th", "te")
+
+
+class PPNTargets(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in TARGET_NAMES]
+
+
 # name -> (restype, argtypes); must list every function of include/ppn_decode.h
 EXPORTS = {
     "ppn_abi_version": (C.c_int, []),
@@ -64,6 +76,7 @@ EXPORTS = {
     "ppn_pack_humans": (C.c_int, [C.POINTER(PPNHumans), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ppn_parse_dense": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.POINTER(PPNParams), C.POINTER(PPNHumans),
                                   C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ppn_encode_targets": (C.c_int, [C.POINTER(PPNPeople), C.POINTER(PPNShape), i32p, C.POINTER(PPNTargets), C.c_void_p]),
     "ppn_profile_enable": (C.c_int, [C.c_int32]),
     "ppn_profile_read": (C.c_int, [f32p, i32p]),
     "ppn_tune": (C.c_int, [C.c_char_p, C.c_int32]),

@@ -585,6 +585,39 @@ int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_e
                                            reinterpret_cast<float*>(p + l.box), (cudaStream_t)stream));
 }
 
+int ppn_encode_targets(const PPNPeople* people, const PPNShape* shape, const int32_t* edges,
+                       const PPNTargets* out, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (!people || !out) return PPN_E_BADARG;
+    if (shape->sH != shape->sW || (shape->sH & 1) == 0) return PPN_E_UNSUPPORTED;      // dataset.py:163-167
+    if (shape->B == 0) return PPN_OK;
+    if (!people->person_off || !out->delta || !out->weight || !out->tx || !out->ty || !out->tx_half || !out->ty_half ||
+        !out->tw || !out->th) return PPN_E_BADARG;
+    if (shape->E > 0 && (!edges || !out->te || !out->weight_ij)) return PPN_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(out->te) & 15) || (reinterpret_cast<uintptr_t>(out->weight_ij) & 15)) return PPN_E_BADARG;
+    ppn::EncodeArgs a;
+    std::memset(&a, 0, sizeof(a));
+    for (int e = 0; e < shape->E; ++e) {
+        const int s = edges[2 * e], t = edges[2 * e + 1];
+        if (s < 0 || s >= shape->K || t < 0 || t >= shape->K) return PPN_E_CHAINS;
+        a.edges.src[e] = (uint8_t)s;
+        a.edges.dst[e] = (uint8_t)t;
+    }
+    a.person_off = people->person_off; a.bbox = people->bbox; a.keypoints = people->keypoints;
+    a.visible = people->visible; a.size = people->size;
+    a.delta = out->delta; a.weight = out->weight; a.weight_ij = out->weight_ij; a.tx = out->tx; a.ty = out->ty;
+    a.tx_half = out->tx_half; a.ty_half = out->ty_half; a.tw = out->tw; a.th = out->th; a.te = out->te;
+    a.K = shape->K; a.E = shape->E; a.H = shape->H; a.W = shape->W; a.sH = shape->sH; a.sW = shape->sW;
+    a.gridW = (float)shape->gridW; a.gridH = (float)shape->gridH;
+    a.inW = (double)shape->inW; a.inH = (double)shape->inH;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    return cuda_rc(ppn::launch_encode_targets(a, shape->B, sms, (cudaStream_t)stream));
+}
+
 int ppn_profile_enable(int32_t on) {
     if (on && !g_prof.ev) {
         g_prof.ev = new cudaEvent_t[(size_t)kMaxProfiled * (2 * kStages)];

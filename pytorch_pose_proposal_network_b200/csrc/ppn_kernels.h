@@ -99,4 +99,20 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
 bool chain_clean(cudaStream_t st);      // the stream's last whole-path launch was a (publishing) fused parse
 void chain_break(cudaStream_t st);      // ... was something else: the next overlapped call starts fully ordered
 
+// ---- training-target encoder (ppn_encode.cu) ----------------------------------------------------------
+struct EdgeTable { uint8_t src[256]; uint8_t dst[256]; };
+struct EncodeArgs {
+    const int32_t* person_off;      // [B + 1]
+    const double* bbox;             // [n, 4] cx, cy, w, h
+    const float* keypoints;         // [n, K - 1, 2]
+    const uint8_t* visible;         // [n, K - 1]
+    const double* size;             // [n]
+    float *delta, *weight, *weight_ij, *tx, *ty, *tx_half, *ty_half, *tw, *th, *te;
+    int32_t K, E, H, W, sH, sW, rows_per_cta;
+    float gridW, gridH;
+    double inW, inH;
+    EdgeTable edges;
+};
+cudaError_t launch_encode_targets(EncodeArgs a, int B, int sms, cudaStream_t st);
+
 }  // namespace ppn
