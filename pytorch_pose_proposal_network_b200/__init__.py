@@ -7,7 +7,9 @@ Public surface:
 * :class:`PoseParser` — batched device entry: ``parser.parse(out)`` on the raw head tensor;
 * :mod:`.datatest` — drop-in ``get_humans_by_feature`` / ``non_maximum_suppression`` /
   ``restore_xy`` / ``restore_size`` with the reference's signatures;
-* :mod:`.sharded` — image-sharded multi-GPU driver (one process per GPU, NCCL gather of poses).
+* :mod:`.sharded` — image-sharded multi-GPU driver (one process per GPU, NCCL gather of poses);
+* :mod:`.dataset` — :class:`TargetEncoder`: the reference's training-target encoder (dataset.py:89-198) as one
+  kernel launch per batch.
 
 All compute happens in ``libppn_decode.so`` (hand-written sm_100a CUDA behind a C ABI, see
 ``include/ppn_decode.h``); there is no CPU or PyTorch fallback.

@@ -609,6 +609,7 @@ int ppn_encode_targets(const PPNPeople* people, const PPNShape* shape, const int
     a.delta = out->delta; a.weight = out->weight; a.weight_ij = out->weight_ij; a.tx = out->tx; a.ty = out->ty;
     a.tx_half = out->tx_half; a.ty_half = out->ty_half; a.tw = out->tw; a.th = out->th; a.te = out->te;
     a.K = shape->K; a.E = shape->E; a.H = shape->H; a.W = shape->W; a.sH = shape->sH; a.sW = shape->sW;
+    a.magic_sW = shape->sW <= 1 ? 0u : (uint32_t)(((1ull << 32) + shape->sW - 1) / shape->sW);
     a.gridW = (float)shape->gridW; a.gridH = (float)shape->gridH;
     a.inW = (double)shape->inW; a.inH = (double)shape->inH;
     int dev = 0, sms = 0;

@@ -99,24 +99,35 @@ encode_targets_kernel(EncodeArgs a) {
     const int r0 = z * a.rows_per_cta, r1 = min(rows, r0 + a.rows_per_cta);
     const size_t big = (size_t)b * rows * HW;
     const int oh = a.sH / 2, ow = a.sW / 2;
-    if ((HW & 3) == 0 && (a.W & 3) == 0) {
-        // four cells of one grid row per thread, 128-bit streaming stores
-        const int HW4 = HW >> 2;
-        for (int i = tid; i < (r1 - r0) * HW4; i += T) {
-            const int r = r0 + i / HW4, c = (i - (r - r0) * HW4) << 2;
-            const int ei = r / S, w_at = r - ei * S, dy = w_at / a.sW, dx = w_at - dy * a.sW;
-            const unsigned char* ds = s_delta + a.edges.src[ei] * HW;
-            const unsigned char* dt = s_delta + a.edges.dst[ei] * HW;
-            const int h = c / a.W, w = c - h * a.W, hh = h + dy - oh;
-            float v[4];
+    if ((HW & 3) == 0 && (a.W & 3) == 0 && (HW >> 2) <= T) {
+        // A thread keeps ONE group of four cells (of one grid row) and walks down the rows of the CTA's
+        // range, RL rows apart: its cell coordinates are computed once, the (limb, dy, dx) of a row by an
+        // increment and one multiply-high — no integer division in the loop — and both big tensors get one
+        // 128-bit streaming store per step.
+        const int HW4 = HW >> 2, RL = T / HW4;
+        const int lane_r = tid / HW4, c = (tid - lane_r * HW4) << 2;
+        if (lane_r < RL) {
+            const int h = c / a.W, w = c - h * a.W;
+            int r = r0 + lane_r;
+            int ei = r / S, wa = r - ei * S;
+            for (; r < r1; r += RL) {
+                const int dy = a.magic_sW ? (int)__umulhi((unsigned)wa, a.magic_sW) : wa, dx = wa - dy * a.sW;
+                const uint32_t ds4 = *reinterpret_cast<const uint32_t*>(s_delta + a.edges.src[ei] * HW + c);   // four source cells
+                const unsigned char* dt = s_delta + a.edges.dst[ei] * HW;
+                const int hh = h + dy - oh, w0 = w + dx - ow;
+                const bool row_in = hh >= 0 && hh < a.H;
+                float v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int ww = w + q + dx - ow;
-                const bool on = ds[c + q] || (hh >= 0 && hh < a.H && ww >= 0 && ww < a.W && dt[hh * a.W + ww]);
-                v[q] = on ? 1.0f : 0.0005f;                              // dataset.py:154-175
+                for (int q = 0; q < 4; ++q) {
+                    const int ww = w0 + q;
+                    const bool on = ((ds4 >> (8 * q)) & 0xffu) || (row_in && ww >= 0 && ww < a.W && dt[hh * a.W + ww]);
+                    v[q] = on ? 1.0f : 0.0005f;                          // dataset.py:154-175
+                }
+                __stcs(reinterpret_cast<float4*>(a.weight_ij + big + (size_t)r * HW + c), make_float4(v[0], v[1], v[2], v[3]));
+                __stcs(reinterpret_cast<float4*>(a.te + big + (size_t)r * HW + c), make_float4(0.f, 0.f, 0.f, 0.f));
+                wa += RL;
+                while (wa >= S) { wa -= S; ++ei; }
             }
-            __stcs(reinterpret_cast<float4*>(a.weight_ij + big + (size_t)r * HW + c), make_float4(v[0], v[1], v[2], v[3]));
-            __stcs(reinterpret_cast<float4*>(a.te + big + (size_t)r * HW + c), make_float4(0.f, 0.f, 0.f, 0.f));
         }
     } else {
         for (int i = tid; i < (r1 - r0) * HW; i += T) {

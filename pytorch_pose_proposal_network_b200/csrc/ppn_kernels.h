@@ -109,6 +109,7 @@ struct EncodeArgs {
     const double* size;             // [n]
     float *delta, *weight, *weight_ij, *tx, *ty, *tx_half, *ty_half, *tw, *th, *te;
     int32_t K, E, H, W, sH, sW, rows_per_cta;
+    uint32_t magic_sW;              // ceil(2^32 / sW) for exact x / sW, 0 <= x < 65536 (0 when sW == 1)
     float gridW, gridH;
     double inW, inH;
     EdgeTable edges;
