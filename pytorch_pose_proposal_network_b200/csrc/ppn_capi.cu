@@ -227,6 +227,8 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "parse.fused")) t.parse_fused = value < 0 ? -1 : (value != 0);
     else if (!std::strcmp(key, "parse.threads")) t.parse_threads = value;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
+    else if (!std::strcmp(key, "encode.sweep")) t.encode_sweep = value != 0;
+    else if (!std::strcmp(key, "encode.ctas_per_sm")) t.encode_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
     else return PPN_E_BADARG;
     return PPN_OK;
 }
@@ -250,6 +252,8 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "parse.fused")) *value = t.parse_fused;
     else if (!std::strcmp(key, "parse.threads")) *value = t.parse_threads;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
+    else if (!std::strcmp(key, "encode.sweep")) *value = t.encode_sweep;
+    else if (!std::strcmp(key, "encode.ctas_per_sm")) *value = t.encode_ctas_per_sm;
     else return PPN_E_BADARG;
     return PPN_OK;
 }
@@ -609,6 +613,8 @@ int ppn_encode_targets(const PPNPeople* people, const PPNShape* shape, const int
     a.delta = out->delta; a.weight = out->weight; a.weight_ij = out->weight_ij; a.tx = out->tx; a.ty = out->ty;
     a.tx_half = out->tx_half; a.ty_half = out->ty_half; a.tw = out->tw; a.th = out->th; a.te = out->te;
     a.K = shape->K; a.E = shape->E; a.H = shape->H; a.W = shape->W; a.sH = shape->sH; a.sW = shape->sW;
+    a.sweep = g_tuning.encode_sweep;
+    a.sweep_ctas_per_sm = g_tuning.encode_ctas_per_sm;
     a.magic_sW = shape->sW <= 1 ? 0u : (uint32_t)(((1ull << 32) + shape->sW - 1) / shape->sW);
     a.gridW = (float)shape->gridW; a.gridH = (float)shape->gridH;
     a.inW = (double)shape->inW; a.inH = (double)shape->inH;

@@ -19,6 +19,8 @@
 //   tx   = x / gridW - ix            fp32 subtraction                     dataset.py:132
 //   tw   = w / inW                   float64 division, rounded to fp32 on the store   dataset.py:134
 // People are applied in order, so a later person overwrites an earlier one's cell values (dataset.py:108).
+#include <algorithm>
+
 #include "ppn_kernels.h"
 
 namespace ppn {
@@ -94,6 +96,7 @@ encode_targets_kernel(EncodeArgs a) {
         }
     }
 
+    if (a.small_only) return;                         // the two limb tensors come from encode_sweep_kernel
     // ---- this CTA's rows of te (zeros) and weight_ij, each element written once -------------------------
     const int rows = a.E * S;
     const int r0 = z * a.rows_per_cta, r1 = min(rows, r0 + a.rows_per_cta);
@@ -157,9 +160,99 @@ encode_targets_kernel(EncodeArgs a) {
     }
 }
 
+// The two limb tensors, swept in ADDRESS ORDER by a persistent grid.  A tile is a run of window rows of one
+// (image, limb): tiles are numbered in memory order and CTA c takes tiles c, c + grid, ..., so at any moment
+// the resident CTAs write one contiguous window of each tensor (a few tens of MB) — the access pattern of a
+// plain fill, which is what DRAM write-back wants (with one CTA per (image, half of the rows) there were
+// ~1 800 slow write streams spread over the whole tensors: 4.4 TB/s; a fill reaches 6.9).  Per tile the CTA
+// rebuilds just the two delta planes it needs (the limb's source and target part) from the image's people.
+__global__ void __launch_bounds__(256)
+encode_sweep_kernel(EncodeArgs a, int B, int chunks, int rows_per_tile) {
+    extern __shared__ __align__(16) unsigned char s_planes[];              // [2][HW]: delta of the source / target part
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int HW = a.H * a.W, S = a.sH * a.sW, HW4 = HW >> 2, RL = T / HW4;
+    const int lane_r = tid / HW4, c = (tid - lane_r * HW4) << 2;
+    const int h = c / a.W, w = c - h * a.W;
+    const int oh = a.sH / 2, ow = a.sW / 2;
+    unsigned char* ds = s_planes;
+    unsigned char* dt = s_planes + HW;
+    const long long n_tiles = (long long)B * a.E * chunks;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int ch = (int)(t % chunks);
+        const long long be = t / chunks;
+        const int ei = (int)(be % a.E), b = (int)(be / a.E);
+        const int p0 = a.person_off[b], n_p = a.person_off[b + 1] - p0;
+        const int ks = a.edges.src[ei], kt = a.edges.dst[ei];
+        __syncthreads();                                                   // the previous tile's planes are dead
+        for (int i = tid; i < (2 * HW) >> 2; i += T) reinterpret_cast<uint32_t*>(s_planes)[i] = 0u;
+        __syncthreads();
+        for (int i = tid; i < 2 * n_p; i += T) {
+            const int p = i >> 1, which = i & 1;
+            const EncPoint q = enc_point(a, p0 + p, which ? kt : ks);
+            if (q.labeled && q.iy >= 0 && q.iy < a.H && q.ix >= 0 && q.ix < a.W) s_planes[which * HW + q.iy * a.W + q.ix] = 1;
+        }
+        __syncthreads();
+        const int wa0 = ch * rows_per_tile, wa1 = min(S, wa0 + rows_per_tile);   // window positions of this tile
+        const size_t base = ((size_t)b * a.E + ei) * S * HW;
+        if (lane_r < RL) {
+            const uint32_t ds4 = *reinterpret_cast<const uint32_t*>(ds + c);       // the four source cells: same for every row
+            for (int wa = wa0 + lane_r; wa < wa1; wa += RL) {
+                const int dy = a.magic_sW ? (int)__umulhi((unsigned)wa, a.magic_sW) : wa, dx = wa - dy * a.sW;
+                const int hh = h + dy - oh, w0 = w + dx - ow;
+                const bool row_in = hh >= 0 && hh < a.H;
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ww = w0 + q;
+                    const bool on = ((ds4 >> (8 * q)) & 0xffu) || (row_in && ww >= 0 && ww < a.W && dt[hh * a.W + ww]);
+                    v[q] = on ? 1.0f : 0.0005f;                              // dataset.py:154-175
+                }
+                __stcs(reinterpret_cast<float4*>(a.weight_ij + base + (size_t)wa * HW + c), make_float4(v[0], v[1], v[2], v[3]));
+                __stcs(reinterpret_cast<float4*>(a.te + base + (size_t)wa * HW + c), make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        }
+        __syncthreads();                              // the zeros of this tile are ordered before its ones
+        for (int p = tid; p < n_p; p += T) {          // dataset.py:137-152
+            const EncPoint s = enc_point(a, p0 + p, ks);
+            if (!s.labeled) continue;
+            const EncPoint q = enc_point(a, p0 + p, kt);
+            if (!q.labeled) continue;
+            if (s.iy < 0 || s.ix < 0 || s.iy >= a.H || s.ix >= a.W) continue;
+            const long long jy = (long long)q.iy - s.iy + oh, jx = (long long)q.ix - s.ix + ow;
+            if (jy < 0 || jx < 0 || jy >= a.sH || jx >= a.sW) continue;
+            const int wa = (int)jy * a.sW + (int)jx;
+            if (wa >= wa0 && wa < wa1) a.te[base + (size_t)wa * HW + s.iy * a.W + s.ix] = 1.0f;
+        }
+    }
+}
+
 cudaError_t launch_encode_targets(EncodeArgs a, int B, int sms, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
     const int rows = a.E * a.sH * a.sW;
+    const int HW = a.H * a.W, S = a.sH * a.sW;
+    const size_t smem_small = ((size_t)a.K * HW + 15) & ~(size_t)15;
+    if (a.sweep && rows > 0 && (HW & 3) == 0 && (a.W & 3) == 0 && (HW >> 2) <= 256 && (size_t)2 * HW <= 48 * 1024) {
+        // vector shapes: the [K, H, W] grids by one small launch, the limb tensors by the address-ordered sweep
+        EncodeArgs small = a;
+        small.small_only = 1;
+        if (smem_small > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(encode_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
+            if (e != cudaSuccess) return e;
+        }
+        encode_targets_kernel<<<dim3(B, 1), 256, smem_small, st>>>(small);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        // tiles of about 48 KB per tensor, whole rows
+        int rows_per_tile = (48 * 1024) / (HW * 4);
+        if (rows_per_tile < 1) rows_per_tile = 1;
+        if (rows_per_tile > S) rows_per_tile = S;
+        const int chunks = (S + rows_per_tile - 1) / rows_per_tile;
+        rows_per_tile = (S + chunks - 1) / chunks;
+        const long long n_tiles = (long long)B * a.E * chunks;
+        const int grid = (int)std::min<long long>(n_tiles, (long long)sms * a.sweep_ctas_per_sm);
+        encode_sweep_kernel<<<grid, 256, (size_t)2 * HW, st>>>(a, B, chunks, rows_per_tile);
+        return cudaGetLastError();
+    }
     // enough CTAs to fill the machine a few times over; every CTA rebuilds the image's byte map (cheap)
     int Z = (4 * sms + B - 1) / B;
     if (Z < 1) Z = 1;

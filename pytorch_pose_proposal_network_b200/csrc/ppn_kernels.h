@@ -23,6 +23,8 @@ struct Tuning {
                                        // CTAs fit on the SMs beside the arg-max ring), 0 never (three kernels), 1 whenever supported
     int parse_chain_calls = 1;         // PDL chain: the first kernel of a call is a programmatic dependent too
     int host_chunk_images = 64;
+    int encode_sweep = 1;              // target encoder: limb tensors by the address-ordered persistent sweep (0: one CTA per image part)
+    int encode_ctas_per_sm = 6;
     int parse_overlap = 2;             // 0 serial; 1 decode+NMS on a side stream beside the arg-max;
                                        // 2 one stream, programmatic dependent launches (PDL chain)
 };
@@ -109,6 +111,7 @@ struct EncodeArgs {
     const double* size;             // [n]
     float *delta, *weight, *weight_ij, *tx, *ty, *tx_half, *ty_half, *tw, *th, *te;
     int32_t K, E, H, W, sH, sW, rows_per_cta;
+    int32_t small_only, sweep, sweep_ctas_per_sm;   // launcher state / tuning (encode.sweep, encode.ctas_per_sm)
     uint32_t magic_sW;              // ceil(2^32 / sW) for exact x / sW, 0 <= x < 65536 (0 when sW == 1)
     float gridW, gridH;
     double inW, inH;

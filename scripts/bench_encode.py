@@ -22,12 +22,16 @@ ap.add_argument("--config", default="cfg2")
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--people", type=int, default=4)
 ap.add_argument("--iters", type=int, default=50)
+ap.add_argument("--sweep", type=int, default=1)
+ap.add_argument("--ctas", type=int, default=6)
 a = ap.parse_args()
 cfg = PRESETS[a.config]()
 K, B = cfg.K, a.batch
 rng = np.random.default_rng(0)
 raw = [encode_gt.random_people(rng, a.people, K, cfg.insize) for _ in range(B)]
 samples = [dict(keypoints=kp, bbox=bb, is_visible=vis, size=size) for kp, bb, vis, size in raw]
+from pytorch_pose_proposal_network_b200 import _lib  # noqa: E402
+_lib.tune(encode_sweep=a.sweep, encode_ctas_per_sm=a.ctas)
 enc = TargetEncoder(cfg)
 flat = [torch.from_numpy(x).cuda() for x in flatten_samples(samples, K)]
 outs = [enc.alloc(B) for _ in range(3)]                       # rotate: each set is larger than L2 at the default size
@@ -62,7 +66,7 @@ t0 = time.perf_counter()
 for kp, bb, vis, size in raw[:n_cpu]:
     encode_gt.encode_targets(kp, bb, vis, size, K, edges, cfg.insize, cfg.outsize, cfg.local_grid_size)
 cpu_ms = (time.perf_counter() - t0) * 1e3 / n_cpu
-print(json.dumps({"op": "ppn_encode_targets", "config": a.config, "images": B, "people_per_image": a.people,
+print(json.dumps({"op": "ppn_encode_targets", "config": a.config, "images": B, "people_per_image": a.people, "sweep": a.sweep, "ctas_per_sm": a.ctas,
                   "ms_per_batch": med, "images_per_s": B / (med * 1e-3), "bytes_written": bytes_out,
                   "achieved_gbs": bytes_out / (med * 1e-3) / 1e9, "peak_gbs": peak, "torch_fill_of_the_two_limb_tensors_ms": fill_ms,
                   "torch_fill_gbs": B * 2 * cfg.E * cfg.S * cfg.HW * 4 / (fill_ms * 1e-3) / 1e9, "frac_of_copy_peak": bytes_out / (med * 1e-3) / 1e9 / peak,

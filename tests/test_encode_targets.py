@@ -100,9 +100,18 @@ def _encoder(meta):
     return TargetEncoder(cfg)
 
 
+@pytest.fixture(params=[1, 0], ids=["sweep", "per_image"])
+def sweep(request):
+    """Both ways of writing the two limb tensors: the address-ordered persistent sweep and one CTA per image part."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    _lib.tune(encode_sweep=request.param)
+    yield request.param
+    _lib.tune(encode_sweep=1)
+
+
 @gpu
 @pytest.mark.parametrize("name", cases())
-def test_gpu_encoder_matches_reference_outputs(name):
+def test_gpu_encoder_matches_reference_outputs(name, sweep):
     meta, fx, want = load(name)
     enc = _encoder(meta)
     dev = [torch.from_numpy(np.ascontiguousarray(fx[k])).cuda() for k in ("person_off", "bbox", "keypoints", "visible", "size")]
@@ -117,7 +126,7 @@ def test_gpu_encoder_matches_reference_outputs(name):
 
 @gpu
 @pytest.mark.parametrize("seed", range(6))
-def test_gpu_encoder_matches_restatement_random(seed):
+def test_gpu_encoder_matches_restatement_random(seed, sweep):
     """Fresh annotation sets in the reference's sample format through TargetEncoder.encode: crowded cells
     (later people overwrite earlier ones), points outside the image on every side, empty images, batch sizes
     around the CTA-splitting thresholds, grids whose width is not a multiple of four (scalar store path)."""

@@ -5,6 +5,7 @@ fp32 boxes / scores (the spec allows 1e-5 relative; the kernels reproduce numpy'
 the tests demand 0 ulp).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -770,6 +771,51 @@ def test_two_kernel_chain_cut_into_sub_batches():
                 assert np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
     finally:
         _lib.tune(parse_fused=-1)
+
+
+def _gatherer_worker(rank, port, tmp):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1")
+    import torch.distributed as dist
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser, entries_to_packed
+    from pytorch_pose_proposal_network_b200.sharded import PoseGatherer
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        cfg = PPNConfig.mpii16()
+        g = O.Geometry.of(cfg)
+        B, steps, gs = 48, 11, 4                                   # 2 full groups + a partial one
+        heads = [synth.make_head(g, "U", seed=40 + i, B=B) for i in range(3)]
+        refs = [c_oracle.parse_batch(h, g, n_threads=4) for h in heads]
+        devs = [torch.from_numpy(h).cuda() for h in heads]
+        parser = PoseParser(cfg)
+        gat = PoseGatherer(parser, B, cap_entries=B * 120, group_steps=gs)
+        outs = [parser.alloc_output(B) for _ in range(2)]
+        for i in range(steps):
+            gat.parse(devs[i % 3], out=outs[i % 2], input_complete=True)
+        gat.finish()
+        torch.cuda.synchronize()
+        ok = True
+        for i in range(((steps - 1) // gs - 1) * gs, steps):       # the two most recent groups are still held
+            rec, ref = gat.records_of(0, step_back=gat.step - 1 - i), refs[i % 3]
+            ok &= not rec["overflow"] and np.array_equal(rec["count"], ref["counts"][:, 2])
+            for b in range(0, B, 5):
+                n = int(ref["counts"][b, 2])
+                pc, ps, pb = entries_to_packed(rec, b, cfg.K)
+                ok &= np.array_equal(pc, ref["part_cell"][b, :n]) and np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
+        open(os.path.join(tmp, "ok" if ok else "bad"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pose_gatherer_single_rank_nccl(tmp_path):
+    """sharded.PoseGatherer.parse end to end on one GPU (NCCL group of one): dense records written by the
+    parse kernel into rotating group buffers, async all_gather per group, partial last group flushed."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + 17
+    mp.spawn(_gatherer_worker, args=(port, str(tmp_path)), nprocs=1, join=True)
+    assert os.listdir(tmp_path) == ["ok"]
 
 
 def test_bad_arguments_raise():
