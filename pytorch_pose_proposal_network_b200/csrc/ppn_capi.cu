@@ -217,6 +217,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.threads")) t.argmax_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) t.argmax_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
     else if (!std::strcmp(key, "argmax.split")) t.argmax_split = value;
+    else if (!std::strcmp(key, "argmax.cluster")) t.argmax_cluster = value;
     else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value != 0;
     else if (!std::strcmp(key, "argmax16.threads")) t.argmax16_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
@@ -242,6 +243,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.threads")) *value = t.argmax_threads;
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) *value = t.argmax_ctas_per_sm;
     else if (!std::strcmp(key, "argmax.split")) *value = t.argmax_split;
+    else if (!std::strcmp(key, "argmax.cluster")) *value = t.argmax_cluster;
     else if (!std::strcmp(key, "parse.overlap")) *value = t.parse_overlap;
     else if (!std::strcmp(key, "argmax.tail_opt")) *value = t.argmax_tail_opt;
     else if (!std::strcmp(key, "argmax16.threads")) *value = t.argmax16_threads;

@@ -517,6 +517,115 @@ limb_argmax_ldg_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
     }
 }
 
+// Tiny batches (the reference's own deployment: one webcam frame at a time, rt_test.py:181-189): there
+// are fewer matrices than SMs, so a matrix per CTA would leave most of the GPU idle and make the call's
+// latency the time ONE SM needs to pull a whole matrix (1 MB at the native shape, ~20 us).  Here a
+// thread-block CLUSTER of C CTAs shares one matrix: CTA r reduces rows [r*S/C, (r+1)*S/C) to a partial
+// (max, index) per column in its shared memory, the cluster synchronises, and CTA 0 merges the C
+// partials straight out of its peers' shared memory (distributed shared memory) — no workspace, no
+// second launch.  Ties across CTAs go to the lower row, NaNs to the first one, like the in-CTA merge.
+template <typename T> struct Vec4Of;
+template <> struct Vec4Of<float> { using type = float4; };
+template <> struct Vec4Of<__half> { using type = uint2; };
+template <> struct Vec4Of<__nv_bfloat16> { using type = uint2; };
+__device__ __forceinline__ void widen4(const float4 r, float* v, float) { v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w; }
+__device__ __forceinline__ void widen4(const uint2 r, float* v, __half) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void widen4(const uint2 r, float* v, __nv_bfloat16) {
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a shared-memory address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void* p, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ Partial ld_dsmem_partial(uint32_t addr) {
+    Partial o;
+    asm volatile("ld.shared::cluster.v2.b32 {%0, %1}, [%2];" : "=f"(o.v), "=r"(o.i) : "r"(addr) : "memory");
+    return o;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ amax, Geom g, int CV, int G, int pdl,
+                           int32_t* __restrict__ zero2) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    Partial* part = reinterpret_cast<Partial*>(smem);                    // [G][HW]; row 0 ends up as the CTA's result
+    using V4 = typename Vec4Of<T>::type;
+    const int tid = threadIdx.x;
+    const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
+    const int m = blockIdx.x / C;
+    if (pdl & PDL_WAIT_START) pdl_wait();
+    if (zero2 && blockIdx.x == 0 && tid == 0) { zero2[0] = 0; zero2[1] = 0; }
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();
+    const int b = m / g.E, ei = m - b * g.E;
+    const V4* src = reinterpret_cast<const V4*>(head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW);
+    const int r_lo = (int)((long long)g.S * rank / C), r_hi = (int)((long long)g.S * (rank + 1) / C);
+    const bool active = tid < CV * G;
+    const int grp = tid / CV, cv = tid - grp * CV;
+    if (active) {
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int idx[4] = {r_lo, r_lo, r_lo, r_lo};                           // an empty row range must never win a tie
+        constexpr int U = 8;                                             // 128 B per thread in flight: latency is all there is here
+        int r = r_lo + grp;
+#pragma unroll 1
+        for (; r + (U - 1) * G < r_hi; r += U * G) {
+            V4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) raw[u] = __ldg(src + (size_t)(r + u * G) * CV + cv);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float v[4];
+                widen4(raw[u], v, T());
+#pragma unroll
+                for (int q = 0; q < 4; ++q) argmax_step(best[q], idx[q], v[q], r + u * G);
+            }
+        }
+        for (; r < r_hi; r += G) {
+            float v[4];
+            widen4(__ldg(src + (size_t)r * CV + cv), v, T());
+#pragma unroll
+            for (int q = 0; q < 4; ++q) argmax_step(best[q], idx[q], v[q], r);
+        }
+        Partial* row = part + (size_t)grp * g.HW + 4 * cv;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) row[q] = Partial{best[q], idx[q]};
+    }
+    __syncthreads();
+    for (int c = tid; c < g.HW; c += blockDim.x) {                       // the CTA's own result in part[0][c]
+        Partial bestp = part[c];
+        for (int q = 1; q < G; ++q) {
+            const Partial o = part[(size_t)q * g.HW + c];
+            if (argmax_beats(o.v, o.i, bestp.v, bestp.i)) bestp = o;
+        }
+        part[c] = bestp;
+    }
+    cluster_sync_all();
+    if (rank == 0) {
+        uint16_t* dst = amax + (size_t)m * g.HW;
+        for (int c = tid; c < g.HW; c += blockDim.x) {
+            Partial bestp = part[c];
+            for (uint32_t q = 1; q < C; ++q) {
+                const Partial o = ld_dsmem_partial(dsmem_addr(&part[c], q));
+                if (argmax_beats(o.v, o.i, bestp.v, bestp.i)) bestp = o;
+            }
+            dst[c] = (uint16_t)bestp.i;
+        }
+    }
+    cluster_sync_all();                                                   // peers' shared memory stays alive until CTA 0 has read it
+    if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
+}
+
 // Any shape (H*W not a multiple of 4, huge grids): one thread per column, scalar loads.
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1617,6 +1726,15 @@ pack_entries_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
 // =========================================================================================
 // launchers
 // =========================================================================================
+// run `...` with T bound to the head tensor's element type
+#define PPN_DISPATCH_HEAD(dtype, ...)                                                        \
+    switch (dtype) {                                                                         \
+        case HEAD_F32: { using T = float; __VA_ARGS__; } break;                              \
+        case HEAD_F16: { using T = __half; __VA_ARGS__; } break;                             \
+        case HEAD_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break;                     \
+        default: return cudaErrorInvalidValue;                                               \
+    }
+
 // Per-stream device words (the only memory the library ever allocates: 2 KB per device, on the
 // first launch — so make the first call outside stream capture):
 //   [0..3] two {next ticket, finished CTAs} pairs of the ring kernels, used ALTERNATELY by successive
@@ -1629,7 +1747,7 @@ constexpr int kSlotWords = 8;
 struct StreamSlot { cudaStream_t stream = nullptr; unsigned launches = 0; int published = 0; bool fast_open = false; };
 struct DeviceInfo { int* tickets = nullptr; StreamSlot slot[kTicketSlots]; int slots_used = 0;
                     int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, tma16[2] = {0, 0}, decode_nms[3] = {0, 0, 0}, ldg = 0, nms = 0,
-                           tree[3] = {0, 0, 0}, tree_light[3] = {0, 0, 0}, fused[2][3] = {{0, 0, 0}, {0, 0, 0}}; };
+                           tree[3] = {0, 0, 0}, tree_light[3] = {0, 0, 0}, fused[2][3] = {{0, 0, 0}, {0, 0, 0}}, cluster[3] = {0, 0, 0}; };
 static DeviceInfo g_dev[64];
 
 // Properties and per-kernel dynamic-shared-memory opt-ins are per device; one process normally
@@ -1847,6 +1965,57 @@ static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const G
     return cudaGetLastError();
 }
 
+// Cluster kernel for tiny batches: taken when the matrices would occupy at most half of the SMs with one CTA
+// each (argmax.cluster: -1 auto, 0 never, n > 1 forces clusters of n).
+static cudaError_t try_launch_argmax_cluster(const void* head_v, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
+                                             bool pdl, int pdl_bits, DeviceInfo* d, int32_t* zero2, bool* done) {
+    *done = false;
+    const int n_mats = g.B * g.E;
+    if (t.argmax_cluster == 0 || t.argmax_variant != 0 || (g.HW & 3) != 0) return cudaSuccess;
+    const size_t es = g.dtype == HEAD_F32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(head_v) & (4 * es - 1)) || (g.img_stride * es) % (4 * es) || (g.limb_off * es) % (4 * es)) return cudaSuccess;
+    int C = t.argmax_cluster > 1 ? t.argmax_cluster : 0;
+    if (!C) {
+        if (n_mats * 2 > d->sms) return cudaSuccess;
+        C = 8;
+        while (C > 1 && n_mats * C > d->sms) C >>= 1;
+    }
+    while (C > 1 && g.S / C < 2) C >>= 1;
+    if (C < 2 || C > 8 || (C & (C - 1))) return cudaSuccess;
+    const int CV = g.HW / 4;
+    if (CV > 1024) return cudaSuccess;
+    const int rows = (g.S + C - 1) / C;
+    int G = 1024 / CV;                                 // as many row groups as a CTA holds: the CTA's share in flight at once
+    if (G < 1) G = 1;
+    if (G > (rows + 1) / 2) G = (rows + 1) / 2;        // at least two rows per group
+    if (G < 1) G = 1;
+    while (G > 1 && CV * G > 1024) --G;
+    const int threads = std::max(64, ((CV * G + 31) / 32) * 32);
+    const size_t smem = (size_t)G * g.HW * sizeof(Partial);
+    if (smem > (size_t)d->smem_optin) return cudaSuccess;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_mats * C));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 2 : 1;
+    cudaError_t e = cudaSuccess;
+    PPN_DISPATCH_HEAD(g.dtype, {
+        if ((e = ensure_smem(limb_argmax_cluster_kernel<T>, smem, &d->cluster[g.dtype])) != cudaSuccess) return e;
+        e = cudaLaunchKernelEx(&cfg, limb_argmax_cluster_kernel<T>, static_cast<const T*>(head_v), amax, g, CV, G, pdl_bits, zero2);
+    });
+    if (e == cudaSuccess) *done = true;
+    return e;
+}
+
 cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g, const Tuning& t, cudaStream_t st,
                                bool pdl, bool* pdl_used, int pdl_bits, int32_t* zero2, bool* zeroed) {
     if (pdl_used) *pdl_used = false;
@@ -1857,6 +2026,16 @@ cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g
     if (e != cudaSuccess) return e;
     const int n_mats = g.B * g.E;
     if (n_mats == 0) return cudaSuccess;
+    {
+        bool done = false;
+        e = try_launch_argmax_cluster(head_v, amax, g, t, st, pdl, pdl_bits, d, zero2, &done);
+        if (e != cudaSuccess) return e;
+        if (done) {
+            if (pdl_used) *pdl_used = pdl;
+            if (zeroed) *zeroed = zero2 != nullptr;
+            return cudaSuccess;
+        }
+    }
     if (g.dtype == HEAD_F16)
         return launch_limb_argmax16(static_cast<const __half*>(head_v), amax, g, t, st, pdl, pdl_used, pdl_bits, d, &d->tma16[0], zero2, zeroed);
     if (g.dtype == HEAD_BF16)
@@ -1913,15 +2092,6 @@ cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g
     limb_argmax_generic_kernel<float><<<grid, 256, 0, st>>>(head, amax, g);
     return cudaGetLastError();
 }
-
-// run `...` with T bound to the head tensor's element type
-#define PPN_DISPATCH_HEAD(dtype, ...)                                                        \
-    switch (dtype) {                                                                         \
-        case HEAD_F32: { using T = float; __VA_ARGS__; } break;                              \
-        case HEAD_F16: { using T = __half; __VA_ARGS__; } break;                             \
-        case HEAD_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break;                     \
-        default: return cudaErrorInvalidValue;                                               \
-    }
 
 cudaError_t launch_decode_candidates(const void* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
                                      float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st) {

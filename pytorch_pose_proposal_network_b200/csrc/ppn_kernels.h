@@ -13,6 +13,8 @@ struct Tuning {
     int argmax_split = -1;             // -1 auto, 0 = groups split rows, 1 = groups take one matrix each
     int argmax_dynamic = 1;            // ring kernels draw work from a global ticket counter (0: static round-robin)
     int argmax_tail_opt = 0;           // split-matrix mode: pick matrices/item that fills the last wave best
+    int argmax_cluster = -1;           // tiny batches: a cluster of CTAs per matrix, partials merged through distributed
+                                       // shared memory.  -1 auto (matrices <= half the SMs), 0 never, 2/4/8 forced
     int argmax_smem_cap = 0;           // > 0: the ring may use at most this much shared memory (set per call by ppn_parse
                                        // so that the fused parse kernel's CTAs fit beside it on every SM)
     int argmax16_threads = 320;        // 16-bit heads: their own ring shape (rows are half as long, so an item

@@ -538,6 +538,40 @@ def test_argmax_sixteen_bit_special_values(dtype, grid, window):
         assert np.array_equal(got, want), (stage_bytes, stages, threads)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("preset,B,cluster", [("cfg2", 1, -1), ("cfg2", 3, -1), ("native", 1, -1), ("native", 2, 4), ("cfg4", 1, 8),
+                                             ("cfg2", 2, 2), ("cfg3", 5, 8)])
+def test_limb_argmax_cluster_kernel_tiny_batches(preset, B, cluster, dtype):
+    """Tiny batches take the thread-block-cluster kernel (C CTAs per matrix, partials merged through
+    distributed shared memory): same arg-max map as numpy's, ties across CTAs and NaNs included, and the
+    whole path on top of it."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    head = torch.from_numpy(synth.make_head(g, "U", seed=70 + B, B=B)).to(dtype)
+    e = head[:, 6 * g.K:].view(B, g.E, g.S, g.H * g.W)
+    e[0, 0, :, 0] = 0.5                                  # a whole column of ties: row 0 must win across all CTAs
+    e[0, 0, g.S // 2:, 1] = 2.0                          # tie that starts in a later CTA's rows
+    e[0, 1, g.S - 1, 2] = float("nan")                   # NaN in the last CTA's rows
+    e[0, 1, 1, 3] = float("nan"); e[0, 1, g.S - 2, 3] = float("nan")     # two NaNs: the first one wins
+    up = head.float().numpy()
+    want = up[:, 6 * g.K:].reshape(B, g.E, g.S, g.H, g.W).argmax(2).astype(np.uint16)
+    _lib.tune(argmax_cluster=cluster)
+    try:
+        parser = PoseParser(cfg)
+        got = parser.limb_argmax(head.cuda()).cpu().numpy()
+        assert np.array_equal(got, want)
+        clean = torch.from_numpy(synth.make_head(g, "U", seed=90 + B, B=B)).to(dtype)
+        ref = c_oracle.parse_batch(clean.float().numpy(), g, n_threads=4)
+        for _ in range(3):
+            packed = parser.parse(clean.cuda(), input_complete=True)
+        assert_packed_equals_oracle(packed.numpy(), ref, B)
+    finally:
+        _lib.tune(argmax_cluster=-1)
+
+
 # ------------------------------------------------------------------------------------------
 # edge cases of the parse (KAT-3)
 # ------------------------------------------------------------------------------------------
