@@ -1346,6 +1346,11 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
         __syncthreads();
     }
     if (pdl & FUSED_TRIGGER_EARLY) pdl_launch_dependents();
+    // resp and conf of every part are read below anyway (delta staging / the walk): ask the L2 for them now,
+    // as one contiguous read, so that those loads find them there instead of each paying a DRAM round trip
+    if (tid == 0 && ((size_t)2 * g.K * g.HW * sizeof(HT)) % 16 == 0 && (g.img_stride * sizeof(HT)) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(head) & 15) == 0)
+        bulk_prefetch_l2(head + (size_t)blockIdx.x * g.img_stride, (uint32_t)2 * g.K * g.HW * (uint32_t)sizeof(HT));
 
     // ---- prologue 1: root candidates of part 0, compacted into shared memory (datatest.py:80-92) ----
     if (tid == 0) { base_s = 0; n_keep_s = 0; }
@@ -1589,13 +1594,12 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
     // ---- the last CTA publishes this call's sequence number ------------------------------------------
     if (pdl & FUSED_PUBLISH) {
         __syncthreads();
-        if (tid == 0) {
+        // (what a later kernel must not overtake are this kernel's READS of the arg-max map, and those are
+        //  long consumed here — no fence per CTA; the one before the flag orders the counter reset)
+        if (tid == 0 && atomicAdd(sync + 1, 1) == (int)gridDim.x - 1) {
+            sync[1] = 0;
             __threadfence();
-            if (atomicAdd(sync + 1, 1) == (int)gridDim.x - 1) {
-                sync[1] = 0;
-                __threadfence();
-                atomicMax(sync, seq + 1);
-            }
+            atomicMax(sync, seq + 1);
         }
     }
 }
@@ -1985,8 +1989,9 @@ static cudaError_t try_launch_argmax_cluster(const void* head_v, uint16_t* amax,
     const int CV = g.HW / 4;
     if (CV > 1024) return cudaSuccess;
     const int rows = (g.S + C - 1) / C;
-    int G = 1024 / CV;                                 // as many row groups as a CTA holds: the CTA's share in flight at once
-    if (G < 1) G = 1;
+    int G = 512 / CV;                                  // CTAs of at most 512 threads: two fit on an SM, so that 17 clusters of 8
+    if (G < 1) G = 1;                                  // (native shape, one image) are resident at once — with 1024-thread CTAs
+                                                       // the last cluster found no free GPC and ran as a second wave (16.7 -> 20.8 us)
     if (G > (rows + 1) / 2) G = (rows + 1) / 2;        // at least two rows per group
     if (G < 1) G = 1;
     while (G > 1 && CV * G > 1024) --G;
