@@ -712,10 +712,14 @@ restore_size_kernel(const float* __restrict__ w, const float* __restrict__ h, fl
 // K2 — greedy IoU NMS, one CTA per box list, everything in shared memory
 // =========================================================================================
 // 1. rank sort by (score desc, index desc) — keys are unique, so the rank is a permutation;
-// 2. upper-triangle suppression bitmask: bit j of row i says "kept box i suppresses later box j";
-// 3. one warp scans in order, 32 candidates at a time: the serial dependency lives in the 32x32
-//    diagonal block (kept in registers), the rows of the boxes kept in that block are then OR-ed
-//    into the per-lane `removed` words.
+// 2. the boxes are visited 32 at a time.  Inside a block of 32 the serial dependency is resolved by one
+//    warp from the block's 32x32 DIAGONAL suppression bits (built up front, in parallel, for all blocks);
+// 3. only the boxes a block KEEPS are then tested against the later blocks (all warps, one warp per
+//    (kept box, later block of 32), the word is a ballot) and OR-ed into the `removed` words.
+// A box that is suppressed never suppresses anything (datatest.py:143-152), so its row of the n x n
+// suppression matrix is never needed: with m survivors of n boxes this evaluates ~ m*n/2 + 16n pairs
+// instead of n*n/2 (the first version built the whole upper triangle: 3-5x the work at the BASELINE
+// shapes, 22 KB of shared memory for it at 576 boxes against 2.4 KB now).
 __device__ __forceinline__ unsigned long long score_key(float s, int idx) {
     unsigned u = __float_as_uint(s);
     u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // monotone map of fp32 order
@@ -728,17 +732,14 @@ struct NmsSmem {
     float* sarea;                 // [stride]
     int32_t* sidx;                // [stride] index into the unsorted list
     int32_t* rank;                // [stride] rank accumulators of the split counting sort
-    unsigned* mask;               // upper triangle of the n x n bit matrix, see tri_row()
+    unsigned* diag;               // [stride] bit t of diag[i]: box i suppresses box 32*(i/32) + t (t > i % 32)
+    unsigned* rem;                // [32] removed set, one word per block of 32 boxes
+    int32_t* ctl;                 // [36] {kept mask of the current block, survivors so far, done, -, kept list[32]}
 };
 
-// The suppression matrix only has bits j > i.  Row i of 32-row block k = i / 32 stores the words
-// wj = k .. Wd-1 (Wd - k of them), rows packed block after block: half the shared memory of the
-// square layout (21.9 KB instead of 41.5 KB at 576 boxes), which is what lets this kernel sit
-// beside the arg-max ring on the same SM.
-__device__ __forceinline__ int tri_block_base(int k, int Wd) { return 32 * (k * Wd - ((k * (k - 1)) >> 1)); }
-__device__ __forceinline__ int tri_row(int i, int Wd) {          // offset of word (i, wj = i / 32)
-    const int k = i >> 5;
-    return tri_block_base(k, Wd) + (i - (k << 5)) * (Wd - k);
+__host__ __device__ inline size_t nms_bytes_per_list(int stride) {
+    return (size_t)stride * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float) + 2 * sizeof(int32_t) + sizeof(unsigned)) +
+           (32 + 36) * sizeof(int32_t);
 }
 
 __device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int stride) {
@@ -748,7 +749,9 @@ __device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int stride) {
     s.sarea = reinterpret_cast<float*>(s.key + stride);
     s.sidx = reinterpret_cast<int32_t*>(s.sarea + stride);
     s.rank = s.sidx + stride;
-    s.mask = reinterpret_cast<unsigned*>(s.rank + stride);
+    s.diag = reinterpret_cast<unsigned*>(s.rank + stride);
+    s.rem = s.diag + stride;
+    s.ctl = reinterpret_cast<int32_t*>(s.rem + 32);
     return s;
 }
 
@@ -769,19 +772,13 @@ __device__ __forceinline__ bool suppresses_finite(const float4 tested, float are
 
 // Whole CTA.  Precondition: s.key[0..n) holds the keys of the n unsorted boxes `ubox` (global or
 // shared), s.rank[0..n) is zero, and a __syncthreads() has made both visible.  Writes
-// out[pos] = map ? map[idx] : idx for the kept boxes in visiting order and returns their number
-// (valid in warp 0 only).
-//   1. counting sort by key: every box's rank = number of larger keys, the key range split over
-//      T/n threads per box;  2. suppression bitmask, one WARP per (row i, 32-column word): lane t
-//      tests pair (i, 32*wj + t) and the word is the ballot;  3. one warp scans in visiting order,
-//      32 boxes at a time: the serial dependency lives in the 32x32 diagonal block (registers,
-//      fully unrolled), then the rows of the boxes kept in that block are OR-ed into the per-lane
-//      `removed` words with independent shared-memory loads.
+// out[pos] = map ? map[idx] : idx for the kept boxes in visiting order and returns their number (in
+// every thread).  n <= 1024.
 __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, int n, float thr, int limit,
                                         int32_t* __restrict__ out, const int32_t* map) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = T >> 5;
     const int Wd = (n + 31) >> 5;
-    // ---- 1. rank -------------------------------------------------------------------------
+    // ---- 1. rank: every box's rank = number of larger keys, the key range split over T/n threads per box
     int split = T / n;
     split = split < 1 ? 1 : (split > 8 ? 8 : split);
     const int chunk = (n + split - 1) / split;
@@ -803,72 +800,84 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         s.sarea[r] = box_area(bx);
         s.sidx[r] = i;
     }
+    if (tid < 32) s.rem[tid] = 0u;
     const bool any_nan = __syncthreads_or(has_nan);
-    // ---- 2. mask -------------------------------------------------------------------------
     const bool thr_pos = thr > 0.0f;
+    // ---- 2. diagonal blocks: one warp per box i, lanes = the boxes of i's own block of 32 -----------------
     for (int i = warp; i < n; i += n_warps) {
         const float4 bi = s.sbox[i];
         const float ai = s.sarea[i];
-        unsigned* mrow = s.mask + tri_row(i, Wd) - (i >> 5);     // mrow[wj] = word (i, wj), wj >= i / 32
-        for (int wj = i >> 5; wj < Wd; ++wj) {
-            const int j = (wj << 5) + lane;
-            bool bit = false;
-            if (j > i && j < n) {
-                const float4 bj = s.sbox[j];
-                bit = any_nan ? suppresses(bj, s.sarea[j], bi, ai, thr, thr_pos)
-                              : suppresses_finite(bj, s.sarea[j], bi, ai, thr, thr_pos);
-            }
-            const unsigned word = __ballot_sync(0xffffffffu, bit);
-            if (lane == 0) mrow[wj] = word;
+        const int j = (i & ~31) + lane;
+        bool bit = false;
+        if (j > i && j < n) {
+            const float4 bj = s.sbox[j];
+            bit = any_nan ? suppresses(bj, s.sarea[j], bi, ai, thr, thr_pos)
+                          : suppresses_finite(bj, s.sarea[j], bi, ai, thr, thr_pos);
         }
+        const unsigned word = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) s.diag[i] = word;
     }
     __syncthreads();
-    if (tid >= 32) return 0;
-    // ---- 3. scan -------------------------------------------------------------------------
-    unsigned removed = 0;            // lane l holds word l of the removed set (n <= 1024)
+    // ---- 3. block by block: warp 0 resolves the block, everybody tests its survivors against the rest ------
     int m = 0;
-    bool done = false;
-    for (int w = 0; w < Wd && !done; ++w) {
-        unsigned cur = __shfl_sync(0xffffffffu, removed, w);
+    for (int w = 0; w < Wd; ++w) {
         const int i0 = w << 5;
-        const int nb = min(32, n - i0);
-        const unsigned valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        const int row_len = Wd - w;                               // words per row in this block
-        const unsigned* blk = s.mask + tri_block_base(w, Wd);     // blk[t * row_len + (l - w)] = word (i0 + t, l)
-        const unsigned diag = (lane < nb) ? blk[lane * row_len] : 0u;
-        unsigned kept = 0;
+        if (warp == 0) {
+            unsigned cur = s.rem[w];
+            const int nb = min(32, n - i0);
+            const unsigned valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            const unsigned diag = (lane < nb) ? s.diag[i0 + lane] : 0u;
+            unsigned kept = 0;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            const unsigned d = __shfl_sync(0xffffffffu, diag, t);
-            const unsigned take = (~cur >> t) & 1u;
-            kept |= take << t;
-            cur |= d & (0u - take);
-        }
-        kept &= valid;
-        if (limit > 0 && m + __popc(kept) >= limit) {      // datatest.py:154-155
-            int need = limit - m;
-            unsigned trimmed = 0;
-            for (unsigned rest = kept; need > 0 && rest; --need) { const unsigned low = rest & (0u - rest); trimmed |= low; rest ^= low; }
-            kept = trimmed;
-            done = true;
-        }
-        if ((kept >> lane) & 1u) {
-            const int idx = s.sidx[i0 + lane];
-            out[m + __popc(kept & ((1u << lane) - 1u))] = map ? map[idx] : idx;
-        }
-        m += __popc(kept);
-        if (lane > w && lane < Wd) {
-            const unsigned* row = blk + (lane - w);
-            unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll
-            for (int t = 0; t < 32; t += 4) {
-                if ((kept >> t) & 1u) a0 |= row[t * row_len];
-                if ((kept >> (t + 1)) & 1u) a1 |= row[(t + 1) * row_len];
-                if ((kept >> (t + 2)) & 1u) a2 |= row[(t + 2) * row_len];
-                if ((kept >> (t + 3)) & 1u) a3 |= row[(t + 3) * row_len];
+            for (int t = 0; t < 32; ++t) {
+                const unsigned d = __shfl_sync(0xffffffffu, diag, t);
+                const unsigned take = (~cur >> t) & 1u;
+                kept |= take << t;
+                cur |= d & (0u - take);
             }
-            removed |= (a0 | a1) | (a2 | a3);
+            kept &= valid;
+            bool done = false;
+            if (limit > 0 && m + __popc(kept) >= limit) {      // datatest.py:154-155
+                int need = limit - m;
+                unsigned trimmed = 0;
+                for (unsigned rest = kept; need > 0 && rest; --need) { const unsigned low = rest & (0u - rest); trimmed |= low; rest ^= low; }
+                kept = trimmed;
+                done = true;
+            }
+            if ((kept >> lane) & 1u) {
+                const int idx = s.sidx[i0 + lane];
+                const int pos = __popc(kept & ((1u << lane) - 1u));
+                out[m + pos] = map ? map[idx] : idx;
+                s.ctl[4 + pos] = lane;                            // the block's survivors, in order
+            }
+            if (lane == 0) { s.ctl[0] = (int)kept; s.ctl[1] = m + __popc(kept); s.ctl[2] = done || w == Wd - 1; }
         }
+        __syncthreads();
+        const unsigned kept = (unsigned)s.ctl[0];
+        m = s.ctl[1];
+        if (s.ctl[2]) break;                                      // uniform: limit reached or last block
+        const int n_later = Wd - w - 1, n_kept = __popc(kept);
+        // (survivor, later block) pairs over the warps without a division: with many later blocks every warp
+        // takes its own blocks and runs through all survivors, otherwise every warp takes its own survivors
+        const bool by_block = n_later >= n_warps;
+        for (int ki = by_block ? 0 : warp; ki < n_kept; ki += by_block ? 1 : n_warps) {
+            const int i = i0 + s.ctl[4 + ki];
+            const float4 bi = s.sbox[i];
+            const float ai = s.sarea[i];
+            for (int wj = w + 1 + (by_block ? warp : 0); wj < Wd; wj += by_block ? n_warps : 1) {
+                const int j = (wj << 5) + lane;
+                // a box already removed needs no further test (a stale read of `rem` only costs work)
+                bool bit = false;
+                if (j < n && !((s.rem[wj] >> lane) & 1u)) {
+                    const float4 bj = s.sbox[j];
+                    bit = any_nan ? suppresses(bj, s.sarea[j], bi, ai, thr, thr_pos)
+                                  : suppresses_finite(bj, s.sarea[j], bi, ai, thr, thr_pos);
+                }
+                const unsigned word = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0 && word) atomicOr(&s.rem[wj], word);
+            }
+        }
+        __syncthreads();
     }
     return m;
 }
@@ -896,7 +905,7 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
 // leaves the kernel is the list of surviving root CELLS in visiting order.  All six values of a
 // cell are loaded up front so the CTA pays one HBM round trip.
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 3)
 decode_nms_kernel(const T* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
                   int32_t* __restrict__ keep_cell, int32_t* __restrict__ keep_count, int pdl) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1274,9 +1283,7 @@ __host__ __device__ inline FusedSmem fused_layout(const Geom& g, bool staged) {
     l.dyx = off;   off += g.S <= 2048 ? (uint32_t)g.S * 4u : 0u;
     off = (off + 15u) & ~15u;
     l.uni = off;                                               // NMS scratch, later reused by the walk
-    const uint32_t Wd = ((uint32_t)g.HW + 31u) / 32u;
-    const uint32_t nms = (uint32_t)g.HW * 16u + (((uint32_t)g.HW + 3u) & ~3u) * 4u +
-                         (uint32_t)g.HW * (16u + 8u + 4u + 4u + 4u) + (32u * Wd * (Wd + 1u) / 2u) * 4u;
+    const uint32_t nms = (uint32_t)g.HW * 16u + (((uint32_t)g.HW + 3u) & ~3u) * 4u + (uint32_t)nms_bytes_per_list(g.HW);
     l.amax = l.uni;
     l.slot = l.amax + ((((uint32_t)g.E * g.HW * 2u) + 15u) & ~15u);
     l.estart = l.slot + (uint32_t)g.HW * 4u;
@@ -2121,11 +2128,7 @@ cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float
     return cudaGetLastError();
 }
 
-size_t nms_smem_bytes(int stride) {
-    const size_t Wd = (stride + 31) / 32;
-    const size_t words = 32 * Wd * (Wd + 1) / 2;                  // upper triangle, whole 32-row blocks
-    return (size_t)stride * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float) + 2 * sizeof(int32_t)) + words * sizeof(unsigned);
-}
+size_t nms_smem_bytes(int stride) { return nms_bytes_per_list(stride); }
 
 cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
                        float thr, int limit, int32_t* keep_idx, int32_t* keep_count, cudaStream_t st) {
