@@ -240,8 +240,12 @@ int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
 /* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
  * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
  * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
- * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "parse.chain_calls", "parse.threads", "parse.stage_all" (-1 auto, 0 none, 1 resp+conf, 2 all six groups),
- * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images".  Returns PPN_E_BADARG for an unknown key. */
+ * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "argmax16.threads", "argmax16.stage_bytes" (ring shape
+ * for 16-bit heads), "argmax.cluster" (tiny batches: -1 auto, 0 never, 2/4/8 = CTAs per matrix),
+ * "parse.fused" (-1 auto, 0 three-kernel chain, 1 two-kernel chain whenever supported, cutting large batches),
+ * "parse.chain_calls", "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
+ * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images",
+ * "encode.sweep" (1 = address-ordered persistent sweep), "encode.ctas_per_sm".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);
 int ppn_tune_get(const char* key, int32_t* value);
 
