@@ -17,6 +17,9 @@
  *                            rt_test.py:109-133 / main.py:946-972 do per image after model(image)
  *   ppn_parse_host ......... the same from host memory (the reference's numpy arrays), with the
  *                            copies the reference's `.cpu()` calls stand for done here in reverse
+ *   ppn_parse_dense ........ ppn_parse that also emits dense (human, part) records (what a multi-GPU job gathers)
+ *   ppn_encode_targets ..... the inverse of the path: the "# Encode samples" half of
+ *                            KeypointsDataset.__getitem__, dataset.py:89-198, for a whole batch
  *
  * Conventions
  *   - plain C: pointers and sizes only; no CUDA or torch types.  `stream` is a cudaStream_t
@@ -24,7 +27,7 @@
  *   - every function returns int: 0 = ok, > 0 = a cudaError_t value, < 0 = a PPN_E_* code;
  *     ppn_strerror() turns either into text.  Nothing throws across the boundary.
  *   - device entry points only ENQUEUE work on `stream`; they never synchronise and never
- *     allocate (one exception: 512 bytes of work counters per device on the very first launch).  The caller owns every buffer (torch tensors in the Python host layer) and
+ *     allocate (one exception: 2 KB of work counters per device on the very first launch).  The caller owns every buffer (torch tensors in the Python host layer) and
  *     selects the device (cudaSetDevice / torch.cuda.set_device) before calling.
  *   - thread-safe for distinct streams and buffers; no global mutable state except the
  *     tuning table set by ppn_tune() (meant for benchmarking, set once before use).
