@@ -36,8 +36,8 @@ def table(lst, title):
 
 out = ["# ncu launch list of `python bench.py --steps 4 --warmup 3 --settle-s 0 --no-cpu-baseline --e2e-steps 1`  (B200, round 1)",
        "# metric gpu__time_duration.sum, --clock-control none.  Under ncu every launch is serialised and cold-cache:",
-       "# compare the SHARES with bench.py's roofline.stage_ms_per_step (event-bracketed serial pass: K3 62.8 / K124 38.7 us -> 62 / 38 %),",
-       "# not the absolutes.  In the timed region itself the two kernels of consecutive steps overlap (step = 57.7 us).",
+       "# compare the SHARES with bench.py's roofline.stage_ms_per_step (event-bracketed serial pass: K3 63.0 / K124 34.0 us -> 65 / 35 %),",
+       "# not the absolutes.  In the timed region itself the two kernels of consecutive steps overlap (step = 56.5 us).",
        "# Raw list: profiles/launches_r1.csv", ""]
 out += table(steps, "## device steps: 12 x ppn_parse on 512 images (warm-up 3+1, timed 4, per-kernel event pass 4): arg-max + fused parse")
 out += [""] + table(chunks, "## end-to-end arm: 3 x ppn_parse_host = 24 chunks of 64 images (host buffers, copies overlapped)")
