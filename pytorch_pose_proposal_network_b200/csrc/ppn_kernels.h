@@ -18,7 +18,7 @@ struct Tuning {
     int argmax_smem_cap = 0;           // > 0: the ring may use at most this much shared memory (set per call by ppn_parse
                                        // so that the fused parse kernel's CTAs fit beside it on every SM)
     int argmax16_threads = 320;        // 16-bit heads: their own ring shape (rows are half as long, so an item
-    int argmax16_stage_bytes = 32 * 1024;   // of G matrices is half the bytes; measured, profiles/sweep_argmax16_*)
+    int argmax16_stage_bytes = 48 * 1024;   // of G matrices is half the bytes; measured, profiles/sweep_argmax16_*)
     int parse_stage_all = -1;          // tree parse stages: -1 auto, 0 nothing, 1 resp+conf, 2 all six groups
     int parse_threads = 0;             // tree-parse CTA size, 0 = by grid size
     int parse_fused = -1;              // whole-path call: decode+NMS+tree parse in one kernel.  -1 auto (when all of its

@@ -21,6 +21,7 @@ ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--overlap", type=int, default=0)
 ap.add_argument("--dense", action="store_true")
 ap.add_argument("--tune", action="append", default=[])
+ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16", "bf16"])
 a = ap.parse_args()
 _lib.tune(parse_overlap=a.overlap)
 for kv in a.tune:
@@ -29,10 +30,12 @@ for kv in a.tune:
 cfg = PRESETS[a.config]()
 B = BATCH[a.config]
 bufs = [torch.rand(B, cfg.C, cfg.H, cfg.W, device="cuda") for _ in range(2)]
+dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[a.head_dtype]
 if a.dense or a.config == "cfg3":
     for t in bufs:
         t[:, :2 * cfg.K] = 0.4 + 0.6 * t[:, :2 * cfg.K]
         t[:, 4 * cfg.K:6 * cfg.K] *= 0.08
+bufs = [t.to(dt) for t in bufs]
 p = PoseParser(cfg)
 for i in range(a.steps):
     out = p.parse(bufs[i % 2])

@@ -534,7 +534,7 @@ def test_argmax_sixteen_bit_special_values(dtype, grid, window):
         try:
             got = PoseParser(cfg).limb_argmax(dev).cpu().numpy()
         finally:
-            _lib.tune(argmax16_stage_bytes=32768, argmax_stages=4, argmax16_threads=320)
+            _lib.tune(argmax16_stage_bytes=49152, argmax_stages=4, argmax16_threads=320)
         assert np.array_equal(got, want), (stage_bytes, stages, threads)
 
 
