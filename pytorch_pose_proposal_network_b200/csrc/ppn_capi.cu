@@ -212,7 +212,7 @@ int ppn_tune(const char* key, int32_t value) {
     if (!key) return PPN_E_BADARG;
     ppn::Tuning& t = g_tuning;
     if (!std::strcmp(key, "argmax.variant")) t.argmax_variant = value;
-    else if (!std::strcmp(key, "argmax.stage_bytes")) t.argmax_stage_bytes = value < 1024 ? 1024 : value;
+    else if (!std::strcmp(key, "argmax.stage_bytes")) t.argmax_stage_bytes = value <= 0 ? 0 : (value < 1024 ? 1024 : value);
     else if (!std::strcmp(key, "argmax.stages")) t.argmax_stages = value < 2 ? 2 : (value > 32 ? 32 : value);
     else if (!std::strcmp(key, "argmax.threads")) t.argmax_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) t.argmax_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);

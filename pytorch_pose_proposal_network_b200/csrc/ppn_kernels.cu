@@ -1881,7 +1881,9 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     p->threads = p->CV * G;
     p->threads_padded = (p->threads + 31) & ~31;
     const int per_row = p->split_mats ? row_bytes * G : row_bytes;     // ring bytes per row index
-    int max_rows = t.argmax_stage_bytes / per_row;
+    const int stage_target = t.argmax_stage_bytes > 0 ? t.argmax_stage_bytes
+                                                      : ((size_t)g.S * row_bytes <= 64 * 1024 ? 48 * 1024 : 32 * 1024);
+    int max_rows = stage_target / per_row;
     if (max_rows < 1) max_rows = 1;
     if (max_rows > g.S) max_rows = g.S;
     p->chunks = (g.S + max_rows - 1) / max_rows;

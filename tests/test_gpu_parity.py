@@ -255,7 +255,7 @@ def test_sixteen_bit_head(preset, dist, B, grid, dtype):
     assert_packed_equals_oracle(host.numpy(), ref, B)
 
 
-TUNE_DEFAULTS = dict(argmax_variant=0, argmax_stage_bytes=32768, argmax_stages=4, argmax_threads=320,
+TUNE_DEFAULTS = dict(argmax_variant=0, argmax_stage_bytes=0, argmax_stages=4, argmax_threads=320,
                      argmax_ctas_per_sm=1, argmax_split=-1, argmax_dynamic=1, argmax_tail_opt=0)
 
 
