@@ -122,7 +122,8 @@ class PoseGatherer:
         self.local = [torch.zeros(self.gs * self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.full = [torch.zeros(self.world * self.gs * self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.work = [None, None]
-        self.step = 0
+        self.step = 0                             # slot cursor: finish() rounds it up to a whole group
+        self._last = -1                           # slot index of the last step really submitted
         self.side = torch.cuda.Stream(device=dev)
         self._filled = [torch.cuda.Event() for _ in range(2)]
         self._parsed = [torch.cuda.Event() for _ in range(4)]
@@ -151,6 +152,7 @@ class PoseGatherer:
                                 cap_entries=self.cap, skip_slots=True)
         if k == self.gs - 1:
             self._ship(i)
+        self._last = self.step
         self.step += 1
         return res
 
@@ -175,6 +177,7 @@ class PoseGatherer:
         if k == self.gs - 1:
             with torch.cuda.stream(self.side):
                 self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
+        self._last = self.step
         self.step += 1
         return released
 
@@ -198,7 +201,11 @@ class PoseGatherer:
         """Host view of `rank`'s records for the last submitted step minus `step_back`
         (within the two most recent groups; call after finish(); synchronises)."""
         from .parser import unpack_entries
-        grp, k = divmod(self.step - 1 - step_back, self.gs)
+        if self._last < 0 or step_back < 0 or step_back > self._last:
+            raise ValueError("no such step")
+        grp, k = divmod(self._last - step_back, self.gs)
+        if grp < self._last // self.gs - 1:
+            raise ValueError("only the two most recent groups of steps are still held")
         buf = self.full[grp & 1]
         lo = (rank * self.gs + k) * self.nbytes
         part = buf[lo:lo + self.nbytes].cpu()

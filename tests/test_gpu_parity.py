@@ -832,7 +832,7 @@ def _gatherer_worker(rank, port, tmp):
         torch.cuda.synchronize()
         ok = True
         for i in range(((steps - 1) // gs - 1) * gs, steps):       # the two most recent groups are still held
-            rec, ref = gat.records_of(0, step_back=gat.step - 1 - i), refs[i % 3]
+            rec, ref = gat.records_of(0, step_back=steps - 1 - i), refs[i % 3]
             ok &= not rec["overflow"] and np.array_equal(rec["count"], ref["counts"][:, 2])
             for b in range(0, B, 5):
                 n = int(ref["counts"][b, 2])
