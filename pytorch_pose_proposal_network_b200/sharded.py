@@ -129,14 +129,19 @@ class PoseGatherer:
         self._parsed = [torch.cuda.Event() for _ in range(4)]
         self._released = [torch.cuda.Event() for _ in range(4)]
         self._slices = [[self.local[i][k * self.nbytes:(k + 1) * self.nbytes] for k in range(self.gs)] for i in range(2)]
+        self._shipped = [self.gs, self.gs]        # slices per rank in the last gather of each buffer set
 
-    def _ship(self, i: int):
-        """All-gather buffer set i on the side stream once the compute stream has filled it."""
+    def _ship(self, i: int, n_slices: Optional[int] = None):
+        """All-gather buffer set i on the side stream once the compute stream has filled it.  A partly
+        filled group (flush) ships only its used slices: rank r's slice k then sits at (r * n + k)."""
+        n = self.gs if n_slices is None else int(n_slices)
+        self._shipped[i] = n
         main = torch.cuda.current_stream(self.parser.device)
         self._filled[i].record(main)
         self.side.wait_event(self._filled[i])
         with torch.cuda.stream(self.side):
-            self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
+            self.work[i] = dist.all_gather_into_tensor(self.full[i][:self.world * n * self.nbytes],
+                                                       self.local[i][:n * self.nbytes], group=self.group, async_op=True)
 
     def parse(self, head, out=None, input_complete: bool = False):
         """The step: parse `head` on the current stream with the poses written straight into this step's
@@ -176,6 +181,7 @@ class PoseGatherer:
         released.record(self.side)
         if k == self.gs - 1:
             with torch.cuda.stream(self.side):
+                self._shipped[i] = self.gs
                 self.work[i] = dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group, async_op=True)
         self._last = self.step
         self.step += 1
@@ -185,8 +191,8 @@ class PoseGatherer:
         """Gather a partly filled last group, then make the CURRENT stream wait for every gather.
         Every rank must have submitted the same number of steps."""
         grp, k = divmod(self.step, self.gs)
-        if k != 0:                                # flush: ship the partial group as it is
-            self._ship(grp & 1)
+        if k != 0:                                # flush: ship the slices of the partial group that were filled
+            self._ship(grp & 1, n_slices=k)
             self.step = (grp + 1) * self.gs
         with torch.cuda.stream(self.side):
             for j in range(2):
@@ -207,6 +213,6 @@ class PoseGatherer:
         if grp < self._last // self.gs - 1:
             raise ValueError("only the two most recent groups of steps are still held")
         buf = self.full[grp & 1]
-        lo = (rank * self.gs + k) * self.nbytes
+        lo = (rank * self._shipped[grp & 1] + k) * self.nbytes
         part = buf[lo:lo + self.nbytes].cpu()
         return unpack_entries(part, self.B, self.cap, self.offsets)
