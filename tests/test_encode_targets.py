@@ -87,6 +87,35 @@ def test_encoded_targets_parse_back():
     assert len(humans) == 2 and all(set(h) == {0, 15, 13} for h in humans)
 
 
+def test_flatten_samples_matches_the_reference_zip():
+    """Host side of TargetEncoder: the reference's encoder loop zips bbox, keypoints, is_visible and size
+    (dataset.py:108), i.e. stops at the shortest — aug.py:115-116 leaves ONE zero person in `keypoints` when no
+    box survived, which must not become a person here either."""
+    from pytorch_pose_proposal_network_b200.dataset import flatten_samples
+    K = 18
+    rng = np.random.default_rng(3)
+    kp, bb, vis, size = encode_gt.random_people(rng, 3, K, (384, 384))
+    empty = dict(keypoints=np.zeros((1, K - 1, 2), np.float32), bbox=np.zeros((0, 4)), is_visible=[], size=[])
+    full = dict(keypoints=torch.from_numpy(kp), bbox=torch.from_numpy(bb), is_visible=vis, size=size)
+    off, fb, fk, fv, fs = flatten_samples([empty, full, empty], K)
+    assert off.tolist() == [0, 0, 3, 3] and off.dtype == np.int32
+    assert fb.dtype == np.float64 and np.array_equal(fb, bb)
+    assert fk.dtype == np.float32 and np.array_equal(fk, kp)
+    assert fv.dtype == np.uint8 and np.array_equal(fv.astype(bool), np.asarray(vis))
+    assert fs.dtype == np.float64 and np.array_equal(fs, np.asarray(size))
+    off, fb, fk, fv, fs = flatten_samples([], K)
+    assert off.tolist() == [0] and fb.shape == (0, 4) and fk.shape == (0, K - 1, 2) and fv.shape == (0, K - 1)
+
+
+def test_encoder_has_no_cpu_path():
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.dataset import TargetEncoder
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-GPU failure mode")
+    with pytest.raises(RuntimeError):
+        TargetEncoder(PPNConfig.reference_native())
+
+
 # ------------------------------------------------------------------------------------------------
 gpu = pytest.mark.gpu
 
