@@ -194,3 +194,37 @@ def test_gpu_encoder_rejects_what_the_reference_cannot_do():
         enc.encode([dict(keypoints=np.zeros((0, 17, 2), np.float32), bbox=np.zeros((0, 4)), is_visible=[], size=[])])
     with pytest.raises(ValueError):
         TargetEncoder(PPNConfig.reference_native(), edges=[[0, 1]])
+
+
+@gpu
+def test_gpu_encode_then_gpu_parse_round_trip_full_batch():
+    """Both directions together at BASELINE batch size: 512 annotation sets -> ppn_encode_targets -> a head tensor
+    assembled on the device exactly as datatest.py:405-412 feeds the parser (resp = delta targets, conf = 1, limb block
+    = te) -> ppn_parse, against the numpy encoder restatement followed by the C parser restatement.  The inputs are
+    the parser's worst case for ties: every score is exactly 1, every empty limb window is all zeros (arg-max 0)."""
+    from oracle import c_oracle, ppn_oracle as O
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.dataset import TargetEncoder
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PPNConfig.mpii16()                                   # K16 / E15, 384x384, 12x12 grid, 9x9 window
+    g = O.Geometry.of(cfg)
+    K, B = cfg.K, 512
+    rng = np.random.default_rng(2024)
+    raw = [encode_gt.random_people(rng, int(rng.integers(0, 13)), K, cfg.insize, spread=1.05) for _ in range(B)]
+    samples = [dict(keypoints=kp, bbox=bb, is_visible=vis, size=size) for kp, bb, vis, size in raw]
+    t = TargetEncoder(cfg).encode(samples)
+    head = torch.cat([t.delta, torch.ones_like(t.delta), t.tx, t.ty, t.tw, t.th,
+                      t.te.reshape(B, cfg.E * cfg.S, cfg.H, cfg.W)], dim=1).contiguous()
+    packed = PoseParser(cfg).parse(head).numpy()
+    want_head = np.empty((B, cfg.C, cfg.H, cfg.W), np.float32)
+    for b, (kp, bb, vis, size) in enumerate(raw):
+        w = encode_gt.encode_targets(kp, bb, vis, size, K, edges_of(K), cfg.insize, cfg.outsize, cfg.local_grid_size)
+        want_head[b] = np.concatenate([w[0], np.ones_like(w[0]), w[3], w[4], w[7], w[8], w[9].reshape(-1, cfg.H, cfg.W)])
+    assert np.array_equal(bits(head.cpu().numpy()), bits(want_head))
+    ref = c_oracle.parse_batch(want_head, g, n_threads=8)
+    assert np.array_equal(packed["count"], ref["counts"][:, 2]) and int(packed["count"].sum()) > B // 2
+    for b in range(B):
+        n = int(ref["counts"][b, 2])
+        assert np.array_equal(packed["part_cell"][b, :n], ref["part_cell"][b, :n]), b
+        assert np.array_equal(bits(packed["part_box"][b, :n]), bits(ref["part_box"][b, :n])), b
+        assert np.array_equal(bits(packed["part_score"][b, :n]), bits(ref["part_score"][b, :n])), b
