@@ -210,8 +210,6 @@ def run_ours(args, rank, world, local_rank):
         del t
     outs = [parser.alloc_output(B) for _ in range(2)]
 
-    released = [None, None]
-
     def step(i):
         # the inputs have been resident in HBM since before the timed region: the parser may overlap
         # consecutive steps (PPN_FLAG_INPUT_COMPLETE); results still complete in step order
