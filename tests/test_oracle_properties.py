@@ -59,3 +59,60 @@ def test_parse_numpy_equals_c(seed, dist, W, H, s):
         assert (p.part_cell[:, 0] == p.root_cell).all()
         assert (p.part_score[p.part_cell >= 0] >= np.float32(g.det_thresh)).all()
         assert (np.diff(p.part_score[:, 0]) <= 0).all()
+
+
+def blockwise_nms_model(b, thr, score, limit=None):
+    """Host model of the CUDA NMS's control flow (csrc/ppn_kernels.cu, nms_core): boxes in visiting order, 32 at a
+    time; a block is resolved from its 32x32 DIAGONAL suppression bits and the `removed` word inherited from earlier
+    blocks; only the boxes a block keeps are then tested against the later blocks (a box already removed is skipped).
+    The claim checked below: this visits exactly the pairs that matter, i.e. equals the plain greedy loop."""
+    n = len(b)
+    order = np.lexsort((-np.arange(n), -score.astype(np.float64)))
+    sb = b[order]
+    area = (sb[:, 2] - sb[:, 0]) * (sb[:, 3] - sb[:, 1])
+    thr = np.float32(thr)
+
+    def sup(i, js):                                             # does kept box i suppress the boxes js?
+        return O.iou_one_to_many(sb[i], area[i], sb[js], area[js]) >= thr if len(js) else np.zeros(0, bool)
+
+    Wd = (n + 31) // 32
+    removed = np.zeros(n, bool)
+    keep = []
+    for w in range(Wd):
+        i0, i1 = 32 * w, min(n, 32 * w + 32)
+        diag = {i: sup(i, np.arange(i + 1, i1)) for i in range(i0, i1)}          # built up front for all blocks
+        kept_here = []
+        for i in range(i0, i1):                                                  # the one-warp scan
+            if removed[i]:
+                continue
+            kept_here.append(i)
+            removed[i + 1:i1] |= diag[i]
+        if limit is not None and len(keep) + len(kept_here) >= limit:
+            keep += kept_here[:limit - len(keep)]
+            break
+        keep += kept_here
+        for i in kept_here:                                                      # survivors against the later blocks
+            later = np.arange(i1, n)
+            later = later[~removed[later]]
+            removed[later] |= sup(i, later)
+    return order[np.asarray(keep, np.int64)].astype(np.int32) if keep else np.zeros(0, np.int32)
+
+
+wide_boxes = st.lists(st.tuples(st.floats(0, 300, width=32), st.floats(0, 300, width=32),
+                                st.floats(0, 200, width=32), st.floats(0, 200, width=32)), min_size=0, max_size=150)
+
+
+@settings(max_examples=120, deadline=None)
+@given(wide_boxes, st.sampled_from([0.05, 0.3, 0.5, 0.9]), st.integers(0, 2 ** 31 - 1), st.sampled_from([None, 2, 40]),
+       st.booleans())
+def test_blockwise_nms_equals_greedy(bx, thr, seed, limit, poison):
+    b = np.array([[y, x, y + h, x + w] for y, x, h, w in bx], np.float32).reshape(-1, 4)
+    n = len(b)
+    rng = np.random.default_rng(seed)
+    if poison and n:                                            # zero-area, inverted and NaN boxes (NaN IoU keeps a box)
+        k = rng.integers(0, n, size=max(1, n // 6))
+        b[k, 2] = b[k, 0]
+        b[k[: len(k) // 2], 3] = np.nan
+    score = rng.permutation(n).astype(np.float32)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(blockwise_nms_model(b, thr, score, limit), O.nms(b, thr, score=score, limit=limit))
