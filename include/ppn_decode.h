@@ -18,6 +18,8 @@
  *   ppn_parse_host ......... the same from host memory (the reference's numpy arrays), with the
  *                            copies the reference's `.cpu()` calls stand for done here in reverse
  *   ppn_parse_dense ........ ppn_parse that also emits dense (human, part) records (what a multi-GPU job gathers)
+ *   ppn_head_parse ......... the network's last layer fused in: conv3 (1x1) + sigmoid, model.py:85,133-136, then
+ *                            the whole parse, without the head tensor ever reaching memory
  *   ppn_encode_targets ..... the inverse of the path: the "# Encode samples" half of
  *                            KeypointsDataset.__getitem__, dataset.py:89-198, for a whole batch
  *
@@ -48,7 +50,7 @@
 extern "C" {
 #endif
 
-#define PPN_ABI_VERSION 4
+#define PPN_ABI_VERSION 5
 
 /* library error codes (negative); positive return values are cudaError_t */
 #define PPN_OK               0
@@ -205,6 +207,26 @@ int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_e
 int ppn_parse_dense(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
                     void* packed, size_t packed_bytes, int32_t cap_entries, int32_t skip_slots,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the network head fused in ---------------------------------------------------
+ * Replaces `conv3_out = self.conv3(lRelu2); out = self.sigmoid(conv3_out)` (model.py:133-136) TOGETHER with the
+ * parse of `out`: feat = lRelu2 [B, Cin, H, W] fp32 NCHW contiguous (Cin = 512, model.py:85), weight = conv3.weight
+ * viewed as [C, Cin] fp32, bias = conv3.bias [C] or NULL; C = 6K + sH*sW*E.  The 1x1 convolution runs on the
+ * tensor cores in TF32 with fp32 accumulation (what cuDNN does for the reference under PyTorch's defaults); the
+ * sigmoid and numpy's first-maximum rule are applied to the accumulators in the GEMM epilogue, so only the 6K
+ * decode planes and the uint16 arg-max map are written — never the [B, C, H, W] head tensor.
+ *   ppn_head_gemm_argmax: that kernel alone.  dec [B, 6K, H*W] fp32 = sigmoid of the decode channels, amax
+ *       [B, E, H*W]; emit_logits / emit_head (each NULL or [B, C, H*W] fp32) additionally receive the convolution
+ *       output and its sigmoid — the reference's head tensor — for parity checks.
+ *   ppn_head_parse: the kernel above, then the fused decode + NMS + tree parse on its output.  Results are
+ *       bit-identical to ppn_parse on the tensor emit_head would hold.  Needs Cin % 32 == 0, H*W % 4 == 0,
+ *       H*W <= PPN_MAX_CELLS, n_nms_parts == 1 and 16-byte aligned feat / weight: PPN_E_UNSUPPORTED otherwise. */
+int ppn_head_workspace_bytes(const PPNShape* shape, size_t* bytes);
+int ppn_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                         float* dec, uint16_t* amax, float* emit_logits, float* emit_head, void* stream);
+int ppn_head_parse(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                   const PPNParams* params, const PPNHumans* out, void* workspace, size_t workspace_bytes,
+                   float* emit_logits, float* emit_head, void* stream);
 
 /* ---- the inverse of the parser: training targets from annotations ------------------------------
  * Replaces the "# Encode samples" half of KeypointsDataset.__getitem__ (dataset.py:89-198) for a whole

@@ -555,6 +555,81 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
     return dense ? pack_after(out, shape, dense, st) : PPN_OK;
 }
 
+// ---- fused network head ---------------------------------------------------------------------
+namespace {
+struct HeadWorkspace { size_t dec, amax, total; };
+HeadWorkspace carve_head(const PPNShape* s) {
+    HeadWorkspace w;
+    const size_t B = (size_t)s->B, HW = (size_t)s->H * s->W;
+    w.dec = 0;
+    w.amax = align_up(B * 6 * s->K * HW * sizeof(float), 256);
+    w.total = w.amax + align_up(B * s->E * HW * sizeof(uint16_t), 256);
+    return w;
+}
+int check_head(const float* feat, const float* weight, int32_t Cin, const PPNShape* s) {
+    if (Cin < 32 || Cin % 32 != 0 || (s->H * s->W) % 4 != 0) return PPN_E_UNSUPPORTED;
+    if (s->head_dtype != PPN_HEAD_F32) return PPN_E_UNSUPPORTED;
+    if (!feat || !weight) return PPN_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(feat) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15)) return PPN_E_BADARG;
+    return PPN_OK;
+}
+}  // namespace
+
+int ppn_head_workspace_bytes(const PPNShape* shape, size_t* bytes) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (!bytes) return PPN_E_BADARG;
+    *bytes = carve_head(shape).total;
+    return PPN_OK;
+}
+
+int ppn_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                         float* dec, uint16_t* amax, float* emit_logits, float* emit_head, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (shape->B == 0) return PPN_OK;
+    if ((rc = check_head(feat, weight, Cin, shape))) return rc;
+    if (!dec || (!amax && shape->E > 0)) return PPN_E_BADARG;
+    return cuda_rc(ppn::launch_head_gemm_argmax(feat, weight, bias, Cin, make_geom(shape), dec, amax, emit_logits, emit_head,
+                                                (cudaStream_t)stream, false, 0));
+}
+
+int ppn_head_parse(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                   const PPNParams* params, const PPNHumans* out, void* workspace, size_t workspace_bytes,
+                   float* emit_logits, float* emit_head, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_params(shape, params))) return rc;
+    if ((rc = check_humans(out))) return rc;
+    ppn::ChainTable ch;
+    if ((rc = make_chains(shape, params, &ch))) return rc;
+    if (shape->B == 0) return PPN_OK;
+    if ((rc = check_head(feat, weight, Cin, shape))) return rc;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return PPN_E_BADARG;
+    if (params->n_nms_parts != 1 || (long long)shape->H * shape->W > PPN_MAX_CELLS) return PPN_E_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(out->part_box) & 15) return PPN_E_BADARG;
+    const HeadWorkspace w = carve_head(shape);
+    if (workspace_bytes < w.total) return PPN_E_WORKSPACE;
+    float* dec = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + w.dec);
+    uint16_t* amax = reinterpret_cast<uint16_t*>(static_cast<unsigned char*>(workspace) + w.amax);
+    const ppn::Geom g = make_geom(shape);
+    // the parse kernel reads the decode planes as a head tensor that holds nothing but its 6K decode channels
+    ppn::Geom gd = g;
+    gd.img_stride = (size_t)6 * g.K * g.HW;
+    if (!ppn::parse_fused_supported(gd, g_tuning.parse_stage_all)) return PPN_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    // two launches: the GEMM kernel waits for whatever produced `feat`, then lets the parse kernel become resident;
+    // the parse kernel waits for the GEMM kernel to COMPLETE before it reads anything (everything it reads is new)
+    if ((e = ppn::launch_head_gemm_argmax(feat, weight, bias, Cin, g, dec, amax, emit_logits, emit_head, st, true,
+                                          ppn::PDL_WAIT_START | ppn::PDL_TRIGGER)) != cudaSuccess) return (int)e;
+    e = ppn::launch_parse_fused(dec, gd, ch, params->det_thresh, params->nms_thresh, params->min_num_keypoints, amax, out->count,
+                                out->root_cell, out->part_cell, out->part_score, out->part_box, out->R, st, true, 1,
+                                g_tuning.parse_stage_all, -1, nullptr, true);
+    ppn::chain_break(st);
+    return cuda_rc(e);
+}
+
 int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centre_yx, void* stream) {
     int rc = check_humans(humans);
     if (rc) return rc;

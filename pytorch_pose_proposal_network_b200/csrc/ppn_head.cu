@@ -1,0 +1,360 @@
+// Fused network head: the final 1x1 convolution (model.py:85 `conv3 = Conv2d(512, lastsize, 1)`), the
+// sigmoid (model.py:133-136) and the limb-window arg-max of the parser (datatest.py:100,113) in ONE
+// kernel, so that the fp32 head tensor [B, 6K + S*E, H, W] — 17.5 MB per image at the reference's shape,
+// 98.6 % of it limb values whose only use is one arg-max per window — is never written to HBM nor
+// read back.  What leaves the kernel is the 6K decode planes (sigmoid applied) and the uint16 arg-max
+// map; the fused decode + NMS + tree-parse kernel (ppn_kernels.cu, K124) consumes both.
+//
+// The 1x1 convolution is a GEMM per image, D[cell, c] = sum_k X[b, k, cell] * W[c, k] (+ bias[c]):
+//   A = X_b^T  [M = cells,    K = Cin]   "MN-major" in memory (cells contiguous: NCHW activations)
+//   B = W      [N = channels, K = Cin]   K-major
+// computed on the 5th-generation tensor cores: tcgen05.mma kind::tf32 (fp32 operands read from shared
+// memory, fp32 accumulation — the precision class of the reference's own cuDNN convolution, which
+// PyTorch runs in TF32 by default), 128 x 256 accumulator tiles in tensor memory (TMEM), operands
+// brought in by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a 4-stage mbarrier ring.
+// Cells are the M dimension on purpose: an accumulator row (TMEM lane) then belongs to ONE cell and
+// the epilogue thread that owns the lane scans the channels in order, keeping numpy's running
+// (max, first index) per limb window in registers — the same per-thread rule as the streaming
+// arg-max kernel, no cross-lane reduction.  The accumulator is double-buffered (2 x 256 TMEM columns):
+// the epilogue of channel tile n runs under the MMAs of tile n + 1.
+//
+// Warp roles (192 threads, one CTA per SM, persistent over M tiles):
+//   warp 0      TMA producer (one lane)
+//   warp 1      TMEM allocation, MMA issue (one lane), TMEM release
+//   warps 2-5   epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias, sigmoid / running arg-max, stores
+//
+// M tiles are built from "cell groups" of 32 cells of one image (a 128-byte swizzle row): a tile is 4
+// consecutive groups of the flattened (image, group) list, each fetched by its own TMA box from the
+// 3-D view [B][Cin][HW] with zero fill past HW — so a 12x12 grid (144 = 4.5 groups) wastes 11 % of
+// the rows, not 44 %, and every epilogue warp (one group) works on a single image.
+//
+// Exactness.  The parser's contract is "bit-exact on sigmoid(logits)".  sigmoid is monotone but not
+// injective in fp32 (neighbouring logits often share a sigmoid value), so an arg-max over logits can
+// differ from numpy's first-maximum over the sigmoid values.  The running rule therefore compares
+// sigmoid values — but evaluates the sigmoid only when a logit exceeds the running maximum logit
+// (a handful of times per window): cand = x > m;  take = sigmoid(x) > sigmoid(best).
+#include <cuda.h>          // CUtensorMap and enums only: the encoder is fetched with cudaGetDriverEntryPoint
+#include <mutex>
+
+#include "ppn_kernels.h"
+
+namespace ppn {
+
+namespace {
+
+constexpr int kBlockM = 128;                 // cells per accumulator tile (4 groups of 32)
+constexpr int kBlockN = 256;                 // channels per accumulator tile
+constexpr int kBlockK = 32;                  // fp32 elements per 128-byte swizzle row
+constexpr int kUmmaK = 8;                    // tf32: 32 bytes of K per instruction
+constexpr int kStages = 4;
+constexpr int kGroupBytes = kBlockK * 128;   // one cell group of a stage: 32 k-rows x 128 B
+constexpr int kABytes = 4 * kGroupBytes;     // 16 KB
+constexpr int kBBytes = kBlockN * 128;       // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 512;               // two 256-column accumulators
+constexpr int kHeadThreads = 192;
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {      // arrives on `bar` when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], one instruction of M x N x 8 (tf32)
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Shared-memory matrix descriptor (sm_100 format: version 1, 128-byte swizzle); offsets in bytes.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t leading_bytes, uint32_t stride_bytes) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((leading_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((stride_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// 32 lanes x 32 consecutive columns of TMEM -> 32 registers per thread (thread = lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// torch.sigmoid's fp32 expression, 1 / (1 + exp(-x)): libdevice expf, one add, one IEEE division
+__device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+}  // namespace
+
+struct HeadArgs {
+    int32_t B, HW, Cin, C, n_dec, S, E;
+    int32_t groups_per_img, n_groups, n_tiles, n_ntiles, n_kblocks;
+    const float* bias;          // [C] or nullptr
+    float* dec;                 // [B, n_dec, HW]   sigmoid of the 6K decode channels
+    uint16_t* amax;             // [B, E, HW]
+    float* emit_logits;         // optional [B, C, HW]: conv output before the sigmoid (parity tests)
+    float* emit_head;           // optional [B, C, HW]: the reference's head tensor, sigmoid(logits)
+};
+
+__global__ void __launch_bounds__(kHeadThreads, 1)
+head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, HeadArgs a, int pdl) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;       // [2] accumulator ready for the epilogue
+    uint64_t* tempty = tfull + 2;            // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tm_x);
+        prefetch_tensormap(&tm_w);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {                         // the allocating warp also frees
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (pdl & PDL_WAIT_START) pdl_wait();            // the activations may come from the kernel before us
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();  // the parse kernel may become resident (it waits for us at its top)
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                int gb[4], gc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int g = tile * 4 + q;
+                    const int b = g / a.groups_per_img;
+                    gb[q] = g < a.n_groups ? b : a.B;                   // past the end: an all-zero box
+                    gc[q] = g < a.n_groups ? (g - b * a.groups_per_img) * 32 : 0;
+                }
+                for (int nt = 0; nt < a.n_ntiles; ++nt)
+                    for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        unsigned char* sa = smem + (size_t)stage * kStageBytes;
+                        mbar_arrive_expect_tx(&full[stage], kStageBytes);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) tma_load_3d(sa + q * kGroupBytes, &tm_x, gc[q], kb * kBlockK, gb[q], &full[stage]);
+                        tma_load_2d(sa + kABytes, &tm_w, kb * kBlockK, nt * kBlockN, &full[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B tf32, A MN-major (cells contiguous), B K-major, M = 128, N = 256
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+                                   ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
+                for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1u);             // the epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)acc * kBlockN;
+                    for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+                        for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+                            // A: 8 k-rows of 128 B = one swizzle atom per cell group, groups 4096 B apart;
+                            // B: 8 channel rows of 128 B per atom (1024 B), K advanced by 32 B inside the row
+                            const uint64_t da = smem_desc(sa + kk * 1024, kGroupBytes, 1024);
+                            const uint64_t db = smem_desc(sb + kk * kUmmaK * 4, 16, 1024);
+                            tc_mma_tf32(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(&empty[stage]);                        // the stage is free once these MMAs have read it
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(&tfull[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
+        }
+    } else {
+        // ------------------------------ epilogue ------------------------------
+        const int ew = warp & 3;                     // the TMEM lane quadrant this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const int g = tile * 4 + ew;
+            const int b = g / a.groups_per_img;
+            const int cell = (g - b * a.groups_per_img) * 32 + lane;
+            const bool valid = g < a.n_groups && cell < a.HW;
+            float m = 0.0f, bs = 0.0f;               // running maximum logit and the best sigmoid value
+            int idx = 0, aw = 0, ei = 0;             // aw: position inside the current limb window (uniform)
+            for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                for (int ch = 0; ch < kBlockN / 32; ++ch) {
+                    const int c0 = nt * kBlockN + ch * 32;
+                    if (c0 >= a.C) break;                                 // uniform
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN + ch * 32), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int c = c0 + j;
+                        if (c >= a.C) break;                              // uniform
+                        float x = __uint_as_float(r[j]);
+                        if (a.bias) x = __fadd_rn(x, __ldg(a.bias + c));
+                        const size_t at = ((size_t)b * a.C + c) * a.HW + cell;
+                        if (a.emit_logits && valid) a.emit_logits[at] = x;
+                        if (c < a.n_dec) {
+                            const float s = sigmoid_f32(x);
+                            if (valid) a.dec[((size_t)b * a.n_dec + c) * a.HW + cell] = s;
+                            if (a.emit_head && valid) a.emit_head[at] = s;
+                        } else {
+                            if (aw == 0) {
+                                m = x; bs = sigmoid_f32(x); idx = 0;
+                            } else if (!(x <= m) && m == m) {             // a larger logit (or the first NaN)
+                                const float sx = sigmoid_f32(x);
+                                if (!(sx <= bs) && bs == bs) { idx = aw; bs = sx; }
+                                m = x;
+                            }
+                            if (a.emit_head && valid) a.emit_head[at] = sigmoid_f32(x);
+                            if (++aw == a.S) {
+                                if (valid) a.amax[((size_t)b * a.E + ei) * a.HW + cell] = (uint16_t)idx;
+                                aw = 0;
+                                ++ei;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+std::mutex g_enc_mu;
+EncodeTiledFn g_encode = nullptr;
+bool g_attr_done[64] = {};
+
+cudaError_t encoder(EncodeTiledFn* out) {
+    std::lock_guard<std::mutex> lock(g_enc_mu);
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    *out = g_encode;
+    return cudaSuccess;
+}
+}  // namespace
+
+size_t head_smem_bytes() { return (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers, TMEM slot */; }
+
+cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int Cin, const Geom& g,
+                                    float* dec, uint16_t* amax, float* emit_logits, float* emit_head, cudaStream_t st,
+                                    bool pdl_attr, int pdl_bits) {
+    if (g.B == 0) return cudaSuccess;
+    if (Cin % kBlockK != 0 || g.HW % 4 != 0) return cudaErrorInvalidValue;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    EncodeTiledFn enc = nullptr;
+    if ((e = encoder(&enc)) != cudaSuccess) return e;
+
+    CUtensorMap tm_x, tm_w;
+    {   // activations [B][Cin][HW] fp32: box = 32 cells x 32 input channels of one image
+        const cuuint64_t dim[3] = {(cuuint64_t)g.HW, (cuuint64_t)Cin, (cuuint64_t)g.B};
+        const cuuint64_t stride[2] = {(cuuint64_t)g.HW * 4, (cuuint64_t)Cin * g.HW * 4};
+        const cuuint32_t box[3] = {32, (cuuint32_t)kBlockK, 1};
+        const cuuint32_t es[3] = {1, 1, 1};
+        if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    {   // weights [C][Cin] fp32: box = 32 input channels x 256 output channels
+        const cuuint64_t dim[2] = {(cuuint64_t)Cin, (cuuint64_t)g.C};
+        const cuuint64_t stride[1] = {(cuuint64_t)Cin * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockN};
+        const cuuint32_t es[2] = {1, 1};
+        if (enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(weight), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    HeadArgs a;
+    a.B = g.B; a.HW = g.HW; a.Cin = Cin; a.C = g.C; a.n_dec = 6 * g.K; a.S = g.S; a.E = g.E;
+    a.groups_per_img = (g.HW + 31) / 32;
+    a.n_groups = g.B * a.groups_per_img;
+    a.n_tiles = (a.n_groups + 3) / 4;
+    a.n_ntiles = (g.C + kBlockN - 1) / kBlockN;
+    a.n_kblocks = Cin / kBlockK;
+    a.bias = bias; a.dec = dec; a.amax = amax; a.emit_logits = emit_logits; a.emit_head = emit_head;
+
+    const size_t smem = head_smem_bytes();
+    {
+        std::lock_guard<std::mutex> lock(g_enc_mu);
+        if (dev >= 0 && dev < 64 && !g_attr_done[dev]) {
+            if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            g_attr_done[dev] = true;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min(sms, a.n_tiles));
+    cfg.blockDim = dim3(kHeadThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel, tm_x, tm_w, a, pdl_bits);
+}
+
+}  // namespace ppn

@@ -1271,6 +1271,7 @@ enum : int {
     FUSED_GUARD = 8,           // poll sync[0] >= seq before the early trigger
     FUSED_TRIGGER_EARLY = 16,  // launch_dependents before the wait (after the guard)
     FUSED_PUBLISH = 32,        // last CTA publishes seq + 1
+    FUSED_WAIT_TOP = 64,       // wait for the previous kernel before reading ANYTHING (the decode planes are its output)
 };
 
 struct FusedSmem { uint32_t delta, root, dyx, uni, amax, slot, estart, pmask, pos, total; };
@@ -1346,6 +1347,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
     const HT* img = head + (size_t)b * g.img_stride;
     const bool use_tab = g.S <= kMaxDyxTable;
 
+    if (pdl & FUSED_WAIT_TOP) pdl_wait();       // fused network head: resp/conf/x/y/w/h are the previous kernel's output
     // ---- let the next call's arg-max be launched (see the header comment): it only queues behind
     //      this call's arg-max, so the earlier the better ---------------------------------------------
     if (pdl & FUSED_GUARD) {
@@ -2325,7 +2327,7 @@ size_t parse_fused_smem_bytes(const Geom& g, int stage_pref) {
 cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
                                float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
-                               int staged_forced, const DenseTarget* dense_to) {
+                               int staged_forced, const DenseTarget* dense_to, bool wait_top) {
     if (g.B == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -2353,6 +2355,7 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
     if (cap == cudaStreamCaptureStatusNone && (e = slot_for(d, st, &slot, &words)) != cudaSuccess) return e;
     int bits = 0;
     if (pdl_attr) bits |= PDL_WAIT_START;
+    if (pdl_attr && wait_top) bits |= FUSED_WAIT_TOP;
     int seq = 0;
     if (slot) { bits |= FUSED_PUBLISH; seq = slot->published; }
     if (pdl_attr && chain_mode == 2 && slot) bits |= FUSED_GUARD | FUSED_TRIGGER_EARLY;

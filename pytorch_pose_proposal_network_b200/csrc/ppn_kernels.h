@@ -100,9 +100,17 @@ struct DenseTarget { int32_t* header; uint32_t* idcell; float* score; float* box
 cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
                                float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
-                               int staged_forced = -1, const DenseTarget* dense_to = nullptr);
+                               int staged_forced = -1, const DenseTarget* dense_to = nullptr, bool wait_top = false);
 bool chain_clean(cudaStream_t st);      // the stream's last whole-path launch was a (publishing) fused parse
 void chain_break(cudaStream_t st);      // ... was something else: the next overlapped call starts fully ordered
+
+// ---- fused network head (ppn_head.cu): 1x1 convolution (tcgen05 GEMM) + sigmoid + limb-window arg-max ---------
+// feat [B, Cin, H, W] fp32, weight [C, Cin] fp32, bias [C] or nullptr  ->  dec [B, 6K, HW] = sigmoid of the decode
+// channels, amax [B, E, HW]; optional emit_logits / emit_head [B, C, HW] for parity tests (model.py:85, 133-136).
+size_t head_smem_bytes();
+cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int Cin, const Geom& g,
+                                    float* dec, uint16_t* amax, float* emit_logits, float* emit_head, cudaStream_t st,
+                                    bool pdl_attr, int pdl_bits);
 
 // ---- training-target encoder (ppn_encode.cu) ----------------------------------------------------------
 struct EdgeTable { uint8_t src[256]; uint8_t dst[256]; };

@@ -285,6 +285,66 @@ class PoseParser:
                                                _ptr(self._host_scratch), self._host_scratch.numel()), "ppn_parse_host")
         return out
 
+    # ---- the network head fused in: conv3 (1x1) + sigmoid + parse (model.py:85, 133-136) ------------ #
+    def _check_features(self, feat, weight, bias):
+        cfg = self.cfg
+        if feat.dtype != torch.float32 or feat.dim() != 4 or tuple(feat.shape[2:]) != (cfg.H, cfg.W) or not feat.is_contiguous():
+            raise ValueError(f"feat must be contiguous fp32 [B, Cin, {cfg.H}, {cfg.W}], got {feat.dtype} {tuple(feat.shape)}")
+        Cin = feat.shape[1]
+        w2 = weight.reshape(weight.shape[0], -1)
+        if weight.dtype != torch.float32 or tuple(w2.shape) != (cfg.C, Cin) or not w2.is_contiguous():
+            raise ValueError(f"weight must be contiguous fp32 [{cfg.C}, {Cin}(, 1, 1)], got {weight.dtype} {tuple(weight.shape)}")
+        if bias is not None and (bias.dtype != torch.float32 or tuple(bias.shape) != (cfg.C,) or not bias.is_contiguous()):
+            raise ValueError(f"bias must be contiguous fp32 [{cfg.C}]")
+        for t in (feat, weight, bias):
+            if t is not None and t.device != self.device:
+                raise ValueError(f"tensor on {t.device}, parser on {self.device}")
+        return feat.shape[0], Cin
+
+    def _emit_buffers(self, B: int, emit: bool):
+        if not emit:
+            return None, None
+        cfg = self.cfg
+        return (torch.empty(B, cfg.C, cfg.H, cfg.W, dtype=torch.float32, device=self.device),
+                torch.empty(B, cfg.C, cfg.H, cfg.W, dtype=torch.float32, device=self.device))
+
+    def head_gemm_argmax(self, feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, emit: bool = False):
+        """The fused head kernel alone (``ppn_head_gemm_argmax``): 1x1 convolution on the tensor cores, sigmoid and
+        limb-window arg-max in the epilogue.  -> (dec [B, 6K, H, W] fp32, amax [B, E, H, W] uint16, logits, head);
+        the last two are the convolution output and its sigmoid [B, C, H, W] when ``emit`` (parity tests), else None."""
+        B, Cin = self._check_features(feat, weight, bias)
+        cfg = self.cfg
+        dec = torch.empty(B, 6 * cfg.K, cfg.H, cfg.W, dtype=torch.float32, device=self.device)
+        amax = torch.empty(B, cfg.E, cfg.H, cfg.W, dtype=torch.uint16, device=self.device)
+        logits, head = self._emit_buffers(B, emit)
+        with self._guard():
+            _lib.check(self.lib.ppn_head_gemm_argmax(feat.data_ptr(), weight.data_ptr(), _ptr(bias), Cin, C.byref(self._shape(B)),
+                                                     dec.data_ptr(), amax.data_ptr(), _ptr(logits), _ptr(head),
+                                                     torch.cuda.current_stream(self.device).cuda_stream), "ppn_head_gemm_argmax")
+        return dec, amax, logits, head
+
+    def parse_features(self, feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                       out: Optional[PackedHumans] = None, emit: bool = False):
+        """``sigmoid(conv3(feat))`` parsed into humans without the head tensor ever being written
+        (``ppn_head_parse``): feat = the input of the network's last layer [B, Cin, H, W] (model.py:133), weight / bias
+        = ``conv3``'s.  Asynchronous on torch's current stream.  -> PackedHumans, or (PackedHumans, logits, head) when
+        ``emit`` — the kernel then also writes the convolution output and its sigmoid for parity checks."""
+        B, Cin = self._check_features(feat, weight, bias)
+        if out is None:
+            out = self.alloc_output(B)
+        need = C.c_size_t()
+        _lib.check(self.lib.ppn_head_workspace_bytes(C.byref(self._shape(B)), C.byref(need)), "ppn_head_workspace_bytes")
+        if getattr(self, "_head_ws", None) is None or self._head_ws.numel() < need.value:
+            self._head_ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+        logits, head = self._emit_buffers(B, emit)
+        hs = self._humans_struct(out)
+        with self._guard():
+            _lib.check(self.lib.ppn_head_parse(feat.data_ptr(), weight.data_ptr(), _ptr(bias), Cin, C.byref(self._shape(B)),
+                                               C.byref(self.c.params), C.byref(hs), self._head_ws.data_ptr(), self._head_ws.numel(),
+                                               _ptr(logits), _ptr(head), torch.cuda.current_stream(self.device).cuda_stream),
+                       "ppn_head_parse")
+        return (out, logits, head) if emit else out
+
     # ---- keypoints (what drawing and AP evaluation read off the boxes) ------------------- #
     def part_centres(self, humans: PackedHumans) -> torch.Tensor:
         """fp32 [B, R, K, 2] = (y, x) centre of every part's box, (0, 0) where absent
