@@ -11,7 +11,8 @@
 // computed on the 5th-generation tensor cores: tcgen05.mma kind::tf32 (fp32 operands read from shared
 // memory, fp32 accumulation — the precision class of the reference's own cuDNN convolution, which
 // PyTorch runs in TF32 by default), 128 x 256 accumulator tiles in tensor memory (TMEM), operands
-// brought in by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a 4-stage mbarrier ring.
+// brought in by TMA (cp.async.bulk.tensor, 128-byte swizzle; 32-byte swizzle atoms for the MN-major
+// activations) through a 4-stage mbarrier ring.
 // Cells are the M dimension on purpose: an accumulator row (TMEM lane) then belongs to ONE cell and
 // the epilogue thread that owns the lane scans the channels in order, keeping numpy's running
 // (max, first index) per limb window in registers — the same per-thread rule as the streaming
@@ -81,23 +82,26 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// Shared-memory matrix descriptor (sm_100 format: version 1, 128-byte swizzle); offsets in bytes.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t leading_bytes, uint32_t stride_bytes) {
+// Shared-memory matrix descriptor (sm_100 format: version 1); offsets in bytes.  layout: 2 = 128-byte swizzle of
+// 16-byte chunks (K-major operands), 1 = 128-byte swizzle of 32-byte chunks — the only layout the tensor core
+// accepts for an MN-major operand of 32-bit elements (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); with the plain
+// 128-byte swizzle the instruction is silently dropped (measured: all-zero accumulators).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t leading_bytes, uint32_t stride_bytes, uint32_t layout) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((leading_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((stride_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((stride_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 // 32 lanes x 32 consecutive columns of TMEM -> 32 registers per thread (thread = lane)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;"            // the registers are defined only after the wait: keep both in one statement
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
           "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
           "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // torch.sigmoid's fp32 expression, 1 / (1 + exp(-x)): libdevice expf, one add, one IEEE division
 __device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
@@ -176,7 +180,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B tf32, A MN-major (cells contiguous), B K-major, M = 128, N = 256
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
-                                   ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+                             ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
@@ -190,10 +194,11 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                         const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes), sb = sa + kABytes;
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
-                            // A: 8 k-rows of 128 B = one swizzle atom per cell group, groups 4096 B apart;
-                            // B: 8 channel rows of 128 B per atom (1024 B), K advanced by 32 B inside the row
-                            const uint64_t da = smem_desc(sa + kk * 1024, kGroupBytes, 1024);
-                            const uint64_t db = smem_desc(sb + kk * kUmmaK * 4, 16, 1024);
+                            // A (MN-major): k-rows of 128 B (32 cells), swizzle atoms of 4 rows (512 B), 8 rows per
+                            //    instruction, cell groups 4096 B apart;
+                            // B (K-major): 8 channel rows of 128 B per atom (1024 B), K advanced by 32 B inside the row
+                            const uint64_t da = smem_desc(sa + kk * 1024, kGroupBytes, 512, 1);
+                            const uint64_t db = smem_desc(sb + kk * kUmmaK * 4, 16, 1024, 2);
                             tc_mma_tf32(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
                         }
                         tc_commit(&empty[stage]);                        // the stage is free once these MMAs have read it
@@ -224,7 +229,6 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     if (c0 >= a.C) break;                                 // uniform
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN + ch * 32), r);
-                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int c = c0 + j;
@@ -315,7 +319,7 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
         const cuuint32_t box[3] = {32, (cuuint32_t)kBlockK, 1};
         const cuuint32_t es[3] = {1, 1, 1};
         if (enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
     {   // weights [C][Cin] fp32: box = 32 input channels x 256 output channels

@@ -1307,7 +1307,10 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 // take their place with one atomicAdd on header[0] (which the caller zeroes before the launch), so
 // the ORDER of the images' blocks is arbitrary and header.start[b] says where image b begins.
 struct DenseOut {
-    int32_t* header;       // nullptr: no dense output
+    int32_t* header;       // nullptr: no dense output.  Always LOCAL memory: the cursor is an atomic
+    int32_t* rheader;      // nullptr, or the header of the buffer the entries go to when that is ANOTHER buffer — e.g. the
+                           // gather root's, mapped over NVLink: the per-image table is then stored there as well, and
+                           // idcell / score / box below point into that buffer (plain stores, nothing is read back)
     uint32_t* idcell;
     float* score;
     float4* box;
@@ -1534,6 +1537,11 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
             dense.header[2 + gb] = base_s;
             dense.header[2 + B + gb] = n_ent;
             dense.header[2 + 2 * B + gb] = start;
+            if (dense.rheader) {
+                dense.rheader[2 + gb] = base_s;
+                dense.rheader[2 + B + gb] = n_ent;
+                dense.rheader[2 + 2 * B + gb] = start;
+            }
             if (start + n_ent > dense.cap) dense.header[1] = 1;
             ebase_s = start + n_ent > dense.cap ? -1 : start;           // -1: the image's entries do not fit
         }
@@ -1598,6 +1606,11 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
         dense.header[2 + gb] = 0;
         dense.header[2 + B + gb] = 0;
         dense.header[2 + 2 * B + gb] = 0;
+        if (dense.rheader) {
+            dense.rheader[2 + gb] = 0;
+            dense.rheader[2 + B + gb] = 0;
+            dense.rheader[2 + 2 * B + gb] = 0;
+        }
     }
     if (tid == 0) h_count[b] = n_keep > 0 ? base_s : 0;
     // ---- the last CTA publishes this call's sequence number ------------------------------------------
@@ -2340,10 +2353,10 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
         smem = fused_layout(g, staged).total;
         if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
     }
-    DenseOut dense = {nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+    DenseOut dense = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
     if (dense_to) {
         if (g.K > 32) return cudaErrorInvalidConfiguration;          // present-part masks are 32 bits
-        dense = DenseOut{dense_to->header, dense_to->idcell, dense_to->score, reinterpret_cast<float4*>(dense_to->box),
+        dense = DenseOut{dense_to->header, dense_to->rheader, dense_to->idcell, dense_to->score, reinterpret_cast<float4*>(dense_to->box),
                          dense_to->cap, dense_to->skip_slots, dense_to->B_total, dense_to->b0};
     }
     // chain_mode 0: plain launch; 1: programmatic dependent that triggers after its wait;

@@ -96,7 +96,8 @@ bool parse_fused_split(const Geom& g, int stage_pref, const Tuning& t, FusedSpli
 size_t parse_fused_smem_bytes(const Geom& g, int stage_pref);
 // dense (human, part) entry buffer written by the fused kernel itself (header[0..1] cleared by the arg-max kernel)
 struct DenseTarget { int32_t* header; uint32_t* idcell; float* score; float* box; int32_t cap; int32_t skip_slots;
-                     int32_t B_total; int32_t b0; };
+                     int32_t B_total; int32_t b0;
+                     int32_t* rheader = nullptr; };   // set: idcell/score/box belong to another buffer (e.g. a peer's), whose header this is
 cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable& ch, float det_thr, float nms_thr, int min_kp,
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
                                float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
