@@ -18,6 +18,7 @@
  *   ppn_parse_host ......... the same from host memory (the reference's numpy arrays), with the
  *                            copies the reference's `.cpu()` calls stand for done here in reverse
  *   ppn_parse_dense ........ ppn_parse that also emits dense (human, part) records (what a multi-GPU job gathers)
+ *   ppn_parse_dense_remote . the same with the records stored straight into a peer GPU's buffer over NVLink
  *   ppn_head_parse ......... the network's last layer fused in: conv3 (1x1) + sigmoid, model.py:85,133-136, then
  *                            the whole parse, without the head tensor ever reaching memory
  *   ppn_encode_targets ..... the inverse of the path: the "# Encode samples" half of
@@ -31,8 +32,8 @@
  *   - device entry points only ENQUEUE work on `stream`; they never synchronise and never
  *     allocate (one exception: 2 KB of work counters per device on the very first launch).  The caller owns every buffer (torch tensors in the Python host layer) and
  *     selects the device (cudaSetDevice / torch.cuda.set_device) before calling.
- *   - thread-safe for distinct streams and buffers; no global mutable state except the
- *     tuning table set by ppn_tune() (meant for benchmarking, set once before use).
+ *   - thread-safe for distinct streams and buffers.  The only global mutable state is the benchmark tuning
+ *     table of include/ppn_decode_bench.h (not part of this interface); every call works on one snapshot of it.
  *   - head tensor: fp32 (or fp16 / bf16, PPNShape.head_dtype), NCHW contiguous [B, 6K + sH*sW*E, H, W]; channel groups resp, conf,
  *     x, y, w, h (K each) then the limb block viewed as [E, sH, sW, H, W] (model.py:64,
  *     rt_test.py:109-120).  16-byte aligned base.
@@ -105,6 +106,11 @@ typedef struct PPNParams {
  * Then the call's arg-max and decode kernels may start while the previous ppn_parse on the same
  * stream is still in its tree parse; results still complete in call order. */
 #define PPN_FLAG_INPUT_COMPLETE 1
+/* Slots [count[b], R) of the result normally keep whatever the caller's buffers held.  With this flag the call
+ * first clears the result arrays on the stream (root_cell / part_cell = -1, scores and boxes = 0), so that a
+ * consumer may scan all R slots.  Costs one pass over the result arrays and orders the call after the memsets
+ * (consecutive calls no longer overlap). */
+#define PPN_FLAG_CLEAR_UNUSED 2
 
 /* Packed result, device memory owned by the caller.  Humans of image b occupy slots
  * [0, min(count[b], R)) in descending root-score (NMS) order, as the reference's list is. */
@@ -127,9 +133,19 @@ int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* 
 /* Number of kernel launches one ppn_parse call enqueues for this shape. */
 int ppn_parse_launches(const PPNShape* shape, const PPNParams* params);
 
+/* How ppn_parse will run this shape: info[4] = {kernel launches, sub-batches of the two-kernel chain, shared-memory
+ * bytes the arg-max ring is capped to so that the parse CTAs fit beside it (0 = uncapped), 1 if delta is staged}. */
+int ppn_parse_plan(const PPNShape* shape, const PPNParams* params, int32_t* info /*[4]*/);
+
 /* amax[B, E, H*W] (uint16) = index in [0, sH*sW) of the FIRST maximum of each limb window;
  * NaN counts as the maximum (numpy argmax).  Streams the limb block once. */
 int ppn_limb_argmax(const void* head, const PPNShape* shape, uint16_t* amax, void* stream);
+
+/* Measurement aid: the SAME bulk-copy ring as ppn_limb_argmax moving the same bytes through shared memory, but
+ * the consumers only release the stages — no compares, nothing written.  Its duration is the read ceiling of this
+ * access pattern on this GPU (bench.py: roofline.read_peak_gbs).  smem_cap > 0 bounds the ring like ppn_parse does
+ * when the parse kernel's CTAs must fit beside it.  `amax` is not written (pass the buffer a real call would get). */
+int ppn_limb_stream_probe(const void* head, const PPNShape* shape, uint16_t* amax, int32_t smem_cap, void* stream);
 
 /* For parts 0..n_parts-1 of every image: cells with resp*conf > det_thresh in ascending cell
  * order, with score and box.  Lists are [B, n_parts, H*W]; cand_count is [B, n_parts]. */
@@ -171,7 +187,8 @@ int ppn_parse(const void* head, const PPNShape* shape, const PPNParams* params,
 /* The whole path from HOST memory (pinned for full speed): uploads `head` in chunks
  * overlapped with the kernels, runs ppn_parse, downloads the packed result into the HOST
  * arrays of `out_host`.  Synchronous.  dev_scratch/dev_scratch_bytes: device memory of at
- * least ppn_parse_host_scratch_bytes(). */
+ * least ppn_parse_host_scratch_bytes().  Of every image only the first max_b min(count[b], R) slots are copied
+ * back (the others carry no humans; their host bytes are left as they were). */
 int ppn_parse_host_scratch_bytes(const PPNShape* shape, const PPNParams* params, int32_t R, size_t* bytes);
 int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams* params,
                    const PPNHumans* out_host, void* dev_scratch, size_t dev_scratch_bytes);
@@ -207,6 +224,32 @@ int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_e
 int ppn_parse_dense(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
                     void* packed, size_t packed_bytes, int32_t cap_entries, int32_t skip_slots,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- multi-GPU pose gather over peer memory ----------------------------------------------
+ * Images are sharded over the GPUs of one box with no data-path collective; what has to travel is each rank's
+ * poses.  ppn_parse_dense_remote is ppn_parse_dense whose entry stores go to ANOTHER buffer of the same layout —
+ * typically the gather root's, mapped into this process over NVLink (ppn_peer_open) — straight from the parse
+ * kernel: `remote_packed` receives the per-image table {count, entries, start} and the idcell / score / box
+ * entries (plain stores; nothing is read back, the block cursor stays in `local_header`), so the gather costs no
+ * extra kernel, copy or collective on the compute stream.  header[0..1] of the remote buffer are not written: the
+ * reader derives the total as sum(entries) and overflow as any(start + entries > cap_entries).  Only where the
+ * fused parse kernel writes the entries itself (n_nms_parts == 1, K <= 32, H*W <= PPN_MAX_CELLS and a batch the
+ * two-kernel chain takes): PPN_E_UNSUPPORTED otherwise.  `local_header`: >= 4 * (2 + 3B) bytes, 256-byte aligned.
+ *
+ * ppn_peer_alloc / _open / _close / _free wrap cudaMalloc + cudaIpcGetMemHandle and cudaIpcOpenMemHandle (which
+ * enables peer access) so that the host layer can exchange the 64-byte handle through its process group
+ * (torch.distributed) and hand the kernels raw peer pointers; ppn_peer_copy is one cudaMemcpyAsync (direction
+ * inferred from the pointers; copy engine, no SM) — between two such buffers for gather variants that ship a group
+ * of steps at a time, or into pinned host memory to read the root's buffer. */
+#define PPN_IPC_HANDLE_BYTES 64
+int ppn_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle /*[64]*/);
+int ppn_peer_open(const unsigned char* handle /*[64]*/, void** dev_ptr);
+int ppn_peer_close(void* dev_ptr);
+int ppn_peer_free(void* dev_ptr);
+int ppn_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int ppn_parse_dense_remote(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+                           void* local_header, size_t local_header_bytes, void* remote_packed, size_t remote_bytes,
+                           int32_t cap_entries, int32_t skip_slots, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- the network head fused in ---------------------------------------------------
  * Replaces `conv3_out = self.conv3(lRelu2); out = self.sigmoid(conv3_out)` (model.py:133-136) TOGETHER with the
@@ -254,25 +297,6 @@ typedef struct PPNTargets {
  * PPN_E_UNSUPPORTED otherwise. */
 int ppn_encode_targets(const PPNPeople* people, const PPNShape* shape, const int32_t* edges,
                        const PPNTargets* out, void* stream);
-
-/* Per-stage timing of ppn_parse for benchmarks.  After ppn_profile_enable(1) every ppn_parse
- * call (up to 4096) records CUDA events on its stream at the stage boundaries;
- * ppn_profile_read() waits for them and returns the summed milliseconds of the four stages
- * {limb arg-max, decode, NMS, tree parse} and the number of calls covered, then resets. */
-int ppn_profile_enable(int32_t on);
-int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
-
-/* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
- * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
- * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
- * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "argmax16.threads", "argmax16.stage_bytes" (ring shape
- * for 16-bit heads), "argmax.cluster" (tiny batches: -1 auto, 0 never, 2/4/8 = CTAs per matrix),
- * "parse.fused" (-1 auto, 0 three-kernel chain, 1 two-kernel chain whenever supported, cutting large batches),
- * "parse.chain_calls", "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
- * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images",
- * "encode.sweep" (1 = address-ordered persistent sweep), "encode.ctas_per_sm".  Returns PPN_E_BADARG for an unknown key. */
-int ppn_tune(const char* key, int32_t value);
-int ppn_tune_get(const char* key, int32_t* value);
 
 #ifdef __cplusplus
 }

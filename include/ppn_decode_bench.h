@@ -1,0 +1,40 @@
+/*
+ * libppn_decode — benchmark and profiling hooks.  NOT part of the drop-in interface (include/ppn_decode.h): nothing a
+ * host of the parser needs is declared here.  bench.py, scripts/ and the tuning-sweep tests use them.
+ *
+ *   - ppn_tune writes one process-wide table under a lock; every entry point of ppn_decode.h takes a snapshot of the
+ *     table when it starts, so a concurrent writer never changes a call in flight.
+ *   - ppn_profile_* is single-threaded by contract (one benchmark thread).
+ */
+#ifndef PPN_DECODE_BENCH_H_
+#define PPN_DECODE_BENCH_H_
+
+#include "ppn_decode.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-stage timing of ppn_parse for benchmarks.  After ppn_profile_enable(1) every ppn_parse
+ * call (up to 4096) records CUDA events on its stream at the stage boundaries;
+ * ppn_profile_read() waits for them and returns the summed milliseconds of the four stages
+ * {limb arg-max, decode, NMS, tree parse} and the number of calls covered, then resets. */
+int ppn_profile_enable(int32_t on);
+int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
+
+/* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
+ * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
+ * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
+ * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "argmax16.threads", "argmax16.stage_bytes" (ring shape
+ * for 16-bit heads), "argmax.cluster" (tiny batches: -1 auto, 0 never, 2/4/8 = CTAs per matrix),
+ * "parse.fused" (-1 auto, 0 three-kernel chain, 1 two-kernel chain whenever supported, cutting large batches),
+ * "parse.chain_calls", "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
+ * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images",
+ * "encode.sweep" (1 = address-ordered persistent sweep), "encode.ctas_per_sm".  Returns PPN_E_BADARG for an unknown key. */
+int ppn_tune(const char* key, int32_t value);
+int ppn_tune_get(const char* key, int32_t* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPN_DECODE_BENCH_H_ */

@@ -233,6 +233,7 @@ def main():
     import config as refcfg                      # the reference's config.py
     assert refcfg.KEYPOINT_NAMES == pcfg.KEYPOINT_NAMES and refcfg.EDGES == pcfg.EDGES
     assert refcfg.DIRECTED_GRAPHS == pcfg.DIRECTED_GRAPHS and refcfg.EDGES_BY_NAME == pcfg.EDGES_BY_NAME
+    assert refcfg.COLOR_MAP == pcfg.COLOR_MAP and list(refcfg.COLOR_MAP) == list(pcfg.COLOR_MAP)
 
     tg = tiny_geometry()
     for seed in (11, 12, 13):

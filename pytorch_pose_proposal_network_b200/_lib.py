@@ -13,9 +13,11 @@ from . import build as _build
 ABI_VERSION = 5
 HEAD_F32, HEAD_F16, HEAD_BF16 = 0, 1, 2
 FLAG_INPUT_COMPLETE = 1
+FLAG_CLEAR_UNUSED = 2
 MAX_CELLS = 1024
 MAX_CHAINS = 32
 MAX_CHAIN_STEPS = 192
+IPC_HANDLE_BYTES = 64
 
 i32p = C.POINTER(C.c_int32)
 f32p = C.POINTER(C.c_float)
@@ -56,7 +58,9 @@ EXPORTS = {
     "ppn_strerror": (C.c_char_p, [C.c_int]),
     "ppn_workspace_bytes": (C.c_int, [C.POINTER(PPNShape), C.POINTER(PPNParams), C.POINTER(C.c_size_t)]),
     "ppn_parse_launches": (C.c_int, [C.POINTER(PPNShape), C.POINTER(PPNParams)]),
+    "ppn_parse_plan": (C.c_int, [C.POINTER(PPNShape), C.POINTER(PPNParams), i32p]),
     "ppn_limb_argmax": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.c_void_p, C.c_void_p]),
+    "ppn_limb_stream_probe": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.c_void_p, C.c_int32, C.c_void_p]),
     "ppn_decode_candidates": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.c_int32, C.c_float,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ppn_restore_xy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(PPNShape), C.c_void_p]),
@@ -76,6 +80,14 @@ EXPORTS = {
     "ppn_pack_humans": (C.c_int, [C.POINTER(PPNHumans), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ppn_parse_dense": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.POINTER(PPNParams), C.POINTER(PPNHumans),
                                   C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ppn_parse_dense_remote": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.POINTER(PPNParams), C.POINTER(PPNHumans),
+                                         C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ppn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ppn_peer_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ppn_peer_close": (C.c_int, [C.c_void_p]),
+    "ppn_peer_free": (C.c_int, [C.c_void_p]),
+    "ppn_peer_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ppn_head_workspace_bytes": (C.c_int, [C.POINTER(PPNShape), C.POINTER(C.c_size_t)]),
     "ppn_head_gemm_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PPNShape), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -6,7 +6,7 @@ and the parser geometry in module globals of ``datatest.py``
 call sites (0.15 at rt_test.py:133 / main.py:972,1141; NMS 0.3 at datatest.py:94;
 ``min_num_keypoints=1`` at datatest.py:74).  Here all of that is one explicit,
 immutable :class:`PPNConfig`; the module-level names ``KEYPOINT_NAMES``, ``EDGES``,
-``EDGES_BY_NAME``, ``TRACK_ORDERS``, ``DIRECTED_GRAPHS`` and ``EPSILON`` keep the
+``EDGES_BY_NAME``, ``TRACK_ORDERS``, ``DIRECTED_GRAPHS``, ``COLOR_MAP`` and ``EPSILON`` keep the
 reference's spelling and values so ``from config import *`` call sites still work.
 """
 from __future__ import annotations
@@ -70,6 +70,16 @@ def directed_graphs(track_orders, edges_by_name, keypoint_names):
 
 DIRECTED_GRAPHS = directed_graphs(TRACK_ORDERS, EDGES_BY_NAME, KEYPOINT_NAMES)
 EPSILON = 1e-6
+
+# Drawing colours of the parts (config.py:23-42): the consumers of the parser's output (datatest.draw_humans,
+# datatest.py:170-221) look parts up here.  One RGB triple per entry of KEYPOINT_NAMES, in that order; the dict
+# keeps the reference's key order (instance, right arm, left arm, right leg, left leg, trunk).
+_PALETTE = ("8f2323 0040ff 4f8f23 0095ff 6aff00 00eaff bfff00 6b238f 23628f aa00ff b9d7ed dcb9ed b9ede0 "
+            "ffff00 ff00aa edb9b9 ff0000 4f2323").split()
+_RGB = {n: tuple(int(h[i:i + 2], 16) for i in (0, 2, 4)) for n, h in zip(KEYPOINT_NAMES, _PALETTE)}
+COLOR_MAP = {n: _RGB[n] for n in (["instance"] + [f"{s}_{j}" for s in ("right", "left") for j in _ARM]
+                                  + [f"{s}_{j}" for s in ("right", "left") for j in _LEG]
+                                  + ["thorax", "pelvis", "neck", "top", "stomach"])}
 
 # --------------------------------------------------------------------------- #
 # 16-part skeleton used by BASELINE.json configs[0:2] ("MPII 16-part PPN"):

@@ -5,14 +5,22 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
-#include <unordered_map>
 
 #include "ppn_decode.h"
+#include "ppn_decode_bench.h"
 #include "ppn_kernels.h"
 
 namespace {
 
-ppn::Tuning g_tuning;
+// Tuning table (ppn_tune, declared in include/ppn_decode_bench.h).  Written under a lock; every entry point takes
+// ONE snapshot when it starts (a local named g_tuning), so a call never sees a half-updated table and concurrent
+// calls on other threads are unaffected by a writer.
+ppn::Tuning g_tuning_shared;
+std::mutex g_tune_mu;
+ppn::Tuning tuning_now() {
+    std::lock_guard<std::mutex> lock(g_tune_mu);
+    return g_tuning_shared;
+}
 
 // ---- optional per-stage timing of ppn_parse (ppn_profile_*) --------------------------------
 // When enabled, ppn_parse runs its kernels back to back and brackets each with a (start, stop)
@@ -61,7 +69,7 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? PPN_OK : (int)e; }
 int check_shape(const PPNShape* s) {
     if (!s) return PPN_E_BADARG;
     if (s->B < 0 || s->K < 1 || s->E < 0 || s->H < 1 || s->W < 1 || s->sH < 1 || s->sW < 1) return PPN_E_BADARG;
-    if (s->inW < 1 || s->inH < 1 || s->gridW < 0 || s->gridH < 0) return PPN_E_BADARG;
+    if (s->inW < 1 || s->inH < 1 || s->gridW < 0 || s->gridH < 0) return PPN_E_BADARG;   // gridW/H = int(in/out) may be 0 for the parser
     if ((long long)s->sH * s->sW > 65535) return PPN_E_UNSUPPORTED;            // arg-max map is uint16
     if (s->K > 255 || s->E > 255) return PPN_E_UNSUPPORTED;                    // chain tables are uint8
     const long long per_img = ((long long)6 * s->K + (long long)s->sH * s->sW * s->E) * s->H * s->W;
@@ -143,16 +151,9 @@ Workspace carve(const PPNShape* s, int n_parts) {
     return w;
 }
 
-// ppn_parse alternates between the two halves of the caller's workspace from call to call, so that
-// a call may overlap the previous one (PPN_FLAG_INPUT_COMPLETE) without sharing scratch with it.
-// Host state: one counter per distinct workspace address ever passed (never erased: a few bytes).
-std::mutex g_parity_mu;
-std::unordered_map<void*, unsigned> g_parity;
-
-unsigned next_parity(void* workspace) {
-    std::lock_guard<std::mutex> lock(g_parity_mu);
-    return g_parity[workspace]++ & 1u;
-}
+// ppn_parse alternates between the two halves of the caller's workspace from call to call on a stream
+// (ppn::next_call_parity), so that a call may overlap the previous one (PPN_FLAG_INPUT_COMPLETE) without
+// sharing scratch with it.
 
 int check_params(const PPNShape* s, const PPNParams* p) {
     if (!p) return PPN_E_BADARG;
@@ -210,7 +211,8 @@ const char* ppn_strerror(int code) {
 
 int ppn_tune(const char* key, int32_t value) {
     if (!key) return PPN_E_BADARG;
-    ppn::Tuning& t = g_tuning;
+    std::lock_guard<std::mutex> lock(g_tune_mu);
+    ppn::Tuning& t = g_tuning_shared;
     if (!std::strcmp(key, "argmax.variant")) t.argmax_variant = value;
     else if (!std::strcmp(key, "argmax.stage_bytes")) t.argmax_stage_bytes = value <= 0 ? 0 : (value < 1024 ? 1024 : value);
     else if (!std::strcmp(key, "argmax.stages")) t.argmax_stages = value < 2 ? 2 : (value > 32 ? 32 : value);
@@ -236,7 +238,7 @@ int ppn_tune(const char* key, int32_t value) {
 
 int ppn_tune_get(const char* key, int32_t* value) {
     if (!key || !value) return PPN_E_BADARG;
-    const ppn::Tuning& t = g_tuning;
+    const ppn::Tuning t = tuning_now();
     if (!std::strcmp(key, "argmax.variant")) *value = t.argmax_variant;
     else if (!std::strcmp(key, "argmax.stage_bytes")) *value = t.argmax_stage_bytes;
     else if (!std::strcmp(key, "argmax.stages")) *value = t.argmax_stages;
@@ -270,6 +272,7 @@ int ppn_workspace_bytes(const PPNShape* shape, const PPNParams* params, size_t* 
 }
 
 int ppn_parse_launches(const PPNShape* shape, const PPNParams* params) {
+    const ppn::Tuning g_tuning = tuning_now();
     if (check_shape(shape) || check_params(shape, params)) return 0;
     if (shape->B <= 0) return 0;
     const ppn::Geom g = make_geom(shape);
@@ -281,13 +284,46 @@ int ppn_parse_launches(const PPNShape* shape, const PPNParams* params) {
     return 3;
 }
 
+int ppn_parse_plan(const PPNShape* shape, const PPNParams* params, int32_t* info) {
+    const ppn::Tuning g_tuning = tuning_now();
+    if (!info) return PPN_E_BADARG;
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_params(shape, params))) return rc;
+    info[0] = ppn_parse_launches(shape, params);
+    info[1] = 1; info[2] = 0; info[3] = 0;
+    if (shape->B <= 0) return PPN_OK;
+    ppn::FusedSplit split;
+    if (params->n_nms_parts == 1 && ppn::parse_fused_split(make_geom(shape), g_tuning.parse_stage_all, g_tuning, &split)) {
+        info[1] = split.n_sub;
+        info[2] = (int32_t)split.ring_cap;
+        info[3] = split.staged ? 1 : 0;
+    }
+    return PPN_OK;
+}
+
 int ppn_limb_argmax(const void* head, const PPNShape* shape, uint16_t* amax, void* stream) {
+    const ppn::Tuning g_tuning = tuning_now();
     int rc = check_shape(shape);
     if (rc) return rc;
     if (shape->B == 0 || shape->E == 0) return PPN_OK;
     if (!head || !amax) return PPN_E_BADARG;
     if (misaligned(head, shape)) return PPN_E_BADARG;
     return cuda_rc(ppn::launch_limb_argmax(head, amax, make_geom(shape), g_tuning, (cudaStream_t)stream));
+}
+
+int ppn_limb_stream_probe(const void* head, const PPNShape* shape, uint16_t* amax, int32_t smem_cap, void* stream) {
+    const ppn::Tuning g_tuning = tuning_now();
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (shape->B == 0 || shape->E == 0) return PPN_OK;
+    if (!head || !amax) return PPN_E_BADARG;
+    if (misaligned(head, shape)) return PPN_E_BADARG;
+    ppn::Tuning t = g_tuning;
+    t.argmax_dry = 1;
+    t.argmax_cluster = 0;                              // the ring kernels are what is being probed
+    if (smem_cap > 0) t.argmax_smem_cap = smem_cap;
+    return cuda_rc(ppn::launch_limb_argmax(head, amax, make_geom(shape), t, (cudaStream_t)stream));
 }
 
 int ppn_decode_candidates(const void* head, const PPNShape* shape, int32_t n_parts, float det_thresh,
@@ -381,8 +417,63 @@ int ppn_parse_dense(const void* head, const PPNShape* shape, const PPNParams* pa
     return parse_impl(head, shape, params, out, workspace, workspace_bytes, stream, &d);
 }
 
+int ppn_parse_dense_remote(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
+                           void* local_header, size_t local_header_bytes, void* remote_packed, size_t remote_bytes,
+                           int32_t cap_entries, int32_t skip_slots, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (cap_entries < 0) return PPN_E_BADARG;
+    if (shape->K > 32 || (long long)shape->H * shape->W > PPN_MAX_CELLS) return PPN_E_UNSUPPORTED;
+    if (shape->B == 0) return PPN_OK;
+    if (!local_header || !remote_packed || (reinterpret_cast<uintptr_t>(local_header) & 255) ||
+        (reinterpret_cast<uintptr_t>(remote_packed) & 255)) return PPN_E_BADARG;
+    const PackedLayout l = packed_layout(shape->B, cap_entries);
+    if (remote_bytes < l.total || local_header_bytes < (size_t)(2 + 3 * (size_t)shape->B) * sizeof(int32_t)) return PPN_E_WORKSPACE;
+    unsigned char* p = static_cast<unsigned char*>(remote_packed);
+    ppn::DenseTarget d;
+    d.header = static_cast<int32_t*>(local_header);
+    d.rheader = reinterpret_cast<int32_t*>(p + l.header);
+    d.idcell = reinterpret_cast<uint32_t*>(p + l.idcell);
+    d.score = reinterpret_cast<float*>(p + l.score);
+    d.box = reinterpret_cast<float*>(p + l.box);
+    d.cap = cap_entries;
+    d.skip_slots = skip_slots != 0;
+    return parse_impl(head, shape, params, out, workspace, workspace_bytes, stream, &d);
+}
+
+int ppn_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle) {
+    if (!dev_ptr || !handle || bytes == 0) return PPN_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == PPN_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return (int)e;
+    if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess) { cudaFree(p); return (int)e; }
+    cudaIpcMemHandle_t h;
+    if ((e = cudaIpcGetMemHandle(&h, p)) != cudaSuccess) { cudaFree(p); return (int)e; }
+    std::memcpy(handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return PPN_OK;
+}
+
+int ppn_peer_open(const unsigned char* handle, void** dev_ptr) {
+    if (!dev_ptr || !handle) return PPN_E_BADARG;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    return cuda_rc(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+}
+
+int ppn_peer_close(void* dev_ptr) { return dev_ptr ? cuda_rc(cudaIpcCloseMemHandle(dev_ptr)) : PPN_E_BADARG; }
+int ppn_peer_free(void* dev_ptr) { return dev_ptr ? cuda_rc(cudaFree(dev_ptr)) : PPN_E_BADARG; }
+
+int ppn_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+    if (!dst || !src) return PPN_E_BADARG;
+    if (bytes == 0) return PPN_OK;
+    return cuda_rc(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+}
+
 static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
                       void* workspace, size_t workspace_bytes, void* stream, const ppn::DenseTarget* dense) {
+    const ppn::Tuning g_tuning = tuning_now();
     int rc = check_shape(shape);
     if (rc) return rc;
     if ((rc = check_params(shape, params))) return rc;
@@ -397,13 +488,21 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
     const int P = params->n_nms_parts;
     const Workspace w = carve(shape, P);
     if (workspace_bytes < 2 * w.total) return PPN_E_WORKSPACE;
-    unsigned char* ws = static_cast<unsigned char*>(workspace) + (next_parity(workspace) ? w.total : 0);
+    unsigned char* ws = static_cast<unsigned char*>(workspace) + (ppn::next_call_parity((cudaStream_t)stream) ? w.total : 0);
     uint16_t* amax = reinterpret_cast<uint16_t*>(ws + w.amax);
     int32_t* keep_idx = reinterpret_cast<int32_t*>(ws + w.keep_idx);
     int32_t* keep_count = reinterpret_cast<int32_t*>(ws + w.keep_count);
     const ppn::Geom g = make_geom(shape);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    if ((params->flags & PPN_FLAG_CLEAR_UNUSED) && !(dense && dense->skip_slots)) {
+        const size_t slots = (size_t)shape->B * out->R, SK = slots * shape->K;
+        if ((e = cudaMemsetAsync(out->root_cell, 0xFF, slots * sizeof(int32_t), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(out->part_cell, 0xFF, SK * sizeof(int32_t), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(out->part_score, 0, SK * sizeof(float), st)) != cudaSuccess) return (int)e;
+        if ((e = cudaMemsetAsync(out->part_box, 0, SK * 4 * sizeof(float), st)) != cudaSuccess) return (int)e;
+        ppn::chain_break(st);                        // what follows the memsets starts fully ordered
+    }
     // Three kernels.  The limb arg-max (K3) and decode+NMS (K12) are independent; the tree parse
     // (K4) needs both.  parse.overlap selects how they are ordered:
     //   2  one stream, programmatic dependent launches: K12 starts, K3 starts beside it at once
@@ -438,6 +537,7 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
     // chain stays intact) or, on the other paths and for K > 32, by the pack kernels after the
     // fixed-stride result
     const bool dense_fused = dense && fused && shape->K <= 32;
+    if (dense && dense->rheader && !dense_fused) return PPN_E_UNSUPPORTED;
     if (fused) {
         using namespace ppn;
         Tuning tuning = g_tuning;
@@ -501,6 +601,7 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
         if (dense && !dense_fused) return pack_after(out, shape, dense, st);
         return PPN_OK;
     }
+    if (dense && dense->rheader) return PPN_E_UNSUPPORTED;     // remote entries are written by the fused parse kernel only
     ppn::chain_break(st);
     if (mode == 2) {
         using namespace ppn;
@@ -597,6 +698,7 @@ int ppn_head_gemm_argmax(const float* feat, const float* weight, const float* bi
 int ppn_head_parse(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
                    const PPNParams* params, const PPNHumans* out, void* workspace, size_t workspace_bytes,
                    float* emit_logits, float* emit_head, void* stream) {
+    const ppn::Tuning g_tuning = tuning_now();
     int rc = check_shape(shape);
     if (rc) return rc;
     if ((rc = check_params(shape, params))) return rc;
@@ -668,9 +770,11 @@ int ppn_pack_humans(const PPNHumans* humans, int32_t B, int32_t K, int32_t cap_e
 
 int ppn_encode_targets(const PPNPeople* people, const PPNShape* shape, const int32_t* edges,
                        const PPNTargets* out, void* stream) {
+    const ppn::Tuning g_tuning = tuning_now();
     int rc = check_shape(shape);
     if (rc) return rc;
     if (!people || !out) return PPN_E_BADARG;
+    if (shape->gridW < 1 || shape->gridH < 1) return PPN_E_BADARG;                     // the encoder divides by them
     if (shape->sH != shape->sW || (shape->sH & 1) == 0) return PPN_E_UNSUPPORTED;      // dataset.py:163-167
     if (shape->B == 0) return PPN_OK;
     if (!people->person_off || !out->delta || !out->weight || !out->tx || !out->ty || !out->tx_half || !out->ty_half ||
@@ -743,6 +847,7 @@ struct HostPlan {
     size_t off_head[2], off_ws[2], off_count, off_root, off_cell, off_score, off_box, total;
 };
 HostPlan plan_host(const PPNShape* s, const PPNParams* p, int R) {
+    const ppn::Tuning g_tuning = tuning_now();
     HostPlan h;
     h.chunk = g_tuning.host_chunk_images;
     if (h.chunk > s->B) h.chunk = s->B > 0 ? s->B : 1;
@@ -790,12 +895,19 @@ int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams
     const size_t K = (size_t)shape->K;
     const size_t per_img_b = ((size_t)6 * shape->K + (size_t)shape->sH * shape->sW * shape->E) * shape->H * shape->W * elem_bytes(shape);
 
-    // two streams ping-pong over two (head, workspace) buffer pairs: the upload of chunk i+1
-    // overlaps the kernels of chunk i; created once per thread and kept.
-    static thread_local cudaStream_t streams[2] = {nullptr, nullptr};
-    cudaError_t e;
+    // two streams ping-pong over two (head, workspace) buffer pairs: the upload of chunk i+1 overlaps the kernels
+    // of chunk i.  Created once per (thread, device) and kept.
+    struct HostLane { cudaStream_t s[2] = {nullptr, nullptr}; };
+    static thread_local HostLane t_lanes[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    cudaStream_t* streams = t_lanes[dev].s;
     for (int i = 0; i < 2; ++i)
         if (!streams[i] && (e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+    // whatever happens, no copy may still be in flight over the caller's buffers when we return
+    auto fail = [&](int code) { cudaStreamSynchronize(streams[0]); cudaStreamSynchronize(streams[1]); return code; };
 
     int32_t* d_count = reinterpret_cast<int32_t*>(d + h.off_count);
     int32_t* d_root = reinterpret_cast<int32_t*>(d + h.off_root);
@@ -811,7 +923,7 @@ int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams
         cudaStream_t st = streams[slot];
         void* d_head = d + h.off_head[slot];
         if ((e = cudaMemcpyAsync(d_head, static_cast<const unsigned char*>(head_host) + (size_t)b0 * per_img_b,
-                                 (size_t)nb * per_img_b, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)e;
+                                 (size_t)nb * per_img_b, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail((int)e);
         PPNShape cs = *shape;
         cs.B = nb;
         PPNHumans dev_out;
@@ -821,16 +933,26 @@ int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams
         dev_out.part_score = d_score + (size_t)b0 * R * K;
         dev_out.part_box = d_box + (size_t)b0 * R * K * 4;
         dev_out.R = R;
-        if ((rc = ppn_parse(d_head, &cs, &chunk_params, &dev_out, d + h.off_ws[slot], h.ws_bytes, st))) return rc;
-        // results of this chunk go home on the same stream, behind its kernels
-        if ((e = cudaMemcpyAsync(out_host->count + b0, dev_out.count, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemcpyAsync(out_host->root_cell + (size_t)b0 * R, dev_out.root_cell, (size_t)nb * R * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemcpyAsync(out_host->part_cell + (size_t)b0 * R * K, dev_out.part_cell, (size_t)nb * R * K * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemcpyAsync(out_host->part_score + (size_t)b0 * R * K, dev_out.part_score, (size_t)nb * R * K * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
-        if ((e = cudaMemcpyAsync(out_host->part_box + (size_t)b0 * R * K * 4, dev_out.part_box, (size_t)nb * R * K * 4 * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)e;
+        if ((rc = ppn_parse(d_head, &cs, &chunk_params, &dev_out, d + h.off_ws[slot], h.ws_bytes, st))) return fail(rc);
+        // the counts of this chunk go home behind its kernels; the slots follow once the largest count is known
+        if ((e = cudaMemcpyAsync(out_host->count + b0, dev_out.count, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail((int)e);
     }
     for (int i = 0; i < 2; ++i)
         if ((e = cudaStreamSynchronize(streams[i])) != cudaSuccess) return (int)e;
+    // Only slots [0, count[b]) of an image carry humans.  Copy the first m = max_b min(count[b], R) slots of every
+    // image (strided copies, one per array) instead of all R: at the BASELINE shapes that is several times fewer
+    // bytes over PCIe (cfg2: ~20 of 144 slots).  Slots >= count[b] of the host arrays are left untouched.
+    int m = 0;
+    for (int b = 0; b < shape->B; ++b) m = std::max(m, std::min(out_host->count[b], R));
+    if (m > 0) {
+        cudaStream_t st = streams[0];
+        const size_t B = (size_t)shape->B;
+        if ((e = cudaMemcpy2DAsync(out_host->root_cell, (size_t)R * 4, d_root, (size_t)R * 4, (size_t)m * 4, B, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail((int)e);
+        if ((e = cudaMemcpy2DAsync(out_host->part_cell, (size_t)R * K * 4, d_cell, (size_t)R * K * 4, (size_t)m * K * 4, B, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail((int)e);
+        if ((e = cudaMemcpy2DAsync(out_host->part_score, (size_t)R * K * 4, d_score, (size_t)R * K * 4, (size_t)m * K * 4, B, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail((int)e);
+        if ((e = cudaMemcpy2DAsync(out_host->part_box, (size_t)R * K * 16, d_box, (size_t)R * K * 16, (size_t)m * K * 16, B, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail((int)e);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return (int)e;
+    }
     return PPN_OK;
 }
 

@@ -101,7 +101,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
         int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
         for (int c = 0; c < p.chunks; ++c) {
             if (c > 0) mbar_wait(&full[stage], phase);
-            if (active) {
+            if (active && !p.dry) {
                 const int rows = min(p.rows, g.S - c * p.rows);
                 const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes) + cv;
                 int a = c * p.rows + grp;
@@ -132,6 +132,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         uint16_t* dst = amax + (size_t)m * g.HW;
+        if (p.dry) continue;
         if (p.G == 1) {
             if (active) {
                 const uint32_t lo = (uint32_t)i0 | ((uint32_t)i1 << 16), hi = (uint32_t)i2 | ((uint32_t)i3 << 16);
@@ -252,7 +253,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
         for (int c = 0; c < p.chunks; ++c) {
             if (c > 0) mbar_wait(&full[stage], phase);
-            if (active) {
+            if (active && !p.dry) {
                 const int rows = min(p.rows, g.S - c * p.rows);
                 const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
                 int a = c * p.rows;
@@ -282,7 +283,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if (active) {
+        if (active && !p.dry) {
             const uint32_t lo = (uint32_t)i0 | ((uint32_t)i1 << 16), hi = (uint32_t)i2 | ((uint32_t)i3 << 16);
             *reinterpret_cast<uint2*>(amax + (size_t)m * g.HW + 4 * cv) = make_uint2(lo, hi);
         }
@@ -414,7 +415,7 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
         for (int q = 0; q < 4; ++q) { best[q] = Packed16<T16>::kNegInf2; idx[q] = 0u; }
         for (int c = 0; c < p.chunks; ++c) {
             if (c > 0) mbar_wait(&full[stage], phase);
-            if (active) {
+            if (active && !p.dry) {
                 const int rows = min(p.rows, g.S - c * p.rows);
                 const uint4* col = reinterpret_cast<const uint4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
                 uint32_t a2 = (uint32_t)(c * p.rows) * 0x00010001u;       // the row index in both halves
@@ -444,7 +445,7 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        if (active) {
+        if (active && !p.dry) {
             bool any_nan = false;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -630,8 +631,8 @@ limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ am
 template <typename T>
 __global__ void __launch_bounds__(256)
 limb_argmax_generic_kernel(const T* __restrict__ head, uint16_t* __restrict__ amax, Geom g) {
-    const int m = blockIdx.y;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.x;                                             // matrices on grid.x: no 65 535 limit
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= g.HW) return;
     const int b = m / g.E, ei = m - b * g.E;
     const T* col = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW + c;
@@ -1770,7 +1771,7 @@ pack_entries_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
 // Kernels on different streams get different slots.
 constexpr int kTicketSlots = 64;
 constexpr int kSlotWords = 8;
-struct StreamSlot { cudaStream_t stream = nullptr; unsigned launches = 0; int published = 0; bool fast_open = false; };
+struct StreamSlot { cudaStream_t stream = nullptr; unsigned launches = 0; unsigned calls = 0; int published = 0; bool fast_open = false; };
 struct DeviceInfo { int* tickets = nullptr; StreamSlot slot[kTicketSlots]; int slots_used = 0;
                     int sms = 0; int smem_optin = 0; size_t tma = 0, tma_multi = 0, tma16[2] = {0, 0}, decode_nms[3] = {0, 0, 0}, ldg = 0, nms = 0,
                            tree[3] = {0, 0, 0}, tree_light[3] = {0, 0, 0}, fused[2][3] = {{0, 0, 0}, {0, 0, 0}}, cluster[3] = {0, 0, 0}; };
@@ -1815,11 +1816,42 @@ static cudaError_t slot_for(DeviceInfo* d, cudaStream_t st, StreamSlot** slot, i
     *words = nullptr;
     for (int i = 0; i < d->slots_used; ++i)
         if (d->slot[i].stream == st) { *slot = &d->slot[i]; *words = d->tickets + kSlotWords * i; return cudaSuccess; }
-    if (d->slots_used == kTicketSlots) return cudaSuccess;
+    if (d->slots_used == kTicketSlots) {
+        // Every slot is taken: hand over one whose stream has nothing in flight (or no longer exists).  Its device
+        // words are at rest then — ticket pairs zero, the published sequence number equal to the host's copy — so
+        // the new stream simply continues the numbering.  A busy stream keeps its slot.
+        for (int i = 0; i < kTicketSlots; ++i) {
+            const cudaError_t q = cudaStreamQuery(d->slot[i].stream);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) (void)cudaGetLastError();          // a destroyed stream: clear the error, take the slot
+            d->slot[i].stream = st;
+            d->slot[i].fast_open = false;
+            *slot = &d->slot[i];
+            *words = d->tickets + kSlotWords * i;
+            return cudaSuccess;
+        }
+        return cudaSuccess;                                          // all busy: the caller deals work statically
+    }
     d->slot[d->slots_used].stream = st;
     *slot = &d->slot[d->slots_used];
     *words = d->tickets + kSlotWords * d->slots_used++;
     return cudaSuccess;
+}
+
+// Which half of the caller's workspace the next whole-path call on `st` uses.  Calls can only overlap their
+// predecessor on the SAME stream, so alternating per stream is enough; streams without a slot (stream capture, more
+// busy streams than slots) alternate on a per-thread counter.
+unsigned next_call_parity(cudaStream_t st) {
+    static thread_local unsigned t_calls = 0;
+    DeviceInfo* d = nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (device_info(&d) != cudaSuccess || cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+        return t_calls++ & 1u;
+    StreamSlot* slot = nullptr;
+    int* words = nullptr;
+    if (slot_for(d, st, &slot, &words) != cudaSuccess || !slot) return t_calls++ & 1u;
+    std::lock_guard<std::mutex> lock(g_ticket_mu);
+    return slot->calls++ & 1u;
 }
 
 // ticket pair for the next ring-kernel launch on `st`
@@ -1906,6 +1938,7 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     p->chunks = (g.S + p->rows - 1) / p->rows;
     p->stage_bytes = (uint32_t)(((size_t)p->rows * per_row + 127) & ~(size_t)127);
     p->stages = t.argmax_stages;
+    p->dry = t.argmax_dry;
     p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
     p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * p->stages * sizeof(uint64_t) +
                     (size_t)p->stages * sizeof(int) + (p->split_mats ? 0 : (size_t)2 * G * g.HW * sizeof(Partial));
@@ -1952,6 +1985,7 @@ static bool plan_argmax16(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p
     p->chunks = (g.S + p->rows - 1) / p->rows;
     p->stage_bytes = (uint32_t)(((size_t)p->rows * per_row + 127) & ~(size_t)127);
     p->stages = t.argmax_stages;
+    p->dry = t.argmax_dry;
     p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * p->stages * sizeof(uint64_t) + (size_t)p->stages * sizeof(int);
     return true;
 }
@@ -1988,7 +2022,7 @@ static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const G
             return e;
         }
     }
-    dim3 grid((g.HW + 255) / 256, n_mats);
+    dim3 grid(n_mats, (g.HW + 255) / 256);
     limb_argmax_generic_kernel<T16><<<grid, 256, 0, st>>>(head, amax, g);
     return cudaGetLastError();
 }
@@ -2117,7 +2151,7 @@ cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g
         limb_argmax_ldg_kernel<<<n_mats, p.threads_padded, smem, st>>>(head, amax, g, p);
         return cudaGetLastError();
     }
-    dim3 grid((g.HW + 255) / 256, n_mats);
+    dim3 grid(n_mats, (g.HW + 255) / 256);
     limb_argmax_generic_kernel<float><<<grid, 256, 0, st>>>(head, amax, g);
     return cudaGetLastError();
 }
@@ -2181,7 +2215,15 @@ cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const 
     pack_count_kernel<<<B, 256, 0, st>>>(count, cell, R, K, header, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    pack_entries_kernel<<<B, 256, (size_t)(R + 1) * sizeof(int), st>>>(count, cell, score, reinterpret_cast<const float4*>(box),
+    const size_t smem = (size_t)(R + 1) * sizeof(int);
+    DeviceInfo* d = nullptr;
+    if ((e = device_info(&d)) != cudaSuccess) return e;
+    if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
+    static size_t have[64] = {};
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if (smem > 48 * 1024 && (e = ensure_smem(pack_entries_kernel, smem, &have[dev & 63])) != cudaSuccess) return e;
+    pack_entries_kernel<<<B, 256, smem, st>>>(count, cell, score, reinterpret_cast<const float4*>(box),
                                                                         B, R, K, cap, header, e_idcell, e_score,
                                                                         reinterpret_cast<float4*>(e_box));
     return cudaGetLastError();

@@ -28,6 +28,7 @@ struct Tuning {
     int host_chunk_images = 64;
     int encode_sweep = 1;              // target encoder: limb tensors by the address-ordered persistent sweep (0: one CTA per image part)
     int encode_ctas_per_sm = 6;
+    int argmax_dry = 0;                // ring kernels only move the bytes (no compares, no stores): the read ceiling of this ring
     int parse_overlap = 2;             // 0 serial; 1 decode+NMS on a side stream beside the arg-max;
                                        // 2 one stream, programmatic dependent launches (PDL chain)
 };
@@ -42,6 +43,7 @@ struct ArgmaxPlan {
     int split_mats;       // 1: the G groups take G different matrices (no merge), 0: they split rows
     int stages;           // ring depth
     int ctas_per_sm;
+    int dry;              // 1: consumers only release the stages (bandwidth probe)
     uint32_t stage_bytes;
     size_t smem_bytes;
 };
@@ -102,6 +104,7 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
                                const uint16_t* amax, int32_t* h_count, int32_t* h_root, int32_t* h_cell, float* h_score,
                                float* h_box, int R, cudaStream_t st, bool pdl_attr, int chain_mode, int stage_pref,
                                int staged_forced = -1, const DenseTarget* dense_to = nullptr, bool wait_top = false);
+unsigned next_call_parity(cudaStream_t st);   // which workspace half the next whole-path call on `st` takes (alternates per stream)
 bool chain_clean(cudaStream_t st);      // the stream's last whole-path launch was a (publishing) fused parse
 void chain_break(cudaStream_t st);      // ... was something else: the next overlapped call starts fully ordered
 

@@ -88,11 +88,23 @@ class TargetEncoder:
         big = lambda: torch.empty(B, cfg.E, cfg.sH, cfg.sW, cfg.H, cfg.W, dtype=torch.float32, device=self.device)
         return TargetBatch(**{n: (big() if n in ("weight_ij", "te") else small()) for n in _lib.TARGET_NAMES})
 
-    def encode_flat(self, person_off, bbox, keypoints, visible, size, out: Optional[TargetBatch] = None) -> TargetBatch:
+    @staticmethod
+    def check_offsets(person_off, n: int) -> None:
+        """person_off must be the running count of people per image: starts at 0, never decreases, ends at n.
+        (The kernel trusts it: a bad table reads outside the annotation arrays.)"""
+        off = np.asarray(person_off.cpu() if isinstance(person_off, torch.Tensor) else person_off, np.int64)
+        if off.ndim != 1 or off.size < 1 or off[0] != 0 or off[-1] != n or (np.diff(off) < 0).any():
+            raise ValueError(f"person_off must rise from 0 to the number of people ({n}) without decreasing")
+
+    def encode_flat(self, person_off, bbox, keypoints, visible, size, out: Optional[TargetBatch] = None,
+                    validate: bool = False) -> TargetBatch:
         """Device tensors in (int32 [B+1], float64 [n,4], fp32 [n,K-1,2], uint8 [n,K-1], float64 [n]),
-        targets out; asynchronous on torch's current stream."""
+        targets out; asynchronous on torch's current stream.  ``validate`` checks `person_off` first (it copies
+        the table to the host, i.e. synchronises; :meth:`encode` checks its host copy for free)."""
         B = int(person_off.numel()) - 1
         n = int(bbox.shape[0])
+        if validate:
+            self.check_offsets(person_off, n)
         want = ((person_off, torch.int32, (B + 1,)), (bbox, torch.float64, (n, 4)), (keypoints, torch.float32, (n, self.cfg.K - 1, 2)),
                 (visible, torch.uint8, (n, self.cfg.K - 1)), (size, torch.float64, (n,)))
         for t, dt, shp in want:
@@ -112,5 +124,6 @@ class TargetEncoder:
     def encode(self, samples: Sequence[dict], out: Optional[TargetBatch] = None) -> TargetBatch:
         """samples: the dicts the reference's transforms return (see :func:`flatten_samples`)."""
         flat = flatten_samples(samples, self.cfg.K)
+        self.check_offsets(flat[0], int(flat[1].shape[0]))
         dev = [torch.from_numpy(a).to(self.device, non_blocking=True) for a in flat]
         return self.encode_flat(*dev, out=out)

@@ -42,6 +42,7 @@ class _CConfig:
         # numpy demotes the Python-float thresholds to fp32 when comparing with fp32 arrays
         self.params = self._make_params(cfg, n_nms_parts, 0)
         self.params_input_complete = self._make_params(cfg, n_nms_parts, _lib.FLAG_INPUT_COMPLETE)
+        self.params_clear = self._make_params(cfg, n_nms_parts, _lib.FLAG_CLEAR_UNUSED)
 
     def _make_params(self, cfg, n_nms_parts, flags):
         return _lib.PPNParams(
@@ -111,7 +112,7 @@ class PackedHumans:
         return result
 
 
-def unpack_entries(buf, B: int, cap_entries: int, offsets):
+def unpack_entries(buf, B: int, cap_entries: int, offsets, derive: bool = False):
     """Host view of one dense entry buffer (see include/ppn_decode.h, ppn_pack_humans).
 
     buf: uint8 numpy array or CPU tensor.  Returns dict(total, overflow, count[B] humans per image,
@@ -124,7 +125,11 @@ def unpack_entries(buf, B: int, cap_entries: int, offsets):
     idcell = a[o_i:o_i + 4 * cap_entries].view(np.uint32)
     score = a[o_s:o_s + 4 * cap_entries].view(np.float32)
     box = a[o_b:o_b + 16 * cap_entries].view(np.float32).reshape(cap_entries, 4)
-    return dict(total=int(header[0]), overflow=bool(header[1]), count=count, entries=entries, start=start,
+    if derive:          # a buffer written remotely (ppn_parse_dense_remote) carries the table but not header[0..1]
+        total, overflow = int(entries.sum()), bool(((start + entries) > cap_entries).any())
+    else:
+        total, overflow = int(header[0]), bool(header[1])
+    return dict(total=total, overflow=overflow, count=count, entries=entries, start=start,
                 part=(idcell >> 16).astype(np.int32), cell=(idcell & 0xffff).astype(np.int32), score=score, box=box)
 
 
@@ -220,7 +225,8 @@ class PoseParser:
 
     # ---- the whole path ---------------------------------------------------------------- #
     def parse(self, head: torch.Tensor, out: Optional[PackedHumans] = None, input_complete: bool = False,
-              dense: Optional[torch.Tensor] = None, cap_entries: int = 0, skip_slots: bool = False) -> PackedHumans:
+              dense: Optional[torch.Tensor] = None, cap_entries: int = 0, skip_slots: bool = False,
+              remote: Optional[Tuple[int, int]] = None, clear_unused: bool = False) -> PackedHumans:
         """Enqueue the whole path for a device batch on torch's current stream (asynchronous).
 
         ``out`` may be a preallocated :meth:`alloc_output` to reuse; otherwise the parser's own
@@ -235,6 +241,13 @@ class PoseParser:
         ``dense`` (a uint8 device buffer of ``packed_layout(B, cap_entries)`` bytes): also produce the
         dense (human, part) entry buffer of the multi-GPU gather (``ppn_parse_dense``); with
         ``skip_slots`` the fixed-stride arrays of ``out`` other than ``count`` may be left unwritten.
+
+        ``remote = (address, bytes)`` of ANOTHER dense buffer of the same layout — e.g. the gather root's,
+        peer-mapped over NVLink (:class:`..sharded.PeerPoseGatherer`): the parse kernel stores the per-image
+        table and the entries there (``ppn_parse_dense_remote``); ``dense`` then only needs to hold the header.
+
+        ``clear_unused`` (``PPN_FLAG_CLEAR_UNUSED``): slots past ``count[b]`` are reset (-1 / 0) instead of keeping
+        whatever ``out`` held.
         """
         B = self._check_head(head)
         if head.device != self.device:
@@ -248,22 +261,44 @@ class PoseParser:
         ws = self._workspace(B)
         hs = self._humans_struct(out)
         with self._guard():
-            params = self.c.params_input_complete if input_complete else self.c.params
+            params = self.c.params_clear if clear_unused else (self.c.params_input_complete if input_complete else self.c.params)
             st = torch.cuda.current_stream(self.device).cuda_stream
             if dense is None:
                 rc = self.lib.ppn_parse(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), C.byref(params), C.byref(hs),
                                         ws.data_ptr(), ws.numel(), st)
+            elif remote is not None:
+                rc = self.lib.ppn_parse_dense_remote(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), C.byref(params),
+                                                     C.byref(hs), dense.data_ptr(), dense.numel(), int(remote[0]), int(remote[1]),
+                                                     int(cap_entries), int(bool(skip_slots)), ws.data_ptr(), ws.numel(), st)
             else:
                 rc = self.lib.ppn_parse_dense(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), C.byref(params),
                                               C.byref(hs), dense.data_ptr(), dense.numel(), int(cap_entries), int(bool(skip_slots)),
                                               ws.data_ptr(), ws.numel(), st)
         if rc:
-            raise _lib.PPNError(rc, "ppn_parse" if dense is None else "ppn_parse_dense")
+            raise _lib.PPNError(rc, "ppn_parse" if dense is None else ("ppn_parse_dense" if remote is None else "ppn_parse_dense_remote"))
         return out
 
     def launches_per_parse(self, B: int) -> int:
         shape = self.c.shape(B)
         return int(self.lib.ppn_parse_launches(C.byref(shape), C.byref(self.c.params)))
+
+    def parse_plan(self, B: int) -> dict:
+        """How ``parse`` runs a batch of B: launches, sub-batches, the arg-max ring's shared-memory cap, staging."""
+        info = (C.c_int32 * 4)()
+        _lib.check(self.lib.ppn_parse_plan(C.byref(self.c.shape(B)), C.byref(self.c.params), info), "ppn_parse_plan")
+        return dict(launches=info[0], sub_batches=info[1], ring_cap=info[2], staged=bool(info[3]))
+
+    def limb_stream_probe(self, head: torch.Tensor, smem_cap: int = 0) -> None:
+        """Run the arg-max kernel's bulk-copy ring over `head` without compares or stores (``ppn_limb_stream_probe``):
+        the read ceiling of that access pattern; asynchronous, on torch's current stream."""
+        B = self._check_head(head)
+        cfg = self.cfg
+        if getattr(self, "_probe_amax", None) is None or self._probe_amax.shape[0] < B:
+            self._probe_amax = torch.empty(B, cfg.E, cfg.H, cfg.W, dtype=torch.uint16, device=self.device)
+        with self._guard():
+            _lib.check(self.lib.ppn_limb_stream_probe(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])),
+                                                      self._probe_amax.data_ptr(), int(smem_cap),
+                                                      torch.cuda.current_stream(self.device).cuda_stream), "ppn_limb_stream_probe")
 
     def parse_host(self, head: torch.Tensor, out: Optional[PackedHumans] = None) -> PackedHumans:
         """The whole path from HOST memory (pinned for full copy speed) to host results;

@@ -216,3 +216,178 @@ class PoseGatherer:
         lo = (rank * self._shipped[grp & 1] + k) * self.nbytes
         part = buf[lo:lo + self.nbytes].cpu()
         return unpack_entries(part, self.B, self.cap, self.offsets)
+
+
+class PeerPoseGatherer:
+    """Gather of every rank's poses at ONE root rank over peer memory — no collective on the data plane.
+
+    ``north_star``: whole images are sharded over the GPUs of one box, "NCCL is used only to gather per-rank pose
+    lists and timings".  The pose lists are small (≈ 1 MB per 512 images) but a collective per step — or one large
+    one per group of steps — costs SM time under the arg-max stream and an exposed tail at the end of a run.  Here
+    the root rank owns one buffer ``[world][slots][packed record]`` allocated by the library (``ppn_peer_alloc``);
+    its CUDA IPC handle goes round once through the process group and every rank maps it (``ppn_peer_open``:
+    NVLink peer access).  Then, per step,
+
+    * ``mode="store"`` (default): the parse kernel writes its dense (human, part) records straight into this
+      rank's slot of the ROOT's buffer (``ppn_parse_dense_remote``): the compute step and the gather are one
+      kernel, the records cross NVLink as plain stores while the kernel runs, exactly as many bytes as were
+      produced;
+    * ``mode="copy"``: the records go to a local slot and every ``notify_every`` steps ONE ``cudaMemcpyAsync``
+      (copy engine, no SM) on a side stream ships the group's slots to the root.
+
+    What remains for NCCL is the control plane: every ``notify_every`` steps an 8-byte ``all_gather`` of step
+    counters on the side stream, ordered after the steps it covers.  When it completes on the root, every rank's
+    records of those steps have landed (a kernel's stores are visible when it has completed; the copy is on the
+    same stream); a consumer's work enqueued on the root's side stream right after it therefore reads complete
+    data, and — being stream-ordered before the root's NEXT notification — is finished before any rank, having
+    seen that next notification complete, reuses a slot.  Hence ``slots >= 2 * notify_every``.
+    """
+
+    def __init__(self, parser, images_per_rank: int, cap_entries: int, group=None, slots: int = 32,
+                 notify_every: int = 8, root: int = 0, mode: str = "store", consumer=None):
+        import ctypes as C
+        from . import _lib
+        if mode not in ("store", "copy"):
+            raise ValueError("mode must be 'store' or 'copy'")
+        self.parser, self.group, self.mode, self.root = parser, group, mode, int(root)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.B, self.cap = int(images_per_rank), int(cap_entries)
+        self.ne = max(1, int(notify_every))
+        self.slots = max(int(slots), 2 * self.ne)
+        self.consumer = consumer
+        self.nbytes, self.offsets = parser.packed_layout(self.B, self.cap)
+        self.lib = parser.lib
+        dev = parser.device
+        region = self.slots * self.nbytes
+        self._owned = None
+        handle = None
+        with torch.cuda.device(dev):
+            if self.rank == self.root:
+                ptr, buf = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+                _lib.check(self.lib.ppn_peer_alloc(self.world * region, C.byref(ptr), buf), "ppn_peer_alloc")
+                self._owned, handle = ptr.value, buf.raw
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=group)
+            if self.rank == self.root:
+                self.base = self._owned
+            else:
+                ptr = C.c_void_p()
+                _lib.check(self.lib.ppn_peer_open(handles[self.root], C.byref(ptr)), "ppn_peer_open")
+                self.base = ptr.value
+        self.region = region
+        self.mine_at = self.base + self.rank * region
+        hdr = -(-4 * (2 + 3 * self.B) // 256) * 256
+        self.local_stride = self.nbytes if mode == "copy" else hdr
+        self.local = torch.zeros(self.slots * self.local_stride, dtype=torch.uint8, device=dev)
+        self._local_slices = [self.local[k * self.local_stride:(k + 1) * self.local_stride] for k in range(self.slots)]
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.seen = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        self.side = torch.cuda.Stream(device=dev)
+        self._events = [torch.cuda.Event() for _ in range(4)]
+        self._notes = []                      # notification n -> work handle (None once waited for)
+        self.step = 0
+        self._covered = 0                     # steps [0, _covered) are covered by an issued notification
+
+    # ---- control plane ------------------------------------------------------------------------------
+    def _notify(self):
+        """Ship (copy mode) and announce every step enqueued so far."""
+        upto, dev = self.step, self.parser.device
+        main = torch.cuda.current_stream(dev)
+        ev = self._events[len(self._notes) % len(self._events)]
+        ev.record(main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            if self._notes and self._notes[-1] is not None:
+                self._notes[-1].wait()         # side stream: the previous notification has read `counter` / written `seen`
+            if self.mode == "copy":
+                s = self._covered
+                while s < upto:                # contiguous runs of slots (a run ends where the ring wraps)
+                    k = s % self.slots
+                    n = min(upto - s, self.slots - k)
+                    with torch.cuda.device(dev):
+                        rc = self.lib.ppn_peer_copy(self.mine_at + k * self.nbytes, self.local.data_ptr() + k * self.nbytes,
+                                                    n * self.nbytes, self.side.cuda_stream)
+                    if rc:
+                        from . import _lib
+                        raise _lib.PPNError(rc, "ppn_peer_copy")
+                    s += n
+            self.counter.fill_(upto)
+            work = dist.all_gather_into_tensor(self.seen, self.counter, group=self.group, async_op=True)
+            if self.consumer is not None and self.rank == self.root:
+                work.wait()                    # side stream: the consumer's kernels run after the records have landed
+                self.consumer(self, self._covered, upto)
+                work = _Done(self.side)
+        self._notes.append(work)
+        self._covered = upto
+
+    def _wait_note(self, n: int):
+        """Make the CURRENT stream wait for notification n (and all earlier ones)."""
+        for i in range(min(n, len(self._notes) - 1) + 1):
+            w = self._notes[i]
+            if w is not None:
+                w.wait()
+                self._notes[i] = None
+
+    # ---- the step -----------------------------------------------------------------------------------
+    def parse(self, head, out=None, input_complete: bool = False):
+        s = self.step
+        k = s % self.slots
+        if s >= self.slots:                   # the slot still holds step s - slots: see the class comment
+            self._wait_note((s - self.slots) // self.ne + 1)
+        if self.mode == "store":
+            res = self.parser.parse(head, out=out, input_complete=input_complete, dense=self._local_slices[k], cap_entries=self.cap,
+                                    skip_slots=True, remote=(self.mine_at + k * self.nbytes, self.nbytes))
+        else:
+            res = self.parser.parse(head, out=out, input_complete=input_complete, dense=self._local_slices[k], cap_entries=self.cap,
+                                    skip_slots=True)
+        self.step += 1
+        if self.step % self.ne == 0:
+            self._notify()
+        return res
+
+    def finish(self):
+        """Announce the remaining steps and make the current stream wait until every rank's records have landed."""
+        if self.step > self._covered:
+            self._notify()
+        self._wait_note(len(self._notes) - 1)
+
+    # ---- reading (root) -----------------------------------------------------------------------------
+    def records_of(self, rank: int, step_back: int = 0):
+        """Host view of `rank`'s records of the last parsed step minus `step_back` (root only; after finish())."""
+        from .parser import unpack_entries
+        if self.rank != self.root:
+            raise RuntimeError("the records are gathered at the root rank only")
+        s = self.step - 1 - step_back
+        if s < 0 or step_back < 0 or step_back >= self.slots - 2 * self.ne + 1:
+            raise ValueError("that step's slot may already have been reused")
+        at = rank * self.region + (s % self.slots) * self.nbytes
+        from . import _lib
+        host = torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize(self.parser.device)
+        with torch.cuda.device(self.parser.device):
+            _lib.check(self.lib.ppn_peer_copy(host.data_ptr(), self.base + at, self.nbytes, None), "ppn_peer_copy")
+        torch.cuda.synchronize(self.parser.device)
+        return unpack_entries(host, self.B, self.cap, self.offsets, derive=(self.mode == "store"))
+
+    def close(self):
+        torch.cuda.synchronize(self.parser.device)
+        with torch.cuda.device(self.parser.device):
+            if self._owned:
+                dist.barrier(group=self.group)            # peers unmap first
+                self.lib.ppn_peer_free(self._owned)
+                self._owned = None
+            elif self.base:
+                self.lib.ppn_peer_close(self.base)
+                dist.barrier(group=self.group)
+            self.base = 0
+
+
+class _Done:
+    """Stands in for a finished collective: waiting makes the current stream wait for `stream` as it is now."""
+
+    def __init__(self, stream):
+        self.ev = torch.cuda.Event()
+        self.ev.record(stream)
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.ev)

@@ -54,10 +54,22 @@ def test_config_validation():
     assert list(off) == [0, 5, 10, 17, 24, 25] and len(limb) == 25 and len(part) == 25
 
 
+def test_color_map_is_the_references():
+    """config.py:23-42 — digest of the reference's own COLOR_MAP (oracle/make_golden.py asserts equality live)."""
+    import hashlib
+    from pytorch_pose_proposal_network_b200 import config as c
+    assert list(c.COLOR_MAP)[:4] == ["instance", "right_shoulder", "right_elbow", "right_wrist"]
+    assert set(c.COLOR_MAP) == set(c.KEYPOINT_NAMES) and c.COLOR_MAP["instance"] == (143, 35, 35)
+    assert hashlib.sha256(repr(list(c.COLOR_MAP.items())).encode()).hexdigest() == \
+        "f5bd531494d0da561eb0b00dbbfb89276dacc417e26f61cf92804303fad6065c"
+
+
 def test_library_exports_every_declared_symbol():
     from pytorch_pose_proposal_network_b200 import _lib
-    header = open(os.path.join(ROOT, "include", "ppn_decode.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("ppn_decode.h", "ppn_decode_bench.h"))
     body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    product = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ppn_decode.h")).read(), flags=re.S)
+    assert "ppn_tune" not in product and "ppn_profile" not in product, "benchmark hooks belong in ppn_decode_bench.h"
     declared = set(re.findall(r"\b(ppn_[a-z_0-9]+)\s*\(", body))
     assert declared, "no declarations found"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
