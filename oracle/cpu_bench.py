@@ -30,16 +30,19 @@ def _init(geom_kwargs, dist, seed, n_images):
     g = O.Geometry(**geom_kwargs)
     _state["g"] = g
     _state["O"] = O
-    # every worker regenerates the same sample locally (no pickling of MBs per task)
+    # every worker regenerates the same sample locally (no pickling of MBs per task); a pass over more images than
+    # the sample holds cycles through it (bench.py's reference arm: 512 images per step from a 32-image sample)
     _state["head"] = synth.make_head(g, dist, seed, B=n_images)
+    _state["n"] = n_images
 
 
 def _work(span):
     O, g, head = _state["O"], _state["g"], _state["head"]
     lo, hi = span
     n_h = 0
+    n = _state["n"]
     for b in range(lo, hi):
-        humans, _ = O.parse_head_like_reference(head[b], g)
+        humans, _ = O.parse_head_like_reference(head[b % n], g)
         n_h += len(humans)
     return n_h
 
@@ -53,13 +56,14 @@ class CpuPool:
     """A pool of `cores` processes holding the same `n_images`-image sample; each pass parses the
     whole sample once, split evenly across the processes."""
 
-    def __init__(self, g, dist="U", seed=0, n_images=None, cores=None):
+    def __init__(self, g, dist="U", seed=0, n_images=None, cores=None, sample_images=None):
         self.cores = cores or host_cores()
         self.n_images = n_images or 4 * self.cores
+        self.sample_images = min(self.n_images, sample_images or self.n_images)
         self.g = g
         ctx = mp.get_context("spawn")          # the parent may hold a CUDA context: never fork it
         self.pool = ctx.Pool(self.cores, initializer=_init,
-                             initargs=(geometry_kwargs(g), dist, seed, self.n_images))
+                             initargs=(geometry_kwargs(g), dist, seed, self.sample_images))
         per = -(-self.n_images // self.cores)
         self.spans = [(lo, min(lo + per, self.n_images)) for lo in range(0, self.n_images, per)]
         self.pool.map(_work, [(0, 1)] * self.cores)   # start every worker, build its sample

@@ -90,15 +90,41 @@ def restore_size(w, h):
 
 
 def _config_from_arrays(delta, e, detection_thresh, min_num_keypoints, nms_thresh, graphs, swap=False) -> PPNConfig:
-    K, H, W = delta.shape
-    E, eH, eW = e.shape[0], e.shape[1], e.shape[2]
-    if tuple(e.shape[3:]) != (H, W):
-        raise ValueError(f"e has grid {tuple(e.shape[3:])}, delta has {(H, W)}")
+    return _config_from_shapes(tuple(delta.shape), tuple(e.shape), detection_thresh, min_num_keypoints, nms_thresh, graphs, swap)
+
+
+def _config_from_shapes(dshape, eshape, detection_thresh, min_num_keypoints, nms_thresh, graphs, swap=False) -> PPNConfig:
+    K, H, W = dshape
+    E, eH, eW = eshape[0], eshape[1], eshape[2]
+    if tuple(eshape[3:]) != (H, W):
+        raise ValueError(f"e has grid {tuple(eshape[3:])}, delta has {(H, W)}")
     if (W, H) != tuple(outsize):
         raise ValueError(f"arrays are {W}x{H} cells but datatest.outsize is {outsize}")
     return PPNConfig(K=K, E=E, insize=tuple(insize), outsize=(W, H), local_grid_size=(eW, eH),
                      directed_graphs=graphs, detection_thresh=detection_thresh, nms_thresh=nms_thresh,
                      min_num_keypoints=min_num_keypoints, swap_window_offsets=swap)
+
+
+_staging = {}
+
+
+def _head_buffer(cfg: PPNConfig, dev: torch.device) -> torch.Tensor:
+    """One device head tensor [1, C, H, W] per geometry, reused from call to call.  The kernels take the layout
+    [resp, conf, x, y, w, h, limbs]; the reference hands over delta = resp * conf already multiplied
+    (rt_test.py:130), so the conf planes hold 1.0 — written once, here: delta * 1 == delta exactly."""
+    key = (cfg.K, cfg.E, cfg.H, cfg.W, cfg.sH, cfg.sW, dev.index)
+    buf = _staging.get(key)
+    if buf is None:
+        buf = _staging[key] = torch.empty(1, cfg.C, cfg.H, cfg.W, dtype=torch.float32, device=dev)
+        buf[0, cfg.K:2 * cfg.K] = 1.0
+    return buf
+
+
+def _fill(dst: torch.Tensor, src) -> None:
+    """src (numpy array or tensor on any device, any float dtype) -> the fp32 device slice `dst`: ONE copy, straight
+    from where the caller's data lives (no intermediate device tensor, no concatenation)."""
+    t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src))
+    dst.copy_(t.reshape(dst.shape), non_blocking=True)
 
 
 def get_humans_by_feature(delta, x, y, w, h, e, detection_thresh=0.15, min_num_keypoints=1):
@@ -108,13 +134,20 @@ def get_humans_by_feature(delta, x, y, w, h, e, detection_thresh=0.15, min_num_k
     ``resp * conf`` (rt_test.py:130).  Returns ``(humans, scores)``: lists, in descending
     root-score order, of dicts ``part id -> float32[4] (ymin, xmin, ymax, xmax)`` and
     ``part id -> float32`` with the reference's key insertion order.
+
+    Per call: six host-to-device copies into a persistent head tensor (the limb block, 98 % of the bytes, in one),
+    two kernel launches, then the counts and only the used result slots back.
     """
-    delta_d, e_d = _dev32(delta), _dev32(e)
-    cfg = _config_from_arrays(delta_d, e_d, detection_thresh, min_num_keypoints, NMS_THRESH, DIRECTED_GRAPHS)
-    K, H, W = delta_d.shape
-    # the kernels take the head-tensor layout [resp, conf, x, y, w, h, limbs]; delta * 1 == delta exactly
-    head = torch.cat([delta_d, torch.ones_like(delta_d), _dev32(x), _dev32(y), _dev32(w), _dev32(h),
-                      e_d.reshape(-1, H, W)], dim=0).unsqueeze(0)
+    dshape, eshape = tuple(np.shape(delta)), tuple(np.shape(e))
+    if len(dshape) != 3 or len(eshape) != 5:
+        raise ValueError(f"delta must be [K, H, W] and e [E, sH, sW, H, W]; got {dshape} and {eshape}")
+    cfg = _config_from_shapes(dshape, eshape, detection_thresh, min_num_keypoints, NMS_THRESH, DIRECTED_GRAPHS)
+    dev = _device()
+    head = _head_buffer(cfg, dev)
+    K = cfg.K
+    for g, src in ((0, delta), (2, x), (3, y), (4, w), (5, h)):
+        _fill(head[0, g * K:(g + 1) * K], src)
+    _fill(head[0, 6 * K:], e)
     packed = _parser_for(cfg).parse(head)
     return packed.humans(0)
 

@@ -81,13 +81,22 @@ class PackedHumans:
         h = self.cpu()
         return {k: getattr(h, k).numpy() for k in ("count", "root_cell", "part_cell", "part_score", "part_box")}
 
+    def numpy_used(self):
+        """Like :meth:`numpy`, but only the slots that carry humans cross to the host: the counts first, then the
+        first max(count) slots of every array (what :meth:`to_lists` needs; the rest of the R slots is padding)."""
+        count = self.count.cpu().numpy()
+        m = int(min(int(count.max()) if count.size else 0, self.R))
+        take = lambda t: (t if t.device.type == "cpu" else t[:, :m].cpu()).numpy()
+        return {"count": count, "root_cell": take(self.root_cell), "part_cell": take(self.part_cell),
+                "part_score": take(self.part_score), "part_box": take(self.part_box)}
+
     def humans(self, b: int = 0):
         """(humans, scores) of image ``b`` exactly as ``get_humans_by_feature`` returns them:
         dicts keyed by part id in first-insertion order, fp32 ``(ymin,xmin,ymax,xmax)`` boxes."""
         return self.to_lists()[b]
 
     def to_lists(self) -> List[Tuple[list, list]]:
-        a = self.numpy()
+        a = self.numpy_used()
         graphs = self.cfg.directed_graphs
         K = self.cfg.K
         result = []
@@ -430,6 +439,19 @@ class PoseParser:
         shape = self.c.shape(B, self._DTYPES[head.dtype])
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ppn_limb_argmax(_ptr(head), C.byref(shape), _ptr(amax), _stream_ptr(self.device)), "ppn_limb_argmax")
+        return amax
+
+    def limb_argmax_into(self, head: torch.Tensor, amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """:meth:`limb_argmax` into a caller's (or a cached) buffer: nothing is allocated per call (benchmarks)."""
+        B = self._check_head(head)
+        cfg = self.cfg
+        if amax is None:
+            if getattr(self, "_probe_amax", None) is None or self._probe_amax.shape[0] < B:
+                self._probe_amax = torch.empty(B, cfg.E, cfg.H, cfg.W, dtype=torch.uint16, device=self.device)
+            amax = self._probe_amax
+        with self._guard():
+            _lib.check(self.lib.ppn_limb_argmax(head.data_ptr(), C.byref(self._shape(B, self._DTYPES[head.dtype])), amax.data_ptr(),
+                                                torch.cuda.current_stream(self.device).cuda_stream), "ppn_limb_argmax")
         return amax
 
     def decode_candidates(self, head: torch.Tensor, n_parts: int = 1, detection_thresh: Optional[float] = None):
