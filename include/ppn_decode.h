@@ -13,6 +13,8 @@
  *   ppn_nms ................ non_maximum_suppression(bbox, thresh, score, limit), datatest.py:134-160
  *   ppn_tree_parse ......... the per-root walk of get_humans_by_feature, datatest.py:103-131
  *   ppn_part_centres ....... box -> keypoint of draw_humans / evaluation, datatest.py:200-211, 314-317
+ *   ppn_skeleton ........... everything draw_humans computes before it draws: root rectangles, keypoints, limb
+ *                            segments, datatest.py:162-232
  *   ppn_parse .............. get_humans_by_feature end to end on a device batch: what
  *                            rt_test.py:109-133 / main.py:946-972 do per image after model(image)
  *   ppn_parse_host ......... the same from host memory (the reference's numpy arrays), with the
@@ -198,6 +200,15 @@ int ppn_parse_host(const void* head_host, const PPNShape* shape, const PPNParams
  * keypoints drawn by draw_humans (datatest.py:200-211) and the x / y of the AP-evaluation records
  * (datatest.py:314-317).  Same fp32 arithmetic as numpy's. */
 int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centre_yx, void* stream);
+
+/* The drawing primitives of draw_humans (datatest.py:162-232; the webcam loop calls it right after the parser,
+ * rt_test.py:138-145) for every slot of a packed result, so that the consumer draws without touching per-human
+ * dicts:  rect [B, R, 4] int32 = the root box as drawn, (xmin, ymin, xmax, ymax) truncated like int()
+ * (datatest.py:177-181);  keypoint_xy [B, R, K, 2] fp32 = (x, y) centre of every present part (:200-202);
+ * segment [B, R, E, 4] fp32 = (bx, by, ex, ey) of every limb whose two parts are present (:213-221).  Absent
+ * parts / limbs and unused slots: NaN (rect: 0).  edges: HOST [E][2] part ids (config.py:65 EDGES). */
+int ppn_skeleton(const PPNHumans* humans, int32_t B, int32_t K, int32_t E, const int32_t* edges,
+                 int32_t* rect, float* keypoint_xy, float* segment, void* stream);
 
 /* Dense pose ENTRIES for shipping results (the multi-GPU gather): one contiguous device buffer
  *   int32  header[2 + 3B] = {total entries, overflow flag, count[B] humans, entries[B] per image,

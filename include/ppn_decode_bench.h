@@ -22,6 +22,11 @@ extern "C" {
 int ppn_profile_enable(int32_t on);
 int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
 
+/* How the ring arg-max kernel cuts a batch into work items on a GPU of `sms` SMs (host arithmetic only, no launch):
+ * info[4] = {matrices per full item, full items, matrices per tail item, items}; first/size (each [max_items] or
+ * NULL) receive every item's first matrix and matrix count.  For the test that the items tile [0, B*E) exactly. */
+int ppn_debug_argmax_items(const PPNShape* shape, int32_t sms, int32_t* info /*[4]*/, int32_t* first, int32_t* size, int32_t max_items);
+
 /* Benchmark knobs.  key: "argmax.variant" (0 = TMA bulk-copy ring, 1 = direct 128-bit loads),
  * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
  * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),

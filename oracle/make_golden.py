@@ -226,6 +226,42 @@ def pred_frame_cases(presets):
         json.dump(cases, f)
 
 
+def drawing_cases(presets):
+    """The image draw_humans produces (datatest.py:162-232) for the humans of three 18-part cases: its sha256 goes
+    into tests/golden/drawings.json.  Checked here: the primitives of oracle/skeleton.py, drawn by the package's
+    drawing module, give the same pixels."""
+    import hashlib
+    from oracle import skeleton
+    from PIL import Image
+    from pytorch_pose_proposal_network_b200 import drawing
+    cases = {}
+    for name, preset, dist, seed in (("native_U_s0", "native", "U", 0), ("native_S_s3000", "native", "S", 3000),
+                                     ("cfg4_U_s1", "cfg4", "U", 1)):
+        g = O.Geometry.of(presets[preset])
+        out = synth.make_head(g, dist, seed)[0]
+        humans, _ = ref_live.reference_parse(out, g)
+        p = O.parse_image(out, g)
+        # the reference's draw_humans raises (PIL: "y1 must be greater than or equal to y0") on a root box less than
+        # two pixels wide or high: such humans of the random tensors are left out, on both sides
+        keep = [i for i, hm in enumerate(humans)
+                if int(hm[0][3]) - int(hm[0][1]) >= 2 and int(hm[0][2]) - int(hm[0][0]) >= 2]
+        humans = [humans[i] for i in keep]
+        part_cell, part_box = p.part_cell[keep], p.part_box[keep]
+        rect, kp, seg = skeleton.primitives(part_cell, part_box, pcfg.EDGES)
+        rec = {"size": g.inW, "humans": len(humans), "kept": keep}
+        for visbbox in (False, True):
+            ref = ref_live.reference_draw(humans, g.inW, visbbox=visbbox)
+            mine = np.asarray(drawing.draw_skeletons(Image.new("RGB", (g.inW, g.inW)), rect, kp, seg, pcfg.KEYPOINT_NAMES,
+                                                     pcfg.EDGES, visbbox=visbbox, part_box=part_box))
+            assert ref.shape == mine.shape and np.array_equal(ref, mine), (name, visbbox, int((ref != mine).sum()))
+            rec["sha256_visbbox" if visbbox else "sha256"] = hashlib.sha256(ref.tobytes()).hexdigest()
+        rec["primitives_sha256"] = hashlib.sha256(rect.tobytes() + kp.tobytes() + seg.tobytes()).hexdigest()
+        cases[name] = rec
+        print(f"drawing {name}: {len(humans)} humans")
+    with open(os.path.join(GOLDEN, "drawings.json"), "w") as f:
+        json.dump(cases, f, sort_keys=True)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     assert ref_live.available(), "run this where /root/reference exists"
@@ -256,6 +292,7 @@ def main():
              dict(preset="cfg2", dist="U", seed=5, min_num_keypoints=-1, detection_thresh=0.09))
 
     pred_frame_cases(presets)
+    drawing_cases(presets)
     roundtrip_case("roundtrip_cfg2_s21", presets["cfg2"], 21, 3)
     roundtrip_case("roundtrip_native_s22", presets["native"], 22, 5)
     nms_cases(dt)

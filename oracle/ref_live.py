@@ -97,6 +97,17 @@ def reference_parse(out, g):
                                     detection_thresh=g.det_thresh, min_num_keypoints=g.min_kp)
 
 
+def reference_draw(humans, size, visbbox=False):
+    """The reference's own ``draw_humans`` (datatest.py:162-232) on a black ``size`` x ``size`` RGB image, as
+    rt_test.py:138-145 calls it (its own KEYPOINT_NAMES / EDGES: the 18-part skeleton).  -> uint8 [size, size, 3]."""
+    import numpy as np
+    from PIL import Image
+    dt = load()
+    img = dt.draw_humans(keypoint_names=dt.KEYPOINT_NAMES, edges=dt.EDGES, pil_image=Image.new("RGB", (size, size)),
+                         humans=humans, visbbox=visbbox, gridOn=False)
+    return np.asarray(img)
+
+
 class _Captured(Exception):
     def __init__(self, gt, pr):
         self.gt, self.pr = gt, pr

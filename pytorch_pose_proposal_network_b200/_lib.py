@@ -76,6 +76,7 @@ EXPORTS = {
     "ppn_parse_host": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.POINTER(PPNParams), C.POINTER(PPNHumans),
                                  C.c_void_p, C.c_size_t]),
     "ppn_part_centres": (C.c_int, [C.POINTER(PPNHumans), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ppn_skeleton": (C.c_int, [C.POINTER(PPNHumans), C.c_int32, C.c_int32, C.c_int32, i32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ppn_packed_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "ppn_pack_humans": (C.c_int, [C.POINTER(PPNHumans), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ppn_parse_dense": (C.c_int, [C.c_void_p, C.POINTER(PPNShape), C.POINTER(PPNParams), C.POINTER(PPNHumans),
@@ -94,6 +95,7 @@ EXPORTS = {
     "ppn_head_parse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PPNShape), C.POINTER(PPNParams),
                                  C.POINTER(PPNHumans), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ppn_encode_targets": (C.c_int, [C.POINTER(PPNPeople), C.POINTER(PPNShape), i32p, C.POINTER(PPNTargets), C.c_void_p]),
+    "ppn_debug_argmax_items": (C.c_int, [C.POINTER(PPNShape), C.c_int32, i32p, i32p, i32p, C.c_int32]),
     "ppn_profile_enable": (C.c_int, [C.c_int32]),
     "ppn_profile_read": (C.c_int, [f32p, i32p]),
     "ppn_tune": (C.c_int, [C.c_char_p, C.c_int32]),

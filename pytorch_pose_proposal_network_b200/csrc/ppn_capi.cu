@@ -743,6 +743,21 @@ int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centr
 }
 
 
+int ppn_skeleton(const PPNHumans* humans, int32_t B, int32_t K, int32_t E, const int32_t* edges,
+                 int32_t* rect, float* keypoint_xy, float* segment, void* stream) {
+    int rc = check_humans(humans);
+    if (rc) return rc;
+    if (B < 0 || K < 1 || E < 0 || K > 255 || E > 255) return PPN_E_BADARG;
+    if (B == 0) return PPN_OK;
+    if (!rect || !keypoint_xy || (E > 0 && (!segment || !edges))) return PPN_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(rect) & 15) || (reinterpret_cast<uintptr_t>(keypoint_xy) & 7) ||
+        (reinterpret_cast<uintptr_t>(segment) & 15) || (reinterpret_cast<uintptr_t>(humans->part_box) & 15)) return PPN_E_BADARG;
+    for (int e = 0; e < E; ++e)
+        if (edges[2 * e] < 0 || edges[2 * e] >= K || edges[2 * e + 1] < 0 || edges[2 * e + 1] >= K) return PPN_E_CHAINS;
+    return cuda_rc(ppn::launch_skeleton(humans->count, humans->part_cell, humans->part_box, B, humans->R, K, E, edges, rect,
+                                        keypoint_xy, segment, (cudaStream_t)stream));
+}
+
 int ppn_packed_bytes(int32_t B, int32_t cap_entries, size_t* bytes, size_t* offsets) {
     if (B < 0 || cap_entries < 0 || !bytes) return PPN_E_BADARG;
     const PackedLayout l = packed_layout(B, cap_entries);
@@ -804,6 +819,24 @@ int ppn_encode_targets(const PPNPeople* people, const PPNShape* shape, const int
     if (e != cudaSuccess) return (int)e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
     return cuda_rc(ppn::launch_encode_targets(a, shape->B, sms, (cudaStream_t)stream));
+}
+
+int ppn_debug_argmax_items(const PPNShape* shape, int32_t sms, int32_t* info, int32_t* first, int32_t* size, int32_t max_items) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (!info || sms < 1) return PPN_E_BADARG;
+    const ppn::Tuning g_tuning = tuning_now();
+    ppn::ArgmaxPlan p;
+    if (!ppn::plan_argmax(make_geom(shape), g_tuning, sms, &p) || !p.split_mats) return PPN_E_UNSUPPORTED;
+    struct Ctx { int32_t* first; int32_t* size; int32_t max; } ctx = {first, size, max_items};
+    int n_items = 0;
+    ppn::argmax_item_partition(p, shape->B * shape->E, &n_items, [](void* c, int it, int m0, int nm) -> int {
+        Ctx* x = static_cast<Ctx*>(c);
+        if (x->first && x->size && it < x->max) { x->first[it] = m0; x->size[it] = nm; }
+        return 0;
+    }, &ctx);
+    info[0] = p.G; info[1] = p.n_big; info[2] = p.small_m; info[3] = n_items;
+    return PPN_OK;
 }
 
 int ppn_profile_enable(int32_t on) {

@@ -32,6 +32,16 @@ namespace ppn {
 
 struct Partial { float v; int32_t i; };
 
+// split-matrix ring kernels: work item -> first matrix and number of matrices (see ArgmaxPlan::n_big)
+__host__ __device__ __forceinline__ int item_first(const ArgmaxPlan& p, int item) {
+    return item < p.n_big ? item * p.G : p.n_big * p.G + (item - p.n_big) * p.small_m;
+}
+__host__ __device__ __forceinline__ int item_size(const ArgmaxPlan& p, int item) { return item < p.n_big ? p.G : p.small_m; }
+__host__ __device__ __forceinline__ int item_count(const ArgmaxPlan& p, int n_mats) {
+    const int rest = n_mats - p.n_big * p.G;
+    return p.n_big + (rest + p.small_m - 1) / p.small_m;
+}
+
 __global__ void __launch_bounds__(1024, 1)
 limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ amax, Geom g, ArgmaxPlan p, int pdl,
                        int* __restrict__ ticket, int32_t* __restrict__ zero2) {
@@ -182,8 +192,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
     const int tid = threadIdx.x;
     const int n_cons = p.threads_padded;
     const int n_mats = g.B * g.E;
-    const int M = p.G;
-    const int n_items = (n_mats + M - 1) / M;
+    const int n_items = item_count(p, n_mats);
     const uint32_t slot_bytes = (uint32_t)p.rows * g.HW * 4u;
 
     if (tid == 0) {
@@ -214,8 +223,9 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
                 if (lane == 0) { s_item[stage] = -1; mbar_arrive(&full[stage]); }
                 break;
             }
-            const int m = item * M + lane;
-            const int nm = min(M, n_mats - item * M);
+            const int m0 = item_first(p, item);
+            const int m = m0 + lane;
+            const int nm = min(item_size(p, item), n_mats - m0);
             const int b = m / g.E, ei = m - b * g.E;
             const float* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
             for (int c = 0; c < p.chunks; ++c) {
@@ -247,8 +257,8 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         mbar_wait(&full[stage], phase);
         const int item = s_item[stage];
         if (item < 0) break;
-        const int m = item * M + j;
-        const bool active = tid < p.threads && m < n_mats;
+        const int m = item_first(p, item) + j;
+        const bool active = tid < p.threads && j < item_size(p, item) && m < n_mats;
         float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
         int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
         for (int c = 0; c < p.chunks; ++c) {
@@ -345,8 +355,7 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
     const int tid = threadIdx.x;
     const int n_cons = p.threads_padded;
     const int n_mats = g.B * g.E;
-    const int M = p.G;
-    const int n_items = (n_mats + M - 1) / M;
+    const int n_items = item_count(p, n_mats);
     const uint32_t slot_bytes = (uint32_t)p.rows * g.HW * 2u;
 
     if (tid == 0) {
@@ -376,8 +385,9 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
                 if (lane == 0) { s_item[stage] = -1; mbar_arrive(&full[stage]); }
                 break;
             }
-            const int m = item * M + lane;
-            const int nm = min(M, n_mats - item * M);
+            const int m0 = item_first(p, item);
+            const int m = m0 + lane;
+            const int nm = min(item_size(p, item), n_mats - m0);
             const int b = m / g.E, ei = m - b * g.E;
             const T16* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
             for (int c = 0; c < p.chunks; ++c) {
@@ -408,8 +418,8 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
         mbar_wait(&full[stage], phase);
         const int item = s_item[stage];
         if (item < 0) break;
-        const int m = item * M + j;
-        const bool active = tid < p.threads && m < n_mats;
+        const int m = item_first(p, item) + j;
+        const bool active = tid < p.threads && j < item_size(p, item) && m < n_mats;
         uint32_t best[4], idx[4];                                   // two columns per register
 #pragma unroll
         for (int q = 0; q < 4; ++q) { best[q] = Packed16<T16>::kNegInf2; idx[q] = 0u; }
@@ -1649,6 +1659,57 @@ part_centres_kernel(const int32_t* __restrict__ count, const int32_t* __restrict
 }
 
 // =========================================================================================
+// skeleton — drawing primitives of the webcam loop, straight from the packed result
+// =========================================================================================
+// What draw_humans (datatest.py:162-232, called at rt_test.py:138-145) computes per human in Python, for every
+// slot of the batch in one launch:
+//   rect     [B, R, 4]    int32  the root box as it is drawn: (xmin, ymin, xmax, ymax) truncated like int() (:177-181)
+//   keypoint [B, R, K, 2] fp32   (x, y) = box centre of every present part (:200-202), NaN where absent
+//   segment  [B, R, E, 4] fp32   (bx, by, ex, ey) of every limb whose two parts are present (:213-221), NaN else
+// One thread per (image, slot, item), item = rect | part k | limb e.  Same fp32 arithmetic as numpy's: an add and
+// an exact halving.  Slots beyond count[b] give rect 0 and NaNs.
+struct EdgePairs { uint8_t src[256]; uint8_t dst[256]; };
+
+__global__ void __launch_bounds__(256)
+skeleton_kernel(const int32_t* __restrict__ count, const int32_t* __restrict__ cell, const float4* __restrict__ box, size_t n,
+                int R, int K, int E, EdgePairs edges, int4* __restrict__ rect, float2* __restrict__ keypoint,
+                float4* __restrict__ segment) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int per = 1 + K + E;
+    const size_t human = i / per;
+    const int item = (int)(i - human * per);
+    const int b = (int)(human / R), slot = (int)(human - (size_t)b * R);
+    const bool live = slot < count[b];
+    const float nan = __int_as_float(0x7fc00000);
+    const size_t base = human * K;
+    auto centre = [&](int k, float& x, float& y) -> bool {
+        if (!live || cell[base + k] < 0) return false;
+        const float4 bx = box[base + k];
+        y = __fmul_rn(__fadd_rn(bx.x, bx.z), 0.5f);
+        x = __fmul_rn(__fadd_rn(bx.y, bx.w), 0.5f);
+        return true;
+    };
+    if (item == 0) {
+        int4 r = make_int4(0, 0, 0, 0);
+        if (live && cell[base] >= 0) {
+            const float4 bx = box[base];                               // (ymin, xmin, ymax, xmax)
+            r = make_int4(__float2int_rz(bx.y), __float2int_rz(bx.x), __float2int_rz(bx.w), __float2int_rz(bx.z));
+        }
+        rect[human] = r;
+    } else if (item <= K) {
+        const int k = item - 1;
+        float x, y;
+        keypoint[base + k] = centre(k, x, y) ? make_float2(x, y) : make_float2(nan, nan);
+    } else {
+        const int e = item - 1 - K;
+        float bx, by, ex, ey;
+        const bool ok = centre(edges.src[e], bx, by) && centre(edges.dst[e], ex, ey);
+        segment[human * E + e] = ok ? make_float4(bx, by, ex, ey) : make_float4(nan, nan, nan, nan);
+    }
+}
+
+// =========================================================================================
 // pack — dense pose entries for the multi-GPU gather
 // =========================================================================================
 // Fixed-stride PPNHumans -> one contiguous buffer of (human, part) ENTRIES, present parts only:
@@ -1894,6 +1955,27 @@ static cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Items of G matrices are drawn by `grid` persistent CTAs.  With equal items the CTAs finish up to one item apart
+// (cfg2: 960 items on 148 CTAs = 6.5 waves, 7 % of the launch is a half-empty last wave).  So all but the last full
+// wave are handed out as items of G, and what is left — between one and two waves of work — as items of G/4:
+// the same code path with fewer of the thread groups busy, and the CTAs finish within a quarter item of one another.
+static void plan_tail(ArgmaxPlan* p, long long n_mats, long long grid, bool shrink) {
+    const long long full_items = n_mats / p->G;
+    const long long waves = grid > 0 ? full_items / grid : 0;
+    p->small_m = shrink && waves >= 2 ? std::max(1, p->G / 4) : p->G;
+    p->n_big = p->small_m == p->G ? (int)((n_mats + p->G - 1) / p->G) : (int)((waves - 1) * grid);
+    if (p->small_m == p->G) p->n_big = (int)full_items;          // the remainder (< G matrices) is one last item
+}
+
+// host-side view of the item partition, for the CPU test that checks it covers every matrix exactly once
+void argmax_item_partition(const ArgmaxPlan& p, int n_mats, int* n_items, int (*first_size)(void*, int, int, int), void* ctx) {
+    *n_items = item_count(p, n_mats);
+    for (int it = 0; it < *n_items; ++it) {
+        const int m0 = item_first(p, it);
+        first_size(ctx, it, m0, std::min(item_size(p, it), n_mats - m0));
+    }
+}
+
 bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     if (g.HW % 4 != 0 || g.HW / 4 > 992) return false;
     p->CV = g.HW / 4;
@@ -1908,23 +1990,11 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     if (p->split_mats) {
         if (G > 32) G = 32;                               // one producer lane per matrix
         if (G > g.B * g.E) G = g.B * g.E;
-        // items are dealt round-robin to `grid` persistent CTAs: among G/2..G matrices per item take
-        // the count whose last wave is fullest (cfg2: 8 -> 960 items, 6.5 waves, 7 % idle; 4 -> 12.97)
-        const long long n_mats = (long long)g.B * g.E;
-        const long long grid = (long long)sms * (t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm);
-        int bestM = G;
-        double best_eff = 0.0;
-        for (int M = G; t.argmax_tail_opt && M >= (G + 1) / 2 && M >= 1; --M) {
-            const long long items = (n_mats + M - 1) / M;
-            const long long waves = (items + grid - 1) / grid;
-            const double eff = (double)n_mats / (double)(waves * grid * M);
-            if (eff > best_eff + 0.02) { best_eff = eff; bestM = M; }
-        }
-        G = bestM;
     } else if (G > g.S) {
         G = g.S;
     }
     p->G = G;
+    plan_tail(p, (long long)g.B * g.E, (long long)sms * (t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm), t.argmax_tail_opt != 0);
     p->threads = p->CV * G;
     p->threads_padded = (p->threads + 31) & ~31;
     const int per_row = p->split_mats ? row_bytes * G : row_bytes;     // ring bytes per row index
@@ -1945,10 +2015,8 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     return true;
 }
 
-// Ring plan for a 16-bit head: always the split-matrix mapping, 16-byte vectors of 8 columns.
-// Items of G matrices are dealt to `grid` persistent CTAs; with few items per CTA (cfg2: 7680
-// matrices, 2-3 items each) the fill of the last wave decides, so among G/2..G matrices per item
-// the count whose last wave is fullest is taken (cfg2: 26 -> 296 items = 2.0 waves).
+// Ring plan for a 16-bit head: always the split-matrix mapping, 16-byte vectors of 8 columns; items of G matrices
+// with the shrinking tail of plan_tail().
 static bool plan_argmax16(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     if (g.HW % 8 != 0 || g.HW / 8 > 992) return false;
     p->CV = g.HW / 8;
@@ -1959,21 +2027,9 @@ static bool plan_argmax16(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p
     if (G > 32) G = 32;
     if (G > g.B * g.E) G = g.B * g.E;
     p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
-    {
-        const long long n_mats = (long long)g.B * g.E;
-        const long long grid = (long long)sms * p->ctas_per_sm;
-        int bestM = G;
-        double best_eff = 0.0;
-        for (int M = G; M >= (G + 1) / 2 && M >= 1; --M) {
-            const long long items = (n_mats + M - 1) / M;
-            const long long waves = (items + grid - 1) / grid;
-            const double eff = (double)n_mats / (double)(waves * grid * M);
-            if (eff > best_eff + 0.02) { best_eff = eff; bestM = M; }
-        }
-        G = bestM;
-    }
     p->split_mats = 1;
     p->G = G;
+    plan_tail(p, (long long)g.B * g.E, (long long)sms * p->ctas_per_sm, t.argmax_tail_opt != 0);
     p->threads = p->CV * G;
     p->threads_padded = (p->threads + 31) & ~31;
     const int per_row = row_bytes * G;
@@ -2012,7 +2068,7 @@ static cudaError_t launch_limb_argmax16(const T16* head, uint16_t* amax, const G
             int* ticket = nullptr;
             if (t.argmax_dynamic && (e = ticket_for(d, st, &ticket)) != cudaSuccess) return e;
             int grid = d->sms * p.ctas_per_sm;
-            const int n_items = (n_mats + p.G - 1) / p.G;
+            const int n_items = item_count(p, n_mats);
             if (grid > n_items) grid = n_items;
             if ((e = ensure_smem(limb_argmax_tma_multi16_kernel<T16>, p.smem_bytes, have)) != cudaSuccess) return e;
             e = launch_kernel(limb_argmax_tma_multi16_kernel<T16>, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
@@ -2124,7 +2180,7 @@ cudaError_t launch_limb_argmax(const void* head_v, uint16_t* amax, const Geom& g
             if (t.argmax_dynamic && (e = ticket_for(d, st, &ticket)) != cudaSuccess) return e;
             int grid = d->sms * p.ctas_per_sm;
             if (p.split_mats) {
-                const int n_items = (n_mats + p.G - 1) / p.G;
+                const int n_items = item_count(p, n_mats);
                 if (grid > n_items) grid = n_items;
                 if ((e = ensure_smem(limb_argmax_tma_multi_kernel, p.smem_bytes, &d->tma_multi)) != cudaSuccess) return e;
                 e = launch_kernel(limb_argmax_tma_multi_kernel, dim3(grid), dim3(p.threads_padded + 32), p.smem_bytes, st, pdl,
@@ -2205,6 +2261,18 @@ cudaError_t launch_part_centres(const int32_t* count, const int32_t* cell, const
     if (n == 0) return cudaSuccess;
     part_centres_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(count, cell, reinterpret_cast<const float4*>(box), n, R, K,
                                                                      reinterpret_cast<float2*>(centre));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_skeleton(const int32_t* count, const int32_t* cell, const float* box, int B, int R, int K, int E,
+                            const int32_t* edges, int32_t* rect, float* keypoint, float* segment, cudaStream_t st) {
+    const size_t n = (size_t)B * R * (1 + K + E);
+    if (n == 0) return cudaSuccess;
+    EdgePairs ep;
+    for (int e = 0; e < E; ++e) { ep.src[e] = (uint8_t)edges[2 * e]; ep.dst[e] = (uint8_t)edges[2 * e + 1]; }
+    skeleton_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(count, cell, reinterpret_cast<const float4*>(box), n, R, K, E, ep,
+                                                                 reinterpret_cast<int4*>(rect), reinterpret_cast<float2*>(keypoint),
+                                                                 reinterpret_cast<float4*>(segment));
     return cudaGetLastError();
 }
 

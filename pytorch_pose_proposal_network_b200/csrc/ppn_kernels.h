@@ -13,7 +13,8 @@ struct Tuning {
     int argmax_ctas_per_sm = 1;
     int argmax_split = -1;             // -1 auto, 0 = groups split rows, 1 = groups take one matrix each
     int argmax_dynamic = 1;            // ring kernels draw work from a global ticket counter (0: static round-robin)
-    int argmax_tail_opt = 0;           // split-matrix mode: pick matrices/item that fills the last wave best
+    int argmax_tail_opt = 1;           // split-matrix mode: the last ~1.5 waves of work are handed out in items a quarter the size,
+                                       // so that the CTAs finish within a quarter item of one another (0: equal items)
     int argmax_cluster = -1;           // tiny batches: a cluster of CTAs per matrix, partials merged through distributed
                                        // shared memory.  -1 auto (matrices <= half the SMs), 0 never, 2/4/8 forced
     int argmax_smem_cap = 0;           // > 0: the ring may use at most this much shared memory (set per call by ppn_parse
@@ -44,11 +45,14 @@ struct ArgmaxPlan {
     int stages;           // ring depth
     int ctas_per_sm;
     int dry;              // 1: consumers only release the stages (bandwidth probe)
+    int n_big;            // split-matrix mode: items [0, n_big) hold G matrices each, the items after them `small_m`
+    int small_m;          //   (a shrinking tail: with equal items the last wave of a persistent grid is on average half empty)
     uint32_t stage_bytes;
     size_t smem_bytes;
 };
 
 bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p);
+void argmax_item_partition(const ArgmaxPlan& p, int n_mats, int* n_items, int (*first_size)(void*, int, int, int), void* ctx);
 
 // pdl: launch as a programmatic dependent of the previous kernel in `st` (starts beside it, waits
 // for it only before completing); *pdl_used tells whether the chosen kernel variant honoured it.
@@ -75,6 +79,9 @@ cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float
 
 cudaError_t launch_part_centres(const int32_t* count, const int32_t* cell, const float* box, int B, int R, int K,
                                 float* centre, cudaStream_t st);
+
+cudaError_t launch_skeleton(const int32_t* count, const int32_t* cell, const float* box, int B, int R, int K, int E,
+                            const int32_t* edges /* host [E][2] */, int32_t* rect, float* keypoint, float* segment, cudaStream_t st);
 
 cudaError_t launch_pack_humans(const int32_t* count, const int32_t* cell, const float* score, const float* box, int B, int R,
                                int K, int cap, int32_t* header, uint32_t* e_idcell, float* e_score, float* e_box,

@@ -401,6 +401,30 @@ class PoseParser:
                                                  torch.cuda.current_stream(self.device).cuda_stream), "ppn_part_centres")
         return out
 
+    def skeleton(self, humans: PackedHumans, edges=None):
+        """Drawing primitives of every slot (``ppn_skeleton``; datatest.py:162-232): -> (rect [B, R, 4] int32
+        (xmin, ymin, xmax, ymax), keypoint [B, R, K, 2] fp32 (x, y), segment [B, R, E, 4] fp32 (bx, by, ex, ey));
+        NaN where a part / limb is absent.  Asynchronous, on torch's current stream."""
+        cfg = self.cfg
+        if edges is None:
+            from . import config as pcfg
+            edges = {(18, 17): pcfg.EDGES, (16, 15): pcfg.EDGES_16}.get((cfg.K, cfg.E))
+            if edges is None:
+                raise ValueError("pass `edges` ([E][2] part ids) for a skeleton that is not one of config.py's")
+        e = np.ascontiguousarray(np.asarray(edges, np.int32).reshape(-1, 2))
+        if e.shape[0] != cfg.E:
+            raise ValueError(f"{e.shape[0]} edges for a configuration with E = {cfg.E}")
+        B = humans.count.shape[0]
+        rect = torch.empty(B, humans.R, 4, dtype=torch.int32, device=self.device)
+        kp = torch.empty(B, humans.R, cfg.K, 2, dtype=torch.float32, device=self.device)
+        seg = torch.empty(B, humans.R, cfg.E, 4, dtype=torch.float32, device=self.device)
+        hs = self._humans_struct(humans)
+        with self._guard():
+            _lib.check(self.lib.ppn_skeleton(C.byref(hs), B, cfg.K, cfg.E, e.ctypes.data_as(_lib.i32p), rect.data_ptr(),
+                                             kp.data_ptr(), seg.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
+                       "ppn_skeleton")
+        return rect, kp, seg
+
     # ---- dense entries (what the multi-GPU gather ships) -------------------------------- #
     def packed_layout(self, B: int, cap_entries: int):
         """-> (bytes, (header, idcell, score, box) byte offsets) of the dense entry buffer."""

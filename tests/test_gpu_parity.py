@@ -135,7 +135,7 @@ def test_dropin_rt_test_inference():
             assert x.shape == (1, 3, 384, 384) and x.dtype == torch.float32
             return fixed
     image = (np.random.default_rng(0).random((384, 384, 3)) * 255).astype(np.uint8)
-    humans, scores = rt_test.inference(image, Head(), (24, 24), (21, 21))
+    humans, scores = rt_test.inference(image, Head(), (24, 24), (21, 21), return_humans=True)
     want_h, want_s = O.humans_as_dicts(O.parse_image(fixed[0].cpu().numpy(), g))
     assert len(humans) == len(want_h) > 0
     for hm, wh, sc, ws in zip(humans, want_h, scores, want_s):

@@ -209,3 +209,32 @@ def test_gather_world2_gloo(tmp_path, n_images):
     port = 29500 + (os.getpid() % 2000) + n_images
     mp.spawn(_gloo_worker, args=(2, port, n_images, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ["rank0.ok", "rank1.ok"]
+
+
+def test_argmax_work_items_tile_the_batch():
+    """The ring kernel's work items (full items, then a tail of quarter items) must cover every (image, limb)
+    matrix exactly once, in order — pure host arithmetic of the launch plan, checked without a GPU."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import _CConfig
+    lib = _lib.lib()
+    for cfg, batches in ((PPNConfig.mpii16(), (1, 7, 64, 300, 512, 513, 2048)), (PPNConfig.coco18(), (3, 1024)),
+                         (PPNConfig.highres(), (256,)), (PPNConfig.reference_native(), (1, 64, 65))):
+        cc = _CConfig(cfg)
+        for B in batches:
+            for sms in (148, 132, 7):
+                shape = cc.shape(B)
+                info = (C.c_int32 * 4)()
+                n_mats = B * cfg.E
+                first, size = (C.c_int32 * (n_mats + 1))(), (C.c_int32 * (n_mats + 1))()
+                rc = lib.ppn_debug_argmax_items(C.byref(shape), sms, info, first, size, n_mats + 1)
+                if rc == -2:
+                    continue                    # this shape does not take the split-matrix ring
+                assert rc == 0
+                G, n_big, small_m, n_items = list(info)
+                assert 1 <= small_m <= G and 0 <= n_big <= n_items <= n_mats
+                at = 0
+                for it in range(n_items):
+                    assert first[it] == at and 1 <= size[it] <= (G if it < n_big else small_m), (B, sms, it)
+                    at += size[it]
+                assert at == n_mats, (B, sms, at, n_mats)
