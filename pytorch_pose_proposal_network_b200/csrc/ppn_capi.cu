@@ -221,7 +221,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.split")) t.argmax_split = value;
     else if (!std::strcmp(key, "argmax.cluster")) t.argmax_cluster = value;
     else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
-    else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value != 0;
+    else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value < 0 ? 0 : (value > 8 ? 8 : value);
     else if (!std::strcmp(key, "argmax16.threads")) t.argmax16_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
     else if (!std::strcmp(key, "argmax16.stage_bytes")) t.argmax16_stage_bytes = value < 1024 ? 1024 : value;
     else if (!std::strcmp(key, "argmax.dynamic")) t.argmax_dynamic = value != 0;

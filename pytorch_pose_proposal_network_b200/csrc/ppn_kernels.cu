@@ -193,7 +193,6 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
     const int n_cons = p.threads_padded;
     const int n_mats = g.B * g.E;
     const int n_items = item_count(p, n_mats);
-    const uint32_t slot_bytes = (uint32_t)p.rows * g.HW * 4u;
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -226,11 +225,13 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
             const int m0 = item_first(p, item);
             const int m = m0 + lane;
             const int nm = min(item_size(p, item), n_mats - m0);
+            const int it_rows = item < p.n_big ? p.rows : p.rows_s, it_chunks = item < p.n_big ? p.chunks : p.chunks_s;
+            const uint32_t it_slot = (uint32_t)it_rows * g.HW * 4u;
             const int b = m / g.E, ei = m - b * g.E;
             const float* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
-            for (int c = 0; c < p.chunks; ++c) {
+            for (int c = 0; c < it_chunks; ++c) {
                 mbar_wait(&empty[stage], phase ^ 1u);
-                const int rows = min(p.rows, g.S - c * p.rows);
+                const int rows = min(it_rows, g.S - c * it_rows);
                 const uint32_t bytes = (uint32_t)rows * g.HW * 4u;
                 if (lane == 0) {
                     if (c == 0) s_item[stage] = item;
@@ -238,8 +239,8 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
                 }
                 __syncwarp();
                 if (lane < nm)
-                    bulk_g2s(ring + (size_t)stage * p.stage_bytes + (size_t)lane * slot_bytes,
-                             src + (size_t)c * p.rows * g.HW, bytes, &full[stage]);
+                    bulk_g2s(ring + (size_t)stage * p.stage_bytes + (size_t)lane * it_slot,
+                             src + (size_t)c * it_rows * g.HW, bytes, &full[stage]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
             if (!ticket) item += gridDim.x;
@@ -259,14 +260,16 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
         if (item < 0) break;
         const int m = item_first(p, item) + j;
         const bool active = tid < p.threads && j < item_size(p, item) && m < n_mats;
+        const int it_rows = item < p.n_big ? p.rows : p.rows_s, it_chunks = item < p.n_big ? p.chunks : p.chunks_s;
+        const uint32_t it_slot = (uint32_t)it_rows * g.HW * 4u;
         float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
         int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-        for (int c = 0; c < p.chunks; ++c) {
+        for (int c = 0; c < it_chunks; ++c) {
             if (c > 0) mbar_wait(&full[stage], phase);
             if (active && !p.dry) {
-                const int rows = min(p.rows, g.S - c * p.rows);
-                const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
-                int a = c * p.rows;
+                const int rows = min(it_rows, g.S - c * it_rows);
+                const float4* col = reinterpret_cast<const float4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * it_slot) + cv;
+                int a = c * it_rows;
                 int r = 0;
 #pragma unroll 1
                 for (; r + 3 < rows; r += 4, a += 4) {
@@ -356,7 +359,6 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
     const int n_cons = p.threads_padded;
     const int n_mats = g.B * g.E;
     const int n_items = item_count(p, n_mats);
-    const uint32_t slot_bytes = (uint32_t)p.rows * g.HW * 2u;
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -388,11 +390,13 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
             const int m0 = item_first(p, item);
             const int m = m0 + lane;
             const int nm = min(item_size(p, item), n_mats - m0);
+            const int it_rows = item < p.n_big ? p.rows : p.rows_s, it_chunks = item < p.n_big ? p.chunks : p.chunks_s;
+            const uint32_t it_slot = (uint32_t)it_rows * g.HW * 2u;
             const int b = m / g.E, ei = m - b * g.E;
             const T16* src = head + (size_t)b * g.img_stride + g.limb_off + (size_t)ei * g.S * g.HW;
-            for (int c = 0; c < p.chunks; ++c) {
+            for (int c = 0; c < it_chunks; ++c) {
                 mbar_wait(&empty[stage], phase ^ 1u);
-                const int rows = min(p.rows, g.S - c * p.rows);
+                const int rows = min(it_rows, g.S - c * it_rows);
                 const uint32_t bytes = (uint32_t)rows * g.HW * 2u;
                 if (lane == 0) {
                     if (c == 0) s_item[stage] = item;
@@ -400,8 +404,8 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
                 }
                 __syncwarp();
                 if (lane < nm)
-                    bulk_g2s(ring + (size_t)stage * p.stage_bytes + (size_t)lane * slot_bytes,
-                             src + (size_t)c * p.rows * g.HW, bytes, &full[stage]);
+                    bulk_g2s(ring + (size_t)stage * p.stage_bytes + (size_t)lane * it_slot,
+                             src + (size_t)c * it_rows * g.HW, bytes, &full[stage]);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
             if (!ticket) item += gridDim.x;
@@ -420,15 +424,17 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
         if (item < 0) break;
         const int m = item_first(p, item) + j;
         const bool active = tid < p.threads && j < item_size(p, item) && m < n_mats;
+        const int it_rows = item < p.n_big ? p.rows : p.rows_s, it_chunks = item < p.n_big ? p.chunks : p.chunks_s;
+        const uint32_t it_slot = (uint32_t)it_rows * g.HW * 2u;
         uint32_t best[4], idx[4];                                   // two columns per register
 #pragma unroll
         for (int q = 0; q < 4; ++q) { best[q] = Packed16<T16>::kNegInf2; idx[q] = 0u; }
-        for (int c = 0; c < p.chunks; ++c) {
+        for (int c = 0; c < it_chunks; ++c) {
             if (c > 0) mbar_wait(&full[stage], phase);
             if (active && !p.dry) {
-                const int rows = min(p.rows, g.S - c * p.rows);
-                const uint4* col = reinterpret_cast<const uint4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * slot_bytes) + cv;
-                uint32_t a2 = (uint32_t)(c * p.rows) * 0x00010001u;       // the row index in both halves
+                const int rows = min(it_rows, g.S - c * it_rows);
+                const uint4* col = reinterpret_cast<const uint4*>(ring + (size_t)stage * p.stage_bytes + (size_t)j * it_slot) + cv;
+                uint32_t a2 = (uint32_t)(c * it_rows) * 0x00010001u;       // the row index in both halves
                 int r = 0;
 #pragma unroll 1
                 for (; r + 3 < rows; r += 4, a2 += 0x00040004u) {
@@ -1957,12 +1963,12 @@ static cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 
 // Items of G matrices are drawn by `grid` persistent CTAs.  With equal items the CTAs finish up to one item apart
 // (cfg2: 960 items on 148 CTAs = 6.5 waves, 7 % of the launch is a half-empty last wave).  So all but the last full
-// wave are handed out as items of G, and what is left — between one and two waves of work — as items of G/4:
+// wave are handed out as items of G, and what is left — between one and two waves of work — as items of G/n (n = 4):
 // the same code path with fewer of the thread groups busy, and the CTAs finish within a quarter item of one another.
-static void plan_tail(ArgmaxPlan* p, long long n_mats, long long grid, bool shrink) {
+static void plan_tail(ArgmaxPlan* p, long long n_mats, long long grid, int divide) {
     const long long full_items = n_mats / p->G;
     const long long waves = grid > 0 ? full_items / grid : 0;
-    p->small_m = shrink && waves >= 2 ? std::max(1, p->G / 4) : p->G;
+    p->small_m = divide > 1 && waves >= 2 ? std::max(1, p->G / divide) : p->G;
     p->n_big = p->small_m == p->G ? (int)((n_mats + p->G - 1) / p->G) : (int)((waves - 1) * grid);
     if (p->small_m == p->G) p->n_big = (int)full_items;          // the remainder (< G matrices) is one last item
 }
@@ -1974,6 +1980,19 @@ void argmax_item_partition(const ArgmaxPlan& p, int n_mats, int* n_items, int (*
         const int m0 = item_first(p, it);
         first_size(ctx, it, m0, std::min(item_size(p, it), n_mats - m0));
     }
+}
+
+// A tail item holds small_m matrices instead of G: it takes G / small_m times the rows per stage, so that a stage
+// still carries about the same bytes (and the bulk copies get longer) — a CTA in the tail streams as fast as before.
+static void plan_tail_rows(ArgmaxPlan* p, int S, int row_bytes) {
+    p->rows_s = p->rows;
+    p->chunks_s = p->chunks;
+    if (!row_bytes || p->small_m >= p->G) return;
+    int max_rows = (int)(p->stage_bytes / ((size_t)row_bytes * p->small_m));
+    max_rows = std::max(1, std::min(max_rows, S));
+    p->chunks_s = (S + max_rows - 1) / max_rows;
+    p->rows_s = (S + p->chunks_s - 1) / p->chunks_s;
+    p->chunks_s = (S + p->rows_s - 1) / p->rows_s;
 }
 
 bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
@@ -1994,7 +2013,7 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
         G = g.S;
     }
     p->G = G;
-    plan_tail(p, (long long)g.B * g.E, (long long)sms * (t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm), t.argmax_tail_opt != 0);
+    plan_tail(p, (long long)g.B * g.E, (long long)sms * (t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm), t.argmax_tail_opt);
     p->threads = p->CV * G;
     p->threads_padded = (p->threads + 31) & ~31;
     const int per_row = p->split_mats ? row_bytes * G : row_bytes;     // ring bytes per row index
@@ -2007,6 +2026,7 @@ bool plan_argmax(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p) {
     p->rows = (g.S + p->chunks - 1) / p->chunks;
     p->chunks = (g.S + p->rows - 1) / p->rows;
     p->stage_bytes = (uint32_t)(((size_t)p->rows * per_row + 127) & ~(size_t)127);
+    plan_tail_rows(p, g.S, p->split_mats ? row_bytes : 0);
     p->stages = t.argmax_stages;
     p->dry = t.argmax_dry;
     p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
@@ -2029,7 +2049,7 @@ static bool plan_argmax16(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p
     p->ctas_per_sm = t.argmax_ctas_per_sm < 1 ? 1 : t.argmax_ctas_per_sm;
     p->split_mats = 1;
     p->G = G;
-    plan_tail(p, (long long)g.B * g.E, (long long)sms * p->ctas_per_sm, t.argmax_tail_opt != 0);
+    plan_tail(p, (long long)g.B * g.E, (long long)sms * p->ctas_per_sm, t.argmax_tail_opt);
     p->threads = p->CV * G;
     p->threads_padded = (p->threads + 31) & ~31;
     const int per_row = row_bytes * G;
@@ -2040,6 +2060,7 @@ static bool plan_argmax16(const Geom& g, const Tuning& t, int sms, ArgmaxPlan* p
     p->rows = (g.S + p->chunks - 1) / p->chunks;
     p->chunks = (g.S + p->rows - 1) / p->rows;
     p->stage_bytes = (uint32_t)(((size_t)p->rows * per_row + 127) & ~(size_t)127);
+    plan_tail_rows(p, g.S, row_bytes);
     p->stages = t.argmax_stages;
     p->dry = t.argmax_dry;
     p->smem_bytes = (size_t)p->stages * p->stage_bytes + (size_t)2 * p->stages * sizeof(uint64_t) + (size_t)p->stages * sizeof(int);

@@ -13,8 +13,11 @@ struct Tuning {
     int argmax_ctas_per_sm = 1;
     int argmax_split = -1;             // -1 auto, 0 = groups split rows, 1 = groups take one matrix each
     int argmax_dynamic = 1;            // ring kernels draw work from a global ticket counter (0: static round-robin)
-    int argmax_tail_opt = 1;           // split-matrix mode: the last ~1.5 waves of work are handed out in items a quarter the size,
-                                       // so that the CTAs finish within a quarter item of one another (0: equal items)
+    int argmax_tail_opt = 0;           // split-matrix mode: n > 1 hands the last ~1.5 waves of work out in items 1/n the size (more rows of
+                                       // fewer matrices per stage), so that the CTAs finish within 1/n item of one another.  Measured at
+                                       // cfg2 (profiles/tail_sweep_r2.txt): isolated launch 60.1 us with equal items, 60.5 / 64.1 / 74.6 us
+                                       // with n = 2 / 4 / 8 — a tail item keeps 1/n of the consumer threads busy and streams slower than
+                                       // the half-empty last wave costs; and inside the call chain the next launch fills that wave anyway
     int argmax_cluster = -1;           // tiny batches: a cluster of CTAs per matrix, partials merged through distributed
                                        // shared memory.  -1 auto (matrices <= half the SMs), 0 never, 2/4/8 forced
     int argmax_smem_cap = 0;           // > 0: the ring may use at most this much shared memory (set per call by ppn_parse
@@ -47,6 +50,7 @@ struct ArgmaxPlan {
     int dry;              // 1: consumers only release the stages (bandwidth probe)
     int n_big;            // split-matrix mode: items [0, n_big) hold G matrices each, the items after them `small_m`
     int small_m;          //   (a shrinking tail: with equal items the last wave of a persistent grid is on average half empty)
+    int rows_s, chunks_s; // rows per stage / stages per matrix of a tail item (more rows of fewer matrices: same bytes per stage)
     uint32_t stage_bytes;
     size_t smem_bytes;
 };

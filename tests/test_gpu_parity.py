@@ -283,8 +283,34 @@ def test_limb_argmax_every_tuning(preset, variant, stage_bytes, stages, threads,
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("dynamic,tail_opt", [(1, 0), (1, 2), (1, 4), (0, 4), (1, 8)])
+def test_limb_argmax_shrinking_tail(dtype, dynamic, tail_opt):
+    """A batch of several waves of work items: the last waves are handed out as smaller items holding more rows of
+    fewer matrices (plan_tail).  Every matrix must still be reduced exactly once, whatever the item sizes."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS["cfg2"]()
+    g = O.Geometry.of(cfg)
+    B = 301                                                       # 4515 matrices: 3-4 waves of 8-matrix items on 148 SMs, ragged end
+    head = torch.from_numpy(synth.make_head(g, "U", seed=31, B=B)).to(dtype)
+    up = head.float().numpy()
+    want = np.stack([c_oracle.limb_argmax(img, g) for img in up]).astype(np.uint16)
+    _lib.tune(argmax_dynamic=dynamic, argmax_tail_opt=tail_opt)
+    try:
+        parser = PoseParser(cfg)
+        dev = head.cuda()
+        for rep in range(2):
+            assert np.array_equal(parser.limb_argmax(dev).cpu().numpy(), want), rep
+        ref = c_oracle.parse_batch(up, g, n_threads=8)
+        assert_packed_equals_oracle(parser.parse(dev, input_complete=True).numpy(), ref, B)
+    finally:
+        _lib.tune(**TUNE_DEFAULTS)
+
+
 @pytest.mark.parametrize("preset", ["cfg2", "cfg4"])
-@pytest.mark.parametrize("dynamic,tail_opt,ctas", [(0, 0, 1), (0, 1, 2), (1, 0, 1), (1, 1, 2)])
+@pytest.mark.parametrize("dynamic,tail_opt,ctas", [(0, 0, 1), (0, 2, 2), (1, 0, 1), (1, 4, 2)])
 def test_limb_argmax_work_distribution(preset, dynamic, tail_opt, ctas):
     """Static round-robin vs ticket scheduling, repeated launches (the counter must reset itself)."""
     from pytorch_pose_proposal_network_b200 import _lib
