@@ -22,6 +22,13 @@ extern "C" {
 int ppn_profile_enable(int32_t on);
 int ppn_profile_read(float* stage_ms /*[4]*/, int32_t* n_calls);
 
+/* Device timeline of ppn_parse's kernels: while `dev_records` (device memory, [max_records][4] uint64, initialised
+ * by the caller to {~0, 0, ~0, 0}) is set, every kernel a ppn_parse call launches takes the next record and writes
+ * {first CTA start, last CTA end, first CTA past its dependency wait, -} in %globaltimer nanoseconds — in launch
+ * order: (arg-max, fused parse) per sub-batch on the two-kernel chain, (decode+NMS, arg-max, tree parse) on the
+ * three-kernel chain.  NULL switches it off.  One benchmark thread; scripts/timeline.py prints the overlap. */
+int ppn_timeline(void* dev_records, int32_t max_records);
+
 /* How the ring arg-max kernel cuts a batch into work items on a GPU of `sms` SMs (host arithmetic only, no launch):
  * info[4] = {matrices per full item, full items, matrices per tail item, items}; first/size (each [max_items] or
  * NULL) receive every item's first matrix and matrix count.  For the test that the items tile [0, B*E) exactly. */
@@ -31,9 +38,10 @@ int ppn_debug_argmax_items(const PPNShape* shape, int32_t sms, int32_t* info /*[
  * "argmax.stage_bytes", "argmax.stages", "argmax.threads", "argmax.ctas_per_sm",
  * "argmax.split" (-1 auto, 0 thread groups split rows, 1 thread groups take one matrix each),
  * "argmax.dynamic" (1 = ticket scheduling), "argmax.tail_opt", "argmax16.threads", "argmax16.stage_bytes" (ring shape
- * for 16-bit heads), "argmax.cluster" (tiny batches: -1 auto, 0 never, 2/4/8 = CTAs per matrix),
+ * for 16-bit heads), "argmax.cluster" (tiny batches: -1 auto, 0 never, 2/4/8 = CTAs per matrix), "argmax.smem_cap" (stand-alone arg-max: bytes of shared
+ * memory the ring may use, 0 = all),
  * "parse.fused" (-1 auto, 0 three-kernel chain, 1 two-kernel chain whenever supported, cutting large batches),
- * "parse.chain_calls", "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
+ * "parse.chain_calls", "parse.persist" (three-kernel chain: decode+NMS CTAs per SM of the persistent grids, 0 = one CTA per image), "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
  * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images",
  * "encode.sweep" (1 = address-ordered persistent sweep), "encode.ctas_per_sm".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);

@@ -66,6 +66,16 @@ cudaError_t side_lane(SideLane** out) {
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? PPN_OK : (int)e; }
 
+// ---- optional device timeline of ppn_parse's kernels (ppn_timeline, include/ppn_decode_bench.h) ------------
+// Every kernel of a call gets one 4 x uint64 record {first CTA start, last CTA end, first CTA past its dependency
+// wait, kind} in %globaltimer nanoseconds, written with atomicMin / atomicMax.  One benchmark thread.
+struct Timeline { unsigned long long* buf = nullptr; int cap = 0, used = 0; } g_timeline;
+inline ppn::Geom timeline_slot(ppn::Geom g) {
+    if (g_timeline.buf && g_timeline.used < g_timeline.cap) { g.tl = g_timeline.buf; g.tl_slot = g_timeline.used++; }
+    else g.tl = nullptr;
+    return g;
+}
+
 int check_shape(const PPNShape* s) {
     if (!s) return PPN_E_BADARG;
     if (s->B < 0 || s->K < 1 || s->E < 0 || s->H < 1 || s->W < 1 || s->sH < 1 || s->sW < 1) return PPN_E_BADARG;
@@ -86,6 +96,8 @@ ppn::Geom make_geom(const PPNShape* s) {
     g.gridW = (float)s->gridW; g.gridH = (float)s->gridH; g.inW = (float)s->inW; g.inH = (float)s->inH;
     g.img_stride = (size_t)g.C * g.HW;
     g.limb_off = (size_t)6 * g.K * g.HW;
+    g.tl = nullptr;
+    g.tl_slot = 0;
     auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
     g.magic_W = magic(g.W);
     g.magic_K = magic(g.K);
@@ -220,6 +232,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) t.argmax_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
     else if (!std::strcmp(key, "argmax.split")) t.argmax_split = value;
     else if (!std::strcmp(key, "argmax.cluster")) t.argmax_cluster = value;
+    else if (!std::strcmp(key, "argmax.smem_cap")) t.argmax_smem_cap = value < 0 ? 0 : value;
     else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value < 0 ? 0 : (value > 8 ? 8 : value);
     else if (!std::strcmp(key, "argmax16.threads")) t.argmax16_threads = value < 32 ? 32 : (value > 992 ? 992 : value);
@@ -227,6 +240,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.dynamic")) t.argmax_dynamic = value != 0;
     else if (!std::strcmp(key, "parse.stage_all")) t.parse_stage_all = value;
     else if (!std::strcmp(key, "parse.chain_calls")) t.parse_chain_calls = value != 0;
+    else if (!std::strcmp(key, "parse.persist")) t.parse_persist = value < 0 ? 0 : (value > 4 ? 4 : value);
     else if (!std::strcmp(key, "parse.fused")) t.parse_fused = value < 0 ? -1 : (value != 0);
     else if (!std::strcmp(key, "parse.threads")) t.parse_threads = value;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
@@ -246,6 +260,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) *value = t.argmax_ctas_per_sm;
     else if (!std::strcmp(key, "argmax.split")) *value = t.argmax_split;
     else if (!std::strcmp(key, "argmax.cluster")) *value = t.argmax_cluster;
+    else if (!std::strcmp(key, "argmax.smem_cap")) *value = t.argmax_smem_cap;
     else if (!std::strcmp(key, "parse.overlap")) *value = t.parse_overlap;
     else if (!std::strcmp(key, "argmax.tail_opt")) *value = t.argmax_tail_opt;
     else if (!std::strcmp(key, "argmax16.threads")) *value = t.argmax16_threads;
@@ -253,6 +268,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.dynamic")) *value = t.argmax_dynamic;
     else if (!std::strcmp(key, "parse.stage_all")) *value = t.parse_stage_all;
     else if (!std::strcmp(key, "parse.chain_calls")) *value = t.parse_chain_calls;
+    else if (!std::strcmp(key, "parse.persist")) *value = t.parse_persist;
     else if (!std::strcmp(key, "parse.fused")) *value = t.parse_fused;
     else if (!std::strcmp(key, "parse.threads")) *value = t.parse_threads;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
@@ -555,7 +571,7 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
         const size_t es = elem_bytes(shape);
         const size_t K = (size_t)shape->K, R = (size_t)out->R;
         auto launch_k3 = [&](int j) -> cudaError_t {
-            Geom gj = g;
+            Geom gj = timeline_slot(g);
             const int b0 = j * sub_B;
             gj.B = std::min(sub_B, g.B - b0);
             // an overlapped K3 may only start beside a fused parse that publishes; after anything else of
@@ -571,7 +587,7 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
             return err;
         };
         auto launch_k124 = [&](int j) -> cudaError_t {
-            Geom gj = g;
+            Geom gj = timeline_slot(g);
             const int b0 = j * sub_B;
             gj.B = std::min(sub_B, g.B - b0);
             DenseTarget dj;
@@ -602,33 +618,54 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
         return PPN_OK;
     }
     if (dense && dense->rheader) return PPN_E_UNSUPPORTED;     // remote entries are written by the fused parse kernel only
-    ppn::chain_break(st);
     if (mode == 2) {
         using namespace ppn;
-        bool chained = false;
-        // K12 is itself a programmatic dependent of whatever precedes it in the stream (normally the
-        // previous call's K4, which triggers once it is past its own wait): it becomes resident under
-        // that kernel.
-        //  * default: it WAITS for that kernel to complete before reading anything (the producer of
-        //    `head` may be that kernel), then releases K3 — only launch latency is hidden;
-        //  * PPN_FLAG_INPUT_COMPLETE: the caller vouches that `head` was completely written before the
-        //    call was enqueued, so K12 and K3 start at once, beside the previous call's tree parse
-        //    (which reads the OTHER workspace set), and K12 only waits for that kernel before it
-        //    COMPLETES.  Completion stays transitive: K4(i+1) waits for K3(i+1), which waits at its end
-        //    for K12(i+1), which waits at its end for K4(i) — so calls complete in order, the two
-        //    workspace sets are never shared, and no waiting kernel can starve the one it waits for
-        //    (K12(i+1) is only launched once every CTA of K4(i) is resident and running).
+        // Three kernels on one stream, chained by programmatic dependent launches, the two small ones as PERSISTENT
+        // grids that are resident beside the arg-max ring (parse.persist; the ring is capped to leave them room):
+        //   K12(i)  decode + NMS      needs only the head tensor; triggers at its top
+        //   K3(i)   limb arg-max      starts beside K12(i) at once; waits for it only before completing
+        //   K4(i)   tree parse        waits for K3(i) (hence K12(i)), then walks
+        //  * default: K12 waits for whatever precedes it in the stream before reading anything (the producer of `head`
+        //    may be that kernel), K4 triggers after its wait — only launch latencies are hidden between calls;
+        //  * PPN_FLAG_INPUT_COMPLETE: K4(i) triggers at its very TOP, so K12(i+1) and K3(i+1) are launched while K3(i)
+        //    still streams: K12(i+1) runs under K3(i) / K3(i+1), K4(i) under K3(i+1), and the limb stream never pauses.
+        //    Safe because K4(i) triggers only after it has SEEN K4(i-1) complete (sequence number published by K4's
+        //    last CTA — the same words the fused parse kernel uses): the kernels of call i+1 write the workspace set
+        //    call i-1 read.  Completion stays transitive: K3 waits at its end for K12, K12 for the previous K4.
+        //    Every kernel of the chain is fully resident when it triggers (persistent grids), so no waiting CTA can
+        //    keep a CTA it waits for off the SMs.
         const bool overlap_calls = (params->flags & PPN_FLAG_INPUT_COMPLETE) != 0;
         const bool chain_calls = g_tuning.parse_chain_calls != 0;
-        if ((e = launch_decode_nms(head, g, P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, chain_calls,
-                                   PDL_TRIGGER | (!chain_calls ? 0 : (overlap_calls ? PDL_WAIT_END : PDL_WAIT_START)))) != cudaSuccess) return (int)e;
-        if ((e = launch_limb_argmax(head, amax, g, g_tuning, st, true, &chained)) != cudaSuccess) return (int)e;
-        if ((e = launch_tree_parse(head, g, ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr, keep_idx,
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if ((e = cudaStreamIsCapturing(st, &cap)) != cudaSuccess) return (int)e;
+        const bool capturing = cap != cudaStreamCaptureStatusNone;
+        Tuning tuning = g_tuning;
+        int k12_ctas = g_tuning.parse_persist, k4_ctas = g_tuning.parse_persist > 0 ? 1 : 0;
+        if (k12_ctas > 0) {
+            const size_t ring_cap = chain3_ring_cap(g, g_tuning.parse_stage_all, k12_ctas);
+            if (ring_cap) tuning.argmax_smem_cap = (int)ring_cap;
+            else k12_ctas = k4_ctas = 0;                    // no room beside a ring: the one-CTA-per-image kernels
+        }
+        const bool early = overlap_calls && chain_calls && !capturing && k4_ctas > 0;
+        // K12 may start beside the previous call's parse only if that one publishes (ours do); after anything else it
+        // starts fully ordered.  Without the flag it waits at its start, so the attribute only hides launch latency.
+        const bool attr12 = chain_calls && (!overlap_calls || capturing || chain_clean(st));
+        const int bits12 = PDL_TRIGGER | (!attr12 ? 0 : (overlap_calls ? PDL_WAIT_END : PDL_WAIT_START));
+        bool chained = false;
+        if ((e = launch_decode_nms(head, timeline_slot(g), P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, attr12,
+                                   bits12, k12_ctas)) != cudaSuccess) return (int)e;
+        if ((e = launch_limb_argmax(head, amax, timeline_slot(g), tuning, st, true, &chained)) != cudaSuccess) return (int)e;
+        if ((e = launch_tree_parse(head, timeline_slot(g), ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr, keep_idx,
                                    keep_count, out->count, out->root_cell, out->part_cell, out->part_score, out->part_box,
                                    out->R, st, chained, chained ? (PDL_WAIT_START | PDL_TRIGGER) : 0, g_tuning.parse_stage_all,
-                                   g_tuning.parse_threads)) != cudaSuccess) return (int)e;
-        return dense ? pack_after(out, shape, dense, st) : PPN_OK;
+                                   g_tuning.parse_threads, chained ? (early ? 2 : 1) : 0, k4_ctas)) != cudaSuccess) return (int)e;
+        if (!chained) chain_break(st);
+        if (!dense) return PPN_OK;
+        rc = pack_after(out, shape, dense, st);             // plain launches: the next call starts fully ordered behind them
+        chain_break(st);
+        return rc;
     }
+    ppn::chain_break(st);
     cudaStream_t side = st;
     SideLane* lane = nullptr;
     if (mode == 1) {
@@ -836,6 +873,13 @@ int ppn_debug_argmax_items(const PPNShape* shape, int32_t sms, int32_t* info, in
         return 0;
     }, &ctx);
     info[0] = p.G; info[1] = p.n_big; info[2] = p.small_m; info[3] = n_items;
+    return PPN_OK;
+}
+
+int ppn_timeline(void* dev_records, int32_t max_records) {
+    g_timeline.buf = static_cast<unsigned long long*>(dev_records);
+    g_timeline.cap = dev_records ? max_records : 0;
+    g_timeline.used = 0;
     return PPN_OK;
 }
 

@@ -28,7 +28,21 @@ struct Geom {               // per-launch constants derived from PPNShape
     size_t limb_off;        // 6*K*HW floats
     uint32_t magic_W, magic_K;   // ceil(2^32 / d) for exact x / d, 0 <= x < 65536 (0 when d == 1)
     int32_t dtype;               // HeadDtype of the head tensor (host side: picks the kernel instantiation)
+    // optional device timeline (benchmarks: ppn_timeline): record `tl_slot` = {first CTA start, last CTA end,
+    // first CTA past its dependency wait, -} in %globaltimer nanoseconds; nullptr = off
+    unsigned long long* tl;
+    int32_t tl_slot;
 };
+
+enum : int { TL_START = 0, TL_END = 1, TL_WAITED = 2 };
+__device__ __forceinline__ void tl_mark(const Geom& g, int what) {
+    if (g.tl && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        unsigned long long* rec = g.tl + 4 * (size_t)g.tl_slot;
+        if (what == TL_END) atomicMax(rec + 1, t); else atomicMin(rec + what, t);
+    }
+}
 
 // ---- head element types ------------------------------------------------------------------
 // The head tensor may be fp32 (the reference's), fp16 or bf16 (a head emitted in 16 bits halves the

@@ -56,6 +56,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
     const int n_cons = p.threads_padded;                 // consumer threads incl. idle lanes of the last warp
     const int n_mats = g.B * g.E;
 
+    tl_mark(g, TL_START);
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
@@ -171,6 +172,7 @@ limb_argmax_tma_kernel(const float* __restrict__ head, uint16_t* __restrict__ am
     }
     // In the PDL chain this kernel started without waiting for decode+NMS (it does not read their
     // output); it must not COMPLETE before they do, because the tree parse waits only for us.
+    tl_mark(g, TL_END);
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
 }
 
@@ -194,6 +196,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
     const int n_mats = g.B * g.E;
     const int n_items = item_count(p, n_mats);
 
+    tl_mark(g, TL_START);
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
@@ -301,6 +304,7 @@ limb_argmax_tma_multi_kernel(const float* __restrict__ head, uint16_t* __restric
             *reinterpret_cast<uint2*>(amax + (size_t)m * g.HW + 4 * cv) = make_uint2(lo, hi);
         }
     }
+    tl_mark(g, TL_END);
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();    // see limb_argmax_tma_kernel
 }
 
@@ -360,6 +364,7 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
     const int n_mats = g.B * g.E;
     const int n_items = item_count(p, n_mats);
 
+    tl_mark(g, TL_START);
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
@@ -480,6 +485,7 @@ limb_argmax_tma_multi16_kernel(const T16* __restrict__ head, uint16_t* __restric
             *reinterpret_cast<uint4*>(amax + (size_t)m * g.HW + 8 * cv) = make_uint4(idx[0], idx[1], idx[2], idx[3]);
         }
     }
+    tl_mark(g, TL_END);
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
 }
 
@@ -917,10 +923,14 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
     if (tid == 0) keep_count[prob] = m;
 }
 
-// K1 + K2 fused for the whole-path call: one CTA per (image, part) decodes the part's cells,
-// compacts the candidates into SHARED memory (never to HBM) and suppresses them right there; what
-// leaves the kernel is the list of surviving root CELLS in visiting order.  All six values of a
-// cell are loaded up front so the CTA pays one HBM round trip.
+// K1 + K2 fused for the whole-path call: a CTA decodes the cells of one (image, part), compacts the candidates
+// into SHARED memory (never to HBM) and suppresses them right there; what leaves the kernel is the list of surviving
+// root CELLS in visiting order.  All six values of a cell are loaded up front so the CTA pays one HBM round trip.
+// PERSISTENT: the grid is at most what is resident at once beside the arg-max ring, and every CTA strides over the
+// (image, part) lists.  A programmatic dependent is only launched once EVERY CTA of its primary has triggered —
+// with one CTA per list a big batch runs in several waves, and whatever follows in the stream (the arg-max kernel)
+// could not start before the last wave had; with a resident grid the trigger fires at once and this kernel's whole
+// run hides under the arg-max stream (cfg3, 1024 dense images: the step went from 359 us to the arg-max's own time).
 template <typename T>
 __global__ void __launch_bounds__(512, 3)
 decode_nms_kernel(const T* __restrict__ head, Geom g, int n_parts, float det_thr, float nms_thr,
@@ -929,59 +939,64 @@ decode_nms_kernel(const T* __restrict__ head, Geom g, int n_parts, float det_thr
     // pdl & 2: launched as a programmatic dependent itself (of the previous call's tree parse, or of
     // whatever kernel produced `head`): it may have become resident early, so it must wait before it
     // reads anything.  pdl & 1: then release the arg-max kernel, which needs nothing from this one.
+    tl_mark(g, TL_START);
     if (pdl & PDL_WAIT_START) pdl_wait();
+    tl_mark(g, TL_WAITED);
     if (pdl & PDL_TRIGGER) pdl_launch_dependents();
     __shared__ int warp_tot[16];
     __shared__ int base_s;
     float4* ubox = reinterpret_cast<float4*>(smem);                         // [HW] candidate boxes, cell order
     int32_t* ucell = reinterpret_cast<int32_t*>(ubox + g.HW);               // [HW]
     const NmsSmem s = nms_carve(reinterpret_cast<unsigned char*>(ucell + ((g.HW + 3) & ~3)), g.HW);
-    const int b = blockIdx.x, k = blockIdx.y;
-    const T* img = head + (size_t)b * g.img_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) base_s = 0;
-    for (int i = tid; i < g.HW; i += blockDim.x) s.rank[i] = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < g.HW; c0 += blockDim.x) {
-        const int c = c0 + tid;
-        float d = 0.0f;
-        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool hit = false;
-        if (c < g.HW) {
-            d = delta_at(img, g, k, c);
-            bx = box_at(img, g, k, c);                       // loads issued before d is tested
-            hit = d > det_thr;                               // strict, datatest.py:89
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
+    const int n_lists = g.B * n_parts;
+    for (int item = blockIdx.x; item < n_lists; item += gridDim.x) {
+        const int b = item / n_parts, k = item - b * n_parts;
+        const T* img = head + (size_t)b * g.img_stride;
+        if (tid == 0) base_s = 0;
+        for (int i = tid; i < g.HW; i += blockDim.x) s.rank[i] = 0;
         __syncthreads();
-        int off = base_s, total = 0;
-        for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) {
-            const int t = warp_tot[wi];
-            if (wi < warp) off += t;
-            total += t;
+        for (int c0 = 0; c0 < g.HW; c0 += blockDim.x) {
+            const int c = c0 + tid;
+            float d = 0.0f;
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool hit = false;
+            if (c < g.HW) {
+                d = delta_at(img, g, k, c);
+                bx = box_at(img, g, k, c);                       // loads issued before d is tested
+                hit = d > det_thr;                               // strict, datatest.py:89
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) warp_tot[warp] = __popc(bal);
+            __syncthreads();
+            int off = base_s, total = 0;
+            for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) {
+                const int t = warp_tot[wi];
+                if (wi < warp) off += t;
+                total += t;
+            }
+            if (hit) {
+                const int slot = off + __popc(bal & ((1u << lane) - 1u));
+                ucell[slot] = c;
+                ubox[slot] = bx;
+                s.key[slot] = score_key(d, slot);                // ties: larger candidate index (= larger cell) first
+            }
+            __syncthreads();
+            if (tid == 0) base_s += total;
+            __syncthreads();
         }
-        if (hit) {
-            const int slot = off + __popc(bal & ((1u << lane) - 1u));
-            ucell[slot] = c;
-            ubox[slot] = bx;
-            s.key[slot] = score_key(d, slot);                // ties: larger candidate index (= larger cell) first
-        }
-        __syncthreads();
-        if (tid == 0) base_s += total;
-        __syncthreads();
+        const int n = base_s;
+        const size_t list = (size_t)item * g.HW;
+        int m = 0;
+        if (n > 0) m = nms_core(s, ubox, n, nms_thr, 0, keep_cell + list, ucell);
+        if (tid == 0) keep_count[item] = m;
+        __syncthreads();                                         // the scratch is reused by this CTA's next list
     }
-    const int n = base_s;
-    const size_t list = ((size_t)b * n_parts + k) * g.HW;
-    int m = 0;
-    if (n > 0) m = nms_core(s, ubox, n, nms_thr, 0, keep_cell + list, ucell);
-    if (tid == 0) {
-        keep_count[(size_t)b * n_parts + k] = m;
-        // overlapped calls (PPN_FLAG_INPUT_COMPLETE): this kernel started without waiting for the
-        // previous call's tree parse; it must not COMPLETE before it, so that "the arg-max kernel
-        // completed" (which waits for us) still implies "everything of the previous call completed"
-        if (pdl & PDL_WAIT_END) pdl_wait();
-    }
+    // overlapped calls (PPN_FLAG_INPUT_COMPLETE): this kernel started without waiting for the
+    // previous call's tree parse; it must not COMPLETE before it, so that "the arg-max kernel
+    // completed" (which waits for us) still implies "everything of the previous call completed"
+    tl_mark(g, TL_END);
+    if (tid == 0 && (pdl & PDL_WAIT_END)) pdl_wait();
 }
 
 // Lists longer than PPN_MAX_CELLS: no bitmask; the CTA visits boxes in order and, for every box
@@ -1051,6 +1066,21 @@ nms_global_kernel(const float4* __restrict__ box, const float* __restrict__ scor
 // shared memory).  `use_tma` = 0 (byte ranges not 16-byte multiples): cooperative loads.
 constexpr int kMaxDyxTable = 2048;
 
+// launch-chain bits shared by the tree parse and the fused parse kernel (see parse_fused_kernel's header comment)
+enum : int {
+    FUSED_GUARD = 8,           // poll sync[0] >= seq before the early trigger
+    FUSED_TRIGGER_EARLY = 16,  // launch_dependents before the wait (after the guard)
+    FUSED_PUBLISH = 32,        // last CTA publishes seq + 1
+    FUSED_WAIT_TOP = 64,       // wait for the previous kernel before reading ANYTHING (the decode planes are its output)
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+
 __device__ __forceinline__ int fast_div(int x, uint32_t magic) {      // exact for 0 <= x < 65536
     return magic ? (int)__umulhi((unsigned)x, magic) : x;
 }
@@ -1096,7 +1126,8 @@ tree_parse_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float thr,
                   const uint16_t* __restrict__ amax, const int32_t* __restrict__ cand_cell,
                   const int32_t* __restrict__ keep_idx, const int32_t* __restrict__ keep_count,
                   int32_t* __restrict__ h_count, int32_t* __restrict__ h_root, int32_t* __restrict__ h_cell,
-                  float* __restrict__ h_score, float4* __restrict__ h_box, int R, int use_tma, int stage_all, int pdl) {
+                  float* __restrict__ h_score, float4* __restrict__ h_box, int R, int use_tma, int stage_all, int pdl,
+                  int* __restrict__ sync, int seq, int xywh_parts) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int KHW = g.K * g.HW;
     // staged channel groups: 0 = none (big grids: the walk reads resp/conf through L2 and the CTA
@@ -1108,154 +1139,230 @@ tree_parse_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float thr,
     int32_t* s_slot = s_root + g.HW;                                                   // [HW]
     int32_t* s_dyx = s_slot + g.HW;                                                    // [S] if small
     int16_t* s_pos = reinterpret_cast<int16_t*>(s_dyx + (g.S <= kMaxDyxTable ? g.S : 0));   // [HW][K]
+    // crowded images: the x / y / w / h planes of `xywh_parts` parts at a time, [4][xywh_parts][HW] (see the write-out)
+    HT* s_xywh = reinterpret_cast<HT*>(reinterpret_cast<unsigned char*>(s_pos) + ((((size_t)g.HW * g.K * 2) + 15) & ~(size_t)15));
     __shared__ __align__(8) uint64_t bar;
     __shared__ int warp_tot[32];
     __shared__ int base_s;
 
-    const int b = blockIdx.x;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const HT* img = head + (size_t)b * g.img_stride;
-    const HT* s_resp = kStaged ? s_planes : img;                   // shared when kStaged, else the head tensor
-    const HT* s_conf = s_resp + KHW;
-    const uint16_t* am = amax + (size_t)b * g.E * g.HW;
     const bool use_tab = g.S <= kMaxDyxTable;
     const uint32_t bytes_planes = (uint32_t)n_groups * KHW * (uint32_t)sizeof(HT), bytes_am = (uint32_t)g.E * g.HW * 2u;
 
-    // ---- prologue: nothing here depends on the kernels before this one -----------------------
-    if (use_tma) {
-        if (tid == 0) {
-            mbar_init(&bar, 1);
-            fence_mbar_init();
-            mbar_arrive_expect_tx(&bar, bytes_planes + bytes_am);
-            if (bytes_planes) bulk_g2s(s_planes, img, bytes_planes, &bar);
-        }
-    } else {
-        for (int i = tid; i < n_groups * KHW; i += T) s_planes[i] = __ldg(img + i);
+    // PERSISTENT: the grid is at most what is resident at once and every CTA strides over the images (see
+    // decode_nms_kernel).  Overlapped calls: like the fused parse kernel, trigger at the very top — once the previous
+    // call's tree parse has been SEEN complete (it read the workspace set the next call's kernels will write).
+    tl_mark(g, TL_START);
+    if (pdl & FUSED_GUARD) {
+        if (tid == 0) while (ld_acquire(sync) < seq) __nanosleep(200);
+        __syncthreads();
     }
-    if (tid == 0) base_s = 0;
+    if (pdl & FUSED_TRIGGER_EARLY) pdl_launch_dependents();
+    if (use_tma && tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
     if (use_tab)
         for (int a = tid; a < g.S; a += T) {
             const int dy = a / g.sW, dx = a - dy * g.sW;
             s_dyx[a] = ((dy - g.off_h) << 16) | ((dx - g.off_w) & 0xffff);
         }
-    // ---- from here on we read what the arg-max and decode+NMS kernels wrote ---------------------
-    if (pdl & PDL_WAIT_START) pdl_wait();
-    if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the NEXT call's decode+NMS may become resident
-    if (use_tma) {
-        if (tid == 0 && bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
-    } else {
-        for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
-    }
-    const int n_keep = min(keep_count[(size_t)b * n_parts], g.HW);
-    // What is not staged is gathered cell by cell in the write-out.  For a crowded image (roots on
-    // more than 3/8 of the cells) have the L2 stream the rest of the image's decode block in now,
-    // as one contiguous read, so that those gathers are L2 hits instead of scattered DRAM sectors
-    // (dense-crowd config: tree parse 111 -> 96 us); for sparse images it would only add traffic.
-    if (use_tma && tid == 0 && n_groups < 6 && n_keep * 8 >= g.HW * 3)
-        bulk_prefetch_l2(img + (size_t)n_groups * KHW, (uint32_t)(6 - n_groups) * KHW * (uint32_t)sizeof(HT));
-    const int32_t* keep = keep_idx + (size_t)b * n_parts * g.HW;
-    const int32_t* cells = cand_cell ? cand_cell + (size_t)b * n_parts * g.HW : nullptr;
-
-    // ---- 1. roots and cleared positions (the loads fly with the bulk copies) --------------------
-    for (int i = tid; i < n_keep * g.K; i += T) s_pos[i] = -1;
-    for (int r = tid; r < n_keep; r += T) s_root[r] = cells ? cells[keep[r]] : keep[r];
-    __syncthreads();                          // also: barrier init / cooperative loads visible
-    for (int r = tid; r < n_keep; r += T) s_pos[r * g.K] = (int16_t)s_root[r];
-    if (use_tma) mbar_wait(&bar, 0);          // on every path: never exit under an in-flight copy
-    if (n_keep == 0) { if (tid == 0) h_count[b] = 0; return; }
     __syncthreads();
+    uint32_t parity = 0;
+    bool first = true;
+    for (int b = blockIdx.x; b < g.B; b += gridDim.x, parity ^= 1u) {
+        const HT* img = head + (size_t)b * g.img_stride;
+        const HT* s_resp = kStaged ? s_planes : img;                   // shared when kStaged, else the head tensor
+        const HT* s_conf = s_resp + KHW;
+        const uint16_t* am = amax + (size_t)b * g.E * g.HW;
 
-    // ---- 2. walk: one thread per (chain, root) when the track orders are a tree -----------------
-    const int n_pad = (n_keep + 31) & ~31;    // whole warps share a chain: uniform chain-table reads
-    const int n_par = ch.parallel_ok ? ch.n_chains : 1;
-    for (int item = tid; item < n_par * n_pad; item += T) {
-        const int cidx = item / n_pad, r = item - cidx * n_pad;
-        if (r < n_keep) {
-            int16_t* my_pos = s_pos + r * g.K;
-            if (ch.parallel_ok) {
-                walk_chain<kStaged, HT>(ch, cidx, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
-            } else {
-                for (int c = 0; c < ch.n_chains; ++c)
-                    walk_chain<kStaged, HT>(ch, c, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+        // ---- prologue: nothing here depends on the kernels before this one -----------------------
+        if (use_tma) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar, bytes_planes + bytes_am);
+                if (bytes_planes) bulk_g2s(s_planes, img, bytes_planes, &bar);
+            }
+        } else {
+            for (int i = tid; i < n_groups * KHW; i += T) s_planes[i] = __ldg(img + i);
+        }
+        if (tid == 0) base_s = 0;
+        // ---- from here on we read what the arg-max and decode+NMS kernels wrote ---------------------
+        if (first) {
+            if (pdl & PDL_WAIT_START) pdl_wait();
+            tl_mark(g, TL_WAITED);
+            if (pdl & PDL_TRIGGER) pdl_launch_dependents();      // the NEXT call's decode+NMS may become resident
+            first = false;
+        }
+        if (use_tma) {
+            if (tid == 0 && bytes_am) bulk_g2s(s_amax, am, bytes_am, &bar);
+        } else {
+            for (int i = tid; i < g.E * g.HW; i += T) s_amax[i] = am[i];
+        }
+        const int n_keep = min(keep_count[(size_t)b * n_parts], g.HW);
+        // What is not staged is gathered cell by cell in the write-out.  For a crowded image (roots on
+        // more than 3/8 of the cells) have the L2 stream the rest of the image's decode block in now,
+        // as one contiguous read, so that those gathers are L2 hits instead of scattered DRAM sectors
+        // (dense-crowd config: tree parse 111 -> 96 us); for sparse images it would only add traffic.
+        const bool crowded = n_keep * 8 >= g.HW * 3;
+        if (use_tma && tid == 0 && n_groups < 6 && crowded)
+            bulk_prefetch_l2(img + (size_t)n_groups * KHW, (uint32_t)(6 - n_groups) * KHW * (uint32_t)sizeof(HT));
+        const int32_t* keep = keep_idx + (size_t)b * n_parts * g.HW;
+        const int32_t* cells = cand_cell ? cand_cell + (size_t)b * n_parts * g.HW : nullptr;
+
+        // ---- 1. roots and cleared positions (the loads fly with the bulk copies) --------------------
+        for (int i = tid; i < n_keep * g.K; i += T) s_pos[i] = -1;
+        for (int r = tid; r < n_keep; r += T) s_root[r] = cells ? cells[keep[r]] : keep[r];
+        __syncthreads();                          // also: cooperative loads visible
+        for (int r = tid; r < n_keep; r += T) s_pos[r * g.K] = (int16_t)s_root[r];
+        if (use_tma) mbar_wait(&bar, parity);     // on every path: never go on under an in-flight copy
+        if (n_keep == 0) {
+            if (tid == 0) h_count[b] = 0;
+            __syncthreads();
+            continue;
+        }
+        __syncthreads();
+
+        // ---- 2. walk: one thread per (chain, root) when the track orders are a tree -----------------
+        const int n_pad = (n_keep + 31) & ~31;    // whole warps share a chain: uniform chain-table reads
+        const int n_par = ch.parallel_ok ? ch.n_chains : 1;
+        for (int item = tid; item < n_par * n_pad; item += T) {
+            const int cidx = item / n_pad, r = item - cidx * n_pad;
+            if (r < n_keep) {
+                int16_t* my_pos = s_pos + r * g.K;
+                if (ch.parallel_ok) {
+                    walk_chain<kStaged, HT>(ch, cidx, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+                } else {
+                    for (int c = 0; c < ch.n_chains; ++c)
+                        walk_chain<kStaged, HT>(ch, c, s_root[r], g, thr, s_resp, s_conf, s_amax, s_dyx, use_tab, my_pos);
+                }
             }
         }
-    }
-    __syncthreads();
-
-    // ---- 3. humans with enough parts take consecutive output slots, in root order ---------------
-    for (int r0 = 0; r0 < n_keep; r0 += T) {
-        const int r = r0 + tid;
-        bool valid = false;
-        if (r < n_keep) {
-            int present = 0;
-            for (int t = 1; t < g.K; ++t) present += (s_pos[r * g.K + t] >= 0);
-            valid = min_kp <= present;                                          // datatest.py:129
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, valid);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
         __syncthreads();
-        int off = base_s, total = 0;
-        for (int wi = 0; wi < (T >> 5); ++wi) {
-            const int v = warp_tot[wi];
-            if (wi < warp) off += v;
-            total += v;
-        }
-        const int slot = off + __popc(bal & ((1u << lane) - 1u));
-        if (r < n_keep) s_slot[r] = (valid && slot < R) ? slot : -1;
-        __syncthreads();
-        if (tid == 0) base_s += total;
-    }
-    __syncthreads();
 
-    // ---- 4. write-out: one (human, part) pair per thread and step, four steps in flight ----------
-    const int n_pairs = n_keep * g.K;
-    for (int p0 = tid; p0 < n_pairs; p0 += 4 * T) {
-        int cc[4], tt[4], ss[4];
-        float xs[4], ys[4], ws[4], hs[4];
+        // ---- 3. humans with enough parts take consecutive output slots, in root order ---------------
+        for (int r0 = 0; r0 < n_keep; r0 += T) {
+            const int r = r0 + tid;
+            bool valid = false;
+            if (r < n_keep) {
+                int present = 0;
+                for (int t = 1; t < g.K; ++t) present += (s_pos[r * g.K + t] >= 0);
+                valid = min_kp <= present;                                          // datatest.py:129
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) warp_tot[warp] = __popc(bal);
+            __syncthreads();
+            int off = base_s, total = 0;
+            for (int wi = 0; wi < (T >> 5); ++wi) {
+                const int v = warp_tot[wi];
+                if (wi < warp) off += v;
+                total += v;
+            }
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            if (r < n_keep) s_slot[r] = (valid && slot < R) ? slot : -1;
+            __syncthreads();
+            if (tid == 0) base_s += total;
+        }
+        __syncthreads();
+
+        // ---- 4. write-out ------------------------------------------------------------------------------
+        // Crowded image (dense crowds: a human on nearly every cell): gathering x, y, w, h of every (human, part)
+        // pair cell by cell costs a 32-byte L2 sector per 4-byte value — 16 K sectors per image, and every one
+        // of them competes with the arg-max stream for L2 throughput (measured at cfg3: the arg-max kernel beside
+        // this one took 307 us instead of 222).  Instead the four planes of a few parts at a time are brought into
+        // shared memory with coalesced loads (exactly the bytes the head tensor holds, once) and read from there.
+        if (crowded && xywh_parts > 0 && n_groups < 6) {
+            const int P = xywh_parts, PHW = P * g.HW;
+            for (int t0 = 0; t0 < g.K; t0 += P) {
+                const int np = min(P, g.K - t0), n_el = np * g.HW;
+                for (int i = tid; i < 4 * n_el; i += T) {
+                    const int q = i / n_el, j = i - q * n_el;
+                    s_xywh[q * PHW + j] = __ldg(img + (size_t)(2 + q) * KHW + (size_t)t0 * g.HW + j);
+                }
+                __syncthreads();
+                for (int pi = tid; pi < n_keep * np; pi += T) {
+                    const int r = pi / np, tt = pi - r * np, t = t0 + tt;
+                    const int sl = s_slot[r];
+                    if (sl < 0) continue;
+                    const int c = s_pos[r * g.K + t];
+                    float score = 0.0f;
+                    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c >= 0) {
+                        const int at = t * g.HW + c, a2 = tt * g.HW + c;
+                        const int h = fast_div(c, g.magic_W), w = c - h * g.W;
+                        score = delta_lookup<kStaged, HT>(s_resp, s_conf, at);
+                        box = box_from(widen(s_xywh[a2]), widen(s_xywh[PHW + a2]), widen(s_xywh[2 * PHW + a2]),
+                                       widen(s_xywh[3 * PHW + a2]), h, w, g);
+                    }
+                    const size_t human = (size_t)b * R + sl, o = human * g.K + t;
+                    if (t == 0) h_root[human] = c;
+                    h_cell[o] = c;
+                    h_score[o] = score;
+                    h_box[o] = box;
+                }
+                __syncthreads();
+            }
+        }
+        // otherwise one (human, part) pair per thread and step, four steps in flight
+        const int n_pairs = (crowded && xywh_parts > 0 && n_groups < 6) ? 0 : n_keep * g.K;
+        for (int p0 = tid; p0 < n_pairs; p0 += 4 * T) {
+            int cc[4], tt[4], ss[4];
+            float xs[4], ys[4], ws[4], hs[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int pair = p0 + u * T;
-            cc[u] = -2;                                       // -2: nothing to write
-            if (pair < n_pairs) {
-                const int r = fast_div(pair, g.magic_K), t = pair - r * g.K;
-                const int sl = s_slot[r];
-                if (sl >= 0) {
-                    cc[u] = s_pos[pair];
-                    tt[u] = t;
-                    ss[u] = sl;
-                    if (cc[u] >= 0) {
-                        const int at = t * g.HW + cc[u];
-                        if (n_groups == 6) {
-                            xs[u] = widen(s_planes[2 * KHW + at]); ys[u] = widen(s_planes[3 * KHW + at]);
-                            ws[u] = widen(s_planes[4 * KHW + at]); hs[u] = widen(s_planes[5 * KHW + at]);
-                        } else {
-                            xs[u] = ldf(img + (size_t)2 * KHW + at); ys[u] = ldf(img + (size_t)3 * KHW + at);
-                            ws[u] = ldf(img + (size_t)4 * KHW + at); hs[u] = ldf(img + (size_t)5 * KHW + at);
+            for (int u = 0; u < 4; ++u) {
+                const int pair = p0 + u * T;
+                cc[u] = -2;                                       // -2: nothing to write
+                if (pair < n_pairs) {
+                    const int r = fast_div(pair, g.magic_K), t = pair - r * g.K;
+                    const int sl = s_slot[r];
+                    if (sl >= 0) {
+                        cc[u] = s_pos[pair];
+                        tt[u] = t;
+                        ss[u] = sl;
+                        if (cc[u] >= 0) {
+                            const int at = t * g.HW + cc[u];
+                            if (n_groups == 6) {
+                                xs[u] = widen(s_planes[2 * KHW + at]); ys[u] = widen(s_planes[3 * KHW + at]);
+                                ws[u] = widen(s_planes[4 * KHW + at]); hs[u] = widen(s_planes[5 * KHW + at]);
+                            } else {
+                                xs[u] = ldf(img + (size_t)2 * KHW + at); ys[u] = ldf(img + (size_t)3 * KHW + at);
+                                ws[u] = ldf(img + (size_t)4 * KHW + at); hs[u] = ldf(img + (size_t)5 * KHW + at);
+                            }
                         }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (cc[u] == -2) continue;
-            const int c = cc[u];
-            float score = 0.0f;
-            float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c >= 0) {
-                const int at = tt[u] * g.HW + c;
-                const int h = fast_div(c, g.magic_W), w = c - h * g.W;
-                score = delta_lookup<kStaged, HT>(s_resp, s_conf, at);
-                box = box_from(xs[u], ys[u], ws[u], hs[u], h, w, g);
+            for (int u = 0; u < 4; ++u) {
+                if (cc[u] == -2) continue;
+                const int c = cc[u];
+                float score = 0.0f;
+                float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c >= 0) {
+                    const int at = tt[u] * g.HW + c;
+                    const int h = fast_div(c, g.magic_W), w = c - h * g.W;
+                    score = delta_lookup<kStaged, HT>(s_resp, s_conf, at);
+                    box = box_from(xs[u], ys[u], ws[u], hs[u], h, w, g);
+                }
+                const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
+                if (tt[u] == 0) h_root[human] = c;
+                h_cell[o] = c;
+                h_score[o] = score;
+                h_box[o] = box;
             }
-            const size_t human = (size_t)b * R + ss[u], o = human * g.K + tt[u];
-            if (tt[u] == 0) h_root[human] = c;
-            h_cell[o] = c;
-            h_score[o] = score;
-            h_box[o] = box;
+        }
+        if (tid == 0) h_count[b] = base_s;
+        __syncthreads();                          // the shared arrays are reused by this CTA's next image
+    }
+    tl_mark(g, TL_END);
+    // ---- the last CTA publishes this call's sequence number (see parse_fused_kernel) ---------------------
+    if (pdl & FUSED_PUBLISH) {
+        __syncthreads();
+        if (tid == 0 && atomicAdd(sync + 1, 1) == (int)gridDim.x - 1) {
+            sync[1] = 0;
+            __threadfence();
+            atomicMax(sync, seq + 1);
         }
     }
-    if (tid == 0) h_count[b] = base_s;
 }
 
 // =========================================================================================
@@ -1284,13 +1391,6 @@ tree_parse_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float thr,
 // Sequence numbers are host state and would be frozen by stream capture; under capture (and without
 // the flag) the kernel triggers only AFTER its wait, which bounds the overlap to two calls without
 // any flag (K3(i+1) launched => K3(i) complete => K124(i-1) complete).
-enum : int {
-    FUSED_GUARD = 8,           // poll sync[0] >= seq before the early trigger
-    FUSED_TRIGGER_EARLY = 16,  // launch_dependents before the wait (after the guard)
-    FUSED_PUBLISH = 32,        // last CTA publishes seq + 1
-    FUSED_WAIT_TOP = 64,       // wait for the previous kernel before reading ANYTHING (the decode planes are its output)
-};
-
 struct FusedSmem { uint32_t delta, root, dyx, uni, amax, slot, estart, pmask, pos, total; };
 
 __host__ __device__ inline FusedSmem fused_layout(const Geom& g, bool staged) {
@@ -1310,12 +1410,6 @@ __host__ __device__ inline FusedSmem fused_layout(const Geom& g, bool staged) {
     const uint32_t walk = (l.pos - l.uni) + ((((uint32_t)g.HW * g.K * 2u) + 15u) & ~15u);
     l.total = l.uni + (nms > walk ? nms : walk);
     return l;
-}
-
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
 }
 
 // Optional second output of the fused kernel: the dense (human, part) entry buffer of the multi-GPU
@@ -1367,6 +1461,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
     const HT* img = head + (size_t)b * g.img_stride;
     const bool use_tab = g.S <= kMaxDyxTable;
 
+    tl_mark(g, TL_START);
     if (pdl & FUSED_WAIT_TOP) pdl_wait();       // fused network head: resp/conf/x/y/w/h are the previous kernel's output
     // ---- let the next call's arg-max be launched (see the header comment): it only queues behind
     //      this call's arg-max, so the earlier the better ---------------------------------------------
@@ -1441,6 +1536,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
 
     // ---- from here on we read what the arg-max kernel wrote -------------------------------------------
     if (pdl & PDL_WAIT_START) pdl_wait();
+    tl_mark(g, TL_WAITED);
     if (pdl & PDL_TRIGGER) pdl_launch_dependents();
     if (n_keep > 0) {
         const uint16_t* am = amax + (size_t)b * g.E * g.HW;    // L2 loads: the map was written while we were resident
@@ -1630,6 +1726,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
         }
     }
     if (tid == 0) h_count[b] = n_keep > 0 ? base_s : 0;
+    tl_mark(g, TL_END);
     // ---- the last CTA publishes this call's sequence number ------------------------------------------
     if (pdl & FUSED_PUBLISH) {
         __syncthreads();
@@ -2323,14 +2420,17 @@ size_t decode_nms_smem_bytes(const Geom& g) {
 }
 
 cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
-                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr, int pdl_bits) {
+                              int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr, int pdl_bits,
+                              int ctas_per_sm) {
     if (g.B == 0 || n_parts == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
     if (e != cudaSuccess) return e;
     const size_t smem = decode_nms_smem_bytes(g);
     if (smem > (size_t)d->smem_optin) return cudaErrorInvalidConfiguration;
-    dim3 grid(g.B, n_parts);
+    // persistent: at most ctas_per_sm CTAs per SM, each striding over the (image, part) lists (0: one CTA per list)
+    const long long lists = (long long)g.B * n_parts;
+    dim3 grid((unsigned)(ctas_per_sm > 0 ? std::min<long long>(lists, (long long)d->sms * ctas_per_sm) : lists));
     PPN_DISPATCH_HEAD(g.dtype, {
         if ((e = ensure_smem(decode_nms_kernel<T>, smem, &d->decode_nms[g.dtype])) != cudaSuccess) return e;
         return launch_kernel(decode_nms_kernel<T>, grid, dim3(g.HW <= 256 ? 256 : 512), smem, st, pdl_attr,
@@ -2341,33 +2441,64 @@ cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, floa
 
 static size_t head_elem_bytes(int dtype) { return dtype == HEAD_F32 ? 4 : 2; }
 
-size_t tree_parse_smem_bytes(const Geom& g, int n_groups) {
+// parts whose x / y / w / h planes the tree parse brings into shared memory at a time for crowded images: as many as
+// fit in 24 KB, and only where that means a handful of passes over the K parts (small grids — where crowds are dense)
+static int tree_parse_xywh_parts(const Geom& g, int n_groups) {
+    if (n_groups >= 6) return 0;
+    const size_t per_part = (size_t)4 * g.HW * head_elem_bytes(g.dtype);
+    int P = (int)((24 * 1024) / per_part);
+    if (P > g.K) P = g.K;
+    return (P >= 1 && (g.K + P - 1) / P <= 4) ? P : 0;
+}
+
+static size_t tree_parse_smem_base(const Geom& g, int n_groups) {
     return ((((size_t)n_groups * g.K * g.HW * head_elem_bytes(g.dtype)) + 15) & ~(size_t)15) +
            ((((size_t)g.E * g.HW + 7) & ~(size_t)7)) * sizeof(uint16_t) +
            (size_t)2 * g.HW * sizeof(int32_t) + (g.S <= kMaxDyxTable ? (size_t)g.S * sizeof(int32_t) : 0) +
-           (((size_t)g.HW * g.K + 7) & ~(size_t)7) * sizeof(int16_t);
+           ((((size_t)g.HW * g.K * sizeof(int16_t)) + 15) & ~(size_t)15);
+}
+
+size_t tree_parse_smem_bytes(const Geom& g, int n_groups) {
+    return tree_parse_smem_base(g, n_groups) + (size_t)tree_parse_xywh_parts(g, n_groups) * 4 * g.HW * head_elem_bytes(g.dtype);
+}
+
+// How much of the decode block the tree parse stages in shared memory (stage_all_pref: -1 auto, 0 none,
+// 1 resp+conf, 2 all six groups).  Auto: all six when that keeps the CTA under 32 KB (tiny
+// grids), resp+conf when under 64 KB (cfg2: 25 KB, cfg3: 57 KB), nothing otherwise — a light CTA lets every
+// image be resident at once, several of them UNDER the arg-max ring, and under the next call's
+// kernels (measured: at 24x24 the 107 KB staged CTA shut both overlaps out).
+static int tree_parse_groups(const Geom& g, int stage_all_pref, int smem_optin) {
+    int n_groups;
+    if (stage_all_pref < 0)
+        n_groups = tree_parse_smem_base(g, 6) <= 32 * 1024 ? 6 : (tree_parse_smem_base(g, 2) <= 64 * 1024 ? 2 : 0);
+    else
+        n_groups = stage_all_pref >= 2 ? 6 : (stage_all_pref == 1 ? 2 : 0);
+    while (n_groups > 0 && tree_parse_smem_bytes(g, n_groups) > (size_t)smem_optin) n_groups = n_groups == 6 ? 2 : 0;
+    return n_groups;
+}
+
+// Shared memory left for the arg-max ring on an SM when `k12_ctas` decode+NMS CTAs and one tree-parse CTA are to be
+// resident beside it (the persistent three-kernel chain); 0 when they would leave less than a two-stage ring.
+size_t chain3_ring_cap(const Geom& g, int stage_all_pref, int k12_ctas) {
+    DeviceInfo* d = nullptr;
+    if (device_info(&d) != cudaSuccess) return 0;
+    const size_t sm_bytes = (size_t)d->smem_optin + 1024;
+    const size_t others = (size_t)k12_ctas * (decode_nms_smem_bytes(g) + 1024) +
+                          tree_parse_smem_bytes(g, tree_parse_groups(g, stage_all_pref, d->smem_optin)) + 1024;
+    if (others + 1024 + 64 * 1024 > sm_bytes) return 0;
+    return sm_bytes - others - 1024;
 }
 
 cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable& ch, float thr, int min_kp, int n_parts,
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
                               float* h_score, float* h_box, int R, cudaStream_t st, bool pdl_attr, int pdl_bits,
-                              int stage_all_pref, int threads_pref) {
+                              int stage_all_pref, int threads_pref, int chain_mode, int ctas_per_sm) {
     if (g.B == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
     if (e != cudaSuccess) return e;
-    // How much of the decode block is staged in shared memory (stage_all_pref: -1 auto, 0 none,
-    // 1 resp+conf, 2 all six groups).  Auto: all six when that keeps the CTA under 32 KB (tiny
-    // grids), resp+conf when under 64 KB (cfg2: 25 KB, cfg3: 57 KB), nothing otherwise — a light CTA lets every
-    // image be resident at once, several of them UNDER the arg-max ring, and under the next call's
-    // kernels (measured: at 24x24 the 107 KB staged CTA shut both overlaps out).
-    int n_groups;
-    if (stage_all_pref < 0)
-        n_groups = tree_parse_smem_bytes(g, 6) <= 32 * 1024 ? 6 : (tree_parse_smem_bytes(g, 2) <= 64 * 1024 ? 2 : 0);
-    else
-        n_groups = stage_all_pref >= 2 ? 6 : (stage_all_pref == 1 ? 2 : 0);
-    while (n_groups > 0 && tree_parse_smem_bytes(g, n_groups) > (size_t)d->smem_optin) n_groups = n_groups == 6 ? 2 : 0;
+    const int n_groups = tree_parse_groups(g, stage_all_pref, d->smem_optin);
     const size_t smem = tree_parse_smem_bytes(g, n_groups);
     // one thread per (chain, root) in the walk and per (human, part) pair in the write-out
     int threads = threads_pref > 0 ? threads_pref : ((g.HW <= 144 || n_groups == 0) ? 256 : 512);
@@ -2379,19 +2510,42 @@ cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable&
     const bool tma_ok = ((size_t)g.K * g.HW * 2 * es) % 16 == 0 && (g.img_stride * es) % 16 == 0 &&
                         ((size_t)g.E * g.HW * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(head) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(amax) & 15) == 0;
+    // persistent: at most ctas_per_sm CTAs per SM, each striding over the images (0: one CTA per image)
+    const dim3 grid((unsigned)(ctas_per_sm > 0 ? std::min<long long>(g.B, (long long)d->sms * ctas_per_sm) : g.B));
+    // chain_mode 0: pdl_bits as given; 1: a publishing link of the call chain that triggers after its wait;
+    //            2: overlapped calls — guard on the previous call's publication, trigger at the very top
+    StreamSlot* slot = nullptr;
+    int* words = nullptr;
+    int bits = pdl_bits, seq = 0;
+    if (chain_mode > 0) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if ((e = cudaStreamIsCapturing(st, &cap)) != cudaSuccess) return e;
+        if (cap == cudaStreamCaptureStatusNone && (e = slot_for(d, st, &slot, &words)) != cudaSuccess) return e;
+        if (slot) { bits |= FUSED_PUBLISH; seq = slot->published; }
+        if (pdl_attr && chain_mode == 2 && slot) bits = (bits & ~PDL_TRIGGER) | FUSED_GUARD | FUSED_TRIGGER_EARLY;
+    }
+    int* sync = words ? words + 4 : nullptr;
     PPN_DISPATCH_HEAD(g.dtype, {
         if (n_groups) {
             if ((e = ensure_smem(tree_parse_kernel<true, T>, smem, &d->tree[g.dtype])) != cudaSuccess) return e;
-            return launch_kernel(tree_parse_kernel<true, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head),
-                                 g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root, h_cell,
-                                 h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, pdl_bits);
+            e = launch_kernel(tree_parse_kernel<true, T>, grid, dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head),
+                              g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root, h_cell,
+                              h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, bits, sync, seq,
+                              tree_parse_xywh_parts(g, n_groups));
+        } else {
+            if ((e = ensure_smem(tree_parse_kernel<false, T>, smem, &d->tree_light[g.dtype])) != cudaSuccess) return e;
+            e = launch_kernel(tree_parse_kernel<false, T>, grid, dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head),
+                              g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root, h_cell,
+                              h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, bits, sync, seq,
+                              tree_parse_xywh_parts(g, n_groups));
         }
-        if ((e = ensure_smem(tree_parse_kernel<false, T>, smem, &d->tree_light[g.dtype])) != cudaSuccess) return e;
-        return launch_kernel(tree_parse_kernel<false, T>, dim3(g.B), dim3(threads), smem, st, pdl_attr, static_cast<const T*>(head),
-                             g, ch, thr, min_kp, n_parts, amax, cand_cell, keep_idx, keep_count, h_count, h_root, h_cell,
-                             h_score, reinterpret_cast<float4*>(h_box), R, tma_ok ? 1 : 0, n_groups, pdl_bits);
     });
-    return cudaErrorInvalidValue;
+    if (e == cudaSuccess && slot) {
+        std::lock_guard<std::mutex> lock(g_ticket_mu);
+        slot->published = seq + 1;
+        slot->fast_open = true;
+    }
+    return e;
 }
 
 // ---- fused decode + NMS + tree parse --------------------------------------------------------------

@@ -29,6 +29,8 @@ struct Tuning {
     int parse_fused = -1;              // whole-path call: decode+NMS+tree parse in one kernel.  -1 auto (when all of its
                                        // CTAs fit on the SMs beside the arg-max ring), 0 never (three kernels), 1 whenever supported
     int parse_chain_calls = 1;         // PDL chain: the first kernel of a call is a programmatic dependent too
+    int parse_persist = 1;             // three-kernel chain: decode+NMS and the tree parse as persistent grids resident beside the
+                                       // arg-max ring (this many decode+NMS CTAs per SM, one tree-parse CTA); 0: one CTA per list / image
     int host_chunk_images = 64;
     int encode_sweep = 1;              // target encoder: limb tensors by the address-ordered persistent sweep (0: one CTA per image part)
     int encode_ctas_per_sm = 6;
@@ -74,7 +76,9 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
 // fused K1+K2 of the whole-path call: surviving root cells per (image, part), nothing else
 cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
                               int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr = false,
-                              int pdl_bits = 0);
+                              int pdl_bits = 0, int ctas_per_sm = 0 /* > 0: persistent grid */);
+// shared memory left for the arg-max ring beside k12_ctas decode+NMS CTAs and one tree-parse CTA per SM (0: no room)
+size_t chain3_ring_cap(const Geom& g, int stage_all_pref, int k12_ctas);
 
 cudaError_t launch_restore_xy(const float* x, const float* y, float* rx, float* ry, size_t n, int H, int W,
                               float gridW, float gridH, cudaStream_t st);
@@ -97,7 +101,8 @@ cudaError_t launch_tree_parse(const void* head, const Geom& g, const ChainTable&
                               const uint16_t* amax, const int32_t* cand_cell, const int32_t* keep_idx,
                               const int32_t* keep_count, int32_t* h_count, int32_t* h_root, int32_t* h_cell,
                               float* h_score, float* h_box, int R, cudaStream_t st, bool pdl_attr = false, int pdl_bits = 0,
-                              int stage_all_pref = -1, int threads_pref = 0);
+                              int stage_all_pref = -1, int threads_pref = 0, int chain_mode = 0 /* 1, 2: a publishing link of the
+                              call chain, see the launcher */, int ctas_per_sm = 0 /* > 0: persistent grid */);
 
 // fused decode + NMS + tree parse (n_nms_parts == 1, H*W <= 1024): the whole-path call's second kernel
 bool parse_fused_supported(const Geom& g, int stage_pref);

@@ -213,12 +213,13 @@ def test_batch_matches_c_oracle(preset, dist, B):
     from pytorch_pose_proposal_network_b200.config import PRESETS
     cfg = PRESETS[preset]()
     g = O.Geometry.of(cfg)
-    head = synth.make_head(g, dist, seed=100 + B, B=B)
+    from tests.gpu_inputs import device_head
+    dev, head = device_head(g, dist, seed=100 + B, B=B)       # generated on the device; the oracle gets the host copy
     assert synth.root_scores_distinct(head, g)
     ref = c_oracle.parse_batch(head, g, n_threads=8)
     from pytorch_pose_proposal_network_b200.parser import PoseParser
     parser = PoseParser(cfg)
-    packed = parser.parse(torch.from_numpy(head).cuda())
+    packed = parser.parse(dev)
     assert_packed_equals_oracle(packed.numpy(), ref, B)
     # the host-memory entry (chunked, overlapped copies) must give the same bytes
     host = parser.parse_host(torch.from_numpy(head).pin_memory())
@@ -238,8 +239,9 @@ def test_sixteen_bit_head(preset, dist, B, grid, dtype):
     if grid:
         cfg = cfg.with_(outsize=grid, insize=(grid[0] * 16, grid[1] * 16))
     g = O.Geometry.of(cfg)
-    head16 = torch.from_numpy(synth.make_head(g, dist, seed=77, B=B)).to(dtype)
-    up = head16.float().numpy()
+    from tests.gpu_inputs import device_head
+    dev16, up = device_head(g, dist, seed=77, B=B, dtype=dtype, distinct=False)           # rounded to 16 bits on the device; `up` = widened host copy
+    head16 = dev16.cpu()
     ref = c_oracle.parse_batch(up, g, n_threads=8)
     parser = PoseParser(cfg)
     dev = head16.cuda()
@@ -373,6 +375,36 @@ def test_overlapped_consecutive_calls(preset, dist, B, fused):
         last = parser.parse(devs[i % n_in], out=outs[0], input_complete=True)
     torch.cuda.synchronize()
     assert_packed_equals_oracle(last.numpy(), refs[5 % n_in], B)
+
+
+@pytest.mark.parametrize("persist", [0, 1, 2])
+@pytest.mark.parametrize("preset,dist,B", [("cfg2", "U", 400), ("cfg3", "D", 310)])
+def test_three_kernel_chain_persistent_grids(preset, dist, B, persist):
+    """The three-kernel chain with more images than resident CTAs: decode+NMS and the tree parse are persistent grids
+    whose CTAs stride over the images (parse.persist CTAs per SM; 0 = one CTA per image), overlapped calls guarded by
+    the published sequence number.  Every call's result must be exact."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[preset]()
+    g = O.Geometry.of(cfg)
+    heads = [synth.make_head(g, dist, seed=700 + i, B=B) for i in range(3)]
+    refs = [c_oracle.parse_batch(h, g, n_threads=8) for h in heads]
+    devs = [torch.from_numpy(h).cuda() for h in heads]
+    _lib.tune(parse_fused=0, parse_persist=persist)
+    try:
+        parser = PoseParser(cfg)
+        assert parser.parse_plan(B)["launches"] == 3
+        n_calls = 14
+        outs = [parser.alloc_output(B) for _ in range(n_calls)]
+        torch.cuda.synchronize()
+        for i in range(n_calls):
+            parser.parse(devs[i % 3], out=outs[i], input_complete=(i % 5 != 2))
+        torch.cuda.synchronize()
+        for i in range(n_calls):
+            assert_packed_equals_oracle(outs[i].numpy(), refs[i % 3], B)
+    finally:
+        _lib.tune(parse_fused=-1, parse_persist=1)
 
 
 def test_overlapped_chain_stress():
@@ -911,11 +943,9 @@ def test_full_size_properties(preset, B, dist):
     from pytorch_pose_proposal_network_b200.parser import PoseParser
     cfg = PRESETS[preset]()
     g = O.Geometry.of(cfg)
+    from tests.gpu_inputs import device_head, distinct_root_scores
     gen = torch.Generator(device="cuda").manual_seed(1234)
-    head = torch.rand(B, cfg.C, cfg.H, cfg.W, device="cuda", generator=gen)
-    if dist == "D":
-        head[:, :2 * cfg.K] = 0.4 + 0.6 * head[:, :2 * cfg.K]
-        head[:, 4 * cfg.K:6 * cfg.K] *= 0.08
+    head, host_all = device_head(g, dist, seed=1234, B=B)      # equal root scores, if any, already moved apart
     parser = PoseParser(cfg)
     first = {k: v.copy() for k, v in parser.parse(head).numpy().items()}
     # determinism / idempotence: same input, same bytes (compare only the valid slots)
@@ -942,11 +972,11 @@ def test_full_size_properties(preset, B, dist):
         assert (np.diff(sc[:, 0]) <= 0).all()                 # descending root score
     # a sample of images against the C restatement, bit for bit
     pick = np.linspace(0, B - 1, 12).astype(int)
-    sub = head[torch.from_numpy(pick).cuda()].cpu().numpy()
-    if synth.root_scores_distinct(sub, g):
-        ref = c_oracle.parse_batch(sub, g, n_threads=8)
-        sample = {k: v[pick] for k, v in first.items()}
-        assert_packed_equals_oracle(sample, ref, len(pick))
+    sub = np.ascontiguousarray(host_all[pick])
+    assert distinct_root_scores(sub, g) == 0 and synth.root_scores_distinct(sub, g)
+    ref = c_oracle.parse_batch(sub, g, n_threads=8)
+    sample = {k: v[pick] for k, v in first.items()}
+    assert_packed_equals_oracle(sample, ref, len(pick))
 
 
 # ------------------------------------------------------------------------------------------
