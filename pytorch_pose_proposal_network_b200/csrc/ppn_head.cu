@@ -127,6 +127,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     uint64_t* tfull = empty + kStages;       // [2] accumulator ready for the epilogue
     uint64_t* tempty = tfull + 2;            // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes + 256);   // [2][kBlockN]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -212,6 +213,8 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     } else {
         // ------------------------------ epilogue ------------------------------
         const int ew = warp & 3;                     // the TMEM lane quadrant this warp may read
+        const int et = tid - 64;                     // 0..127 among the epilogue threads
+        const bool emit = a.emit_logits != nullptr || a.emit_head != nullptr;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -219,9 +222,25 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
             const int b = g / a.groups_per_img;
             const int cell = (g - b * a.groups_per_img) * 32 + lane;
             const bool valid = g < a.n_groups && cell < a.HW;
-            float m = 0.0f, bs = 0.0f;               // running maximum logit and the best sigmoid value
+            // running state of the current limb window: m = largest logit so far (+inf once a NaN has been taken:
+            // nothing may follow the first NaN), bs = the sigmoid value the arg-max stands on, idx = its position
+            float m = 0.0f, bs = 0.0f;
             int idx = 0, aw = 0, ei = 0;             // aw: position inside the current limb window (uniform)
+            // a logit that beats the running maximum: decide on the SIGMOID values (numpy sees those)
+            auto challenger = [&](float x, int at_pos) {
+                const float sx = sigmoid_f32(x);
+                if (!(sx <= bs) && bs == bs) { idx = at_pos; bs = sx; }
+                m = (x != x) ? INFINITY : x;
+            };
             for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                // the tile's bias values, once per channel tile (double-buffered on the accumulator parity: whoever
+                // overwrites a buffer has passed the next tile's barrier, i.e. everybody is done reading it)
+                float* sb = s_bias + acc * kBlockN;
+                for (int i = et; i < kBlockN; i += 128) {
+                    const int c = nt * kBlockN + i;
+                    sb[i] = (a.bias && c < a.C) ? __ldg(a.bias + c) : -0.0f;       // x + (-0) == x, bit for bit
+                }
+                named_bar_sync(1, 128);
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 for (int ch = 0; ch < kBlockN / 32; ++ch) {
@@ -229,12 +248,23 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     if (c0 >= a.C) break;                                 // uniform
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN + ch * 32), r);
+                    const float* sbc = sb + ch * 32;
+                    // fast path: 32 limb channels strictly inside one window (no window starts or ends here) —
+                    // an add, a compare and a rarely taken branch per column
+                    if (!emit && c0 >= a.n_dec && c0 + 32 <= a.C && aw != 0 && a.S - aw > 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __fadd_rn(__uint_as_float(r[j]), sbc[j]);
+                            if (!(x <= m)) challenger(x, aw + j);
+                        }
+                        aw += 32;
+                        continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int c = c0 + j;
                         if (c >= a.C) break;                              // uniform
-                        float x = __uint_as_float(r[j]);
-                        if (a.bias) x = __fadd_rn(x, __ldg(a.bias + c));
+                        const float x = __fadd_rn(__uint_as_float(r[j]), sbc[j]);
                         const size_t at = ((size_t)b * a.C + c) * a.HW + cell;
                         if (a.emit_logits && valid) a.emit_logits[at] = x;
                         if (c < a.n_dec) {
@@ -243,11 +273,9 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                             if (a.emit_head && valid) a.emit_head[at] = s;
                         } else {
                             if (aw == 0) {
-                                m = x; bs = sigmoid_f32(x); idx = 0;
-                            } else if (!(x <= m) && m == m) {             // a larger logit (or the first NaN)
-                                const float sx = sigmoid_f32(x);
-                                if (!(sx <= bs) && bs == bs) { idx = aw; bs = sx; }
-                                m = x;
+                                m = (x != x) ? INFINITY : x; bs = sigmoid_f32(x); idx = 0;
+                            } else if (!(x <= m)) {
+                                challenger(x, aw);
                             }
                             if (a.emit_head && valid) a.emit_head[at] = sigmoid_f32(x);
                             if (++aw == a.S) {
@@ -298,7 +326,7 @@ cudaError_t encoder(EncodeTiledFn* out) {
 }
 }  // namespace
 
-size_t head_smem_bytes() { return (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers, TMEM slot */; }
+size_t head_smem_bytes() { return (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers, TMEM slot */ + 2 * kBlockN * sizeof(float) /* bias */; }
 
 cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int Cin, const Geom& g,
                                     float* dec, uint16_t* amax, float* emit_logits, float* emit_head, cudaStream_t st,

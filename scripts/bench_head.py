@@ -1,0 +1,71 @@
+"""The fused network head (ppn_head_parse: tcgen05 1x1-conv GEMM + sigmoid + arg-max epilogue, then the fused parse)
+next to what it replaces: cuDNN's 1x1 convolution in TF32 + sigmoid (writing the fp32 head tensor) + ppn_parse reading it.
+
+    python scripts/bench_head.py [--configs cfg2,native] [--iters 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pytorch_pose_proposal_network_b200.config import PRESETS  # noqa: E402
+from pytorch_pose_proposal_network_b200.parser import PoseParser  # noqa: E402
+
+BATCH = {"cfg2": 512, "cfg3": 1024, "cfg4": 256, "native": 64}
+ap = argparse.ArgumentParser()
+ap.add_argument("--configs", default="cfg2,native")
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--cin", type=int, default=512)
+args = ap.parse_args()
+peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+bf16 = json.load(open(peaks))["bf16_tflops"] if os.path.exists(peaks) else 1590.0
+tf32_peak = bf16 / 2                                     # TF32 runs at half the bf16 rate
+torch.backends.cudnn.allow_tf32 = True                   # PyTorch's default: the reference's conv3 runs in TF32
+
+
+def timed(fn, iters):
+    for i in range(3):
+        fn(i)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+for name in args.configs.split(","):
+    cfg = PRESETS[name]()
+    B, Cin = BATCH[name], args.cin
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    feats = [torch.randn(B, Cin, cfg.H, cfg.W, device="cuda", generator=gen) for _ in range(3)]
+    weight = (torch.randn(cfg.C, Cin, device="cuda", generator=gen) * (2.0 / (1.01 * Cin)) ** 0.5).contiguous()
+    bias = torch.randn(cfg.C, device="cuda", generator=gen) * 0.5
+    bias[:2 * cfg.K] += 1.0
+    w4 = weight[:, :, None, None].contiguous()
+    parser = PoseParser(cfg)
+    outs = [parser.alloc_output(B) for _ in range(2)]
+    flops = 2.0 * B * cfg.HW * cfg.C * Cin
+
+    def fused(i):
+        parser.parse_features(feats[i % 3], weight, bias, out=outs[i % 2])
+
+    def unfused(i):
+        head = torch.sigmoid(torch.nn.functional.conv2d(feats[i % 3], w4, bias))
+        parser.parse(head, out=outs[i % 2])
+
+    def conv_only(i):
+        torch.nn.functional.conv2d(feats[i % 3], w4, bias)
+
+    t_f, t_u, t_c = timed(fused, args.iters), timed(unfused, args.iters), timed(conv_only, args.iters)
+    print(f"{name}: B={B} Cin={Cin} C={cfg.C} grid {cfg.H}x{cfg.W}: {flops / 1e9:.1f} GFLOP per batch")
+    print(f"   fused head+parse   {t_f * 1e3:8.1f} us  {B / t_f / 1e3:8.1f} k img/s  {flops / t_f / 1e9:7.1f} TFLOP/s = {flops / t_f / 1e9 / tf32_peak:.3f} of the TF32 peak "
+          f"({tf32_peak:.0f} TF/s = measured bf16 {bf16:.0f} / 2)")
+    print(f"   cuDNN conv (TF32) + sigmoid + ppn_parse   {t_u * 1e3:8.1f} us  {B / t_u / 1e3:8.1f} k img/s   (conv alone {t_c * 1e3:.1f} us = {flops / t_c / 1e9:.1f} TFLOP/s)")
+    del feats, outs, parser
+    torch.cuda.empty_cache()
