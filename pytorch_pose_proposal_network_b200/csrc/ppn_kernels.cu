@@ -849,16 +849,25 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
             unsigned cur = s.rem[w];
             const int nb = min(32, n - i0);
             const unsigned valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-            const unsigned diag = (lane < nb) ? s.diag[i0 + lane] : 0u;
+            // The 32-step dependency of the block runs in ONE lane on words it has loaded itself: ~5 dependent ALU
+            // operations per step.  (First version: every step fetched its word from the owning lane with a shuffle —
+            // the shuffle's latency, ~25 cycles, sat on the critical path 32 times per block.)
             unsigned kept = 0;
+            if (lane == 0) {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const unsigned d = __shfl_sync(0xffffffffu, diag, t);
-                const unsigned take = (~cur >> t) & 1u;
-                kept |= take << t;
-                cur |= d & (0u - take);
+                for (int t0 = 0; t0 < 32; t0 += 8) {                  // eight words at a time: registers are scarce here
+                    unsigned d[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) d[t] = (t0 + t < nb) ? s.diag[i0 + t0 + t] : 0u;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const unsigned take = (~cur >> (t0 + t)) & 1u;
+                        kept |= take << (t0 + t);
+                        cur |= d[t] & (0u - take);
+                    }
+                }
             }
-            kept &= valid;
+            kept = __shfl_sync(0xffffffffu, kept, 0) & valid;
             bool done = false;
             if (limit > 0 && m + __popc(kept) >= limit) {      // datatest.py:154-155
                 int need = limit - m;
