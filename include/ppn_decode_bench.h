@@ -41,7 +41,7 @@ int ppn_debug_argmax_items(const PPNShape* shape, int32_t sms, int32_t* info /*[
  * for 16-bit heads), "argmax.cluster" (tiny batches: -1 auto, 0 never, 2/4/8 = CTAs per matrix), "argmax.smem_cap" (stand-alone arg-max: bytes of shared
  * memory the ring may use, 0 = all),
  * "parse.fused" (-1 auto, 0 three-kernel chain, 1 two-kernel chain whenever supported, cutting large batches),
- * "parse.chain_calls", "parse.persist" (three-kernel chain: decode+NMS CTAs per SM of the persistent grids, 0 = one CTA per image), "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
+ * "parse.chain_calls", "parse.persist" (three-kernel chain: decode+NMS CTAs per SM of the persistent grids, 0 = one CTA per image), "parse.k12_threads" (decode+NMS CTA size of the three-kernel chain, 0 = auto), "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
  * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images",
  * "encode.sweep" (1 = address-ordered persistent sweep), "encode.ctas_per_sm".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);

@@ -241,6 +241,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "parse.stage_all")) t.parse_stage_all = value;
     else if (!std::strcmp(key, "parse.chain_calls")) t.parse_chain_calls = value != 0;
     else if (!std::strcmp(key, "parse.persist")) t.parse_persist = value < 0 ? 0 : (value > 4 ? 4 : value);
+    else if (!std::strcmp(key, "parse.k12_threads")) t.parse_k12_threads = value < 0 ? 0 : value;
     else if (!std::strcmp(key, "parse.fused")) t.parse_fused = value < 0 ? -1 : (value != 0);
     else if (!std::strcmp(key, "parse.threads")) t.parse_threads = value;
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
@@ -269,6 +270,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "parse.stage_all")) *value = t.parse_stage_all;
     else if (!std::strcmp(key, "parse.chain_calls")) *value = t.parse_chain_calls;
     else if (!std::strcmp(key, "parse.persist")) *value = t.parse_persist;
+    else if (!std::strcmp(key, "parse.k12_threads")) *value = t.parse_k12_threads;
     else if (!std::strcmp(key, "parse.fused")) *value = t.parse_fused;
     else if (!std::strcmp(key, "parse.threads")) *value = t.parse_threads;
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
@@ -653,7 +655,7 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
         const int bits12 = PDL_TRIGGER | (!attr12 ? 0 : (overlap_calls ? PDL_WAIT_END : PDL_WAIT_START));
         bool chained = false;
         if ((e = launch_decode_nms(head, timeline_slot(g), P, params->det_thresh, params->nms_thresh, keep_idx, keep_count, st, attr12,
-                                   bits12, k12_ctas)) != cudaSuccess) return (int)e;
+                                   bits12, k12_ctas, g_tuning.parse_k12_threads)) != cudaSuccess) return (int)e;
         if ((e = launch_limb_argmax(head, amax, timeline_slot(g), tuning, st, true, &chained)) != cudaSuccess) return (int)e;
         if ((e = launch_tree_parse(head, timeline_slot(g), ch, params->det_thresh, params->min_num_keypoints, P, amax, nullptr, keep_idx,
                                    keep_count, out->count, out->root_cell, out->part_cell, out->part_score, out->part_box,

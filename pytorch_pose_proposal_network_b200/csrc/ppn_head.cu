@@ -19,10 +19,11 @@
 // arg-max kernel, no cross-lane reduction.  The accumulator is double-buffered (2 x 256 TMEM columns):
 // the epilogue of channel tile n runs under the MMAs of tile n + 1.
 //
-// Warp roles (192 threads, one CTA per SM, persistent over M tiles):
+// Warp roles (192 or 448 threads, one CTA per SM, persistent over M tiles):
 //   warp 0      TMA producer (one lane)
 //   warp 1      TMEM allocation, MMA issue (one lane), TMEM release
-//   warps 2-5   epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias, sigmoid / running arg-max, stores
+//   warps 2-5 (or 2-13: three per TMEM lane quadrant, for short limb windows)
+//               epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias, sigmoid / running arg-max, stores
 //
 // M tiles are built from "cell groups" of 32 cells of one image (a 128-byte swizzle row): a tile is 4
 // consecutive groups of the flattened (image, group) list, each fetched by its own TMA box from the
@@ -31,9 +32,9 @@
 //
 // Exactness.  The parser's contract is "bit-exact on sigmoid(logits)".  sigmoid is monotone but not
 // injective in fp32 (neighbouring logits often share a sigmoid value), so an arg-max over logits can
-// differ from numpy's first-maximum over the sigmoid values.  The running rule therefore compares
-// sigmoid values — but evaluates the sigmoid only when a logit exceeds the running maximum logit
-// (a handful of times per window): cand = x > m;  take = sigmoid(x) > sigmoid(best).
+// differ from numpy's first-maximum over the sigmoid values.  The running rule therefore decides on
+// sigmoid values — but only a logit that exceeds the running maximum logit can change the answer, and
+// of those only near-ties and the saturated tails need the two sigmoids evaluated (see the epilogue).
 #include <cuda.h>          // CUtensorMap and enums only: the encoder is fetched with cudaGetDriverEntryPoint
 #include <mutex>
 
@@ -53,7 +54,7 @@ constexpr int kABytes = 4 * kGroupBytes;     // 16 KB
 constexpr int kBBytes = kBlockN * 128;       // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 512;               // two 256-column accumulators
-constexpr int kHeadThreads = 192;
+constexpr int kMaxEpiSubs = 3;               // epilogue warps per TMEM lane quadrant (template parameter of the kernel)
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
@@ -90,27 +91,39 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t leading_by
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((leading_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((stride_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
-// 32 lanes x 32 consecutive columns of TMEM -> 32 registers per thread (thread = lane)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        "tcgen05.wait::ld.sync.aligned;"            // the registers are defined only after the wait: keep both in one statement
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
-          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
-          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
+// 32 lanes x 8 consecutive columns of TMEM -> 8 registers per thread (thread = lane).  The load is asynchronous: the
+// registers are defined only after tcgen05.wait::ld, which therefore takes them as read-write operands — the compiler
+// then cannot move a use above the wait.  Issue the next group's load, process the current group, wait: the TMEM
+// latency hides under the compares.  (Eight columns at a time in a ROLLED loop on purpose: the first version unrolled
+// 32 columns with the sigmoid paths inlined — 7 752 SASS instructions, 26 % of all stall samples "no instruction":
+// the four epilogue warps thrashed the instruction cache.)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
 }
 
 // torch.sigmoid's fp32 expression, 1 / (1 + exp(-x)): libdevice expf, one add, one IEEE division
 __device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// Does a logit x that exceeds every logit so far beat the standing arg-max, whose logit is bx <= x?  numpy sees sigmoid
+// values: only if sigmoid(x) > sigmoid(bx) (a tie keeps the earlier index), and never once a NaN stands.  Out of line:
+// it runs a few times per limb window and must not be replicated into every column of the epilogue.
+__device__ __noinline__ bool beats_in_sigmoid(float x, float bx) {
+    const float sx = sigmoid_f32(x), sb = sigmoid_f32(bx);
+    return !(sx <= sb) && sb == sb;
+}
 
 }  // namespace
 
 struct HeadArgs {
     int32_t B, HW, Cin, C, n_dec, S, E;
     int32_t groups_per_img, n_groups, n_tiles, n_ntiles, n_kblocks;
+    uint32_t magic_S;           // ceil(2^32 / S): exact p / S for p < 2^22 (S <= 65535 and S * E channels)
     const float* bias;          // [C] or nullptr
     float* dec;                 // [B, n_dec, HW]   sigmoid of the 6K decode channels
     uint16_t* amax;             // [B, E, HW]
@@ -118,7 +131,8 @@ struct HeadArgs {
     float* emit_head;           // optional [B, C, HW]: the reference's head tensor, sigmoid(logits)
 };
 
-__global__ void __launch_bounds__(kHeadThreads, 1)
+template <int kSubs>
+__global__ void __launch_bounds__(64 + 128 * kSubs, 1)
 head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, HeadArgs a, int pdl) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -135,7 +149,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         prefetch_tensormap(&tm_x);
         prefetch_tensormap(&tm_w);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4); }
+        for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4 * kSubs); }
         fence_mbar_init();
     }
     if (warp == 1) {                         // the allocating warp also frees
@@ -212,8 +226,17 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         }
     } else {
         // ------------------------------ epilogue ------------------------------
+        // kEpiSubs warps share each TMEM lane quadrant (32 cells): the decode channels go to sub-warp 0 and limb window
+        // ei to sub-warp ei % kEpiSubs, which loads only the 8-column groups that touch its windows.  A window's running
+        // arg-max thus lives in ONE thread from its first to its last channel, across channel tiles, and the epilogue
+        // of a tile takes 1/kEpiSubs of the time (with one warp per quadrant it was 3.5x the MMA time of a tile).
         const int ew = warp & 3;                     // the TMEM lane quadrant this warp may read
-        const int et = tid - 64;                     // 0..127 among the epilogue threads
+        const int sub = (warp - 2) >> 2;             // which of the quadrant's warps
+        const int et = tid - 64;                     // 0 .. among the epilogue threads
+        constexpr int n_sub = kSubs, n_et = 128 * kSubs;   // windows longer than a channel tile keep ONE sub-warp busy at a time
+                                                     // whatever their number (measured at S = 441: 1 206 us with one, 1 381 us
+                                                     // with three), short windows (S = 81) spread over all three (610 -> 544 us):
+                                                     // the launcher picks the instantiation by window size
         const bool emit = a.emit_logits != nullptr || a.emit_head != nullptr;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -222,69 +245,112 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
             const int b = g / a.groups_per_img;
             const int cell = (g - b * a.groups_per_img) * 32 + lane;
             const bool valid = g < a.n_groups && cell < a.HW;
-            // running state of the current limb window: m = largest logit so far (+inf once a NaN has been taken:
-            // nothing may follow the first NaN), bs = the sigmoid value the arg-max stands on, idx = its position
-            float m = 0.0f, bs = 0.0f;
-            int idx = 0, aw = 0, ei = 0;             // aw: position inside the current limb window (uniform)
-            // a logit that beats the running maximum: decide on the SIGMOID values (numpy sees those)
-            auto challenger = [&](float x, int at_pos) {
-                const float sx = sigmoid_f32(x);
-                if (!(sx <= bs) && bs == bs) { idx = at_pos; bs = sx; }
-                m = (x != x) ? INFINITY : x;
+            // Running state of the limb window this thread is in: m = largest logit so far (+inf once a NaN has been
+            // taken: nothing may follow the first NaN), idx = the arg-max so far and bx = the logit it stands on (bx <= m:
+            // a larger logit whose sigmoid TIES with the standing one does not move the arg-max).  A window starts from
+            // (-inf, -inf, 0): sigmoid(-inf) = 0 stands until something beats it — the first column is no special case.
+            float m = -INFINITY, bx = -INFINITY;
+            int idx = 0;
+            // One limb column at window position aw.  A logit above the running maximum beats the standing arg-max iff
+            // sigmoid(x) > sigmoid(bx) (numpy sees sigmoid values).  For x - m > 0.01 and |x| <= 8 it certainly does:
+            // sigmoid' >= 3.3e-4 on [-8.01, 8], so the sigmoids are >= 3.3e-6 apart — tens of ulps, far beyond either one's
+            // evaluation error — and m >= bx: that case is three selects, no branch.  Only the rest (near-ties, the
+            // saturated tails, NaN, +-inf) branches out to evaluate the two sigmoids.
+            auto limb_column = [&](float x, int aw) {
+                const bool gt = !(x <= m);
+                const bool fast = gt && __fsub_rn(x, m) > 0.01f && fabsf(x) <= 8.0f;
+                idx = fast ? aw : idx;
+                bx = fast ? x : bx;
+                if (gt && !fast) {
+                    if (beats_in_sigmoid(x, bx)) { idx = aw; bx = x; }
+                    m = (x != x) ? INFINITY : x;
+                }
+                m = fast ? x : m;
+            };
+            auto window_end = [&](int ei) {
+                if (valid) a.amax[((size_t)b * a.E + ei) * a.HW + cell] = (uint16_t)idx;
+                idx = 0; m = -INFINITY; bx = -INFINITY;
+            };
+            // limb window and position of channel c >= n_dec (uniform; exact magic division, c - n_dec < 2^22)
+            auto window_of = [&](int c, int& ei, int& aw) {
+                const int p = c - a.n_dec;
+                ei = (int)(((unsigned long long)(unsigned)p * a.magic_S) >> 32);
+                aw = p - ei * a.S;
+            };
+            // does the 8-column group at channel c0 hold a column of this sub-warp?
+            auto mine = [&](int c0) -> bool {
+                const int c1 = min(c0 + 7, a.C - 1);
+                if (c0 < a.n_dec && sub == 0) return true;
+                if (c1 < a.n_dec) return false;
+                int e0, e1, aw;
+                window_of(max(c0, a.n_dec), e0, aw);
+                window_of(c1, e1, aw);
+                return e0 % n_sub == sub || e1 % n_sub == sub || e1 - e0 >= n_sub;
+            };
+            // eight columns starting at channel c0, biases at sbc
+            auto group = [&](const uint32_t* r, int c0, const float* sbc) {
+                if (!emit && c0 >= a.n_dec && c0 + 8 <= a.C) {
+                    int ei, aw;
+                    window_of(c0, ei, aw);
+                    if (aw + 8 <= a.S) {                                  // all eight in window ei — this sub-warp's, or mine() lied
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) limb_column(__fadd_rn(__uint_as_float(r[j]), sbc[j]), aw + j);
+                        if (aw + 8 == a.S) window_end(ei);
+                        return;
+                    }
+                }
+                // decode channels, a window boundary, the ragged last group, or a run that also emits logits / the head
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j;
+                    if (c >= a.C) break;                                  // uniform
+                    int ei = 0, aw = 0;
+                    const bool limb = c >= a.n_dec;
+                    if (limb) window_of(c, ei, aw);
+                    if ((limb ? ei % n_sub : 0) != sub) continue;         // uniform: another sub-warp's column
+                    const float x = __fadd_rn(__uint_as_float(r[j]), sbc[j]);
+                    const size_t at = ((size_t)b * a.C + c) * a.HW + cell;
+                    if (a.emit_logits && valid) a.emit_logits[at] = x;
+                    if (!limb || a.emit_head) {
+                        const float sg = sigmoid_f32(x);
+                        if (!limb && valid) a.dec[((size_t)b * a.n_dec + c) * a.HW + cell] = sg;
+                        if (a.emit_head && valid) a.emit_head[at] = sg;
+                    }
+                    if (limb) {
+                        limb_column(x, aw);
+                        if (aw + 1 == a.S) window_end(ei);
+                    }
+                }
             };
             for (int nt = 0; nt < a.n_ntiles; ++nt) {
                 // the tile's bias values, once per channel tile (double-buffered on the accumulator parity: whoever
                 // overwrites a buffer has passed the next tile's barrier, i.e. everybody is done reading it)
                 float* sb = s_bias + acc * kBlockN;
-                for (int i = et; i < kBlockN; i += 128) {
+                for (int i = et; i < kBlockN; i += n_et) {
                     const int c = nt * kBlockN + i;
                     sb[i] = (a.bias && c < a.C) ? __ldg(a.bias + c) : -0.0f;       // x + (-0) == x, bit for bit
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, n_et);
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
-                for (int ch = 0; ch < kBlockN / 32; ++ch) {
-                    const int c0 = nt * kBlockN + ch * 32;
-                    if (c0 >= a.C) break;                                 // uniform
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN + ch * 32), r);
-                    const float* sbc = sb + ch * 32;
-                    // fast path: 32 limb channels strictly inside one window (no window starts or ends here) —
-                    // an add, a compare and a rarely taken branch per column
-                    if (!emit && c0 >= a.n_dec && c0 + 32 <= a.C && aw != 0 && a.S - aw > 32) {
+                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN);
+                const int c_tile = nt * kBlockN;
+                const int n_cols = min(kBlockN, a.C - c_tile);            // > 0
+                // this sub-warp's groups, the next one's TMEM load in flight while the current one is processed
+                uint32_t cur[8], nxt[8];
+                int c8 = 0;
+                while (c8 < n_cols && !mine(c_tile + c8)) c8 += 8;
+                if (c8 < n_cols) tmem_ld8_issue(t_row + (uint32_t)c8, nxt);
+#pragma unroll 1
+                while (c8 < n_cols) {
+                    tmem_ld8_wait(nxt);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float x = __fadd_rn(__uint_as_float(r[j]), sbc[j]);
-                            if (!(x <= m)) challenger(x, aw + j);
-                        }
-                        aw += 32;
-                        continue;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = c0 + j;
-                        if (c >= a.C) break;                              // uniform
-                        const float x = __fadd_rn(__uint_as_float(r[j]), sbc[j]);
-                        const size_t at = ((size_t)b * a.C + c) * a.HW + cell;
-                        if (a.emit_logits && valid) a.emit_logits[at] = x;
-                        if (c < a.n_dec) {
-                            const float s = sigmoid_f32(x);
-                            if (valid) a.dec[((size_t)b * a.n_dec + c) * a.HW + cell] = s;
-                            if (a.emit_head && valid) a.emit_head[at] = s;
-                        } else {
-                            if (aw == 0) {
-                                m = (x != x) ? INFINITY : x; bs = sigmoid_f32(x); idx = 0;
-                            } else if (!(x <= m)) {
-                                challenger(x, aw);
-                            }
-                            if (a.emit_head && valid) a.emit_head[at] = sigmoid_f32(x);
-                            if (++aw == a.S) {
-                                if (valid) a.amax[((size_t)b * a.E + ei) * a.HW + cell] = (uint16_t)idx;
-                                aw = 0;
-                                ++ei;
-                            }
-                        }
-                    }
+                    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+                    int n8 = c8 + 8;
+                    while (n8 < n_cols && !mine(c_tile + n8)) n8 += 8;
+                    if (n8 < n_cols) tmem_ld8_issue(t_row + (uint32_t)n8, nxt);
+                    group(cur, c_tile + c8, sb + c8);
+                    c8 = n8;
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -366,19 +432,22 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
     a.n_tiles = (a.n_groups + 3) / 4;
     a.n_ntiles = (g.C + kBlockN - 1) / kBlockN;
     a.n_kblocks = Cin / kBlockK;
+    a.magic_S = g.S <= 1 ? 0u : (uint32_t)(((1ull << 32) + g.S - 1) / g.S);
     a.bias = bias; a.dec = dec; a.amax = amax; a.emit_logits = emit_logits; a.emit_head = emit_head;
 
     const size_t smem = head_smem_bytes();
+    const bool three = g.S <= 128;                    // short limb windows: three epilogue warps per lane quadrant
     {
         std::lock_guard<std::mutex> lock(g_enc_mu);
         if (dev >= 0 && dev < 64 && !g_attr_done[dev]) {
-            if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<kMaxEpiSubs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
             g_attr_done[dev] = true;
         }
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)std::min(sms, a.n_tiles));
-    cfg.blockDim = dim3(kHeadThreads);
+    cfg.blockDim = dim3(64 + 128 * (three ? kMaxEpiSubs : 1));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -386,7 +455,8 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_attr ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel, tm_x, tm_w, a, pdl_bits);
+    return three ? cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel<kMaxEpiSubs>, tm_x, tm_w, a, pdl_bits)
+                 : cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel<1>, tm_x, tm_w, a, pdl_bits);
 }
 
 }  // namespace ppn

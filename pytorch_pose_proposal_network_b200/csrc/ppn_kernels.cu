@@ -849,25 +849,18 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
             unsigned cur = s.rem[w];
             const int nb = min(32, n - i0);
             const unsigned valid = nb == 32 ? 0xffffffffu : ((1u << nb) - 1u);
-            // The 32-step dependency of the block runs in ONE lane on words it has loaded itself: ~5 dependent ALU
-            // operations per step.  (First version: every step fetched its word from the owning lane with a shuffle —
-            // the shuffle's latency, ~25 cycles, sat on the critical path 32 times per block.)
+            // (tried: the 32-step chain in ONE lane on words it loads itself instead of a shuffle per step — slower,
+            //  decode+NMS 90.8 -> 103.4 us at the dense-crowd shape: the kernel has 40 registers and the words spill)
+            const unsigned diag = (lane < nb) ? s.diag[i0 + lane] : 0u;
             unsigned kept = 0;
-            if (lane == 0) {
 #pragma unroll
-                for (int t0 = 0; t0 < 32; t0 += 8) {                  // eight words at a time: registers are scarce here
-                    unsigned d[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) d[t] = (t0 + t < nb) ? s.diag[i0 + t0 + t] : 0u;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const unsigned take = (~cur >> (t0 + t)) & 1u;
-                        kept |= take << (t0 + t);
-                        cur |= d[t] & (0u - take);
-                    }
-                }
+            for (int t = 0; t < 32; ++t) {
+                const unsigned d = __shfl_sync(0xffffffffu, diag, t);
+                const unsigned take = (~cur >> t) & 1u;
+                kept |= take << t;
+                cur |= d & (0u - take);
             }
-            kept = __shfl_sync(0xffffffffu, kept, 0) & valid;
+            kept &= valid;
             bool done = false;
             if (limit > 0 && m + __popc(kept) >= limit) {      // datatest.py:154-155
                 int need = limit - m;
@@ -2440,7 +2433,7 @@ size_t decode_nms_smem_bytes(const Geom& g) {
 
 cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
                               int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr, int pdl_bits,
-                              int ctas_per_sm) {
+                              int ctas_per_sm, int threads_pref) {
     if (g.B == 0 || n_parts == 0) return cudaSuccess;
     DeviceInfo* d = nullptr;
     cudaError_t e = device_info(&d);
@@ -2452,7 +2445,8 @@ cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, floa
     dim3 grid((unsigned)(ctas_per_sm > 0 ? std::min<long long>(lists, (long long)d->sms * ctas_per_sm) : lists));
     PPN_DISPATCH_HEAD(g.dtype, {
         if ((e = ensure_smem(decode_nms_kernel<T>, smem, &d->decode_nms[g.dtype])) != cudaSuccess) return e;
-        return launch_kernel(decode_nms_kernel<T>, grid, dim3(g.HW <= 256 ? 256 : 512), smem, st, pdl_attr,
+        const int threads = threads_pref > 0 ? std::min(512, std::max(64, (threads_pref + 31) & ~31)) : (g.HW <= 256 ? 256 : 512);
+        return launch_kernel(decode_nms_kernel<T>, grid, dim3(threads), smem, st, pdl_attr,
                              static_cast<const T*>(head), g, n_parts, det_thr, nms_thr, keep_cell, keep_count, pdl_bits);
     });
     return cudaErrorInvalidValue;

@@ -29,6 +29,7 @@ struct Tuning {
     int parse_fused = -1;              // whole-path call: decode+NMS+tree parse in one kernel.  -1 auto (when all of its
                                        // CTAs fit on the SMs beside the arg-max ring), 0 never (three kernels), 1 whenever supported
     int parse_chain_calls = 1;         // PDL chain: the first kernel of a call is a programmatic dependent too
+    int parse_k12_threads = 0;         // decode+NMS CTA size in the whole-path call, 0 = by grid size (256 up to 256 cells, else 512)
     int parse_persist = 1;             // three-kernel chain: decode+NMS and the tree parse as persistent grids resident beside the
                                        // arg-max ring (this many decode+NMS CTAs per SM, one tree-parse CTA); 0: one CTA per list / image
     int host_chunk_images = 64;
@@ -76,7 +77,7 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
 // fused K1+K2 of the whole-path call: surviving root cells per (image, part), nothing else
 cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, float det_thr, float nms_thr,
                               int32_t* keep_cell, int32_t* keep_count, cudaStream_t st, bool pdl_attr = false,
-                              int pdl_bits = 0, int ctas_per_sm = 0 /* > 0: persistent grid */);
+                              int pdl_bits = 0, int ctas_per_sm = 0 /* > 0: persistent grid */, int threads_pref = 0);
 // shared memory left for the arg-max ring beside k12_ctas decode+NMS CTAs and one tree-parse CTA per SM (0: no room)
 size_t chain3_ring_cap(const Geom& g, int stage_all_pref, int k12_ctas);
 

@@ -729,6 +729,40 @@ def test_tie_rule_is_larger_cell_first():
     assert list(ref["root_cell"][0, :4]) == [41, 40, 17, 5]
 
 
+def test_threshold_rounding_rule():
+    """the limb-step test `delta < detection_thresh` (datatest.py:121) is an fp32 comparison with
+    float32(thr) — NumPy >= 2 semantics, which the fixtures were generated under.  At thr = 0.7 (float32(0.7) < 0.7) a
+    delta exactly equal to float32(0.7) is therefore ACCEPTED (NumPy 1.x would compare in float64 and break the chain);
+    the root test `delta > thr` rejects the same value in both."""
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS["cfg2"]().with_(detection_thresh=0.7)
+    g = O.Geometry.of(cfg)
+    thr32 = np.float32(0.7)
+    assert float(thr32) < 0.7
+    head = synth.make_head(g, "U", seed=4, B=1)
+    K = g.K
+    head[0, :K] *= np.float32(0.5)                                 # nothing above the threshold by accident
+    root, tgt = 5 * g.W + 5, 5 * g.W + 6
+    head[0, 0].reshape(-1)[root] = 1.0
+    head[0, K].reshape(-1)[root] = 0.9                              # a root: delta 0.9 > thr
+    limb0, part0 = g.graphs[0][0][0], g.graphs[0][1][0]            # first step of the first track order
+    e = head[0, 6 * K:].reshape(g.E, g.S, g.H * g.W)
+    e[limb0, :, root] = 0.0
+    e[limb0, (g.sH // 2) * g.sW + g.sW // 2 + 1, root] = 1.0        # points one cell to the right
+    head[0, part0].reshape(-1)[tgt] = 1.0
+    head[0, K + part0].reshape(-1)[tgt] = thr32                      # delta == float32(thr) exactly
+    ref = c_oracle.parse_batch(head, g)
+    got = PoseParser(cfg).parse(torch.from_numpy(head).cuda()).numpy()
+    assert_packed_equals_oracle(got, ref, 1)
+    assert int(got["count"][0]) == 1 and got["part_cell"][0, 0, part0] == tgt          # accepted: not < float32(thr)
+    assert bits(got["part_score"][0, 0, part0]) == bits(thr32)
+    # the same value as a ROOT score is rejected by `>`
+    head[0, K].reshape(-1)[root] = thr32
+    got = PoseParser(cfg).parse(torch.from_numpy(head).cuda()).numpy()
+    assert int(got["count"][0]) == 0
+
+
 def test_capacity_limit_keeps_top_scores():
     from pytorch_pose_proposal_network_b200.parser import PoseParser
     from pytorch_pose_proposal_network_b200.config import PPNConfig
