@@ -69,9 +69,9 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? PPN_OK : (int)e; }
 // ---- optional device timeline of ppn_parse's kernels (ppn_timeline, include/ppn_decode_bench.h) ------------
 // Every kernel of a call gets one 4 x uint64 record {first CTA start, last CTA end, first CTA past its dependency
 // wait, kind} in %globaltimer nanoseconds, written with atomicMin / atomicMax.  One benchmark thread.
-struct Timeline { unsigned long long* buf = nullptr; int cap = 0, used = 0; } g_timeline;
+struct Timeline { unsigned long long* buf = nullptr; int cap = 0, used = 0, phase = 0; } g_timeline;
 inline ppn::Geom timeline_slot(ppn::Geom g) {
-    if (g_timeline.buf && g_timeline.used < g_timeline.cap) { g.tl = g_timeline.buf; g.tl_slot = g_timeline.used++; }
+    if (g_timeline.buf && g_timeline.used < g_timeline.cap) { g.tl = g_timeline.buf; g.tl_slot = g_timeline.used++; g.tl_phase = g_timeline.phase; }
     else g.tl = nullptr;
     return g;
 }
@@ -98,6 +98,7 @@ ppn::Geom make_geom(const PPNShape* s) {
     g.limb_off = (size_t)6 * g.K * g.HW;
     g.tl = nullptr;
     g.tl_slot = 0;
+    g.tl_phase = 0;
     auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + d - 1) / d); };
     g.magic_W = magic(g.W);
     g.magic_K = magic(g.K);
@@ -247,6 +248,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else if (!std::strcmp(key, "encode.sweep")) t.encode_sweep = value != 0;
     else if (!std::strcmp(key, "encode.ctas_per_sm")) t.encode_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
+    else if (!std::strcmp(key, "timeline.phase")) g_timeline.phase = value;      // which in-kernel phase boundary ppn_timeline records
     else return PPN_E_BADARG;
     return PPN_OK;
 }

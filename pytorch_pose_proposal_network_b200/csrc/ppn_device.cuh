@@ -29,9 +29,11 @@ struct Geom {               // per-launch constants derived from PPNShape
     uint32_t magic_W, magic_K;   // ceil(2^32 / d) for exact x / d, 0 <= x < 65536 (0 when d == 1)
     int32_t dtype;               // HeadDtype of the head tensor (host side: picks the kernel instantiation)
     // optional device timeline (benchmarks: ppn_timeline): record `tl_slot` = {first CTA start, last CTA end,
-    // first CTA past its dependency wait, -} in %globaltimer nanoseconds; nullptr = off
+    // first CTA past its dependency wait, first CTA past phase `tl_phase` of the kernel} in %globaltimer nanoseconds;
+    // nullptr = off
     unsigned long long* tl;
     int32_t tl_slot;
+    int32_t tl_phase;
 };
 
 enum : int { TL_START = 0, TL_END = 1, TL_WAITED = 2 };
@@ -41,6 +43,15 @@ __device__ __forceinline__ void tl_mark(const Geom& g, int what) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         unsigned long long* rec = g.tl + 4 * (size_t)g.tl_slot;
         if (what == TL_END) atomicMax(rec + 1, t); else atomicMin(rec + what, t);
+    }
+}
+
+// phase boundaries inside a kernel, one per run (tune key "timeline.phase"): where a single image's latency goes
+__device__ __forceinline__ void tl_phase(const Geom& g, int phase) {
+    if (g.tl && threadIdx.x == 0 && g.tl_phase == phase) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(g.tl + 4 * (size_t)g.tl_slot + 3, t);
     }
 }
 

@@ -588,7 +588,9 @@ limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ am
     const int tid = threadIdx.x;
     const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
     const int m = blockIdx.x / C;
+    tl_mark(g, TL_START);
     if (pdl & PDL_WAIT_START) pdl_wait();
+    tl_mark(g, TL_WAITED);
     if (zero2 && blockIdx.x == 0 && tid == 0) { zero2[0] = 0; zero2[1] = 0; }
     if (pdl & PDL_TRIGGER) pdl_launch_dependents();
     const int b = m / g.E, ei = m - b * g.E;
@@ -646,6 +648,7 @@ limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ am
         }
     }
     cluster_sync_all();                                                   // peers' shared memory stays alive until CTA 0 has read it
+    tl_mark(g, TL_END);
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
 }
 
@@ -757,24 +760,28 @@ struct NmsSmem {
     int32_t* rank;                // [stride] rank accumulators of the split counting sort
     unsigned* diag;               // [stride] bit t of diag[i]: box i suppresses box 32*(i/32) + t (t > i % 32)
     unsigned* rem;                // [32] removed set, one word per block of 32 boxes
-    int32_t* ctl;                 // [36] {kept mask of the current block, survivors so far, done, -, kept list[32]}
+    int32_t* ctl;                 // [4] {kept mask of the current block, survivors so far, done, -}
+    float4* kbox;                 // [32] the current block's survivors, compacted: boxes
+    float* karea;                 // [32]   and areas
 };
 
 __host__ __device__ inline size_t nms_bytes_per_list(int stride) {
     return (size_t)stride * (sizeof(float4) + sizeof(unsigned long long) + sizeof(float) + 2 * sizeof(int32_t) + sizeof(unsigned)) +
-           (32 + 36) * sizeof(int32_t);
+           32 * (sizeof(float4) + sizeof(float)) + (32 + 4) * sizeof(int32_t);
 }
 
 __device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int stride) {
     NmsSmem s;
     s.sbox = reinterpret_cast<float4*>(base);
-    s.key = reinterpret_cast<unsigned long long*>(s.sbox + stride);
+    s.kbox = s.sbox + stride;
+    s.key = reinterpret_cast<unsigned long long*>(s.kbox + 32);
     s.sarea = reinterpret_cast<float*>(s.key + stride);
     s.sidx = reinterpret_cast<int32_t*>(s.sarea + stride);
     s.rank = s.sidx + stride;
     s.diag = reinterpret_cast<unsigned*>(s.rank + stride);
     s.rem = s.diag + stride;
     s.ctl = reinterpret_cast<int32_t*>(s.rem + 32);
+    s.karea = reinterpret_cast<float*>(s.ctl + 4);
     return s;
 }
 
@@ -793,12 +800,14 @@ __device__ __forceinline__ bool suppresses_finite(const float4 tested, float are
     return iou >= thr;
 }
 
+constexpr int kNmsWalkMax = 12;   // resolve a block survivor by survivor when at most this many of its boxes are still alive
+
 // Whole CTA.  Precondition: s.key[0..n) holds the keys of the n unsorted boxes `ubox` (global or
 // shared), s.rank[0..n) is zero, and a __syncthreads() has made both visible.  Writes
 // out[pos] = map ? map[idx] : idx for the kept boxes in visiting order and returns their number (in
 // every thread).  n <= 1024.
 __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, int n, float thr, int limit,
-                                        int32_t* __restrict__ out, const int32_t* map) {
+                                        int32_t* __restrict__ out, const int32_t* map, const Geom* tg = nullptr) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = T >> 5;
     const int Wd = (n + 31) >> 5;
     // ---- 1. rank: every box's rank = number of larger keys, the key range split over T/n threads per box
@@ -814,6 +823,7 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         if (split == 1) s.rank[i] = r; else atomicAdd(&s.rank[i], r);
     }
     __syncthreads();
+    if (tg) tl_phase(*tg, 11);
     bool has_nan = false;
     for (int i = tid; i < n; i += T) {
         const float4 bx = ubox[i];
@@ -826,6 +836,13 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
     if (tid < 32) s.rem[tid] = 0u;
     const bool any_nan = __syncthreads_or(has_nan);
     const bool thr_pos = thr > 0.0f;
+    if (tg) tl_phase(*tg, 12);
+    // (tried, round 2: the FULL n x n suppression bit matrix built by all warps first, then either every box deciding
+    //  for itself from its column, round after round, or one warp walking the survivors with ballot / find-first-set and
+    //  OR-ing their rows into the removed set.  Exact both ways (tests/test_oracle_properties.py keeps the model of the
+    //  second), and slower both ways: all n^2/2 pair tests instead of survivors x rest, ~2 barrier rounds resp. ~210
+    //  dependent cycles per SURVIVOR.  One image at the reference's native shape, 351 candidates -> 58 survivors:
+    //  28 us block by block, 35 us with the matrix; 1024 dense images (256 -> 225): 91 -> 105 us.)
     // ---- 2. diagonal blocks: one warp per box i, lanes = the boxes of i's own block of 32 -----------------
     for (int i = warp; i < n; i += n_warps) {
         const float4 bi = s.sbox[i];
@@ -841,6 +858,7 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         if (lane == 0) s.diag[i] = word;
     }
     __syncthreads();
+    if (tg) tl_phase(*tg, 13);
     // ---- 3. block by block: warp 0 resolves the block, everybody tests its survivors against the rest ------
     int m = 0;
     for (int w = 0; w < Wd; ++w) {
@@ -853,14 +871,25 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
             //  decode+NMS 90.8 -> 103.4 us at the dense-crowd shape: the kernel has 40 registers and the words spill)
             const unsigned diag = (lane < nb) ? s.diag[i0 + lane] : 0u;
             unsigned kept = 0;
+            unsigned open = ~cur & valid;                          // boxes of the block the earlier blocks left alive
+            if (__popc(open) <= kNmsWalkMax) {
+                // few of them (every block but the first ones when boxes overlap a lot): hop from survivor to survivor
+                // with find-first-set, one dependent shuffle per SURVIVOR instead of one per box
+                while (open) {
+                    const int t = __ffs((int)open) - 1;
+                    kept |= 1u << t;
+                    open &= ~(__shfl_sync(0xffffffffu, diag, t) | (1u << t));
+                }
+            } else {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const unsigned d = __shfl_sync(0xffffffffu, diag, t);
-                const unsigned take = (~cur >> t) & 1u;
-                kept |= take << t;
-                cur |= d & (0u - take);
+                for (int t = 0; t < 32; ++t) {
+                    const unsigned d = __shfl_sync(0xffffffffu, diag, t);
+                    const unsigned take = (~cur >> t) & 1u;
+                    kept |= take << t;
+                    cur |= d & (0u - take);
+                }
+                kept &= valid;
             }
-            kept &= valid;
             bool done = false;
             if (limit > 0 && m + __popc(kept) >= limit) {      // datatest.py:154-155
                 int need = limit - m;
@@ -873,7 +902,8 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
                 const int idx = s.sidx[i0 + lane];
                 const int pos = __popc(kept & ((1u << lane) - 1u));
                 out[m + pos] = map ? map[idx] : idx;
-                s.ctl[4 + pos] = lane;                            // the block's survivors, in order
+                s.kbox[pos] = s.sbox[i0 + lane];                  // the block's survivors, compacted for the phase below
+                s.karea[pos] = s.sarea[i0 + lane];
             }
             if (lane == 0) { s.ctl[0] = (int)kept; s.ctl[1] = m + __popc(kept); s.ctl[2] = done || w == Wd - 1; }
         }
@@ -882,22 +912,41 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         m = s.ctl[1];
         if (s.ctl[2]) break;                                      // uniform: limit reached or last block
         const int n_kept = __popc(kept);
-        // Every LANE holds one of the block's survivors in registers; the warps stride over the later boxes, one box
-        // per step, read by all lanes from the same shared-memory address (a broadcast): 32 pair tests per step in
-        // straight-line code — no per-lane bounds or `removed` checks, no divergence to reconverge (the first
-        // version paired a survivor with 32 later boxes per step: same number of steps, ~50 instructions each
-        // against ~18 here; ncu at the dense-crowd shape: 62 M warp instructions per launch, 45 M of them there).
+        // A warp takes a whole WORD of later boxes, one box per lane, and runs over the block's survivors (compacted by
+        // warp 0 above: broadcast reads of consecutive addresses, nothing in the loop depends on the previous turn but
+        // the OR); one ballot and one plain store per word — a word has one writer per phase, so no atomics.
+        // (Until round 2 it was the other way round — lanes held the survivors, the warps strode over the later boxes,
+        // one vote and one shared-memory atomicOr per suppressed box: 32 x words turns instead of survivors x words, and
+        // with a handful of survivors removing nearly everything behind them, 16 warps' atomics queueing on one or two
+        // words.  1024 dense images, decode+NMS alone: 90.8 -> 77.4 us, the whole step 304 -> 270 us; one image of 351 candidates at the
+        // native shape: 32.9 -> 31.6 us, where 16 warps' dependent instruction chains and 22 barriers are what is left.)
         if (n_kept == 0) { __syncthreads(); continue; }
-        const bool mine = lane < n_kept;
-        const int ik = i0 + s.ctl[4 + (mine ? lane : 0)];
-        const float4 bi = s.sbox[ik];
-        const float ai = s.sarea[ik];
-        for (int j = i0 + 32 + warp; j < n; j += n_warps) {
-            if ((s.rem[j >> 5] >> (j & 31)) & 1u) continue;        // uniform: already removed (a stale read only costs work)
-            const float4 bj = s.sbox[j];
-            const float aj = s.sarea[j];
-            const bool bit = mine && (any_nan ? suppresses(bj, aj, bi, ai, thr, thr_pos) : suppresses_finite(bj, aj, bi, ai, thr, thr_pos));
-            if (__any_sync(0xffffffffu, bit) && lane == 0) atomicOr(&s.rem[j >> 5], 1u << (j & 31));
+        // When fewer words are left than there are warps, the survivors are split as well: G warps per word, each with
+        // its share of them, OR-ed together with at most G atomics per word.
+        const int n_words = Wd - w - 1;
+        int G = n_words > 0 ? n_warps / n_words : 1;
+        G = G < 1 ? 1 : (G > n_kept ? n_kept : G);
+        const int chunk = (n_kept + G - 1) / G;
+        for (int item = warp; item < n_words * G; item += n_warps) {
+            const int grp = item / n_words, w2 = w + 1 + (item - grp * n_words);
+            const int q0 = grp * chunk, q1 = min(n_kept, q0 + chunk);
+            const int j = (w2 << 5) + lane;
+            const unsigned remw = s.rem[w2];
+            bool bit = false;
+            if (j < n && !((remw >> lane) & 1u)) {
+                const float4 bj = s.sbox[j];
+                const float aj = s.sarea[j];
+                if (any_nan) {
+                    for (int q = q0; q < q1; ++q) bit |= suppresses(bj, aj, s.kbox[q], s.karea[q], thr, thr_pos);
+                } else {
+#pragma unroll 4
+                    for (int q = q0; q < q1; ++q) bit |= suppresses_finite(bj, aj, s.kbox[q], s.karea[q], thr, thr_pos);
+                }
+            }
+            const unsigned word = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0 && word) {
+                if (G == 1) s.rem[w2] = remw | word; else atomicOr(&s.rem[w2], word);
+            }
         }
         __syncthreads();
     }
@@ -1488,6 +1537,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
         (reinterpret_cast<uintptr_t>(head) & 15) == 0)
         bulk_prefetch_l2(head + (size_t)blockIdx.x * g.img_stride, (uint32_t)2 * g.K * g.HW * (uint32_t)sizeof(HT));
 
+    tl_phase(g, 1);
     // ---- prologue 1: root candidates of part 0, compacted into shared memory (datatest.py:80-92) ----
     if (tid == 0) { base_s = 0; n_keep_s = 0; }
     for (int i = tid; i < g.HW; i += T) s.rank[i] = 0;
@@ -1526,17 +1576,20 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
         if (tid == 0) base_s += total;
         __syncthreads();
     }
+    tl_phase(g, 2);
     // ---- prologue 2: delta of every (part, cell), one coalesced pass (rt_test.py:130) -----------------
     if (kStaged)
         for (int i = tid; i < KHW; i += T) s_delta[i] = __fmul_rn(ldf(img + i), ldf(img + KHW + i));
+    tl_phase(g, 3);
     // ---- prologue 3: NMS of the candidates, survivors' cells in visiting order (datatest.py:93-95) ----
     const int n_cand = base_s;
     if (n_cand > 0) {
-        const int m = nms_core(s, ubox, n_cand, nms_thr, 0, s_root, ucell);
+        const int m = nms_core(s, ubox, n_cand, nms_thr, 0, s_root, ucell, &g);
         if (tid == 0) n_keep_s = m;
     }
     __syncthreads();                                          // NMS scratch is dead from here; n_keep_s, s_root visible
     const int n_keep = n_keep_s;
+    tl_phase(g, 4);
     // for a crowded image have the L2 stream the x/y/w/h planes in now (one contiguous read): the
     // write-out's scattered gathers are then L2 hits
     if (tid == 0 && n_keep * 8 >= g.HW * 3 && ((size_t)KHW * sizeof(HT)) % 16 == 0 && (g.img_stride * sizeof(HT)) % 16 == 0 &&
@@ -1564,6 +1617,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
     }
     __syncthreads();
 
+    tl_phase(g, 5);
     if (n_keep > 0) {
         const HT* resp = img;
         const HT* conf = img + KHW;
@@ -1602,6 +1656,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
             }
         }
         __syncthreads();
+        tl_phase(g, 6);
         if (tid == 0) { base_s = 0; ebase_s = 0; }
         __syncthreads();
         // ---- humans with enough parts take consecutive output slots, in root order (datatest.py:129);
@@ -1654,6 +1709,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
             if (tid == 0) { base_s += total; ebase_s += etotal; }
         }
         __syncthreads();
+        tl_phase(g, 7);
         // ---- the image's place in the dense buffer ---------------------------------------------------
         const bool want_dense = dense.header != nullptr;
         if (want_dense && tid == 0) {

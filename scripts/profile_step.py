@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="cfg2")
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--overlap", type=int, default=0)
+ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--dense", action="store_true")
 ap.add_argument("--tune", action="append", default=[])
 ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16", "bf16"])
@@ -28,7 +29,7 @@ for kv in a.tune:
     k, v = kv.split("=")
     _lib.tune(**{k.replace(".", "_"): int(v)})
 cfg = PRESETS[a.config]()
-B = BATCH[a.config]
+B = a.batch or BATCH[a.config]
 bufs = [torch.rand(B, cfg.C, cfg.H, cfg.W, device="cuda") for _ in range(2)]
 dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[a.head_dtype]
 if a.dense or a.config == "cfg3":

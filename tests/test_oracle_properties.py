@@ -116,3 +116,57 @@ def test_blockwise_nms_equals_greedy(bx, thr, seed, limit, poison):
     score = rng.permutation(n).astype(np.float32)
     with np.errstate(all="ignore"):
         assert np.array_equal(blockwise_nms_model(b, thr, score, limit), O.nms(b, thr, score=score, limit=limit))
+
+
+def matrix_nms_model(b, thr, score, limit=None):
+    """Host model of an NMS formulation the CUDA path tried and does NOT use (nms_core's comment): the
+    full suppression matrix first — row i, 32-bit words, bit j set when box i suppresses the LATER box j, words before
+    i's own never written — then a walk over the survivors: the first box not in the removed set is kept, marked
+    visited, and the words of its row from its own word on are OR-ed into the set.  Exact, but slower on the GPU than
+    the block-by-block scheme above; kept as a property check of the formulation."""
+    n = len(b)
+    order = np.lexsort((-np.arange(n), -score.astype(np.float64)))
+    sb = b[order]
+    area = (sb[:, 2] - sb[:, 0]) * (sb[:, 3] - sb[:, 1])
+    thr = np.float32(thr)
+    Wd = (n + 31) // 32
+    rng = np.random.default_rng(n)
+    mat = rng.integers(0, 2 ** 32, size=(n, max(Wd, 1)), dtype=np.uint64)          # unwritten words hold garbage
+    for i in range(n):
+        later = np.arange(i + 1, n)
+        bits = np.zeros(Wd * 32, bool)
+        if len(later):
+            bits[later] = O.iou_one_to_many(sb[i], area[i], sb[later], area[later]) >= thr
+        words = np.packbits(bits.reshape(Wd, 32), axis=1, bitorder="little").view("<u4").ravel().astype(np.uint64)
+        mat[i, i // 32:] = words[i // 32:]
+    rem = np.array([0 if n - 32 * w >= 32 else (0xffffffff & ~((1 << max(n - 32 * w, 0)) - 1)) for w in range(Wd)], np.uint64)
+    keep = []
+    while True:
+        free = [w for w in range(Wd) if rem[w] != 0xffffffff]
+        if not free:
+            break
+        fw = free[0]
+        fb = (~int(rem[fw])) & 0xffffffff
+        i = 32 * fw + (fb & -fb).bit_length() - 1
+        keep.append(i)
+        if limit is not None and len(keep) >= limit:
+            break
+        rem[fw:] |= mat[i, fw:]
+        rem[fw] |= np.uint64(1 << (i & 31))
+    return order[np.asarray(keep, np.int64)].astype(np.int32) if keep else np.zeros(0, np.int32)
+
+
+@settings(max_examples=120, deadline=None)
+@given(wide_boxes, st.sampled_from([0.05, 0.3, 0.5, 0.9]), st.integers(0, 2 ** 31 - 1), st.sampled_from([None, 2, 40]),
+       st.booleans())
+def test_matrix_nms_equals_greedy(bx, thr, seed, limit, poison):
+    b = np.array([[y, x, y + h, x + w] for y, x, h, w in bx], np.float32).reshape(-1, 4)
+    n = len(b)
+    rng = np.random.default_rng(seed)
+    if poison and n:
+        k = rng.integers(0, n, size=max(1, n // 6))
+        b[k, 2] = b[k, 0]
+        b[k[: len(k) // 2], 3] = np.nan
+    score = rng.permutation(n).astype(np.float32)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(matrix_nms_model(b, thr, score, limit), O.nms(b, thr, score=score, limit=limit))
