@@ -233,6 +233,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) t.argmax_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
     else if (!std::strcmp(key, "argmax.split")) t.argmax_split = value;
     else if (!std::strcmp(key, "argmax.cluster")) t.argmax_cluster = value;
+    else if (!std::strcmp(key, "argmax.cluster_ring")) t.argmax_cluster_ring = value != 0;
     else if (!std::strcmp(key, "argmax.smem_cap")) t.argmax_smem_cap = value < 0 ? 0 : value;
     else if (!std::strcmp(key, "parse.overlap")) t.parse_overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!std::strcmp(key, "argmax.tail_opt")) t.argmax_tail_opt = value < 0 ? 0 : (value > 8 ? 8 : value);
@@ -263,6 +264,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "argmax.ctas_per_sm")) *value = t.argmax_ctas_per_sm;
     else if (!std::strcmp(key, "argmax.split")) *value = t.argmax_split;
     else if (!std::strcmp(key, "argmax.cluster")) *value = t.argmax_cluster;
+    else if (!std::strcmp(key, "argmax.cluster_ring")) *value = t.argmax_cluster_ring;
     else if (!std::strcmp(key, "argmax.smem_cap")) *value = t.argmax_smem_cap;
     else if (!std::strcmp(key, "parse.overlap")) *value = t.parse_overlap;
     else if (!std::strcmp(key, "argmax.tail_opt")) *value = t.argmax_tail_opt;

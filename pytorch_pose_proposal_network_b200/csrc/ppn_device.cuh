@@ -51,7 +51,8 @@ __device__ __forceinline__ void tl_phase(const Geom& g, int phase) {
     if (g.tl && threadIdx.x == 0 && g.tl_phase == phase) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        atomicMin(g.tl + 4 * (size_t)g.tl_slot + 3, t);
+        if (phase >= 100) atomicMax(g.tl + 4 * (size_t)g.tl_slot + 3, t);      // 100+: the LAST CTA past the point
+        else atomicMin(g.tl + 4 * (size_t)g.tl_slot + 3, t);
     }
 }
 

@@ -581,14 +581,16 @@ __device__ __forceinline__ Partial ld_dsmem_partial(uint32_t addr) {
 template <typename T>
 __global__ void __launch_bounds__(1024, 1)
 limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ amax, Geom g, int CV, int G, int pdl,
-                           int32_t* __restrict__ zero2) {
+                           int32_t* __restrict__ zero2, int ring_rows) {
     extern __shared__ __align__(128) unsigned char smem[];
     Partial* part = reinterpret_cast<Partial*>(smem);                    // [G][HW]; row 0 ends up as the CTA's result
+    constexpr int NS = 4;                                                // ring stages (ring_rows > 0)
     using V4 = typename Vec4Of<T>::type;
     const int tid = threadIdx.x;
     const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
     const int m = blockIdx.x / C;
     tl_mark(g, TL_START);
+    tl_phase(g, 121);
     if (pdl & PDL_WAIT_START) pdl_wait();
     tl_mark(g, TL_WAITED);
     if (zero2 && blockIdx.x == 0 && tid == 0) { zero2[0] = 0; zero2[1] = 0; }
@@ -598,7 +600,58 @@ limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ am
     const int r_lo = (int)((long long)g.S * rank / C), r_hi = (int)((long long)g.S * (rank + 1) / C);
     const bool active = tid < CV * G;
     const int grp = tid / CV, cv = tid - grp * CV;
-    if (active) {
+    if (ring_rows > 0) {
+        // The CTA's rows are one contiguous slab of the limb block: thread 0 streams it through a 4-stage ring of 1-D
+        // bulk copies (everything the ring holds is in flight at once — with 128-bit loads a thread had 8 rows in
+        // flight, two rounds and a tail of single loads per CTA, each a DRAM round trip: 4.4 - 7.7 us for 128 KB),
+        // every thread then reads its columns out of shared memory.
+        uint64_t* full = reinterpret_cast<uint64_t*>(smem + (((size_t)G * g.HW * sizeof(Partial) + 15) & ~(size_t)15));
+        uint64_t* empty = full + NS;
+        unsigned char* ring = smem + (((size_t)G * g.HW * sizeof(Partial) + 16 * sizeof(uint64_t) + 127) & ~(size_t)127);
+        const uint32_t row_bytes = (uint32_t)g.HW * (uint32_t)sizeof(T), stage_bytes = (uint32_t)ring_rows * row_bytes;
+        const int n_rows = r_hi - r_lo, n_chunks = (n_rows + ring_rows - 1) / ring_rows;
+        const unsigned char* slab = reinterpret_cast<const unsigned char*>(src) + (size_t)r_lo * row_bytes;
+        if (tid == 0) {
+            for (int st = 0; st < NS; ++st) { mbar_init(&full[st], 1); mbar_init(&empty[st], (uint32_t)(CV * G)); }
+            fence_mbar_init();
+        }
+        __syncthreads();
+        auto issue = [&](int c) {
+            const uint32_t bytes = (uint32_t)min(ring_rows, n_rows - c * ring_rows) * row_bytes;
+            mbar_arrive_expect_tx(&full[c % NS], bytes);
+            bulk_g2s(ring + (size_t)(c % NS) * stage_bytes, slab + (size_t)c * stage_bytes, bytes, &full[c % NS]);
+        };
+        if (tid == 0) for (int c = 0; c < NS && c < n_chunks; ++c) issue(c);
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int idx[4] = {r_lo, r_lo, r_lo, r_lo};                           // an empty row range must never win a tie
+        for (int c = 0; c < n_chunks; ++c) {
+            const int st = c % NS, ph = (c / NS) & 1;
+            if (active) {
+                mbar_wait(&full[st], (uint32_t)ph);
+                const int l0 = c * ring_rows, l1 = min(n_rows, l0 + ring_rows);
+                int lr = l0 + (grp - l0 % G + G) % G;                    // this group's first row of the chunk
+                const V4* rows = reinterpret_cast<const V4*>(ring + (size_t)st * stage_bytes);
+                for (; lr < l1; lr += G) {
+                    float v[4];
+                    widen4(rows[(size_t)(lr - l0) * CV + cv], v, T());
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) argmax_step(best[q], idx[q], v[q], r_lo + lr);
+                }
+                mbar_arrive(&empty[st]);
+            }
+            if (tid == 0 && c + NS < n_chunks) {                         // the stage is free once every reader has left it
+                mbar_wait(&empty[st], (uint32_t)ph);
+                issue(c + NS);
+            }
+        }
+        if (active) {
+            tl_phase(g, 22);
+            tl_phase(g, 122);
+            Partial* row = part + (size_t)grp * g.HW + 4 * cv;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) row[q] = Partial{best[q], idx[q]};
+        }
+    } else if (active) {
         float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         int idx[4] = {r_lo, r_lo, r_lo, r_lo};                           // an empty row range must never win a tie
         constexpr int U = 8;                                             // 128 B per thread in flight: latency is all there is here
@@ -622,6 +675,8 @@ limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ am
 #pragma unroll
             for (int q = 0; q < 4; ++q) argmax_step(best[q], idx[q], v[q], r);
         }
+        tl_phase(g, 22);
+        tl_phase(g, 122);
         Partial* row = part + (size_t)grp * g.HW + 4 * cv;
 #pragma unroll
         for (int q = 0; q < 4; ++q) row[q] = Partial{best[q], idx[q]};
@@ -635,7 +690,9 @@ limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ am
         }
         part[c] = bestp;
     }
+    tl_phase(g, 23);
     cluster_sync_all();
+    tl_phase(g, 24);
     if (rank == 0) {
         uint16_t* dst = amax + (size_t)m * g.HW;
         for (int c = tid; c < g.HW; c += blockDim.x) {
@@ -647,6 +704,7 @@ limb_argmax_cluster_kernel(const T* __restrict__ head, uint16_t* __restrict__ am
             dst[c] = (uint16_t)bestp.i;
         }
     }
+    tl_phase(g, 25);
     cluster_sync_all();                                                   // peers' shared memory stays alive until CTA 0 has read it
     tl_mark(g, TL_END);
     if ((pdl & PDL_WAIT_END) && tid == 0) pdl_wait();
@@ -2296,7 +2354,17 @@ static cudaError_t try_launch_argmax_cluster(const void* head_v, uint16_t* amax,
     if (G < 1) G = 1;
     while (G > 1 && CV * G > 1024) --G;
     const int threads = std::max(64, ((CV * G + 31) / 32) * 32);
-    const size_t smem = (size_t)G * g.HW * sizeof(Partial);
+    size_t smem = (size_t)G * g.HW * sizeof(Partial);
+    // ring of bulk copies when rows are whole 16-byte units (always so for fp32: HW % 4 == 0): 4 stages of ~16 KB, so
+    // that two CTAs still share an SM (see the note on G above)
+    int ring_rows = 0;
+    const size_t row_bytes = (size_t)g.HW * es;
+    if (t.argmax_cluster_ring && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(head_v) & 15) == 0 &&
+        (g.img_stride * es) % 16 == 0 && (g.limb_off * es) % 16 == 0 && row_bytes <= 32 * 1024) {
+        ring_rows = (int)std::max<size_t>(1, (16 * 1024) / row_bytes);
+        ring_rows = std::min(ring_rows, std::max(1, (rows + 3) / 4));
+        smem = ((smem + 16 * sizeof(uint64_t) + 127) & ~(size_t)127) + (size_t)4 * ring_rows * row_bytes;
+    }
     if (smem > (size_t)d->smem_optin) return cudaSuccess;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_mats * C));
@@ -2315,7 +2383,7 @@ static cudaError_t try_launch_argmax_cluster(const void* head_v, uint16_t* amax,
     cudaError_t e = cudaSuccess;
     PPN_DISPATCH_HEAD(g.dtype, {
         if ((e = ensure_smem(limb_argmax_cluster_kernel<T>, smem, &d->cluster[g.dtype])) != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, limb_argmax_cluster_kernel<T>, static_cast<const T*>(head_v), amax, g, CV, G, pdl_bits, zero2);
+        e = cudaLaunchKernelEx(&cfg, limb_argmax_cluster_kernel<T>, static_cast<const T*>(head_v), amax, g, CV, G, pdl_bits, zero2, ring_rows);
     });
     if (e == cudaSuccess) *done = true;
     return e;

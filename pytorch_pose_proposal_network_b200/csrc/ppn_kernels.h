@@ -20,6 +20,9 @@ struct Tuning {
                                        // the half-empty last wave costs; and inside the call chain the next launch fills that wave anyway
     int argmax_cluster = -1;           // tiny batches: a cluster of CTAs per matrix, partials merged through distributed
                                        // shared memory.  -1 auto (matrices <= half the SMs), 0 never, 2/4/8 forced
+    int argmax_cluster_ring = 0;       // 1: the cluster kernel streams its rows through a 4-stage ring of bulk copies instead of
+                                       // 128-bit loads (measured equal, 12.3 vs 12.5 us for one native image: fixed latencies, not the
+                                       // load pattern, bound a 128 KB slab per CTA — kept as a tested option)
     int argmax_smem_cap = 0;           // > 0: the ring may use at most this much shared memory (set per call by ppn_parse
                                        // so that the fused parse kernel's CTAs fit beside it on every SM)
     int argmax16_threads = 320;        // 16-bit heads: their own ring shape (rows are half as long, so an item

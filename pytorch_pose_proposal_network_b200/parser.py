@@ -158,6 +158,18 @@ def entries_to_packed(rec, b: int, K: int):
     return pc, ps, pb
 
 
+class CapturedParse:
+    """A recorded ``PoseParser.parse`` (see :meth:`PoseParser.capture`): ``replay()`` re-runs it on the captured
+    ``head`` / ``out`` buffers."""
+
+    def __init__(self, graph, head: torch.Tensor, out: PackedHumans):
+        self.graph, self.head, self.out = graph, head, out
+
+    def replay(self) -> PackedHumans:
+        self.graph.replay()
+        return self.out
+
+
 class PoseParser:
     """Decode + NMS + limb arg-max + tree parse of PPN head tensors on one B200.
 
@@ -286,6 +298,24 @@ class PoseParser:
         if rc:
             raise _lib.PPNError(rc, "ppn_parse" if dense is None else ("ppn_parse_dense" if remote is None else "ppn_parse_dense_remote"))
         return out
+
+    def capture(self, head: torch.Tensor, out: Optional[PackedHumans] = None, **parse_kwargs) -> "CapturedParse":
+        """Record ``parse(head, out)`` into a CUDA graph for repeated use on the SAME buffers — the single-image
+        loop of rt_test.py:87-147, where the network writes its output into one tensor frame after frame: a replay
+        is one graph launch instead of two or three kernel launches from Python.  ``head`` (and ``out``) must stay
+        alive and in place; refill ``head`` and call ``replay()`` (asynchronous, on torch's current stream)."""
+        B = self._check_head(head)
+        if out is None:
+            out = self.alloc_output(B)
+        self.parse(head, out=out, **parse_kwargs)                    # warm-up outside the capture: workspace, attributes
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.graph(graph, stream=side):
+            self.parse(head, out=out, **parse_kwargs)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        return CapturedParse(graph, head, out)
 
     def launches_per_parse(self, B: int) -> int:
         shape = self.c.shape(B)

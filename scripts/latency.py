@@ -120,6 +120,23 @@ for name in args.configs.split(","):
         ok = rr[:, 3] < (1 << 62)
         if ok.any():
             phases[ph] = statistics.median(((rr[ok, 3] - rr[ok, 0]) / 1e3).tolist())
+    k3 = {}
+    for ph in (22, 23, 24, 25, 121, 122):                                  # the arg-max (cluster) kernel's own phases
+        _lib.tune(timeline_phase=ph)
+        spin_up(100)
+        rec.zero_()
+        rec[:, 0] = rec[:, 2] = rec[:, 3] = torch.iinfo(torch.int64).max
+        if ph >= 100:
+            rec[:, 3] = 0
+        _lib.check(_lib.lib().ppn_timeline(rec.data_ptr(), rec.shape[0]), "ppn_timeline")
+        for i in range(args.calls):
+            parser.parse(bufs[i % n_buf], out=out)
+            torch.cuda.synchronize()
+        _lib.check(_lib.lib().ppn_timeline(None, 0), "ppn_timeline")
+        rr = rec.cpu().numpy().reshape(args.calls, n_k, 4)[:, 0]
+        ok = (rr[:, 3] < (1 << 62)) & (rr[:, 3] > 0)
+        if ok.any():
+            k3[ph] = statistics.median(((rr[ok, 3] - rr[ok, 0]) / 1e3).tolist())
     _lib.tune(timeline_phase=0)
     waited = statistics.median(((r[:, n_k - 1, 2] - r[:, n_k - 1, 0]) / 1e3).tolist())
 
@@ -134,13 +151,50 @@ for name in args.configs.split(","):
     stream = a.elapsed_time(b) * 1e3 / (args.calls * 5)
 
     clk.append(sm_mhz())
+    # the same call replayed from a CUDA graph on one buffer that is refilled from the rotating inputs (a device copy,
+    # outside the events): what PoseParser.capture() gives a frame loop
+    static = torch.empty_like(bufs[0])
+    cap = parser.capture(static)
+    spin_up()
+    gr = []
+    for i in range(args.calls):
+        static.copy_(bufs[i % n_buf])
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        cap.replay()
+        b.record()
+        torch.cuda.synchronize()
+        gr.append(a.elapsed_time(b) * 1e3)
+    import time
+    wall = []
+    for i in range(args.calls):
+        static.copy_(bufs[i % n_buf])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cap.replay()
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e6)
+    wall_plain = []
+    for i in range(args.calls):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        parser.parse(bufs[i % n_buf], out=out)
+        torch.cuda.synchronize()
+        wall_plain.append((time.perf_counter() - t0) * 1e6)
+
     print(f"{name} B={B} dist {args.dist}: {img_bytes / 1e6:.1f} MB per call, {n_k} launches, {float(out.count.float().mean()):.0f} humans, tune={args.tune}, inputs rotate over {n_buf * img_bytes / 1e6:.0f} MB, "
           f"SM clock sampled around the loops {clk} MHz")
     print(f"   events around one isolated call   median {statistics.median(ev):6.1f} us   min {min(ev):6.1f} us")
+    print(f"   events around one graph replay    median {statistics.median(gr):6.1f} us   min {min(gr):6.1f} us   (the buffer is L2-warm: just copied)")
+    print(f"   host wall, call -> synchronised   median {statistics.median(wall_plain):6.1f} us plain, {statistics.median(wall):6.1f} us graph replay")
     print(f"   device span (first start->last end) median {statistics.median(span):6.1f} us   min {min(span):6.1f} us   "
           + "  ".join(f"k{j} {statistics.median(per_k[j]):.1f}" for j in range(n_k)))
     print("   parse kernel, us after its start: " + "  ".join(f"p{k} {v:.1f}" for k, v in phases.items()) + f"  past-wait {waited:.1f}"
           "   (1 guard, 2 candidates, 3 delta staged, 4 NMS, 5 arg-max map staged, 6 walk, 7 slots assigned; inside the NMS: 11 ranked, 12 sorted, 13 diagonal blocks)")
+    if k3:
+        print("   arg-max kernel, us after its start (first CTA past each point): " + "  ".join(f"p{k} {v:.1f}" for k, v in k3.items())
+              + "   (22 rows streamed, 23 CTA reduced, 24 cluster barrier, 25 rank 0 gathered and stored; 121 / 122: the LAST CTA started / had its rows streamed)")
     print(f"   back to back on the stream          {stream:6.1f} us per call   ({img_bytes / stream / 1e3:.0f} GB/s)")
     del bufs, parser
     torch.cuda.empty_cache()

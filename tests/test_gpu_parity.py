@@ -463,6 +463,24 @@ def test_overlapped_chain_every_result():
         assert_packed_equals_oracle(o.numpy(), refs[i % 3], B)
 
 
+
+def test_captured_parse_replays_on_refilled_buffer():
+    """PoseParser.capture: one graph launch per frame on a buffer the caller refills (the rt_test.py loop)."""
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS["native"]()
+    g = O.Geometry.of(cfg)
+    parser = PoseParser(cfg)
+    head = torch.zeros(1, cfg.C, cfg.H, cfg.W, device="cuda")
+    cap = parser.capture(head)
+    for seed in (5, 6, 7):
+        frame = synth.make_head(g, "S" if seed == 6 else "U", seed=seed, B=1)
+        head.copy_(torch.from_numpy(frame))
+        packed = cap.replay()
+        torch.cuda.synchronize()
+        assert_packed_equals_oracle(packed.numpy(), c_oracle.parse_batch(frame, g), 1)
+
+
 @pytest.mark.parametrize("overlap", [1, 2])
 def test_cuda_graph_capture(overlap, fused):
     """The whole path is capturable: three parses (PDL chain or side-stream fork/join) recorded into
@@ -599,10 +617,11 @@ def test_argmax_sixteen_bit_special_values(dtype, grid, window):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("preset,B,cluster", [("cfg2", 1, -1), ("cfg2", 3, -1), ("native", 1, -1), ("native", 2, 4), ("cfg4", 1, 8),
                                              ("cfg2", 2, 2), ("cfg3", 5, 8)])
-def test_limb_argmax_cluster_kernel_tiny_batches(preset, B, cluster, dtype):
+@pytest.mark.parametrize("ring", [1, 0])
+def test_limb_argmax_cluster_kernel_tiny_batches(preset, B, cluster, dtype, ring):
     """Tiny batches take the thread-block-cluster kernel (C CTAs per matrix, partials merged through
     distributed shared memory): same arg-max map as numpy's, ties across CTAs and NaNs included, and the
-    whole path on top of it."""
+    whole path on top of it.  ring = 1: the rows stream through a ring of bulk copies; 0: 128-bit loads."""
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PRESETS
     from pytorch_pose_proposal_network_b200.parser import PoseParser
@@ -616,7 +635,7 @@ def test_limb_argmax_cluster_kernel_tiny_batches(preset, B, cluster, dtype):
     e[0, 1, 1, 3] = float("nan"); e[0, 1, g.S - 2, 3] = float("nan")     # two NaNs: the first one wins
     up = head.float().numpy()
     want = up[:, 6 * g.K:].reshape(B, g.E, g.S, g.H, g.W).argmax(2).astype(np.uint16)
-    _lib.tune(argmax_cluster=cluster)
+    _lib.tune(argmax_cluster=cluster, argmax_cluster_ring=ring)
     try:
         parser = PoseParser(cfg)
         got = parser.limb_argmax(head.cuda()).cpu().numpy()
@@ -627,7 +646,7 @@ def test_limb_argmax_cluster_kernel_tiny_batches(preset, B, cluster, dtype):
             packed = parser.parse(clean.cuda(), input_complete=True)
         assert_packed_equals_oracle(packed.numpy(), ref, B)
     finally:
-        _lib.tune(argmax_cluster=-1)
+        _lib.tune(argmax_cluster=-1, argmax_cluster_ring=0)
 
 
 # ------------------------------------------------------------------------------------------
