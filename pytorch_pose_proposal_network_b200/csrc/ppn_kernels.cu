@@ -897,7 +897,7 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
     if (tg) tl_phase(*tg, 12);
     // (tried, round 2: the FULL n x n suppression bit matrix built by all warps first, then either every box deciding
     //  for itself from its column, round after round, or one warp walking the survivors with ballot / find-first-set and
-    //  OR-ing their rows into the removed set.  Exact both ways (tests/test_oracle_properties.py keeps the model of the
+    //  OR-ing their rows into the removed set.  Exact both ways (the property tests keep a host model of the
     //  second), and slower both ways: all n^2/2 pair tests instead of survivors x rest, ~2 barrier rounds resp. ~210
     //  dependent cycles per SURVIVOR.  One image at the reference's native shape, 351 candidates -> 58 survivors:
     //  28 us block by block, 35 us with the matrix; 1024 dense images (256 -> 225): 91 -> 105 us.)
