@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PPN_ABI_VERSION 5
+#define PPN_ABI_VERSION 6
 
 /* library error codes (negative); positive return values are cudaError_t */
 #define PPN_OK               0
@@ -281,6 +281,38 @@ int ppn_head_gemm_argmax(const float* feat, const float* weight, const float* bi
 int ppn_head_parse(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
                    const PPNParams* params, const PPNHumans* out, void* workspace, size_t workspace_bytes,
                    float* emit_logits, float* emit_head, void* stream);
+
+/* The same with a choice of tensor-core operand type and activation layout.
+ *   operand      PPN_GEMM_TF32: as above (fp32 NCHW activations read in place).
+ *                PPN_GEMM_F16 / PPN_GEMM_BF16: operands rounded to fp16 / bf16 (round to nearest even), products
+ *                accumulated in fp32 — what the reference's conv3 computes under its apex AMP training setup
+ *                (main.py:282-289).  fp16 keeps TF32's 10 mantissa bits (activations beyond +-65504 overflow);
+ *                bf16 keeps fp32's range with 7.  Twice the tensor-core rate on half the operand bytes.
+ *   feat_layout  PPN_FEAT_NCHW_F32: feat is fp32 [B, Cin, H, W]; for a 16-bit operand a pre-pass kernel packs it to
+ *                [B*H*W, Cin] in the workspace (one extra read of feat, one 16-bit write).
+ *                PPN_FEAT_NHWC_16: feat already is [B, H, W, Cin] in the operand type (a channels_last tensor of
+ *                an autocast network): read in place, no pre-pass.  16-bit operands only.
+ * The 16-bit path needs 64 <= Cin <= 512, Cin % 64 == 0 (conv3 has Cin = 512): PPN_E_UNSUPPORTED otherwise.
+ * Everything downstream of the logits is exact as above: results are bit-identical to ppn_parse on emit_head.
+ * `workspace` (ppn_head_workspace_bytes_opt, 256-byte aligned) holds dec, amax and the packed operands;
+ * ppn_head_gemm_argmax_opt writes dec / amax to the caller's buffers and uses the workspace for the packed
+ * operands only (it may be NULL for PPN_GEMM_TF32). */
+#define PPN_GEMM_TF32      0
+#define PPN_GEMM_F16       1
+#define PPN_GEMM_BF16      2
+#define PPN_FEAT_NCHW_F32  0
+#define PPN_FEAT_NHWC_16   1
+typedef struct PPNHeadOptions {
+    int32_t operand;        /* PPN_GEMM_*                                                           */
+    int32_t feat_layout;    /* PPN_FEAT_*                                                           */
+} PPNHeadOptions;
+int ppn_head_workspace_bytes_opt(const PPNShape* shape, int32_t Cin, const PPNHeadOptions* opt, size_t* bytes);
+int ppn_head_gemm_argmax_opt(const void* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                             const PPNHeadOptions* opt, void* workspace, size_t workspace_bytes,
+                             float* dec, uint16_t* amax, float* emit_logits, float* emit_head, void* stream);
+int ppn_head_parse_opt(const void* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                       const PPNParams* params, const PPNHeadOptions* opt, const PPNHumans* out, void* workspace,
+                       size_t workspace_bytes, float* emit_logits, float* emit_head, void* stream);
 
 /* ---- the inverse of the parser: training targets from annotations ------------------------------
  * Replaces the "# Encode samples" half of KeypointsDataset.__getitem__ (dataset.py:89-198) for a whole

@@ -10,8 +10,10 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 HEAD_F32, HEAD_F16, HEAD_BF16 = 0, 1, 2
+GEMM_TF32, GEMM_F16, GEMM_BF16 = 0, 1, 2
+FEAT_NCHW_F32, FEAT_NHWC_16 = 0, 1
 FLAG_INPUT_COMPLETE = 1
 FLAG_CLEAR_UNUSED = 2
 MAX_CELLS = 1024
@@ -38,6 +40,10 @@ class PPNParams(C.Structure):
 class PPNHumans(C.Structure):
     _fields_ = [("count", C.c_void_p), ("root_cell", C.c_void_p), ("part_cell", C.c_void_p),
                 ("part_score", C.c_void_p), ("part_box", C.c_void_p), ("R", C.c_int32)]
+
+
+class PPNHeadOptions(C.Structure):
+    _fields_ = [("operand", C.c_int32), ("feat_layout", C.c_int32)]
 
 
 class PPNPeople(C.Structure):
@@ -94,6 +100,12 @@ EXPORTS = {
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "ppn_head_parse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PPNShape), C.POINTER(PPNParams),
                                  C.POINTER(PPNHumans), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ppn_head_workspace_bytes_opt": (C.c_int, [C.POINTER(PPNShape), C.c_int32, C.POINTER(PPNHeadOptions), C.POINTER(C.c_size_t)]),
+    "ppn_head_gemm_argmax_opt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PPNShape), C.POINTER(PPNHeadOptions),
+                                           C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ppn_head_parse_opt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PPNShape), C.POINTER(PPNParams),
+                                     C.POINTER(PPNHeadOptions), C.POINTER(PPNHumans), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "ppn_encode_targets": (C.c_int, [C.POINTER(PPNPeople), C.POINTER(PPNShape), i32p, C.POINTER(PPNTargets), C.c_void_p]),
     "ppn_debug_argmax_items": (C.c_int, [C.POINTER(PPNShape), C.c_int32, i32p, i32p, i32p, C.c_int32]),
     "ppn_timeline": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -246,6 +246,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "parse.k12_threads")) t.parse_k12_threads = value < 0 ? 0 : value;
     else if (!std::strcmp(key, "parse.fused")) t.parse_fused = value < 0 ? -1 : (value != 0);
     else if (!std::strcmp(key, "parse.threads")) t.parse_threads = value;
+    else if (!std::strcmp(key, "head.subs")) t.head_subs = value < 1 ? 1 : (value > 4 ? 4 : value);
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else if (!std::strcmp(key, "encode.sweep")) t.encode_sweep = value != 0;
     else if (!std::strcmp(key, "encode.ctas_per_sm")) t.encode_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
@@ -701,16 +702,18 @@ static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* 
 
 // ---- fused network head ---------------------------------------------------------------------
 namespace {
-struct HeadWorkspace { size_t dec, amax, total; };
+struct HeadWorkspace { size_t dec, amax, keys, total; };
 HeadWorkspace carve_head(const PPNShape* s) {
     HeadWorkspace w;
     const size_t B = (size_t)s->B, HW = (size_t)s->H * s->W;
     w.dec = 0;
     w.amax = align_up(B * 6 * s->K * HW * sizeof(float), 256);
-    w.total = w.amax + align_up(B * s->E * HW * sizeof(uint16_t), 256);
+    w.keys = w.amax + align_up(B * s->E * HW * sizeof(uint16_t), 256);
+    w.total = w.keys + align_up(B * s->E * HW * sizeof(unsigned long long), 256);     // the epilogue's running maxima
     return w;
 }
 int check_head(const float* feat, const float* weight, int32_t Cin, const PPNShape* s) {
+    if ((long long)s->H * s->W > 65536) return PPN_E_UNSUPPORTED;
     if (Cin < 32 || Cin % 32 != 0 || (s->H * s->W) % 4 != 0) return PPN_E_UNSUPPORTED;
     if (s->head_dtype != PPN_HEAD_F32) return PPN_E_UNSUPPORTED;
     if (!feat || !weight) return PPN_E_BADARG;
@@ -729,18 +732,84 @@ int ppn_head_workspace_bytes(const PPNShape* shape, size_t* bytes) {
 
 int ppn_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
                          float* dec, uint16_t* amax, float* emit_logits, float* emit_head, void* stream) {
+    const ppn::Tuning g_tuning = tuning_now();
     int rc = check_shape(shape);
     if (rc) return rc;
     if (shape->B == 0) return PPN_OK;
     if ((rc = check_head(feat, weight, Cin, shape))) return rc;
-    if (!dec || (!amax && shape->E > 0)) return PPN_E_BADARG;
-    return cuda_rc(ppn::launch_head_gemm_argmax(feat, weight, bias, Cin, make_geom(shape), dec, amax, emit_logits, emit_head,
-                                                (cudaStream_t)stream, false, 0));
+    if (!dec || (!amax && shape->E > 0) || (reinterpret_cast<uintptr_t>(bias) & 15)) return PPN_E_BADARG;
+    // no workspace in this signature: the running maxima live in a stream-ordered allocation
+    const ppn::Geom g = make_geom(shape);
+    cudaStream_t st = (cudaStream_t)stream;
+    void* keys = nullptr;
+    cudaError_t e = cudaMallocAsync(&keys, std::max<size_t>(ppn::head_keys_bytes(g), 256), st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = ppn::launch_head_gemm_argmax(feat, weight, bias, Cin, g, dec, amax, static_cast<unsigned long long*>(keys), emit_logits,
+                                     emit_head, st, false, 0, g_tuning.head_subs);
+    const cudaError_t e2 = cudaFreeAsync(keys, st);
+    return cuda_rc(e != cudaSuccess ? e : e2);
 }
 
-int ppn_head_parse(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
-                   const PPNParams* params, const PPNHumans* out, void* workspace, size_t workspace_bytes,
-                   float* emit_logits, float* emit_head, void* stream) {
+namespace {
+struct HeadWorkspaceOpt { size_t dec, amax, keys, xt, wt, total; };
+bool opt_16bit(const PPNHeadOptions* o) { return o->operand == PPN_GEMM_F16 || o->operand == PPN_GEMM_BF16; }
+int check_head_opt(const void* feat, const float* weight, int32_t Cin, const PPNShape* s, const PPNHeadOptions* o) {
+    if (!o) return PPN_E_BADARG;
+    if (o->operand < PPN_GEMM_TF32 || o->operand > PPN_GEMM_BF16) return PPN_E_BADARG;
+    if (o->feat_layout != PPN_FEAT_NCHW_F32 && o->feat_layout != PPN_FEAT_NHWC_16) return PPN_E_BADARG;
+    if (!opt_16bit(o) && o->feat_layout != PPN_FEAT_NCHW_F32) return PPN_E_UNSUPPORTED;
+    if (s->B == 0) return PPN_OK;
+    if (!opt_16bit(o)) return check_head(static_cast<const float*>(feat), weight, Cin, s);
+    if (s->head_dtype != PPN_HEAD_F32) return PPN_E_UNSUPPORTED;
+    if (!ppn::head16_supported(Cin, make_geom(s))) return PPN_E_UNSUPPORTED;
+    if (!feat || !weight) return PPN_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(feat) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15)) return PPN_E_BADARG;
+    return PPN_OK;
+}
+HeadWorkspaceOpt carve_head_opt(const PPNShape* s, int32_t Cin, const PPNHeadOptions* o) {
+    const HeadWorkspace w = carve_head(s);
+    HeadWorkspaceOpt r;
+    r.dec = w.dec; r.amax = w.amax; r.keys = w.keys; r.xt = r.wt = r.total = w.total;
+    if (opt_16bit(o)) {
+        const ppn::Geom g = make_geom(s);
+        r.wt = r.xt + (o->feat_layout == PPN_FEAT_NCHW_F32 ? align_up(ppn::head16_packed_feat_bytes(Cin, g), 1024) : 0);
+        r.total = r.wt + align_up(ppn::head16_packed_weight_bytes(Cin, g), 1024);
+    }
+    return r;
+}
+}  // namespace
+
+int ppn_head_workspace_bytes_opt(const PPNShape* shape, int32_t Cin, const PPNHeadOptions* opt, size_t* bytes) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if (!bytes || !opt || Cin < 1) return PPN_E_BADARG;
+    *bytes = carve_head_opt(shape, Cin, opt).total;
+    return PPN_OK;
+}
+
+int ppn_head_gemm_argmax_opt(const void* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                             const PPNHeadOptions* opt, void* workspace, size_t workspace_bytes,
+                             float* dec, uint16_t* amax, float* emit_logits, float* emit_head, void* stream) {
+    int rc = check_shape(shape);
+    if (rc) return rc;
+    if ((rc = check_head_opt(feat, weight, Cin, shape, opt))) return rc;
+    if (!opt_16bit(opt))
+        return ppn_head_gemm_argmax(static_cast<const float*>(feat), weight, bias, Cin, shape, dec, amax, emit_logits, emit_head, stream);
+    if (shape->B == 0) return PPN_OK;
+    if (!dec || (!amax && shape->E > 0) || (reinterpret_cast<uintptr_t>(bias) & 15)) return PPN_E_BADARG;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return PPN_E_BADARG;
+    const HeadWorkspaceOpt w = carve_head_opt(shape, Cin, opt);
+    if (workspace_bytes < w.total) return PPN_E_WORKSPACE;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    return cuda_rc(ppn::launch_head_gemm16_argmax(feat, opt->feat_layout == PPN_FEAT_NCHW_F32, weight, bias, Cin,
+                                                  opt->operand == PPN_GEMM_BF16, make_geom(shape), ws + w.xt, ws + w.wt, dec, amax,
+                                                  reinterpret_cast<unsigned long long*>(ws + w.keys), emit_logits, emit_head,
+                                                  (cudaStream_t)stream, 0, tuning_now().head_subs));
+}
+
+int ppn_head_parse_opt(const void* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                       const PPNParams* params, const PPNHeadOptions* opt, const PPNHumans* out, void* workspace,
+                       size_t workspace_bytes, float* emit_logits, float* emit_head, void* stream) {
     const ppn::Tuning g_tuning = tuning_now();
     int rc = check_shape(shape);
     if (rc) return rc;
@@ -748,15 +817,16 @@ int ppn_head_parse(const float* feat, const float* weight, const float* bias, in
     if ((rc = check_humans(out))) return rc;
     ppn::ChainTable ch;
     if ((rc = make_chains(shape, params, &ch))) return rc;
+    if ((rc = check_head_opt(feat, weight, Cin, shape, opt))) return rc;
     if (shape->B == 0) return PPN_OK;
-    if ((rc = check_head(feat, weight, Cin, shape))) return rc;
     if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return PPN_E_BADARG;
     if (params->n_nms_parts != 1 || (long long)shape->H * shape->W > PPN_MAX_CELLS) return PPN_E_UNSUPPORTED;
-    if (reinterpret_cast<uintptr_t>(out->part_box) & 15) return PPN_E_BADARG;
-    const HeadWorkspace w = carve_head(shape);
+    if ((reinterpret_cast<uintptr_t>(out->part_box) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15)) return PPN_E_BADARG;
+    const HeadWorkspaceOpt w = carve_head_opt(shape, Cin, opt);
     if (workspace_bytes < w.total) return PPN_E_WORKSPACE;
-    float* dec = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + w.dec);
-    uint16_t* amax = reinterpret_cast<uint16_t*>(static_cast<unsigned char*>(workspace) + w.amax);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* dec = reinterpret_cast<float*>(ws + w.dec);
+    uint16_t* amax = reinterpret_cast<uint16_t*>(ws + w.amax);
     const ppn::Geom g = make_geom(shape);
     // the parse kernel reads the decode planes as a head tensor that holds nothing but its 6K decode channels
     ppn::Geom gd = g;
@@ -764,15 +834,28 @@ int ppn_head_parse(const float* feat, const float* weight, const float* bias, in
     if (!ppn::parse_fused_supported(gd, g_tuning.parse_stage_all)) return PPN_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-    // two launches: the GEMM kernel waits for whatever produced `feat`, then lets the parse kernel become resident;
-    // the parse kernel waits for the GEMM kernel to COMPLETE before it reads anything (everything it reads is new)
-    if ((e = ppn::launch_head_gemm_argmax(feat, weight, bias, Cin, g, dec, amax, emit_logits, emit_head, st, true,
-                                          ppn::PDL_WAIT_START | ppn::PDL_TRIGGER)) != cudaSuccess) return (int)e;
+    // launches: clear the running maxima, [pack the operands,] GEMM + epilogue, maxima -> arg-max map, parse (a programmatic
+    // dependent of the last: it becomes resident early and waits at its top)
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + w.keys);
+    if (opt_16bit(opt))
+        e = ppn::launch_head_gemm16_argmax(feat, opt->feat_layout == PPN_FEAT_NCHW_F32, weight, bias, Cin, opt->operand == PPN_GEMM_BF16,
+                                           g, ws + w.xt, ws + w.wt, dec, amax, keys, emit_logits, emit_head, st, 0, g_tuning.head_subs);
+    else
+        e = ppn::launch_head_gemm_argmax(static_cast<const float*>(feat), weight, bias, Cin, g, dec, amax, keys, emit_logits, emit_head, st,
+                                         false, 0, g_tuning.head_subs);
+    if (e != cudaSuccess) return (int)e;
     e = ppn::launch_parse_fused(dec, gd, ch, params->det_thresh, params->nms_thresh, params->min_num_keypoints, amax, out->count,
                                 out->root_cell, out->part_cell, out->part_score, out->part_box, out->R, st, true, 1,
                                 g_tuning.parse_stage_all, -1, nullptr, true);
     ppn::chain_break(st);
     return cuda_rc(e);
+}
+
+int ppn_head_parse(const float* feat, const float* weight, const float* bias, int32_t Cin, const PPNShape* shape,
+                   const PPNParams* params, const PPNHumans* out, void* workspace, size_t workspace_bytes,
+                   float* emit_logits, float* emit_head, void* stream) {
+    const PPNHeadOptions opt = {PPN_GEMM_TF32, PPN_FEAT_NCHW_F32};
+    return ppn_head_parse_opt(feat, weight, bias, Cin, shape, params, &opt, out, workspace, workspace_bytes, emit_logits, emit_head, stream);
 }
 
 int ppn_part_centres(const PPNHumans* humans, int32_t B, int32_t K, float* centre_yx, void* stream) {

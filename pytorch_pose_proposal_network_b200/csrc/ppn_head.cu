@@ -30,6 +30,12 @@
 // 3-D view [B][Cin][HW] with zero fill past HW — so a 12x12 grid (144 = 4.5 groups) wastes 11 % of
 // the rows, not 44 %, and every epilogue warp (one group) works on a single image.
 //
+// Two operand paths (HeadOperand): TF32 on the fp32 NCHW activations read in place (above), and a 16-bit path
+// (fp16 or bf16 operands, kind::f16, fp32 accumulation — what the reference's conv3 computes under its apex AMP
+// training setup, main.py:282-289): a pre-pass packs activations and weights K-major in 16 bits (or the caller hands
+// in channels_last 16-bit activations), the A tile of a block of 128 cells stays resident in shared memory for all
+// channel tiles and only the weights stream.  See head_gemm16_argmax_kernel.
+//
 // Exactness.  The parser's contract is "bit-exact on sigmoid(logits)".  sigmoid is monotone but not
 // injective in fp32 (neighbouring logits often share a sigmoid value), so an arg-max over logits can
 // differ from numpy's first-maximum over the sigmoid values.  The running rule therefore decides on
@@ -54,7 +60,6 @@ constexpr int kABytes = 4 * kGroupBytes;     // 16 KB
 constexpr int kBBytes = kBlockN * 128;       // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 512;               // two 256-column accumulators
-constexpr int kMaxEpiSubs = 3;               // epilogue warps per TMEM lane quadrant (template parameter of the kernel)
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
@@ -74,14 +79,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {      // arrives on `bar` when every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], one instruction of M x N x 8 (tf32)
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem] * B[smem], one instruction of M x N x 32 bytes of K: kind 0 = tf32 (K = 8), 1 = f16 / bf16 (K = 16)
+template <int kKind>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kKind == 0)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // Shared-memory matrix descriptor (sm_100 format: version 1); offsets in bytes.  layout: 2 = 128-byte swizzle of
 // 16-byte chunks (K-major operands), 1 = 128-byte swizzle of 32-byte chunks — the only layout the tensor core
@@ -123,17 +137,189 @@ __device__ __noinline__ bool beats_in_sigmoid(float x, float bx) {
 struct HeadArgs {
     int32_t B, HW, Cin, C, n_dec, S, E;
     int32_t groups_per_img, n_groups, n_tiles, n_ntiles, n_kblocks;
+    int32_t n_last;             // channels of the LAST channel tile, rounded up to 16: its MMAs and its weight box are that narrow
+    int32_t n_rows;             // 16-bit path: B * HW rows of the packed activation matrix
+    int32_t n_bstages;          // 16-bit path: stages of the weight ring
+    int32_t bf16;               // 16-bit path: operands are bf16 (else fp16)
     uint32_t magic_S;           // ceil(2^32 / S): exact p / S for p < 2^22 (S <= 65535 and S * E channels)
     const float* bias;          // [C] or nullptr
     float* dec;                 // [B, n_dec, HW]   sigmoid of the 6K decode channels
-    uint16_t* amax;             // [B, E, HW]
+    unsigned long long* keys;   // [B, E, HW]  running (sigmoid, ~position) maxima, zero before the kernel
     float* emit_logits;         // optional [B, C, HW]: conv output before the sigmoid (parity tests)
     float* emit_head;           // optional [B, C, HW]: the reference's head tensor, sigmoid(logits)
 };
 
+// ------------------------------ epilogue (both operand paths) ------------------------------
+// kSubs warps share each TMEM lane quadrant (32 accumulator rows = 32 cells).  Every channel tile's columns are cut
+// into kSubs runs of whole 8-column groups and sub-warp s takes run s — the same share of every tile whatever the
+// window size, so the sub-warps never wait for one another (no barrier between them: the bias comes through the
+// read-only cache, the accumulator is released by per-warp arrivals).  A sub-warp's run crosses limb windows; each
+// maximal stretch of one window inside a run is a PIECE: the thread scans it with numpy's running first-maximum rule
+// and publishes (sigmoid of the winner, its window position) with ONE 64-bit atomic max on keys[b][ei][cell]:
+//     key = sigmoid bits << 32 | ~position        (sigmoid in [0, 1]: bit order == value order; NaN -> 0xffffffff)
+// so the largest sigmoid wins, equal sigmoids resolve to the smallest position, the first NaN beats everything —
+// numpy.argmax over the whole window, whichever sub-warps, channel tiles or order the pieces came from.  The keys
+// start at zero (memset) and head_amax_finalize_kernel turns them into the uint16 map.
+// (Round-2 history: windows were owned by sub-warps and the bias was staged in shared memory behind a barrier per
+// channel tile; ncu: 55 warp instructions per accumulator column — skip scans with two divisions per group, the
+// per-column generic path at every window boundary — and 20 % of all samples at that barrier: 107 us per tile of
+// 128 cells x 1311 channels, the same for TF32 and 16-bit operands.  The kernel was bound by its epilogue.)
+// kDense: accumulator row r of tile t is row t * 128 + r of the flattened (image, cell) list (16-bit path: no padding);
+// otherwise the tile is 4 cell groups of 32 cells of one image each (TF32 path).
+__device__ __noinline__ void publish_piece(unsigned long long* slot, float bx, int idx, bool valid) {
+    const float sb = sigmoid_f32(bx);
+    const uint32_t hi = (sb != sb) ? 0xFFFFFFFFu : __float_as_uint(sb);
+    if (valid) atomicMax(slot, ((unsigned long long)hi << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx));
+}
+
+template <int kSubs, bool kDense>
+__device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ew = warp & 3;                     // the TMEM lane quadrant this warp may read
+    const int sub = (warp - 2) >> 2;             // which of the quadrant's warps
+    const bool emit = a.emit_logits != nullptr || a.emit_head != nullptr;
+    const bool bias_vec = a.bias != nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int b, cell;
+        bool valid;
+        if constexpr (kDense) {
+            const int r = tile * kBlockM + ew * 32 + lane;
+            valid = r < a.n_rows;
+            b = valid ? r / a.HW : 0;
+            cell = valid ? r - b * a.HW : 0;
+        } else {
+            const int g = tile * 4 + ew;
+            b = g / a.groups_per_img;
+            cell = (g - b * a.groups_per_img) * 32 + lane;
+            valid = g < a.n_groups && cell < a.HW;
+            if (!valid) { b = 0; cell = 0; }
+        }
+        unsigned long long* const key0 = a.keys + (size_t)b * a.E * a.HW + cell;      // + ei * HW
+        for (int nt = 0; nt < a.n_ntiles; ++nt) {
+            const int c_tile = nt * kBlockN;
+            const int n_cols = min(kBlockN, a.C - c_tile);            // > 0
+            // this sub-warp's run of the tile: whole 8-column groups
+            const int n8 = (n_cols + 7) >> 3, per = (n8 + kSubs - 1) / kSubs;
+            const int r_lo = c_tile + min(sub * per, n8) * 8;
+            const int r_hi = min(c_tile + min((sub + 1) * per, n8) * 8, c_tile + n_cols);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            if (r_lo < r_hi) {
+                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN) - (uint32_t)c_tile;
+                // state of the piece being scanned: m = largest logit so far (+inf once a NaN has been taken: nothing may
+                // follow the first NaN), idx = the arg-max so far (window position) and bx = the logit it stands on
+                // (bx <= m: a larger logit whose sigmoid TIES with the standing one does not move the arg-max).  A piece
+                // starts from (-inf, -inf, its first position): sigmoid(-inf) = 0 stands until something beats it.
+                bool limb = false;
+                int ei = 0, wbase = 0, seg_end = 0, idx = 0;
+                float m = -INFINITY, bx = -INFINITY;
+                auto begin = [&](int c) {                             // uniform
+                    if (c < a.n_dec) { limb = false; seg_end = min(a.n_dec, r_hi); return; }
+                    const int p = c - a.n_dec;                        // exact magic division, p < 2^22
+                    ei = (int)(((unsigned long long)(unsigned)p * a.magic_S) >> 32);
+                    const int aw = p - ei * a.S;
+                    limb = true; wbase = c - aw; seg_end = min(wbase + a.S, r_hi);
+                    m = -INFINITY; bx = -INFINITY; idx = aw;
+                };
+                // One limb column at window position aw.  A logit above the running maximum beats the standing arg-max
+                // iff sigmoid(x) > sigmoid(bx) (numpy sees sigmoid values).  For x - m > 0.01 and |x| <= 8 it certainly
+                // does: sigmoid' >= 3.3e-4 on [-8.01, 8], so the sigmoids are >= 3.3e-6 apart — tens of ulps, far beyond
+                // either one's evaluation error — and m >= bx: that case is three selects, no branch.  Only the rest
+                // (near-ties, the saturated tails, NaN, +-inf) branches out to evaluate the two sigmoids.
+                auto limb_column = [&](float x, int aw) {
+                    const bool gt = !(x <= m);
+                    const bool fast = gt && __fsub_rn(x, m) > 0.01f && fabsf(x) <= 8.0f;
+                    idx = fast ? aw : idx;
+                    bx = fast ? x : bx;
+                    if (gt && !fast) {
+                        if (beats_in_sigmoid(x, bx)) { idx = aw; bx = x; }
+                        m = (x != x) ? INFINITY : x;
+                    }
+                    m = fast ? x : m;
+                };
+                auto load_group = [&](int c0, uint32_t* r, float* bs) {
+                    tmem_ld8_issue(t_row + (uint32_t)c0, r);
+                    if (bias_vec && c0 + 8 <= a.C) {
+                        const float4 lo = __ldg(reinterpret_cast<const float4*>(a.bias + c0));
+                        const float4 hi = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + 1);
+                        bs[0] = lo.x; bs[1] = lo.y; bs[2] = lo.z; bs[3] = lo.w; bs[4] = hi.x; bs[5] = hi.y; bs[6] = hi.z; bs[7] = hi.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) bs[j] = (bias_vec && c0 + j < a.C) ? __ldg(a.bias + c0 + j) : -0.0f;   // x + (-0) == x
+                    }
+                };
+                uint32_t cur[8], nxt[8];
+                float bcur[8], bnxt[8];
+                begin(r_lo);
+                load_group(r_lo, nxt, bnxt);
+#pragma unroll 1
+                for (int c0 = r_lo; c0 < r_hi; c0 += 8) {
+                    tmem_ld8_wait(nxt);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { cur[j] = nxt[j]; bcur[j] = bnxt[j]; }
+                    if (c0 + 8 < r_hi) load_group(c0 + 8, nxt, bnxt);      // in flight while this group is scanned
+                    if (limb && !emit && c0 + 8 <= seg_end) {               // eight columns of one window
+                        const int aw0 = c0 - wbase;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) limb_column(__fadd_rn(__uint_as_float(cur[j]), bcur[j]), aw0 + j);
+                        if (c0 + 8 == seg_end) {
+                            publish_piece(key0 + (size_t)ei * a.HW, bx, idx, valid);
+                            if (c0 + 8 < r_hi) begin(c0 + 8);
+                        }
+                    } else {
+                        // decode channels, a window boundary inside the group, the ragged end of the run, or a call that also
+                        // emits logits / the head tensor
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = c0 + j;
+                            if (c < r_hi) {                                 // uniform
+                                const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
+                                const size_t at = ((size_t)b * a.C + c) * a.HW + cell;
+                                if (a.emit_logits && valid) a.emit_logits[at] = x;
+                                if (!limb || a.emit_head) {
+                                    const float sg = sigmoid_f32(x);
+                                    if (!limb && valid) a.dec[((size_t)b * a.n_dec + c) * a.HW + cell] = sg;
+                                    if (a.emit_head && valid) a.emit_head[at] = sg;
+                                }
+                                if (limb) limb_column(x, c - wbase);
+                                if (c + 1 == seg_end) {
+                                    if (limb) publish_piece(key0 + (size_t)ei * a.HW, bx, idx, valid);
+                                    if (c + 1 < r_hi) begin(c + 1);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+}
+
+// keys -> the uint16 arg-max map (low half of a key = ~position)
+__global__ void __launch_bounds__(256)
+head_amax_finalize_kernel(const unsigned long long* __restrict__ keys, uint16_t* __restrict__ amax, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) amax[i] = (uint16_t)(0xFFFFFFFFu - (uint32_t)keys[i]);
+}
+
+// instruction descriptor: D fp32; formats 0 = f16, 1 = bf16, 2 = tf32; bit 15 / 16: A / B MN-major; N >> 3; M >> 4
+__device__ __forceinline__ uint32_t mma_idesc(uint32_t fmt, uint32_t a_mn_major, int n) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn_major << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+// ------------------------------ TF32 path: fp32 NCHW activations read in place ------------------------------
 template <int kSubs>
 __global__ void __launch_bounds__(64 + 128 * kSubs, 1)
-head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, HeadArgs a, int pdl) {
+head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                        const __grid_constant__ CUtensorMap tm_wt, HeadArgs a, int pdl) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
@@ -141,13 +327,13 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     uint64_t* tfull = empty + kStages;       // [2] accumulator ready for the epilogue
     uint64_t* tempty = tfull + 2;            // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* s_bias = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes + 256);   // [2][kBlockN]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_x);
         prefetch_tensormap(&tm_w);
+        prefetch_tensormap(&tm_wt);
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4 * kSubs); }
         fence_mbar_init();
@@ -178,28 +364,31 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     gb[q] = g < a.n_groups ? b : a.B;                   // past the end: an all-zero box
                     gc[q] = g < a.n_groups ? (g - b * a.groups_per_img) * 32 : 0;
                 }
-                for (int nt = 0; nt < a.n_ntiles; ++nt)
+                for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                    const bool last = nt == a.n_ntiles - 1;             // the last channel tile is only n_last channels wide
+                    const uint32_t bytes = kABytes + (uint32_t)(last ? a.n_last : kBlockN) * 128u;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char* sa = smem + (size_t)stage * kStageBytes;
-                        mbar_arrive_expect_tx(&full[stage], kStageBytes);
+                        mbar_arrive_expect_tx(&full[stage], bytes);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) tma_load_3d(sa + q * kGroupBytes, &tm_x, gc[q], kb * kBlockK, gb[q], &full[stage]);
-                        tma_load_2d(sa + kABytes, &tm_w, kb * kBlockK, nt * kBlockN, &full[stage]);
+                        tma_load_2d(sa + kABytes, last ? &tm_wt : &tm_w, kb * kBlockK, nt * kBlockN, &full[stage]);
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
+                }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
-            // instruction descriptor: D fp32, A/B tf32, A MN-major (cells contiguous), B K-major, M = 128, N = 256
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
-                             ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+            // A/B tf32, A MN-major (cells contiguous), B K-major, M = 128, N = 256 (n_last for the last channel tile)
+            const uint32_t idesc_full = mma_idesc(2u, 1u, kBlockN), idesc_last = mma_idesc(2u, 1u, a.n_last);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
                 for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                    const uint32_t idesc = nt == a.n_ntiles - 1 ? idesc_last : idesc_full;
                     mbar_wait(&tempty[acc], acc_phase ^ 1u);             // the epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)acc * kBlockN;
@@ -214,7 +403,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                             // B (K-major): 8 channel rows of 128 B per atom (1024 B), K advanced by 32 B inside the row
                             const uint64_t da = smem_desc(sa + kk * 1024, kGroupBytes, 512, 1);
                             const uint64_t db = smem_desc(sb + kk * kUmmaK * 4, 16, 1024, 2);
-                            tc_mma_tf32(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+                            tc_mma<0>(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
                         }
                         tc_commit(&empty[stage]);                        // the stage is free once these MMAs have read it
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -225,146 +414,187 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                 }
         }
     } else {
-        // ------------------------------ epilogue ------------------------------
-        // kEpiSubs warps share each TMEM lane quadrant (32 cells): the decode channels go to sub-warp 0 and limb window
-        // ei to sub-warp ei % kEpiSubs, which loads only the 8-column groups that touch its windows.  A window's running
-        // arg-max thus lives in ONE thread from its first to its last channel, across channel tiles, and the epilogue
-        // of a tile takes 1/kEpiSubs of the time (with one warp per quadrant it was 3.5x the MMA time of a tile).
-        const int ew = warp & 3;                     // the TMEM lane quadrant this warp may read
-        const int sub = (warp - 2) >> 2;             // which of the quadrant's warps
-        const int et = tid - 64;                     // 0 .. among the epilogue threads
-        constexpr int n_sub = kSubs, n_et = 128 * kSubs;   // windows longer than a channel tile keep ONE sub-warp busy at a time
-                                                     // whatever their number (measured at S = 441: 1 206 us with one, 1 381 us
-                                                     // with three), short windows (S = 81) spread over all three (610 -> 544 us):
-                                                     // the launcher picks the instantiation by window size
-        const bool emit = a.emit_logits != nullptr || a.emit_head != nullptr;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            const int g = tile * 4 + ew;
-            const int b = g / a.groups_per_img;
-            const int cell = (g - b * a.groups_per_img) * 32 + lane;
-            const bool valid = g < a.n_groups && cell < a.HW;
-            // Running state of the limb window this thread is in: m = largest logit so far (+inf once a NaN has been
-            // taken: nothing may follow the first NaN), idx = the arg-max so far and bx = the logit it stands on (bx <= m:
-            // a larger logit whose sigmoid TIES with the standing one does not move the arg-max).  A window starts from
-            // (-inf, -inf, 0): sigmoid(-inf) = 0 stands until something beats it — the first column is no special case.
-            float m = -INFINITY, bx = -INFINITY;
-            int idx = 0;
-            // One limb column at window position aw.  A logit above the running maximum beats the standing arg-max iff
-            // sigmoid(x) > sigmoid(bx) (numpy sees sigmoid values).  For x - m > 0.01 and |x| <= 8 it certainly does:
-            // sigmoid' >= 3.3e-4 on [-8.01, 8], so the sigmoids are >= 3.3e-6 apart — tens of ulps, far beyond either one's
-            // evaluation error — and m >= bx: that case is three selects, no branch.  Only the rest (near-ties, the
-            // saturated tails, NaN, +-inf) branches out to evaluate the two sigmoids.
-            auto limb_column = [&](float x, int aw) {
-                const bool gt = !(x <= m);
-                const bool fast = gt && __fsub_rn(x, m) > 0.01f && fabsf(x) <= 8.0f;
-                idx = fast ? aw : idx;
-                bx = fast ? x : bx;
-                if (gt && !fast) {
-                    if (beats_in_sigmoid(x, bx)) { idx = aw; bx = x; }
-                    m = (x != x) ? INFINITY : x;
-                }
-                m = fast ? x : m;
-            };
-            auto window_end = [&](int ei) {
-                if (valid) a.amax[((size_t)b * a.E + ei) * a.HW + cell] = (uint16_t)idx;
-                idx = 0; m = -INFINITY; bx = -INFINITY;
-            };
-            // limb window and position of channel c >= n_dec (uniform; exact magic division, c - n_dec < 2^22)
-            auto window_of = [&](int c, int& ei, int& aw) {
-                const int p = c - a.n_dec;
-                ei = (int)(((unsigned long long)(unsigned)p * a.magic_S) >> 32);
-                aw = p - ei * a.S;
-            };
-            // does the 8-column group at channel c0 hold a column of this sub-warp?
-            auto mine = [&](int c0) -> bool {
-                const int c1 = min(c0 + 7, a.C - 1);
-                if (c0 < a.n_dec && sub == 0) return true;
-                if (c1 < a.n_dec) return false;
-                int e0, e1, aw;
-                window_of(max(c0, a.n_dec), e0, aw);
-                window_of(c1, e1, aw);
-                return e0 % n_sub == sub || e1 % n_sub == sub || e1 - e0 >= n_sub;
-            };
-            // eight columns starting at channel c0, biases at sbc
-            auto group = [&](const uint32_t* r, int c0, const float* sbc) {
-                if (!emit && c0 >= a.n_dec && c0 + 8 <= a.C) {
-                    int ei, aw;
-                    window_of(c0, ei, aw);
-                    if (aw + 8 <= a.S) {                                  // all eight in window ei — this sub-warp's, or mine() lied
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) limb_column(__fadd_rn(__uint_as_float(r[j]), sbc[j]), aw + j);
-                        if (aw + 8 == a.S) window_end(ei);
-                        return;
-                    }
-                }
-                // decode channels, a window boundary, the ragged last group, or a run that also emits logits / the head
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = c0 + j;
-                    if (c >= a.C) break;                                  // uniform
-                    int ei = 0, aw = 0;
-                    const bool limb = c >= a.n_dec;
-                    if (limb) window_of(c, ei, aw);
-                    if ((limb ? ei % n_sub : 0) != sub) continue;         // uniform: another sub-warp's column
-                    const float x = __fadd_rn(__uint_as_float(r[j]), sbc[j]);
-                    const size_t at = ((size_t)b * a.C + c) * a.HW + cell;
-                    if (a.emit_logits && valid) a.emit_logits[at] = x;
-                    if (!limb || a.emit_head) {
-                        const float sg = sigmoid_f32(x);
-                        if (!limb && valid) a.dec[((size_t)b * a.n_dec + c) * a.HW + cell] = sg;
-                        if (a.emit_head && valid) a.emit_head[at] = sg;
-                    }
-                    if (limb) {
-                        limb_column(x, aw);
-                        if (aw + 1 == a.S) window_end(ei);
-                    }
-                }
-            };
-            for (int nt = 0; nt < a.n_ntiles; ++nt) {
-                // the tile's bias values, once per channel tile (double-buffered on the accumulator parity: whoever
-                // overwrites a buffer has passed the next tile's barrier, i.e. everybody is done reading it)
-                float* sb = s_bias + acc * kBlockN;
-                for (int i = et; i < kBlockN; i += n_et) {
-                    const int c = nt * kBlockN + i;
-                    sb[i] = (a.bias && c < a.C) ? __ldg(a.bias + c) : -0.0f;       // x + (-0) == x, bit for bit
-                }
-                named_bar_sync(1, n_et);
-                mbar_wait(&tfull[acc], acc_phase);
-                tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN);
-                const int c_tile = nt * kBlockN;
-                const int n_cols = min(kBlockN, a.C - c_tile);            // > 0
-                // this sub-warp's groups, the next one's TMEM load in flight while the current one is processed
-                uint32_t cur[8], nxt[8];
-                int c8 = 0;
-                while (c8 < n_cols && !mine(c_tile + c8)) c8 += 8;
-                if (c8 < n_cols) tmem_ld8_issue(t_row + (uint32_t)c8, nxt);
-#pragma unroll 1
-                while (c8 < n_cols) {
-                    tmem_ld8_wait(nxt);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-                    int n8 = c8 + 8;
-                    while (n8 < n_cols && !mine(c_tile + n8)) n8 += 8;
-                    if (n8 < n_cols) tmem_ld8_issue(t_row + (uint32_t)n8, nxt);
-                    group(cur, c_tile + c8, sb + c8);
-                    c8 = n8;
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
-            }
-        }
+        head_epilogue<kSubs, false>(a, tmem_base, tfull, tempty);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------ 16-bit path: packed K-major operands ------------------------------
+// Activations [B * HW][Cin] and weights [C][Cin] in fp16 or bf16, both K-major (input channels contiguous: what
+// head_pack_kernel writes, or a channels_last 16-bit tensor of the network itself), kind::f16 MMAs at twice the TF32
+// rate on half the operand bytes.  A tile is 128 consecutive rows of the flattened (image, cell) list — no padding
+// of H*W to a multiple of 32 — and its activations (Cin <= 512: at most 128 KB) are loaded ONCE and stay in shared
+// memory for all channel tiles; only the weights stream through a ring.  Each k-block slot of the resident A tile has
+// its own full/empty barrier pair, so the next tile's activations stream in right behind the last channel tile's
+// sweep over the slots instead of after it.
+constexpr int kBlockK16 = 64;                // 16-bit elements per 128-byte swizzle row
+constexpr int kUmmaK16 = 16;
+constexpr int kMaxKBlocks16 = 8;             // Cin <= 512
+constexpr int kA16Bytes = kBlockM * 128;     // one k-block of the A tile: 16 KB
+constexpr int kB16Bytes = kBlockN * 128;     // one stage of the weight ring: 32 KB
+constexpr int kMaxBStages = 6;
+constexpr int kBar16Bytes = 384;
+
+template <int kSubs>
+__global__ void __launch_bounds__(64 + 128 * kSubs, 1)
+head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                          const __grid_constant__ CUtensorMap tm_wt, HeadArgs a, int pdl) {
+    extern __shared__ __align__(1024) unsigned char smem16[];
+    unsigned char* sA = smem16;                                               // [n_kblocks][16 KB]
+    unsigned char* sB = smem16 + (size_t)a.n_kblocks * kA16Bytes;             // [n_bstages][32 KB]
+    uint64_t* afull = reinterpret_cast<uint64_t*>(sB + (size_t)a.n_bstages * kB16Bytes);
+    uint64_t* aempty = afull + kMaxKBlocks16;
+    uint64_t* bfull = aempty + kMaxKBlocks16;
+    uint64_t* bempty = bfull + kMaxBStages;
+    uint64_t* tfull = bempty + kMaxBStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0 && lane == 0) {
+        if (smem_u32(smem16) & 1023u) __trap();      // the 128-byte swizzle atoms need the 1024-byte alignment asked for
+        prefetch_tensormap(&tm_x);
+        prefetch_tensormap(&tm_w);
+        prefetch_tensormap(&tm_wt);
+        for (int s = 0; s < kMaxKBlocks16; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+        for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4 * kSubs); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (pdl & PDL_WAIT_START) pdl_wait();            // the packed operands come from the kernel before us
+    if (pdl & PDL_TRIGGER) pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, a_phase = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                    const bool last = nt == a.n_ntiles - 1;
+                    const uint32_t b_bytes = (uint32_t)(last ? a.n_last : kBlockN) * 128u;
+                    for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                        if (nt == 0) {                                   // this tile's activations, k-block by k-block
+                            mbar_wait(&aempty[kb], a_phase ^ 1u);
+                            mbar_arrive_expect_tx(&afull[kb], kA16Bytes);
+                            tma_load_2d(sA + (size_t)kb * kA16Bytes, &tm_x, kb * kBlockK16, tile * kBlockM, &afull[kb]);
+                        }
+                        mbar_wait(&bempty[stage], phase ^ 1u);
+                        mbar_arrive_expect_tx(&bfull[stage], b_bytes);
+                        tma_load_2d(sB + (size_t)stage * kB16Bytes, last ? &tm_wt : &tm_w, kb * kBlockK16, nt * kBlockN, &bfull[stage]);
+                        if (++stage == a.n_bstages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                a_phase ^= 1u;
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        if (lane == 0) {
+            const uint32_t fmt = a.bf16 ? 1u : 0u;
+            const uint32_t idesc_full = mma_idesc(fmt, 0u, kBlockN), idesc_last = mma_idesc(fmt, 0u, a.n_last);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                    const bool last = nt == a.n_ntiles - 1;
+                    const uint32_t idesc = last ? idesc_last : idesc_full;
+                    mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)acc * kBlockN;
+                    for (int kb = 0; kb < a.n_kblocks; ++kb) {
+                        if (nt == 0) mbar_wait(&afull[kb], a_phase);
+                        mbar_wait(&bfull[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(sA + (size_t)kb * kA16Bytes), sb = smem_u32(sB + (size_t)stage * kB16Bytes);
+#pragma unroll
+                        for (int kk = 0; kk < kBlockK16 / kUmmaK16; ++kk) {
+                            // both K-major: 8 rows of 128 B per swizzle atom (1024 B), K advanced by 32 B inside the row
+                            const uint64_t da = smem_desc(sa + kk * kUmmaK16 * 2, 16, 1024, 2);
+                            const uint64_t db = smem_desc(sb + kk * kUmmaK16 * 2, 16, 1024, 2);
+                            tc_mma<1>(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(&bempty[stage]);
+                        if (last) tc_commit(&aempty[kb]);                // the next tile's k-block may land here
+                        if (++stage == a.n_bstages) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(&tfull[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
+                a_phase ^= 1u;
+            }
+        }
+    } else {
+        head_epilogue<kSubs, true>(a, tmem_base, tfull, tempty);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------ operand packing for the 16-bit path ------------------------------
+// feat [B][Cin][HW] fp32 (NCHW) -> xt [B * HW][Cin] T (round to nearest even), weight [C][Cin] fp32 -> wt [C][Cin] T.
+// Blocks [0, n_feat_blocks): one 64-channel x 32-cell tile each, transposed through shared memory (128-byte reads along
+// the cells, 128-byte writes along the channels); the blocks after them convert the weights.
+template <typename T> __device__ __forceinline__ T narrow(float v);
+template <> __device__ __forceinline__ __half narrow<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 narrow<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ uint32_t bits16(__half v) { return __half_as_ushort(v); }
+__device__ __forceinline__ uint32_t bits16(__nv_bfloat16 v) { return __bfloat16_as_ushort(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_pack_kernel(const float* __restrict__ feat, const float* __restrict__ weight, T* __restrict__ xt, T* __restrict__ wt,
+                 int Cin, int HW, int chunks_per_img, int kchunks, int n_feat_blocks, size_t n_weight) {
+    __shared__ float tile[64][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((int)blockIdx.x < n_feat_blocks) {
+        const int kc = blockIdx.x % kchunks;
+        const int t = blockIdx.x / kchunks;
+        const int b = t / chunks_per_img, cc = t - b * chunks_per_img;
+        const int cell = cc * 32 + lane;
+        const float* src = feat + ((size_t)b * Cin + (size_t)kc * 64) * HW;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = cell < HW ? __ldg(src + (size_t)(warp * 8 + i) * HW + cell) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[warp * 8 + i][lane] = v[i];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cl = warp * 4 + i, c = cc * 32 + cl;
+            if (c < HW) {
+                const uint32_t pair = bits16(narrow<T>(tile[2 * lane][cl])) | (bits16(narrow<T>(tile[2 * lane + 1][cl])) << 16);
+                *reinterpret_cast<uint32_t*>(xt + ((size_t)b * HW + c) * Cin + (size_t)kc * 64 + 2 * lane) = pair;
+            }
+        }
+    } else {
+        const size_t n4 = n_weight / 4;
+        const size_t stride = (size_t)(gridDim.x - n_feat_blocks) * blockDim.x;
+        for (size_t i = (size_t)(blockIdx.x - n_feat_blocks) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(weight) + i);
+            *reinterpret_cast<uint2*>(wt + 4 * i) = make_uint2(bits16(narrow<T>(w.x)) | (bits16(narrow<T>(w.y)) << 16),
+                                                                bits16(narrow<T>(w.z)) | (bits16(narrow<T>(w.w)) << 16));
+        }
     }
 }
 
@@ -390,13 +620,89 @@ cudaError_t encoder(EncodeTiledFn* out) {
     *out = g_encode;
     return cudaSuccess;
 }
+
+// 2-D row-major matrix [rows][cols] of `elem_bytes`-wide elements, box = box_cols x box_rows, 128-byte swizzle
+bool map_2d(EncodeTiledFn enc, CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t cols, uint64_t rows,
+            uint32_t box_cols, uint32_t box_rows) {
+    const cuuint64_t dim[2] = {cols, rows};
+    const cuuint64_t stride[1] = {cols * (uint64_t)elem_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t es[2] = {1, 1};
+    return enc(m, dt, 2, const_cast<void*>(base), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t head16_smem_bytes(int n_kblocks, int n_bstages) {
+    return (size_t)n_kblocks * kA16Bytes + (size_t)n_bstages * kB16Bytes + kBar16Bytes;
+}
+
+void fill_common(HeadArgs& a, const Geom& g, int Cin, const float* bias, float* dec, unsigned long long* keys, float* emit_logits, float* emit_head) {
+    a.B = g.B; a.HW = g.HW; a.Cin = Cin; a.C = g.C; a.n_dec = 6 * g.K; a.S = g.S; a.E = g.E;
+    a.n_ntiles = (g.C + kBlockN - 1) / kBlockN;
+    a.n_last = ((g.C - (a.n_ntiles - 1) * kBlockN) + 15) & ~15;            // 16 .. 256
+    a.magic_S = g.S <= 1 ? 0u : (uint32_t)(((1ull << 32) + g.S - 1) / g.S);
+    a.bias = bias; a.dec = dec; a.keys = keys; a.emit_logits = emit_logits; a.emit_head = emit_head;
+    a.n_rows = g.B * g.HW; a.n_bstages = 0; a.bf16 = 0;
+    a.groups_per_img = (g.HW + 31) / 32;
+    a.n_groups = g.B * a.groups_per_img;
+}
+template <bool k16, int kSubs>
+cudaError_t launch_gemm_n(int grid, size_t smem, cudaStream_t st, bool pdl_attr, const CUtensorMap& tm_x, const CUtensorMap& tm_w,
+                          const CUtensorMap& tm_wt, const HeadArgs& a, int pdl_bits) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(64 + 128 * kSubs);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_attr ? 1 : 0;
+    if constexpr (k16) return cudaLaunchKernelEx(&cfg, head_gemm16_argmax_kernel<kSubs>, tm_x, tm_w, tm_wt, a, pdl_bits);
+    else return cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel<kSubs>, tm_x, tm_w, tm_wt, a, pdl_bits);
+}
+// epilogue warps per TMEM lane quadrant: 1 .. kMaxEpiSubs
+template <bool k16>
+cudaError_t launch_gemm(int subs, int grid, size_t smem, cudaStream_t st, bool pdl_attr, const CUtensorMap& tm_x, const CUtensorMap& tm_w,
+                        const CUtensorMap& tm_wt, const HeadArgs& a, int pdl_bits) {
+    switch (subs) {
+        case 1: return launch_gemm_n<k16, 1>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+        case 2: return launch_gemm_n<k16, 2>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+        case 3: return launch_gemm_n<k16, 3>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+        default: return launch_gemm_n<k16, 4>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+    }
+}
+template <bool k16>
+cudaError_t set_smem_attr(int bytes) {
+    cudaError_t e;
+    if constexpr (k16) {
+        if ((e = cudaFuncSetAttribute(head_gemm16_argmax_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(head_gemm16_argmax_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(head_gemm16_argmax_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        return cudaFuncSetAttribute(head_gemm16_argmax_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    } else {
+        if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+        return cudaFuncSetAttribute(head_gemm_argmax_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    }
+}
+cudaError_t finalize_amax(const unsigned long long* keys, uint16_t* amax, const Geom& g, cudaStream_t st) {
+    const size_t n = (size_t)g.B * g.E * g.HW;
+    if (n == 0) return cudaSuccess;
+    head_amax_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, amax, n);
+    return cudaGetLastError();
+}
 }  // namespace
 
-size_t head_smem_bytes() { return (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers, TMEM slot */ + 2 * kBlockN * sizeof(float) /* bias */; }
+size_t head_keys_bytes(const Geom& g) { return (size_t)g.B * g.E * g.HW * sizeof(unsigned long long); }
+
+size_t head_smem_bytes() { return (size_t)kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers, TMEM slot */; }
 
 cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int Cin, const Geom& g,
-                                    float* dec, uint16_t* amax, float* emit_logits, float* emit_head, cudaStream_t st,
-                                    bool pdl_attr, int pdl_bits) {
+                                    float* dec, uint16_t* amax, unsigned long long* keys, float* emit_logits, float* emit_head,
+                                    cudaStream_t st, bool pdl_attr, int pdl_bits, int subs) {
     if (g.B == 0) return cudaSuccess;
     if (Cin % kBlockK != 0 || g.HW % 4 != 0) return cudaErrorInvalidValue;
     int dev = 0, sms = 0;
@@ -406,7 +712,12 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
     EncodeTiledFn enc = nullptr;
     if ((e = encoder(&enc)) != cudaSuccess) return e;
 
-    CUtensorMap tm_x, tm_w;
+    HeadArgs a;
+    fill_common(a, g, Cin, bias, dec, keys, emit_logits, emit_head);
+    a.n_tiles = (a.n_groups + 3) / 4;
+    a.n_kblocks = Cin / kBlockK;
+
+    CUtensorMap tm_x, tm_w, tm_wt;
     {   // activations [B][Cin][HW] fp32: box = 32 cells x 32 input channels of one image
         const cuuint64_t dim[3] = {(cuuint64_t)g.HW, (cuuint64_t)Cin, (cuuint64_t)g.B};
         const cuuint64_t stride[2] = {(cuuint64_t)g.HW * 4, (cuuint64_t)Cin * g.HW * 4};
@@ -416,47 +727,91 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    {   // weights [C][Cin] fp32: box = 32 input channels x 256 output channels
-        const cuuint64_t dim[2] = {(cuuint64_t)Cin, (cuuint64_t)g.C};
-        const cuuint64_t stride[1] = {(cuuint64_t)Cin * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockN};
-        const cuuint32_t es[2] = {1, 1};
-        if (enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(weight), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return cudaErrorInvalidValue;
-    }
-    HeadArgs a;
-    a.B = g.B; a.HW = g.HW; a.Cin = Cin; a.C = g.C; a.n_dec = 6 * g.K; a.S = g.S; a.E = g.E;
-    a.groups_per_img = (g.HW + 31) / 32;
-    a.n_groups = g.B * a.groups_per_img;
-    a.n_tiles = (a.n_groups + 3) / 4;
-    a.n_ntiles = (g.C + kBlockN - 1) / kBlockN;
-    a.n_kblocks = Cin / kBlockK;
-    a.magic_S = g.S <= 1 ? 0u : (uint32_t)(((1ull << 32) + g.S - 1) / g.S);
-    a.bias = bias; a.dec = dec; a.amax = amax; a.emit_logits = emit_logits; a.emit_head = emit_head;
+    // weights [C][Cin] fp32: box = 32 input channels x 256 output channels (x n_last for the last channel tile)
+    if (!map_2d(enc, &tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, weight, Cin, g.C, kBlockK, kBlockN) ||
+        !map_2d(enc, &tm_wt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, weight, Cin, g.C, kBlockK, a.n_last))
+        return cudaErrorInvalidValue;
 
     const size_t smem = head_smem_bytes();
-    const bool three = g.S <= 128;                    // short limb windows: three epilogue warps per lane quadrant
     {
         std::lock_guard<std::mutex> lock(g_enc_mu);
         if (dev >= 0 && dev < 64 && !g_attr_done[dev]) {
-            if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-            if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<kMaxEpiSubs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            if ((e = set_smem_attr<false>((int)smem)) != cudaSuccess) return e;
             g_attr_done[dev] = true;
         }
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)std::min(sms, a.n_tiles));
-    cfg.blockDim = dim3(64 + 128 * (three ? kMaxEpiSubs : 1));
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_attr ? 1 : 0;
-    return three ? cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel<kMaxEpiSubs>, tm_x, tm_w, a, pdl_bits)
-                 : cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel<1>, tm_x, tm_w, a, pdl_bits);
+    if ((e = cudaMemsetAsync(keys, 0, head_keys_bytes(g), st)) != cudaSuccess) return e;
+    if ((e = launch_gemm<false>(subs, std::min(sms, a.n_tiles), smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits)) != cudaSuccess) return e;
+    return finalize_amax(keys, amax, g, st);
+}
+
+bool head16_supported(int Cin, const Geom& g) {
+    return Cin >= kBlockK16 && Cin % kBlockK16 == 0 && Cin <= kMaxKBlocks16 * kBlockK16 && (long long)g.B * g.HW < (1ll << 31) - kBlockM;
+}
+
+size_t head16_packed_feat_bytes(int Cin, const Geom& g) { return (size_t)g.B * g.HW * Cin * 2; }
+size_t head16_packed_weight_bytes(int Cin, const Geom& g) { return (size_t)g.C * Cin * 2; }
+
+// feat: fp32 NCHW when `feat_nchw_f32` (packed into `xt` first), else 16-bit [B * HW][Cin] in the operand type, used in place
+cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, const float* weight, const float* bias, int Cin, bool bf16,
+                                      const Geom& g, void* xt, void* wt, float* dec, uint16_t* amax, unsigned long long* keys,
+                                      float* emit_logits, float* emit_head, cudaStream_t st, int pdl_bits, int subs) {
+    if (g.B == 0) return cudaSuccess;
+    if (!head16_supported(Cin, g)) return cudaErrorInvalidValue;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    EncodeTiledFn enc = nullptr;
+    if ((e = encoder(&enc)) != cudaSuccess) return e;
+
+    HeadArgs a;
+    fill_common(a, g, Cin, bias, dec, keys, emit_logits, emit_head);
+    a.n_tiles = (a.n_rows + kBlockM - 1) / kBlockM;
+    a.n_kblocks = Cin / kBlockK16;
+    a.bf16 = bf16 ? 1 : 0;
+    int max_smem = 0;
+    if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    a.n_bstages = kMaxBStages;
+    while (a.n_bstages > 2 && head16_smem_bytes(a.n_kblocks, a.n_bstages) > (size_t)max_smem) --a.n_bstages;
+    const size_t smem = head16_smem_bytes(a.n_kblocks, a.n_bstages);
+    if (smem > (size_t)max_smem) return cudaErrorInvalidValue;
+
+    if ((e = cudaMemsetAsync(keys, 0, head_keys_bytes(g), st)) != cudaSuccess) return e;
+    // 1. pack: activations (unless they already are K-major 16-bit) and weights
+    {
+        const int chunks = (g.HW + 31) / 32, kchunks = Cin / 64;
+        const int n_feat_blocks = feat_nchw_f32 ? g.B * chunks * kchunks : 0;
+        const size_t n_weight = (size_t)g.C * Cin;
+        const int n_w_blocks = (int)std::min<size_t>((n_weight / 4 + 255) / 256, 4 * (size_t)sms);
+        const float* f32 = feat_nchw_f32 ? static_cast<const float*>(feat) : nullptr;
+        if (bf16)
+            head_pack_kernel<__nv_bfloat16><<<n_feat_blocks + n_w_blocks, 256, 0, st>>>(f32, weight, static_cast<__nv_bfloat16*>(xt), static_cast<__nv_bfloat16*>(wt),
+                                                                                        Cin, g.HW, chunks, kchunks, n_feat_blocks, n_weight);
+        else
+            head_pack_kernel<__half><<<n_feat_blocks + n_w_blocks, 256, 0, st>>>(f32, weight, static_cast<__half*>(xt), static_cast<__half*>(wt),
+                                                                                 Cin, g.HW, chunks, kchunks, n_feat_blocks, n_weight);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    // 2. GEMM + epilogue
+    const void* x16 = feat_nchw_f32 ? xt : feat;
+    const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap tm_x, tm_w, tm_wt;
+    if (!map_2d(enc, &tm_x, dt, 2, x16, Cin, (uint64_t)a.n_rows, kBlockK16, kBlockM) ||
+        !map_2d(enc, &tm_w, dt, 2, wt, Cin, g.C, kBlockK16, kBlockN) ||
+        !map_2d(enc, &tm_wt, dt, 2, wt, Cin, g.C, kBlockK16, a.n_last))
+        return cudaErrorInvalidValue;
+    {
+        std::lock_guard<std::mutex> lock(g_enc_mu);
+        static bool done16[64] = {};
+        if (dev >= 0 && dev < 64 && !done16[dev]) {
+            if ((e = set_smem_attr<true>(max_smem)) != cudaSuccess) return e;
+            done16[dev] = true;
+        }
+    }
+    // its prologue (barriers, TMEM, tensor maps) runs under the pack kernel's tail
+    if ((e = launch_gemm<true>(subs, std::min(sms, a.n_tiles), smem, st, true, tm_x, tm_w, tm_wt, a, pdl_bits | PDL_WAIT_START)) != cudaSuccess) return e;
+    return finalize_amax(keys, amax, g, st);
 }
 
 }  // namespace ppn

@@ -39,6 +39,7 @@ struct Tuning {
     int encode_sweep = 1;              // target encoder: limb tensors by the address-ordered persistent sweep (0: one CTA per image part)
     int encode_ctas_per_sm = 6;
     int argmax_dry = 0;                // ring kernels only move the bytes (no compares, no stores): the read ceiling of this ring
+    int head_subs = 3;                 // fused head: epilogue warps per TMEM lane quadrant (1 .. 4)
     int parse_overlap = 2;             // 0 serial; 1 decode+NMS on a side stream beside the arg-max;
                                        // 2 one stream, programmatic dependent launches (PDL chain)
 };
@@ -132,9 +133,21 @@ void chain_break(cudaStream_t st);      // ... was something else: the next over
 // feat [B, Cin, H, W] fp32, weight [C, Cin] fp32, bias [C] or nullptr  ->  dec [B, 6K, HW] = sigmoid of the decode
 // channels, amax [B, E, HW]; optional emit_logits / emit_head [B, C, HW] for parity tests (model.py:85, 133-136).
 size_t head_smem_bytes();
+// keys: scratch of head_keys_bytes() (the epilogue's running maxima; the launcher clears it and converts it to amax);
+// subs: epilogue warps per TMEM lane quadrant (1 .. 4).  Launches: memset, [pack,] GEMM, finalize.
+size_t head_keys_bytes(const Geom& g);
 cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, const float* bias, int Cin, const Geom& g,
-                                    float* dec, uint16_t* amax, float* emit_logits, float* emit_head, cudaStream_t st,
-                                    bool pdl_attr, int pdl_bits);
+                                    float* dec, uint16_t* amax, unsigned long long* keys, float* emit_logits, float* emit_head,
+                                    cudaStream_t st, bool pdl_attr, int pdl_bits, int subs);
+// The 16-bit operand path: fp16 / bf16 K-major operands.  feat = fp32 NCHW (packed into `xt` [B * HW][Cin] by a
+// pre-pass) or, when !feat_nchw_f32, already [B * HW][Cin] in the operand type (channels_last) and read in place;
+// wt [C][Cin] receives the converted weights.  Two launches (pack, GEMM as its programmatic dependent).
+bool head16_supported(int Cin, const Geom& g);
+size_t head16_packed_feat_bytes(int Cin, const Geom& g);
+size_t head16_packed_weight_bytes(int Cin, const Geom& g);
+cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, const float* weight, const float* bias, int Cin, bool bf16,
+                                      const Geom& g, void* xt, void* wt, float* dec, uint16_t* amax, unsigned long long* keys,
+                                      float* emit_logits, float* emit_head, cudaStream_t st, int pdl_bits, int subs);
 
 // ---- training-target encoder (ppn_encode.cu) ----------------------------------------------------------
 struct EdgeTable { uint8_t src[256]; uint8_t dst[256]; };

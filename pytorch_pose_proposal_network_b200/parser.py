@@ -360,10 +360,24 @@ class PoseParser:
         return out
 
     # ---- the network head fused in: conv3 (1x1) + sigmoid + parse (model.py:85, 133-136) ------------ #
-    def _check_features(self, feat, weight, bias):
+    _OPERANDS = {"tf32": _lib.GEMM_TF32, "f16": _lib.GEMM_F16, "bf16": _lib.GEMM_BF16}
+
+    def _check_features(self, feat, weight, bias, operand="tf32"):
+        """-> (B, Cin, PPNHeadOptions).  feat: fp32 NCHW contiguous, or — 16-bit operands only — a 16-bit tensor of
+        the operand type whose memory is [B, H, W, Cin] (torch.channels_last), read in place."""
         cfg = self.cfg
-        if feat.dtype != torch.float32 or feat.dim() != 4 or tuple(feat.shape[2:]) != (cfg.H, cfg.W) or not feat.is_contiguous():
-            raise ValueError(f"feat must be contiguous fp32 [B, Cin, {cfg.H}, {cfg.W}], got {feat.dtype} {tuple(feat.shape)}")
+        if operand not in self._OPERANDS:
+            raise ValueError(f"operand must be one of {sorted(self._OPERANDS)}, got {operand!r}")
+        if feat.dim() != 4 or tuple(feat.shape[2:]) != (cfg.H, cfg.W):
+            raise ValueError(f"feat must be [B, Cin, {cfg.H}, {cfg.W}], got {tuple(feat.shape)}")
+        want16 = {"f16": torch.float16, "bf16": torch.bfloat16}.get(operand)
+        if feat.dtype == torch.float32 and feat.is_contiguous():
+            layout = _lib.FEAT_NCHW_F32
+        elif want16 is not None and feat.dtype == want16 and feat.permute(0, 2, 3, 1).is_contiguous():
+            layout = _lib.FEAT_NHWC_16
+        else:
+            raise ValueError("feat must be contiguous fp32 NCHW" + (f" or channels_last {want16}" if want16 else "") +
+                             f", got {feat.dtype} with strides {feat.stride()}")
         Cin = feat.shape[1]
         w2 = weight.reshape(weight.shape[0], -1)
         if weight.dtype != torch.float32 or tuple(w2.shape) != (cfg.C, Cin) or not w2.is_contiguous():
@@ -373,7 +387,7 @@ class PoseParser:
         for t in (feat, weight, bias):
             if t is not None and t.device != self.device:
                 raise ValueError(f"tensor on {t.device}, parser on {self.device}")
-        return feat.shape[0], Cin
+        return feat.shape[0], Cin, _lib.PPNHeadOptions(self._OPERANDS[operand], layout)
 
     def _emit_buffers(self, B: int, emit: bool):
         if not emit:
@@ -382,41 +396,54 @@ class PoseParser:
         return (torch.empty(B, cfg.C, cfg.H, cfg.W, dtype=torch.float32, device=self.device),
                 torch.empty(B, cfg.C, cfg.H, cfg.W, dtype=torch.float32, device=self.device))
 
-    def head_gemm_argmax(self, feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, emit: bool = False):
-        """The fused head kernel alone (``ppn_head_gemm_argmax``): 1x1 convolution on the tensor cores, sigmoid and
+    def _head_workspace(self, B: int, Cin: int, opt) -> torch.Tensor:
+        need = C.c_size_t()
+        _lib.check(self.lib.ppn_head_workspace_bytes_opt(C.byref(self._shape(B)), Cin, C.byref(opt), C.byref(need)),
+                   "ppn_head_workspace_bytes_opt")
+        if getattr(self, "_head_ws", None) is None or self._head_ws.numel() < need.value:
+            self._head_ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+        return self._head_ws
+
+    def head_gemm_argmax(self, feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, emit: bool = False,
+                         operand: str = "tf32"):
+        """The fused head kernel alone (``ppn_head_gemm_argmax_opt``): 1x1 convolution on the tensor cores, sigmoid and
         limb-window arg-max in the epilogue.  -> (dec [B, 6K, H, W] fp32, amax [B, E, H, W] uint16, logits, head);
-        the last two are the convolution output and its sigmoid [B, C, H, W] when ``emit`` (parity tests), else None."""
-        B, Cin = self._check_features(feat, weight, bias)
+        the last two are the convolution output and its sigmoid [B, C, H, W] when ``emit`` (parity tests), else None.
+        ``operand``: "tf32" (fp32 activations read in place), "f16" or "bf16" (see ``parse_features``)."""
+        B, Cin, opt = self._check_features(feat, weight, bias, operand)
         cfg = self.cfg
         dec = torch.empty(B, 6 * cfg.K, cfg.H, cfg.W, dtype=torch.float32, device=self.device)
         amax = torch.empty(B, cfg.E, cfg.H, cfg.W, dtype=torch.uint16, device=self.device)
         logits, head = self._emit_buffers(B, emit)
+        ws = self._head_workspace(B, Cin, opt)
         with self._guard():
-            _lib.check(self.lib.ppn_head_gemm_argmax(feat.data_ptr(), weight.data_ptr(), _ptr(bias), Cin, C.byref(self._shape(B)),
-                                                     dec.data_ptr(), amax.data_ptr(), _ptr(logits), _ptr(head),
-                                                     torch.cuda.current_stream(self.device).cuda_stream), "ppn_head_gemm_argmax")
+            _lib.check(self.lib.ppn_head_gemm_argmax_opt(feat.data_ptr(), weight.data_ptr(), _ptr(bias), Cin, C.byref(self._shape(B)),
+                                                         C.byref(opt), ws.data_ptr(), ws.numel(), dec.data_ptr(), amax.data_ptr(),
+                                                         _ptr(logits), _ptr(head), torch.cuda.current_stream(self.device).cuda_stream),
+                       "ppn_head_gemm_argmax_opt")
         return dec, amax, logits, head
 
     def parse_features(self, feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                       out: Optional[PackedHumans] = None, emit: bool = False):
+                       out: Optional[PackedHumans] = None, emit: bool = False, operand: str = "tf32"):
         """``sigmoid(conv3(feat))`` parsed into humans without the head tensor ever being written
-        (``ppn_head_parse``): feat = the input of the network's last layer [B, Cin, H, W] (model.py:133), weight / bias
-        = ``conv3``'s.  Asynchronous on torch's current stream.  -> PackedHumans, or (PackedHumans, logits, head) when
-        ``emit`` — the kernel then also writes the convolution output and its sigmoid for parity checks."""
-        B, Cin = self._check_features(feat, weight, bias)
+        (``ppn_head_parse_opt``): feat = the input of the network's last layer [B, Cin, H, W] (model.py:133), weight /
+        bias = ``conv3``'s.  ``operand`` picks the tensor-core operand type: "tf32" (default: fp32 activations read in
+        place, the precision of the reference's conv under PyTorch's defaults), "f16" or "bf16" (operands rounded to 16
+        bits, fp32 accumulation — the reference's conv under its AMP setup, main.py:282-289; feat may then also be a
+        channels_last tensor of that type, read in place).  Asynchronous on torch's current stream.
+        -> PackedHumans, or (PackedHumans, logits, head) when ``emit`` — the kernel then also writes the convolution
+        output and its sigmoid for parity checks."""
+        B, Cin, opt = self._check_features(feat, weight, bias, operand)
         if out is None:
             out = self.alloc_output(B)
-        need = C.c_size_t()
-        _lib.check(self.lib.ppn_head_workspace_bytes(C.byref(self._shape(B)), C.byref(need)), "ppn_head_workspace_bytes")
-        if getattr(self, "_head_ws", None) is None or self._head_ws.numel() < need.value:
-            self._head_ws = torch.empty(max(need.value, 256), dtype=torch.uint8, device=self.device)
+        ws = self._head_workspace(B, Cin, opt)
         logits, head = self._emit_buffers(B, emit)
         hs = self._humans_struct(out)
         with self._guard():
-            _lib.check(self.lib.ppn_head_parse(feat.data_ptr(), weight.data_ptr(), _ptr(bias), Cin, C.byref(self._shape(B)),
-                                               C.byref(self.c.params), C.byref(hs), self._head_ws.data_ptr(), self._head_ws.numel(),
-                                               _ptr(logits), _ptr(head), torch.cuda.current_stream(self.device).cuda_stream),
-                       "ppn_head_parse")
+            _lib.check(self.lib.ppn_head_parse_opt(feat.data_ptr(), weight.data_ptr(), _ptr(bias), Cin, C.byref(self._shape(B)),
+                                                   C.byref(self.c.params), C.byref(opt), C.byref(hs), ws.data_ptr(), ws.numel(),
+                                                   _ptr(logits), _ptr(head), torch.cuda.current_stream(self.device).cuda_stream),
+                       "ppn_head_parse_opt")
         return (out, logits, head) if emit else out
 
     # ---- keypoints (what drawing and AP evaluation read off the boxes) ------------------- #

@@ -19,10 +19,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--configs", default="cfg2,native")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--cin", type=int, default=512)
+ap.add_argument("--subs", type=int, default=0, help="epilogue warps per TMEM lane quadrant (tune key head.subs), 0 = library default")
 args = ap.parse_args()
 peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 bf16 = json.load(open(peaks))["bf16_tflops"] if os.path.exists(peaks) else 1590.0
 tf32_peak = bf16 / 2                                     # TF32 runs at half the bf16 rate
+if args.subs:
+    from pytorch_pose_proposal_network_b200 import _lib
+    _lib.tune(head_subs=args.subs)
+    print(f"# head.subs = {args.subs}")
 torch.backends.cudnn.allow_tf32 = True                   # PyTorch's default: the reference's conv3 runs in TF32
 
 
@@ -64,8 +69,29 @@ for name in args.configs.split(","):
 
     t_f, t_u, t_c = timed(fused, args.iters), timed(unfused, args.iters), timed(conv_only, args.iters)
     print(f"{name}: B={B} Cin={Cin} C={cfg.C} grid {cfg.H}x{cfg.W}: {flops / 1e9:.1f} GFLOP per batch")
-    print(f"   fused head+parse   {t_f * 1e3:8.1f} us  {B / t_f / 1e3:8.1f} k img/s  {flops / t_f / 1e9:7.1f} TFLOP/s = {flops / t_f / 1e9 / tf32_peak:.3f} of the TF32 peak "
+    print(f"   TF32 operands (fp32 NCHW activations read in place)")
+    print(f"      fused head+parse   {t_f * 1e3:8.1f} us  {B / t_f / 1e3:8.1f} k img/s  {flops / t_f / 1e9:7.1f} TFLOP/s = {flops / t_f / 1e9 / tf32_peak:.3f} of the TF32 peak "
           f"({tf32_peak:.0f} TF/s = measured bf16 {bf16:.0f} / 2)")
-    print(f"   cuDNN conv (TF32) + sigmoid + ppn_parse   {t_u * 1e3:8.1f} us  {B / t_u / 1e3:8.1f} k img/s   (conv alone {t_c * 1e3:.1f} us = {flops / t_c / 1e9:.1f} TFLOP/s)")
+    print(f"      cuDNN conv (TF32) + sigmoid + ppn_parse   {t_u * 1e3:8.1f} us  {B / t_u / 1e3:8.1f} k img/s   (conv alone {t_c * 1e3:.1f} us = {flops / t_c / 1e9:.1f} TFLOP/s)")
+    if Cin % 64 == 0 and Cin <= 512:
+        for op, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+            feats_cl = [f.to(dt).contiguous(memory_format=torch.channels_last) for f in feats]
+            w4h, bh = w4.to(dt).contiguous(memory_format=torch.channels_last), bias.to(dt)
+
+            def fused16(i):
+                parser.parse_features(feats[i % 3], weight, bias, out=outs[i % 2], operand=op)
+
+            def fused16_cl(i):
+                parser.parse_features(feats_cl[i % 3], weight, bias, out=outs[i % 2], operand=op)
+
+            def conv16(i):
+                torch.nn.functional.conv2d(feats_cl[i % 3], w4h, bh)
+
+            t1, t2, t3 = timed(fused16, args.iters), timed(fused16_cl, args.iters), timed(conv16, args.iters)
+            print(f"   {op} operands, fp32 accumulation (peak {bf16:.0f} TF/s measured)")
+            print(f"      fused head+parse, fp32 NCHW in (pack pre-pass)   {t1 * 1e3:8.1f} us  {B / t1 / 1e3:8.1f} k img/s  {flops / t1 / 1e9:7.1f} TFLOP/s = {flops / t1 / 1e9 / bf16:.3f} of the peak")
+            print(f"      fused head+parse, channels_last {op} in (in place) {t2 * 1e3:8.1f} us  {B / t2 / 1e3:8.1f} k img/s  {flops / t2 / 1e9:7.1f} TFLOP/s = {flops / t2 / 1e9 / bf16:.3f} of the peak")
+            print(f"      cuDNN conv alone ({op}, channels_last)            {t3 * 1e3:8.1f} us  {flops / t3 / 1e9:7.1f} TFLOP/s")
+            del feats_cl
     del feats, outs, parser
     torch.cuda.empty_cache()

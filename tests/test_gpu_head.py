@@ -19,6 +19,12 @@ from tests.test_gpu_parity import assert_packed_equals_oracle, bits, cfg_of, par
 pytestmark = pytest.mark.gpu
 
 ATOL, RTOL = 4e-3, 4e-3
+# 16-bit operands: against the fp32 convolution of the UNROUNDED operands — fp16 keeps TF32's 10
+# mantissa bits, bf16 keeps 7; against the convolution of the operands rounded to 16 bits only the fp32 accumulation
+# of Cin products is left
+TOL16 = {"f16": (4e-3, 4e-3), "bf16": (3e-2, 3e-2)}
+TOL_ACC = (1e-4, 1e-4)
+DT16 = {"f16": torch.float16, "bf16": torch.bfloat16}
 
 
 def geometry(name):
@@ -150,3 +156,91 @@ def test_head_rejects_bad_arguments():
     feat, weight, bias = make_layer(g, 1, 64, seed=1)
     with pytest.raises(ValueError):
         parser.head_gemm_argmax(feat, weight[:-1].contiguous(), bias)
+
+
+@pytest.mark.parametrize("operand", ["f16", "bf16"])
+@pytest.mark.parametrize("name,B,Cin", [("cfg1", 3, 64), ("cfg1", 5, 512), ("cfg2", 9, 256), ("cfg3", 2, 512), ("native", 2, 512)])
+def test_head16_logits_and_epilogue(name, B, Cin, operand):
+    """16-bit operand path: packed K-major operands, resident A tile, narrow last channel tile, rows that cross images."""
+    g = geometry(name)
+    parser = parser_for(g)
+    feat, weight, bias = make_layer(g, B, Cin, seed=150 + B)
+    dec, amax, logits, head = parser.head_gemm_argmax(feat, weight, bias, emit=True, operand=operand)
+    torch.cuda.synchronize()
+    ref = conv_fp32(feat, weight, bias)
+    err = (logits - ref).abs()
+    atol, rtol = TOL16[operand]
+    assert bool((err <= atol + rtol * ref.abs()).all()), f"max |logit error| {float(err.max()):.3e} vs the fp32 convolution"
+    dt = DT16[operand]
+    ref16 = conv_fp32(feat.to(dt).float(), weight.to(dt).float(), bias)
+    err = (logits - ref16).abs()
+    assert bool((err <= TOL_ACC[0] + TOL_ACC[1] * ref16.abs()).all()), \
+        f"max |logit error| {float(err.max()):.3e} vs the convolution of the rounded operands (accumulation only)"
+    check_against_emitted(g, parser, dec, amax, logits, head)
+    dec2, amax2, _, _ = parser.head_gemm_argmax(feat, weight, bias, emit=False, operand=operand)
+    # a channels_last tensor of the operand type is read in place: same operands bit for bit, same result
+    feat_cl = feat.to(dt).contiguous(memory_format=torch.channels_last)
+    dec3, amax3, logits3, _ = parser.head_gemm_argmax(feat_cl, weight, bias, emit=True, operand=operand)
+    torch.cuda.synchronize()
+    assert torch.equal(dec2, dec) and torch.equal(amax2.view(torch.int16), amax.view(torch.int16))
+    assert torch.equal(dec3, dec) and torch.equal(amax3.view(torch.int16), amax.view(torch.int16))
+    assert torch.equal(logits3.view(torch.int32), logits.view(torch.int32))
+
+
+@pytest.mark.parametrize("operand", ["f16", "bf16"])
+@pytest.mark.parametrize("name,B", [("cfg1", 7), ("cfg2", 64), ("cfg3", 8), ("native", 3)])
+def test_head16_parse_matches_oracle_on_emitted_head(name, B, operand):
+    g = geometry(name)
+    parser = parser_for(g)
+    feat, weight, bias = make_layer(g, B, 512, seed=177)
+    packed, logits, head = parser.parse_features(feat, weight, bias, emit=True, operand=operand)
+    torch.cuda.synchronize()
+    ref = c_oracle.parse_batch(head.cpu().numpy(), g)
+    assert int(ref["counts"][:, 2].sum()) > 0, "degenerate test input: no humans"
+    assert_packed_equals_oracle(packed.numpy(), ref, B)
+    two_step = parser.parse(head, out=parser.alloc_output(B)).numpy()
+    plain = parser.parse_features(feat, weight, bias, out=parser.alloc_output(B), operand=operand).numpy()
+    feat_cl = feat.to(DT16[operand]).contiguous(memory_format=torch.channels_last)
+    in_place = parser.parse_features(feat_cl, weight, bias, out=parser.alloc_output(B), operand=operand).numpy()
+    torch.cuda.synchronize()
+    for other in (two_step, plain, in_place):
+        assert np.array_equal(other["count"], packed.numpy()["count"])
+        assert_packed_equals_oracle(other, ref, B)
+
+
+def test_head16_many_tiles_persistent_loop():
+    """More M tiles than SMs: every CTA loops over several tiles (A-slot and accumulator phases wrap)."""
+    g = geometry("cfg2")
+    parser = parser_for(g)
+    B = 400                                                    # 400 * 144 / 128 = 450 tiles on 148 SMs
+    feat, weight, bias = make_layer(g, B, 128, seed=9)
+    dec, amax, logits, head = parser.head_gemm_argmax(feat, weight, bias, emit=True, operand="f16")
+    torch.cuda.synchronize()
+    ref16 = conv_fp32(feat.half().float(), weight.half().float(), bias)
+    err = (logits - ref16).abs()
+    assert bool((err <= TOL_ACC[0] + TOL_ACC[1] * ref16.abs()).all()), f"max |logit error| {float(err.max()):.3e}"
+    dec2, amax2, _, _ = parser.head_gemm_argmax(feat, weight, bias, emit=False, operand="f16")
+    torch.cuda.synchronize()
+    assert torch.equal(dec2, dec) and torch.equal(amax2.view(torch.int16), amax.view(torch.int16))
+    want = torch.argmax(head[:, 6 * g.K:].reshape(B, g.E, g.S, g.H * g.W), dim=2)
+    # torch.argmax picks the first maximum like numpy for distinct values; exact ties are checked on a sample by numpy
+    hs = head[:16].cpu().numpy()[:, 6 * g.K:].reshape(16, g.E, g.S, g.H * g.W)
+    assert np.array_equal(amax2[:16].cpu().numpy().reshape(16, g.E, -1), np.argmax(hs, axis=2).astype(np.uint16))
+    mism = (want != amax2.reshape(B, g.E, -1).to(torch.int64)).float().mean()
+    assert float(mism) < 1e-4, f"{float(mism):.2e} of the arg-max entries differ from torch.argmax"
+
+
+def test_head16_rejects_what_it_cannot_take():
+    from pytorch_pose_proposal_network_b200 import _lib
+    g = geometry("cfg1")
+    parser = parser_for(g)
+    feat, weight, bias = make_layer(g, 1, 96, seed=1)                     # Cin not a multiple of 64
+    with pytest.raises(_lib.PPNError):
+        parser.head_gemm_argmax(feat, weight, bias, operand="f16")
+    feat, weight, bias = make_layer(g, 1, 64, seed=1)
+    with pytest.raises(ValueError):                                       # a bf16 tensor for fp16 operands
+        parser.head_gemm_argmax(feat.bfloat16().contiguous(memory_format=torch.channels_last), weight, bias, operand="f16")
+    with pytest.raises(ValueError):                                       # 16-bit NCHW is not a layout the kernel reads
+        parser.head_gemm_argmax(feat.half(), weight, bias, operand="f16")
+    with pytest.raises(ValueError):
+        parser.head_gemm_argmax(feat, weight, bias, operand="fp8")
