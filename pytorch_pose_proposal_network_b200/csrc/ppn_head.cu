@@ -43,6 +43,7 @@
 // of those only near-ties and the saturated tails need the two sigmoids evaluated (see the epilogue).
 #include <cuda.h>          // CUtensorMap and enums only: the encoder is fetched with cudaGetDriverEntryPoint
 #include <mutex>
+#include <type_traits>
 
 #include "ppn_kernels.h"
 
@@ -121,6 +122,23 @@ __device__ __forceinline__ void tmem_ld8_wait(uint32_t* r) {
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
 }
 
+// Waiting without eating the issue slots of the scheduler's working warps: between polls the thread sleeps.  (ncu, round 2:
+// 30 % of the kernel's executed instructions were the try_wait / branch pairs of the producer, the MMA issuer and the
+// epilogue warps that were ahead.)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep(ns);
+    }
+}
+
 // torch.sigmoid's fp32 expression, 1 / (1 + exp(-x)): libdevice expf, one add, one IEEE division
 __device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
@@ -141,6 +159,7 @@ struct HeadArgs {
     int32_t n_rows;             // 16-bit path: B * HW rows of the packed activation matrix
     int32_t n_bstages;          // 16-bit path: stages of the weight ring
     int32_t bf16;               // 16-bit path: operands are bf16 (else fp16)
+    int32_t dry;                // benchmarks only (tune key head.dry): the epilogue releases every accumulator unread
     uint32_t magic_S;           // ceil(2^32 / S): exact p / S for p < 2^22 (S <= 65535 and S * E channels)
     const float* bias;          // [C] or nullptr
     float* dec;                 // [B, n_dec, HW]   sigmoid of the 6K decode channels
@@ -170,6 +189,30 @@ __device__ __noinline__ void publish_piece(unsigned long long* slot, float bx, i
     const float sb = sigmoid_f32(bx);
     const uint32_t hi = (sb != sb) ? 0xFFFFFFFFu : __float_as_uint(sb);
     if (valid) atomicMax(slot, ((unsigned long long)hi << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx));
+}
+
+// Decode channels of one group: the LOGITS go to dec (head_finalize_kernel applies the sigmoid in place — 6K sigmoids per
+// cell inside the epilogue made the sub-warp that met them four times slower than its neighbours on that channel tile).
+// Out of line, all address arithmetic inside: inlined, the compiler hoisted sixteen 64-bit address chains per group
+// above the branch that almost never needs them (146 of 460 instructions per group, ncu round 2).
+__device__ __noinline__ void decode_group(float* dec, int b, int c0, int cell, int HW, int n_dec,
+                                          uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t r5, uint32_t r6, uint32_t r7,
+                                          float b0, float b1, float b2, float b3, float b4, float b5, float b6, float b7,
+                                          int j_lo, int j_hi, bool valid) {
+    if (!valid) return;
+    float* p = dec + ((size_t)b * n_dec + c0) * HW + cell;
+    const uint32_t r[8] = {r0, r1, r2, r3, r4, r5, r6, r7};
+    const float bs[8] = {b0, b1, b2, b3, b4, b5, b6, b7};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (j >= j_lo && j < j_hi) p[(size_t)j * HW] = __fadd_rn(__uint_as_float(r[j]), bs[j]);
+}
+// a column of a call that also emits the logits and the head tensor (parity tests)
+__device__ __noinline__ void emit_column(float* emit_logits, float* emit_head, int b, int c, int cell, int C, int HW, float x, bool valid) {
+    if (!valid) return;
+    const size_t at = ((size_t)b * C + c) * HW + cell;
+    if (emit_logits) emit_logits[at] = x;
+    if (emit_head) emit_head[at] = sigmoid_f32(x);
 }
 
 template <int kSubs, bool kDense>
@@ -204,9 +247,9 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
             const int n8 = (n_cols + 7) >> 3, per = (n8 + kSubs - 1) / kSubs;
             const int r_lo = c_tile + min(sub * per, n8) * 8;
             const int r_hi = min(c_tile + min((sub + 1) * per, n8) * 8, c_tile + n_cols);
-            mbar_wait(&tfull[acc], acc_phase);
+            mbar_wait_sleep(&tfull[acc], acc_phase, 40);
             tc_fence_after();
-            if (r_lo < r_hi) {
+            if (r_lo < r_hi && !(a.dry & 1)) {
                 const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN) - (uint32_t)c_tile;
                 // state of the piece being scanned: m = largest logit so far (+inf once a NaN has been taken: nothing may
                 // follow the first NaN), idx = the arg-max so far (window position) and bx = the logit it stands on
@@ -250,47 +293,96 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
                         for (int j = 0; j < 8; ++j) bs[j] = (bias_vec && c0 + j < a.C) ? __ldg(a.bias + c0 + j) : -0.0f;   // x + (-0) == x
                     }
                 };
-                uint32_t cur[8], nxt[8];
-                float bcur[8], bnxt[8];
-                begin(r_lo);
-                load_group(r_lo, nxt, bnxt);
-#pragma unroll 1
-                for (int c0 = r_lo; c0 < r_hi; c0 += 8) {
-                    tmem_ld8_wait(nxt);
+                uint32_t cur[8];
+                float bcur[8];
+                // Speculative scan of columns [j_lo, j_hi) of the loaded group (uniform bounds; kFull: all eight, straight-line
+                // code whose columns overlap in the pipeline).  No branch and no predicate on the chain through m: m' =
+                // max(m, x); a column may move the arg-max only if it is FAST (x - m > 0.01 and |x| <= 8: a certainly larger
+                // sigmoid, see limb_column); a lane that meets anything else above its running maximum — a near-tie, a
+                // saturated tail, NaN, +-inf — marks itself bad, restores the state the group started from and rescans its
+                // columns with the exact rule.  (The branchy exact rule on every column cost ~120 cycles per column and warp:
+                // each column's branch waits for the predicate chain of the column before it.)
+                auto spec_scan = [&](auto full_tag, int j_lo, int j_hi, int aw0) {
+                    constexpr bool kFull = decltype(full_tag)::value;
+                    const float m0 = m, bx0 = bx;
+                    const int idx0 = idx;
+                    bool bad = false;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { cur[j] = nxt[j]; bcur[j] = bnxt[j]; }
-                    if (c0 + 8 < r_hi) load_group(c0 + 8, nxt, bnxt);      // in flight while this group is scanned
-                    if (limb && !emit && c0 + 8 <= seg_end) {               // eight columns of one window
-                        const int aw0 = c0 - wbase;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) limb_column(__fadd_rn(__uint_as_float(cur[j]), bcur[j]), aw0 + j);
-                        if (c0 + 8 == seg_end) {
-                            publish_piece(key0 + (size_t)ei * a.HW, bx, idx, valid);
-                            if (c0 + 8 < r_hi) begin(c0 + 8);
+                    for (int j = 0; j < 8; ++j)
+                        if (kFull || (j >= j_lo && j < j_hi)) {
+                            const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
+                            const float d = __fsub_rn(x, m);
+                            const bool fast = d > 0.01f && fabsf(x) <= 8.0f;
+                            bad |= !(d <= 0.0f || fast);                    // NaN differences land here too
+                            idx = fast ? aw0 + j : idx;
+                            bx = fast ? x : bx;
+                            m = fmaxf(m, x);
                         }
-                    } else {
-                        // decode channels, a window boundary inside the group, the ragged end of the run, or a call that also
-                        // emits logits / the head tensor
+                    if (bad) {
+                        // (the values pass through an opaque move: otherwise the compiler computes this block's NaN tests
+                        // and selects for all eight columns ABOVE the branch, 32 instructions per group)
+                        m = m0; bx = bx0; idx = idx0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int c = c0 + j;
-                            if (c < r_hi) {                                 // uniform
-                                const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
-                                const size_t at = ((size_t)b * a.C + c) * a.HW + cell;
-                                if (a.emit_logits && valid) a.emit_logits[at] = x;
-                                if (!limb || a.emit_head) {
-                                    const float sg = sigmoid_f32(x);
-                                    if (!limb && valid) a.dec[((size_t)b * a.n_dec + c) * a.HW + cell] = sg;
-                                    if (a.emit_head && valid) a.emit_head[at] = sg;
-                                }
-                                if (limb) limb_column(x, c - wbase);
-                                if (c + 1 == seg_end) {
-                                    if (limb) publish_piece(key0 + (size_t)ei * a.HW, bx, idx, valid);
-                                    if (c + 1 < r_hi) begin(c + 1);
-                                }
+                        for (int j = 0; j < 8; ++j)
+                            if (kFull || (j >= j_lo && j < j_hi)) {
+                                uint32_t v;
+                                asm volatile("mov.b32 %0, %1;" : "=r"(v) : "r"(cur[j]));
+                                limb_column(__fadd_rn(__uint_as_float(v), bcur[j]), aw0 + j);
+                            }
+                    }
+                };
+                begin(r_lo);
+                int c0 = r_lo;
+#pragma unroll 1
+                while (c0 < r_hi) {
+                    if (limb && !emit && c0 + 8 <= seg_end) {
+                        // whole groups inside the current piece: the hot loop.  No register double-buffering: the other
+                        // warps of the scheduler cover the TMEM latency (a second register set cost 16 moves per group)
+#pragma unroll 1
+                        do {
+                            load_group(c0, cur, bcur);
+                            tmem_ld8_wait(cur);
+                            spec_scan(std::true_type{}, 0, 8, c0 - wbase);
+                            c0 += 8;
+                        } while (c0 + 8 <= seg_end);
+                        if (c0 == seg_end) {
+                            publish_piece(key0 + (size_t)ei * a.HW, bx, idx, valid);
+                            if (seg_end < r_hi) begin(seg_end);
+                        }
+                        continue;
+                    }
+                    // a group that holds a piece boundary, decode channels, the ragged end of the run, or any group of a call
+                    // that also emits the logits / the head tensor: piece by piece, columns [j_lo, j_hi) at a time
+                    load_group(c0, cur, bcur);
+                    tmem_ld8_wait(cur);
+                    int j_lo = 0;
+#pragma unroll 1
+                    do {
+                        const int j_hi = min(8, seg_end - c0);              // seg_end <= r_hi
+                        const int aw0 = c0 - wbase;
+                        if (limb && !emit) {
+                            spec_scan(std::false_type{}, j_lo, j_hi, aw0);
+                        } else {
+                            if (!limb)                                      // decode channels: the logit now, its sigmoid in the finalize pass
+                                decode_group(a.dec, b, c0, cell, a.HW, a.n_dec, cur[0], cur[1], cur[2], cur[3], cur[4], cur[5], cur[6], cur[7],
+                                             bcur[0], bcur[1], bcur[2], bcur[3], bcur[4], bcur[5], bcur[6], bcur[7], j_lo, j_hi, valid);
+                            if (emit) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (j >= j_lo && j < j_hi) {
+                                        const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
+                                        emit_column(a.emit_logits, a.emit_head, b, c0 + j, cell, a.C, a.HW, x, valid);
+                                        if (limb) limb_column(x, aw0 + j);
+                                    }
                             }
                         }
-                    }
+                        j_lo = j_hi;
+                        if (c0 + j_hi == seg_end) {
+                            if (limb) publish_piece(key0 + (size_t)ei * a.HW, bx, idx, valid);
+                            if (seg_end < r_hi) begin(seg_end);
+                        }
+                    } while (j_lo < 8 && c0 + j_lo < r_hi);
+                    c0 += 8;
                 }
             }
             tc_fence_before();
@@ -302,11 +394,12 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
     }
 }
 
-// keys -> the uint16 arg-max map (low half of a key = ~position)
+// keys -> the uint16 arg-max map (low half of a key = ~position); decode logits -> their sigmoid, in place
 __global__ void __launch_bounds__(256)
-head_amax_finalize_kernel(const unsigned long long* __restrict__ keys, uint16_t* __restrict__ amax, size_t n) {
+head_finalize_kernel(const unsigned long long* __restrict__ keys, uint16_t* __restrict__ amax, size_t n_keys, float* __restrict__ dec, size_t n_dec) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) amax[i] = (uint16_t)(0xFFFFFFFFu - (uint32_t)keys[i]);
+    if (i < n_keys) amax[i] = (uint16_t)(0xFFFFFFFFu - (uint32_t)keys[i]);
+    if (i < n_dec) dec[i] = sigmoid_f32(dec[i]);
 }
 
 // instruction descriptor: D fp32; formats 0 = f16, 1 = bf16, 2 = tf32; bit 15 / 16: A / B MN-major; N >> 3; M >> 4
@@ -368,7 +461,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     const bool last = nt == a.n_ntiles - 1;             // the last channel tile is only n_last channels wide
                     const uint32_t bytes = kABytes + (uint32_t)(last ? a.n_last : kBlockN) * 128u;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1u);
+                        mbar_wait_sleep(&empty[stage], phase ^ 1u, 100);
                         unsigned char* sa = smem + (size_t)stage * kStageBytes;
                         mbar_arrive_expect_tx(&full[stage], bytes);
 #pragma unroll
@@ -389,11 +482,11 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
                 for (int nt = 0; nt < a.n_ntiles; ++nt) {
                     const uint32_t idesc = nt == a.n_ntiles - 1 ? idesc_last : idesc_full;
-                    mbar_wait(&tempty[acc], acc_phase ^ 1u);             // the epilogue has drained this accumulator
+                    mbar_wait_sleep(&tempty[acc], acc_phase ^ 1u, 40);   // the epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)acc * kBlockN;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                        mbar_wait(&full[stage], phase);
+                        mbar_wait_sleep(&full[stage], phase, 20);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes), sb = sa + kABytes;
 #pragma unroll
@@ -490,11 +583,11 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                     const uint32_t b_bytes = (uint32_t)(last ? a.n_last : kBlockN) * 128u;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
                         if (nt == 0) {                                   // this tile's activations, k-block by k-block
-                            mbar_wait(&aempty[kb], a_phase ^ 1u);
+                            mbar_wait_sleep(&aempty[kb], a_phase ^ 1u, 100);
                             mbar_arrive_expect_tx(&afull[kb], kA16Bytes);
                             tma_load_2d(sA + (size_t)kb * kA16Bytes, &tm_x, kb * kBlockK16, tile * kBlockM, &afull[kb]);
                         }
-                        mbar_wait(&bempty[stage], phase ^ 1u);
+                        mbar_wait_sleep(&bempty[stage], phase ^ 1u, 100);
                         mbar_arrive_expect_tx(&bfull[stage], b_bytes);
                         tma_load_2d(sB + (size_t)stage * kB16Bytes, last ? &tm_wt : &tm_w, kb * kBlockK16, nt * kBlockN, &bfull[stage]);
                         if (++stage == a.n_bstages) { stage = 0; phase ^= 1u; }
@@ -514,12 +607,12 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                 for (int nt = 0; nt < a.n_ntiles; ++nt) {
                     const bool last = nt == a.n_ntiles - 1;
                     const uint32_t idesc = last ? idesc_last : idesc_full;
-                    mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                    mbar_wait_sleep(&tempty[acc], acc_phase ^ 1u, 40);
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)acc * kBlockN;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                        if (nt == 0) mbar_wait(&afull[kb], a_phase);
-                        mbar_wait(&bfull[stage], phase);
+                        if (nt == 0) mbar_wait_sleep(&afull[kb], a_phase, 20);
+                        mbar_wait_sleep(&bfull[stage], phase, 20);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(sA + (size_t)kb * kA16Bytes), sb = smem_u32(sB + (size_t)stage * kB16Bytes);
 #pragma unroll
@@ -527,7 +620,7 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                             // both K-major: 8 rows of 128 B per swizzle atom (1024 B), K advanced by 32 B inside the row
                             const uint64_t da = smem_desc(sa + kk * kUmmaK16 * 2, 16, 1024, 2);
                             const uint64_t db = smem_desc(sb + kk * kUmmaK16 * 2, 16, 1024, 2);
-                            tc_mma<1>(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+                            if (!(a.dry & 2) || kb == 0) tc_mma<1>(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
                         }
                         tc_commit(&bempty[stage]);
                         if (last) tc_commit(&aempty[kb]);                // the next tile's k-block may land here
@@ -642,7 +735,7 @@ void fill_common(HeadArgs& a, const Geom& g, int Cin, const float* bias, float* 
     a.n_last = ((g.C - (a.n_ntiles - 1) * kBlockN) + 15) & ~15;            // 16 .. 256
     a.magic_S = g.S <= 1 ? 0u : (uint32_t)(((1ull << 32) + g.S - 1) / g.S);
     a.bias = bias; a.dec = dec; a.keys = keys; a.emit_logits = emit_logits; a.emit_head = emit_head;
-    a.n_rows = g.B * g.HW; a.n_bstages = 0; a.bf16 = 0;
+    a.n_rows = g.B * g.HW; a.n_bstages = 0; a.bf16 = 0; a.dry = 0;
     a.groups_per_img = (g.HW + 31) / 32;
     a.n_groups = g.B * a.groups_per_img;
 }
@@ -670,28 +763,32 @@ cudaError_t launch_gemm(int subs, int grid, size_t smem, cudaStream_t st, bool p
         case 1: return launch_gemm_n<k16, 1>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
         case 2: return launch_gemm_n<k16, 2>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
         case 3: return launch_gemm_n<k16, 3>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-        default: return launch_gemm_n<k16, 4>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+        case 4: return launch_gemm_n<k16, 4>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+        case 5: return launch_gemm_n<k16, 5>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+        case 6: return launch_gemm_n<k16, 6>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+        default: return launch_gemm_n<k16, 7>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
     }
+}
+template <bool k16, int kSubs>
+cudaError_t set_smem_attr_n(int bytes) {
+    if constexpr (k16) return cudaFuncSetAttribute(head_gemm16_argmax_kernel<kSubs>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    else return cudaFuncSetAttribute(head_gemm_argmax_kernel<kSubs>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 template <bool k16>
 cudaError_t set_smem_attr(int bytes) {
     cudaError_t e;
-    if constexpr (k16) {
-        if ((e = cudaFuncSetAttribute(head_gemm16_argmax_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(head_gemm16_argmax_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(head_gemm16_argmax_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        return cudaFuncSetAttribute(head_gemm16_argmax_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    } else {
-        if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(head_gemm_argmax_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-        return cudaFuncSetAttribute(head_gemm_argmax_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    }
+    if ((e = set_smem_attr_n<k16, 1>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_attr_n<k16, 2>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_attr_n<k16, 3>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_attr_n<k16, 4>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_attr_n<k16, 5>(bytes)) != cudaSuccess) return e;
+    if ((e = set_smem_attr_n<k16, 6>(bytes)) != cudaSuccess) return e;
+    return set_smem_attr_n<k16, 7>(bytes);
 }
-cudaError_t finalize_amax(const unsigned long long* keys, uint16_t* amax, const Geom& g, cudaStream_t st) {
-    const size_t n = (size_t)g.B * g.E * g.HW;
+cudaError_t finalize_amax(const unsigned long long* keys, uint16_t* amax, float* dec, const Geom& g, cudaStream_t st) {
+    const size_t n_keys = (size_t)g.B * g.E * g.HW, n_dec = (size_t)g.B * 6 * g.K * g.HW, n = std::max(n_keys, n_dec);
     if (n == 0) return cudaSuccess;
-    head_amax_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, amax, n);
+    head_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, amax, n_keys, dec, n_dec);
     return cudaGetLastError();
 }
 }  // namespace
@@ -714,6 +811,8 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
 
     HeadArgs a;
     fill_common(a, g, Cin, bias, dec, keys, emit_logits, emit_head);
+    a.dry = (subs >> 8) & 3;
+    subs &= 255;
     a.n_tiles = (a.n_groups + 3) / 4;
     a.n_kblocks = Cin / kBlockK;
 
@@ -742,7 +841,7 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
     }
     if ((e = cudaMemsetAsync(keys, 0, head_keys_bytes(g), st)) != cudaSuccess) return e;
     if ((e = launch_gemm<false>(subs, std::min(sms, a.n_tiles), smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits)) != cudaSuccess) return e;
-    return finalize_amax(keys, amax, g, st);
+    return finalize_amax(keys, amax, dec, g, st);
 }
 
 bool head16_supported(int Cin, const Geom& g) {
@@ -767,6 +866,8 @@ cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, cons
 
     HeadArgs a;
     fill_common(a, g, Cin, bias, dec, keys, emit_logits, emit_head);
+    a.dry = (subs >> 8) & 3;
+    subs &= 255;
     a.n_tiles = (a.n_rows + kBlockM - 1) / kBlockM;
     a.n_kblocks = Cin / kBlockK16;
     a.bf16 = bf16 ? 1 : 0;
@@ -811,7 +912,7 @@ cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, cons
     }
     // its prologue (barriers, TMEM, tensor maps) runs under the pack kernel's tail
     if ((e = launch_gemm<true>(subs, std::min(sms, a.n_tiles), smem, st, true, tm_x, tm_w, tm_wt, a, pdl_bits | PDL_WAIT_START)) != cudaSuccess) return e;
-    return finalize_amax(keys, amax, g, st);
+    return finalize_amax(keys, amax, dec, g, st);
 }
 
 }  // namespace ppn

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--configs", default="cfg2,native")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--cin", type=int, default=512)
+ap.add_argument("--dry", action="store_true", help="epilogue skipped (results invalid): what the operand stream and the MMAs alone take")
 ap.add_argument("--subs", type=int, default=0, help="epilogue warps per TMEM lane quadrant (tune key head.subs), 0 = library default")
 args = ap.parse_args()
 peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -28,6 +29,10 @@ if args.subs:
     from pytorch_pose_proposal_network_b200 import _lib
     _lib.tune(head_subs=args.subs)
     print(f"# head.subs = {args.subs}")
+if args.dry:
+    from pytorch_pose_proposal_network_b200 import _lib
+    _lib.tune(head_dry=1)
+    print("# head.dry = 1: the epilogue releases the accumulators unread; times are the operand stream + MMAs only")
 torch.backends.cudnn.allow_tf32 = True                   # PyTorch's default: the reference's conv3 runs in TF32
 
 

@@ -20,6 +20,9 @@ feat = torch.randn(B, 512, cfg.H, cfg.W, device="cuda", generator=gen)
 weight = torch.randn(cfg.C, 512, device="cuda", generator=gen) * 0.06
 bias = torch.randn(cfg.C, device="cuda", generator=gen) * 0.5
 bias[:2 * cfg.K] += 1.0
+if os.environ.get("HEAD_SUBS"):
+    from pytorch_pose_proposal_network_b200 import _lib
+    _lib.tune(head_subs=int(os.environ["HEAD_SUBS"]))
 p = PoseParser(cfg)
 out = p.parse_features(feat, weight, bias, operand=operand)
 torch.cuda.synchronize()
