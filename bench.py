@@ -238,6 +238,61 @@ def measure_other_config(torch, name, dev, steps=30, warmup=5):
                                                                    else " (smaller than L2: a latency figure, not a bandwidth one)")}
 
 
+def measure_fused_head(torch, dev, peaks, name="cfg2", B=512, Cin=512, iters=20):
+    """The widened path of SURVEY §8f row 1 on the same preset: conv3 (1x1, model.py:85) + sigmoid + the whole parse from
+    the last layer's INPUT (PoseParser.parse_features -> ppn_head_parse_opt), beside cuDNN's convolution alone.
+    FLOPs against the measured bf16 tensor peak (TF32 runs at half of it)."""
+    from pytorch_pose_proposal_network_b200.config import PRESETS
+    from pytorch_pose_proposal_network_b200.parser import PoseParser
+    cfg = PRESETS[name]()
+    gen = torch.Generator(device=dev).manual_seed(5)
+    feats = [torch.randn(B, Cin, cfg.H, cfg.W, device=dev, generator=gen) for _ in range(3)]
+    weight = (torch.randn(cfg.C, Cin, device=dev, generator=gen) * (2.0 / (1.01 * Cin)) ** 0.5).contiguous()
+    bias = torch.randn(cfg.C, device=dev, generator=gen) * 0.5
+    bias[:2 * cfg.K] += 1.0
+    parser = PoseParser(cfg, device=dev)
+    outs = [parser.alloc_output(B) for _ in range(2)]
+    flops = 2.0 * B * cfg.HW * cfg.C * Cin
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        a.record()
+        for i in range(iters):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / iters
+
+    bf16_peak = peaks.get("bf16_tflops") or 1590.0
+    rec = {"preset": name, "images_per_call": B, "Cin": Cin, "gflop_per_call": flops / 1e9, "calls": iters,
+           "api": "PoseParser.parse_features(feat, conv3.weight, conv3.bias, operand=...) -> ppn_head_parse_opt: memset, [pack,] "
+                  "tcgen05 GEMM + arg-max epilogue, finalize, fused parse; inputs resident, 3 feature batches rotated"}
+    ms = timed(lambda i: parser.parse_features(feats[i % 3], weight, bias, out=outs[i % 2]))
+    rec["tf32_nchw_in_place"] = {"ms_per_call": ms, "images_per_s": B / ms * 1e3, "tflops": flops / ms / 1e9,
+                                 "frac_of_tensor_peak": flops / ms / 1e9 / (bf16_peak / 2), "peak_tflops": bf16_peak / 2}
+    ms = timed(lambda i: parser.parse_features(feats[i % 3], weight, bias, out=outs[i % 2], operand="f16"))
+    rec["f16_nchw_packed"] = {"ms_per_call": ms, "images_per_s": B / ms * 1e3, "tflops": flops / ms / 1e9,
+                              "frac_of_tensor_peak": flops / ms / 1e9 / bf16_peak, "peak_tflops": bf16_peak}
+    cl = [f.half().contiguous(memory_format=torch.channels_last) for f in feats]
+    ms = timed(lambda i: parser.parse_features(cl[i % 3], weight, bias, out=outs[i % 2], operand="f16"))
+    rec["f16_channels_last_in_place"] = {"ms_per_call": ms, "images_per_s": B / ms * 1e3, "tflops": flops / ms / 1e9,
+                                         "frac_of_tensor_peak": flops / ms / 1e9 / bf16_peak, "peak_tflops": bf16_peak}
+    w4 = weight[:, :, None, None].contiguous()
+    torch.backends.cudnn.allow_tf32 = True
+    ms = timed(lambda i: torch.nn.functional.conv2d(feats[i % 3], w4, bias))
+    rec["cudnn_conv_tf32_alone_ms"] = ms
+    head = torch.sigmoid(torch.nn.functional.conv2d(feats[0], w4, bias))
+    ms = timed(lambda i: parser.parse(torch.sigmoid(torch.nn.functional.conv2d(feats[i % 3], w4, bias)), out=outs[i % 2]))
+    rec["cudnn_conv_sigmoid_then_ppn_parse_ms"] = ms
+    rec["humans_per_image"] = float(parser.parse(head, out=outs[0]).count.float().mean())
+    del feats, cl, outs, head, parser
+    torch.cuda.empty_cache()
+    return rec
+
+
 def measure_compat(torch, dev, calls=20):
     """Wall time of the reference-signature call (datatest.get_humans_by_feature: numpy arrays in, lists of dicts out)
     at the reference's native shape — what rt_test.py:109-133 costs per frame with the drop-in."""
@@ -632,6 +687,8 @@ def run_ours(args, rank, world, local_rank):
                           "pipeline_frac = whole head tensor / step time / the measured copy peak; cfg1 is one image per call: a latency")
         line["other_configs"] = others
         line["compat_e2e"] = measure_compat(torch, dev)
+        if args.config == "cfg2" and args.head_dtype == "f32":
+            line["fused_head"] = measure_fused_head(torch, dev, json.load(open(peaks_path)) if os.path.exists(peaks_path) else {})
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, args)
     if rank == 0:

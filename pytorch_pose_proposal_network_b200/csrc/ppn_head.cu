@@ -308,16 +308,18 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
                     const int idx0 = idx;
                     bool bad = false;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (kFull || (j >= j_lo && j < j_hi)) {
-                            const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
-                            const float d = __fsub_rn(x, m);
-                            const bool fast = d > 0.01f && fabsf(x) <= 8.0f;
-                            bad |= !(d <= 0.0f || fast);                    // NaN differences land here too
-                            idx = fast ? aw0 + j : idx;
-                            bx = fast ? x : bx;
-                            m = fmaxf(m, x);
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        // columns outside [j_lo, j_hi) are masked by their (uniform) predicate, not branched around: the
+                        // eight columns stay one basic block
+                        const bool act = kFull || (j >= j_lo && j < j_hi);
+                        const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
+                        const float d = __fsub_rn(x, m);
+                        const bool fast = act && d > 0.01f && fabsf(x) <= 8.0f;
+                        bad |= act && !(d <= 0.0f || fast);                 // NaN differences land here too
+                        idx = fast ? aw0 + j : idx;
+                        bx = fast ? x : bx;
+                        m = fmaxf(m, act ? x : -INFINITY);
+                    }
                     if (bad) {
                         // (the values pass through an opaque move: otherwise the compiler computes this block's NaN tests
                         // and selects for all eight columns ABOVE the branch, 32 instructions per group)
@@ -755,19 +757,14 @@ cudaError_t launch_gemm_n(int grid, size_t smem, cudaStream_t st, bool pdl_attr,
     if constexpr (k16) return cudaLaunchKernelEx(&cfg, head_gemm16_argmax_kernel<kSubs>, tm_x, tm_w, tm_wt, a, pdl_bits);
     else return cudaLaunchKernelEx(&cfg, head_gemm_argmax_kernel<kSubs>, tm_x, tm_w, tm_wt, a, pdl_bits);
 }
-// epilogue warps per TMEM lane quadrant: 1 .. kMaxEpiSubs
+// epilogue warps per TMEM lane quadrant: instantiated for 1, 2, 4 and 6 (3 runs as 4, 5 and 7 as 6)
 template <bool k16>
 cudaError_t launch_gemm(int subs, int grid, size_t smem, cudaStream_t st, bool pdl_attr, const CUtensorMap& tm_x, const CUtensorMap& tm_w,
                         const CUtensorMap& tm_wt, const HeadArgs& a, int pdl_bits) {
-    switch (subs) {
-        case 1: return launch_gemm_n<k16, 1>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-        case 2: return launch_gemm_n<k16, 2>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-        case 3: return launch_gemm_n<k16, 3>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-        case 4: return launch_gemm_n<k16, 4>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-        case 5: return launch_gemm_n<k16, 5>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-        case 6: return launch_gemm_n<k16, 6>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-        default: return launch_gemm_n<k16, 7>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
-    }
+    if (subs <= 1) return launch_gemm_n<k16, 1>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+    if (subs == 2) return launch_gemm_n<k16, 2>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+    if (subs <= 4) return launch_gemm_n<k16, 4>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
+    return launch_gemm_n<k16, 6>(grid, smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits);
 }
 template <bool k16, int kSubs>
 cudaError_t set_smem_attr_n(int bytes) {
@@ -779,11 +776,8 @@ cudaError_t set_smem_attr(int bytes) {
     cudaError_t e;
     if ((e = set_smem_attr_n<k16, 1>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_attr_n<k16, 2>(bytes)) != cudaSuccess) return e;
-    if ((e = set_smem_attr_n<k16, 3>(bytes)) != cudaSuccess) return e;
     if ((e = set_smem_attr_n<k16, 4>(bytes)) != cudaSuccess) return e;
-    if ((e = set_smem_attr_n<k16, 5>(bytes)) != cudaSuccess) return e;
-    if ((e = set_smem_attr_n<k16, 6>(bytes)) != cudaSuccess) return e;
-    return set_smem_attr_n<k16, 7>(bytes);
+    return set_smem_attr_n<k16, 6>(bytes);
 }
 cudaError_t finalize_amax(const unsigned long long* keys, uint16_t* amax, float* dec, const Geom& g, cudaStream_t st) {
     const size_t n_keys = (size_t)g.B * g.E * g.HW, n_dec = (size_t)g.B * 6 * g.K * g.HW, n = std::max(n_keys, n_dec);

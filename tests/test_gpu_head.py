@@ -244,3 +244,27 @@ def test_head16_rejects_what_it_cannot_take():
         parser.head_gemm_argmax(feat.half(), weight, bias, operand="f16")
     with pytest.raises(ValueError):
         parser.head_gemm_argmax(feat, weight, bias, operand="fp8")
+
+
+@pytest.mark.parametrize("operand", ["tf32", "f16"])
+def test_head_every_epilogue_width_gives_the_same_answer(operand):
+    """head.subs = epilogue warps per TMEM lane quadrant: the pieces a window is cut into change with it, the merged
+    arg-max map and the decode planes must not (the key maximum is order-independent and exact)."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    g = geometry("cfg2")
+    parser = parser_for(g)
+    feat, weight, bias = make_layer(g, 40, 128, seed=23)
+    want = None
+    try:
+        for subs in (1, 2, 4, 6):
+            _lib.tune(head_subs=subs)
+            dec, amax, _, _ = parser.head_gemm_argmax(feat, weight, bias, operand=operand)
+            torch.cuda.synchronize()
+            if want is None:
+                want = (dec.clone(), amax.clone())
+                _, _, logits, head = parser.head_gemm_argmax(feat, weight, bias, emit=True, operand=operand)
+                check_against_emitted(g, parser, dec, amax, logits, head)
+            else:
+                assert torch.equal(dec, want[0]) and torch.equal(amax.view(torch.int16), want[1].view(torch.int16)), f"subs={subs}"
+    finally:
+        _lib.tune(head_subs=4)
