@@ -139,6 +139,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
     }
 }
 
+// When is a logit x above the running maximum m CERTAINLY a larger sigmoid value (as torch / numpy see them in fp32)?
+// For x - m > kSureStep and |x| <= kSureRange: sigmoid' >= 2.46e-3 on [-6.001, 6], so the true sigmoids are >= 2.46e-6
+// apart, while each evaluated sigmoid (expf <= 2 ulp, one add, one IEEE division) is within ~4 ulp <= 2.4e-7 of the
+// truth: a factor 5 of margin; below zero the values shrink like e^x and so does their spacing — the relative gap
+// stays >= 1e-3.  Everything else (near-ties, the saturated tails, NaN, +-inf) evaluates the two sigmoids.
+// (Round 2 started with 0.01 / 8 — margin 7 — and 17 % of the 8-column groups had a lane inside the 0.01 band and went
+// through the exact rescan; with 1e-3 it is ~2 %.)
+constexpr float kSureStep = 1e-3f, kSureRange = 6.0f;
+
 // torch.sigmoid's fp32 expression, 1 / (1 + exp(-x)): libdevice expf, one add, one IEEE division
 __device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
@@ -266,14 +275,13 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
                     limb = true; wbase = c - aw; seg_end = min(wbase + a.S, r_hi);
                     m = -INFINITY; bx = -INFINITY; idx = aw;
                 };
-                // One limb column at window position aw.  A logit above the running maximum beats the standing arg-max
-                // iff sigmoid(x) > sigmoid(bx) (numpy sees sigmoid values).  For x - m > 0.01 and |x| <= 8 it certainly
-                // does: sigmoid' >= 3.3e-4 on [-8.01, 8], so the sigmoids are >= 3.3e-6 apart — tens of ulps, far beyond
-                // either one's evaluation error — and m >= bx: that case is three selects, no branch.  Only the rest
-                // (near-ties, the saturated tails, NaN, +-inf) branches out to evaluate the two sigmoids.
+                // One limb column at window position aw, the exact rule.  A logit above the running maximum beats the standing
+                // arg-max iff sigmoid(x) > sigmoid(bx) (numpy sees sigmoid values).  When it is a sure step (kSureStep,
+                // kSureRange above) it certainly does, and m >= bx: three selects, no branch.  Only the rest branches out to
+                // evaluate the two sigmoids.
                 auto limb_column = [&](float x, int aw) {
                     const bool gt = !(x <= m);
-                    const bool fast = gt && __fsub_rn(x, m) > 0.01f && fabsf(x) <= 8.0f;
+                    const bool fast = gt && __fsub_rn(x, m) > kSureStep && fabsf(x) <= kSureRange;
                     idx = fast ? aw : idx;
                     bx = fast ? x : bx;
                     if (gt && !fast) {
@@ -297,7 +305,7 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
                 float bcur[8];
                 // Speculative scan of columns [j_lo, j_hi) of the loaded group (uniform bounds; kFull: all eight, straight-line
                 // code whose columns overlap in the pipeline).  No branch and no predicate on the chain through m: m' =
-                // max(m, x); a column may move the arg-max only if it is FAST (x - m > 0.01 and |x| <= 8: a certainly larger
+                // max(m, x); a column may move the arg-max only if it is FAST (a sure step, kSureStep / kSureRange: a certainly larger
                 // sigmoid, see limb_column); a lane that meets anything else above its running maximum — a near-tie, a
                 // saturated tail, NaN, +-inf — marks itself bad, restores the state the group started from and rescans its
                 // columns with the exact rule.  (The branchy exact rule on every column cost ~120 cycles per column and warp:
@@ -314,7 +322,7 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
                         const bool act = kFull || (j >= j_lo && j < j_hi);
                         const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
                         const float d = __fsub_rn(x, m);
-                        const bool fast = act && d > 0.01f && fabsf(x) <= 8.0f;
+                        const bool fast = act && d > kSureStep && fabsf(x) <= kSureRange;
                         bad |= act && !(d <= 0.0f || fast);                 // NaN differences land here too
                         idx = fast ? aw0 + j : idx;
                         bx = fast ? x : bx;
