@@ -164,6 +164,8 @@ __device__ __noinline__ bool beats_in_sigmoid(float x, float bx) {
 struct HeadArgs {
     int32_t B, HW, Cin, C, n_dec, S, E;
     int32_t groups_per_img, n_groups, n_tiles, n_ntiles, n_kblocks;
+    int32_t n_chunks, chunk_tiles, n_items;   // a work item = (cell tile, chunk of chunk_tiles consecutive channel tiles): small batches
+                                              // spread one cell tile's channels over several CTAs (the key maxima merge them)
     int32_t n_last;             // channels of the LAST channel tile, rounded up to 16: its MMAs and its weight box are that narrow
     int32_t n_rows;             // 16-bit path: B * HW rows of the packed activation matrix
     int32_t n_bstages;          // 16-bit path: stages of the weight ring
@@ -176,6 +178,13 @@ struct HeadArgs {
     float* emit_logits;         // optional [B, C, HW]: conv output before the sigmoid (parity tests)
     float* emit_head;           // optional [B, C, HW]: the reference's head tensor, sigmoid(logits)
 };
+
+// work item -> cell tile and its range of channel tiles
+__device__ __forceinline__ void head_item(const HeadArgs& a, int item, int& tile, int& nt0, int& nt1) {
+    tile = item / a.n_chunks;
+    nt0 = (item - tile * a.n_chunks) * a.chunk_tiles;
+    nt1 = min(nt0 + a.chunk_tiles, a.n_ntiles);
+}
 
 // ------------------------------ epilogue (both operand paths) ------------------------------
 // kSubs warps share each TMEM lane quadrant (32 accumulator rows = 32 cells).  Every channel tile's columns are cut
@@ -233,7 +242,9 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
     const bool bias_vec = a.bias != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int tile, nt0, nt1;
+        head_item(a, item, tile, nt0, nt1);
         int b, cell;
         bool valid;
         if constexpr (kDense) {
@@ -249,7 +260,7 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
             if (!valid) { b = 0; cell = 0; }
         }
         unsigned long long* const key0 = a.keys + (size_t)b * a.E * a.HW + cell;      // + ei * HW
-        for (int nt = 0; nt < a.n_ntiles; ++nt) {
+        for (int nt = nt0; nt < nt1; ++nt) {
             const int c_tile = nt * kBlockN;
             const int n_cols = min(kBlockN, a.C - c_tile);            // > 0
             // this sub-warp's run of the tile: whole 8-column groups
@@ -458,7 +469,9 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+                int tile, nt0, nt1;
+                head_item(a, item, tile, nt0, nt1);
                 int gb[4], gc[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -467,7 +480,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     gb[q] = g < a.n_groups ? b : a.B;                   // past the end: an all-zero box
                     gc[q] = g < a.n_groups ? (g - b * a.groups_per_img) * 32 : 0;
                 }
-                for (int nt = 0; nt < a.n_ntiles; ++nt) {
+                for (int nt = nt0; nt < nt1; ++nt) {
                     const bool last = nt == a.n_ntiles - 1;             // the last channel tile is only n_last channels wide
                     const uint32_t bytes = kABytes + (uint32_t)(last ? a.n_last : kBlockN) * 128u;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
@@ -489,8 +502,10 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
             const uint32_t idesc_full = mma_idesc(2u, 1u, kBlockN), idesc_last = mma_idesc(2u, 1u, a.n_last);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
-                for (int nt = 0; nt < a.n_ntiles; ++nt) {
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+                int tile, nt0, nt1;
+                head_item(a, item, tile, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt) {
                     const uint32_t idesc = nt == a.n_ntiles - 1 ? idesc_last : idesc_full;
                     mbar_wait_sleep(&tempty[acc], acc_phase ^ 1u, 40);   // the epilogue has drained this accumulator
                     tc_fence_after();
@@ -515,6 +530,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1u;
                 }
+            }
         }
     } else {
         head_epilogue<kSubs, false>(a, tmem_base, tfull, tempty);
@@ -587,12 +603,14 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, a_phase = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                for (int nt = 0; nt < a.n_ntiles; ++nt) {
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+                int tile, nt0, nt1;
+                head_item(a, item, tile, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt) {
                     const bool last = nt == a.n_ntiles - 1;
                     const uint32_t b_bytes = (uint32_t)(last ? a.n_last : kBlockN) * 128u;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                        if (nt == 0) {                                   // this tile's activations, k-block by k-block
+                        if (nt == nt0) {                                 // this item's activations, k-block by k-block
                             mbar_wait_sleep(&aempty[kb], a_phase ^ 1u, 100);
                             mbar_arrive_expect_tx(&afull[kb], kA16Bytes);
                             tma_load_2d(sA + (size_t)kb * kA16Bytes, &tm_x, kb * kBlockK16, tile * kBlockM, &afull[kb]);
@@ -613,15 +631,17 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
             const uint32_t idesc_full = mma_idesc(fmt, 0u, kBlockN), idesc_last = mma_idesc(fmt, 0u, a.n_last);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, a_phase = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                for (int nt = 0; nt < a.n_ntiles; ++nt) {
-                    const bool last = nt == a.n_ntiles - 1;
+            for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+                int tile, nt0, nt1;
+                head_item(a, item, tile, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    const bool last = nt == a.n_ntiles - 1, last_of_item = nt == nt1 - 1;
                     const uint32_t idesc = last ? idesc_last : idesc_full;
                     mbar_wait_sleep(&tempty[acc], acc_phase ^ 1u, 40);
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)acc * kBlockN;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
-                        if (nt == 0) mbar_wait_sleep(&afull[kb], a_phase, 20);
+                        if (nt == nt0) mbar_wait_sleep(&afull[kb], a_phase, 20);
                         mbar_wait_sleep(&bfull[stage], phase, 20);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(sA + (size_t)kb * kA16Bytes), sb = smem_u32(sB + (size_t)stage * kB16Bytes);
@@ -633,7 +653,7 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                             if (!(a.dry & 2) || kb == 0) tc_mma<1>(d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
                         }
                         tc_commit(&bempty[stage]);
-                        if (last) tc_commit(&aempty[kb]);                // the next tile's k-block may land here
+                        if (last_of_item) tc_commit(&aempty[kb]);        // the next item's k-block may land here
                         if (++stage == a.n_bstages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit(&tfull[acc]);
@@ -793,6 +813,16 @@ cudaError_t finalize_amax(const unsigned long long* keys, uint16_t* amax, float*
     head_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, amax, n_keys, dec, n_dec);
     return cudaGetLastError();
 }
+// Fewer cell tiles than SMs (small batches — one image of the reference's shape is 5 tiles): cut every cell tile's channel
+// tiles into chunks, one work item each, so that about one item lands on every SM.  The pieces of a limb window meet in
+// the key maxima wherever they were scanned, so nothing else changes; a CTA re-loads its activations per item.
+void plan_items(HeadArgs& a, int sms) {
+    int chunks = 1;
+    if (a.n_tiles < sms) chunks = std::min(a.n_ntiles, std::max(1, sms / a.n_tiles));
+    a.chunk_tiles = (a.n_ntiles + chunks - 1) / chunks;
+    a.n_chunks = (a.n_ntiles + a.chunk_tiles - 1) / a.chunk_tiles;
+    a.n_items = a.n_tiles * a.n_chunks;
+}
 }  // namespace
 
 size_t head_keys_bytes(const Geom& g) { return (size_t)g.B * g.E * g.HW * sizeof(unsigned long long); }
@@ -817,6 +847,7 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
     subs &= 255;
     a.n_tiles = (a.n_groups + 3) / 4;
     a.n_kblocks = Cin / kBlockK;
+    plan_items(a, sms);
 
     CUtensorMap tm_x, tm_w, tm_wt;
     {   // activations [B][Cin][HW] fp32: box = 32 cells x 32 input channels of one image
@@ -842,7 +873,7 @@ cudaError_t launch_head_gemm_argmax(const float* feat, const float* weight, cons
         }
     }
     if ((e = cudaMemsetAsync(keys, 0, head_keys_bytes(g), st)) != cudaSuccess) return e;
-    if ((e = launch_gemm<false>(subs, std::min(sms, a.n_tiles), smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits)) != cudaSuccess) return e;
+    if ((e = launch_gemm<false>(subs, std::min(sms, a.n_items), smem, st, pdl_attr, tm_x, tm_w, tm_wt, a, pdl_bits)) != cudaSuccess) return e;
     return finalize_amax(keys, amax, dec, g, st);
 }
 
@@ -872,6 +903,7 @@ cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, cons
     subs &= 255;
     a.n_tiles = (a.n_rows + kBlockM - 1) / kBlockM;
     a.n_kblocks = Cin / kBlockK16;
+    plan_items(a, sms);
     a.bf16 = bf16 ? 1 : 0;
     int max_smem = 0;
     if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
@@ -913,7 +945,7 @@ cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, cons
         }
     }
     // its prologue (barriers, TMEM, tensor maps) runs under the pack kernel's tail
-    if ((e = launch_gemm<true>(subs, std::min(sms, a.n_tiles), smem, st, true, tm_x, tm_w, tm_wt, a, pdl_bits | PDL_WAIT_START)) != cudaSuccess) return e;
+    if ((e = launch_gemm<true>(subs, std::min(sms, a.n_items), smem, st, true, tm_x, tm_w, tm_wt, a, pdl_bits | PDL_WAIT_START)) != cudaSuccess) return e;
     return finalize_amax(keys, amax, dec, g, st);
 }
 

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--configs", default="cfg2,native")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--cin", type=int, default=512)
+ap.add_argument("--batch", type=int, default=0, help="images per call (default: the preset's throughput batch)")
 ap.add_argument("--dry", action="store_true", help="epilogue skipped (results invalid): what the operand stream and the MMAs alone take")
 ap.add_argument("--subs", type=int, default=0, help="epilogue warps per TMEM lane quadrant (tune key head.subs), 0 = library default")
 args = ap.parse_args()
@@ -51,7 +52,7 @@ def timed(fn, iters):
 
 for name in args.configs.split(","):
     cfg = PRESETS[name]()
-    B, Cin = BATCH[name], args.cin
+    B, Cin = args.batch or BATCH[name], args.cin
     gen = torch.Generator(device="cuda").manual_seed(5)
     feats = [torch.randn(B, Cin, cfg.H, cfg.W, device="cuda", generator=gen) for _ in range(3)]
     weight = (torch.randn(cfg.C, Cin, device="cuda", generator=gen) * (2.0 / (1.01 * Cin)) ** 0.5).contiguous()
