@@ -446,6 +446,26 @@ class PoseParser:
                        "ppn_head_parse_opt")
         return (out, logits, head) if emit else out
 
+    def capture_features(self, feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                         out: Optional[PackedHumans] = None, operand: str = "tf32") -> "CapturedParse":
+        """Record ``parse_features(feat, weight, bias, out)`` into a CUDA graph for repeated use on the SAME buffers
+        (the single-image loop of rt_test.py:87-147 with the backbone writing ``feat`` in place): a replay is one graph
+        launch instead of four or five launches from Python.  All tensors must stay alive and in place."""
+        B, _, _ = self._check_features(feat, weight, bias, operand)
+        if out is None:
+            out = self.alloc_output(B)
+        self.parse_features(feat, weight, bias, out=out, operand=operand)      # warm-up outside the capture: workspace, attributes
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.graph(graph, stream=side):
+            self.parse_features(feat, weight, bias, out=out, operand=operand)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        cap = CapturedParse(graph, feat, out)
+        cap.keep = (weight, bias, self._head_ws)                               # the graph holds their addresses
+        return cap
+
     # ---- keypoints (what drawing and AP evaluation read off the boxes) ------------------- #
     def part_centres(self, humans: PackedHumans) -> torch.Tensor:
         """fp32 [B, R, K, 2] = (y, x) centre of every part's box, (0, 0) where absent

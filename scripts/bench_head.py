@@ -74,6 +74,13 @@ for name in args.configs.split(","):
         torch.nn.functional.conv2d(feats[i % 3], w4, bias)
 
     t_f, t_u, t_c = timed(fused, args.iters), timed(unfused, args.iters), timed(conv_only, args.iters)
+    if B <= 16:                                            # small batches are bound by the host's launches: also replay a CUDA graph
+        cap = parser.capture_features(feats[0], weight, bias, out=outs[0])
+        cap16 = parser.capture_features(feats[1].half().contiguous(memory_format=torch.channels_last), weight, bias, out=outs[1], operand="f16") \
+            if Cin % 64 == 0 and Cin <= 512 else None
+        t_g = timed(lambda i: cap.replay(), args.iters)
+        t_g16 = timed(lambda i: cap16.replay(), args.iters) if cap16 else float("nan")
+        print(f"{name}: B={B}: fused head+parse replayed from a CUDA graph: TF32 {t_g * 1e3:.1f} us, f16 channels_last {t_g16 * 1e3:.1f} us per call")
     print(f"{name}: B={B} Cin={Cin} C={cfg.C} grid {cfg.H}x{cfg.W}: {flops / 1e9:.1f} GFLOP per batch")
     print(f"   TF32 operands (fp32 NCHW activations read in place)")
     print(f"      fused head+parse   {t_f * 1e3:8.1f} us  {B / t_f / 1e3:8.1f} k img/s  {flops / t_f / 1e9:7.1f} TFLOP/s = {flops / t_f / 1e9 / tf32_peak:.3f} of the TF32 peak "

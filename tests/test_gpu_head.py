@@ -268,3 +268,27 @@ def test_head_every_epilogue_width_gives_the_same_answer(operand):
                 assert torch.equal(dec, want[0]) and torch.equal(amax.view(torch.int16), want[1].view(torch.int16)), f"subs={subs}"
     finally:
         _lib.tune(head_subs=4)
+
+
+@pytest.mark.parametrize("operand", ["tf32", "f16"])
+def test_head_small_batch_items_and_graph_replay(operand):
+    """One image of the reference's shape: 5 cell tiles, so every tile's channel tiles are spread over the SMs as work
+    items (the key maxima merge them); and the whole call replayed from a CUDA graph on a refilled feature buffer."""
+    g = geometry("native")
+    parser = parser_for(g)
+    feat, weight, bias = make_layer(g, 1, 512, seed=31)
+    packed, logits, head = parser.parse_features(feat, weight, bias, emit=True, operand=operand)
+    torch.cuda.synchronize()
+    ref = c_oracle.parse_batch(head.cpu().numpy(), g)
+    assert int(ref["counts"][:, 2].sum()) > 0
+    assert_packed_equals_oracle(packed.numpy(), ref, 1)
+    cap = parser.capture_features(feat, weight, bias, operand=operand)
+    feat2, _, _ = make_layer(g, 1, 512, seed=32)
+    feat.copy_(feat2)                                                       # the next frame, written in place
+    got = cap.replay().numpy()
+    torch.cuda.synchronize()
+    packed2, _, head2 = parser.parse_features(feat2, weight, bias, emit=True, operand=operand)
+    torch.cuda.synchronize()
+    ref2 = c_oracle.parse_batch(head2.cpu().numpy(), g)
+    assert_packed_equals_oracle(got, ref2, 1)
+    assert_packed_equals_oracle(packed2.numpy(), ref2, 1)
