@@ -251,6 +251,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;
     else if (!std::strcmp(key, "encode.sweep")) t.encode_sweep = value != 0;
     else if (!std::strcmp(key, "encode.ctas_per_sm")) t.encode_ctas_per_sm = value < 1 ? 1 : (value > 8 ? 8 : value);
+    else if (!std::strcmp(key, "nms.blockwise")) ppn::set_nms_blockwise(value);   // NMS phase 3 block by block (round 1/2) instead of the warp wavefront
     else if (!std::strcmp(key, "timeline.phase")) g_timeline.phase = value;      // which in-kernel phase boundary ppn_timeline records
     else return PPN_E_BADARG;
     return PPN_OK;
@@ -282,6 +283,7 @@ int ppn_tune_get(const char* key, int32_t* value) {
     else if (!std::strcmp(key, "host.chunk_images")) *value = t.host_chunk_images;
     else if (!std::strcmp(key, "encode.sweep")) *value = t.encode_sweep;
     else if (!std::strcmp(key, "encode.ctas_per_sm")) *value = t.encode_ctas_per_sm;
+    else if (!std::strcmp(key, "nms.blockwise")) *value = ppn::get_nms_blockwise();
     else return PPN_E_BADARG;
     return PPN_OK;
 }

@@ -56,6 +56,15 @@ __device__ __forceinline__ void tl_phase(const Geom& g, int phase) {
     }
 }
 
+// the same from any warp (lane 0): phase boundaries of code that runs warp by warp
+__device__ __forceinline__ void tl_phase_warp(const Geom& g, int phase) {
+    if (g.tl && (threadIdx.x & 31) == 0 && g.tl_phase == phase) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(g.tl + 4 * (size_t)g.tl_slot + 3, t);
+    }
+}
+
 // ---- head element types ------------------------------------------------------------------
 // The head tensor may be fp32 (the reference's), fp16 or bf16 (a head emitted in 16 bits halves the
 // HBM traffic of this path).  Every element is widened to fp32 — exactly — the

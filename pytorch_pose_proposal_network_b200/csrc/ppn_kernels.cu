@@ -8,6 +8,7 @@
 //
 // Launchers at the bottom are called by ppn_capi.cu.
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 
 #include "ppn_kernels.h"
@@ -832,11 +833,11 @@ __device__ __forceinline__ NmsSmem nms_carve(unsigned char* base, int stride) {
     NmsSmem s;
     s.sbox = reinterpret_cast<float4*>(base);
     s.kbox = s.sbox + stride;
-    s.key = reinterpret_cast<unsigned long long*>(s.kbox + 32);
-    s.sarea = reinterpret_cast<float*>(s.key + stride);
-    s.sidx = reinterpret_cast<int32_t*>(s.sarea + stride);
-    s.rank = s.sidx + stride;
-    s.diag = reinterpret_cast<unsigned*>(s.rank + stride);
+    s.key = reinterpret_cast<unsigned long long*>(s.kbox + 32);      // key, sarea, rank: 16 contiguous bytes per box, reused
+    s.sarea = reinterpret_cast<float*>(s.key + stride);              //   as the survivor list of the wavefront NMS
+    s.rank = reinterpret_cast<int32_t*>(s.sarea + stride);
+    s.sidx = s.rank + stride;
+    s.diag = reinterpret_cast<unsigned*>(s.sidx + stride);
     s.rem = s.diag + stride;
     s.ctl = reinterpret_cast<int32_t*>(s.rem + 32);
     s.karea = reinterpret_cast<float*>(s.ctl + 4);
@@ -858,19 +859,66 @@ __device__ __forceinline__ bool suppresses_finite(const float4 tested, float are
     return iou >= thr;
 }
 
-constexpr int kNmsWalkMax = 12;   // resolve a block survivor by survivor when at most this many of its boxes are still alive
+// Branch-free pre-classification of one IoU test (boxes without NaN coordinates, 1e-6 <= thr <= 1e6).  The exact rule
+// is RN(inter / den) >= thr with an IEEE division; here the quotient comes from the approximate divide (2 ulp for
+// |den| within [2^-126, 2^126], CUDA math API) and only answers that are 2^-18 (relative) clear of the threshold
+// count: `yes` when surely >= thr, `amb` raised when neither side is sure (or den is outside [1e-18, 1e18], NaN
+// included) — the caller then evaluates suppresses_finite() for that pair.  No divergent branch, no division
+// sequence: four to eight of these pipeline in a warp, where the exact test is ~250 dependent cycles behind a branch
+// (one image at the native shape: 32 boxes against 10 survivors took 2.9 us on the wavefront's critical path).
+__device__ __forceinline__ bool boxes_overlap(const float4 a, const float4 b) {      // tl < br on both axes (datatest.py:148)
+    return fmaxf(a.x, b.x) < fminf(a.z, b.z) && fmaxf(a.y, b.y) < fminf(a.w, b.w);
+}
+__device__ __forceinline__ bool iou_sure(const float4 tested, float area_tested, const float4 kept, float area_kept,
+                                         float thr_lo, float thr_hi, bool& amb) {
+    const float tly = fmaxf(tested.x, kept.x), tlx = fmaxf(tested.y, kept.y);
+    const float bry = fminf(tested.z, kept.z), brx = fminf(tested.w, kept.w);
+    const bool overlap = tly < bry && tlx < brx;
+    const float prod = __fmul_rn(__fsub_rn(bry, tly), __fsub_rn(brx, tlx));
+    const float inter = overlap ? prod : 0.0f;
+    const float den = __fsub_rn(__fadd_rn(area_tested, area_kept), inter);
+    const float q = __fdividef(inter, den);
+    const bool in_range = fabsf(den) > 1e-18f && fabsf(den) < 1e18f;
+    const bool yes = q > thr_hi, no = q < thr_lo;
+    amb |= !(in_range && (yes || no));
+    return yes;
+}
+
+constexpr int kNmsWalkMax = 12;      // resolve a block survivor by survivor when at most this many of its boxes are still alive
+constexpr int NMS_BLOCKWISE = 128;   // launch bit of the decode+NMS and fused parse kernels: phase 3 block by block (see nms_core)
 
 // Whole CTA.  Precondition: s.key[0..n) holds the keys of the n unsorted boxes `ubox` (global or
 // shared), s.rank[0..n) is zero, and a __syncthreads() has made both visible.  Writes
 // out[pos] = map ? map[idx] : idx for the kept boxes in visiting order and returns their number (in
 // every thread).  n <= 1024.
+__device__ __forceinline__ unsigned ld_acquire_cta_shared(const void* p) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(void* p, unsigned v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// `blockwise` (tune key "nms.blockwise", off by default): round 1/2's barrier-per-block phase 3 instead of the
+// warp wavefront below — kept for A/B measurements and as a second implementation the tests compare.
 __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, int n, float thr, int limit,
-                                        int32_t* __restrict__ out, const int32_t* map, const Geom* tg = nullptr) {
+                                        int32_t* __restrict__ out, const int32_t* map, const Geom* tg = nullptr,
+                                        bool blockwise = false, bool quick = true) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, n_warps = T >> 5;
     const int Wd = (n + 31) >> 5;
-    // ---- 1. rank: every box's rank = number of larger keys, the key range split over T/n threads per box
-    int split = T / n;
-    split = split < 1 ? 1 : (split > 8 ? 8 : split);
+    // ---- 1. rank: every box's rank = number of larger keys.  The n x n comparisons are cut into n * split items of
+    //      n / split keys; split is the power of two that gives the threads the shortest longest share (n = 576 on 512
+    //      threads: split 1 would leave 64 threads with two whole passes, 1152 keys each; split 8 gives everybody 9
+    //      items of 72 = 648)
+    int split = 1;
+    {
+        int best = ((n + T - 1) / T) * (n + 12);                   // + 12: an item's fixed cost, in key comparisons
+        for (int sp = 2; sp <= 16; ++sp) {
+            const int cost = ((n * sp + T - 1) / T) * ((n + sp - 1) / sp + 12);
+            if (cost < best) { best = cost; split = sp; }
+        }
+    }
     const int chunk = (n + split - 1) / split;
     for (int item = tid; item < n * split; item += T) {
         const int part = item / n, i = item - part * n;
@@ -892,6 +940,7 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
         s.sidx[r] = i;
     }
     if (tid < 32) s.rem[tid] = 0u;
+    if (tid == 0) s.ctl[0] = 0;
     const bool any_nan = __syncthreads_or(has_nan);
     const bool thr_pos = thr > 0.0f;
     if (tg) tl_phase(*tg, 12);
@@ -902,21 +951,167 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
     //  dependent cycles per SURVIVOR.  One image at the reference's native shape, 351 candidates -> 58 survivors:
     //  28 us block by block, 35 us with the matrix; 1024 dense images (256 -> 225): 91 -> 105 us.)
     // ---- 2. diagonal blocks: one warp per box i, lanes = the boxes of i's own block of 32 -----------------
-    for (int i = warp; i < n; i += n_warps) {
-        const float4 bi = s.sbox[i];
-        const float ai = s.sarea[i];
-        const int j = (i & ~31) + lane;
-        bool bit = false;
-        if (j > i && j < n) {
-            const float4 bj = s.sbox[j];
-            bit = any_nan ? suppresses(bj, s.sarea[j], bi, ai, thr, thr_pos)
-                          : suppresses_finite(bj, s.sarea[j], bi, ai, thr, thr_pos);
+    // `quick`: latency over instruction count.  iou_sure() costs ~28 instructions a pair where the exact test leaves
+    // after ~10 when the boxes do not overlap at all: right for the one-CTA-per-image kernels, whose dependent chains
+    // are what a small batch waits for, wrong for the throughput-bound decode+NMS grid of a dense crowd (1024 images of
+    // 225 people: 72 -> 104 us with it).
+    const bool fast_ok = quick && !any_nan && thr >= 1e-6f && thr <= 1e6f;
+    const float thr_lo = thr * (1.0f - 3.8147e-6f), thr_hi = thr * (1.0f + 3.8147e-6f);
+    if (fast_ok) {
+        // two boxes i per warp and turn: independent, branch-free tests in flight together
+        for (int i = warp; i < n; i += 2 * n_warps) {
+            unsigned word[2], ambw = 0u;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int ii = min(i + u * n_warps, n - 1);
+                const int j = (ii & ~31) + lane, jj = min(j, n - 1);
+                bool amb = false;
+                const bool yes = iou_sure(s.sbox[jj], s.sarea[jj], s.sbox[ii], s.sarea[ii], thr_lo, thr_hi, amb);
+                const bool valid = j > ii && j < n;
+                word[u] = __ballot_sync(0xffffffffu, yes && valid);
+                ambw |= __ballot_sync(0xffffffffu, amb && valid);
+            }
+            if (ambw) {                                               // rare: a quotient within 2^-18 of the threshold
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ii = min(i + u * n_warps, n - 1);
+                    const int j = (ii & ~31) + lane;
+                    bool bit = false;
+                    if (j > ii && j < n) bit = suppresses_finite(s.sbox[j], s.sarea[j], s.sbox[ii], s.sarea[ii], thr, thr_pos);
+                    word[u] = __ballot_sync(0xffffffffu, bit);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (lane == 0 && i + u * n_warps < n) s.diag[i + u * n_warps] = word[u];
         }
-        const unsigned word = __ballot_sync(0xffffffffu, bit);
-        if (lane == 0) s.diag[i] = word;
+    } else {
+        for (int i = warp; i < n; i += n_warps) {
+            const float4 bi = s.sbox[i];
+            const float ai = s.sarea[i];
+            const int j = (i & ~31) + lane;
+            bool bit = false;
+            if (j > i && j < n) {
+                const float4 bj = s.sbox[j];
+                bit = any_nan ? suppresses(bj, s.sarea[j], bi, ai, thr, thr_pos)
+                              : suppresses_finite(bj, s.sarea[j], bi, ai, thr, thr_pos);
+            }
+            const unsigned word = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) s.diag[i] = word;
+        }
     }
     __syncthreads();
     if (tg) tl_phase(*tg, 13);
+    if (!blockwise) {
+        // ---- 3. WAVEFRONT: a warp owns a word of 32 boxes (box = lane) from here to its verdict; no CTA barrier.
+        //      The survivors so far are a list in shared memory that only grows, published together with the number
+        //      of resolved words in ONE word (release / acquire).  A warp keeps testing its boxes against whatever
+        //      survivors have been published — the earlier words' survivors, long before its predecessor is
+        //      resolved — and when the count of resolved words reaches its own, it has seen every earlier survivor:
+        //      it resolves its own 32-box dependency, appends its survivors and publishes.  On the critical path per
+        //      word: notice the predecessor's survivors (a handful), test them, resolve, publish — the block-by-block
+        //      version below pays two CTA barriers, a compaction by warp 0 and the whole cross phase per word.
+        //      The resolve is not the 32-step chain either: the word's diagonal bits are transposed beforehand (5
+        //      shuffle butterflies, off the critical path) so that lane t holds the EARLIER boxes that would suppress
+        //      box t; then rounds of two ballots — a box with a kept suppressor dies, a box none of whose
+        //      suppressors is still undecided is kept — as many rounds as the longest suppression chain (2-4).
+        //      Survivors' boxes live in the 16 bytes per box of {sort keys, areas, ranks}, all dead by now; areas are
+        //      recomputed (same operations, same bits).
+        float4* kall = reinterpret_cast<float4*>(s.key);
+        for (int w = warp; w < Wd; w += n_warps) {
+            const int i0 = w << 5, nb = min(32, n - i0);
+            const bool inb = lane < nb;
+            const float4 bj = s.sbox[inb ? i0 + lane : i0];
+            const float aj = box_area(bj);
+            unsigned col = inb ? s.diag[i0 + lane] : 0u;               // row form: the later boxes of the word that box `lane` suppresses
+#pragma unroll
+            for (int sh = 16; sh >= 1; sh >>= 1) {                     // 32 x 32 bit transpose across the lanes
+                const unsigned m = sh == 16 ? 0x0000ffffu : sh == 8 ? 0x00ff00ffu : sh == 4 ? 0x0f0f0f0fu : sh == 2 ? 0x33333333u : 0x55555555u;
+                const unsigned other = __shfl_xor_sync(0xffffffffu, col, sh);
+                col = (lane & sh) ? ((col & ~m) | ((other >> sh) & m)) : ((col & m) | ((other & m) << sh));
+            }                                                          // column form: the earlier boxes of the word that suppress box `lane`
+            bool dead = !inb;
+            int seen = 0;
+            bool fin = false;
+            for (;;) {
+                unsigned st = 0u;
+                if (lane == 0) st = ld_acquire_cta_shared(&s.ctl[0]);
+                st = __shfl_sync(0xffffffffu, st, 0);
+                __syncwarp();
+                const int m_pub = (int)(st & 0xffffu), wd = (int)((st >> 16) & 0x7fffu);
+                fin = (st >> 31) != 0u;
+                if (fin) break;
+                if (m_pub > seen) {
+                    bool exact = !fast_ok;
+                    if (fast_ok && __any_sync(0xffffffffu, !dead)) {
+                        bool hit = false, amb = false;                 // every lane, dead or not: nothing diverges
+#pragma unroll 4
+                        for (int q = seen; q < m_pub; ++q) {
+                            const float4 kb = kall[q];
+                            hit |= iou_sure(bj, aj, kb, box_area(kb), thr_lo, thr_hi, amb);
+                        }
+                        exact = __any_sync(0xffffffffu, amb && !hit && !dead);   // rare
+                        if (!exact) dead |= hit;
+                    }
+                    if (exact && !dead) {
+                        bool hit = false;
+                        if (any_nan) {
+                            for (int q = seen; q < m_pub; ++q) {
+                                const float4 kb = kall[q];
+                                hit |= suppresses(bj, aj, kb, box_area(kb), thr, thr_pos);
+                            }
+                        } else {
+                            for (int q = seen; q < m_pub; ++q) {
+                                const float4 kb = kall[q];
+                                hit |= suppresses_finite(bj, aj, kb, box_area(kb), thr, thr_pos);
+                            }
+                        }
+                        dead = hit;
+                    }
+                    seen = m_pub;
+                }
+                if (wd >= w) break;                                    // every earlier word is resolved, and `seen` covers their survivors
+            }
+            if (fin) break;
+            if (tg) { if (w == 0) tl_phase_warp(*tg, 14); else if (w == 1) tl_phase_warp(*tg, 16); }
+            unsigned und = ~__ballot_sync(0xffffffffu, dead);          // still to decide (lanes past the list count as dead)
+            unsigned kept = 0u;
+            while (und) {
+                const bool mine = (und >> lane) & 1u;
+                const bool killed = mine && (col & kept) != 0u;
+                const bool free_ = mine && !killed && (col & und) == 0u;
+                const unsigned k = __ballot_sync(0xffffffffu, free_);
+                const unsigned d = __ballot_sync(0xffffffffu, killed);
+                kept |= k;
+                und &= ~(k | d);
+            }
+            bool done = false;
+            if (limit > 0 && seen + __popc(kept) >= limit) {           // datatest.py:154-155
+                int need = limit - seen;
+                unsigned trimmed = 0u;
+                for (unsigned rest = kept; need > 0 && rest; --need) { const unsigned low = rest & (0u - rest); trimmed |= low; rest ^= low; }
+                kept = trimmed;
+                done = true;
+            }
+            if ((kept >> lane) & 1u) {
+                const int idx = s.sidx[i0 + lane];
+                const int pos = seen + __popc(kept & ((1u << lane) - 1u));
+                out[pos] = map ? map[idx] : idx;
+                kall[pos] = bj;
+            }
+            __syncwarp();
+            if (lane == 0)
+                st_release_cta_shared(&s.ctl[0], ((done || w == Wd - 1) ? 0x80000000u : 0u) | ((unsigned)(w + 1) << 16) |
+                                                     (unsigned)(seen + __popc(kept)));
+            if (tg) {
+                if (w == 0) tl_phase_warp(*tg, 15); else if (w == 1) tl_phase_warp(*tg, 17); else if (w == 2) tl_phase_warp(*tg, 18);
+                if (w == Wd - 1) tl_phase_warp(*tg, 19);
+            }
+            if (done) break;
+        }
+        __syncthreads();
+        return s.ctl[0] & 0xffff;
+    }
     // ---- 3. block by block: warp 0 resolves the block, everybody tests its survivors against the rest ------
     int m = 0;
     for (int w = 0; w < Wd; ++w) {
@@ -1013,7 +1208,7 @@ __device__ __forceinline__ int nms_core(const NmsSmem& s, const float4* ubox, in
 
 __global__ void __launch_bounds__(512)
 nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score, const int32_t* __restrict__ count,
-                int stride, float thr, int limit, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count) {
+                int stride, float thr, int limit, int32_t* __restrict__ keep_idx, int32_t* __restrict__ keep_count, int blockwise) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int prob = blockIdx.x;
     const int n = min(count[prob], stride);
@@ -1025,7 +1220,7 @@ nms_smem_kernel(const float4* __restrict__ box, const float* __restrict__ score,
         s.rank[i] = 0;
     }
     __syncthreads();
-    const int m = nms_core(s, box + (size_t)prob * stride, n, thr, limit, keep_idx + (size_t)prob * stride, nullptr);
+    const int m = nms_core(s, box + (size_t)prob * stride, n, thr, limit, keep_idx + (size_t)prob * stride, nullptr, nullptr, blockwise != 0);
     if (tid == 0) keep_count[prob] = m;
 }
 
@@ -1094,7 +1289,7 @@ decode_nms_kernel(const T* __restrict__ head, Geom g, int n_parts, float det_thr
         const int n = base_s;
         const size_t list = (size_t)item * g.HW;
         int m = 0;
-        if (n > 0) m = nms_core(s, ubox, n, nms_thr, 0, keep_cell + list, ucell);
+        if (n > 0) m = nms_core(s, ubox, n, nms_thr, 0, keep_cell + list, ucell, nullptr, (pdl & NMS_BLOCKWISE) != 0, false);
         if (tid == 0) keep_count[item] = m;
         __syncthreads();                                         // the scratch is reused by this CTA's next list
     }
@@ -1642,7 +1837,7 @@ parse_fused_kernel(const HT* __restrict__ head, Geom g, ChainTable ch, float det
     // ---- prologue 3: NMS of the candidates, survivors' cells in visiting order (datatest.py:93-95) ----
     const int n_cand = base_s;
     if (n_cand > 0) {
-        const int m = nms_core(s, ubox, n_cand, nms_thr, 0, s_root, ucell, &g);
+        const int m = nms_core(s, ubox, n_cand, nms_thr, 0, s_root, ucell, &g, (pdl & NMS_BLOCKWISE) != 0);
         if (tid == 0) n_keep_s = m;
     }
     __syncthreads();                                          // NMS scratch is dead from here; n_keep_s, s_root visible
@@ -2491,6 +2686,11 @@ cudaError_t launch_restore_size(const float* w, const float* h, float* rw, float
 
 size_t nms_smem_bytes(int stride) { return nms_bytes_per_list(stride); }
 
+// benchmark knob "nms.blockwise" (ppn_tune): process-wide, read at launch time
+static std::atomic<int> g_nms_blockwise{0};
+void set_nms_blockwise(int on) { g_nms_blockwise.store(on != 0); }
+int get_nms_blockwise() { return g_nms_blockwise.load(); }
+
 cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
                        float thr, int limit, int32_t* keep_idx, int32_t* keep_count, cudaStream_t st) {
     if (n_problems == 0) return cudaSuccess;
@@ -2501,7 +2701,8 @@ cudaError_t launch_nms(const float* box, const float* score, const int32_t* coun
     if (stride <= 1024 && smem <= (size_t)d->smem_optin) {
         if ((e = ensure_smem(nms_smem_kernel, smem, &d->nms)) != cudaSuccess) return e;
         nms_smem_kernel<<<n_problems, stride <= 256 ? 256 : 512, smem, st>>>(reinterpret_cast<const float4*>(box), score, count,
-                                                                             stride, thr, limit, keep_idx, keep_count);
+                                                                             stride, thr, limit, keep_idx, keep_count,
+                                                                             g_nms_blockwise.load());
         return cudaGetLastError();
     }
     nms_global_kernel<<<n_problems, 1024, 0, st>>>(reinterpret_cast<const float4*>(box), score, count, stride, thr,
@@ -2571,7 +2772,8 @@ cudaError_t launch_decode_nms(const void* head, const Geom& g, int n_parts, floa
         if ((e = ensure_smem(decode_nms_kernel<T>, smem, &d->decode_nms[g.dtype])) != cudaSuccess) return e;
         const int threads = threads_pref > 0 ? std::min(512, std::max(64, (threads_pref + 31) & ~31)) : (g.HW <= 256 ? 256 : 512);
         return launch_kernel(decode_nms_kernel<T>, grid, dim3(threads), smem, st, pdl_attr,
-                             static_cast<const T*>(head), g, n_parts, det_thr, nms_thr, keep_cell, keep_count, pdl_bits);
+                             static_cast<const T*>(head), g, n_parts, det_thr, nms_thr, keep_cell, keep_count,
+                             pdl_bits | (g_nms_blockwise.load() ? NMS_BLOCKWISE : 0));
     });
     return cudaErrorInvalidValue;
 }
@@ -2796,6 +2998,7 @@ cudaError_t launch_parse_fused(const void* head, const Geom& g, const ChainTable
     if (slot) { bits |= FUSED_PUBLISH; seq = slot->published; }
     if (pdl_attr && chain_mode == 2 && slot) bits |= FUSED_GUARD | FUSED_TRIGGER_EARLY;
     else if (pdl_attr) bits |= PDL_TRIGGER;
+    if (g_nms_blockwise.load()) bits |= NMS_BLOCKWISE;
     const int threads = g.HW <= 256 ? 256 : 512;
     int* sync = words ? words + 4 : nullptr;
     PPN_DISPATCH_HEAD(g.dtype, {

@@ -75,6 +75,8 @@ cudaError_t launch_limb_argmax(const void* head, uint16_t* amax, const Geom& g, 
 cudaError_t launch_decode_candidates(const void* head, const Geom& g, int n_parts, float thr, int32_t* cand_cell,
                                      float* cand_score, float* cand_box, int32_t* cand_count, cudaStream_t st);
 
+void set_nms_blockwise(int on);     // benchmark knob "nms.blockwise"
+int get_nms_blockwise();
 cudaError_t launch_nms(const float* box, const float* score, const int32_t* count, int n_problems, int stride,
                        float thr, int limit, int32_t* keep_idx, int32_t* keep_count, cudaStream_t st);
 

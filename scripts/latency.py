@@ -106,7 +106,7 @@ for name in args.configs.split(","):
     # where the parse kernel's time goes: one phase boundary per run (tune key timeline.phase), first CTA
     clk.append(sm_mhz())
     phases = {}
-    for ph in list(range(1, 8)) + [11, 12, 13]:
+    for ph in list(range(1, 8)) + list(range(11, 20)):
         _lib.tune(timeline_phase=ph)
         spin_up(100)
         rec.zero_()
@@ -191,7 +191,7 @@ for name in args.configs.split(","):
     print(f"   device span (first start->last end) median {statistics.median(span):6.1f} us   min {min(span):6.1f} us   "
           + "  ".join(f"k{j} {statistics.median(per_k[j]):.1f}" for j in range(n_k)))
     print("   parse kernel, us after its start: " + "  ".join(f"p{k} {v:.1f}" for k, v in phases.items()) + f"  past-wait {waited:.1f}"
-          "   (1 guard, 2 candidates, 3 delta staged, 4 NMS, 5 arg-max map staged, 6 walk, 7 slots assigned; inside the NMS: 11 ranked, 12 sorted, 13 diagonal blocks)")
+          "   (1 guard, 2 candidates, 3 delta staged, 4 NMS, 5 arg-max map staged, 6 walk, 7 slots assigned; inside the NMS: 11 ranked, 12 sorted, 13 diagonal blocks; wavefront: 14 word 0 ready to resolve, 15 published, 16 word 1 ready, 17 published, 18 word 2 published, 19 last word published)")
     if k3:
         print("   arg-max kernel, us after its start (first CTA past each point): " + "  ".join(f"p{k} {v:.1f}" for k, v in k3.items())
               + "   (22 rows streamed, 23 CTA reduced, 24 cluster barrier, 25 rank 0 gathered and stored; 121 / 122: the LAST CTA started / had its rows streamed)")

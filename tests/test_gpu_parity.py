@@ -203,6 +203,33 @@ def test_nms_long_list_uses_global_kernel():
         assert np.array_equal(got, c_oracle.nms(box, 0.3, score=sc, limit=lim))
 
 
+@pytest.mark.parametrize("blockwise", [0, 1], ids=["wavefront", "blockwise"])
+def test_nms_both_phase3_implementations(blockwise):
+    """The warp-wavefront NMS (default) and the block-by-block one (`nms.blockwise`) against the C restatement:
+    list lengths around the 32-box words and the 16-warp wrap, crowded and sparse lists, limits, NaN boxes."""
+    from pytorch_pose_proposal_network_b200 import _lib, datatest as dt
+    rng = np.random.default_rng(77)
+    _lib.tune(nms_blockwise=blockwise)
+    try:
+        for n in (1, 2, 31, 32, 33, 64, 65, 200, 511, 512, 513, 576, 1000, 1024):
+            for spread, size in ((40.0, 30.0), (400.0, 30.0), (4000.0, 20.0)):
+                c = rng.random((n, 2), dtype=np.float32) * np.float32(spread)
+                sz = rng.random((n, 2), dtype=np.float32) * np.float32(size) + 2
+                box = np.concatenate([c - sz / 2, c + sz / 2], axis=1).astype(np.float32)
+                score = rng.permutation(n).astype(np.float32)
+                for lim in (None, 1, 7, 40):
+                    got = dt.non_maximum_suppression(box, 0.3, score=score, limit=lim)
+                    assert np.array_equal(got, c_oracle.nms(box, 0.3, score=score, limit=lim)), (n, spread, lim)
+                nb = box.copy()
+                nb[rng.integers(0, n, max(1, n // 17)), rng.integers(0, 4, max(1, n // 17))] = np.nan
+                got = dt.non_maximum_suppression(nb, 0.3, score=score)
+                assert np.array_equal(got, c_oracle.nms(nb, 0.3, score=score)), (n, spread, "nan")
+                got = dt.non_maximum_suppression(box, 0.0)            # threshold 0: no early-out, everything overlapping goes
+                assert np.array_equal(got, c_oracle.nms(box, 0.0)), (n, spread, "thr0")
+    finally:
+        _lib.tune(nms_blockwise=0)
+
+
 # ------------------------------------------------------------------------------------------
 # batches against the C restatement, every distribution and preset
 # ------------------------------------------------------------------------------------------
