@@ -321,8 +321,48 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
                 // saturated tail, NaN, +-inf — marks itself bad, restores the state the group started from and rescans its
                 // columns with the exact rule.  (The branchy exact rule on every column cost ~120 cycles per column and warp:
                 // each column's branch waits for the predicate chain of the column before it.)
-                auto spec_scan = [&](auto full_tag, int j_lo, int j_hi, int aw0) {
+                auto spec_scan = [&](auto full_tag, const uint32_t* cur, const float* bcur, int j_lo, int j_hi, int aw0) {
                     constexpr bool kFull = decltype(full_tag)::value;
+                    if constexpr (kFull) {
+                        // The hot loop's form, 7 instructions a column instead of 10: per column only the difference, "a sure
+                        // step" (d > kSureStep), "nothing or a sure step" (else the group is rescanned), the LAST stepping
+                        // column and the running maximum.  The range half of the sure-step rule moves to the group: steps
+                        // only go up, so all stepping columns lie within [-kSureRange, kSureRange] iff the last one (= the
+                        // final maximum) is <= kSureRange and the first one is >= -kSureRange, which holds when the maximum
+                        // the group started from is (or, at the start of a piece, m = -inf, when column 0 is: it always
+                        // steps).  A group that started from a finite maximum below -kSureRange and steps is simply rescanned.
+                        // After a clean group with a step, bx = the final maximum (the last stepping column carries it; later
+                        // columns are <= it) and idx = that column; arg-max and bx are not touched inside the loop.
+                        const float m0 = m;
+                        bool good = true;
+                        int js = -1;
+                        float x0 = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float x = __fadd_rn(__uint_as_float(cur[j]), bcur[j]);
+                            if (j == 0) x0 = x;
+                            const float d = __fsub_rn(x, m);
+                            const bool step = d > kSureStep;
+                            good = good && (d <= 0.0f || step);          // NaN differences fail both
+                            js = step ? j : js;
+                            m = fmaxf(m, x);
+                        }
+                        const bool any = js >= 0;
+                        const bool in_range = m <= kSureRange && (m0 >= -kSureRange || (m0 == -INFINITY && x0 >= -kSureRange));
+                        if (good && (!any || in_range)) {
+                            bx = any ? m : bx;
+                            idx = any ? aw0 + js : idx;
+                        } else {
+                            m = m0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                uint32_t v;
+                                asm volatile("mov.b32 %0, %1;" : "=r"(v) : "r"(cur[j]));
+                                limb_column(__fadd_rn(__uint_as_float(v), bcur[j]), aw0 + j);
+                            }
+                        }
+                        return;
+                    }
                     const float m0 = m, bx0 = bx;
                     const int idx0 = idx;
                     bool bad = false;
@@ -357,13 +397,15 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
 #pragma unroll 1
                 while (c0 < r_hi) {
                     if (limb && !emit && c0 + 8 <= seg_end) {
-                        // whole groups inside the current piece: the hot loop.  No register double-buffering: the other
-                        // warps of the scheduler cover the TMEM latency (a second register set cost 16 moves per group)
+                        // whole groups inside the current piece: the hot loop
+                        // (tried: two register sets, ping-pong, the next group's accumulator columns and bias loaded while this
+                        //  group is scanned — 56 bytes of spills at the 96 registers ptxas settles on, cfg2 f16 185 -> 190 us,
+                        //  native 346 -> 356 us; the other warps of the scheduler cover the TMEM latency)
 #pragma unroll 1
                         do {
                             load_group(c0, cur, bcur);
                             tmem_ld8_wait(cur);
-                            spec_scan(std::true_type{}, 0, 8, c0 - wbase);
+                            spec_scan(std::true_type{}, cur, bcur, 0, 8, c0 - wbase);
                             c0 += 8;
                         } while (c0 + 8 <= seg_end);
                         if (c0 == seg_end) {
@@ -382,7 +424,7 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
                         const int j_hi = min(8, seg_end - c0);              // seg_end <= r_hi
                         const int aw0 = c0 - wbase;
                         if (limb && !emit) {
-                            spec_scan(std::false_type{}, j_lo, j_hi, aw0);
+                            spec_scan(std::false_type{}, cur, bcur, j_lo, j_hi, aw0);
                         } else {
                             if (!limb)                                      // decode channels: the logit now, its sigmoid in the finalize pass
                                 decode_group(a.dec, b, c0, cell, a.HW, a.n_dec, cur[0], cur[1], cur[2], cur[3], cur[4], cur[5], cur[6], cur[7],
