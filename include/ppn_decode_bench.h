@@ -43,6 +43,10 @@ int ppn_debug_argmax_items(const PPNShape* shape, int32_t sms, int32_t* info /*[
  * "parse.fused" (-1 auto, 0 three-kernel chain, 1 two-kernel chain whenever supported, cutting large batches),
  * "parse.chain_calls", "parse.persist" (three-kernel chain: decode+NMS CTAs per SM of the persistent grids, 0 = one CTA per image), "parse.k12_threads" (decode+NMS CTA size of the three-kernel chain, 0 = auto), "parse.threads", "parse.stage_all" (-1 auto, 0 nothing staged, >= 1 staged whenever it fits),
  * "parse.overlap" (0 serial, 1 decode+NMS on a side stream, 2 single-stream PDL chain = default), "host.chunk_images",
+ * "nms.blockwise" (1 = the NMS's round-2 block-by-block phase and n x n ranking instead of the warp wavefront and the bucket sort:
+ * a second implementation for A/B timing and for the parity test that compares the two),
+ * "head.subs" (fused head: epilogue warps per TMEM lane quadrant), "head.dry" (fused head probes, results invalid: 1 epilogue
+ * skipped, 2 an eighth of the MMAs), "timeline.phase" (which in-kernel phase mark ppn_timeline records),
  * "encode.sweep" (1 = address-ordered persistent sweep), "encode.ctas_per_sm".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);
 int ppn_tune_get(const char* key, int32_t* value);
