@@ -372,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
         if kind == "nccl":                      # one async all_gather per group of steps; the group sized from the run
             return PoseGatherer(parser, B, cap_entries, group_steps=max(1, min(args.gather_every, (K * steps_per_pass) // 4 or 1)))
         return PeerPoseGatherer(parser, B, cap_entries, slots=args.gather_slots, notify_every=args.notify_every,
-                                mode="store" if kind == "peer_store" else "copy")
+                                mode="store" if kind == "peer_store" else "copy", control=args.gather_control)
     gatherer = make_gatherer(args.gather)
 
     def make_step(g):
@@ -499,8 +499,13 @@ def run_ours(args, rank, world, local_rank):
                                + ("are stored by the parse kernel straight into rank 0's peer-mapped buffer over NVLink (exactly the bytes produced, "
                                   if args.gather == "peer_store" else
                                   f"go to a local slot; one cudaMemcpyAsync (copy engine) per {args.notify_every} steps ships them to rank 0 (slot capacity, ")
-                               + f"{tot / world * 24 / 1e6:.2f} MB per rank and step); NCCL: one 8-byte all_gather of step counters per {args.notify_every} "
-                                 f"steps + one at the end of the timed region ('landed' notification)")
+                               + f"{tot / world * 24 / 1e6:.2f} MB per rank and step); "
+                               + ("'landed' = a 64-bit counter per rank in rank 0's buffer, stored (release.sys) behind every "
+                                  f"{args.notify_every} steps and at the end; rank 0's stream waits for all of them inside the timed region — no collective"
+                                  if args.gather_control == "flags" else
+                                  f"NCCL: one 8-byte all_gather of step counters per {args.notify_every} "
+                                  "steps + one at the end of the timed region ('landed' notification)"))
+                gatherer.check_landed()
         else:
             for r in range(world):
                 rec = gatherer.records_of(r)
@@ -779,6 +784,8 @@ def main():
     ap.add_argument("--max-humans", type=int, default=0, help="slots per image in the packed output (default H*W)")
     ap.add_argument("--gather", default="peer_store", choices=["peer_store", "peer_copy", "nccl", "none"],
                     help="how the poses of N > 1 GPUs reach rank 0 (see sharded.py)")
+    ap.add_argument("--gather-control", default="flags", choices=["flags", "nccl"],
+                    help="peer gather: how rank 0 learns that the records have landed (counters in its buffer, or an 8-byte NCCL all_gather)")
     ap.add_argument("--gather-entries", type=int, default=0,
                     help="average (human, part) entries per image a gather slot holds (default 6*K; overflow is detected)")
     ap.add_argument("--gather-every", type=int, default=32, help="--gather nccl: steps per all_gather (at most a quarter of the run)")

@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PPN_ABI_VERSION 6
+#define PPN_ABI_VERSION 7
 
 /* library error codes (negative); positive return values are cudaError_t */
 #define PPN_OK               0
@@ -258,6 +258,15 @@ int ppn_peer_open(const unsigned char* handle /*[64]*/, void** dev_ptr);
 int ppn_peer_close(void* dev_ptr);
 int ppn_peer_free(void* dev_ptr);
 int ppn_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+/* Landing flags of the gather, without a collective: ppn_peer_post stores `value` (release, system scope) into a
+ * 64-bit counter — this rank's, in the ROOT's buffer — behind everything enqueued on `stream` so far (a one-thread
+ * kernel, launched fully ordered: the parse kernels before it have completed, so their records have landed);
+ * ppn_peer_wait makes `stream` wait until all `n` counters have reached `target` (one polling warp per 32 counters,
+ * acquire loads at system scope; after `timeout_ms` it gives up and sets *timed_out, a device int32, so that a dead
+ * peer cannot hang the stream).  What the reference would do with a blocking gather after its loop
+ * (main.py:240-245 is its only use of the process group) costs one 8-byte store per rank here. */
+int ppn_peer_post(void* counter, long long value, void* stream);
+int ppn_peer_wait(const void* counters, int32_t n, long long target, uint32_t timeout_ms, int32_t* timed_out, void* stream);
 int ppn_parse_dense_remote(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
                            void* local_header, size_t local_header_bytes, void* remote_packed, size_t remote_bytes,
                            int32_t cap_entries, int32_t skip_slots, void* workspace, size_t workspace_bytes, void* stream);

@@ -10,7 +10,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 HEAD_F32, HEAD_F16, HEAD_BF16 = 0, 1, 2
 GEMM_TF32, GEMM_F16, GEMM_BF16 = 0, 1, 2
 FEAT_NCHW_F32, FEAT_NHWC_16 = 0, 1
@@ -95,6 +95,8 @@ EXPORTS = {
     "ppn_peer_close": (C.c_int, [C.c_void_p]),
     "ppn_peer_free": (C.c_int, [C.c_void_p]),
     "ppn_peer_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ppn_peer_post": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p]),
+    "ppn_peer_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_longlong, C.c_uint32, C.c_void_p, C.c_void_p]),
     "ppn_head_workspace_bytes": (C.c_int, [C.POINTER(PPNShape), C.POINTER(C.c_size_t)]),
     "ppn_head_gemm_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PPNShape), C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -413,6 +413,45 @@ int ppn_tree_parse(const void* head, const PPNShape* shape, const PPNParams* par
                                           (cudaStream_t)stream));
 }
 
+// ---- landing flags of the peer gather: a counter per rank in the ROOT's memory -----------------------------
+namespace {
+// One thread; launched WITHOUT the programmatic attribute, so every kernel before it in the stream (the parse
+// kernels whose stores crossed NVLink) has completed and its writes are performed before the flag is released.
+__global__ void peer_post_kernel(long long* counter, long long value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(counter), "l"(value) : "memory");
+}
+// Lane r polls counter r until it has reached `target`; gives up after timeout_ns (a dead peer must not hang the
+// stream) and then raises *timed_out.
+__global__ void peer_wait_kernel(const long long* counters, int n, long long target, unsigned long long timeout_ns, int* timed_out) {
+    const int r = threadIdx.x;
+    if (r >= n) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counters + r) : "memory");
+        if (v >= target) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { if (timed_out) *timed_out = 1; return; }
+        __nanosleep(200);
+    }
+}
+}  // namespace
+
+int ppn_peer_post(void* counter, long long value, void* stream) {
+    if (!counter || (reinterpret_cast<uintptr_t>(counter) & 7)) return PPN_E_BADARG;
+    peer_post_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<long long*>(counter), value);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ppn_peer_wait(const void* counters, int32_t n, long long target, uint32_t timeout_ms, int32_t* timed_out, void* stream) {
+    if (!counters || n < 1 || n > 1024 || (reinterpret_cast<uintptr_t>(counters) & 7)) return PPN_E_BADARG;
+    peer_wait_kernel<<<1, (n + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(static_cast<const long long*>(counters), n, target,
+                                                                      (unsigned long long)timeout_ms * 1000000ull, timed_out);
+    return cuda_rc(cudaGetLastError());
+}
+
 static int parse_impl(const void* head, const PPNShape* shape, const PPNParams* params, const PPNHumans* out,
                       void* workspace, size_t workspace_bytes, void* stream, const ppn::DenseTarget* dense);
 

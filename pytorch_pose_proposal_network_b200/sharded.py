@@ -235,7 +235,18 @@ class PeerPoseGatherer:
     * ``mode="copy"``: the records go to a local slot and every ``notify_every`` steps ONE ``cudaMemcpyAsync``
       (copy engine, no SM) on a side stream ships the group's slots to the root.
 
-    What remains for NCCL is the control plane: every ``notify_every`` steps an 8-byte ``all_gather`` of step
+    The control plane — "have the records landed?" — has two forms (``control``):
+
+    * ``"flags"`` (default without a consumer): no collective at all.  Behind the steps it covers, every rank stores
+      its step counter into ITS 64-bit slot of a counter array at the end of the root's buffer (``ppn_peer_post``: a
+      one-thread kernel on the side stream, fully ordered behind the parse kernels, release at system scope); at
+      ``finish()`` the root's stream waits until all counters have reached the step count (``ppn_peer_wait``: one
+      polling warp, with a timeout).  A rank reuses a slot ``slots`` steps later — long after its own kernel that
+      wrote it has completed (stream order), so nothing else is needed while nobody consumes the records between
+      steps.  At the driver's 20 steps the exposed tail of a run is one store per rank instead of an NCCL collective;
+    * ``"nccl"`` (round 2's first form; required with a ``consumer``, whose progress gates the reuse of slots):
+
+    every ``notify_every`` steps an 8-byte ``all_gather`` of step
     counters on the side stream, ordered after the steps it covers.  When it completes on the root, every rank's
     records of those steps have landed (a kernel's stores are visible when it has completed; the copy is on the
     same stream); a consumer's work enqueued on the root's side stream right after it therefore reads complete
@@ -244,11 +255,18 @@ class PeerPoseGatherer:
     """
 
     def __init__(self, parser, images_per_rank: int, cap_entries: int, group=None, slots: int = 32,
-                 notify_every: int = 8, root: int = 0, mode: str = "store", consumer=None):
+                 notify_every: int = 8, root: int = 0, mode: str = "store", consumer=None, control: str = None,
+                 timeout_ms: int = 5000):
         import ctypes as C
         from . import _lib
         if mode not in ("store", "copy"):
             raise ValueError("mode must be 'store' or 'copy'")
+        control = control or ("nccl" if consumer is not None else "flags")
+        if control not in ("flags", "nccl"):
+            raise ValueError("control must be 'flags' or 'nccl'")
+        if control == "flags" and consumer is not None:
+            raise ValueError("a consumer needs control='nccl': its progress gates the reuse of slots")
+        self.control, self.timeout_ms = control, int(timeout_ms)
         self.parser, self.group, self.mode, self.root = parser, group, mode, int(root)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.B, self.cap = int(images_per_rank), int(cap_entries)
@@ -264,7 +282,7 @@ class PeerPoseGatherer:
         with torch.cuda.device(dev):
             if self.rank == self.root:
                 ptr, buf = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
-                _lib.check(self.lib.ppn_peer_alloc(self.world * region, C.byref(ptr), buf), "ppn_peer_alloc")
+                _lib.check(self.lib.ppn_peer_alloc(self.world * region + 8 * self.world + 256, C.byref(ptr), buf), "ppn_peer_alloc")
                 self._owned, handle = ptr.value, buf.raw
             handles = [None] * self.world
             dist.all_gather_object(handles, handle, group=group)
@@ -276,6 +294,16 @@ class PeerPoseGatherer:
                 self.base = ptr.value
         self.region = region
         self.mine_at = self.base + self.rank * region
+        self.flags_at = self.base + -(-self.world * region // 256) * 256     # int64 [world]: the landing counters (root's memory)
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        if control == "flags":
+            if self.rank == self.root:                                       # cleared before anybody can post
+                zeros = torch.zeros(self.world, dtype=torch.int64, device=dev)
+                with torch.cuda.device(dev):
+                    _lib.check(self.lib.ppn_peer_copy(self.flags_at, zeros.data_ptr(), 8 * self.world,
+                                                      torch.cuda.current_stream(dev).cuda_stream), "ppn_peer_copy")
+                torch.cuda.synchronize(dev)
+            dist.barrier(group=group)
         hdr = -(-4 * (2 + 3 * self.B) // 256) * 256
         self.local_stride = self.nbytes if mode == "copy" else hdr
         self.local = torch.zeros(self.slots * self.local_stride, dtype=torch.uint8, device=dev)
@@ -311,6 +339,14 @@ class PeerPoseGatherer:
                         from . import _lib
                         raise _lib.PPNError(rc, "ppn_peer_copy")
                     s += n
+            if self.control == "flags":
+                with torch.cuda.device(dev):
+                    rc = self.lib.ppn_peer_post(self.flags_at + 8 * self.rank, upto, self.side.cuda_stream)
+                if rc:
+                    from . import _lib
+                    raise _lib.PPNError(rc, "ppn_peer_post")
+                self._covered = upto
+                return
             self.counter.fill_(upto)
             work = dist.all_gather_into_tensor(self.seen, self.counter, group=self.group, async_op=True)
             if self.consumer is not None and self.rank == self.root:
@@ -332,7 +368,7 @@ class PeerPoseGatherer:
     def parse(self, head, out=None, input_complete: bool = False):
         s = self.step
         k = s % self.slots
-        if s >= self.slots:                   # the slot still holds step s - slots: see the class comment
+        if s >= self.slots and self.control == "nccl":      # the slot still holds step s - slots: see the class comment
             self._wait_note((s - self.slots) // self.ne + 1)
         if self.mode == "store":
             res = self.parser.parse(head, out=out, input_complete=input_complete, dense=self._local_slices[k], cap_entries=self.cap,
@@ -349,7 +385,24 @@ class PeerPoseGatherer:
         """Announce the remaining steps and make the current stream wait until every rank's records have landed."""
         if self.step > self._covered:
             self._notify()
+        if self.control == "flags":
+            dev = self.parser.device
+            if self.rank == self.root:
+                with torch.cuda.stream(self.side), torch.cuda.device(dev):
+                    rc = self.lib.ppn_peer_wait(self.flags_at, self.world, self.step, self.timeout_ms,
+                                                self.timed_out.data_ptr(), self.side.cuda_stream)
+                if rc:
+                    from . import _lib
+                    raise _lib.PPNError(rc, "ppn_peer_wait")
+            torch.cuda.current_stream(dev).wait_stream(self.side)
+            self._notes = []
+            return
         self._wait_note(len(self._notes) - 1)
+
+    def check_landed(self):
+        """After finish() and a synchronize: raise if the root gave up waiting for a rank's landing counter."""
+        if int(self.timed_out.item()):
+            raise RuntimeError(f"peer gather: a rank's records had not landed after {self.timeout_ms} ms")
 
     # ---- reading (root) -----------------------------------------------------------------------------
     def records_of(self, rank: int, step_back: int = 0):
@@ -358,7 +411,8 @@ class PeerPoseGatherer:
         if self.rank != self.root:
             raise RuntimeError("the records are gathered at the root rank only")
         s = self.step - 1 - step_back
-        if s < 0 or step_back < 0 or step_back >= self.slots - 2 * self.ne + 1:
+        held = self.slots if self.control == "flags" else self.slots - 2 * self.ne + 1     # flags: a slot is only rewritten `slots` steps later
+        if s < 0 or step_back < 0 or step_back >= held:
             raise ValueError("that step's slot may already have been reused")
         at = rank * self.region + (s % self.slots) * self.nbytes
         from . import _lib

@@ -45,8 +45,9 @@ def _worker(rank, port, mode, result_path):
         cap = CHUNK * 6 * cfg.K
         if mode == "nccl":
             g = PoseGatherer(parser, CHUNK, cap, group_steps=2)            # 5 chunks: two full groups and a flushed one
-        else:
-            g = PeerPoseGatherer(parser, CHUNK, cap, slots=8, notify_every=2, mode=mode)
+        else:                                                              # "store" / "copy" [+ "-nccl": the all_gather notification]
+            g = PeerPoseGatherer(parser, CHUNK, cap, slots=8, notify_every=2, mode=mode.split("-")[0],
+                                 control="nccl" if mode.endswith("-nccl") else "flags")
         outs = [parser.alloc_output(CHUNK) for _ in range(2)]
         heads = [_chunk(cfg, c, dev) for c in mine]
         torch.cuda.synchronize(dev)
@@ -54,6 +55,8 @@ def _worker(rank, port, mode, result_path):
             g.parse(h, out=outs[i % 2], input_complete=True)
         g.finish()
         torch.cuda.synchronize(dev)
+        if hasattr(g, "check_landed"):
+            g.check_landed()
         dist.barrier()
         ok, detail = True, ""
         if rank == 0:
@@ -91,7 +94,7 @@ def _worker(rank, port, mode, result_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["store", "copy", "nccl"])
+@pytest.mark.parametrize("mode", ["store", "copy", "nccl", "store-nccl", "copy-nccl"])
 def test_two_gpus_gathered_equals_single_gpu(mode, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")

@@ -990,6 +990,75 @@ def test_pose_gatherer_single_rank_nccl(tmp_path):
     assert os.listdir(tmp_path) == ["ok"]
 
 
+def _peer_gatherer_worker(rank, port, tmp, control, mode):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1")
+    import torch.distributed as dist
+    from pytorch_pose_proposal_network_b200.config import PPNConfig
+    from pytorch_pose_proposal_network_b200.parser import PoseParser, entries_to_packed
+    from pytorch_pose_proposal_network_b200.sharded import PeerPoseGatherer
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        cfg = PPNConfig.mpii16()
+        g = O.Geometry.of(cfg)
+        B, steps, slots = 48, 21, 8                                # the ring of slots wraps twice
+        heads = [synth.make_head(g, "U", seed=60 + i, B=B) for i in range(3)]
+        refs = [c_oracle.parse_batch(h, g, n_threads=4) for h in heads]
+        devs = [torch.from_numpy(h).cuda() for h in heads]
+        parser = PoseParser(cfg)
+        gat = PeerPoseGatherer(parser, B, B * 120, slots=slots, notify_every=3, mode=mode, control=control)
+        outs = [parser.alloc_output(B) for _ in range(2)]
+        for i in range(steps):
+            gat.parse(devs[i % 3], out=outs[i % 2], input_complete=True)
+        gat.finish()
+        torch.cuda.synchronize()
+        gat.check_landed()
+        ok = True
+        held = slots if control == "flags" else slots - 2 * 3 + 1
+        for i in range(steps - held, steps):                       # the slots still hold the most recent steps
+            rec, ref = gat.records_of(0, step_back=steps - 1 - i), refs[i % 3]
+            ok &= not rec["overflow"] and np.array_equal(rec["count"], ref["counts"][:, 2])
+            for b in range(0, B, 5):
+                n = int(ref["counts"][b, 2])
+                pc, ps, pb = entries_to_packed(rec, b, cfg.K)
+                ok &= np.array_equal(pc, ref["part_cell"][b, :n]) and np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
+        gat.close()
+        open(os.path.join(tmp, "ok" if ok else "bad"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("control,mode", [("flags", "store"), ("flags", "copy"), ("nccl", "store")])
+def test_peer_pose_gatherer_single_rank(tmp_path, control, mode):
+    """sharded.PeerPoseGatherer on one GPU (process group of one, the 'root' buffer is local): records stored by the
+    parse kernel (or copied) into the slot ring, landing announced by counters in the buffer (`flags`) or by NCCL."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + 31
+    mp.spawn(_peer_gatherer_worker, args=(port, str(tmp_path), control, mode), nprocs=1, join=True)
+    assert os.listdir(tmp_path) == ["ok"]
+
+
+def test_peer_wait_times_out_instead_of_hanging():
+    """ppn_peer_wait on a counter nobody posts: gives up after the timeout and raises the flag; after ppn_peer_post
+    the same wait passes."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    lib = _lib.lib()
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.ppn_peer_wait(counters.data_ptr(), 4, 3, 20, flag.data_ptr(), st), "ppn_peer_wait")
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 1
+    flag.zero_()
+    for r in range(4):
+        _lib.check(lib.ppn_peer_post(counters.data_ptr() + 8 * r, 3 + r, st), "ppn_peer_post")
+    _lib.check(lib.ppn_peer_wait(counters.data_ptr(), 4, 3, 2000, flag.data_ptr(), st), "ppn_peer_wait")
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0 and counters.tolist() == [3, 4, 5, 6]
+    assert lib.ppn_peer_post(None, 1, st) != 0 and lib.ppn_peer_wait(None, 4, 0, 1, None, st) != 0       # bad arguments are refused
+
+
 def test_bad_arguments_raise():
     from pytorch_pose_proposal_network_b200 import _lib
     from pytorch_pose_proposal_network_b200.config import PPNConfig

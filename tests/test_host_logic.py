@@ -76,7 +76,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.ppn_abi_version() == _lib.ABI_VERSION == 6
+    assert lib.ppn_abi_version() == _lib.ABI_VERSION == 7
     assert b"workspace" in lib.ppn_strerror(-3)
 
 
