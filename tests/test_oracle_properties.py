@@ -170,3 +170,87 @@ def test_matrix_nms_equals_greedy(bx, thr, seed, limit, poison):
     score = rng.permutation(n).astype(np.float32)
     with np.errstate(all="ignore"):
         assert np.array_equal(matrix_nms_model(b, thr, score, limit), O.nms(b, thr, score=score, limit=limit))
+
+
+def wavefront_nms_model(b, thr, score, limit=None):
+    """Host model of the control flow of nms_core's default path (csrc/ppn_kernels.cu): ranks from a 128-bucket sort on
+    the upper key word (min/max, shift, counts, suffix sums, the n x n count only inside a bucket), the boxes visited a
+    32-box word at a time; a word tests its boxes against the survivor LIST of the earlier words only, then settles
+    its own dependency from the TRANSPOSED diagonal bits (column t = the earlier boxes of the word that would suppress
+    box t) by rounds: a box with a kept suppressor dies, a box none of whose suppressors is still undecided is kept."""
+    n = len(b)
+    if n == 0:
+        return np.zeros(0, np.int32)
+    # keys as the kernels build them: monotone image of the fp32 score in the upper word, the index in the lower
+    u = score.astype(np.float32).view(np.uint32).astype(np.uint64)
+    hi = np.where(u & 0x80000000, ~u & 0xffffffff, u | 0x80000000).astype(np.uint64)
+    key = (hi << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+    lo_, hi_ = int(hi.min()), int(hi.max())
+    rng_ = hi_ - lo_
+    clz = 32 - rng_.bit_length()
+    shift = max(0, 25 - clz)
+    bucket = ((hi.astype(np.int64) - lo_) >> shift).astype(np.int64)
+    assert bucket.max() < 128
+    counts = np.bincount(bucket, minlength=128)
+    above = np.concatenate([np.cumsum(counts[::-1])[::-1][1:], [0]])           # boxes in higher buckets
+    rank = np.empty(n, np.int64)
+    for i in range(n):
+        same = np.nonzero(bucket == bucket[i])[0]
+        rank[i] = above[bucket[i]] + int((key[same] > key[i]).sum())
+    assert sorted(rank.tolist()) == list(range(n))                             # a permutation
+    order = np.empty(n, np.int64)
+    order[rank] = np.arange(n)
+    sb = b[order]
+    area = (sb[:, 2] - sb[:, 0]) * (sb[:, 3] - sb[:, 1])
+    thr = np.float32(thr)
+    survivors = []                                                             # positions in visiting order
+    for i0 in range(0, n, 32):
+        idx = np.arange(i0, min(n, i0 + 32))
+        nb = len(idx)
+        dead = np.zeros(nb, bool)
+        for q in survivors:                                                    # the list published by the earlier words
+            dead |= O.iou_one_to_many(sb[q], area[q], sb[idx], area[idx]) >= thr
+        row = np.zeros((nb, nb), bool)                                         # row[i, t]: box i suppresses the later box t
+        for i in range(nb):
+            if i + 1 < nb:
+                row[i, i + 1:] = O.iou_one_to_many(sb[idx[i]], area[idx[i]], sb[idx[i + 1:]], area[idx[i + 1:]]) >= thr
+        col = row.T                                                            # col[t, i]: the transposed bits a lane holds
+        und, kept = ~dead, np.zeros(nb, bool)
+        rounds = 0
+        while und.any():
+            killed = und & (col & kept[None, :]).any(axis=1)
+            free = und & ~killed & ~(col & und[None, :]).any(axis=1)
+            assert (killed | free).any()                                       # the first undecided box always decides
+            kept |= free
+            und &= ~(killed | free)
+            rounds += 1
+        assert rounds <= 32
+        new = idx[kept].tolist()
+        if limit is not None and len(survivors) + len(new) >= limit:
+            survivors += new[:max(limit - len(survivors), 0)]
+            break
+        survivors += new
+    return order[np.asarray(survivors, np.int64)].astype(np.int32) if survivors else np.zeros(0, np.int32)
+
+
+@settings(max_examples=120, deadline=None)
+@given(wide_boxes, st.sampled_from([0.05, 0.3, 0.5, 0.9]), st.integers(0, 2 ** 31 - 1), st.sampled_from([None, 1, 2, 40]),
+       st.booleans(), st.sampled_from(["perm", "few", "equal", "uniform"]))
+def test_wavefront_nms_equals_greedy(bx, thr, seed, limit, poison, scores):
+    b = np.array([[y, x, y + h, x + w] for y, x, h, w in bx], np.float32).reshape(-1, 4)
+    n = len(b)
+    rng = np.random.default_rng(seed)
+    if poison and n:
+        k = rng.integers(0, n, size=max(1, n // 6))
+        b[k, 2] = b[k, 0]
+        b[k[: len(k) // 2], 3] = np.nan
+    score = {"perm": lambda: rng.permutation(n).astype(np.float32),
+             "few": lambda: rng.integers(0, 3, n).astype(np.float32),            # many ties: long buckets, index order decides
+             "equal": lambda: np.full(n, 0.5, np.float32),                       # one bucket
+             "uniform": lambda: (0.15 + 0.85 * rng.random(n)).astype(np.float32)}[scores]()
+    with np.errstate(all="ignore"):
+        got = wavefront_nms_model(b, thr, score, limit)
+        # the reference's order of exactly equal scores is unspecified (argsort); the rule here is larger index first
+        order = np.lexsort((-np.arange(n), -score.astype(np.float64)))
+        want = order[O.nms(b[order], thr, score=None, limit=limit)] if n else np.zeros(0, np.int32)
+        assert np.array_equal(got, want.astype(np.int32))
