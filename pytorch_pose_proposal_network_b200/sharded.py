@@ -345,6 +345,8 @@ class PeerPoseGatherer:
                 if rc:
                     from . import _lib
                     raise _lib.PPNError(rc, "ppn_peer_post")
+                if self.mode == "copy":        # the local slots of these steps may be rewritten once this copy has run
+                    self._notes.append(_Done(self.side))
                 self._covered = upto
                 return
             self.counter.fill_(upto)
@@ -368,7 +370,9 @@ class PeerPoseGatherer:
     def parse(self, head, out=None, input_complete: bool = False):
         s = self.step
         k = s % self.slots
-        if s >= self.slots and self.control == "nccl":      # the slot still holds step s - slots: see the class comment
+        if s >= self.slots and (self.control == "nccl" or self.mode == "copy"):
+            # the slot still holds step s - slots: see the class comment (flags + store: nothing to wait for — the kernel
+            # that wrote it has long completed; flags + copy: the side-stream copy that shipped it must have run)
             self._wait_note((s - self.slots) // self.ne + 1)
         if self.mode == "store":
             res = self.parser.parse(head, out=out, input_complete=input_complete, dense=self._local_slices[k], cap_entries=self.cap,
@@ -395,7 +399,6 @@ class PeerPoseGatherer:
                     from . import _lib
                     raise _lib.PPNError(rc, "ppn_peer_wait")
             torch.cuda.current_stream(dev).wait_stream(self.side)
-            self._notes = []
             return
         self._wait_note(len(self._notes) - 1)
 
