@@ -644,6 +644,11 @@ def run_ours(args, rank, world, local_rank):
                 "pipeline_gbs": gbs(batch_bytes, step_ms), "pipeline_frac": gbs(batch_bytes, step_ms) / peak,
                 "pipeline_frac_of_read_peak": gbs(batch_bytes, step_ms) / read_peak if read_peak else None}
 
+    # kernels of the library launched in the timed region besides the parse kernels: the peer gather's landing counters
+    # (one one-thread store kernel per `notify_every` steps and at the end; on rank 0 one polling warp at the end)
+    gather_launches = 0
+    if isinstance(gatherer, PeerPoseGatherer) and gatherer.control == "flags":
+        gather_launches = -(-n_steps // gatherer.ne) + (1 if rank == gatherer.root else 0)
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "strong" if job else "weak", "vs_baseline": None,
@@ -663,7 +668,7 @@ def run_ours(args, rank, world, local_rank):
                    "step i's tree parse finishes; steps complete in order",
                    "pose_gather": gather_note},
         "roofline": roofline, "e2e": e2e, "clocks": clocks,
-        "gpu_launches": plan["launches"] * n_steps,
+        "gpu_launches": plan["launches"] * n_steps + gather_launches,
         "repeats": {"ms_per_step": repeat_ms, "median_ms_per_step": sorted(repeat_ms)[len(repeat_ms) // 2],
                     "min_ms_per_step": min(repeat_ms), "note": "the timed region run five times; `value` is the first"},
     }
