@@ -46,7 +46,7 @@ int ppn_debug_argmax_items(const PPNShape* shape, int32_t sms, int32_t* info /*[
  * "nms.blockwise" (1 = the NMS's round-2 block-by-block phase and n x n ranking instead of the warp wavefront and the bucket sort:
  * a second implementation for A/B timing and for the parity test that compares the two),
  * "head.subs" (fused head: epilogue warps per TMEM lane quadrant), "head.dry" (fused head probes, results invalid: 1 epilogue
- * skipped, 2 an eighth of the MMAs), "timeline.phase" (which in-kernel phase mark ppn_timeline records),
+ * skipped, 2 an eighth of the MMAs), "head.acc" (16-bit path: 128 = four TMEM accumulators of 128 channels, default two of 256), "timeline.phase" (which in-kernel phase mark ppn_timeline records),
  * "encode.sweep" (1 = address-ordered persistent sweep), "encode.ctas_per_sm".  Returns PPN_E_BADARG for an unknown key. */
 int ppn_tune(const char* key, int32_t value);
 int ppn_tune_get(const char* key, int32_t* value);

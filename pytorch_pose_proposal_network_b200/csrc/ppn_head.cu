@@ -166,6 +166,7 @@ struct HeadArgs {
     int32_t groups_per_img, n_groups, n_tiles, n_ntiles, n_kblocks;
     int32_t n_chunks, chunk_tiles, n_items;   // a work item = (cell tile, chunk of chunk_tiles consecutive channel tiles): small batches
                                               // spread one cell tile's channels over several CTAs (the key maxima merge them)
+    int32_t acc_n, acc_stages;  // channels per accumulator tile and how many accumulators TMEM holds: 256 x 2 (TF32 path) or 128 x 4
     int32_t n_last;             // channels of the LAST channel tile, rounded up to 16: its MMAs and its weight box are that narrow
     int32_t n_rows;             // 16-bit path: B * HW rows of the packed activation matrix
     int32_t n_bstages;          // 16-bit path: stages of the weight ring
@@ -261,8 +262,8 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
         }
         unsigned long long* const key0 = a.keys + (size_t)b * a.E * a.HW + cell;      // + ei * HW
         for (int nt = nt0; nt < nt1; ++nt) {
-            const int c_tile = nt * kBlockN;
-            const int n_cols = min(kBlockN, a.C - c_tile);            // > 0
+            const int c_tile = nt * a.acc_n;
+            const int n_cols = min(a.acc_n, a.C - c_tile);            // > 0
             // this sub-warp's run of the tile: whole 8-column groups
             const int n8 = (n_cols + 7) >> 3, per = (n8 + kSubs - 1) / kSubs;
             const int r_lo = c_tile + min(sub * per, n8) * 8;
@@ -270,7 +271,7 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
             mbar_wait_sleep(&tfull[acc], acc_phase, 40);
             tc_fence_after();
             if (r_lo < r_hi && !(a.dry & 1)) {
-                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN) - (uint32_t)c_tile;
+                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * a.acc_n) - (uint32_t)c_tile;
                 // state of the piece being scanned: m = largest logit so far (+inf once a NaN has been taken: nothing may
                 // follow the first NaN), idx = the arg-max so far (window position) and bx = the logit it stands on
                 // (bx <= m: a larger logit whose sigmoid TIES with the standing one does not move the arg-max).  A piece
@@ -451,8 +452,7 @@ __device__ __forceinline__ void head_epilogue(const HeadArgs& a, uint32_t tmem_b
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            if (++acc == a.acc_stages) { acc = 0; acc_phase ^= 1u; }
         }
     }
 }
@@ -569,8 +569,7 @@ head_gemm_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit(&tfull[acc]);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
+                    if (++acc == a.acc_stages) { acc = 0; acc_phase ^= 1u; }
                 }
             }
         }
@@ -597,9 +596,9 @@ constexpr int kBlockK16 = 64;                // 16-bit elements per 128-byte swi
 constexpr int kUmmaK16 = 16;
 constexpr int kMaxKBlocks16 = 8;             // Cin <= 512
 constexpr int kA16Bytes = kBlockM * 128;     // one k-block of the A tile: 16 KB
-constexpr int kB16Bytes = kBlockN * 128;     // one stage of the weight ring: 32 KB
-constexpr int kMaxBStages = 6;
-constexpr int kBar16Bytes = 384;
+constexpr int kMaxBStages = 12;              // stages of the weight ring: acc_n rows of 128 bytes each (16 KB at 128 channels)
+constexpr int kMaxAcc16 = 4;                 // accumulators: 4 x 128 columns (or 2 x 256)
+constexpr int kBar16Bytes = 512;
 
 template <int kSubs>
 __global__ void __launch_bounds__(64 + 128 * kSubs, 1)
@@ -608,13 +607,14 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
     extern __shared__ __align__(1024) unsigned char smem16[];
     unsigned char* sA = smem16;                                               // [n_kblocks][16 KB]
     unsigned char* sB = smem16 + (size_t)a.n_kblocks * kA16Bytes;             // [n_bstages][32 KB]
-    uint64_t* afull = reinterpret_cast<uint64_t*>(sB + (size_t)a.n_bstages * kB16Bytes);
+    const uint32_t b_stage_bytes = (uint32_t)a.acc_n * 128u;                   // one stage of the weight ring: acc_n rows of one k-block
+    uint64_t* afull = reinterpret_cast<uint64_t*>(sB + (size_t)a.n_bstages * b_stage_bytes);
     uint64_t* aempty = afull + kMaxKBlocks16;
     uint64_t* bfull = aempty + kMaxKBlocks16;
     uint64_t* bempty = bfull + kMaxBStages;
     uint64_t* tfull = bempty + kMaxBStages;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + kMaxAcc16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kMaxAcc16);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -625,7 +625,7 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         prefetch_tensormap(&tm_wt);
         for (int s = 0; s < kMaxKBlocks16; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-        for (int q = 0; q < 2; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4 * kSubs); }
+        for (int q = 0; q < kMaxAcc16; ++q) { mbar_init(&tfull[q], 1); mbar_init(&tempty[q], 4 * kSubs); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -650,7 +650,7 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                 head_item(a, item, tile, nt0, nt1);
                 for (int nt = nt0; nt < nt1; ++nt) {
                     const bool last = nt == a.n_ntiles - 1;
-                    const uint32_t b_bytes = (uint32_t)(last ? a.n_last : kBlockN) * 128u;
+                    const uint32_t b_bytes = (uint32_t)(last ? a.n_last : a.acc_n) * 128u;
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
                         if (nt == nt0) {                                 // this item's activations, k-block by k-block
                             mbar_wait_sleep(&aempty[kb], a_phase ^ 1u, 100);
@@ -659,7 +659,7 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                         }
                         mbar_wait_sleep(&bempty[stage], phase ^ 1u, 100);
                         mbar_arrive_expect_tx(&bfull[stage], b_bytes);
-                        tma_load_2d(sB + (size_t)stage * kB16Bytes, last ? &tm_wt : &tm_w, kb * kBlockK16, nt * kBlockN, &bfull[stage]);
+                        tma_load_2d(sB + (size_t)stage * b_stage_bytes, last ? &tm_wt : &tm_w, kb * kBlockK16, nt * a.acc_n, &bfull[stage]);
                         if (++stage == a.n_bstages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -670,7 +670,7 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
             const uint32_t fmt = a.bf16 ? 1u : 0u;
-            const uint32_t idesc_full = mma_idesc(fmt, 0u, kBlockN), idesc_last = mma_idesc(fmt, 0u, a.n_last);
+            const uint32_t idesc_full = mma_idesc(fmt, 0u, a.acc_n), idesc_last = mma_idesc(fmt, 0u, a.n_last);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, a_phase = 0;
             for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -681,12 +681,12 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                     const uint32_t idesc = last ? idesc_last : idesc_full;
                     mbar_wait_sleep(&tempty[acc], acc_phase ^ 1u, 40);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)acc * kBlockN;
+                    const uint32_t d = tmem_base + (uint32_t)(acc * a.acc_n);
                     for (int kb = 0; kb < a.n_kblocks; ++kb) {
                         if (nt == nt0) mbar_wait_sleep(&afull[kb], a_phase, 20);
                         mbar_wait_sleep(&bfull[stage], phase, 20);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(sA + (size_t)kb * kA16Bytes), sb = smem_u32(sB + (size_t)stage * kB16Bytes);
+                        const uint32_t sa = smem_u32(sA + (size_t)kb * kA16Bytes), sb = smem_u32(sB + (size_t)stage * b_stage_bytes);
 #pragma unroll
                         for (int kk = 0; kk < kBlockK16 / kUmmaK16; ++kk) {
                             // both K-major: 8 rows of 128 B per swizzle atom (1024 B), K advanced by 32 B inside the row
@@ -699,8 +699,7 @@ head_gemm16_argmax_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
                         if (++stage == a.n_bstages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit(&tfull[acc]);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
+                    if (++acc == a.acc_stages) { acc = 0; acc_phase ^= 1u; }
                 }
                 a_phase ^= 1u;
             }
@@ -797,14 +796,16 @@ bool map_2d(EncodeTiledFn enc, CUtensorMap* m, CUtensorMapDataType dt, int elem_
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-size_t head16_smem_bytes(int n_kblocks, int n_bstages) {
-    return (size_t)n_kblocks * kA16Bytes + (size_t)n_bstages * kB16Bytes + kBar16Bytes;
+size_t head16_smem_bytes(int n_kblocks, int n_bstages, int acc_n) {
+    return (size_t)n_kblocks * kA16Bytes + (size_t)n_bstages * acc_n * 128 + kBar16Bytes;
 }
 
-void fill_common(HeadArgs& a, const Geom& g, int Cin, const float* bias, float* dec, unsigned long long* keys, float* emit_logits, float* emit_head) {
+void fill_common(HeadArgs& a, const Geom& g, int Cin, const float* bias, float* dec, unsigned long long* keys, float* emit_logits, float* emit_head,
+                 int acc_n = kBlockN) {
     a.B = g.B; a.HW = g.HW; a.Cin = Cin; a.C = g.C; a.n_dec = 6 * g.K; a.S = g.S; a.E = g.E;
-    a.n_ntiles = (g.C + kBlockN - 1) / kBlockN;
-    a.n_last = ((g.C - (a.n_ntiles - 1) * kBlockN) + 15) & ~15;            // 16 .. 256
+    a.acc_n = acc_n; a.acc_stages = kTmemCols / acc_n;
+    a.n_ntiles = (g.C + acc_n - 1) / acc_n;
+    a.n_last = ((g.C - (a.n_ntiles - 1) * acc_n) + 15) & ~15;              // 16 .. acc_n
     a.magic_S = g.S <= 1 ? 0u : (uint32_t)(((1ull << 32) + g.S - 1) / g.S);
     a.bias = bias; a.dec = dec; a.keys = keys; a.emit_logits = emit_logits; a.emit_head = emit_head;
     a.n_rows = g.B * g.HW; a.n_bstages = 0; a.bf16 = 0; a.dry = 0;
@@ -940,7 +941,12 @@ cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, cons
     if ((e = encoder(&enc)) != cudaSuccess) return e;
 
     HeadArgs a;
-    fill_common(a, g, Cin, bias, dec, keys, emit_logits, emit_head);
+    // accumulators: two of 256 channels.  (tune key head.acc = 128: four of 128 channels, the weight ring in 16 KB stages —
+    // meant to give the MMA side and the epilogue more slack around each other; measured, it halves the work per barrier
+    // round trip of the one MMA-issuing thread instead: operand stream + MMAs alone 212 -> 375 us at the native shape, the
+    // whole kernel 299 -> 438 us.  Parity-green, kept as a knob.)
+    const int acc_n = ((subs >> 12) & 1) ? 128 : 256;
+    fill_common(a, g, Cin, bias, dec, keys, emit_logits, emit_head, acc_n);
     a.dry = (subs >> 8) & 3;
     subs &= 255;
     a.n_tiles = (a.n_rows + kBlockM - 1) / kBlockM;
@@ -950,8 +956,8 @@ cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, cons
     int max_smem = 0;
     if ((e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
     a.n_bstages = kMaxBStages;
-    while (a.n_bstages > 2 && head16_smem_bytes(a.n_kblocks, a.n_bstages) > (size_t)max_smem) --a.n_bstages;
-    const size_t smem = head16_smem_bytes(a.n_kblocks, a.n_bstages);
+    while (a.n_bstages > 2 && head16_smem_bytes(a.n_kblocks, a.n_bstages, acc_n) > (size_t)max_smem) --a.n_bstages;
+    const size_t smem = head16_smem_bytes(a.n_kblocks, a.n_bstages, acc_n);
     if (smem > (size_t)max_smem) return cudaErrorInvalidValue;
 
     if ((e = cudaMemsetAsync(keys, 0, head_keys_bytes(g), st)) != cudaSuccess) return e;
@@ -975,7 +981,7 @@ cudaError_t launch_head_gemm16_argmax(const void* feat, bool feat_nchw_f32, cons
     const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUtensorMap tm_x, tm_w, tm_wt;
     if (!map_2d(enc, &tm_x, dt, 2, x16, Cin, (uint64_t)a.n_rows, kBlockK16, kBlockM) ||
-        !map_2d(enc, &tm_w, dt, 2, wt, Cin, g.C, kBlockK16, kBlockN) ||
+        !map_2d(enc, &tm_w, dt, 2, wt, Cin, g.C, kBlockK16, acc_n) ||
         !map_2d(enc, &tm_wt, dt, 2, wt, Cin, g.C, kBlockK16, a.n_last))
         return cudaErrorInvalidValue;
     {

@@ -20,7 +20,9 @@ ap.add_argument("--configs", default="cfg2,native")
 ap.add_argument("--subs", default="3,4")
 ap.add_argument("--operands", default="f16,tf32")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--acc", type=int, default=256, help="16-bit path: channels per accumulator (128 x 4 or 256 x 2)")
 args = ap.parse_args()
+_lib.tune(head_acc=args.acc)
 
 
 def timed(fn, iters):

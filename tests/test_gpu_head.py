@@ -270,6 +270,31 @@ def test_head_every_epilogue_width_gives_the_same_answer(operand):
         _lib.tune(head_subs=4)
 
 
+@pytest.mark.parametrize("operand", ["f16", "bf16"])
+@pytest.mark.parametrize("name,B,Cin", [("cfg2", 40, 128), ("native", 2, 512)])
+def test_head16_four_narrow_accumulators_give_the_same_answer(name, B, Cin, operand):
+    """head.acc = 128: four TMEM accumulators of 128 channels (16 KB weight stages) instead of two of 256 — another tiling
+    of the same GEMM and another cut of the windows into pieces; decode planes and arg-max map must not change."""
+    from pytorch_pose_proposal_network_b200 import _lib
+    g = geometry(name)
+    parser = parser_for(g)
+    feat, weight, bias = make_layer(g, B, Cin, seed=29)
+    try:
+        dec, amax, _, _ = parser.head_gemm_argmax(feat, weight, bias, operand=operand)
+        torch.cuda.synchronize()
+        want = (dec.clone(), amax.clone())
+        _lib.tune(head_acc=128)
+        dec, amax, logits, head = parser.head_gemm_argmax(feat, weight, bias, emit=True, operand=operand)
+        torch.cuda.synchronize()
+        check_against_emitted(g, parser, dec, amax, logits, head)
+        dec, amax, _, _ = parser.head_gemm_argmax(feat, weight, bias, operand=operand)
+        torch.cuda.synchronize()
+        assert torch.equal(amax.view(torch.int16), want[1].view(torch.int16))
+        assert torch.equal(dec, want[0])
+    finally:
+        _lib.tune(head_acc=256)
+
+
 @pytest.mark.parametrize("operand", ["tf32", "f16"])
 def test_head_small_batch_items_and_graph_replay(operand):
     """One image of the reference's shape: 5 cell tiles, so every tile's channel tiles are spread over the SMs as work
