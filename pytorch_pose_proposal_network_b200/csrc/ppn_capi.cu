@@ -246,7 +246,7 @@ int ppn_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "parse.k12_threads")) t.parse_k12_threads = value < 0 ? 0 : value;
     else if (!std::strcmp(key, "parse.fused")) t.parse_fused = value < 0 ? -1 : (value != 0);
     else if (!std::strcmp(key, "parse.threads")) t.parse_threads = value;
-    else if (!std::strcmp(key, "head.subs")) t.head_subs = (t.head_subs & 0x1300) | (value < 1 ? 1 : (value > 7 ? 7 : value));
+    else if (!std::strcmp(key, "head.subs")) t.head_subs = (t.head_subs & 0x1300) | (value < 1 ? 0 : (value > 7 ? 7 : value));   // 0 = auto
     else if (!std::strcmp(key, "head.dry")) t.head_subs = (t.head_subs & 0x10ff) | ((value & 3) << 8);   // benchmarks: epilogue skipped, results invalid
     else if (!std::strcmp(key, "head.acc")) t.head_subs = (t.head_subs & 0x3ff) | (value == 128 ? 0x1000 : 0);   // 16-bit path: 128 = four accumulators of 128 channels (default two of 256)
     else if (!std::strcmp(key, "host.chunk_images")) t.host_chunk_images = value < 1 ? 1 : value;

@@ -39,7 +39,9 @@ struct Tuning {
     int encode_sweep = 1;              // target encoder: limb tensors by the address-ordered persistent sweep (0: one CTA per image part)
     int encode_ctas_per_sm = 6;
     int argmax_dry = 0;                // ring kernels only move the bytes (no compares, no stores): the read ceiling of this ring
-    int head_subs = 4;                 // fused head: epilogue warps per TMEM lane quadrant (1, 2, 4 or 6; bits 8-9: the head.dry probes)
+    int head_subs = 0;                 // fused head: epilogue warps per TMEM lane quadrant (1, 2, 4 or 6; 0 = auto: 4 for TF32 operands, 6 for
+                                       // 16-bit ones, where the faster MMAs leave the latency-bound epilogue warps more to hide; bits 8-9:
+                                       // the head.dry probes, bit 12: head.acc = 128)
     int parse_overlap = 2;             // 0 serial; 1 decode+NMS on a side stream beside the arg-max;
                                        // 2 one stream, programmatic dependent launches (PDL chain)
 };

@@ -267,7 +267,7 @@ def test_head_every_epilogue_width_gives_the_same_answer(operand):
             else:
                 assert torch.equal(dec, want[0]) and torch.equal(amax.view(torch.int16), want[1].view(torch.int16)), f"subs={subs}"
     finally:
-        _lib.tune(head_subs=4)
+        _lib.tune(head_subs=0)
 
 
 @pytest.mark.parametrize("operand", ["f16", "bf16"])
