@@ -240,8 +240,9 @@ class PeerPoseGatherer:
     * ``"flags"`` (default without a consumer): no collective at all.  Behind the steps it covers, every rank stores
       its step counter into ITS 64-bit slot of a counter array at the end of the root's buffer (``ppn_peer_post``: a
       one-thread kernel on the side stream, fully ordered behind the parse kernels, release at system scope); at
-      ``finish()`` the root's stream waits until all counters have reached the step count (``ppn_peer_wait``: one
-      polling warp, with a timeout).  A rank reuses a slot ``slots`` steps later — long after its own kernel that
+      ``finish()`` every rank posts once more with the run number in the counter's upper half, and the root's stream
+      waits until all counters carry it (``ppn_peer_wait``: one polling warp, with a timeout) — however many steps each
+      rank parsed.  A rank reuses a slot ``slots`` steps later — long after its own kernel that
       wrote it has completed (stream order), so nothing else is needed while nobody consumes the records between
       steps.  At the driver's 20 steps the exposed tail of a run is one store per rank instead of an NCCL collective;
     * ``"nccl"`` (round 2's first form; required with a ``consumer``, whose progress gates the reuse of slots):
@@ -315,6 +316,7 @@ class PeerPoseGatherer:
         self._notes = []                      # notification n -> work handle (None once waited for)
         self.step = 0
         self._covered = 0                     # steps [0, _covered) are covered by an issued notification
+        self._epoch = 0                       # finish() calls so far (flags control: upper half of the landing counters)
 
     # ---- control plane ------------------------------------------------------------------------------
     def _notify(self):
@@ -341,7 +343,7 @@ class PeerPoseGatherer:
                     s += n
             if self.control == "flags":
                 with torch.cuda.device(dev):
-                    rc = self.lib.ppn_peer_post(self.flags_at + 8 * self.rank, upto, self.side.cuda_stream)
+                    rc = self.lib.ppn_peer_post(self.flags_at + 8 * self.rank, (self._epoch << 32) | upto, self.side.cuda_stream)
                 if rc:
                     from . import _lib
                     raise _lib.PPNError(rc, "ppn_peer_post")
@@ -387,19 +389,23 @@ class PeerPoseGatherer:
 
     def finish(self):
         """Announce the remaining steps and make the current stream wait until every rank's records have landed."""
-        if self.step > self._covered:
-            self._notify()
         if self.control == "flags":
+            # the counters carry (number of finish() calls << 32 | steps): the root waits for every rank to have finished
+            # THIS run, however many steps each of them parsed (uneven shards)
+            self._epoch += 1
+            self._notify()
             dev = self.parser.device
             if self.rank == self.root:
                 with torch.cuda.stream(self.side), torch.cuda.device(dev):
-                    rc = self.lib.ppn_peer_wait(self.flags_at, self.world, self.step, self.timeout_ms,
+                    rc = self.lib.ppn_peer_wait(self.flags_at, self.world, self._epoch << 32, self.timeout_ms,
                                                 self.timed_out.data_ptr(), self.side.cuda_stream)
                 if rc:
                     from . import _lib
                     raise _lib.PPNError(rc, "ppn_peer_wait")
             torch.cuda.current_stream(dev).wait_stream(self.side)
             return
+        if self.step > self._covered:
+            self._notify()
         self._wait_note(len(self._notes) - 1)
 
     def check_landed(self):

@@ -1023,6 +1023,13 @@ def _peer_gatherer_worker(rank, port, tmp, control, mode):
                 n = int(ref["counts"][b, 2])
                 pc, ps, pb = entries_to_packed(rec, b, cfg.K)
                 ok &= np.array_equal(pc, ref["part_cell"][b, :n]) and np.array_equal(bits(pb), bits(ref["part_box"][b, :n]))
+        for i in range(steps, steps + 4):                         # a second run on the same gatherer: the counters carry the run number
+            gat.parse(devs[i % 3], out=outs[i % 2], input_complete=True)
+        gat.finish()
+        torch.cuda.synchronize()
+        gat.check_landed()
+        rec, ref = gat.records_of(0), refs[(steps + 3) % 3]
+        ok &= not rec["overflow"] and np.array_equal(rec["count"], ref["counts"][:, 2])
         gat.close()
         open(os.path.join(tmp, "ok" if ok else "bad"), "w").close()
     finally:
